@@ -1,0 +1,52 @@
+"""Shared helpers for the parity tests (rebuild golden-case inputs without the reference)."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from pnpvcve_b200 import synthetic, weights
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_cases():
+    with open(os.path.join(GOLDEN, "cases.json")) as f:
+        return json.load(f)
+
+
+def build_case(name):
+    """(state_dict, clip dict, golden npz) for a committed golden case."""
+    case = golden_cases()[name]
+    clips = [synthetic.make_clip(**kw) for kw in case["clips"]]
+    clip = synthetic.cat_clips(clips)
+    if case.get("mirror"):
+        t = clip["lq"].shape[1]
+        half = clip["lq"][:, : t // 2]
+        clip["lq"] = torch.cat([half, half.flip(1)], dim=1).contiguous()
+    sd = weights.random_state_dict(case["weight_seed"], num_blocks=case["num_blocks"])
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return sd, clip, gold
+
+
+def check_against_golden(out, gold, tol):
+    """max-abs error on the stored lattice + relative error of the float64 frame sums."""
+    out = out.detach().float().cpu()
+    assert tuple(out.shape) == tuple(int(v) for v in gold["shape"])
+    lat = torch.from_numpy(gold["lattice"])
+    err = (out[..., ::2, ::2] - lat).abs().max().item()
+    assert err <= tol, f"lattice max-abs {err:.3e} > {tol:.1e}"
+    fs = out.double().sum(dim=(2, 3, 4)).numpy()
+    npix = out.shape[2] * out.shape[3] * out.shape[4]
+    sum_err = np.abs(fs - gold["frame_sum"]).max() / npix
+    assert sum_err <= tol, f"frame mean error {sum_err:.3e} > {tol:.1e}"
+    return err
+
+
+def warp_case():
+    g = torch.Generator().manual_seed(4242)
+    x = torch.randn((1, 2, 720, 1280), generator=g)
+    flow_b = torch.randint(-64, 65, (1, 2, 90, 160), generator=g).float() / 4.0
+    flow = flow_b.repeat_interleave(8, 2).repeat_interleave(8, 3)
+    gold = np.load(os.path.join(GOLDEN, "warp_720p.npz"))
+    return x, flow, gold
