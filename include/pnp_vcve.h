@@ -1,0 +1,140 @@
+/*
+ * pnp_vcve.h -- C ABI of libpnpvcve.so, the sm_100a kernels behind the BAE+CAA generator.
+ *
+ * The reference (ZeldaM1/PnP-VCVE) is pure Python/PyTorch and has no FFI of its own; every entry
+ * point below replaces a group of library calls the reference makes on its hot path, cited as
+ * reference file:line.  The Python class that mirrors the reference's registry interface
+ * (pnpvcve_b200/backbone.py, same name / kwargs / state_dict as
+ * mmedit/models/backbones/sr_backbones/iconvsr_ipb_par.py:16-44) binds these with ctypes; see
+ * INTEGRATION.md for the stub a maintainer adds on the reference side.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); all pointers are DEVICE pointers
+ * unless stated; `stream` is a cudaStream_t passed as void*; nothing is allocated or retained by
+ * the library (buffers, workspaces and packed weights are owned by the caller); every function
+ * returns 0 on success or a negative pnp_status and never throws.  Kernels launch asynchronously
+ * on `stream`.  sm_100a only: on any other device the calls return PNP_ERR_ARCH.
+ */
+#ifndef PNP_VCVE_H_
+#define PNP_VCVE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pnp_status {
+  PNP_OK = 0,
+  PNP_ERR_ARG = -1,     /* null pointer / bad shape / misaligned pointer */
+  PNP_ERR_ARCH = -2,    /* current device is not compute capability 10.x */
+  PNP_ERR_CUDA = -3,    /* a CUDA runtime/driver call failed (see pnp_last_error) */
+  PNP_ERR_RESOURCE = -4 /* shared-memory budget cannot be met */
+} pnp_status;
+
+/* Library / device info. */
+int pnp_abi_version(void);
+const char* pnp_last_error(void);          /* message of the last failing call in this thread */
+int pnp_device_check(void);                /* PNP_OK iff the current device is sm_100 */
+/* 0 (default): UMMA descriptor base_offset = (addr >> 7) & 7 as the PTX ISA prescribes for
+ * starts that are not 1024-byte aligned; 1: always 0.  Diagnostic knob. */
+int pnp_set_base_offset_mode(int mode);
+
+/*
+ * K1 -- MV-guided bilinear warp of a 64-channel feature map.
+ * Replaces flow_warp (mmedit/models/common/flow_warp.py:6-50) as called by VOSAlignment.forward
+ * (mmedit/models/backbones/sr_backbones/iconvsr_mv.py:17-18): grid_sample(bilinear, zeros,
+ * align_corners=True) of x + mv, including the reference's fp32 normalise/un-normalise sequence.
+ *   src, dst : bf16 NHWC (H, W, 64), 16-byte aligned, distinct buffers
+ *   flow_x/y : fp32 planes, element (y,x) at [y*flow_row_stride + x]   (a (2,H,W) slice of `mvs`)
+ *   dbg_x0/y0: optional int32 (H*W) outputs of the integer north-west tap (floor), may be NULL
+ */
+int pnp_mv_warp(const void* src, const float* flow_x, const float* flow_y, int64_t flow_row_stride,
+                void* dst, int H, int W, int32_t* dbg_x0, int32_t* dbg_y0, void* stream);
+
+/*
+ * LR frames -> im2col'd bf16 operand (N, H, W, 64), channel k = tap*3 + c for k < 27, zero for
+ * 27..31; channels 32..63 are not written (allocate the buffer zeroed once).  Carries the
+ * 3-channel slice of the reference's input conv (basicvsr_net.py:484 on the cat at
+ * iconvsr_ipb_par.py:90,125).  lr is an fp32 (N,3,H,W) view with element strides sn, sc, sy (x: 1).
+ */
+int pnp_lr_im2col(const float* lr, int64_t sn, int64_t sc, int64_t sy, void* dst, int N, int H, int W,
+                  void* stream);
+
+/*
+ * K4 -- weight packing (run once per checkpoint / once per distinct CRF, results stay resident).
+ * A packed conv is a sequence of 8192-byte blocks, [64 out][64 in] bf16, rows pre-swizzled for the
+ * tensor-core shared-memory layout, centre tap first (center_chunks blocks), then taps
+ * 0,1,2,3,5,6,7,8.
+ *   pnp_pack_conv3x3: w is fp32 (E, out_ch, in_total, 3, 3); block = sum_e coef[e]*w[e] restricted to
+ *     input channels [in_begin, in_begin+in_count) (+ the slice at in_begin2 if >= 0).  coef is a
+ *     DEVICE pointer to E floats or NULL (E must then be 1).  Replaces the per-block, per-frame
+ *     torch.mm expert mixing of Dynamic_conv2d_se.forward (sr_backbone_utils.py:198-199).
+ *   pnp_pack_rows: fp32 matrix (rows<=64, cols<=64; element strides) into packed rows
+ *     row_offset.. of dst (used for the three 1x1 partition convs, sr_backbone_utils.py:285-287,
+ *     stacked under the centre tap: rows 64.., 128.., 192..).
+ *   pnp_pack_aux: first 3 input channels of w (out_ch, in_total, 3, 3) as one [64][tap*3+c] block.
+ */
+int pnp_pack_conv3x3(const float* w, int n_experts, const float* coef, int out_ch, int in_total,
+                     int in_begin, int in_begin2, int in_count, void* dst, int center_chunks,
+                     void* stream);
+int pnp_pack_rows(const float* w, int rows, int cols, int64_t row_stride, int64_t col_stride, void* dst,
+                  int row_offset, void* stream);
+int pnp_pack_aux(const float* w, int out_ch, int in_total, void* dst, void* stream);
+
+/*
+ * CAA heads for `frames` frames: experts (frames, n_experts) = Base_Predictor(base_qp)
+ * (domain_aware.py:172-183), gamma (frames, 64) = SEModule(qp) (domain_aware.py:201-222).
+ * Weights are the reference's parameters, fp32, contiguous.
+ */
+int pnp_caa_heads(const float* base_qp, const float* qp, int frames, const float* base0_w,
+                  const float* base0_b, const float* base2_w, const float* base2_b, const float* se0_w,
+                  const float* se2_w, int n_experts, int se_hidden, float* experts, float* gamma,
+                  void* stream);
+/* out[f][blk][c] = gamma[f][c] * sum_e experts[f][e] * conv2_bias[blk][e][c]
+ * (sr_backbone_utils.py:200-208); conv2_bias is (n_blocks, n_experts, 64) contiguous. */
+int pnp_mix_bias(const float* conv2_bias, int n_blocks, int n_experts, const float* experts,
+                 const float* gamma, int frames, float* out, void* stream);
+
+/*
+ * K2/K3/K5 -- fused 3x3 convolution on tcgen05 tensor cores (implicit GEMM, TMA fed, TMEM
+ * accumulators).  One call replaces one F.conv2d of the reference plus the elementwise work
+ * around it:
+ *   acc  = conv3x3(src, W) [+ conv1x1(aux, Waux)]
+ *   v    = acc * scale + bias [+ sum_k par_k * conv1x1_k(src)] [+ idt]      (fp32)
+ *   out  = act(v)                       -> bf16 NHWC               (mode PNP_CONV_BF16)
+ *   outf = v[0:3] + lq                  -> fp32 NCHW view          (mode PNP_CONV_LAST)
+ * Reference call sites: ResidualBlockNoBNDynamic_drt.forward (sr_backbone_utils.py:304-333),
+ * input_conv (basicvsr_net.py:484,515), conv_hr/conv_last (iconvsr_ipb_par.py:144-146).
+ */
+enum { PNP_CONV_BF16 = 0, PNP_CONV_LAST = 1 };
+enum { PNP_ACT_NONE = 0, PNP_ACT_LRELU = 1, PNP_ACT_RELU = 2 };
+
+typedef struct pnp_conv_desc {
+  const void* src;     /* bf16 (N,H,W,64) */
+  const void* aux;     /* bf16 (N,H,W,64) im2col'd LR, or NULL */
+  const void* idt;     /* bf16 (N,H,W,64) added before the activation, or NULL */
+  void* out;           /* bf16 (N,H,W,64); PNP_CONV_BF16 only */
+  const void* wpack;   /* packed weights, n_wchunks * 8192 bytes */
+  const float* scale;  /* [64] or NULL */
+  const float* bias;   /* [64] ([3] for PNP_CONV_LAST) or NULL */
+  const float* par;    /* fp32 (N,3,H,W) view of the partition map or NULL; needs center_n == 256 */
+  int64_t par_sn, par_sc, par_sy;
+  const float* lq;     /* PNP_CONV_LAST: fp32 (N,3,H,W) view */
+  int64_t lq_sn, lq_sc, lq_sy;
+  float* outf;         /* PNP_CONV_LAST: fp32 (N,3,H,W) view */
+  int64_t of_sn, of_sc, of_sy;
+  int32_t N, H, W;
+  int32_t n_wchunks;   /* 9, 10 (with aux) or 12 (with par) */
+  int32_t center_n;    /* 64, 256 (with par) or 16 (PNP_CONV_LAST) */
+  int32_t tap_n;       /* 64 or 16 */
+  int32_t aux_k16;     /* K/16 of aux (2 for the 27-entry LR im2col), 0 without aux */
+  int32_t act;
+  int32_t mode;
+} pnp_conv_desc;
+
+int pnp_conv3x3(const pnp_conv_desc* desc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNP_VCVE_H_ */

@@ -1,0 +1,380 @@
+// 3x3 convolution (64 -> 64 | 16 channels) as an implicit GEMM on the 5th-gen tensor cores.
+//
+// Replaces, per launch, one F.conv2d of the reference plus everything elementwise around it:
+//   * ResidualBlockNoBNDynamic_drt.forward  (mmedit/models/common/sr_backbone_utils.py:304-333):
+//       launch A:  t = relu( gamma * (conv3x3(x, Wmix) + bmix) + sum_k par_k * conv1x1_k(x) )
+//       launch B:  x = x + conv3x3(t, W1) + b1
+//   * input_conv + LeakyReLU (basicvsr_net.py:484,515), one source tensor per launch, partial sums
+//     chained through the `id` operand; the 3-channel LR frame rides along as an im2col'd 1x1 (aux)
+//   * conv_hr + LeakyReLU, conv_last + `out += lq`  (iconvsr_ipb_par.py:144-146)
+//
+// Layout: activations are NHWC bf16 with 64 channels = one 128-byte row per pixel, which is exactly
+// one SWIZZLE_128B row for TMA and for the UMMA shared-memory descriptor.
+//
+// Work decomposition: an output tile is 128 consecutive pixels of one image row (UMMA M = 128).
+// A persistent CTA walks down a 128-pixel-wide strip; source rows (130 pixels incl. x halo) are
+// streamed once by TMA into a ring, and the nine taps of a tile are nine *views* of three ring rows:
+// the A descriptor start is moved by (dx+1) pixels = (dx+1)*128 bytes and dy selects the ring slot.
+// TMA zero fill outside the image implements the conv padding.  Weights stay resident in smem.
+// Accumulators live in TMEM (two 256-column buffers) so the epilogue of tile i overlaps the MMAs of
+// tile i+1.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
+#include "pnp_conv.cuh"
+#include "pnp_ptx.cuh"
+
+namespace pnp {
+
+namespace {
+
+struct SmemLayout {
+  uint32_t w, a, aux, io, misc, total;
+};
+
+__host__ __device__ inline SmemLayout make_layout(int n_wchunks, int s_a, int has_aux, int n_io) {
+  SmemLayout l;
+  l.w = 0;
+  l.a = l.w + n_wchunks * kWChunkBytes;
+  l.aux = l.a + s_a * kASlotBytes;
+  l.io = l.aux + (has_aux ? 2 * kTileBytes : 0);
+  l.misc = l.io + n_io * kTileBytes;
+  l.total = l.misc + 1024;
+  return l;
+}
+
+// misc region: 64 floats scale, 64 floats bias, then barriers
+struct Misc {
+  float scale[64];
+  float bias[64];
+  uint64_t w_full;
+  uint64_t a_full[kMaxASlots];
+  uint64_t a_empty[kMaxASlots];
+  uint64_t aux_full[2];
+  uint64_t aux_empty[2];
+  uint64_t id_full[kMaxIoSlots];
+  uint64_t io_empty[kMaxIoSlots];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Misc) <= 1024, "misc region overflow");
+
+struct TileCoord {
+  int n, x0, y;
+  bool first, last;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t, int t_begin, int t_end) {
+  TileCoord c;
+  int col = t / p.H;
+  c.y = t - col * p.H;
+  c.n = col / p.strips;
+  c.x0 = (col - c.n * p.strips) * kTilePx;
+  c.first = (t == t_begin) || (c.y == 0);
+  c.last = (t == t_end - 1) || (c.y == p.H - 1);
+  return c;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == kActLrelu) return v > 0.f ? v : 0.1f * v;
+  if (act == kActRelu) return fmaxf(v, 0.f);
+  return v;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;            // 1024-byte aligned window
+  uint8_t* sgen = smem_raw + (sbase - raw);
+  const SmemLayout L = make_layout(p.n_wchunks, p.s_a, p.aux_k16 > 0, p.n_io);
+  Misc* misc = reinterpret_cast<Misc*>(sgen + L.misc);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int t_begin = blockIdx.x * p.tiles_per_cta;
+  const int t_end = min(p.tiles_total, t_begin + p.tiles_per_cta);
+  const int s_a = p.s_a;
+  const int n_io = p.n_io;
+
+  // ---------------------------------------------------------------- setup
+  if (threadIdx.x < 64) {
+    misc->scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.0f;
+    const int nb = (p.mode == kModeLast) ? 3 : 64;
+    misc->bias[threadIdx.x] = (p.bias && threadIdx.x < nb) ? p.bias[threadIdx.x] : 0.0f;
+  }
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(smem_u32(&misc->w_full), 1);
+      for (int i = 0; i < kMaxASlots; ++i) {
+        mbar_init(smem_u32(&misc->a_full[i]), 1);
+        mbar_init(smem_u32(&misc->a_empty[i]), 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(smem_u32(&misc->aux_full[i]), 1);
+        mbar_init(smem_u32(&misc->aux_empty[i]), 1);
+        mbar_init(smem_u32(&misc->acc_full[i]), 1);
+        mbar_init(smem_u32(&misc->acc_empty[i]), 128);
+      }
+      for (int i = 0; i < kMaxIoSlots; ++i) {
+        mbar_init(smem_u32(&misc->id_full[i]), 1);
+        mbar_init(smem_u32(&misc->io_empty[i]), 1);
+      }
+      mbar_fence_init();
+      tma_prefetch_desc(&p.tm_src);
+      tma_prefetch_desc(&p.tm_out);
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&misc->tmem_base), kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = misc->tmem_base;
+
+  const uint32_t w_smem = sbase + L.w;
+  const uint32_t a_smem = sbase + L.a;
+  const uint32_t aux_smem = sbase + L.aux;
+  const uint32_t io_smem = sbase + L.io;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer (one lane)
+    if (lane == 0) {
+      const uint32_t wbar = smem_u32(&misc->w_full);
+      mbar_arrive_expect_tx(wbar, p.n_wchunks * kWChunkBytes);
+      for (int c = 0; c < p.n_wchunks; ++c)
+        bulk_load_1d(w_smem + c * kWChunkBytes,
+                     reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)c * kWChunkBytes, kWChunkBytes,
+                     wbar);
+      uint32_t ld = 0;
+      for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
+        const TileCoord c = decode_tile(p, t, t_begin, t_end);
+        for (int r = c.first ? c.y - 1 : c.y + 1; r <= c.y + 1; ++r, ++ld) {
+          const uint32_t slot = ld % s_a, ph = (ld / s_a) & 1;
+          mbar_wait(smem_u32(&misc->a_empty[slot]), ph ^ 1, 1);
+          const uint32_t fb = smem_u32(&misc->a_full[slot]);
+          mbar_arrive_expect_tx(fb, kRowBytes);
+          tma_load_4d(a_smem + slot * kASlotBytes, &p.tm_src, fb, 0, c.x0 - 1, r, c.n);
+        }
+        if (p.aux_k16 > 0) {
+          const uint32_t s = it & 1, ph = (it >> 1) & 1;
+          mbar_wait(smem_u32(&misc->aux_empty[s]), ph ^ 1, 2);
+          const uint32_t fb = smem_u32(&misc->aux_full[s]);
+          mbar_arrive_expect_tx(fb, kTileBytes);
+          tma_load_4d(aux_smem + s * kTileBytes, &p.tm_aux, fb, 0, c.x0, c.y, c.n);
+        }
+        if (p.has_id) {
+          const uint32_t s = it % n_io, ph = (it / n_io) & 1;
+          mbar_wait(smem_u32(&misc->io_empty[s]), ph ^ 1, 3);
+          const uint32_t fb = smem_u32(&misc->id_full[s]);
+          mbar_arrive_expect_tx(fb, kTileBytes);
+          tma_load_4d(io_smem + s * kTileBytes, &p.tm_id, fb, 0, c.x0, c.y, c.n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer (one lane)
+    if (lane == 0) {
+      const uint32_t idesc_center = umma_idesc_bf16(128, p.center_n);
+      const uint32_t idesc_tap = umma_idesc_bf16(128, p.tap_n);
+      const int center_chunks = (p.center_n == 256) ? 4 : 1;
+      const bool doc_bo = (p.base_off_mode == 0);
+      mbar_wait(smem_u32(&misc->w_full), 0, 4);
+      uint32_t ld_base = 0, ld_next = 0, confirmed = 0;
+      for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
+        const TileCoord c = decode_tile(p, t, t_begin, t_end);
+        if (c.first) {
+          ld_base = ld_next;
+          ld_next += 3;
+        } else {
+          ld_base += 1;
+          ld_next += 1;
+        }
+        while (confirmed < ld_base + 3) {
+          mbar_wait(smem_u32(&misc->a_full[confirmed % s_a]), (confirmed / s_a) & 1, 5);
+          ++confirmed;
+        }
+        const uint32_t b = it & 1;
+        mbar_wait(smem_u32(&misc->acc_empty[b]), ((it >> 1) & 1) ^ 1, 6);
+        if (p.aux_k16 > 0) mbar_wait(smem_u32(&misc->aux_full[it & 1]), (it >> 1) & 1, 7);
+        tc_fence_after();
+        const uint32_t d = tmem_base + b * kAccStride;
+        uint32_t accum = 0;
+#pragma unroll 1
+        for (int j = 0; j < 9; ++j) {
+          const int tap = (j == 0) ? 4 : (j <= 4 ? j - 1 : j);   // centre first, then row-major
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          const uint32_t slot = (ld_base + dy + 1) % s_a;
+          const uint32_t a_addr = a_smem + slot * kASlotBytes + (dx + 1) * 128;
+          const uint32_t b_addr = w_smem + (j == 0 ? 0 : (center_chunks + j - 1)) * kWChunkBytes;
+          const uint32_t idesc = (j == 0) ? idesc_center : idesc_tap;
+          const uint32_t bo = doc_bo ? ((a_addr >> 7) & 7u) : 0u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(d, umma_desc_sw128(a_addr + k * 32, bo), umma_desc_sw128(b_addr + k * 32, 0), idesc,
+                      accum);
+            accum = 1;
+          }
+        }
+        if (p.aux_k16 > 0) {
+          const uint32_t a_addr = aux_smem + (it & 1) * kTileBytes;
+          const uint32_t b_addr = w_smem + (center_chunks + 8) * kWChunkBytes;
+          for (int k = 0; k < p.aux_k16; ++k)
+            umma_bf16(d, umma_desc_sw128(a_addr + k * 32, 0), umma_desc_sw128(b_addr + k * 32, 0), idesc_tap,
+                      1);
+        }
+        umma_commit(smem_u32(&misc->a_empty[ld_base % s_a]));
+        if (c.last) {
+          umma_commit(smem_u32(&misc->a_empty[(ld_base + 1) % s_a]));
+          umma_commit(smem_u32(&misc->a_empty[(ld_base + 2) % s_a]));
+        }
+        if (p.aux_k16 > 0) umma_commit(smem_u32(&misc->aux_empty[it & 1]));
+        umma_commit(smem_u32(&misc->acc_full[b]));
+      }
+    }
+  } else {
+    // ============================================================ epilogue (4 warps, 128 threads)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;          // pixel inside the tile == TMEM lane
+    const bool leader = (threadIdx.x == 64);
+    const uint32_t sw = (uint32_t)(row & 7);
+    for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
+      const TileCoord c = decode_tile(p, t, t_begin, t_end);
+      const int x = c.x0 + row;
+      const bool valid = x < p.W;
+      const uint32_t b = it & 1;
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+      if (p.par != nullptr && valid) {
+        const float* pp = p.par + (long long)c.n * p.par_sn + (long long)c.y * p.par_sy + x;
+        p0 = __ldg(pp);
+        p1 = __ldg(pp + p.par_sc);
+        p2 = __ldg(pp + 2 * p.par_sc);
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * kAccStride;
+      if (p.mode == kModeLast) {
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+        if (valid) {
+          const float* lp = p.lq + (long long)c.n * p.lq_sn + (long long)c.y * p.lq_sy + x;
+          r0 = __ldg(lp);
+          r1 = __ldg(lp + p.lq_sc);
+          r2 = __ldg(lp + 2 * p.lq_sc);
+        }
+        mbar_wait(smem_u32(&misc->acc_full[b]), (it >> 1) & 1, 9);
+        tc_fence_after();
+        float v[16];
+        tmem_ld16(taddr, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&misc->acc_empty[b]));
+        if (valid) {
+          float* op = p.outf + (long long)c.n * p.of_sn + (long long)c.y * p.of_sy + x;
+          op[0] = v[0] + misc->bias[0] + r0;
+          op[p.of_sc] = v[1] + misc->bias[1] + r1;
+          op[2 * p.of_sc] = v[2] + misc->bias[2] + r2;
+        }
+        continue;
+      }
+      const uint32_t s_io = it % n_io;
+      if (p.has_id) {
+        mbar_wait(smem_u32(&misc->id_full[s_io]), (it / n_io) & 1, 8);
+      } else {
+        named_bar_sync(1, 128);             // leader has drained the store that last used this slot
+      }
+      mbar_wait(smem_u32(&misc->acc_full[b]), (it >> 1) & 1, 9);
+      tc_fence_after();
+      uint8_t* rowp = sgen + L.io + s_io * kTileBytes + row * 128;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        float v[16];
+        tmem_ld16(taddr + g * 16, v);
+        if (p.center_n == 256) {
+          float a1[16], a2[16], a3[16];
+          tmem_ld16(taddr + 64 + g * 16, a1);
+          tmem_ld16(taddr + 128 + g * 16, a2);
+          tmem_ld16(taddr + 192 + g * 16, a3);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ch = g * 16 + j;
+            v[j] = fmaf(v[j], misc->scale[ch], misc->bias[ch]);
+            v[j] = fmaf(p0, a1[j], v[j]);
+            v[j] = fmaf(p1, a2[j], v[j]);
+            v[j] = fmaf(p2, a3[j], v[j]);
+          }
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ch = g * 16 + j;
+            v[j] = fmaf(v[j], misc->scale[ch], misc->bias[ch]);
+          }
+        }
+        uint4* c0 = reinterpret_cast<uint4*>(rowp + (((2 * g) ^ sw) << 4));
+        uint4* c1 = reinterpret_cast<uint4*>(rowp + (((2 * g + 1) ^ sw) << 4));
+        if (p.has_id) {
+          const uint4 i0 = *c0, i1 = *c1;
+          const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[2 * j] += bf16_lo(iw[j]);
+            v[2 * j + 1] += bf16_hi(iw[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(v[0], v[1]);
+        o0.y = pack_bf16x2(v[2], v[3]);
+        o0.z = pack_bf16x2(v[4], v[5]);
+        o0.w = pack_bf16x2(v[6], v[7]);
+        o1.x = pack_bf16x2(v[8], v[9]);
+        o1.y = pack_bf16x2(v[10], v[11]);
+        o1.z = pack_bf16x2(v[12], v[13]);
+        o1.w = pack_bf16x2(v[14], v[15]);
+        *c0 = o0;
+        *c1 = o1;
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&misc->acc_empty[b]));
+      fence_proxy_async_smem();
+      named_bar_sync(2, 128);
+      if (leader) {
+        tma_store_4d(&p.tm_out, io_smem + s_io * kTileBytes, 0, c.x0, c.y, c.n);
+        tma_store_commit();
+        // the slot tile it+1 will use was last read by the store of tile it+1-n_io
+        if (n_io == 2) tma_store_wait_read<1>();
+        else if (n_io == 3) tma_store_wait_read<2>();
+        else tma_store_wait_read<3>();
+        if (p.has_id && it + 1 >= n_io) mbar_arrive(smem_u32(&misc->io_empty[(it + 1) % n_io]));
+      }
+    }
+    if (leader) tma_store_wait_all<0>();
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+size_t conv_smem_bytes(const ConvParams& p) {
+  return make_layout(p.n_wchunks, p.s_a, p.aux_k16 > 0, p.n_io).total + 1024;  // + alignment slack
+}
+
+cudaError_t launch_conv(const ConvParams& p, int grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  const size_t smem = conv_smem_bytes(p);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         232448);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  conv3x3_umma_kernel<<<grid, kConvThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace pnp

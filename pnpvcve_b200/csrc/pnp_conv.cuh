@@ -1,0 +1,54 @@
+// Parameters of the tcgen05 implicit-GEMM 3x3 convolution kernel (pnp_conv.cu).
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace pnp {
+
+constexpr int kTilePx = 128;                 // output pixels per UMMA tile (one image-row segment)
+constexpr int kHaloPx = kTilePx + 2;         // source pixels staged per row (x halo of 1 each side)
+constexpr int kRowBytes = kHaloPx * 128;     // 16640: one staged source row, 64 bf16 per pixel
+constexpr int kASlotBytes = 17 * 1024;       // ring slot (1024-aligned, >= kRowBytes)
+constexpr int kTileBytes = kTilePx * 128;    // 16384: one 128-pixel x 64-channel bf16 tile
+constexpr int kWChunkBytes = 8192;           // one 64(N) x 64(K) bf16 weight block
+constexpr int kConvThreads = 192;            // warp0 TMA producer, warp1 MMA issuer, warps2-5 epilogue
+constexpr int kMaxASlots = 8;
+constexpr int kMaxIoSlots = 4;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;              // TMEM columns per accumulator buffer (2 buffers)
+
+enum ConvMode { kModeBf16 = 0, kModeLast = 1 };
+enum ConvAct { kActNone = 0, kActLrelu = 1, kActRelu = 2 };
+
+struct ConvParams {
+  CUtensorMap tm_src;   // (64, W, H, N) bf16, box (64,130,1,1), SWIZZLE_128B
+  CUtensorMap tm_aux;   // box (64,128,1,1)
+  CUtensorMap tm_id;    // box (64,128,1,1)
+  CUtensorMap tm_out;   // box (64,128,1,1)
+  const void* wpack;    // n_wchunks * 8192 bytes, pre-swizzled, in consumption order
+  const float* scale;   // [64] per-output-channel scale of the 3x3 accumulator, or null
+  const float* bias;    // [64] ([3] in kModeLast), or null
+  const float* par;     // partition map (n,3,H,W) fp32 view, or null
+  long long par_sn, par_sc, par_sy;
+  const float* lq;      // kModeLast: (n,3,H,W) fp32 view added to the output
+  long long lq_sn, lq_sc, lq_sy;
+  float* outf;          // kModeLast: (n,3,H,W) fp32 view
+  long long of_sn, of_sc, of_sy;
+  int H, W, N, strips;
+  int tiles_total, tiles_per_cta;
+  int n_wchunks;
+  int center_n;         // N of the centre-tap MMA: 64, 256 (3x3 + three 1x1 partition convs) or 16
+  int tap_n;            // N of the other taps: 64 or 16
+  int aux_k16;          // K/16 of the aux source (centre tap only); 0 = no aux
+  int has_id;
+  int act;
+  int mode;
+  int s_a;              // A ring slots
+  int n_io;             // id/out staging slots
+  int base_off_mode;    // 0: descriptor base_offset=(addr>>7)&7 (PTX ISA); 1: always 0
+};
+
+size_t conv_smem_bytes(const ConvParams& p);
+cudaError_t launch_conv(const ConvParams& p, int grid, cudaStream_t stream);
+
+}  // namespace pnp

@@ -1,0 +1,295 @@
+// Memory-bound kernels of the BAE path: MV-guided warp (K1), LR im2col packing, weight packing with
+// expert mixing (K4) and the CAA heads.
+#include "pnp_ops.cuh"
+#include "pnp_ptx.cuh"
+
+namespace pnp {
+
+// =====================================================================================
+// K1: motion-vector guided bilinear warp.
+// Reference: flow_warp (mmedit/models/common/flow_warp.py:6-50) called by VOSAlignment.forward
+// (mmedit/models/backbones/sr_backbones/iconvsr_mv.py:17-18) -> F.grid_sample(bilinear, zeros,
+// align_corners=True).  The reference normalises x+mv to [-1,1] and ATen un-normalises it again;
+// that fp32 round trip is not the identity, so the exact operation sequence is replayed with
+// explicitly rounded intrinsics (no FMA contraction) to keep the integer taps bit-exact.
+//
+// One thread = one pixel x 8 channels (16 bytes): 8 consecutive threads read one 128-byte NHWC
+// pixel per tap, a warp writes 512 contiguous bytes.
+// =====================================================================================
+__device__ __forceinline__ float warp_coord(float pos, float mv, float size_m1_div, float size_m1) {
+  const float g = __fadd_rn(pos, mv);                                  // grid + flow
+  const float nrm = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, g), size_m1_div), 1.0f);  // 2*g/max(s-1,1) - 1
+  return __fmul_rn(__fmul_rn(__fadd_rn(nrm, 1.0f), 0.5f), size_m1);    // ((c+1)/2)*(s-1)
+}
+
+__global__ void __launch_bounds__(256)
+mv_warp_kernel(const uint4* __restrict__ src, const float* __restrict__ flow_x,
+               const float* __restrict__ flow_y, long long flow_sy, uint4* __restrict__ dst, int H, int W,
+               int* __restrict__ dbg_x0, int* __restrict__ dbg_y0) {
+  const long long total = (long long)H * W * 8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int chunk = (int)(idx & 7);
+    const long long pix = idx >> 3;
+    const int y = (int)(pix / W);
+    const int x = (int)(pix - (long long)y * W);
+    const float fx = __ldg(flow_x + (long long)y * flow_sy + x);
+    const float fy = __ldg(flow_y + (long long)y * flow_sy + x);
+    const float ix = warp_coord((float)x, fx, (float)max(W - 1, 1), (float)(W - 1));
+    const float iy = warp_coord((float)y, fy, (float)max(H - 1, 1), (float)(H - 1));
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const float x1f = __fadd_rn(x0f, 1.0f), y1f = __fadd_rn(y0f, 1.0f);
+    const float wx1 = __fsub_rn(ix, x0f), wx0 = __fsub_rn(x1f, ix);
+    const float wy1 = __fsub_rn(iy, y0f), wy0 = __fsub_rn(y1f, iy);
+    const float wnw = __fmul_rn(wx0, wy0), wne = __fmul_rn(wx1, wy0);
+    const float wsw = __fmul_rn(wx0, wy1), wse = __fmul_rn(wx1, wy1);
+    // clamp before the int conversion so huge |mv| cannot overflow; out-of-range taps are dropped
+    const int x0 = (int)fminf(fmaxf(x0f, -2.0f), (float)W + 1.0f);
+    const int y0 = (int)fminf(fmaxf(y0f, -2.0f), (float)H + 1.0f);
+    if (dbg_x0 != nullptr && chunk == 0) {
+      dbg_x0[pix] = (int)fminf(fmaxf(x0f, -2147483000.0f), 2147483000.0f);
+      dbg_y0[pix] = (int)fminf(fmaxf(y0f, -2147483000.0f), 2147483000.0f);
+    }
+    const bool okx0 = x0 >= 0 && x0 < W, okx1 = x0 + 1 >= 0 && x0 + 1 < W;
+    const bool oky0 = y0 >= 0 && y0 < H, oky1 = y0 + 1 >= 0 && y0 + 1 < H;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const uint4 vnw = (okx0 && oky0) ? __ldg(src + ((long long)y0 * W + x0) * 8 + chunk) : z;
+    const uint4 vne = (okx1 && oky0) ? __ldg(src + ((long long)y0 * W + x0 + 1) * 8 + chunk) : z;
+    const uint4 vsw = (okx0 && oky1) ? __ldg(src + ((long long)(y0 + 1) * W + x0) * 8 + chunk) : z;
+    const uint4 vse = (okx1 && oky1) ? __ldg(src + ((long long)(y0 + 1) * W + x0 + 1) * 8 + chunk) : z;
+    const uint32_t a[4] = {vnw.x, vnw.y, vnw.z, vnw.w};
+    const uint32_t b[4] = {vne.x, vne.y, vne.z, vne.w};
+    const uint32_t c[4] = {vsw.x, vsw.y, vsw.z, vsw.w};
+    const uint32_t d[4] = {vse.x, vse.y, vse.z, vse.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // out = nw*wnw + ne*wne + sw*wsw + se*wse, products rounded, summed left to right (ATen order)
+      float lo = __fmul_rn(bf16_lo(a[j]), wnw);
+      lo = __fadd_rn(lo, __fmul_rn(bf16_lo(b[j]), wne));
+      lo = __fadd_rn(lo, __fmul_rn(bf16_lo(c[j]), wsw));
+      lo = __fadd_rn(lo, __fmul_rn(bf16_lo(d[j]), wse));
+      float hi = __fmul_rn(bf16_hi(a[j]), wnw);
+      hi = __fadd_rn(hi, __fmul_rn(bf16_hi(b[j]), wne));
+      hi = __fadd_rn(hi, __fmul_rn(bf16_hi(c[j]), wsw));
+      hi = __fadd_rn(hi, __fmul_rn(bf16_hi(d[j]), wse));
+      o[j] = pack_bf16x2(lo, hi);
+    }
+    dst[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+cudaError_t launch_mv_warp(const void* src, const float* flow_x, const float* flow_y, long long flow_sy,
+                           void* dst, int H, int W, int* dbg_x0, int* dbg_y0, int num_sms,
+                           cudaStream_t stream) {
+  const long long total = (long long)H * W * 8;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms * 64;
+  if (blocks > cap) blocks = cap;
+  mv_warp_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), flow_x, flow_y,
+                                                  flow_sy, reinterpret_cast<uint4*>(dst), H, W, dbg_x0,
+                                                  dbg_y0);
+  return cudaGetLastError();
+}
+
+// =====================================================================================
+// LR frame -> im2col'd bf16 NHWC "aux" operand: channel k = tap*3 + c (27 used, 5 zero pad, the
+// upper 32 channels of the 64-channel row are never read).  The 3-channel part of the reference's
+// 131/195-channel input conv (basicvsr_net.py:484 on cat([lr, ...]), iconvsr_ipb_par.py:90,125)
+// becomes a K=32 centre-tap GEMM.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+lr_im2col_kernel(const float* __restrict__ lr, long long sn, long long sc, long long sy, uint4* __restrict__ dst,
+                 int N, int H, int W) {
+  const long long total = (long long)N * H * W;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(pix / ((long long)H * W));
+    const long long rem = pix - (long long)n * H * W;
+    const int y = (int)(rem / W);
+    const int x = (int)(rem - (long long)y * W);
+    float v[32];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        v[tap * 3 + c] = ok ? __ldg(lr + (long long)n * sn + (long long)c * sc + (long long)yy * sy + xx) : 0.f;
+    }
+#pragma unroll
+    for (int k = 27; k < 32; ++k) v[k] = 0.f;
+    uint4* o = dst + pix * 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      o[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                        pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+  }
+}
+
+cudaError_t launch_lr_im2col(const float* lr, long long sn, long long sc, long long sy, void* dst, int N,
+                             int H, int W, int num_sms, cudaStream_t stream) {
+  const long long total = (long long)N * H * W;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms * 32;
+  if (blocks > cap) blocks = cap;
+  lr_im2col_kernel<<<(int)blocks, 256, 0, stream>>>(lr, sn, sc, sy, reinterpret_cast<uint4*>(dst), N, H, W);
+  return cudaGetLastError();
+}
+
+// =====================================================================================
+// K4: weight packing.  A packed 3x3 conv is a sequence of 8 KB blocks [64 rows = out channel]
+// [64 cols = in channel] bf16, rows of 128 bytes with the 128B swizzle pre-applied (16-byte
+// column group g of row r is stored at g ^ (r & 7)), block order = MMA consumption order:
+// centre tap first (occupying `center_chunks` blocks), then taps 0,1,2,3,5,6,7,8.
+//
+// With n_experts > 1 the block is the expert mixture  sum_e coef[e] * w[e]  of
+// Dynamic_conv2d_se.forward (sr_backbone_utils.py:198-199), evaluated once per distinct CRF instead
+// of once per block per frame.  `in_begin2 >= 0` adds a second input-channel slice (the
+// neighbour == key_warp case of iconvsr_ipb_par.py:85-88, where two K slices see the same tensor).
+// =====================================================================================
+__device__ __forceinline__ size_t packed_offset(int block, int row, int col) {
+  return (size_t)block * kPackBlockBytes + (size_t)row * 128 + (size_t)((((col >> 3) ^ (row & 7)) << 4)) +
+         (size_t)(col & 7) * 2;
+}
+
+__global__ void __launch_bounds__(256)
+pack_conv3x3_kernel(const float* __restrict__ w, int n_experts, const float* __restrict__ coef,
+                    int out_ch, int in_total, int in_begin, int in_begin2, int in_count,
+                    uint8_t* __restrict__ dst, int center_chunks) {
+  // one thread per (tap, row<64, col<64)
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 9 * 64 * 64) return;
+  const int col = idx & 63, row = (idx >> 6) & 63, tap = idx >> 12;
+  float acc = 0.f;
+  if (row < out_ch && col < in_count) {
+    const size_t per_expert = (size_t)out_ch * in_total * 9;
+    for (int e = 0; e < n_experts; ++e) {
+      const float ce = coef ? coef[e] : 1.0f;
+      float v = w[e * per_expert + ((size_t)row * in_total + in_begin + col) * 9 + tap];
+      if (in_begin2 >= 0) v += w[e * per_expert + ((size_t)row * in_total + in_begin2 + col) * 9 + tap];
+      acc = fmaf(ce, v, acc);
+    }
+  }
+  const int block = (tap == 4) ? 0 : (center_chunks + (tap < 4 ? tap : tap - 1));
+  *reinterpret_cast<__nv_bfloat16*>(dst + packed_offset(block, row, col)) = __float2bfloat16_rn(acc);
+}
+
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float* __restrict__ w, int rows, int cols, long long row_stride, long long col_stride,
+                 uint8_t* __restrict__ dst, int row_offset) {
+  // generic [rows<=64][cols<=64] matrix into rows row_offset.. of a packed block sequence
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 64) return;
+  const int col = idx & 63, row = idx >> 6;
+  float v = 0.f;
+  if (row < rows && col < cols) v = w[(long long)row * row_stride + (long long)col * col_stride];
+  const int r = row_offset + row;
+  *reinterpret_cast<__nv_bfloat16*>(dst + packed_offset(r >> 6, r & 63, col)) = __float2bfloat16_rn(v);
+}
+
+__global__ void __launch_bounds__(256)
+pack_aux_kernel(const float* __restrict__ w, int out_ch, int in_total, uint8_t* __restrict__ dst) {
+  // [64 rows][64 cols]: col = tap*3 + c for the first 3 input channels
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 64) return;
+  const int col = idx & 63, row = idx >> 6;
+  float v = 0.f;
+  if (row < out_ch && col < 27) {
+    const int tap = col / 3, c = col - tap * 3;
+    v = w[((size_t)row * in_total + c) * 9 + tap];
+  }
+  *reinterpret_cast<__nv_bfloat16*>(dst + packed_offset(0, row, col)) = __float2bfloat16_rn(v);
+}
+
+cudaError_t launch_pack_conv3x3(const float* w, int n_experts, const float* coef, int out_ch, int in_total,
+                                int in_begin, int in_begin2, int in_count, void* dst, int center_chunks,
+                                cudaStream_t stream) {
+  pack_conv3x3_kernel<<<(9 * 64 * 64 + 255) / 256, 256, 0, stream>>>(
+      w, n_experts, coef, out_ch, in_total, in_begin, in_begin2, in_count, reinterpret_cast<uint8_t*>(dst),
+      center_chunks);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_rows(const float* w, int rows, int cols, long long row_stride, long long col_stride,
+                             void* dst, int row_offset, cudaStream_t stream) {
+  pack_rows_kernel<<<16, 256, 0, stream>>>(w, rows, cols, row_stride, col_stride,
+                                           reinterpret_cast<uint8_t*>(dst), row_offset);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_aux(const float* w, int out_ch, int in_total, void* dst, cudaStream_t stream) {
+  pack_aux_kernel<<<16, 256, 0, stream>>>(w, out_ch, in_total, reinterpret_cast<uint8_t*>(dst));
+  return cudaGetLastError();
+}
+
+// =====================================================================================
+// CAA heads (compression-aware adaptation), one thread block per frame:
+//   experts = softmax(W2 relu(W1 crf + b1) + b2)            Base_Predictor, domain_aware.py:172-183
+//   gamma   = relu6(V2 relu(V1 qp) + 3) / 3                 SEModule/Hsigmoid, domain_aware.py:201-222
+// and the per-frame, per-block epilogue bias  gamma * (experts . conv2.bias)
+// (sr_backbone_utils.py:200-208), so that the conv kernels only see (scale, bias) vectors.
+// =====================================================================================
+__global__ void __launch_bounds__(64)
+caa_heads_kernel(const float* __restrict__ base_qp, const float* __restrict__ qp, int frames,
+                 const float* __restrict__ b0w, const float* __restrict__ b0b, const float* __restrict__ b2w,
+                 const float* __restrict__ b2b, const float* __restrict__ s0w, const float* __restrict__ s2w,
+                 int n_experts, int se_hidden, float* __restrict__ experts, float* __restrict__ gamma) {
+  __shared__ float h[64];
+  __shared__ float logit[16];
+  const int f = blockIdx.x, tid = threadIdx.x;
+  if (f >= frames) return;
+  const float crf = base_qp[f], q = qp[f];
+  h[tid] = fmaxf(fmaf(b0w[tid], crf, b0b[tid]), 0.f);
+  __syncthreads();
+  if (tid < n_experts) {
+    float a = b2b[tid];
+    for (int k = 0; k < 64; ++k) a = fmaf(b2w[tid * 64 + k], h[k], a);
+    logit[tid] = a;
+  }
+  __syncthreads();
+  if (tid < n_experts) {
+    float m = logit[0];
+    for (int e = 1; e < n_experts; ++e) m = fmaxf(m, logit[e]);
+    float s = 0.f;
+    for (int e = 0; e < n_experts; ++e) s += expf(logit[e] - m);
+    experts[(size_t)f * n_experts + tid] = expf(logit[tid] - m) / s;
+  }
+  float g = 0.f;
+  for (int k = 0; k < se_hidden; ++k) g = fmaf(s2w[tid * se_hidden + k], fmaxf(s0w[k] * q, 0.f), g);
+  g = fminf(fmaxf(g + 3.0f, 0.f), 6.0f) / 3.0f;
+  gamma[(size_t)f * 64 + tid] = g;
+}
+
+__global__ void __launch_bounds__(64)
+mix_bias_kernel(const float* __restrict__ conv2_bias, long long block_stride, int n_blocks, int n_experts,
+                const float* __restrict__ experts, const float* __restrict__ gamma, int frames,
+                float* __restrict__ out) {
+  // out[f][blk][c] = gamma[f][c] * sum_e experts[f][e] * conv2_bias[blk][e][c]
+  const int f = blockIdx.x, blk = blockIdx.y, c = threadIdx.x;
+  if (f >= frames) return;
+  const float* b = conv2_bias + (long long)blk * block_stride;
+  float a = 0.f;
+  for (int e = 0; e < n_experts; ++e) a = fmaf(experts[(size_t)f * n_experts + e], b[e * 64 + c], a);
+  out[((size_t)f * n_blocks + blk) * 64 + c] = a * gamma[(size_t)f * 64 + c];
+}
+
+cudaError_t launch_caa_heads(const float* base_qp, const float* qp, int frames, const float* b0w,
+                             const float* b0b, const float* b2w, const float* b2b, const float* s0w,
+                             const float* s2w, int n_experts, int se_hidden, float* experts, float* gamma,
+                             cudaStream_t stream) {
+  caa_heads_kernel<<<frames, 64, 0, stream>>>(base_qp, qp, frames, b0w, b0b, b2w, b2b, s0w, s2w, n_experts,
+                                              se_hidden, experts, gamma);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mix_bias(const float* conv2_bias, long long block_stride, int n_blocks, int n_experts,
+                            const float* experts, const float* gamma, int frames, float* out,
+                            cudaStream_t stream) {
+  dim3 grid(frames, n_blocks);
+  mix_bias_kernel<<<grid, 64, 0, stream>>>(conv2_bias, block_stride, n_blocks, n_experts, experts, gamma,
+                                           frames, out);
+  return cudaGetLastError();
+}
+
+}  // namespace pnp

@@ -1,0 +1,29 @@
+// Launchers of the memory-bound kernels in pnp_ops.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pnp {
+
+constexpr int kPackBlockBytes = 8192;
+
+cudaError_t launch_mv_warp(const void* src, const float* flow_x, const float* flow_y, long long flow_sy,
+                           void* dst, int H, int W, int* dbg_x0, int* dbg_y0, int num_sms,
+                           cudaStream_t stream);
+cudaError_t launch_lr_im2col(const float* lr, long long sn, long long sc, long long sy, void* dst, int N,
+                             int H, int W, int num_sms, cudaStream_t stream);
+cudaError_t launch_pack_conv3x3(const float* w, int n_experts, const float* coef, int out_ch, int in_total,
+                                int in_begin, int in_begin2, int in_count, void* dst, int center_chunks,
+                                cudaStream_t stream);
+cudaError_t launch_pack_rows(const float* w, int rows, int cols, long long row_stride, long long col_stride,
+                             void* dst, int row_offset, cudaStream_t stream);
+cudaError_t launch_pack_aux(const float* w, int out_ch, int in_total, void* dst, cudaStream_t stream);
+cudaError_t launch_caa_heads(const float* base_qp, const float* qp, int frames, const float* b0w,
+                             const float* b0b, const float* b2w, const float* b2b, const float* s0w,
+                             const float* s2w, int n_experts, int se_hidden, float* experts, float* gamma,
+                             cudaStream_t stream);
+cudaError_t launch_mix_bias(const float* conv2_bias, long long block_stride, int n_blocks, int n_experts,
+                            const float* experts, const float* gamma, int frames, float* out,
+                            cudaStream_t stream);
+
+}  // namespace pnp

@@ -1,0 +1,186 @@
+"""Tensor-level wrappers over the C ABI (raw pointers + current CUDA stream).
+
+PyTorch is used for device memory and streams only; all arithmetic happens in libpnpvcve.so.
+Layouts: feature maps are bf16 NHWC ``(N, H, W, 64)``; frames / motion vectors / partition maps
+stay in the reference's fp32 NCHW layout and are consumed through strided views.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (PNP_ACT_LRELU, PNP_ACT_NONE, PNP_ACT_RELU, PNP_CONV_BF16,  # noqa: F401
+                   PNP_CONV_LAST, ConvDesc)
+
+CHUNK_BYTES = 8192
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _feat_check(t, name):
+    if t.dtype != torch.bfloat16 or t.dim() != 4 or t.shape[-1] != 64 or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous bf16 (N,H,W,64) tensor, got "
+                         f"{tuple(t.shape)} {t.dtype}")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must live on a CUDA device")
+
+
+def _plane_view_check(t, name):
+    """fp32 (N,3|2,H,W)-like view whose innermost stride is 1."""
+    if t.dtype != torch.float32 or t.stride(-1) != 1 or not t.is_cuda:
+        raise ValueError(f"{name} must be an fp32 CUDA view with unit innermost stride")
+
+
+def new_feature(n, h, w, device, zero=False):
+    f = torch.zeros if zero else torch.empty
+    return f((n, h, w, 64), dtype=torch.bfloat16, device=device)
+
+
+def new_wpack(n_chunks, device):
+    return torch.zeros(n_chunks * CHUNK_BYTES, dtype=torch.uint8, device=device)
+
+
+def mv_warp(src, flow, dst, debug=False):
+    """K1.  src/dst (1,H,W,64) bf16; flow (2,H,W) fp32 view (x then y).  Returns (x0,y0) if debug."""
+    _feat_check(src, "src")
+    _feat_check(dst, "dst")
+    _plane_view_check(flow, "flow")
+    _, h, w, _ = src.shape
+    if flow.shape != (2, h, w) or src.shape[0] != 1 or dst.shape != src.shape:
+        raise ValueError(f"The spatial sizes of input ({(h, w)}) and flow ({tuple(flow.shape[1:])}) "
+                         "are not the same.")
+    dx = dy = None
+    if debug:
+        dx = torch.empty((h, w), dtype=torch.int32, device=src.device)
+        dy = torch.empty((h, w), dtype=torch.int32, device=src.device)
+    lib = _lib.load()
+    _lib.check(lib.pnp_mv_warp(_ptr(src), _ptr(flow[0]), _ptr(flow[1]), flow.stride(1), _ptr(dst), h, w,
+                               _ptr(dx), _ptr(dy), _stream()), "pnp_mv_warp")
+    return (dx, dy) if debug else None
+
+
+def lr_im2col(lr, dst):
+    """lr (N,3,H,W) fp32 view -> dst (N,H,W,64) bf16 (channels 0..31 written)."""
+    _plane_view_check(lr, "lr")
+    _feat_check(dst, "dst")
+    n, c, h, w = lr.shape
+    if c != 3 or dst.shape != (n, h, w, 64):
+        raise ValueError("lr_im2col: shape mismatch")
+    lib = _lib.load()
+    _lib.check(lib.pnp_lr_im2col(_ptr(lr), lr.stride(0), lr.stride(1), lr.stride(2), _ptr(dst), n, h, w,
+                                 _stream()), "pnp_lr_im2col")
+
+
+def pack_conv3x3(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=None, center_chunks=1):
+    """w fp32 (O,I,3,3) or (E,O,I,3,3) contiguous -> packed blocks in dst (uint8)."""
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        raise ValueError("pack_conv3x3: w must be contiguous fp32")
+    if w.dim() == 4:
+        e, (o, i) = 1, w.shape[:2]
+    else:
+        e, o, i = w.shape[:3]
+    in_count = i - in_begin if in_count is None else in_count
+    lib = _lib.load()
+    _lib.check(lib.pnp_pack_conv3x3(_ptr(w), e, _ptr(coef), o, i, in_begin, in_begin2, in_count,
+                                    _ptr(dst), center_chunks, _stream()), "pnp_pack_conv3x3")
+
+
+def pack_rows(w2d, dst, row_offset):
+    """fp32 (rows<=64, cols<=64) view -> packed rows row_offset.. of dst."""
+    if w2d.dtype != torch.float32 or w2d.dim() != 2:
+        raise ValueError("pack_rows: need an fp32 matrix")
+    lib = _lib.load()
+    _lib.check(lib.pnp_pack_rows(_ptr(w2d), w2d.shape[0], w2d.shape[1], w2d.stride(0), w2d.stride(1),
+                                 _ptr(dst), row_offset, _stream()), "pnp_pack_rows")
+
+
+def pack_aux(w, dst):
+    if w.dtype != torch.float32 or not w.is_contiguous() or w.dim() != 4:
+        raise ValueError("pack_aux: w must be contiguous fp32 (O,I,3,3)")
+    lib = _lib.load()
+    _lib.check(lib.pnp_pack_aux(_ptr(w), w.shape[0], w.shape[1], _ptr(dst), _stream()), "pnp_pack_aux")
+
+
+def caa_heads(base_qp, qp, params, n_experts):
+    """base_qp/qp: fp32 (F,) -> experts (F,E), gamma (F,64).  params: dict of the six CAA tensors."""
+    f = base_qp.numel()
+    dev = base_qp.device
+    experts = torch.empty((f, n_experts), dtype=torch.float32, device=dev)
+    gamma = torch.empty((f, 64), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.pnp_caa_heads(_ptr(base_qp), _ptr(qp), f, _ptr(params["b0w"]), _ptr(params["b0b"]),
+                                 _ptr(params["b2w"]), _ptr(params["b2b"]), _ptr(params["s0w"]),
+                                 _ptr(params["s2w"]), n_experts, params["s0w"].numel(), _ptr(experts),
+                                 _ptr(gamma), _stream()), "pnp_caa_heads")
+    return experts, gamma
+
+
+def mix_bias(conv2_bias, experts, gamma):
+    """conv2_bias (B,E,64), experts (F,E), gamma (F,64) -> (F,B,64)."""
+    b, e, _ = conv2_bias.shape
+    f = experts.shape[0]
+    out = torch.empty((f, b, 64), dtype=torch.float32, device=experts.device)
+    lib = _lib.load()
+    _lib.check(lib.pnp_mix_bias(_ptr(conv2_bias), b, e, _ptr(experts), _ptr(gamma), f, _ptr(out),
+                                _stream()), "pnp_mix_bias")
+    return out
+
+
+def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
+                   act=PNP_ACT_NONE, lq=None, outf=None):
+    """Fill a ConvDesc in place (reusable across launches)."""
+    n, h, w, _ = src.shape
+    last = outf is not None
+    d.src, d.aux, d.idt = src.data_ptr(), (aux.data_ptr() if aux is not None else None), \
+        (idt.data_ptr() if idt is not None else None)
+    d.out = out.data_ptr() if out is not None else None
+    d.wpack = wpack.data_ptr()
+    d.scale = scale.data_ptr() if scale is not None else None
+    d.bias = bias.data_ptr() if bias is not None else None
+    if par is not None:
+        d.par, d.par_sn, d.par_sc, d.par_sy = par.data_ptr(), par.stride(0), par.stride(1), par.stride(2)
+    else:
+        d.par, d.par_sn, d.par_sc, d.par_sy = None, 0, 0, 0
+    if last:
+        d.lq, d.lq_sn, d.lq_sc, d.lq_sy = lq.data_ptr(), lq.stride(0), lq.stride(1), lq.stride(2)
+        d.outf, d.of_sn, d.of_sc, d.of_sy = outf.data_ptr(), outf.stride(0), outf.stride(1), outf.stride(2)
+    else:
+        d.lq, d.lq_sn, d.lq_sc, d.lq_sy = None, 0, 0, 0
+        d.outf, d.of_sn, d.of_sc, d.of_sy = None, 0, 0, 0
+    d.N, d.H, d.W = n, h, w
+    d.center_n = 16 if last else (256 if par is not None else 64)
+    d.tap_n = 16 if last else 64
+    d.aux_k16 = 2 if aux is not None else 0
+    d.n_wchunks = (4 if par is not None else 1) + 8 + (1 if aux is not None else 0)
+    d.act = act
+    d.mode = PNP_CONV_LAST if last else PNP_CONV_BF16
+    return d
+
+
+def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
+            act=PNP_ACT_NONE, lq=None, outf=None):
+    """Fused tcgen05 3x3 conv (see include/pnp_vcve.h: pnp_conv3x3)."""
+    _feat_check(src, "src")
+    for t, nm in ((out, "out"), (aux, "aux"), (idt, "idt")):
+        if t is not None:
+            _feat_check(t, nm)
+            if t.shape != src.shape:
+                raise ValueError(f"conv3x3: {nm} shape {tuple(t.shape)} != src {tuple(src.shape)}")
+    for t, nm in ((par, "par"), (lq, "lq"), (outf, "outf")):
+        if t is not None:
+            _plane_view_check(t, nm)
+            if t.dim() != 4 or t.shape[1] != 3 or t.shape[0] != src.shape[0] or \
+                    tuple(t.shape[2:]) != tuple(src.shape[1:3]):
+                raise ValueError(f"conv3x3: {nm} must be (N,3,H,W) matching src")
+    d = fill_conv_desc(ConvDesc(), src, wpack, out, aux, idt, scale, bias, par, act, lq, outf)
+    if wpack.numel() < d.n_wchunks * CHUNK_BYTES:
+        raise ValueError("conv3x3: packed weight buffer too small for this configuration")
+    lib = _lib.load()
+    _lib.check(lib.pnp_conv3x3(ctypes.byref(d), _stream()), "pnp_conv3x3")
+    return out if outf is None else outf
