@@ -35,8 +35,9 @@ typedef enum pnp_status {
 int pnp_abi_version(void);
 const char* pnp_last_error(void);          /* message of the last failing call in this thread */
 int pnp_device_check(void);                /* PNP_OK iff the current device is sm_100 */
-/* 0 (default): UMMA descriptor base_offset = (addr >> 7) & 7 as the PTX ISA prescribes for
- * starts that are not 1024-byte aligned; 1: always 0.  Diagnostic knob. */
+/* Diagnostic knob for the UMMA shared-memory descriptor of pixel-shifted views.
+ * 0 (default, measured-correct on B200): base_offset = 0 (swizzle acts on absolute address bits);
+ * 1: base_offset = (addr >> 7) & 7. */
 int pnp_set_base_offset_mode(int mode);
 
 /*

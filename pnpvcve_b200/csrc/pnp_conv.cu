@@ -178,7 +178,7 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
       const uint32_t idesc_center = umma_idesc_bf16(128, p.center_n);
       const uint32_t idesc_tap = umma_idesc_bf16(128, p.tap_n);
       const int center_chunks = (p.center_n == 256) ? 4 : 1;
-      const bool doc_bo = (p.base_off_mode == 0);
+      const bool doc_bo = (p.base_off_mode == 1);
       mbar_wait(smem_u32(&misc->w_full), 0, 4);
       uint32_t ld_base = 0, ld_next = 0, confirmed = 0;
       for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {

@@ -45,7 +45,7 @@ struct ConvParams {
   int mode;
   int s_a;              // A ring slots
   int n_io;             // id/out staging slots
-  int base_off_mode;    // 0: descriptor base_offset=(addr>>7)&7 (PTX ISA); 1: always 0
+  int base_off_mode;    // 0: descriptor base_offset = 0 (measured-correct on B200); 1: (addr>>7)&7
 };
 
 size_t conv_smem_bytes(const ConvParams& p);

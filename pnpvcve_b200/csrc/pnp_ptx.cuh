@@ -137,8 +137,11 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // ------------------------------------------------------------------ UMMA (tcgen05.mma)
 // Shared-memory matrix descriptor, K-major operand stored as 128-byte rows with the 128B swizzle
 // (the layout TMA writes for a box whose inner extent is 64 bf16): 8-row atoms of 1024 bytes,
-// SBO = 1024.  `start` may be any 16-byte aligned address inside a 1024-aligned tile; the swizzle
-// phase of an unaligned start goes into base_offset = (start >> 7) & 7 (PTX ISA, matrix descriptor).
+// SBO = 1024.  `start` may be any 16-byte aligned address inside a 1024-aligned tile: measured on
+// B200 (tools/gpu_probe.py, profiles/r01_probe.log) the hardware applies the swizzle XOR to the
+// absolute shared-memory address bits, so a view that starts k pixels (k*128 bytes) into a TMA-written
+// tile reads the right data with base_offset = 0; setting base_offset = (start >> 7) & 7 as the PTX
+// ISA text suggests for unaligned starts double-counts the phase and returns garbage.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t start, uint32_t base_offset) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((start & 0x3FFFFu) >> 4);            // bits [0,14)  start address

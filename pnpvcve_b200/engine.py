@@ -57,16 +57,25 @@ def keyframe_rows(slices_host):
 class _Launcher:
     """Pre-bound ctypes call of pnp_conv3x3 with a reusable descriptor."""
 
-    def __init__(self):
+    def __init__(self, prof=None):
         self.lib = _lib.load()
         self.fn = self.lib.pnp_conv3x3
         self.desc = ops.ConvDesc()
         self.ref = ctypes.byref(self.desc)
+        self.prof = prof          # None or {label: [(start_event, end_event), ...]}
 
     def __call__(self, stream, src, wpack, out=None, aux=None, idt=None, scale=None, bias=None,
-                 par=None, act=PNP_ACT_NONE, lq=None, outf=None):
+                 par=None, act=PNP_ACT_NONE, lq=None, outf=None, label=None):
         ops.fill_conv_desc(self.desc, src, wpack, out, aux, idt, scale, bias, par, act, lq, outf)
+        timed = self.prof is not None and label in self.prof
+        if timed:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = self.fn(self.ref, stream)
+        if timed:
+            e1.record()
+            self.prof[label].append((e0, e1))
         if rc != 0:
             _lib.check(rc, "pnp_conv3x3")
 
@@ -82,6 +91,9 @@ class BaeEngine:
         self.buf_key = None
         self.buf = None
         self.launch_count = 0
+        #: set to {label: []} (labels: "block_a", "block_b", "input", "hr", "last", "warp") to have the
+        #: next forward bracket those launches with CUDA events on the launching stream (bench.py)
+        self.prof = None
 
     # ------------------------------------------------------------------ weights
     def _param_key(self):
@@ -232,11 +244,23 @@ class BaeEngine:
         feats = buf["feats"]
         out = torch.empty((n, t, 3, h, w), dtype=torch.float32, device=dev)
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        conv = _Launcher()
+        conv = _Launcher(self.prof)
+        prof = self.prof
         launches = 0
         bwd_feats = None
         if return_features:
             bwd_feats = torch.empty_like(feats)
+
+        def warp(src, flow, dst):
+            timed = prof is not None and "warp" in prof
+            if timed:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            ops.mv_warp(src, flow, dst)
+            if timed:
+                e1.record()
+                prof["warp"].append((e0, e1))
 
         def stack(name, blk_off, b, i, x, dst, mixed):
             """8 BAE blocks: x (in xa/xb) -> dst.  ResidualBlockNoBNDynamic_drt, sr_backbone_utils.py:304-333"""
@@ -247,10 +271,10 @@ class BaeEngine:
             other = buf["xb"] if x is buf["xa"] else buf["xa"]
             for k in range(nb):
                 conv(stream, x, mixed[name][k], out=buf["t"], scale=g, bias=bias_tab[f, blk_off + k],
-                     par=par, act=PNP_ACT_RELU)
+                     par=par, act=PNP_ACT_RELU, label="block_a")
                 o = dst if k == nb - 1 else other
                 conv(stream, buf["t"], st[name + "_conv1_w"][k], out=o, idt=x,
-                     bias=st[name + "_conv1_b"][k], act=PNP_ACT_NONE)
+                     bias=st[name + "_conv1_b"][k], act=PNP_ACT_NONE, label="block_b")
                 x, other = o, x
                 launches += 2
 
@@ -265,21 +289,21 @@ class BaeEngine:
                 x0 = buf["xa"]
                 if i < t - 1:
                     kidx = bwd_key[i]
-                    ops.mv_warp(feats[b, kidx].unsqueeze(0), mvs[b, i, 2:4], buf["kw"])
+                    warp(feats[b, kidx].unsqueeze(0), mvs[b, i, 2:4], buf["kw"])
                     launches += 1
                     if kidx == i + 1:                     # align_key: neighbour is the warped key
                         conv(stream, buf["kw"], st["bwd_merged_aux"], out=x0, aux=buf["lr64"],
-                             bias=st["bwd_in_bias"], act=PNP_ACT_LRELU)
+                             bias=st["bwd_in_bias"], act=PNP_ACT_LRELU, label="input")
                         launches += 1
                     else:
                         conv(stream, buf["kw"], st["bwd_key_aux"], out=buf["pa"], aux=buf["lr64"],
-                             bias=st["bwd_in_bias"], act=PNP_ACT_NONE)
+                             bias=st["bwd_in_bias"], act=PNP_ACT_NONE, label="input")
                         conv(stream, feats[b, i + 1].unsqueeze(0), st["bwd_nb"], out=x0, idt=buf["pa"],
-                             act=PNP_ACT_LRELU)
+                             act=PNP_ACT_LRELU, label="input")
                         launches += 2
                 else:                                     # zeros for key_warp / neighbour (:69-70)
                     conv(stream, buf["zero"], st["bwd_merged_aux"], out=x0, aux=buf["lr64"],
-                         bias=st["bwd_in_bias"], act=PNP_ACT_LRELU)
+                         bias=st["bwd_in_bias"], act=PNP_ACT_LRELU, label="input")
                     launches += 1
                 stack("bwd", 0, b, i, x0, feats[b, i].unsqueeze(0), mixed)
             if return_features:
@@ -294,28 +318,28 @@ class BaeEngine:
                 cur = feats[b, i].unsqueeze(0)            # backward feature of frame i (outputs[i])
                 if i > 0:
                     kidx = fwd_key[i]
-                    ops.mv_warp(feats[b, kidx].unsqueeze(0), mvs[b, i, 0:2], buf["kw"])
+                    warp(feats[b, kidx].unsqueeze(0), mvs[b, i, 0:2], buf["kw"])
                     conv(stream, cur, st["fwd_bf_aux"], out=buf["pa"], aux=buf["lr64"],
-                         bias=st["fwd_in_bias"], act=PNP_ACT_NONE)
+                         bias=st["fwd_in_bias"], act=PNP_ACT_NONE, label="input")
                     launches += 2
                     if kidx == i - 1:
-                        conv(stream, buf["kw"], st["fwd_merged"], out=x0, idt=buf["pa"], act=PNP_ACT_LRELU)
+                        conv(stream, buf["kw"], st["fwd_merged"], out=x0, idt=buf["pa"], act=PNP_ACT_LRELU, label="input")
                         launches += 1
                     else:
                         conv(stream, buf["kw"], st["fwd_key"], out=buf["pb"], idt=buf["pa"],
-                             act=PNP_ACT_NONE)
+                             act=PNP_ACT_NONE, label="input")
                         conv(stream, feats[b, i - 1].unsqueeze(0), st["fwd_nb"], out=x0, idt=buf["pb"],
-                             act=PNP_ACT_LRELU)
+                             act=PNP_ACT_LRELU, label="input")
                         launches += 2
                 else:
                     conv(stream, cur, st["fwd_bf_aux"], out=x0, aux=buf["lr64"], bias=st["fwd_in_bias"],
-                         act=PNP_ACT_LRELU)
+                         act=PNP_ACT_LRELU, label="input")
                     launches += 1
                 stack("fwd", nb, b, i, x0, cur, mixed)
                 # out = conv_last(lrelu(conv_hr(x))) + lq   (:144-146)
-                conv(stream, cur, st["hr_w"], out=buf["hr"], bias=st["hr_b"], act=PNP_ACT_LRELU)
+                conv(stream, cur, st["hr_w"], out=buf["hr"], bias=st["hr_b"], act=PNP_ACT_LRELU, label="hr")
                 conv(stream, buf["hr"], st["last_w"], bias=st["last_b"], lq=lrs[b:b + 1, i],
-                     outf=out[b:b + 1, i])
+                     outf=out[b:b + 1, i], label="last")
                 launches += 2
         self.launch_count = launches
         if return_features:

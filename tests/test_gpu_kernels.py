@@ -1,0 +1,234 @@
+"""Kernel-level parity on a real B200, every call going through the C ABI (libpnpvcve.so)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import bae_oracle as O
+from pnpvcve_b200 import _lib, ops, weights
+
+from helpers import warp_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    _lib.require_device()            # raises if libpnpvcve.so is missing or the device is not sm_100
+    return torch.device("cuda:0")
+
+
+def bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def nchw(x):
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def assert_bf16_close(got, ref, what):
+    """within one bf16 rounding step of the fp32 reference result"""
+    tol = ref.abs() * 2.0 ** -7 + 2e-3
+    bad = (got - ref).abs() > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.numel()} off, max {float((got - ref).abs().max())}"
+
+
+# ------------------------------------------------------------------ K1 warp
+@pytest.mark.parametrize("h,w,qpel", [(720, 1280, 64), (376, 1244, 64), (180, 320, 32), (64, 64, 200)])
+def test_mv_warp_taps_bit_exact_and_values(dev, h, w, qpel):
+    g = torch.Generator().manual_seed(h * 7 + w)
+    x = bf(torch.randn((64, h, w), generator=g))
+    fb = torch.randint(-qpel, qpel + 1, (2, (h + 7) // 8, (w + 7) // 8), generator=g).float() / 4.0
+    flow = fb.repeat_interleave(8, 1).repeat_interleave(8, 2)[:, :h, :w].contiguous()
+    src = nhwc(x[None]).to(dev)
+    dst = ops.new_feature(1, h, w, dev)
+    x0, y0 = ops.mv_warp(src, flow.to(dev), dst, debug=True)
+    torch.cuda.synchronize()
+    ex0, ey0 = O.warp_taps(flow, h, w)                 # CPU oracle: integer taps must be identical
+    assert torch.equal(x0.cpu(), ex0), "x tap indices differ from the oracle"
+    assert torch.equal(y0.cpu(), ey0), "y tap indices differ from the oracle"
+    ref = O.warp_bilinear(x, flow)                     # fp32 CPU oracle on the same bf16-valued input
+    assert_bf16_close(nchw(dst)[0].cpu(), ref, "warp values")
+
+
+def test_mv_warp_matches_reference_golden(dev):
+    x, flow, gold = warp_case()                        # reference flow_warp output (fp32 input)
+    xb = torch.zeros((1, 64, 720, 1280))
+    xb[:, :2] = bf(x)
+    dst = ops.new_feature(1, 720, 1280, dev)
+    ops.mv_warp(nhwc(xb).to(dev), flow[0].to(dev), dst)
+    got = nchw(dst)[0, :2, ::8, ::8].cpu()
+    lat = torch.from_numpy(gold["lattice"])[0]
+    # input rounded to bf16 (2^-9 relative) and output rounded to bf16: tolerance 2^-6 relative
+    assert ((got - lat).abs() <= lat.abs() * 2.0 ** -6 + 4e-2).all()
+    assert (got - lat).abs().mean().item() < 6e-3
+
+
+def test_mv_warp_zero_and_integer_flow(dev):
+    g = torch.Generator().manual_seed(3)
+    x = bf(torch.randn((1, 64, 72, 136), generator=g))
+    src = nhwc(x).to(dev)
+    dst = ops.new_feature(1, 72, 136, dev)
+    ops.mv_warp(src, torch.zeros((2, 72, 136), device=dev), dst)
+    assert_bf16_close(nchw(dst).cpu(), x, "zero flow")
+    flow = torch.zeros((2, 72, 136))
+    flow[0] += 5.0
+    flow[1] -= 3.0
+    ops.mv_warp(src, flow.to(dev), dst)
+    exp = torch.zeros_like(x)
+    exp[:, :, 3:, : 136 - 5] = x[:, :, : 72 - 3, 5:]
+    assert_bf16_close(nchw(dst).cpu(), exp, "integer shift")
+
+
+def test_mv_warp_rejects_bad_arguments(dev):
+    a = ops.new_feature(1, 64, 64, dev)
+    with pytest.raises(ValueError):
+        ops.mv_warp(a, torch.zeros((2, 60, 64), device=dev), ops.new_feature(1, 64, 64, dev))
+    with pytest.raises(_lib.PnpError):
+        ops.mv_warp(a, torch.zeros((2, 64, 64), device=dev), a)      # aliasing
+
+
+# ------------------------------------------------------------------ conv
+SHAPES = [(1, 64, 64), (1, 68, 132), (2, 72, 200), (1, 180, 320), (1, 376, 1244)]
+
+
+@pytest.mark.parametrize("n,h,w", SHAPES)
+def test_conv_variants_match_fp32_conv2d(dev, n, h, w):
+    g = torch.Generator(device=dev).manual_seed(n * 100000 + h * 1000 + w)
+    x = bf(torch.randn((n, 64, h, w), generator=g, device=dev))
+    wt = bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05)
+    bias = torch.randn(64, generator=g, device=dev) * 0.1
+    scale = torch.rand(64, generator=g, device=dev) + 0.5
+    xs = nhwc(x)
+    ref0 = F.conv2d(x, wt, padding=1)
+    wp = ops.new_wpack(9, dev)
+    ops.pack_conv3x3(wt, wp)
+    out = ops.new_feature(n, h, w, dev)
+
+    ops.conv3x3(xs, wp, out=out)
+    assert_bf16_close(nchw(out), ref0, "plain")
+    ops.conv3x3(xs, wp, out=out, bias=bias, act=ops.PNP_ACT_LRELU)
+    assert_bf16_close(nchw(out), F.leaky_relu(ref0 + bias.view(1, -1, 1, 1), 0.1), "bias+lrelu")
+    idt = bf(torch.randn((n, 64, h, w), generator=g, device=dev))
+    ops.conv3x3(xs, wp, out=out, bias=bias, scale=scale, idt=nhwc(idt), act=ops.PNP_ACT_RELU)
+    assert_bf16_close(nchw(out), F.relu(ref0 * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1) + idt),
+                      "scale+bias+id+relu")
+
+    # LR frame through the im2col'd aux operand == the first 3 input channels of a 131-ch conv
+    lr = torch.rand((n, 3, h, w), generator=g, device=dev)
+    w_in = bf(torch.randn((64, 131, 3, 3), generator=g, device=dev) * 0.05)
+    wpa = ops.new_wpack(10, dev)
+    ops.pack_conv3x3(w_in, wpa, in_begin=3, in_count=64)
+    ops.pack_aux(w_in, wpa[9 * ops.CHUNK_BYTES:])
+    lr64 = ops.new_feature(n, h, w, dev, zero=True)
+    ops.lr_im2col(lr, lr64)
+    ops.conv3x3(xs, wpa, out=out, aux=lr64, bias=bias, act=ops.PNP_ACT_LRELU)
+    ref = F.leaky_relu(F.conv2d(torch.cat([bf(lr), x], 1), w_in[:, :67], bias, padding=1), 0.1)
+    assert_bf16_close(nchw(out), ref, "aux")
+
+    # merged K slices (neighbour == key_warp): weights of two input slices summed
+    wpm = ops.new_wpack(9, dev)
+    ops.pack_conv3x3(w_in, wpm, in_begin=3, in_begin2=67, in_count=64)
+    ops.conv3x3(xs, wpm, out=out)
+    assert_bf16_close(nchw(out), F.conv2d(x, bf(w_in[:, 3:67] + w_in[:, 67:131]), padding=1), "merged")
+
+    # 3x3 + three partition-modulated 1x1 convs, general (non one-hot) float partition map
+    par = torch.rand((n, 3, h, w), generator=g, device=dev) * \
+        (torch.rand((n, 3, h, w), generator=g, device=dev) > 0.5)
+    w1 = [bf(torch.randn((64, 64), generator=g, device=dev) * 0.1) for _ in range(3)]
+    wpp = ops.new_wpack(12, dev)
+    ops.pack_conv3x3(wt, wpp, center_chunks=4)
+    for j in range(3):
+        ops.pack_rows(w1[j], wpp, 64 * (j + 1))
+    ops.conv3x3(xs, wpp, out=out, scale=scale, bias=bias, par=par, act=ops.PNP_ACT_RELU)
+    ref = ref0 * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    for j in range(3):
+        ref = ref + F.conv2d(x, w1[j].view(64, 64, 1, 1)) * par[:, j:j + 1]
+    assert_bf16_close(nchw(out), F.relu(ref), "par")
+
+    # reconstruction tail: 64 -> 3, + lq, fp32 NCHW output
+    wl = bf(torch.randn((3, 64, 3, 3), generator=g, device=dev) * 0.05)
+    bl = torch.randn(3, generator=g, device=dev) * 0.1
+    wpl = ops.new_wpack(9, dev)
+    ops.pack_conv3x3(wl, wpl)
+    outf = torch.empty((n, 3, h, w), device=dev)
+    ops.conv3x3(xs, wpl, bias=bl, lq=lr, outf=outf)
+    assert (outf - (F.conv2d(x, wl, bl, padding=1) + lr)).abs().max().item() < 1e-4
+
+
+def test_conv_expert_mixing_matches_reference_formula(dev):
+    """pack_conv3x3 with coef == torch.mm(softmax_attention, weight) of Dynamic_conv2d_se."""
+    g = torch.Generator(device=dev).manual_seed(11)
+    w = torch.randn((6, 64, 64, 3, 3), generator=g, device=dev) * 0.05
+    coef = torch.softmax(torch.randn(6, generator=g, device=dev), 0)
+    x = bf(torch.randn((1, 64, 64, 96), generator=g, device=dev))
+    wp = ops.new_wpack(9, dev)
+    ops.pack_conv3x3(w, wp, coef=coef)
+    out = ops.new_feature(1, 64, 96, dev)
+    ops.conv3x3(nhwc(x), wp, out=out)
+    mixed = torch.mm(coef.view(1, 6), w.view(6, -1)).view(64, 64, 3, 3)
+    assert_bf16_close(nchw(out), F.conv2d(x, bf(mixed), padding=1), "expert mix")
+
+
+def test_conv_full_720p_linearity_and_identity(dev):
+    """Size-independent properties at the full REDS4 shape: identity kernel and linearity."""
+    g = torch.Generator(device=dev).manual_seed(5)
+    h, w = 720, 1280
+    x = nhwc(bf(torch.randn((1, 64, h, w), generator=g, device=dev)))
+    y = nhwc(bf(torch.randn((1, 64, h, w), generator=g, device=dev)))
+    eye = torch.zeros((64, 64, 3, 3), device=dev)
+    eye[:, :, 1, 1] = torch.eye(64, device=dev)
+    wp = ops.new_wpack(9, dev)
+    ops.pack_conv3x3(eye, wp)
+    out = ops.new_feature(1, h, w, dev)
+    ops.conv3x3(x, wp, out=out)
+    assert torch.equal(out, x)
+    # conv(x) + y through the id operand with the identity kernel == x + y (bf16 rounded once)
+    ops.conv3x3(x, wp, out=out, idt=y)
+    assert torch.equal(out, (x.float() + y.float()).to(torch.bfloat16))
+    # shift kernel: tap (0,2) moves the image one pixel left with zero fill at the right edge
+    sh = torch.zeros((64, 64, 3, 3), device=dev)
+    sh[:, :, 0, 2] = torch.eye(64, device=dev)
+    ops.pack_conv3x3(sh, wp)
+    ops.conv3x3(x, wp, out=out)
+    exp = torch.zeros_like(x)
+    exp[:, 1:, : w - 1] = x[:, : h - 1, 1:]
+    assert torch.equal(out, exp)
+
+
+def test_conv_rejects_bad_descriptors(dev):
+    x = ops.new_feature(1, 64, 64, dev)
+    wp = ops.new_wpack(12, dev)
+    with pytest.raises(_lib.PnpError):
+        ops.conv3x3(x, wp, out=x)                       # out aliases src
+    with pytest.raises(ValueError):
+        ops.conv3x3(x, wp, out=ops.new_feature(1, 64, 68, dev))
+    with pytest.raises(ValueError):
+        ops.conv3x3(x.float(), wp, out=ops.new_feature(1, 64, 64, dev))
+
+
+# ------------------------------------------------------------------ CAA heads
+def test_caa_heads_match_oracle(dev):
+    sd = weights.random_state_dict(3)
+    crf = torch.tensor([15, 25, 35, 25, 51, 0], dtype=torch.float32) / 255.0
+    qp = torch.tensor([73, 66, 80, 20, 30, 40], dtype=torch.float32) / 255.0
+    params = dict(b0w=sd["BasePredictor.BaseNet.0.weight"], b0b=sd["BasePredictor.BaseNet.0.bias"],
+                  b2w=sd["BasePredictor.BaseNet.2.weight"], b2b=sd["BasePredictor.BaseNet.2.bias"],
+                  s0w=sd["BiasePredictor.fc.0.weight"], s2w=sd["BiasePredictor.fc.2.weight"])
+    params = {k: v.to(dev).contiguous() for k, v in params.items()}
+    experts, gamma = ops.caa_heads(crf.to(dev), qp.to(dev), params, 6)
+    e_ref = O.base_predictor(sd, crf.view(1, -1, 1, 1, 1))[0]
+    g_ref = O.se_module(sd, qp.view(1, -1, 1, 1, 1))[0]
+    assert (experts.cpu() - e_ref).abs().max().item() < 1e-6
+    assert (gamma.cpu() - g_ref).abs().max().item() < 1e-6
+    b2 = torch.randn((4, 6, 64), device=dev)
+    tab = ops.mix_bias(b2, experts, gamma)
+    ref = torch.einsum("fe,bec->fbc", experts, b2) * gamma[:, None, :]
+    assert (tab - ref).abs().max().item() < 1e-5

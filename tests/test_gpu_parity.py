@@ -1,0 +1,149 @@
+"""End-to-end parity of the registry-built generator on a B200 against the reference's golden
+vectors and the CPU oracle.  north_star tolerance: max-abs 2e-3 on [0,1] frames, PSNR delta
+<= 0.02 dB, key schedule / tap indices bit exact (taps: tests/test_gpu_kernels.py)."""
+import pytest
+import torch
+
+from oracle import bae_oracle as O
+import pnpvcve_b200 as P
+from pnpvcve_b200 import synthetic, weights
+
+from helpers import build_case, check_against_golden, golden_cases
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-3
+GENERATOR_CFG = dict(
+    type="IconVSR_restore_wo_refill_mv_ipb_fast_domain_dynamic_with_par",
+    mid_channels=64, num_blocks=8, padding=3, with_cat=True, use_base_qp=True, num_experts=6,
+    expert_softmax=True, init_weight=True, with_bias=True, with_se=True, with_par=True,
+    one_layer=True, blocktype="drt", channel_first=True, sparse_val=False, align_key=True, vsr=False)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def build(sd, dev, **over):
+    cfg = dict(GENERATOR_CFG)
+    cfg.update(over)
+    net = P.build_backbone(cfg)
+    net.load_state_dict(sd, strict=True)
+    return net.to(dev).eval()
+
+
+def run(net, clip, dev):
+    args = [a.to(dev) for a in synthetic.generator_args(clip)]
+    with torch.no_grad():
+        out = net(*args)
+    torch.cuda.synchronize()
+    return out
+
+
+CASES = [c for c in golden_cases() if c != "warp_720p"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_generator_matches_reference_golden(dev, name):
+    sd, clip, gold = build_case(name)
+    net = build(sd, dev)
+    out = run(net, clip, dev)
+    assert out.dtype == torch.float32 and out.is_cuda
+    err = check_against_golden(out, gold, tol=TOL)
+    assert net.gpu_launches > 0
+    print(f"{name}: max-abs vs reference golden {err:.2e}")
+
+
+def psnr_delta(out, ref, seed=0):
+    """PSNR (tensor2img uint8, metrics.py psnr) of both outputs against a synthetic ground truth."""
+    g = torch.Generator().manual_seed(seed)
+    worst = 0.0
+    for b in range(out.shape[0]):
+        for i in range(out.shape[1]):
+            gt = (ref[b, i] + 0.02 * torch.randn(ref[b, i].shape, generator=g)).clamp(0, 1)
+            gt8 = O.tensor2img_u8(gt)
+            worst = max(worst, abs(O.psnr_u8(O.tensor2img_u8(out[b, i]), gt8)
+                                   - O.psnr_u8(O.tensor2img_u8(ref[b, i]), gt8)))
+    return worst
+
+
+def test_generator_matches_oracle_features_and_psnr(dev):
+    """C1 shape, both propagation feature stacks + output + PSNR delta against the CPU oracle."""
+    sd = weights.random_state_dict(7)
+    clip = synthetic.make_config_clip("C1", clip_idx=3, crf=35)
+    ref, bwd_ref, fwd_ref = O.generator_forward(sd, *synthetic.generator_args(clip), return_features=True)
+    net = build(sd, dev)
+    args = [a.to(dev) for a in synthetic.generator_args(clip)]
+    out, bwd, fwd = net.forward_with_features(*args)
+    out = out.cpu()
+    assert (out - ref).abs().max().item() <= TOL
+    t = ref.shape[1]
+    for i in range(t):
+        for got, exp in ((bwd[0, i], bwd_ref[0][i][0]), (fwd[0, i], fwd_ref[0][i][0])):
+            got = got.float().permute(2, 0, 1).cpu()
+            scale = exp.abs().max().item()
+            assert (got - exp).abs().max().item() <= 0.03 * scale + 1e-2
+    assert psnr_delta(out, ref) <= 0.02
+
+
+def test_generator_kitti_shape_edges_and_ipb(dev):
+    """C5: 376x1244 (non multiple of the 128-pixel tile), I/P pair, IPB conditioning."""
+    sd = weights.random_state_dict(9)
+    clip = synthetic.make_config_clip("C5", clip_idx=1, crf=25)
+    ref = O.generator_forward(sd, *synthetic.generator_args(clip))
+    out = run(build(sd, dev), clip, dev).cpu()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() <= TOL
+    assert psnr_delta(out, ref) <= 0.02
+
+
+def test_generator_720p_short_clip(dev):
+    """C2/C3 shape, T=3 (I B B -> keys 0 and forced 2), CPU-oracle spot check."""
+    sd = weights.random_state_dict(11)
+    clip = synthetic.make_config_clip("C3", clip_idx=0, t=3, crf=15)
+    ref = O.generator_forward(sd, *synthetic.generator_args(clip))
+    out = run(build(sd, dev), clip, dev).cpu()
+    assert (out - ref).abs().max().item() <= TOL
+    assert psnr_delta(out, ref) <= 0.02
+
+
+def test_generator_batch_equals_single_clips(dev):
+    """n=2 with different slice patterns / CRFs == the two clips run alone (bit identical)."""
+    sd = weights.random_state_dict(13)
+    a = synthetic.make_clip(64, 96, 5, seed=1, crf=15, pattern="IBBP", ipb=True)
+    b = synthetic.make_clip(64, 96, 5, seed=2, crf=35, pattern="allB", ipb=True)
+    net = build(sd, dev)
+    both = run(net, synthetic.cat_clips([a, b]), dev)
+    assert torch.equal(both[0:1], run(net, a, dev))
+    assert torch.equal(both[1:2], run(net, b, dev))
+
+
+def test_generator_reflect_padding_and_size_errors(dev):
+    sd = weights.random_state_dict(1, num_blocks=2)
+    net = build(sd, dev, num_blocks=2)
+    clip = synthetic.make_clip(64, 64, 2, seed=1)
+    small = {k: (v[..., :60, :60].contiguous() if v.dim() == 5 and v.shape[-1] == 64 else v)
+             for k, v in clip.items()}
+    with pytest.raises(AssertionError):
+        run(net, small, dev)
+    clip = synthetic.make_clip(66, 70, 2, seed=1)       # reference raises for non-x4 sizes too
+    with pytest.raises(ValueError):
+        run(net, clip, dev)
+    # C5 contract: lq NOT pre-padded (reflect-padded inside), mvs / partitions zero-padded by caller
+    clip = synthetic.make_clip(68, 72, 2, seed=4, pattern="IP")
+    lq = clip["lq"][..., :66, :70].contiguous()
+    ref = O.generator_forward(sd, lq, *synthetic.generator_args(clip)[1:], num_blocks=2)
+    clip2 = dict(clip, lq=lq)
+    out = run(net, clip2, dev).cpu()
+    assert out.shape[-2:] == (68, 72)
+    assert (out - ref).abs().max().item() <= TOL
+
+
+def test_unsupported_kwargs_raise():
+    with pytest.raises(NotImplementedError):
+        P.build_backbone(dict(GENERATOR_CFG, vsr=True))
+    with pytest.raises(NotImplementedError):
+        P.build_backbone(dict(GENERATOR_CFG, blocktype="sft"))

@@ -1,0 +1,193 @@
+"""Host-side logic and the C-ABI surface -- runs without a GPU."""
+import ctypes
+import os
+import re
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import pnpvcve_b200 as P
+from oracle import bae_oracle as O
+from oracle import refshim
+from pnpvcve_b200 import _lib, driver, engine, synthetic, weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GEN = "IconVSR_restore_wo_refill_mv_ipb_fast_domain_dynamic_with_par"
+CFG = dict(type=GEN, mid_channels=64, num_blocks=8, padding=3, with_cat=True, use_base_qp=True,
+           num_experts=6, expert_softmax=True, init_weight=True, with_bias=True, with_se=True,
+           with_par=True, one_layer=True, blocktype="drt", channel_first=True, sparse_val=False,
+           align_key=True, vsr=False)
+
+
+# ------------------------------------------------------------------ C ABI
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "pnp_vcve.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pnp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/pnp_vcve.h but not exported"
+    assert sorted(_lib.EXPORTS) == syms
+    assert _lib.load().pnp_abi_version() == 1
+
+
+def test_abi_argument_errors_without_gpu():
+    lib = _lib.load()
+    assert lib.pnp_conv3x3(None, None) == -1                      # PNP_ERR_ARG
+    assert b"null" in lib.pnp_last_error()
+    assert lib.pnp_mv_warp(None, None, None, 0, None, 4, 4, None, None, None) == -1
+    assert lib.pnp_set_base_offset_mode(7) == -1
+    assert lib.pnp_set_base_offset_mode(0) == 0
+    if not torch.cuda.is_available():
+        assert lib.pnp_device_check() != 0                         # no device: loud failure, no fallback
+        with pytest.raises(_lib.PnpError):
+            _lib.require_device()
+
+
+def test_conv_desc_matches_header_layout():
+    d = _lib.ConvDesc()
+    assert ctypes.sizeof(d) == 7 * 8 + 4 * 8 + 4 * 8 + 4 * 8 + 9 * 4 + 4   # 8-byte aligned tail pad
+    assert _lib.ConvDesc.N.offset == 152 and _lib.ConvDesc.mode.offset == 184
+
+
+# ------------------------------------------------------------------ registry / boundary
+def test_registry_builds_generator_and_state_dict_layout():
+    assert GEN in P.BACKBONES
+    net = P.build_backbone(CFG)
+    sd = net.state_dict()
+    shapes = weights.state_dict_shapes()
+    assert set(sd) == set(shapes)
+    assert all(tuple(sd[k].shape) == shapes[k] for k in shapes)
+    assert sum(p.numel() for p in net.parameters()) == 4559885
+    assert not list(net.buffers())
+    net.load_state_dict(weights.random_state_dict(0), strict=True)
+    with pytest.raises(KeyError):
+        P.build_backbone(dict(CFG, type="NoSuchBackbone"))
+    for bad in (dict(vsr=True), dict(blocktype="sft"), dict(with_se=False), dict(deform="fvc"),
+                dict(sparse_val=True), dict(mid_channels=32)):
+        with pytest.raises(NotImplementedError):
+            P.build_backbone(dict(CFG, **bad))
+
+
+def test_init_weights_contract(tmp_path):
+    net = P.build_backbone(CFG)
+    net.init_weights(None)
+    with pytest.raises(TypeError):
+        net.init_weights(123)
+    sd = weights.random_state_dict(5)
+    path = str(tmp_path / "ckpt.pth")
+    torch.save({"state_dict": {"generator." + k: v for k, v in sd.items()}}, path)
+    net.init_weights(path, strict=True)
+    assert torch.equal(net.state_dict()["conv_last.weight"], sd["conv_last.weight"])
+
+
+def test_forward_refuses_cpu_and_training():
+    net = P.build_backbone(CFG)
+    clip = synthetic.make_clip(64, 64, 2, seed=0)
+    with pytest.raises(RuntimeError):
+        net(*synthetic.generator_args(clip))                       # training mode + grad
+    net.eval()
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        net(*synthetic.generator_args(clip))                       # CPU tensors: no fallback
+
+
+def test_config_loader_base_inheritance(tmp_path):
+    (tmp_path / "base.py").write_text(
+        "model = dict(type='BasicVSR', generator=dict(type='%s', num_blocks=8, vsr=False))\n"
+        "data = dict(test=dict(type='A', lq_folder='x'))\n" % GEN)
+    (tmp_path / "child.py").write_text(
+        "_base_ = './base.py'\nmodel = dict(generator=dict(num_blocks=4))\n"
+        "data = dict(test=dict(_delete_=True, type='B'))\n")
+    cfg = P.Config.fromfile(str(tmp_path / "child.py"))
+    assert cfg.model.generator.type == GEN and cfg.model.generator.num_blocks == 4
+    assert cfg.model.generator.vsr is False and cfg.model.type == "BasicVSR"
+    assert dict(cfg.data.test) == {"type": "B"}
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("cfgname", ["HR_davis_LR_128x128.py", "HR_davis_LR_128x128_IPB.py",
+                                     "HR_davis_LR_128x128_IPB_LR_test.py"])
+def test_reference_configs_build_unchanged(cfgname):
+    cfg = P.Config.fromfile(os.path.join(refshim.REFERENCE_ROOT, "configs", cfgname))
+    net = P.build_backbone(cfg.model.generator)
+    assert type(net).__name__ == GEN and net.num_blocks == 8 and net.num_experts == 6
+
+
+# ------------------------------------------------------------------ schedule
+def test_key_schedule_equals_oracle_on_random_patterns():
+    g = torch.Generator().manual_seed(0)
+    for t in (1, 2, 3, 7, 16, 100):
+        for _ in range(5):
+            s = torch.tensor([[73, 80, 66][i] for i in torch.randint(0, 3, (t,), generator=g)])
+            sl = s.float().view(1, t, 1, 1, 1)
+            rows = engine.keyframe_rows(sl.view(1, t).clone())
+            assert rows == O.keyframe_mask(sl).tolist()
+            if t > 1:
+                assert engine.key_schedule(rows[0]) == O.key_schedule(rows[0])
+
+
+def test_synthetic_clip_semantics():
+    c = synthetic.make_config_clip("C1")
+    assert c["lq"].shape == (1, 7, 3, 128, 128) and c["mvs"].shape == (1, 7, 4, 128, 128)
+    assert c["slices"].flatten().tolist() == [73, 66, 66, 80, 66, 66, 80]
+    assert c["mvs"][0, 0].abs().max() == 0 and c["partitions"][0, 0].abs().max() == 0   # I frame
+    p = c["partitions"][0, 1]
+    assert torch.unique(p).tolist() == [0.0, torch.tensor(1.0 / 255.0).item()]
+    assert torch.allclose(p.sum(0), torch.full((128, 128), 1.0 / 255.0))
+    assert torch.equal(c["mvs"][0, 1] * 4, (c["mvs"][0, 1] * 4).round())                # quarter pel
+    assert torch.equal(c["mvs"][0, 1, :, :8, :8], c["mvs"][0, 1, :, :1, :1].expand(4, 8, 8))
+    c3 = synthetic.make_config_clip("C3", t=4)
+    assert torch.equal(c3["QPs"], c3["slices"] / 255.0)
+    again = synthetic.make_config_clip("C1")
+    assert all(torch.equal(c[k], again[k]) for k in c)
+
+
+# ------------------------------------------------------------------ multi-process (gloo, world 2)
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, num_clips, t, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = driver.shard_clips(num_clips, rank, world)
+    local = torch.stack([torch.full((t, driver.N_METRICS), float(c)) for c in mine], 0) if mine \
+        else torch.empty((0, t, driver.N_METRICS))
+    full = driver.gather_metrics(local, num_clips, rank, world)
+    q.put((rank, full))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("num_clips", [5, 4, 1])
+def test_clip_sharding_and_metric_gather_world2(num_clips):
+    world, t = 2, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, num_clips, t, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    exp = torch.arange(num_clips, dtype=torch.float32).view(-1, 1, 1).expand(num_clips, t, driver.N_METRICS)
+    for _, full in got:
+        assert torch.equal(full, exp)
+    assert sorted(driver.shard_clips(5, 0, 2) + driver.shard_clips(5, 1, 2)) == list(range(5))

@@ -75,7 +75,7 @@ def main():
             print(f"mode {mode} raised: {e}", flush=True)
             results[mode] = False
     print("base-offset mode results:", results, flush=True)
-    good = 0 if results.get(0) else (1 if results.get(1) else None)
+    good = 0 if results.get(0) else (1 if results.get(1) else None)   # 0 = library default
     if good is None:
         print("NO base-offset mode reproduces shifted taps -- stop here", flush=True)
         return 1

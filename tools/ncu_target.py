@@ -1,0 +1,36 @@
+"""Tiny launch sequence for `ncu` captures at the REDS4 shape (720p): per round
+   4x conv (block launch A: 3x3 + partition 1x1s), 4x conv (block launch B: + identity), 4x mv_warp.
+Not a benchmark: numbers printed under a profiler are never bench values."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pnpvcve_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+h, w = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (720, 1280)
+g = torch.Generator(device=dev).manual_seed(0)
+x = torch.randn((1, h, w, 64), generator=g, device=dev).to(torch.bfloat16)
+idt = torch.randn((1, h, w, 64), generator=g, device=dev).to(torch.bfloat16)
+t = ops.new_feature(1, h, w, dev)
+out = ops.new_feature(1, h, w, dev)
+wa = ops.new_wpack(12, dev)
+ops.pack_conv3x3(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05, wa, center_chunks=4)
+for j in range(3):
+    ops.pack_rows(torch.randn((64, 64), generator=g, device=dev) * 0.1, wa, 64 * (j + 1))
+wb = ops.new_wpack(9, dev)
+ops.pack_conv3x3(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05, wb)
+par = torch.rand((1, 3, h, w), generator=g, device=dev)
+scale = torch.rand(64, generator=g, device=dev) + 0.5
+bias = torch.randn(64, generator=g, device=dev) * 0.1
+flow = (torch.randint(-64, 65, (2, (h + 7) // 8, (w + 7) // 8), generator=g, device=dev).float() / 4
+        ).repeat_interleave(8, 1).repeat_interleave(8, 2)[:, :h, :w].contiguous()
+torch.cuda.synchronize()
+for _ in range(4):
+    ops.conv3x3(x, wa, out=t, scale=scale, bias=bias, par=par, act=ops.PNP_ACT_RELU)
+    ops.conv3x3(t, wb, out=out, idt=x, bias=bias)
+    ops.mv_warp(x, flow, out)
+torch.cuda.synchronize()
+print("done")
