@@ -17,7 +17,7 @@
 // the A descriptor start is moved by (dx+1) pixels = (dx+1)*128 bytes and dy selects the ring slot.
 // TMA zero fill outside the image implements the conv padding.  Weights stay resident in smem.
 // Accumulators live in TMEM (two 256-column buffers) so the epilogue of tile i overlaps the MMAs of
-// tile i+1.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
+// tile i+1.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue.
 #include "pnp_conv.cuh"
 #include "pnp_ptx.cuh"
 
@@ -114,7 +114,7 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
         mbar_init(smem_u32(&misc->aux_full[i]), 1);
         mbar_init(smem_u32(&misc->aux_empty[i]), 1);
         mbar_init(smem_u32(&misc->acc_full[i]), 1);
-        mbar_init(smem_u32(&misc->acc_empty[i]), 128);
+        mbar_init(smem_u32(&misc->acc_empty[i]), kConvThreads - 64);
       }
       for (int i = 0; i < kMaxIoSlots; ++i) {
         mbar_init(smem_u32(&misc->id_full[i]), 1);
@@ -122,7 +122,7 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
       }
       mbar_fence_init();
       tma_prefetch_desc(&p.tm_src);
-      tma_prefetch_desc(&p.tm_out);
+      if (p.mode != kModeLast) tma_prefetch_desc(&p.tm_out);
     }
     __syncwarp();
     tmem_alloc(smem_u32(&misc->tmem_base), kTmemCols);
@@ -138,8 +138,8 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
   const uint32_t io_smem = sbase + L.io;
 
   if (warp == 0) {
-    // ============================================================ TMA producer (one lane)
-    if (lane == 0) {
+    // ============================================================ TMA producer (one elected lane)
+    if (elect_one()) {
       const uint32_t wbar = smem_u32(&misc->w_full);
       mbar_arrive_expect_tx(wbar, p.n_wchunks * kWChunkBytes);
       for (int c = 0; c < p.n_wchunks; ++c)
@@ -173,87 +173,87 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer (one lane)
-    if (lane == 0) {
-      const uint32_t idesc_center = umma_idesc_bf16(128, p.center_n);
-      const uint32_t idesc_tap = umma_idesc_bf16(128, p.tap_n);
-      const int center_chunks = (p.center_n == 256) ? 4 : 1;
-      const bool doc_bo = (p.base_off_mode == 1);
-      mbar_wait(smem_u32(&misc->w_full), 0, 4);
-      uint32_t ld_base = 0, ld_next = 0, confirmed = 0;
-      for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
-        const TileCoord c = decode_tile(p, t, t_begin, t_end);
-        if (c.first) {
-          ld_base = ld_next;
-          ld_next += 3;
-        } else {
-          ld_base += 1;
-          ld_next += 1;
-        }
-        while (confirmed < ld_base + 3) {
-          mbar_wait(smem_u32(&misc->a_full[confirmed % s_a]), (confirmed / s_a) & 1, 5);
-          ++confirmed;
-        }
-        const uint32_t b = it & 1;
-        mbar_wait(smem_u32(&misc->acc_empty[b]), ((it >> 1) & 1) ^ 1, 6);
-        if (p.aux_k16 > 0) mbar_wait(smem_u32(&misc->aux_full[it & 1]), (it >> 1) & 1, 7);
-        tc_fence_after();
+    // ============================================================ MMA issuer
+    // The whole warp walks the tile list and waits on the barriers (warp-uniform control flow keeps
+    // addresses in uniform registers); one elected lane issues the 36..48 tcgen05.mma of a tile as
+    // straight-line code: descriptor = per-row base word + compile-time offset.
+    const uint32_t idesc_center = umma_idesc_bf16(128, p.center_n);
+    const uint32_t idesc_tap = umma_idesc_bf16(128, p.tap_n);
+    const uint32_t center_chunks = (p.center_n == 256) ? 4 : 1;
+    const uint32_t bo_mul = (p.base_off_mode == 1) ? (1u << 17) : 0u;   // diagnostic only
+    const uint32_t w_lo = umma_desc_lo(w_smem);
+    mbar_wait(smem_u32(&misc->w_full), 0, 4);
+    uint32_t ld_base = 0, ld_next = 0, confirmed = 0;
+    for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
+      const TileCoord c = decode_tile(p, t, t_begin, t_end);
+      if (c.first) {
+        ld_base = ld_next;
+        ld_next += 3;
+      } else {
+        ld_base += 1;
+        ld_next += 1;
+      }
+      while (confirmed < ld_base + 3) {
+        mbar_wait(smem_u32(&misc->a_full[confirmed % s_a]), (confirmed / s_a) & 1, 5);
+        ++confirmed;
+      }
+      const uint32_t b = it & 1;
+      mbar_wait(smem_u32(&misc->acc_empty[b]), ((it >> 1) & 1) ^ 1, 6);
+      if (p.aux_k16 > 0) mbar_wait(smem_u32(&misc->aux_full[it & 1]), (it >> 1) & 1, 7);
+      tc_fence_after();
+      const uint32_t s0 = ld_base % s_a, s1 = (ld_base + 1) % s_a, s2 = (ld_base + 2) % s_a;
+      if (elect_one()) {
         const uint32_t d = tmem_base + b * kAccStride;
-        uint32_t accum = 0;
-#pragma unroll 1
+        const uint32_t row_lo[3] = {umma_desc_lo(a_smem + s0 * kASlotBytes),
+                                    umma_desc_lo(a_smem + s1 * kASlotBytes),
+                                    umma_desc_lo(a_smem + s2 * kASlotBytes)};
+        const uint32_t tap_lo = w_lo + center_chunks * (kWChunkBytes >> 4);
+#pragma unroll
         for (int j = 0; j < 9; ++j) {
           const int tap = (j == 0) ? 4 : (j <= 4 ? j - 1 : j);   // centre first, then row-major
           const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-          const uint32_t slot = (ld_base + dy + 1) % s_a;
-          const uint32_t a_addr = a_smem + slot * kASlotBytes + (dx + 1) * 128;
-          const uint32_t b_addr = w_smem + (j == 0 ? 0 : (center_chunks + j - 1)) * kWChunkBytes;
+          const uint32_t a_lo = row_lo[dy + 1] + (dx + 1) * (128 >> 4);
+          const uint32_t a_hi = kDescHiSw128 + bo_mul * (uint32_t)(dx + 1);
+          const uint32_t b_lo = (j == 0) ? w_lo : tap_lo + (j - 1) * (kWChunkBytes >> 4);
           const uint32_t idesc = (j == 0) ? idesc_center : idesc_tap;
-          const uint32_t bo = doc_bo ? ((a_addr >> 7) & 7u) : 0u;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16(d, umma_desc_sw128(a_addr + k * 32, bo), umma_desc_sw128(b_addr + k * 32, 0), idesc,
-                      accum);
-            accum = 1;
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_lo(d, a_lo + 2 * k, a_hi, b_lo + 2 * k, kDescHiSw128, idesc, (j | k) != 0);
         }
         if (p.aux_k16 > 0) {
-          const uint32_t a_addr = aux_smem + (it & 1) * kTileBytes;
-          const uint32_t b_addr = w_smem + (center_chunks + 8) * kWChunkBytes;
+          const uint32_t a_lo = umma_desc_lo(aux_smem + (it & 1) * kTileBytes);
+          const uint32_t b_lo = tap_lo + 8 * (kWChunkBytes >> 4);
           for (int k = 0; k < p.aux_k16; ++k)
-            umma_bf16(d, umma_desc_sw128(a_addr + k * 32, 0), umma_desc_sw128(b_addr + k * 32, 0), idesc_tap,
-                      1);
+            umma_bf16_lo(d, a_lo + 2 * k, kDescHiSw128, b_lo + 2 * k, kDescHiSw128, idesc_tap, 1);
         }
-        umma_commit(smem_u32(&misc->a_empty[ld_base % s_a]));
+        umma_commit(smem_u32(&misc->a_empty[s0]));
         if (c.last) {
-          umma_commit(smem_u32(&misc->a_empty[(ld_base + 1) % s_a]));
-          umma_commit(smem_u32(&misc->a_empty[(ld_base + 2) % s_a]));
+          umma_commit(smem_u32(&misc->a_empty[s1]));
+          umma_commit(smem_u32(&misc->a_empty[s2]));
         }
         if (p.aux_k16 > 0) umma_commit(smem_u32(&misc->aux_empty[it & 1]));
         umma_commit(smem_u32(&misc->acc_full[b]));
       }
+      __syncwarp();
     }
   } else {
-    // ============================================================ epilogue (4 warps, 128 threads)
-    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    // ============================================================ epilogue (8 warps, 256 threads)
+    // A warp may only read the TMEM lane quarter (warp % 4); the two warps of a quarter split the
+    // 64 output channels in halves.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;       // 0: channels 0..31, 1: channels 32..63
     const int row = q * 32 + lane;          // pixel inside the tile == TMEM lane
-    const bool leader = (threadIdx.x == 64);
+    const bool store_warp = (warp == 2);
     const uint32_t sw = (uint32_t)(row & 7);
     for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
       const TileCoord c = decode_tile(p, t, t_begin, t_end);
       const int x = c.x0 + row;
       const bool valid = x < p.W;
       const uint32_t b = it & 1;
-      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-      if (p.par != nullptr && valid) {
-        const float* pp = p.par + (long long)c.n * p.par_sn + (long long)c.y * p.par_sy + x;
-        p0 = __ldg(pp);
-        p1 = __ldg(pp + p.par_sc);
-        p2 = __ldg(pp + 2 * p.par_sc);
-      }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * kAccStride;
       if (p.mode == kModeLast) {
         float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-        if (valid) {
+        if (valid && half == 0) {
           const float* lp = p.lq + (long long)c.n * p.lq_sn + (long long)c.y * p.lq_sy + x;
           r0 = __ldg(lp);
           r1 = __ldg(lp + p.lq_sc);
@@ -262,11 +262,13 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
         mbar_wait(smem_u32(&misc->acc_full[b]), (it >> 1) & 1, 9);
         tc_fence_after();
         float v[16];
-        tmem_ld16(taddr, v);
-        tmem_ld_wait();
+        if (half == 0) {
+          tmem_ld16(taddr, v);
+          tmem_ld_wait();
+        }
         tc_fence_before();
         mbar_arrive(smem_u32(&misc->acc_empty[b]));
-        if (valid) {
+        if (valid && half == 0) {
           float* op = p.outf + (long long)c.n * p.of_sn + (long long)c.y * p.of_sy + x;
           op[0] = v[0] + misc->bias[0] + r0;
           op[p.of_sc] = v[1] + misc->bias[1] + r1;
@@ -274,17 +276,25 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
         }
         continue;
       }
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+      if (p.par != nullptr && valid) {
+        const float* pp = p.par + (long long)c.n * p.par_sn + (long long)c.y * p.par_sy + x;
+        p0 = __ldg(pp);
+        p1 = __ldg(pp + p.par_sc);
+        p2 = __ldg(pp + 2 * p.par_sc);
+      }
       const uint32_t s_io = it % n_io;
       if (p.has_id) {
         mbar_wait(smem_u32(&misc->id_full[s_io]), (it / n_io) & 1, 8);
       } else {
-        named_bar_sync(1, 128);             // leader has drained the store that last used this slot
+        named_bar_sync(1, 256);             // the store that last used this slot has been drained
       }
       mbar_wait(smem_u32(&misc->acc_full[b]), (it >> 1) & 1, 9);
       tc_fence_after();
       uint8_t* rowp = sgen + L.io + s_io * kTileBytes + row * 128;
-#pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
+#pragma unroll
+      for (int gg = 0; gg < 2; ++gg) {
+        const int g = half * 2 + gg;        // 16-channel group
         float v[16];
         tmem_ld16(taddr + g * 16, v);
         if (p.center_n == 256) {
@@ -337,18 +347,24 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
       tc_fence_before();
       mbar_arrive(smem_u32(&misc->acc_empty[b]));
       fence_proxy_async_smem();
-      named_bar_sync(2, 128);
-      if (leader) {
-        tma_store_4d(&p.tm_out, io_smem + s_io * kTileBytes, 0, c.x0, c.y, c.n);
-        tma_store_commit();
-        // the slot tile it+1 will use was last read by the store of tile it+1-n_io
-        if (n_io == 2) tma_store_wait_read<1>();
-        else if (n_io == 3) tma_store_wait_read<2>();
-        else tma_store_wait_read<3>();
-        if (p.has_id && it + 1 >= n_io) mbar_arrive(smem_u32(&misc->io_empty[(it + 1) % n_io]));
+      named_bar_sync(2, 256);
+      if (store_warp) {
+        if (elect_one()) {
+          tma_store_4d(&p.tm_out, io_smem + s_io * kTileBytes, 0, c.x0, c.y, c.n);
+          tma_store_commit();
+          // the slot tile it+1 will use was last read by the store of tile it+1-n_io
+          if (n_io == 2) tma_store_wait_read<1>();
+          else if (n_io == 3) tma_store_wait_read<2>();
+          else tma_store_wait_read<3>();
+          if (p.has_id && it + 1 >= n_io) mbar_arrive(smem_u32(&misc->io_empty[(it + 1) % n_io]));
+        }
+        __syncwarp();
       }
     }
-    if (leader) tma_store_wait_all<0>();
+    if (store_warp) {
+      if (elect_one()) tma_store_wait_all<0>();
+      __syncwarp();
+    }
   }
 
   // ---------------------------------------------------------------- teardown

@@ -160,6 +160,36 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
          | ((n >> 3) << 17)   // N >> 3
          | ((m >> 4) << 24);  // M >> 4
 }
+// True for exactly one lane of a converged warp.  Guarding uniform-datapath instructions (UTCHMMA,
+// UTMALDG, UTMASTG) with elect.sync instead of `lane == 0` lets ptxas emit them once instead of
+// wrapping each in an elect-and-branch loop over the possibly-active lanes.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// High word shared by every K-major SWIZZLE_128B descriptor here: SBO=1024, version 1, swizzle 128B.
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+// Low word: start address (>>4) and LBO=1.  Advancing by n bytes == adding n/16 to the low word.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t start) {
+  return ((start & 0x3FFFFu) >> 4) | (1u << 16);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T from descriptor words; issued by ONE thread.
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                             uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                           uint32_t idesc, uint32_t accumulate) {
