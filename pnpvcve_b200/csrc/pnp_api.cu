@@ -2,6 +2,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/pnp_vcve.h"
@@ -264,20 +265,27 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   p.act = c->act;
   p.mode = last ? pnp::kModeLast : pnp::kModeBf16;
   p.base_off_mode = g_base_off_mode;
-  // shared-memory budget: weights + (aux ring) + io ring + A ring from what is left
-  const long long budget = 232448 - 2048;
-  p.n_io = last ? 2 : (c->idt ? 3 : 2);
-  long long fixed = (long long)p.n_wchunks * pnp::kWChunkBytes + (c->aux ? 2 * pnp::kTileBytes : 0) +
-                    (long long)p.n_io * pnp::kTileBytes;
-  long long slots = (budget - fixed) / pnp::kASlotBytes;
-  if (slots > 6) slots = 6;
-  if (slots < 4) {
-    p.n_io = 2;
-    fixed = (long long)p.n_wchunks * pnp::kWChunkBytes + (c->aux ? 2 * pnp::kTileBytes : 0) +
-            (long long)p.n_io * pnp::kTileBytes;
-    slots = (budget - fixed) / pnp::kASlotBytes;
-    if (slots > 6) slots = 6;
+  {
+    const char* dbg = getenv("PNP_DEBUG_SKIP");   // what-if profiling only; results are wrong when set
+    p.debug_skip = dbg ? atoi(dbg) : 0;
+    const char* trc = getenv("PNP_TRACE_PTR");    // device pointer (decimal) of a >= 4 KB buffer
+    p.trace = trc ? reinterpret_cast<long long*>(strtoull(trc, nullptr, 10)) : nullptr;
   }
+  // shared-memory budget: weights + (aux ring) + staging ring + source-row ring from what is left.
+  // With an identity operand the staging ring also prefetches identity tiles (n_io - 2 tiles ahead),
+  // so it gets 4 slots as long as 5 source rows (3 in use + 2 in flight) still fit.
+  const long long budget = 232448 - 2048;
+  auto fixed_bytes = [&](int n_io) {
+    return (long long)p.n_wchunks * pnp::kWChunkBytes + (c->aux ? 2 * pnp::kTileBytes : 0) +
+           (long long)n_io * pnp::kTileBytes;
+  };
+  p.n_io = 2;
+  if (c->idt) {
+    p.n_io = 4;
+    while (p.n_io > 2 && (budget - fixed_bytes(p.n_io)) / pnp::kASlotBytes < 5) --p.n_io;
+  }
+  long long slots = (budget - fixed_bytes(p.n_io)) / pnp::kASlotBytes;
+  if (slots > pnp::kMaxASlots) slots = pnp::kMaxASlots;
   if (slots < 4) return fail(PNP_ERR_RESOURCE, "pnp_conv3x3: shared-memory budget cannot hold 4 source rows");
   p.s_a = (int)slots;
   cudaError_t e = pnp::launch_conv(p, grid, static_cast<cudaStream_t>(stream));

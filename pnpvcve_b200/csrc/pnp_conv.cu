@@ -57,21 +57,44 @@ struct Misc {
 };
 static_assert(sizeof(Misc) <= 1024, "misc region overflow");
 
-struct TileCoord {
-  int n, x0, y;
-  bool first, last;
+// Walks the tiles [t_begin, t_end) of a CTA in (image, strip, row) order.  One division at
+// construction, none per tile: the per-tile critical path of the MMA warp is only ~2000 cycles long
+// and an integer division costs ~100 of them.
+struct TileIter {
+  int t, t_begin, t_end, H, strips, n, strip, y;
+  __device__ TileIter(const ConvParams& p, int b, int e) : t(b), t_begin(b), t_end(e), H(p.H), strips(p.strips) {
+    const int col = b / p.H;
+    y = b - col * p.H;
+    n = col / p.strips;
+    strip = col - n * p.strips;
+  }
+  __device__ __forceinline__ bool valid() const { return t < t_end; }
+  __device__ __forceinline__ bool first() const { return t == t_begin || y == 0; }
+  __device__ __forceinline__ bool last() const { return t == t_end - 1 || y == H - 1; }
+  __device__ __forceinline__ int x0() const { return strip * kTilePx; }
+  __device__ __forceinline__ void next() {
+    ++t;
+    if (++y == H) {
+      y = 0;
+      if (++strip == strips) {
+        strip = 0;
+        ++n;
+      }
+    }
+  }
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t, int t_begin, int t_end) {
-  TileCoord c;
-  int col = t / p.H;
-  c.y = t - col * p.H;
-  c.n = col / p.strips;
-  c.x0 = (col - c.n * p.strips) * kTilePx;
-  c.first = (t == t_begin) || (c.y == 0);
-  c.last = (t == t_end - 1) || (c.y == p.H - 1);
-  return c;
-}
+// Slot / phase-parity cursor of a ring of mbarrier-guarded buffers.
+struct Ring {
+  uint32_t slot, phase, size;
+  __device__ explicit Ring(uint32_t n) : slot(0), phase(0), size(n) {}
+  __device__ __forceinline__ void advance() {
+    if (++slot == size) {
+      slot = 0;
+      phase ^= 1;
+    }
+  }
+};
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == kActLrelu) return v > 0.f ? v : 0.1f * v;
@@ -81,6 +104,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 }  // namespace
 
+template <bool kPar, bool kScale>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -146,29 +170,33 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
         bulk_load_1d(w_smem + c * kWChunkBytes,
                      reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)c * kWChunkBytes, kWChunkBytes,
                      wbar);
-      uint32_t ld = 0;
-      for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
-        const TileCoord c = decode_tile(p, t, t_begin, t_end);
-        for (int r = c.first ? c.y - 1 : c.y + 1; r <= c.y + 1; ++r, ++ld) {
-          const uint32_t slot = ld % s_a, ph = (ld / s_a) & 1;
-          mbar_wait(smem_u32(&misc->a_empty[slot]), ph ^ 1, 1);
-          const uint32_t fb = smem_u32(&misc->a_full[slot]);
-          mbar_arrive_expect_tx(fb, kRowBytes);
-          tma_load_4d(a_smem + slot * kASlotBytes, &p.tm_src, fb, 0, c.x0 - 1, r, c.n);
+      Ring ar(s_a), ior(n_io);
+      uint32_t loads = 0;
+      int it = 0;
+      for (TileIter c(p, t_begin, t_end); c.valid(); c.next(), ++it) {
+        for (int r = c.first() ? c.y - 1 : c.y + 1; r <= c.y + 1; ++r, ++loads, ar.advance()) {
+          mbar_wait(smem_u32(&misc->a_empty[ar.slot]), ar.phase ^ 1, 1);
+          const uint32_t fb = smem_u32(&misc->a_full[ar.slot]);
+          if ((p.debug_skip & 1) && loads >= (uint32_t)s_a) {
+            mbar_arrive(fb);
+          } else {
+            mbar_arrive_expect_tx(fb, kRowBytes);
+            tma_load_4d(a_smem + ar.slot * kASlotBytes, &p.tm_src, fb, 0, c.x0() - 1, r, c.n);
+          }
         }
         if (p.aux_k16 > 0) {
           const uint32_t s = it & 1, ph = (it >> 1) & 1;
           mbar_wait(smem_u32(&misc->aux_empty[s]), ph ^ 1, 2);
           const uint32_t fb = smem_u32(&misc->aux_full[s]);
           mbar_arrive_expect_tx(fb, kTileBytes);
-          tma_load_4d(aux_smem + s * kTileBytes, &p.tm_aux, fb, 0, c.x0, c.y, c.n);
+          tma_load_4d(aux_smem + s * kTileBytes, &p.tm_aux, fb, 0, c.x0(), c.y, c.n);
         }
         if (p.has_id) {
-          const uint32_t s = it % n_io, ph = (it / n_io) & 1;
-          mbar_wait(smem_u32(&misc->io_empty[s]), ph ^ 1, 3);
-          const uint32_t fb = smem_u32(&misc->id_full[s]);
+          mbar_wait(smem_u32(&misc->io_empty[ior.slot]), ior.phase ^ 1, 3);
+          const uint32_t fb = smem_u32(&misc->id_full[ior.slot]);
           mbar_arrive_expect_tx(fb, kTileBytes);
-          tma_load_4d(io_smem + s * kTileBytes, &p.tm_id, fb, 0, c.x0, c.y, c.n);
+          tma_load_4d(io_smem + ior.slot * kTileBytes, &p.tm_id, fb, 0, c.x0(), c.y, c.n);
+          ior.advance();
         }
       }
     }
@@ -183,25 +211,45 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
     const uint32_t bo_mul = (p.base_off_mode == 1) ? (1u << 17) : 0u;   // diagnostic only
     const uint32_t w_lo = umma_desc_lo(w_smem);
     mbar_wait(smem_u32(&misc->w_full), 0, 4);
-    uint32_t ld_base = 0, ld_next = 0, confirmed = 0;
-    for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
-      const TileCoord c = decode_tile(p, t, t_begin, t_end);
-      if (c.first) {
-        ld_base = ld_next;
-        ld_next += 3;
+    Ring ar(s_a);                              // cursor of the next source-row load to consume
+    uint32_t s0 = 0, s1 = 0, s2 = 0;           // ring slots of rows y-1, y, y+1
+    bool pend_valid = false, pend_last = false;   // previous tile, whose commits are still owed
+    uint32_t pend_s0 = 0, pend_s1 = 0, pend_s2 = 0, pend_b = 0;
+    int it = 0;
+    for (TileIter c(p, t_begin, t_end); c.valid(); c.next(), ++it) {
+      if (pend_valid && pend_last) {
+        // the previous tile closed a strip segment: its three rows must be handed back before the
+        // three rows of the new segment can arrive (the ring may be only 5 deep), so no deferral
+        if (elect_one()) {
+          umma_commit(smem_u32(&misc->a_empty[pend_s0]));
+          umma_commit(smem_u32(&misc->a_empty[pend_s1]));
+          umma_commit(smem_u32(&misc->a_empty[pend_s2]));
+          if (p.aux_k16 > 0) umma_commit(smem_u32(&misc->aux_empty[pend_b]));
+          umma_commit(smem_u32(&misc->acc_full[pend_b]));
+        }
+        __syncwarp();
+        pend_valid = false;
+      }
+      if (c.first()) {
+        mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
+        s0 = ar.slot;
+        ar.advance();
+        mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
+        s1 = ar.slot;
+        ar.advance();
       } else {
-        ld_base += 1;
-        ld_next += 1;
+        s0 = s1;
+        s1 = s2;
       }
-      while (confirmed < ld_base + 3) {
-        mbar_wait(smem_u32(&misc->a_full[confirmed % s_a]), (confirmed / s_a) & 1, 5);
-        ++confirmed;
-      }
+      mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
+      s2 = ar.slot;
+      ar.advance();
       const uint32_t b = it & 1;
       mbar_wait(smem_u32(&misc->acc_empty[b]), ((it >> 1) & 1) ^ 1, 6);
       if (p.aux_k16 > 0) mbar_wait(smem_u32(&misc->aux_full[it & 1]), (it >> 1) & 1, 7);
       tc_fence_after();
-      const uint32_t s0 = ld_base % s_a, s1 = (ld_base + 1) % s_a, s2 = (ld_base + 2) % s_a;
+      const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && it < 64;
+      if (tr && lane == 0) p.trace[it * 8 + 0] = clock64();
       if (elect_one()) {
         const uint32_t d = tmem_base + b * kAccStride;
         const uint32_t row_lo[3] = {umma_desc_lo(a_smem + s0 * kASlotBytes),
@@ -219,6 +267,16 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16_lo(d, a_lo + 2 * k, a_hi, b_lo + 2 * k, kDescHiSw128, idesc, (j | k) != 0);
+          if (tr && j == 0) p.trace[it * 8 + 6] = clock64();
+          if (tr && j == 4) p.trace[it * 8 + 7] = clock64();
+          if (j == 0 && pend_valid) {
+            // Deferred commits of the PREVIOUS tile: tcgen05.commit stalls this thread until the
+            // MMAs before it have drained, so it is issued only after this tile's first MMAs are
+            // queued behind them -- the tensor pipe keeps running through the per-tile bookkeeping.
+            umma_commit(smem_u32(&misc->a_empty[pend_s0]));
+            if (p.aux_k16 > 0) umma_commit(smem_u32(&misc->aux_empty[pend_b]));
+            umma_commit(smem_u32(&misc->acc_full[pend_b]));
+          }
         }
         if (p.aux_k16 > 0) {
           const uint32_t a_lo = umma_desc_lo(aux_smem + (it & 1) * kTileBytes);
@@ -226,13 +284,20 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
           for (int k = 0; k < p.aux_k16; ++k)
             umma_bf16_lo(d, a_lo + 2 * k, kDescHiSw128, b_lo + 2 * k, kDescHiSw128, idesc_tap, 1);
         }
-        umma_commit(smem_u32(&misc->a_empty[s0]));
-        if (c.last) {
-          umma_commit(smem_u32(&misc->a_empty[s1]));
-          umma_commit(smem_u32(&misc->a_empty[s2]));
-        }
-        if (p.aux_k16 > 0) umma_commit(smem_u32(&misc->aux_empty[it & 1]));
-        umma_commit(smem_u32(&misc->acc_full[b]));
+      }
+      pend_valid = true;
+      pend_last = c.last();
+      pend_s0 = s0;
+      pend_s1 = s1;
+      pend_s2 = s2;
+      pend_b = b;
+      __syncwarp();
+      if (tr && lane == 0) p.trace[it * 8 + 1] = clock64();
+    }
+    if (pend_valid) {
+      if (elect_one()) {
+        umma_commit(smem_u32(&misc->a_empty[pend_s0]));
+        umma_commit(smem_u32(&misc->acc_full[pend_b]));
       }
       __syncwarp();
     }
@@ -245,9 +310,19 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
     const int row = q * 32 + lane;          // pixel inside the tile == TMEM lane
     const bool store_warp = (warp == 2);
     const uint32_t sw = (uint32_t)(row & 7);
-    for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
-      const TileCoord c = decode_tile(p, t, t_begin, t_end);
-      const int x = c.x0 + row;
+    // per-channel epilogue constants of this warp's 32 channels live in registers for the whole
+    // kernel (re-reading them from shared memory per tile costs as many smem wavefronts as the
+    // output staging itself, and the shared-memory pipe is what bounds this kernel)
+    float bias_r[32], scale_r[kScale ? 32 : 1];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      bias_r[j] = misc->bias[half * 32 + j];
+      if (kScale) scale_r[j] = misc->scale[half * 32 + j];
+    }
+    Ring ior(n_io), rel(n_io);               // staging slot of this tile / slot to hand back
+    int it = 0;
+    for (TileIter c(p, t_begin, t_end); c.valid(); c.next(), ++it) {
+      const int x = c.x0() + row;
       const bool valid = x < p.W;
       const uint32_t b = it & 1;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * kAccStride;
@@ -277,27 +352,47 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
         continue;
       }
       float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-      if (p.par != nullptr && valid) {
+      if (kPar && valid) {
         const float* pp = p.par + (long long)c.n * p.par_sn + (long long)c.y * p.par_sy + x;
         p0 = __ldg(pp);
         p1 = __ldg(pp + p.par_sc);
         p2 = __ldg(pp + 2 * p.par_sc);
       }
-      const uint32_t s_io = it % n_io;
+      const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && it < 64 && threadIdx.x == 64;
+      if (tr) p.trace[it * 8 + 2] = clock64();
+      const uint32_t s_io = ior.slot;
+      // Staging-slot recycling.  All stores but the most recent one have finished READING shared
+      // memory once wait_group.read<1> returns, i.e. the slots of tiles <= it-2 are free: hand the
+      // slot of tile it-2 back to the producer now, so the identity tile of tile it-2+n_io is in
+      // flight while this tile and the next are computed (its HBM latency is ~2 tiles long).
+      if (store_warp) {
+        if (elect_one()) {
+          tma_store_wait_read<1>();
+          if (p.has_id && it >= 2) mbar_arrive(smem_u32(&misc->io_empty[rel.slot]));
+        }
+        __syncwarp();
+      }
+      if (it >= 2) rel.advance();
       if (p.has_id) {
-        mbar_wait(smem_u32(&misc->id_full[s_io]), (it / n_io) & 1, 8);
+        mbar_wait(smem_u32(&misc->id_full[s_io]), ior.phase, 8);
       } else {
-        named_bar_sync(1, 256);             // the store that last used this slot has been drained
+        named_bar_sync(1, 256);             // n_io == 2: tile it-2's store has drained this slot
       }
       mbar_wait(smem_u32(&misc->acc_full[b]), (it >> 1) & 1, 9);
       tc_fence_after();
+      if (tr) p.trace[it * 8 + 3] = clock64();
       uint8_t* rowp = sgen + L.io + s_io * kTileBytes + row * 128;
 #pragma unroll
       for (int gg = 0; gg < 2; ++gg) {
         const int g = half * 2 + gg;        // 16-channel group
         float v[16];
-        tmem_ld16(taddr + g * 16, v);
-        if (p.center_n == 256) {
+        if (p.debug_skip & 4) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        } else {
+          tmem_ld16(taddr + g * 16, v);
+        }
+        if (kPar) {
           float a1[16], a2[16], a3[16];
           tmem_ld16(taddr + 64 + g * 16, a1);
           tmem_ld16(taddr + 128 + g * 16, a2);
@@ -305,8 +400,7 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int ch = g * 16 + j;
-            v[j] = fmaf(v[j], misc->scale[ch], misc->bias[ch]);
+            v[j] = kScale ? fmaf(v[j], scale_r[gg * 16 + j], bias_r[gg * 16 + j]) : v[j] + bias_r[gg * 16 + j];
             v[j] = fmaf(p0, a1[j], v[j]);
             v[j] = fmaf(p1, a2[j], v[j]);
             v[j] = fmaf(p2, a3[j], v[j]);
@@ -314,10 +408,8 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
         } else {
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int ch = g * 16 + j;
-            v[j] = fmaf(v[j], misc->scale[ch], misc->bias[ch]);
-          }
+          for (int j = 0; j < 16; ++j)
+            v[j] = kScale ? fmaf(v[j], scale_r[gg * 16 + j], bias_r[gg * 16 + j]) : v[j] + bias_r[gg * 16 + j];
         }
         uint4* c0 = reinterpret_cast<uint4*>(rowp + (((2 * g) ^ sw) << 4));
         uint4* c1 = reinterpret_cast<uint4*>(rowp + (((2 * g + 1) ^ sw) << 4));
@@ -341,25 +433,27 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
         o1.y = pack_bf16x2(v[10], v[11]);
         o1.z = pack_bf16x2(v[12], v[13]);
         o1.w = pack_bf16x2(v[14], v[15]);
-        *c0 = o0;
-        *c1 = o1;
+        if (!(p.debug_skip & 2)) {
+          *c0 = o0;
+          *c1 = o1;
+        }
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&misc->acc_empty[b]));
+      if (tr) p.trace[it * 8 + 4] = clock64();
       fence_proxy_async_smem();
       named_bar_sync(2, 256);
+      if (tr) p.trace[it * 8 + 5] = clock64();
       if (store_warp) {
         if (elect_one()) {
-          tma_store_4d(&p.tm_out, io_smem + s_io * kTileBytes, 0, c.x0, c.y, c.n);
-          tma_store_commit();
-          // the slot tile it+1 will use was last read by the store of tile it+1-n_io
-          if (n_io == 2) tma_store_wait_read<1>();
-          else if (n_io == 3) tma_store_wait_read<2>();
-          else tma_store_wait_read<3>();
-          if (p.has_id && it + 1 >= n_io) mbar_arrive(smem_u32(&misc->io_empty[(it + 1) % n_io]));
+          if (!(p.debug_skip & 2)) {
+            tma_store_4d(&p.tm_out, io_smem + s_io * kTileBytes, 0, c.x0(), c.y, c.n);
+            tma_store_commit();
+          }
         }
         __syncwarp();
       }
+      ior.advance();
     }
     if (store_warp) {
       if (elect_one()) tma_store_wait_all<0>();
@@ -380,17 +474,33 @@ size_t conv_smem_bytes(const ConvParams& p) {
   return make_layout(p.n_wchunks, p.s_a, p.aux_k16 > 0, p.n_io).total + 1024;  // + alignment slack
 }
 
-cudaError_t launch_conv(const ConvParams& p, int grid, cudaStream_t stream) {
-  static bool attr_set = false;
-  const size_t smem = conv_smem_bytes(p);
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         232448);
+namespace {
+template <bool kPar, bool kScale>
+cudaError_t launch_variant(const ConvParams& p, int grid, size_t smem, cudaStream_t stream) {
+  // opt in to the full 227 KB once per device (one device per process is the deployment model,
+  // but several are tolerated)
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    e = cudaFuncSetAttribute(conv3x3_umma_kernel<kPar, kScale>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             232448);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
-  conv3x3_umma_kernel<<<grid, kConvThreads, smem, stream>>>(p);
+  conv3x3_umma_kernel<kPar, kScale><<<grid, kConvThreads, smem, stream>>>(p);
   return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t launch_conv(const ConvParams& p, int grid, cudaStream_t stream) {
+  const size_t smem = conv_smem_bytes(p);
+  const bool par = (p.center_n == 256), scale = (p.scale != nullptr);
+  if (par) return scale ? launch_variant<true, true>(p, grid, smem, stream)
+                        : launch_variant<true, false>(p, grid, smem, stream);
+  return scale ? launch_variant<false, true>(p, grid, smem, stream)
+               : launch_variant<false, false>(p, grid, smem, stream);
 }
 
 }  // namespace pnp

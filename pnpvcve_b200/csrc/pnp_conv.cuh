@@ -45,6 +45,8 @@ struct ConvParams {
   int mode;
   int s_a;              // A ring slots
   int n_io;             // id/out staging slots
+  long long* trace;      // optional device buffer for per-tile clock64 stamps of CTA 0 (diagnostics)
+  int debug_skip;        // what-if profiling bits (results are WRONG): 1 skip row loads, 2 skip output staging/store, 4 skip TMEM loads
   int base_off_mode;    // 0: descriptor base_offset = 0 (measured-correct on B200); 1: (addr>>7)&7
 };
 

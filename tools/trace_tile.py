@@ -1,0 +1,24 @@
+"""Per-tile clock64 trace of CTA 0 of the conv kernel (diagnostic)."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pnpvcve_b200 import ops
+dev = torch.device("cuda:0"); h, w = 720, 1280
+x = torch.randn((1, h, w, 64), device=dev).to(torch.bfloat16)
+out = ops.new_feature(1, h, w, dev)
+wp9 = ops.new_wpack(9, dev); ops.pack_conv3x3(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp9)
+trace = torch.zeros(64 * 8, dtype=torch.int64, device=dev)
+for _ in range(3): ops.conv3x3(x, wp9, out=out)
+torch.cuda.synchronize()
+os.environ["PNP_TRACE_PTR"] = str(trace.data_ptr())
+ops.conv3x3(x, wp9, out=out)
+torch.cuda.synchronize()
+t = trace.view(64, 8).cpu()
+t0 = int(t[0, 0])
+print("tile  mma_ready  mma_issued | epi_start  acc_full   epi_math   epi_bar   (cycles since first MMA ready; deltas in brackets)")
+prev = None
+for i in range(49):
+    r = [int(v) - t0 for v in t[i, :8]]
+    d = "" if prev is None else f"  [period {r[0]-prev[0]:5d}  issue {r[1]-r[0]:4d} (4 MMAs +{r[6]-r[0]:4d}, 20 MMAs +{r[7]-r[0]:4d})  gap {r[0]-prev[1]:4d}  accwait {r[3]-r[2]:5d}  math {r[4]-r[3]:4d}  bar {r[5]-r[4]:4d}]"
+    print(f"{i:3d} {r[0]:9d} {r[1]:9d} | {r[2]:9d} {r[3]:9d} {r[4]:9d} {r[5]:9d}{d}")
+    prev = r

@@ -1,0 +1,28 @@
+"""What-if timing of the conv kernel with parts of the pipeline disabled (PNP_DEBUG_SKIP bits)."""
+import os, sys, subprocess
+if len(sys.argv) > 1:
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from pnpvcve_b200 import ops
+    dev = torch.device("cuda:0"); h, w = 720, 1280
+    x = torch.randn((1, h, w, 64), device=dev).to(torch.bfloat16)
+    idt = torch.randn((1, h, w, 64), device=dev).to(torch.bfloat16)
+    out = ops.new_feature(1, h, w, dev)
+    wp9 = ops.new_wpack(9, dev); ops.pack_conv3x3(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp9)
+    wp = ops.new_wpack(12, dev); ops.pack_conv3x3(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp, center_chunks=4)
+    par = torch.rand((1, 3, h, w), device=dev)
+    def timeit(fn, iters=30):
+        for _ in range(5): fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters): fn()
+        e.record(); torch.cuda.synchronize()
+        return s.elapsed_time(e) / iters * 1e3
+    a = timeit(lambda: ops.conv3x3(x, wp9, out=out))
+    b = timeit(lambda: ops.conv3x3(x, wp9, out=out, idt=idt))
+    c = timeit(lambda: ops.conv3x3(x, wp, out=out, par=par, act=2))
+    print(f"skip={os.environ.get('PNP_DEBUG_SKIP','0'):>2s}: plain {a:6.1f} us   +id {b:6.1f} us   +par {c:6.1f} us", flush=True)
+else:
+    for bits in (0, 1, 2, 4, 3, 6, 7):
+        env = dict(os.environ, PNP_DEBUG_SKIP=str(bits))
+        subprocess.run([sys.executable, __file__, "run"], env=env)
