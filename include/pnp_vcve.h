@@ -80,6 +80,13 @@ int pnp_pack_conv3x3(const float* w, int n_experts, const float* coef, int out_c
                      void* stream);
 int pnp_pack_rows(const float* w, int rows, int cols, int64_t row_stride, int64_t col_stride, void* dst,
                   int row_offset, void* stream);
+/* Row-stacked layout (pnp_conv_desc.wlayout = PNP_WLAYOUT_ROWSTACK): per kx one block of 3*tap_n
+ * 128-byte rows, sub-block sb = 0,1,2 holding ky = 2 - sb, so that one source row can be multiplied
+ * against the weights of the three output rows it feeds in a single N = 3*tap_n MMA.  tap_n is 64, or
+ * 16 for the 64->3 tail; total 9*tap_n*128 bytes.  Same mixing arguments as pnp_pack_conv3x3. */
+int pnp_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, int out_ch, int in_total,
+                              int in_begin, int in_begin2, int in_count, void* dst, int tap_n,
+                              void* stream);
 int pnp_pack_aux(const float* w, int out_ch, int in_total, void* dst, void* stream);
 
 /*
@@ -108,6 +115,7 @@ int pnp_mix_bias(const float* conv2_bias, int n_blocks, int n_experts, const flo
  * input_conv (basicvsr_net.py:484,515), conv_hr/conv_last (iconvsr_ipb_par.py:144-146).
  */
 enum { PNP_CONV_BF16 = 0, PNP_CONV_LAST = 1 };
+enum { PNP_WLAYOUT_TAPMAJOR = 0, PNP_WLAYOUT_ROWSTACK = 1 };
 enum { PNP_ACT_NONE = 0, PNP_ACT_LRELU = 1, PNP_ACT_RELU = 2 };
 
 typedef struct pnp_conv_desc {
@@ -131,6 +139,8 @@ typedef struct pnp_conv_desc {
   int32_t aux_k16;     /* K/16 of aux (2 for the 27-entry LR im2col), 0 without aux */
   int32_t act;
   int32_t mode;
+  int32_t wlayout;     /* PNP_WLAYOUT_TAPMAJOR (n_wchunks blocks, required with par) or PNP_WLAYOUT_ROWSTACK
+                          (9*tap_n*128 bytes, followed by the 8192-byte aux block when aux is given) */
 } pnp_conv_desc;
 
 int pnp_conv3x3(const pnp_conv_desc* desc, void* stream);

@@ -11,11 +11,13 @@ LIB_PATH = os.path.join(HERE, "libpnpvcve.so")
 
 PNP_CONV_BF16, PNP_CONV_LAST = 0, 1
 PNP_ACT_NONE, PNP_ACT_LRELU, PNP_ACT_RELU = 0, 1, 2
+PNP_WLAYOUT_TAPMAJOR, PNP_WLAYOUT_ROWSTACK = 0, 1
 
 #: every symbol include/pnp_vcve.h declares
 EXPORTS = [
     "pnp_abi_version", "pnp_last_error", "pnp_device_check", "pnp_set_base_offset_mode",
-    "pnp_mv_warp", "pnp_lr_im2col", "pnp_pack_conv3x3", "pnp_pack_rows", "pnp_pack_aux",
+    "pnp_mv_warp", "pnp_lr_im2col", "pnp_pack_conv3x3", "pnp_pack_conv3x3_rowstack", "pnp_pack_rows",
+    "pnp_pack_aux",
     "pnp_caa_heads", "pnp_mix_bias", "pnp_conv3x3",
 ]
 
@@ -34,6 +36,7 @@ class ConvDesc(_c.Structure):
         ("N", _c.c_int32), ("H", _c.c_int32), ("W", _c.c_int32),
         ("n_wchunks", _c.c_int32), ("center_n", _c.c_int32), ("tap_n", _c.c_int32),
         ("aux_k16", _c.c_int32), ("act", _c.c_int32), ("mode", _c.c_int32),
+        ("wlayout", _c.c_int32),
     ]
 
 
@@ -45,6 +48,7 @@ _PROTOS = {
     "pnp_mv_warp": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
     "pnp_lr_im2col": (_i, [_vp, _i64, _i64, _i64, _vp, _i, _i, _i, _vp]),
     "pnp_pack_conv3x3": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "pnp_pack_conv3x3_rowstack": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "pnp_pack_rows": (_i, [_vp, _i, _i, _i64, _i64, _vp, _i, _vp]),
     "pnp_pack_aux": (_i, [_vp, _i, _i, _vp, _vp]),
     "pnp_caa_heads": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),

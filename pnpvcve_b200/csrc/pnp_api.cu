@@ -150,6 +150,22 @@ int pnp_pack_conv3x3(const float* w, int n_experts, const float* coef, int out_c
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_pack_conv3x3");
 }
 
+int pnp_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, int out_ch, int in_total,
+                              int in_begin, int in_begin2, int in_count, void* dst, int tap_n,
+                              void* stream) {
+  if (!w || !dst) return fail(PNP_ERR_ARG, "pnp_pack_conv3x3_rowstack: null pointer");
+  if (n_experts < 1 || (coef == nullptr && n_experts != 1) || out_ch < 1 || (tap_n != 64 && tap_n != 16) ||
+      out_ch > tap_n || in_count < 1 || in_count > 64 || in_begin < 0 || in_begin + in_count > in_total ||
+      (in_begin2 >= 0 && in_begin2 + in_count > in_total) || !aligned16(dst))
+    return fail(PNP_ERR_ARG, "pnp_pack_conv3x3_rowstack: bad argument");
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  cudaError_t e = pnp::launch_pack_conv3x3_rowstack(w, n_experts, coef, out_ch, in_total, in_begin, in_begin2,
+                                                    in_count, dst, tap_n, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_pack_conv3x3_rowstack");
+}
+
 int pnp_pack_rows(const float* w, int rows, int cols, int64_t row_stride, int64_t col_stride, void* dst,
                   int row_offset, void* stream) {
   if (!w || !dst) return fail(PNP_ERR_ARG, "pnp_pack_rows: null pointer");
@@ -222,9 +238,14 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   if ((c->aux != nullptr) != (c->aux_k16 > 0) || c->aux_k16 < 0 || c->aux_k16 > 4)
     return fail(PNP_ERR_ARG, "pnp_conv3x3: aux / aux_k16 mismatch");
   if (c->aux && c->center_n == 256) return fail(PNP_ERR_ARG, "pnp_conv3x3: aux and par are exclusive");
+  const bool rowstack = (c->wlayout == PNP_WLAYOUT_ROWSTACK);
+  if (c->wlayout != PNP_WLAYOUT_TAPMAJOR && !rowstack) return fail(PNP_ERR_ARG, "pnp_conv3x3: bad wlayout");
+  if (rowstack && c->center_n != c->tap_n)
+    return fail(PNP_ERR_ARG, "pnp_conv3x3: the row-stacked layout does not carry the partition 1x1 convs");
   const int center_chunks = (c->center_n == 256) ? 4 : 1;
   const int need_chunks = center_chunks + 8 + (c->aux ? 1 : 0);
-  if (c->n_wchunks != need_chunks) return fail(PNP_ERR_ARG, "pnp_conv3x3: n_wchunks does not match the layout");
+  if (!rowstack && c->n_wchunks != need_chunks)
+    return fail(PNP_ERR_ARG, "pnp_conv3x3: n_wchunks does not match the layout");
   if (c->act < 0 || c->act > 2) return fail(PNP_ERR_ARG, "pnp_conv3x3: bad act");
   if (!aligned16(c->src) || !aligned16(c->wpack) || (c->aux && !aligned16(c->aux)) ||
       (c->idt && !aligned16(c->idt)) || (c->out && !aligned16(c->out)))
@@ -275,9 +296,10 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   // With an identity operand the staging ring also prefetches identity tiles (n_io - 2 tiles ahead),
   // so it gets 4 slots as long as 5 source rows (3 in use + 2 in flight) still fit.
   const long long budget = 232448 - 2048;
+  const long long w_bytes = rowstack ? (((long long)9 * c->tap_n * 128 + (c->aux ? pnp::kWChunkBytes : 0) + 1023) & ~1023LL)
+                                     : (long long)p.n_wchunks * pnp::kWChunkBytes;
   auto fixed_bytes = [&](int n_io) {
-    return (long long)p.n_wchunks * pnp::kWChunkBytes + (c->aux ? 2 * pnp::kTileBytes : 0) +
-           (long long)n_io * pnp::kTileBytes;
+    return w_bytes + (c->aux ? 2 * pnp::kTileBytes : 0) + (long long)n_io * pnp::kTileBytes;
   };
   p.n_io = 2;
   if (c->idt) {
@@ -285,10 +307,16 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
     while (p.n_io > 2 && (budget - fixed_bytes(p.n_io)) / pnp::kASlotBytes < 5) --p.n_io;
   }
   long long slots = (budget - fixed_bytes(p.n_io)) / pnp::kASlotBytes;
-  if (slots > pnp::kMaxASlots) slots = pnp::kMaxASlots;
+  const long long max_slots = rowstack ? 6 : pnp::kMaxASlots;   // a row lives one step there: 6 = 5 in flight
+  if (slots > max_slots) slots = max_slots;
   if (slots < 4) return fail(PNP_ERR_RESOURCE, "pnp_conv3x3: shared-memory budget cannot hold 4 source rows");
+  // the row-stacked MMA thread checks the next step's barriers before the current step is committed;
+  // with an identity operand that needs a staging ring of >= 3 slots to stay deadlock free
+  if (rowstack && c->idt && p.n_io < 3)
+    return fail(PNP_ERR_RESOURCE, "pnp_conv3x3: row-stacked layout with idt needs 3 staging slots (drop aux)");
   p.s_a = (int)slots;
-  cudaError_t e = pnp::launch_conv(p, grid, static_cast<cudaStream_t>(stream));
+  cudaError_t e = rowstack ? pnp::launch_conv_rows(p, grid, static_cast<cudaStream_t>(stream))
+                           : pnp::launch_conv(p, grid, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_conv3x3");
 }
 

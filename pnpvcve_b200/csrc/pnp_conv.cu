@@ -205,57 +205,71 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
     // The whole warp walks the tile list and waits on the barriers (warp-uniform control flow keeps
     // addresses in uniform registers); one elected lane issues the 36..48 tcgen05.mma of a tile as
     // straight-line code: descriptor = per-row base word + compile-time offset.
-    const uint32_t idesc_center = umma_idesc_bf16(128, p.center_n);
-    const uint32_t idesc_tap = umma_idesc_bf16(128, p.tap_n);
-    const uint32_t center_chunks = (p.center_n == 256) ? 4 : 1;
-    const uint32_t bo_mul = (p.base_off_mode == 1) ? (1u << 17) : 0u;   // diagnostic only
-    const uint32_t w_lo = umma_desc_lo(w_smem);
-    mbar_wait(smem_u32(&misc->w_full), 0, 4);
-    Ring ar(s_a);                              // cursor of the next source-row load to consume
-    uint32_t s0 = 0, s1 = 0, s2 = 0;           // ring slots of rows y-1, y, y+1
-    bool pend_valid = false, pend_last = false;   // previous tile, whose commits are still owed
-    uint32_t pend_s0 = 0, pend_s1 = 0, pend_s2 = 0, pend_b = 0;
-    int it = 0;
-    for (TileIter c(p, t_begin, t_end); c.valid(); c.next(), ++it) {
-      if (pend_valid && pend_last) {
-        // the previous tile closed a strip segment: its three rows must be handed back before the
-        // three rows of the new segment can arrive (the ring may be only 5 deep), so no deferral
-        if (elect_one()) {
-          umma_commit(smem_u32(&misc->a_empty[pend_s0]));
-          umma_commit(smem_u32(&misc->a_empty[pend_s1]));
-          umma_commit(smem_u32(&misc->a_empty[pend_s2]));
-          if (p.aux_k16 > 0) umma_commit(smem_u32(&misc->aux_empty[pend_b]));
-          umma_commit(smem_u32(&misc->acc_full[pend_b]));
+    if (elect_one()) {
+      const uint32_t idesc_center = umma_idesc_bf16(128, p.center_n);
+      const uint32_t idesc_tap = umma_idesc_bf16(128, p.tap_n);
+      const uint32_t center_chunks = (p.center_n == 256) ? 4 : 1;
+      const uint32_t bo_mul = (p.base_off_mode == 1) ? (1u << 17) : 0u;   // diagnostic only
+      const uint32_t w_lo = umma_desc_lo(w_smem);
+      const uint32_t tap_lo = w_lo + center_chunks * (kWChunkBytes >> 4);
+      mbar_wait(smem_u32(&misc->w_full), 0, 4);
+
+      // Everything a tile's issue code needs.  The barriers of tile i+1 are checked in the middle
+      // of tile i (an already-complete mbarrier wait costs ~200 cycles; the tensor pipe rides out
+      // only ~300 cycles of silence from this thread -- tools/umma_bench.cu).
+      struct TileCtx {
+        bool valid, last;
+        uint32_t s0, s1, s2, b, it;
+      };
+      Ring ar(s_a);
+      TileIter ti(p, t_begin, t_end);
+      auto acquire = [&](TileCtx& c, const TileCtx& prev) {   // waits + ring slots of the tile at `ti`
+        c.valid = ti.valid();
+        if (!c.valid) return;
+        if (ti.first()) {
+          mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
+          c.s0 = ar.slot;
+          ar.advance();
+          mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
+          c.s1 = ar.slot;
+          ar.advance();
+        } else {
+          c.s0 = prev.s1;
+          c.s1 = prev.s2;
         }
-        __syncwarp();
-        pend_valid = false;
-      }
-      if (c.first()) {
         mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
-        s0 = ar.slot;
+        c.s2 = ar.slot;
         ar.advance();
-        mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
-        s1 = ar.slot;
-        ar.advance();
-      } else {
-        s0 = s1;
-        s1 = s2;
-      }
-      mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
-      s2 = ar.slot;
-      ar.advance();
-      const uint32_t b = it & 1;
-      mbar_wait(smem_u32(&misc->acc_empty[b]), ((it >> 1) & 1) ^ 1, 6);
-      if (p.aux_k16 > 0) mbar_wait(smem_u32(&misc->aux_full[it & 1]), (it >> 1) & 1, 7);
+        c.it = prev.it + 1;
+        c.b = c.it & 1;
+        c.last = ti.last();
+        mbar_wait(smem_u32(&misc->acc_empty[c.b]), ((c.it >> 1) & 1) ^ 1, 6);
+        if (p.aux_k16 > 0) mbar_wait(smem_u32(&misc->aux_full[c.b]), (c.it >> 1) & 1, 7);
+      };
+      auto commit_tile = [&](const TileCtx& c) {
+        umma_commit(smem_u32(&misc->a_empty[c.s0]));
+        if (c.last) {
+          umma_commit(smem_u32(&misc->a_empty[c.s1]));
+          umma_commit(smem_u32(&misc->a_empty[c.s2]));
+        }
+        if (p.aux_k16 > 0) umma_commit(smem_u32(&misc->aux_empty[c.b]));
+        umma_commit(smem_u32(&misc->acc_full[c.b]));
+      };
+      TileCtx none{false, false, 0, 0, 0, 0, 0xFFFFFFFFu};   // it + 1 == 0 for the first tile
+      TileCtx cur;
+      acquire(cur, none);
       tc_fence_after();
-      const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && it < 64;
-      if (tr && lane == 0) p.trace[it * 8 + 0] = clock64();
-      if (elect_one()) {
-        const uint32_t d = tmem_base + b * kAccStride;
-        const uint32_t row_lo[3] = {umma_desc_lo(a_smem + s0 * kASlotBytes),
-                                    umma_desc_lo(a_smem + s1 * kASlotBytes),
-                                    umma_desc_lo(a_smem + s2 * kASlotBytes)};
-        const uint32_t tap_lo = w_lo + center_chunks * (kWChunkBytes >> 4);
+      bool pend = false;
+      TileCtx pend_ctx = none;
+      while (cur.valid) {
+        const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && cur.it < 64;
+        if (tr) p.trace[cur.it * 8 + 0] = clock64();
+        const uint32_t d = tmem_base + cur.b * kAccStride;
+        const uint32_t row_lo[3] = {umma_desc_lo(a_smem + cur.s0 * kASlotBytes),
+                                    umma_desc_lo(a_smem + cur.s1 * kASlotBytes),
+                                    umma_desc_lo(a_smem + cur.s2 * kASlotBytes)};
+        TileCtx nxt;
+        nxt.valid = false;
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
           const int tap = (j == 0) ? 4 : (j <= 4 ? j - 1 : j);   // centre first, then row-major
@@ -267,39 +281,41 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16_lo(d, a_lo + 2 * k, a_hi, b_lo + 2 * k, kDescHiSw128, idesc, (j | k) != 0);
-          if (tr && j == 0) p.trace[it * 8 + 6] = clock64();
-          if (tr && j == 4) p.trace[it * 8 + 7] = clock64();
-          if (j == 0 && pend_valid) {
-            // Deferred commits of the PREVIOUS tile: tcgen05.commit stalls this thread until the
-            // MMAs before it have drained, so it is issued only after this tile's first MMAs are
-            // queued behind them -- the tensor pipe keeps running through the per-tile bookkeeping.
-            umma_commit(smem_u32(&misc->a_empty[pend_s0]));
-            if (p.aux_k16 > 0) umma_commit(smem_u32(&misc->aux_empty[pend_b]));
-            umma_commit(smem_u32(&misc->acc_full[pend_b]));
+          if (j == 0 && pend) {
+            // commits of the PREVIOUS tile ride behind this tile's first MMAs
+            commit_tile(pend_ctx);
+            pend = false;
+          }
+          if (j == 5 && !cur.last) {
+            // barriers of the NEXT tile while ~8 MMAs of this one are queued.  (A tile that closes a
+            // strip segment must first hand its three rows back -- the ring may be only 5 deep -- so
+            // its look-ahead happens after the commit below.)
+            ti.next();
+            acquire(nxt, cur);
+            tc_fence_after();
           }
         }
         if (p.aux_k16 > 0) {
-          const uint32_t a_lo = umma_desc_lo(aux_smem + (it & 1) * kTileBytes);
+          const uint32_t a_lo = umma_desc_lo(aux_smem + cur.b * kTileBytes);
           const uint32_t b_lo = tap_lo + 8 * (kWChunkBytes >> 4);
           for (int k = 0; k < p.aux_k16; ++k)
             umma_bf16_lo(d, a_lo + 2 * k, kDescHiSw128, b_lo + 2 * k, kDescHiSw128, idesc_tap, 1);
         }
+        if (tr) p.trace[cur.it * 8 + 1] = clock64();
+        if (cur.last) {
+          // segment end: commit now (frees the three rows), then look ahead
+          commit_tile(cur);
+          pend = false;
+          ti.next();
+          acquire(nxt, cur);
+          tc_fence_after();
+        } else {
+          pend = true;
+          pend_ctx = cur;
+        }
+        cur = nxt;
       }
-      pend_valid = true;
-      pend_last = c.last();
-      pend_s0 = s0;
-      pend_s1 = s1;
-      pend_s2 = s2;
-      pend_b = b;
-      __syncwarp();
-      if (tr && lane == 0) p.trace[it * 8 + 1] = clock64();
-    }
-    if (pend_valid) {
-      if (elect_one()) {
-        umma_commit(smem_u32(&misc->a_empty[pend_s0]));
-        umma_commit(smem_u32(&misc->acc_full[pend_b]));
-      }
-      __syncwarp();
+      if (pend) commit_tile(pend_ctx);
     }
   } else {
     // ============================================================ epilogue (8 warps, 256 threads)

@@ -52,5 +52,8 @@ struct ConvParams {
 
 size_t conv_smem_bytes(const ConvParams& p);
 cudaError_t launch_conv(const ConvParams& p, int grid, cudaStream_t stream);
+// row-stacked kernel (pnp_conv_rows.cu): weights packed as [dx][dy sub-block][tap_n rows]
+size_t conv_rows_smem_bytes(const ConvParams& p);
+cudaError_t launch_conv_rows(const ConvParams& p, int grid, cudaStream_t stream);
 
 }  // namespace pnp

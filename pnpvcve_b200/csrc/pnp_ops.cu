@@ -175,6 +175,35 @@ pack_conv3x3_kernel(const float* __restrict__ w, int n_experts, const float* __r
   *reinterpret_cast<__nv_bfloat16*>(dst + packed_offset(block, row, col)) = __float2bfloat16_rn(acc);
 }
 
+// Row-stacked layout of pnp_conv_rows.cu: per dx one block of 3*tap_n rows, sub-block sb = 0,1,2
+// holding the weights of ky = 2 - sb (dy = +1, 0, -1); rows are 128-byte, 128B-swizzled.
+__global__ void __launch_bounds__(256)
+pack_conv3x3_rowstack_kernel(const float* __restrict__ w, int n_experts, const float* __restrict__ coef,
+                             int out_ch, int in_total, int in_begin, int in_begin2, int in_count,
+                             uint8_t* __restrict__ dst, int tap_n) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_dx = 3 * tap_n * 64;
+  if (idx >= 3 * per_dx) return;
+  const int dxi = idx / per_dx;
+  const int rem = idx - dxi * per_dx;
+  const int col = rem & 63, r = rem >> 6;          // r = sb * tap_n + o
+  const int sb = r / tap_n, o = r - sb * tap_n;
+  const int ky = 2 - sb, kx = dxi;
+  float acc = 0.f;
+  if (o < out_ch && col < in_count) {
+    const size_t per_expert = (size_t)out_ch * in_total * 9;
+    for (int e = 0; e < n_experts; ++e) {
+      const float ce = coef ? coef[e] : 1.0f;
+      float v = w[e * per_expert + ((size_t)o * in_total + in_begin + col) * 9 + ky * 3 + kx];
+      if (in_begin2 >= 0) v += w[e * per_expert + ((size_t)o * in_total + in_begin2 + col) * 9 + ky * 3 + kx];
+      acc = fmaf(ce, v, acc);
+    }
+  }
+  const size_t off = (size_t)dxi * (3 * tap_n * 128) + (size_t)r * 128 + (size_t)((((col >> 3) ^ (r & 7)) << 4)) +
+                     (size_t)(col & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(dst + off) = __float2bfloat16_rn(acc);
+}
+
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const float* __restrict__ w, int rows, int cols, long long row_stride, long long col_stride,
                  uint8_t* __restrict__ dst, int row_offset) {
@@ -208,6 +237,15 @@ cudaError_t launch_pack_conv3x3(const float* w, int n_experts, const float* coef
   pack_conv3x3_kernel<<<(9 * 64 * 64 + 255) / 256, 256, 0, stream>>>(
       w, n_experts, coef, out_ch, in_total, in_begin, in_begin2, in_count, reinterpret_cast<uint8_t*>(dst),
       center_chunks);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, int out_ch,
+                                         int in_total, int in_begin, int in_begin2, int in_count, void* dst,
+                                         int tap_n, cudaStream_t stream) {
+  const int total = 3 * 3 * tap_n * 64;
+  pack_conv3x3_rowstack_kernel<<<(total + 255) / 256, 256, 0, stream>>>(
+      w, n_experts, coef, out_ch, in_total, in_begin, in_begin2, in_count, reinterpret_cast<uint8_t*>(dst), tap_n);
   return cudaGetLastError();
 }
 

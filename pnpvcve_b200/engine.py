@@ -66,7 +66,9 @@ class _Launcher:
 
     def __call__(self, stream, src, wpack, out=None, aux=None, idt=None, scale=None, bias=None,
                  par=None, act=PNP_ACT_NONE, lq=None, outf=None, label=None):
-        ops.fill_conv_desc(self.desc, src, wpack, out, aux, idt, scale, bias, par, act, lq, outf)
+        # every conv without partition modulation uses the row-stacked weight layout (N=192 MMAs)
+        ops.fill_conv_desc(self.desc, src, wpack, out, aux, idt, scale, bias, par, act, lq, outf,
+                           wlayout=0 if par is not None else 1)
         timed = self.prof is not None and label in self.prof
         if timed:
             e0 = torch.cuda.Event(enable_timing=True)
@@ -118,8 +120,8 @@ class BaeEngine:
             # K slices of the 131/195-channel input conv: [0:3] lr, [3:67] key_warp, [67:131] neighbour,
             # [131:195] backward feature (iconvsr_ipb_par.py:90,125)
             def pack(in_begin, in_begin2=-1, with_aux=False, w_in=w_in):
-                buf = ops.new_wpack(10 if with_aux else 9, dev)
-                ops.pack_conv3x3(w_in, buf, in_begin=in_begin, in_begin2=in_begin2, in_count=64)
+                buf = ops.new_wpack_rowstack(dev, with_aux=with_aux)
+                ops.pack_conv3x3_rowstack(w_in, buf, in_begin=in_begin, in_begin2=in_begin2, in_count=64)
                 if with_aux:
                     ops.pack_aux(w_in, buf[9 * ops.CHUNK_BYTES:])
                 return buf
@@ -134,8 +136,8 @@ class BaeEngine:
                 st["fwd_nb"] = pack(67)
             conv1_w, conv1_b, c2w, c2b, onebyone = [], [], [], [], []
             for blk in branch.main:
-                buf = ops.new_wpack(9, dev)
-                ops.pack_conv3x3(f32(blk.conv1.weight), buf)
+                buf = ops.new_wpack_rowstack(dev)
+                ops.pack_conv3x3_rowstack(f32(blk.conv1.weight), buf)
                 conv1_w.append(buf)
                 conv1_b.append(f32(blk.conv1.bias))
                 c2w.append(f32(blk.conv2.weight))
@@ -146,11 +148,11 @@ class BaeEngine:
             st[name + "_conv2_w"], st[name + "_1x1"] = c2w, onebyone
             st[name + "_conv2_bias"] = torch.stack(c2b, 0).contiguous()      # (nb, E, 64)
         st["conv2_bias_all"] = torch.cat([st["bwd_conv2_bias"], st["fwd_conv2_bias"]], 0).contiguous()
-        hr = ops.new_wpack(9, dev)
-        ops.pack_conv3x3(f32(m.conv_hr.weight), hr)
+        hr = ops.new_wpack_rowstack(dev)
+        ops.pack_conv3x3_rowstack(f32(m.conv_hr.weight), hr)
         st["hr_w"], st["hr_b"] = hr, f32(m.conv_hr.bias)
-        last = ops.new_wpack(9, dev)
-        ops.pack_conv3x3(f32(m.conv_last.weight), last)
+        last = ops.new_wpack_rowstack(dev, tap_n=16)
+        ops.pack_conv3x3_rowstack(f32(m.conv_last.weight), last, tap_n=16)
         st["last_w"], st["last_b"] = last, f32(m.conv_last.bias)
         st["caa"] = dict(b0w=f32(m.BasePredictor.BaseNet[0].weight), b0b=f32(m.BasePredictor.BaseNet[0].bias),
                          b2w=f32(m.BasePredictor.BaseNet[2].weight), b2b=f32(m.BasePredictor.BaseNet[2].bias),

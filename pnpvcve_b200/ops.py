@@ -91,6 +91,30 @@ def pack_conv3x3(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=None, cen
                                     _ptr(dst), center_chunks, _stream()), "pnp_pack_conv3x3")
 
 
+def rowstack_bytes(tap_n=64, with_aux=False):
+    """Size of a row-stacked weight pack (see pnp_pack_conv3x3_rowstack)."""
+    return 9 * tap_n * 128 + (CHUNK_BYTES if with_aux else 0)
+
+
+def new_wpack_rowstack(device, tap_n=64, with_aux=False):
+    n = (rowstack_bytes(tap_n, with_aux) + 1023) // 1024 * 1024
+    return torch.zeros(n, dtype=torch.uint8, device=device)
+
+
+def pack_conv3x3_rowstack(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=None, tap_n=64):
+    """w fp32 (O,I,3,3) or (E,O,I,3,3) -> row-stacked blocks [kx][ky=2,1,0][tap_n rows] in dst."""
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        raise ValueError("pack_conv3x3_rowstack: w must be contiguous fp32")
+    if w.dim() == 4:
+        e, (o, i) = 1, w.shape[:2]
+    else:
+        e, o, i = w.shape[:3]
+    in_count = i - in_begin if in_count is None else in_count
+    lib = _lib.load()
+    _lib.check(lib.pnp_pack_conv3x3_rowstack(_ptr(w), e, _ptr(coef), o, i, in_begin, in_begin2, in_count,
+                                             _ptr(dst), tap_n, _stream()), "pnp_pack_conv3x3_rowstack")
+
+
 def pack_rows(w2d, dst, row_offset):
     """fp32 (rows<=64, cols<=64) view -> packed rows row_offset.. of dst."""
     if w2d.dtype != torch.float32 or w2d.dim() != 2:
@@ -133,7 +157,7 @@ def mix_bias(conv2_bias, experts, gamma):
 
 
 def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
-                   act=PNP_ACT_NONE, lq=None, outf=None):
+                   act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0):
     """Fill a ConvDesc in place (reusable across launches)."""
     n, h, w, _ = src.shape
     last = outf is not None
@@ -160,11 +184,12 @@ def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias
     d.n_wchunks = (4 if par is not None else 1) + 8 + (1 if aux is not None else 0)
     d.act = act
     d.mode = PNP_CONV_LAST if last else PNP_CONV_BF16
+    d.wlayout = wlayout
     return d
 
 
 def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
-            act=PNP_ACT_NONE, lq=None, outf=None):
+            act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0):
     """Fused tcgen05 3x3 conv (see include/pnp_vcve.h: pnp_conv3x3)."""
     _feat_check(src, "src")
     for t, nm in ((out, "out"), (aux, "aux"), (idt, "idt")):
@@ -178,8 +203,9 @@ def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par
             if t.dim() != 4 or t.shape[1] != 3 or t.shape[0] != src.shape[0] or \
                     tuple(t.shape[2:]) != tuple(src.shape[1:3]):
                 raise ValueError(f"conv3x3: {nm} must be (N,3,H,W) matching src")
-    d = fill_conv_desc(ConvDesc(), src, wpack, out, aux, idt, scale, bias, par, act, lq, outf)
-    if wpack.numel() < d.n_wchunks * CHUNK_BYTES:
+    d = fill_conv_desc(ConvDesc(), src, wpack, out, aux, idt, scale, bias, par, act, lq, outf, wlayout)
+    need = rowstack_bytes(d.tap_n, aux is not None) if wlayout == 1 else d.n_wchunks * CHUNK_BYTES
+    if wpack.numel() < need:
         raise ValueError("conv3x3: packed weight buffer too small for this configuration")
     lib = _lib.load()
     _lib.check(lib.pnp_conv3x3(ctypes.byref(d), _stream()), "pnp_conv3x3")

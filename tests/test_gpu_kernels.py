@@ -99,8 +99,21 @@ def test_mv_warp_rejects_bad_arguments(dev):
 SHAPES = [(1, 64, 64), (1, 68, 132), (2, 72, 200), (1, 180, 320), (1, 376, 1244)]
 
 
+def _pack(wt, dev, layout, **kw):
+    """Pack a 3x3 conv in the tap-major (0) or row-stacked (1) weight layout."""
+    if layout == 0:
+        wp = ops.new_wpack(10, dev)
+        ops.pack_conv3x3(wt, wp, **kw)
+    else:
+        tap_n = 16 if wt.shape[-4] <= 16 else 64
+        wp = ops.new_wpack_rowstack(dev, tap_n=tap_n, with_aux=True)
+        ops.pack_conv3x3_rowstack(wt, wp, tap_n=tap_n, **kw)
+    return wp
+
+
+@pytest.mark.parametrize("layout", [0, 1], ids=["tapmajor", "rowstack"])
 @pytest.mark.parametrize("n,h,w", SHAPES)
-def test_conv_variants_match_fp32_conv2d(dev, n, h, w):
+def test_conv_variants_match_fp32_conv2d(dev, n, h, w, layout):
     g = torch.Generator(device=dev).manual_seed(n * 100000 + h * 1000 + w)
     x = bf(torch.randn((n, 64, h, w), generator=g, device=dev))
     wt = bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05)
@@ -108,58 +121,55 @@ def test_conv_variants_match_fp32_conv2d(dev, n, h, w):
     scale = torch.rand(64, generator=g, device=dev) + 0.5
     xs = nhwc(x)
     ref0 = F.conv2d(x, wt, padding=1)
-    wp = ops.new_wpack(9, dev)
-    ops.pack_conv3x3(wt, wp)
+    wp = _pack(wt, dev, layout)
     out = ops.new_feature(n, h, w, dev)
 
-    ops.conv3x3(xs, wp, out=out)
+    ops.conv3x3(xs, wp, out=out, wlayout=layout)
     assert_bf16_close(nchw(out), ref0, "plain")
-    ops.conv3x3(xs, wp, out=out, bias=bias, act=ops.PNP_ACT_LRELU)
+    ops.conv3x3(xs, wp, out=out, bias=bias, act=ops.PNP_ACT_LRELU, wlayout=layout)
     assert_bf16_close(nchw(out), F.leaky_relu(ref0 + bias.view(1, -1, 1, 1), 0.1), "bias+lrelu")
     idt = bf(torch.randn((n, 64, h, w), generator=g, device=dev))
-    ops.conv3x3(xs, wp, out=out, bias=bias, scale=scale, idt=nhwc(idt), act=ops.PNP_ACT_RELU)
+    ops.conv3x3(xs, wp, out=out, bias=bias, scale=scale, idt=nhwc(idt), act=ops.PNP_ACT_RELU, wlayout=layout)
     assert_bf16_close(nchw(out), F.relu(ref0 * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1) + idt),
                       "scale+bias+id+relu")
 
     # LR frame through the im2col'd aux operand == the first 3 input channels of a 131-ch conv
     lr = torch.rand((n, 3, h, w), generator=g, device=dev)
     w_in = bf(torch.randn((64, 131, 3, 3), generator=g, device=dev) * 0.05)
-    wpa = ops.new_wpack(10, dev)
-    ops.pack_conv3x3(w_in, wpa, in_begin=3, in_count=64)
+    wpa = _pack(w_in, dev, layout, in_begin=3, in_count=64)
     ops.pack_aux(w_in, wpa[9 * ops.CHUNK_BYTES:])
     lr64 = ops.new_feature(n, h, w, dev, zero=True)
     ops.lr_im2col(lr, lr64)
-    ops.conv3x3(xs, wpa, out=out, aux=lr64, bias=bias, act=ops.PNP_ACT_LRELU)
+    ops.conv3x3(xs, wpa, out=out, aux=lr64, bias=bias, act=ops.PNP_ACT_LRELU, wlayout=layout)
     ref = F.leaky_relu(F.conv2d(torch.cat([bf(lr), x], 1), w_in[:, :67], bias, padding=1), 0.1)
     assert_bf16_close(nchw(out), ref, "aux")
 
     # merged K slices (neighbour == key_warp): weights of two input slices summed
-    wpm = ops.new_wpack(9, dev)
-    ops.pack_conv3x3(w_in, wpm, in_begin=3, in_begin2=67, in_count=64)
-    ops.conv3x3(xs, wpm, out=out)
+    wpm = _pack(w_in, dev, layout, in_begin=3, in_begin2=67, in_count=64)
+    ops.conv3x3(xs, wpm, out=out, wlayout=layout)
     assert_bf16_close(nchw(out), F.conv2d(x, bf(w_in[:, 3:67] + w_in[:, 67:131]), padding=1), "merged")
 
-    # 3x3 + three partition-modulated 1x1 convs, general (non one-hot) float partition map
-    par = torch.rand((n, 3, h, w), generator=g, device=dev) * \
-        (torch.rand((n, 3, h, w), generator=g, device=dev) > 0.5)
-    w1 = [bf(torch.randn((64, 64), generator=g, device=dev) * 0.1) for _ in range(3)]
-    wpp = ops.new_wpack(12, dev)
-    ops.pack_conv3x3(wt, wpp, center_chunks=4)
-    for j in range(3):
-        ops.pack_rows(w1[j], wpp, 64 * (j + 1))
-    ops.conv3x3(xs, wpp, out=out, scale=scale, bias=bias, par=par, act=ops.PNP_ACT_RELU)
-    ref = ref0 * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
-    for j in range(3):
-        ref = ref + F.conv2d(x, w1[j].view(64, 64, 1, 1)) * par[:, j:j + 1]
-    assert_bf16_close(nchw(out), F.relu(ref), "par")
+    if layout == 0:
+        # 3x3 + three partition-modulated 1x1 convs, general (non one-hot) float partition map
+        par = torch.rand((n, 3, h, w), generator=g, device=dev) * \
+            (torch.rand((n, 3, h, w), generator=g, device=dev) > 0.5)
+        w1 = [bf(torch.randn((64, 64), generator=g, device=dev) * 0.1) for _ in range(3)]
+        wpp = ops.new_wpack(12, dev)
+        ops.pack_conv3x3(wt, wpp, center_chunks=4)
+        for j in range(3):
+            ops.pack_rows(w1[j], wpp, 64 * (j + 1))
+        ops.conv3x3(xs, wpp, out=out, scale=scale, bias=bias, par=par, act=ops.PNP_ACT_RELU)
+        ref = ref0 * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+        for j in range(3):
+            ref = ref + F.conv2d(x, w1[j].view(64, 64, 1, 1)) * par[:, j:j + 1]
+        assert_bf16_close(nchw(out), F.relu(ref), "par")
 
     # reconstruction tail: 64 -> 3, + lq, fp32 NCHW output
     wl = bf(torch.randn((3, 64, 3, 3), generator=g, device=dev) * 0.05)
     bl = torch.randn(3, generator=g, device=dev) * 0.1
-    wpl = ops.new_wpack(9, dev)
-    ops.pack_conv3x3(wl, wpl)
+    wpl = _pack(wl, dev, layout)
     outf = torch.empty((n, 3, h, w), device=dev)
-    ops.conv3x3(xs, wpl, bias=bl, lq=lr, outf=outf)
+    ops.conv3x3(xs, wpl, bias=bl, lq=lr, outf=outf, wlayout=layout)
     assert (outf - (F.conv2d(x, wl, bl, padding=1) + lr)).abs().max().item() < 1e-4
 
 
@@ -177,7 +187,8 @@ def test_conv_expert_mixing_matches_reference_formula(dev):
     assert_bf16_close(nchw(out), F.conv2d(x, bf(mixed), padding=1), "expert mix")
 
 
-def test_conv_full_720p_linearity_and_identity(dev):
+@pytest.mark.parametrize("layout", [0, 1], ids=["tapmajor", "rowstack"])
+def test_conv_full_720p_linearity_and_identity(dev, layout):
     """Size-independent properties at the full REDS4 shape: identity kernel and linearity."""
     g = torch.Generator(device=dev).manual_seed(5)
     h, w = 720, 1280
@@ -185,19 +196,18 @@ def test_conv_full_720p_linearity_and_identity(dev):
     y = nhwc(bf(torch.randn((1, 64, h, w), generator=g, device=dev)))
     eye = torch.zeros((64, 64, 3, 3), device=dev)
     eye[:, :, 1, 1] = torch.eye(64, device=dev)
-    wp = ops.new_wpack(9, dev)
-    ops.pack_conv3x3(eye, wp)
+    wp = _pack(eye, dev, layout)
     out = ops.new_feature(1, h, w, dev)
-    ops.conv3x3(x, wp, out=out)
+    ops.conv3x3(x, wp, out=out, wlayout=layout)
     assert torch.equal(out, x)
     # conv(x) + y through the id operand with the identity kernel == x + y (bf16 rounded once)
-    ops.conv3x3(x, wp, out=out, idt=y)
+    ops.conv3x3(x, wp, out=out, idt=y, wlayout=layout)
     assert torch.equal(out, (x.float() + y.float()).to(torch.bfloat16))
     # shift kernel: tap (0,2) moves the image one pixel left with zero fill at the right edge
     sh = torch.zeros((64, 64, 3, 3), device=dev)
     sh[:, :, 0, 2] = torch.eye(64, device=dev)
-    ops.pack_conv3x3(sh, wp)
-    ops.conv3x3(x, wp, out=out)
+    wp = _pack(sh, dev, layout)
+    ops.conv3x3(x, wp, out=out, wlayout=layout)
     exp = torch.zeros_like(x)
     exp[:, 1:, : w - 1] = x[:, : h - 1, 1:]
     assert torch.equal(out, exp)

@@ -6,12 +6,16 @@ from pnpvcve_b200 import ops
 dev = torch.device("cuda:0"); h, w = 720, 1280
 x = torch.randn((1, h, w, 64), device=dev).to(torch.bfloat16)
 out = ops.new_feature(1, h, w, dev)
-wp9 = ops.new_wpack(9, dev); ops.pack_conv3x3(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp9)
+LAYOUT = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+if LAYOUT == 0:
+    wp9 = ops.new_wpack(9, dev); ops.pack_conv3x3(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp9)
+else:
+    wp9 = ops.new_wpack_rowstack(dev); ops.pack_conv3x3_rowstack(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp9)
 trace = torch.zeros(64 * 8, dtype=torch.int64, device=dev)
-for _ in range(3): ops.conv3x3(x, wp9, out=out)
+for _ in range(3): ops.conv3x3(x, wp9, out=out, wlayout=LAYOUT)
 torch.cuda.synchronize()
 os.environ["PNP_TRACE_PTR"] = str(trace.data_ptr())
-ops.conv3x3(x, wp9, out=out)
+ops.conv3x3(x, wp9, out=out, wlayout=LAYOUT)
 torch.cuda.synchronize()
 t = trace.view(64, 8).cpu()
 t0 = int(t[0, 0])
@@ -19,6 +23,11 @@ print("tile  mma_ready  mma_issued | epi_start  acc_full   epi_math   epi_bar   
 prev = None
 for i in range(49):
     r = [int(v) - t0 for v in t[i, :8]]
+    if LAYOUT == 1:
+        d = "" if prev is None else f"  [step period {r[0]-prev[0]:5d}  issue {r[1]-r[0]:4d}  gap {r[0]-prev[1]:4d} | epi period {r[2]-prev[2]:5d} wait {r[3]-r[2]:5d}  math {r[4]-r[3]:4d}  bar {r[5]-r[4]:4d}]"
+        print(f"{i:3d} {r[0]:9d} {r[1]:9d} | {r[2]:9d} {r[3]:9d} {r[4]:9d} {r[5]:9d}{d}")
+        prev = r
+        continue
     d = "" if prev is None else f"  [period {r[0]-prev[0]:5d}  issue {r[1]-r[0]:4d} (4 MMAs +{r[6]-r[0]:4d}, 20 MMAs +{r[7]-r[0]:4d})  gap {r[0]-prev[1]:4d}  accwait {r[3]-r[2]:5d}  math {r[4]-r[3]:4d}  bar {r[5]-r[4]:4d}]"
     print(f"{i:3d} {r[0]:9d} {r[1]:9d} | {r[2]:9d} {r[3]:9d} {r[4]:9d} {r[5]:9d}{d}")
     prev = r

@@ -14,7 +14,7 @@ using namespace pnp;
 // (in 16-byte units) so successive MMAs read different smem (like conv taps / K steps)
 __global__ void __launch_bounds__(128, 1)
 bench_kernel(int n, int n_acc, int per_group, int reps, int a_span, int b_span, int a_shift, int commit_every,
-             long long* out_cycles) {
+             int acc_off, long long* out_cycles) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar;
   __shared__ uint64_t bar2[2];
@@ -54,7 +54,7 @@ bench_kernel(int n, int n_acc, int per_group, int reps, int a_span, int b_span, 
         for (int i0 = 0; i0 < per_group; i0 += inner) {
 #pragma unroll 4
           for (int i = i0; i < i0 + inner; ++i) {   // spans / n_acc are powers of two: mask, no division
-            const uint32_t acc = (uint32_t)(i & (n_acc - 1)) * n;
+            const uint32_t acc = (uint32_t)(i & (n_acc - 1)) * n + (uint32_t)acc_off;
             umma_bf16_lo(tmem + acc, a_lo0 + (uint32_t)((i * 2) & (a_span - 1)), kDescHiSw128,
                          b_lo0 + (uint32_t)((i * 2) & (b_span - 1)), kDescHiSw128, idesc, i >= n_acc);
           }
@@ -71,6 +71,71 @@ bench_kernel(int n, int n_acc, int per_group, int reps, int a_span, int b_span, 
     }
     t1 = clock64();
     if ((threadIdx.x & 31) == 0) out_cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// Replica of one CTA of the row-stacked conv kernel's MMA thread: per step [N=128 acc + N=64 overwrite],
+// optional deferred commit, 11 x N=192, optional `gap_waits` already-complete mbarrier waits between steps.
+__global__ void __launch_bounds__(128, 1)
+step_kernel(int steps, int use_commit, int gap_waits, int spin_warps, long long* out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar, done_bar[8], ready_bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    if (threadIdx.x == 0) {
+      mbar_init(smem_u32(&bar), 1);
+      mbar_init(smem_u32(&ready_bar), 1);
+      for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&done_bar[i]), 1);
+      mbar_fence_init();
+      mbar_arrive(smem_u32(&ready_bar));      // phase 0 complete: waits on parity 0 return at once
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&tmem_slot), 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t id64 = umma_idesc_bf16(128, 64), id128 = umma_idesc_bf16(128, 128),
+                     id192 = umma_idesc_bf16(128, 192);
+      const uint32_t a_lo0 = umma_desc_lo(sbase), b_lo0 = umma_desc_lo(sbase + 96 * 1024);
+      const long long t0 = clock64();
+      bool pend = false;
+      uint32_t pend_bar = 0;
+      for (int sIdx = 0; sIdx < steps; ++sIdx) {
+        for (int g = 0; g < gap_waits; ++g) mbar_wait(smem_u32(&ready_bar), 0, 97);
+        tc_fence_after();
+        const uint32_t slot = (uint32_t)(sIdx & 3) * 64;      // keep N=192 inside 512 columns
+        const uint32_t a_row = a_lo0 + (uint32_t)(sIdx & 3) * 1088;
+        umma_bf16_lo(tmem + slot, a_row, kDescHiSw128, b_lo0, kDescHiSw128, id128, 1);
+        umma_bf16_lo(tmem + slot + 128, a_row, kDescHiSw128, b_lo0 + 1024, kDescHiSw128, id64, 0);
+        if (pend && use_commit) umma_commit(pend_bar);
+#pragma unroll
+        for (int i = 1; i < 12; ++i)
+          umma_bf16_lo(tmem + slot, a_row + (i >> 2) * 8 + 2 * (i & 3), kDescHiSw128,
+                       b_lo0 + (i >> 2) * 1536 + 2 * (i & 3), kDescHiSw128, id192, 1);
+        pend = true;
+        pend_bar = smem_u32(&done_bar[sIdx & 7]);
+      }
+      umma_commit(smem_u32(&bar));
+      mbar_wait(smem_u32(&bar), 0, 96);
+      out_cycles[blockIdx.x] = clock64() - t0;
+    }
+  } else if (warp >= 2 && warp < 2 + spin_warps) {
+    // emulate epilogue warps polling a barrier that never completes until the end
+    while (!mbar_try_wait(smem_u32(&bar), 0)) {
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -137,7 +202,7 @@ int main() {
   long long* d;
   cudaMalloc(&d, sizeof(long long) * sms);
   cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  struct Pat { int n, n_acc, per_group, a_span, b_span; const char* what; int a_shift = 0; int commit_every = 0; };
+  struct Pat { int n, n_acc, per_group, a_span, b_span; const char* what; int a_shift = 0; int commit_every = 0; int acc_off = 0; };
   const Pat pats[] = {
       {64, 1, 36, 4096, 4096, "N=64  1 accumulator, 36 per group (drain each tile)"},
       {64, 1, 144, 4096, 4096, "N=64  1 accumulator, 144 per group"},
@@ -146,7 +211,19 @@ int main() {
       {64, 2, 72, 4096, 4096, "N=64  2 accumulators interleaved"},
       {64, 4, 144, 4096, 4096, "N=64  4 accumulators interleaved"},
       {64, 1, 144, 2, 2, "N=64  1 accumulator, same operands every MMA"},
+      {192, 1, 144, 4096, 2048, "N=192 1 accumulator"},
+      {192, 1, 144, 4096, 2048, "N=192, 1 un-waited commit every 12", 0, 12},
+      {192, 1, 144, 4096, 2048, "N=192 D at column 64", 0, 0, 64},
+      {192, 1, 144, 4096, 2048, "N=192 D at column 128", 0, 0, 128},
+      {192, 1, 144, 4096, 2048, "N=192 D at column 192", 0, 0, 192},
+      {192, 1, 144, 4096, 2048, "N=192 D at column 320", 0, 0, 320},
+      {128, 1, 144, 4096, 4096, "N=128 D at column 64", 0, 0, 64},
+      {128, 1, 144, 4096, 4096, "N=128 D at column 192", 0, 0, 192},
+      {64, 1, 144, 4096, 4096, "N=64  D at column 448", 0, 0, 448},
+      {96, 1, 144, 4096, 4096, "N=96  1 accumulator"},
+      {160, 1, 144, 4096, 2048, "N=160 1 accumulator"},
       {128, 1, 144, 4096, 4096, "N=128 1 accumulator"},
+      {128, 1, 144, 4096, 4096, "N=128, 2 un-waited commits every 12", 0, 12},
       {128, 2, 72, 4096, 4096, "N=128 2 accumulators interleaved"},
       {256, 1, 144, 4096, 2048, "N=256 1 accumulator"},
       {256, 2, 72, 4096, 2048, "N=256 2 accumulators interleaved"},
@@ -169,9 +246,24 @@ int main() {
     for (int i = 1; i <= 24; ++i) printf(" %lld", h[i]);
     printf("\n");
   }
+  cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  struct SP { int commit, gaps, spin; const char* what; };
+  const SP sps[] = {{0, 0, 0, "steps: no commit, no gap"},       {1, 0, 0, "steps: deferred commit, no gap"},
+                    {0, 4, 0, "steps: no commit, 4 waits gap"},  {1, 4, 0, "steps: deferred commit, 4 waits gap"},
+                    {1, 4, 2, "steps: commit + gap + 2 polling warps"}, {1, 2, 0, "steps: deferred commit, 2 waits gap"}};
+  for (const SP& sp : sps) {
+    step_kernel<<<sms, 128, 200 * 1024>>>(200, sp.commit, sp.gaps, sp.spin, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s: %s\n", sp.what, cudaGetErrorString(e)); return 1; }
+    long long h[256];
+    cudaMemcpy(h, d, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+    double mean = 0;
+    for (int i = 0; i < sms; ++i) mean += (double)h[i];
+    printf("%-48s %7.0f cycles/step (ideal 12 x 98.6 + 18 = 1201)\n", sp.what, mean / sms / 200.0);
+  }
   const int reps = 200;
   for (const Pat& p : pats) {
-    bench_kernel<<<sms, 128, 200 * 1024>>>(p.n, p.n_acc, p.per_group, reps, p.a_span, p.b_span, p.a_shift, p.commit_every, d);
+    bench_kernel<<<sms, 128, 200 * 1024>>>(p.n, p.n_acc, p.per_group, reps, p.a_span, p.b_span, p.a_shift, p.commit_every, p.acc_off, d);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
       printf("%s: %s\n", p.what, cudaGetErrorString(e));
