@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--frames", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prof-every", type=int, default=8,
+                    help="bracket every N-th launch of the profiled kernels with CUDA events")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -227,6 +229,7 @@ def main():
             step_resident(i)
         barrier()
         net._engine.prof = {"block_a": [], "warp": [], "block_b": []}
+        net._engine.prof_every = args.prof_every
         sampler = ClockSampler(local_rank) if rank == 0 else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches = 0
@@ -253,12 +256,13 @@ def main():
     a_tflops = FLOP_BLOCK_A_PER_PX * H * W / (a_ms * 1e-3) / 1e12 if a_ms else 0.0
     w_gbs = WARP_BYTES_PER_PX * H * W / (w_ms * 1e-3) / 1e9 if w_ms else 0.0
     steps_ms = total_ms / args.steps
-    share_a = a_ms * len(prof["block_a"]) / args.steps / steps_ms if a_ms else 0.0
+    share_a = a_ms * len(prof["block_a"]) * args.prof_every / args.steps / steps_ms if a_ms else 0.0
     roofline = dict(bound="tensor", kernel="conv3x3_umma_kernel (block launch A: 3x3 + 3 partition 1x1, N=256 centre tap)",
                     achieved=a_tflops, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
                     frac=a_tflops / peaks["bf16_tflops_sustained"], traffic=None,
                     peak_source=f"{peaks['source']} sustained cuBLAS bf16 (kernel timed inside a long step)",
-                    ms_per_launch=a_ms, launches_timed=len(prof["block_a"]), share_of_step=share_a,
+                    ms_per_launch=a_ms, launches_timed=len(prof["block_a"]), timed_every=args.prof_every,
+                    share_of_step=share_a,
                     whole_path_tflops=FLOP_PER_PX_FRAME * H * W * value / 1e12,
                     whole_path_frac=FLOP_PER_PX_FRAME * H * W * value / 1e12 / peaks["bf16_tflops_sustained"])
     roofline_warp = dict(bound="hbm", kernel="mv_warp_kernel", achieved=w_gbs, peak=peaks["hbm_gbs"],

@@ -139,8 +139,10 @@ typedef struct pnp_conv_desc {
   int32_t aux_k16;     /* K/16 of aux (2 for the 27-entry LR im2col), 0 without aux */
   int32_t act;
   int32_t mode;
-  int32_t wlayout;     /* PNP_WLAYOUT_TAPMAJOR (n_wchunks blocks, required with par) or PNP_WLAYOUT_ROWSTACK
-                          (9*tap_n*128 bytes, followed by the 8192-byte aux block when aux is given) */
+  int32_t wlayout;     /* PNP_WLAYOUT_TAPMAJOR (n_wchunks blocks) or PNP_WLAYOUT_ROWSTACK (9*tap_n*128 bytes,
+                          followed by the 8192-byte aux block when aux is given, or by the three 1x1
+                          partition convs as 192 packed rows (pnp_pack_rows, offsets 0/64/128 from there)
+                          when par is given; par then excludes aux and idt) */
 } pnp_conv_desc;
 
 int pnp_conv3x3(const pnp_conv_desc* desc, void* stream);

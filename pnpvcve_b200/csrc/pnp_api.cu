@@ -240,8 +240,8 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   if (c->aux && c->center_n == 256) return fail(PNP_ERR_ARG, "pnp_conv3x3: aux and par are exclusive");
   const bool rowstack = (c->wlayout == PNP_WLAYOUT_ROWSTACK);
   if (c->wlayout != PNP_WLAYOUT_TAPMAJOR && !rowstack) return fail(PNP_ERR_ARG, "pnp_conv3x3: bad wlayout");
-  if (rowstack && c->center_n != c->tap_n)
-    return fail(PNP_ERR_ARG, "pnp_conv3x3: the row-stacked layout does not carry the partition 1x1 convs");
+  if (rowstack && c->center_n == 256 && (c->aux || c->idt))
+    return fail(PNP_ERR_ARG, "pnp_conv3x3: row-stacked layout with partition convs takes no aux / idt");
   const int center_chunks = (c->center_n == 256) ? 4 : 1;
   const int need_chunks = center_chunks + 8 + (c->aux ? 1 : 0);
   if (!rowstack && c->n_wchunks != need_chunks)
@@ -296,7 +296,8 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   // With an identity operand the staging ring also prefetches identity tiles (n_io - 2 tiles ahead),
   // so it gets 4 slots as long as 5 source rows (3 in use + 2 in flight) still fit.
   const long long budget = 232448 - 2048;
-  const long long w_bytes = rowstack ? (((long long)9 * c->tap_n * 128 + (c->aux ? pnp::kWChunkBytes : 0) + 1023) & ~1023LL)
+  const long long w_bytes = rowstack ? (((long long)9 * c->tap_n * 128 + (c->aux ? pnp::kWChunkBytes : 0) +
+                                         (c->center_n == 256 ? 3 * 64 * 128 : 0) + 1023) & ~1023LL)
                                      : (long long)p.n_wchunks * pnp::kWChunkBytes;
   auto fixed_bytes = [&](int n_io) {
     return w_bytes + (c->aux ? 2 * pnp::kTileBytes : 0) + (long long)n_io * pnp::kTileBytes;

@@ -54,6 +54,7 @@ struct Misc {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
+  uint32_t go_tile;                // scout -> MMA: tiles whose barriers have all completed
 };
 static_assert(sizeof(Misc) <= 1024, "misc region overflow");
 
@@ -105,7 +106,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }  // namespace
 
 template <bool kPar, bool kScale>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kRowsThreads, 1)
 conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -138,12 +139,13 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
         mbar_init(smem_u32(&misc->aux_full[i]), 1);
         mbar_init(smem_u32(&misc->aux_empty[i]), 1);
         mbar_init(smem_u32(&misc->acc_full[i]), 1);
-        mbar_init(smem_u32(&misc->acc_empty[i]), kConvThreads - 64);
+        mbar_init(smem_u32(&misc->acc_empty[i]), kEpilogueWarps);
       }
       for (int i = 0; i < kMaxIoSlots; ++i) {
         mbar_init(smem_u32(&misc->id_full[i]), 1);
         mbar_init(smem_u32(&misc->io_empty[i]), 1);
       }
+      misc->go_tile = 0;
       mbar_fence_init();
       tma_prefetch_desc(&p.tm_src);
       if (p.mode != kModeLast) tma_prefetch_desc(&p.tm_out);
@@ -155,6 +157,11 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = misc->tmem_base;
+  // Programmatic dependent launch: launch latency, block scheduling and the prologue above overlap
+  // the tail of the previous kernel in the stream; nothing below touches global memory before the
+  // previous kernel has completed (packed weights may have been written by the kernel just before).
+  griddep_launch_dependents();
+  griddep_wait();
 
   const uint32_t w_smem = sbase + L.w;
   const uint32_t a_smem = sbase + L.a;
@@ -223,28 +230,28 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
       };
       Ring ar(s_a);
       TileIter ti(p, t_begin, t_end);
-      auto acquire = [&](TileCtx& c, const TileCtx& prev) {   // waits + ring slots of the tile at `ti`
+      const uint32_t go_tile = smem_u32(&misc->go_tile);
+      auto acquire = [&](TileCtx& c, const TileCtx& prev) {   // ring slots of the tile at `ti`
         c.valid = ti.valid();
         if (!c.valid) return;
         if (ti.first()) {
-          mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
           c.s0 = ar.slot;
           ar.advance();
-          mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
           c.s1 = ar.slot;
           ar.advance();
         } else {
           c.s0 = prev.s1;
           c.s1 = prev.s2;
         }
-        mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
         c.s2 = ar.slot;
         ar.advance();
         c.it = prev.it + 1;
         c.b = c.it & 1;
         c.last = ti.last();
-        mbar_wait(smem_u32(&misc->acc_empty[c.b]), ((c.it >> 1) & 1) ^ 1, 6);
-        if (p.aux_k16 > 0) mbar_wait(smem_u32(&misc->aux_full[c.b]), (c.it >> 1) & 1, 7);
+        // every mbarrier this tile depends on (source rows, accumulator buffer, aux tile) has been
+        // waited for by the scout warp; an acquire load of its counter costs ~30 cycles, an
+        // already-complete mbarrier wait 220-290 in this kernel
+        spin_until_ge(go_tile, c.it + 1, 5);
       };
       auto commit_tile = [&](const TileCtx& c) {
         umma_commit(smem_u32(&misc->a_empty[c.s0]));
@@ -317,6 +324,22 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
       }
       if (pend) commit_tile(pend_ctx);
     }
+  } else if (warp == 10) {
+    // ============================================================ barrier scout (one elected lane)
+    if (elect_one()) {
+      const uint32_t go_tile = smem_u32(&misc->go_tile);
+      Ring ar(s_a);
+      uint32_t it = 0;
+      for (TileIter c(p, t_begin, t_end); c.valid(); c.next(), ++it) {
+        const int rows = c.first() ? 3 : 1;
+        for (int r = 0; r < rows; ++r, ar.advance())
+          mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
+        const uint32_t b = it & 1;
+        mbar_wait(smem_u32(&misc->acc_empty[b]), ((it >> 1) & 1) ^ 1, 6);
+        if (p.aux_k16 > 0) mbar_wait(smem_u32(&misc->aux_full[b]), (it >> 1) & 1, 7);
+        st_release_shared(go_tile, it + 1);
+      }
+    }
   } else {
     // ============================================================ epilogue (8 warps, 256 threads)
     // A warp may only read the TMEM lane quarter (warp % 4); the two warps of a quarter split the
@@ -358,7 +381,7 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
           tmem_ld_wait();
         }
         tc_fence_before();
-        mbar_arrive(smem_u32(&misc->acc_empty[b]));
+        warp_arrive(smem_u32(&misc->acc_empty[b]));
         if (valid && half == 0) {
           float* op = p.outf + (long long)c.n * p.of_sn + (long long)c.y * p.of_sy + x;
           op[0] = v[0] + misc->bias[0] + r0;
@@ -455,7 +478,7 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
         }
       }
       tc_fence_before();
-      mbar_arrive(smem_u32(&misc->acc_empty[b]));
+      warp_arrive(smem_u32(&misc->acc_empty[b]));
       if (tr) p.trace[it * 8 + 4] = clock64();
       fence_proxy_async_smem();
       named_bar_sync(2, 256);
@@ -505,8 +528,17 @@ cudaError_t launch_variant(const ConvParams& p, int grid, size_t smem, cudaStrea
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  conv3x3_umma_kernel<kPar, kScale><<<grid, kConvThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kRowsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv3x3_umma_kernel<kPar, kScale>, p);
 }
 }  // namespace
 

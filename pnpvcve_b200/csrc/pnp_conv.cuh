@@ -12,6 +12,8 @@ constexpr int kASlotBytes = 17 * 1024;       // ring slot (1024-aligned, >= kRow
 constexpr int kTileBytes = kTilePx * 128;    // 16384: one 128-pixel x 64-channel bf16 tile
 constexpr int kWChunkBytes = 8192;           // one 64(N) x 64(K) bf16 weight block
 constexpr int kConvThreads = 320;            // warp0 TMA producer, warp1 MMA issuer, warps2-9 epilogue
+constexpr int kRowsThreads = 352;            // row-stacked kernel: + warp10 barrier scout
+constexpr int kEpilogueWarps = 8;
 constexpr int kMaxASlots = 8;
 constexpr int kMaxIoSlots = 4;
 constexpr int kTmemCols = 512;

@@ -9,8 +9,12 @@
 // (8 x 64 columns = all 512), each source row is staged in shared memory for exactly one step, and
 // an output row is finished -- and handed to the epilogue -- one step after its own source row.
 //
-// Same reference semantics as pnp_conv.cu (F.conv2d + bias/activation/identity/LR-aux/+lq fused);
-// the partition-modulated block launch (center_n == 256) stays on the tap-major kernel for now.
+// Same reference semantics as pnp_conv.cu (F.conv2d + bias/activation/identity/LR-aux/+lq fused).
+//
+// kPar (block launch A of ResidualBlockNoBNDynamic_drt, sr_backbone_utils.py:310-311): the three
+// partition-modulated 1x1 convs are one extra N=192 MMA group on the centre row into a dedicated
+// 192-column TMEM region; the epilogue folds sum_k par_k * conv1x1_k(x) into registers one step
+// ahead of the 3x3 result (accumulator ring shrinks to 5 x 64 columns to make room).
 #include "pnp_conv.cuh"
 #include "pnp_ptx.cuh"
 
@@ -18,8 +22,9 @@ namespace pnp {
 
 namespace {
 
-constexpr int kAccRing = 8;      // output-row accumulators in TMEM
+constexpr int kAccRingMax = 8;   // output-row accumulators in TMEM (8 x 64 columns; 5 with kPar)
 constexpr int kStepRing = 8;     // step-completion barriers
+constexpr int kParCol = 320;     // TMEM column of the partition 1x1 accumulators (3 x 64)
 
 struct RowsLayout {
   uint32_t w, a, aux, io, misc, total;
@@ -42,11 +47,15 @@ struct RowsMisc {
   uint64_t w_full;
   uint64_t a_full[kMaxASlots];
   uint64_t step_done[kStepRing];   // tcgen05.commit after every step (one source row)
-  uint64_t acc_free[kAccRing];     // epilogue -> MMA: accumulator slot drained
+  uint64_t acc_free[kAccRingMax];  // epilogue -> MMA: accumulator slot drained
+  uint64_t par_done;               // MMA -> epilogue: partition 1x1 accumulators of a row are ready
+  uint64_t par_free;               // epilogue -> MMA: ... and have been read
   uint64_t aux_full[2];
   uint64_t id_full[kMaxIoSlots];
   uint64_t io_empty[kMaxIoSlots];
   uint32_t tmem_base;
+  uint32_t go_step;                // scout -> MMA: steps whose barriers have all completed
+  uint32_t go_par;                 // scout -> MMA: rows whose partition accumulators may be overwritten
 };
 static_assert(sizeof(RowsMisc) <= 1024, "misc region overflow");
 
@@ -104,16 +113,17 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 
 }  // namespace
 
-template <bool kScale>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <bool kPar, bool kScale>
+__global__ void __launch_bounds__(kRowsThreads, 1)
 conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int kAccRing = kPar ? 5 : 8;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - raw);
   const int tap_n = p.tap_n;                            // 64, or 16 for the 64->3 tail
   const int dx_block_bytes = 3 * tap_n * 128;           // [3 dy sub-blocks][tap_n rows][128 B]
-  const int w_bytes = 3 * dx_block_bytes + (p.aux_k16 > 0 ? kWChunkBytes : 0);
+  const int w_bytes = 3 * dx_block_bytes + (p.aux_k16 > 0 ? kWChunkBytes : 0) + (kPar ? 3 * 64 * 128 : 0);
   const RowsLayout L = rows_layout(w_bytes, p.s_a, p.aux_k16 > 0, p.n_io);
   RowsMisc* misc = reinterpret_cast<RowsMisc*>(sgen + L.misc);
 
@@ -135,12 +145,16 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       mbar_init(smem_u32(&misc->w_full), 1);
       for (int i = 0; i < kMaxASlots; ++i) mbar_init(smem_u32(&misc->a_full[i]), 1);
       for (int i = 0; i < kStepRing; ++i) mbar_init(smem_u32(&misc->step_done[i]), 1);
-      for (int i = 0; i < kAccRing; ++i) mbar_init(smem_u32(&misc->acc_free[i]), kConvThreads - 64);
+      for (int i = 0; i < kAccRingMax; ++i) mbar_init(smem_u32(&misc->acc_free[i]), kEpilogueWarps);
+      mbar_init(smem_u32(&misc->par_done), 1);
+      mbar_init(smem_u32(&misc->par_free), kEpilogueWarps);
       for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&misc->aux_full[i]), 1);
       for (int i = 0; i < kMaxIoSlots; ++i) {
         mbar_init(smem_u32(&misc->id_full[i]), 1);
         mbar_init(smem_u32(&misc->io_empty[i]), 1);
       }
+      misc->go_step = 0;
+      misc->go_par = 0;
       mbar_fence_init();
       tma_prefetch_desc(&p.tm_src);
       if (!last_mode) tma_prefetch_desc(&p.tm_out);
@@ -152,6 +166,11 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = misc->tmem_base;
+  // Programmatic dependent launch: launch latency, block scheduling and the prologue above overlap
+  // the tail of the previous kernel in the stream; nothing below touches global memory before the
+  // previous kernel has completed (packed weights may have been written by the kernel just before).
+  griddep_launch_dependents();
+  griddep_wait();
   const uint32_t w_smem = sbase + L.w;
   const uint32_t a_smem = sbase + L.a;
   const uint32_t aux_smem = sbase + L.aux;
@@ -166,7 +185,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         const int n = min(kWChunkBytes, w_bytes - off);
         bulk_load_1d(w_smem + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, n, wbar);
       }
-      Ring ar(s_a), ior(n_io);
+      Ring ar(s_a);
       uint32_t sc = 0, ord = 0;            // step counter, output-row ordinal
       uint32_t aux_step[2] = {0, 0};       // step in which each aux slot was last consumed
       for (SegIter it(p, t_begin, t_end); it.valid();) {
@@ -196,13 +215,6 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
               mbar_arrive_expect_tx(ab, kTileBytes);
               tma_load_4d(aux_smem + as * kTileBytes, &p.tm_aux, ab, 0, x0, s.y_b + j, s.n);
             }
-            if (p.has_id) {
-              mbar_wait(smem_u32(&misc->io_empty[ior.slot]), ior.phase ^ 1, 3);
-              const uint32_t ib = smem_u32(&misc->id_full[ior.slot]);
-              mbar_arrive_expect_tx(ib, kTileBytes);
-              tma_load_4d(io_smem + ior.slot * kTileBytes, &p.tm_id, ib, 0, x0, s.y_b + j, s.n);
-              ior.advance();
-            }
             ++ord;
           }
         }
@@ -217,7 +229,8 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       const uint32_t w_lo = umma_desc_lo(w_smem);
       const uint32_t dxb = (uint32_t)dx_block_bytes >> 4;      // descriptor units per dx block
       const uint32_t sbb = (uint32_t)(tap_n * 128) >> 4;       // ... per dy sub-block
-      const uint32_t aux_w_lo = w_lo + 3 * dxb;
+      const uint32_t aux_w_lo = w_lo + 3 * dxb;                 // LR im2col block (aux) ...
+      const uint32_t par_w_lo = w_lo + 3 * dxb;                 // ... or the stacked 1x1 block (kPar)
       mbar_wait(smem_u32(&misc->w_full), 0, 4);
       // One step = one in-image source row.  `StepCtx` carries everything the issue code needs, so
       // the barriers of step s+1 can be checked in the MIDDLE of step s: an already-complete
@@ -259,19 +272,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         const int new_from = (c.j == c.j_first) ? lo : c.j + 1;   // rows first touched in this step
         old_cnt = min(max(new_from - lo, 0), cnt);
       };
-      auto wait_for = [&](const StepCtx& c) {
-        mbar_wait(smem_u32(&misc->a_full[c.a_slot]), c.a_phase, 5);
-        int lo, cnt, old_cnt;
-        ranges(c, lo, cnt, old_cnt);
-        for (int o = lo + old_cnt; o < lo + cnt; ++o) {          // new rows: slot must be drained
-          const uint32_t od = c.ord0 + o;
-          mbar_wait(smem_u32(&misc->acc_free[od & (kAccRing - 1)]), ((od >> 3) & 1) ^ 1, 6);
-        }
-        if (p.aux_k16 > 0 && c.j >= 0 && c.j < c.len) {
-          const uint32_t od = c.ord0 + c.j;
-          mbar_wait(smem_u32(&misc->aux_full[od & 1]), (od >> 1) & 1, 7);
-        }
-      };
+      const uint32_t go_step = smem_u32(&misc->go_step), go_par = smem_u32(&misc->go_par);
       bool pend = false;
       uint32_t pend_bar = 0;
 
@@ -283,7 +284,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
           umma_bf16_lo(tmem_base, a_lo, kDescHiSw128, b_lo + n1 * sbb, kDescHiSw128, idesc0 + (cnt - n1) * idesc_step, acc);
       };
 
-      if (cur.valid) wait_for(cur);
+      if (cur.valid) spin_until_ge(go_step, 1, 5);
       tc_fence_after();
       while (cur.valid) {
         const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && cur.sc < 64;
@@ -292,7 +293,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         ranges(cur, lo, cnt, old_cnt);
         const int new_cnt = cnt - old_cnt;
         const bool centre = (cur.j >= 0 && cur.j < cur.len);
-        const uint32_t slot_lo = (cur.ord0 + lo) & (kAccRing - 1);
+        const uint32_t slot_lo = (cur.ord0 + lo) % kAccRing;
         const uint32_t a_row = umma_desc_lo(a_smem + cur.a_slot * kASlotBytes);
         const uint32_t b_row = w_lo + (uint32_t)(lo - (cur.j - 1)) * sbb;   // first dy sub-block in range
         const uint32_t cur_sc = cur.sc;
@@ -301,10 +302,13 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         advance(nxt);
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
+          if (tr && dx == 1) p.trace[cur_sc * 8 + 6] = clock64();
           if (dx == 2) {
             // barriers of the NEXT step, checked while ~8 MMAs of this step are still queued
-            if (nxt.valid) wait_for(nxt);
+            if (tr) p.trace[cur_sc * 8 + 7] = clock64();
+            if (nxt.valid) spin_until_ge(go_step, nxt.sc + 1, 5);   // normally long satisfied
             tc_fence_after();
+            if (tr) p.trace[cur_sc * 8 + 2] = clock64();   // (slot 2 is otherwise the epilogue's)
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -314,7 +318,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
               // first MMA of the step: rows touched before accumulate, new rows are overwritten
               if (old_cnt > 0) mma_range(slot_lo, old_cnt, a_lo, b_lo, 1);
               if (new_cnt > 0)
-                mma_range((slot_lo + old_cnt) & (kAccRing - 1), new_cnt, a_lo, b_lo + old_cnt * sbb, 0);
+                mma_range((slot_lo + old_cnt) % kAccRing, new_cnt, a_lo, b_lo + old_cnt * sbb, 0);
               if (pend) {
                 // the previous step's commit rides behind this step's first MMA
                 umma_commit(pend_bar);
@@ -328,8 +332,20 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         if (p.aux_k16 > 0 && centre) {
           const uint32_t a_lo = umma_desc_lo(aux_smem + (cur_od & 1) * kTileBytes);
           for (int k = 0; k < p.aux_k16; ++k)
-            umma_bf16_lo(tmem_base + (cur_od & (kAccRing - 1)) * tap_n, a_lo + 2 * k, kDescHiSw128,
+            umma_bf16_lo(tmem_base + (cur_od % kAccRing) * tap_n, a_lo + 2 * k, kDescHiSw128,
                          aux_w_lo + 2 * k, kDescHiSw128, idesc0 + idesc_step, 1);
+        }
+        if (kPar && centre) {
+          // Partition 1x1 convs of this row: centre pixel column (dx index 1), N = 192, own TMEM
+          // region.  Issued LAST in the step: the epilogue then has a whole step to read the region
+          // before the next row needs it (issued first, the hand-back sat on the critical path).
+          spin_until_ge(go_par, cur_od + 1, 10);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_lo(tmem_base + kParCol, a_row + 8 + 2 * k, kDescHiSw128, par_w_lo + 2 * k, kDescHiSw128,
+                         idesc0 + 3 * idesc_step, k > 0);
+          umma_commit(smem_u32(&misc->par_done));
         }
         pend = true;
         pend_bar = smem_u32(&misc->step_done[cur_sc & (kStepRing - 1)]);
@@ -338,137 +354,275 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       }
       if (pend) umma_commit(pend_bar);
     }
+  } else if (warp == 10) {
+    // ============================================================ barrier scout (one elected lane)
+    // Walks the same step sequence as the MMA thread, one or more steps ahead, performs every
+    // mbarrier wait the MMAs depend on (an already-complete try_wait costs 220-290 cycles in this
+    // kernel) and publishes plain progress counters the MMA thread can poll in ~30 cycles.
+    if (elect_one()) {
+      const uint32_t go_step = smem_u32(&misc->go_step), go_par = smem_u32(&misc->go_par);
+      Ring ar(s_a);
+      uint32_t sc = 0, ord0 = 0;
+      for (SegIter it(p, t_begin, t_end); it.valid();) {
+        const Segment s = it.get();
+        for (int j = s.j_first; j <= s.j_last; ++j, ++sc, ar.advance()) {
+          mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
+          const int lo = max(j - 1, 0), hi = min(j + 1, s.len - 1);
+          const int new_from = (j == s.j_first) ? lo : j + 1;
+          for (int o = max(new_from, lo); o <= hi; ++o) {          // rows first touched in this step
+            const uint32_t od = ord0 + o;
+            mbar_wait(smem_u32(&misc->acc_free[od % kAccRing]), ((od / kAccRing) & 1) ^ 1, 6);
+          }
+          const bool centre = (j >= 0 && j < s.len);
+          if (p.aux_k16 > 0 && centre) {
+            const uint32_t od = ord0 + j;
+            mbar_wait(smem_u32(&misc->aux_full[od & 1]), (od >> 1) & 1, 7);
+          }
+          st_release_shared(go_step, sc + 1);
+          if (kPar && centre) {                                    // previous row's 1x1 results read
+            const uint32_t od = ord0 + j;
+            if (od >= 1) mbar_wait(smem_u32(&misc->par_free), (od - 1) & 1, 10);
+            st_release_shared(go_par, od + 1);
+          }
+        }
+        ord0 += s.len;
+        it.next(s);
+      }
+    }
   } else {
     // ============================================================ epilogue (8 warps, 256 threads)
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;          // warps 2..9 only
     const int row = q * 32 + lane;
     const bool store_warp = (warp == 2);
     const uint32_t sw = (uint32_t)(row & 7);
-    float bias_r[32], scale_r[kScale ? 32 : 1];
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    // non-partition variants keep the per-channel constants of this warp's 32 channels in registers;
+    // the partition variant needs those registers for the 1x1 blend and re-reads them as float4
+    float bias_r[kPar ? 1 : 32], scale_r[(kScale && !kPar) ? 32 : 1];
+    if (!kPar) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      bias_r[j] = misc->bias[half * 32 + j];
-      if (kScale) scale_r[j] = misc->scale[half * 32 + j];
+      for (int j = 0; j < 32; ++j) {
+        bias_r[j] = misc->bias[half * 32 + j];
+        if (kScale) scale_r[j] = misc->scale[half * 32 + j];
+      }
     }
-    Ring ior(n_io), rel(n_io);
-    uint32_t ord = 0, sc0 = 0;
-    for (SegIter it(p, t_begin, t_end); it.valid();) {
-      const Segment s = it.get();
+
+    // flat cursor over this CTA's output rows (copyable: the partition path looks one row ahead)
+    struct TileCur {
+      SegIter it;
+      Segment s;
+      int o;
+      uint32_t ord, sc0;
+      bool valid;
+    };
+    TileCur cur{SegIter(p, t_begin, t_end), Segment{0, 0, 0, 0, 0, -1}, 0, 0u, 0u, false};
+    cur.valid = cur.it.valid();
+    if (cur.valid) cur.s = cur.it.get();
+    auto tile_next = [](TileCur& c) {
+      ++c.ord;
+      if (++c.o < c.s.len) return;
+      c.sc0 += (uint32_t)(c.s.j_last - c.s.j_first + 1);
+      c.it.next(c.s);
+      c.valid = c.it.valid();
+      c.o = 0;
+      if (c.valid) c.s = c.it.get();
+    };
+
+    // sum_k par_k * conv1x1_k(x) for the row at `c`: read the 3 x 32 columns of this warp's channel
+    // half from the partition accumulators, blend with the pixel's partition values, free the region
+    float dy_cur[kPar ? 32 : 1], dy_nxt[kPar ? 32 : 1];
+    auto par_part = [&](const TileCur& c, float* dy) {
+      const int x = c.s.strip * kTilePx + row;
+      const int y = c.s.y_b + c.o;
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+      if (x < p.W) {
+        const float* pp = p.par + (long long)c.s.n * p.par_sn + (long long)y * p.par_sy + x;
+        p0 = __ldg(pp);
+        p1 = __ldg(pp + p.par_sc);
+        p2 = __ldg(pp + 2 * p.par_sc);
+      }
+      mbar_wait(smem_u32(&misc->par_done), c.ord & 1, 11);
+      tc_fence_after();
+#pragma unroll
+      for (int gg = 0; gg < 2; ++gg) {
+        float a1[16], a2[16], a3[16];
+        const uint32_t col = kParCol + half * 32 + gg * 16;
+        tmem_ld16(lane_base + col, a1);
+        tmem_ld16(lane_base + col + 64, a2);
+        tmem_ld16(lane_base + col + 128, a3);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dy[gg * 16 + j] = fmaf(p2, a3[j], fmaf(p1, a2[j], p0 * a1[j]));
+      }
+      tc_fence_before();
+      warp_arrive(smem_u32(&misc->par_free));
+    };
+    if (kPar && cur.valid) par_part(cur, dy_cur);
+
+    // Identity tiles are fetched by the epilogue's own store lane: it is the one who knows when a
+    // staging slot has been drained (wait_group.read), so the TMA producer never blocks on them and
+    // keeps its source rows s_a-1 steps ahead.  `idc` runs n_io-2 output rows ahead of `cur`.
+    TileCur idc = cur;
+    Ring idr(n_io);
+    auto load_id = [&](const TileCur& c, uint32_t slot) {
+      const uint32_t ib = smem_u32(&misc->id_full[slot]);
+      mbar_arrive_expect_tx(ib, kTileBytes);
+      tma_load_4d(io_smem + slot * kTileBytes, &p.tm_id, ib, 0, c.s.strip * kTilePx, c.s.y_b + c.o, c.s.n);
+    };
+    if (p.has_id && store_warp) {
+      if (elect_one()) {
+        for (int i = 0; i < n_io && idc.valid; ++i) {     // all slots start out free
+          load_id(idc, idr.slot);
+          idr.advance();
+          tile_next(idc);
+        }
+      }
+      __syncwarp();
+    }
+
+    Ring ior(n_io);
+    while (cur.valid) {
+      const Segment& s = cur.s;
+      const int o = cur.o;
+      const uint32_t ord = cur.ord;
       const int x = s.strip * kTilePx + row;
       const bool valid = x < p.W;
-      for (int o = 0; o < s.len; ++o, ++ord) {
-        const int y = s.y_b + o;
-        const uint32_t sc_last = sc0 + (uint32_t)(min(o + 1, s.j_last) - s.j_first);
-        const uint32_t slot = ord & (kAccRing - 1);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * tap_n;
-        if (last_mode) {
-          float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-          if (valid && half == 0) {
-            const float* lp = p.lq + (long long)s.n * p.lq_sn + (long long)y * p.lq_sy + x;
-            r0 = __ldg(lp);
-            r1 = __ldg(lp + p.lq_sc);
-            r2 = __ldg(lp + 2 * p.lq_sc);
-          }
-          mbar_wait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> 3) & 1, 9);
-          tc_fence_after();
-          float v[16];
-          if (half == 0) {
-            tmem_ld16(taddr, v);
-            tmem_ld_wait();
-          }
-          tc_fence_before();
-          mbar_arrive(smem_u32(&misc->acc_free[slot]));
-          if (valid && half == 0) {
-            float* op = p.outf + (long long)s.n * p.of_sn + (long long)y * p.of_sy + x;
-            op[0] = v[0] + misc->bias[0] + r0;
-            op[p.of_sc] = v[1] + misc->bias[1] + r1;
-            op[2 * p.of_sc] = v[2] + misc->bias[2] + r2;
-          }
-          continue;
-        }
-        const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && ord < 64 && threadIdx.x == 64;
-        if (tr) p.trace[ord * 8 + 2] = clock64();
-        const uint32_t s_io = ior.slot;
-        if (store_warp) {
-          if (elect_one()) {
-            tma_store_wait_read<1>();      // stores of output rows <= ord-2 no longer read smem
-            if (p.has_id && ord >= 2) mbar_arrive(smem_u32(&misc->io_empty[rel.slot]));
-          }
-          __syncwarp();
-        }
-        if (ord >= 2) rel.advance();
-        if (p.has_id) {
-          mbar_wait(smem_u32(&misc->id_full[s_io]), ior.phase, 8);
-        } else {
-          named_bar_sync(1, 256);
+      const int y = s.y_b + o;
+      const uint32_t sc_last = cur.sc0 + (uint32_t)(min(o + 1, s.j_last) - s.j_first);
+      const uint32_t slot = ord % kAccRing;
+      const uint32_t taddr = lane_base + slot * tap_n;
+      TileCur nxt = cur;
+      tile_next(nxt);
+      if (last_mode) {
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+        if (valid && half == 0) {
+          const float* lp = p.lq + (long long)s.n * p.lq_sn + (long long)y * p.lq_sy + x;
+          r0 = __ldg(lp);
+          r1 = __ldg(lp + p.lq_sc);
+          r2 = __ldg(lp + 2 * p.lq_sc);
         }
         mbar_wait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> 3) & 1, 9);
         tc_fence_after();
-        if (tr) p.trace[ord * 8 + 3] = clock64();
-        uint8_t* rowp = sgen + L.io + s_io * kTileBytes + row * 128;
-        float v[32];
-        if (p.debug_skip & 4) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        } else {
-          tmem_ld16(taddr + half * 32, v);
-          tmem_ld16(taddr + half * 32 + 16, v + 16);
+        float v[16];
+        if (half == 0) {
+          tmem_ld16(taddr, v);
           tmem_ld_wait();
         }
         tc_fence_before();
-        mbar_arrive(smem_u32(&misc->acc_free[slot]));   // accumulator is in registers: slot reusable
+        warp_arrive(smem_u32(&misc->acc_free[slot]));
+        if (valid && half == 0) {
+          float* op = p.outf + (long long)s.n * p.of_sn + (long long)y * p.of_sy + x;
+          op[0] = v[0] + misc->bias[0] + r0;
+          op[p.of_sc] = v[1] + misc->bias[1] + r1;
+          op[2 * p.of_sc] = v[2] + misc->bias[2] + r2;
+        }
+        cur = nxt;
+        continue;
+      }
+      const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && ord < 64 && threadIdx.x == 64;
+      // the partition blend of the NEXT row comes first: its accumulators are ready a full step
+      // before this row's 3x3 result, and the MMA thread needs the region back early in that step
+      if (kPar && nxt.valid) par_part(nxt, dy_nxt);
+      const uint32_t s_io = ior.slot;
+      if (store_warp) {
+        if (elect_one()) {
+          tma_store_wait_read<1>();      // stores of output rows <= ord-2 no longer read smem
+          if (p.has_id && ord >= 2 && idc.valid) {
+            load_id(idc, idr.slot);      // slot of row ord-2 == slot of row ord-2+n_io
+            idr.advance();
+            tile_next(idc);
+          }
+        }
+        __syncwarp();
+      }
+      if (p.has_id) {
+        mbar_wait(smem_u32(&misc->id_full[s_io]), ior.phase, 8);
+      } else {
+        named_bar_sync(1, 256);
+      }
+      mbar_wait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> 3) & 1, 9);
+      tc_fence_after();
+      if (tr) p.trace[ord * 8 + 3] = clock64();
+      uint8_t* rowp = sgen + L.io + s_io * kTileBytes + row * 128;
+      float v[32];
+      if (p.debug_skip & 4) {
 #pragma unroll
-        for (int gg = 0; gg < 2; ++gg) {
-          const int g = half * 2 + gg;
-          float* vv = v + gg * 16;
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      } else {
+        tmem_ld16(taddr + half * 32, v);
+        tmem_ld16(taddr + half * 32 + 16, v + 16);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      warp_arrive(smem_u32(&misc->acc_free[slot]));   // accumulator is in registers: slot reusable
+#pragma unroll
+      for (int gg = 0; gg < 2; ++gg) {
+        const int g = half * 2 + gg;
+        float* vv = v + gg * 16;
+        if (kPar) {
+          const float4* sc4 = reinterpret_cast<const float4*>(&misc->scale[g * 16]);
+          const float4* bi4 = reinterpret_cast<const float4*>(&misc->bias[g * 16]);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 sc = kScale ? sc4[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 bi = bi4[j4];
+            vv[4 * j4 + 0] = fmaf(vv[4 * j4 + 0], sc.x, bi.x) + dy_cur[gg * 16 + 4 * j4 + 0];
+            vv[4 * j4 + 1] = fmaf(vv[4 * j4 + 1], sc.y, bi.y) + dy_cur[gg * 16 + 4 * j4 + 1];
+            vv[4 * j4 + 2] = fmaf(vv[4 * j4 + 2], sc.z, bi.z) + dy_cur[gg * 16 + 4 * j4 + 2];
+            vv[4 * j4 + 3] = fmaf(vv[4 * j4 + 3], sc.w, bi.w) + dy_cur[gg * 16 + 4 * j4 + 3];
+          }
+        } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            vv[j] = kScale ? fmaf(vv[j], scale_r[gg * 16 + j], bias_r[gg * 16 + j]) : vv[j] + bias_r[gg * 16 + j];
-          uint4* c0 = reinterpret_cast<uint4*>(rowp + (((2 * g) ^ sw) << 4));
-          uint4* c1 = reinterpret_cast<uint4*>(rowp + (((2 * g + 1) ^ sw) << 4));
-          if (p.has_id) {
-            const uint4 i0 = *c0, i1 = *c1;
-            const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+            vv[j] = (kScale && !kPar) ? fmaf(vv[j], scale_r[gg * 16 + j], bias_r[gg * 16 + j]) : vv[j] + bias_r[gg * 16 + j];
+        }
+        uint4* c0 = reinterpret_cast<uint4*>(rowp + (((2 * g) ^ sw) << 4));
+        uint4* c1 = reinterpret_cast<uint4*>(rowp + (((2 * g + 1) ^ sw) << 4));
+        if (p.has_id) {
+          const uint4 i0 = *c0, i1 = *c1;
+          const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              vv[2 * j] += bf16_lo(iw[j]);
-              vv[2 * j + 1] += bf16_hi(iw[j]);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) vv[j] = act_fn(vv[j], p.act);
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(vv[0], vv[1]);
-          o0.y = pack_bf16x2(vv[2], vv[3]);
-          o0.z = pack_bf16x2(vv[4], vv[5]);
-          o0.w = pack_bf16x2(vv[6], vv[7]);
-          o1.x = pack_bf16x2(vv[8], vv[9]);
-          o1.y = pack_bf16x2(vv[10], vv[11]);
-          o1.z = pack_bf16x2(vv[12], vv[13]);
-          o1.w = pack_bf16x2(vv[14], vv[15]);
-          if (!(p.debug_skip & 2)) {
-            *c0 = o0;
-            *c1 = o1;
+          for (int j = 0; j < 8; ++j) {
+            vv[2 * j] += bf16_lo(iw[j]);
+            vv[2 * j + 1] += bf16_hi(iw[j]);
           }
         }
-        if (tr) p.trace[ord * 8 + 4] = clock64();
-        fence_proxy_async_smem();
-        named_bar_sync(2, 256);
-        if (tr) p.trace[ord * 8 + 5] = clock64();
-        if (store_warp) {
-          if (elect_one()) {
-            if (!(p.debug_skip & 2)) {
-              tma_store_4d(&p.tm_out, io_smem + s_io * kTileBytes, 0, s.strip * kTilePx, y, s.n);
-              tma_store_commit();
-            }
-          }
-          __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) vv[j] = act_fn(vv[j], p.act);
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(vv[0], vv[1]);
+        o0.y = pack_bf16x2(vv[2], vv[3]);
+        o0.z = pack_bf16x2(vv[4], vv[5]);
+        o0.w = pack_bf16x2(vv[6], vv[7]);
+        o1.x = pack_bf16x2(vv[8], vv[9]);
+        o1.y = pack_bf16x2(vv[10], vv[11]);
+        o1.z = pack_bf16x2(vv[12], vv[13]);
+        o1.w = pack_bf16x2(vv[14], vv[15]);
+        if (!(p.debug_skip & 2)) {
+          *c0 = o0;
+          *c1 = o1;
         }
-        ior.advance();
       }
-      sc0 += (uint32_t)(s.j_last - s.j_first + 1);
-      it.next(s);
+      if (tr) p.trace[ord * 8 + 4] = clock64();
+      fence_proxy_async_smem();
+      named_bar_sync(2, 256);
+      if (tr) p.trace[ord * 8 + 5] = clock64();
+      if (store_warp) {
+        if (elect_one()) {
+          if (!(p.debug_skip & 2)) {
+            tma_store_4d(&p.tm_out, io_smem + s_io * kTileBytes, 0, s.strip * kTilePx, y, s.n);
+            tma_store_commit();
+          }
+        }
+        __syncwarp();
+      }
+      ior.advance();
+      if (kPar) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dy_cur[j] = dy_nxt[j];
+      }
+      cur = nxt;
     }
     if (store_warp) {
       if (elect_one()) tma_store_wait_all<0>();
@@ -485,31 +639,44 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
 }
 
 size_t conv_rows_smem_bytes(const ConvParams& p) {
-  const int w_bytes = 3 * 3 * p.tap_n * 128 + (p.aux_k16 > 0 ? kWChunkBytes : 0);
+  const int w_bytes = 3 * 3 * p.tap_n * 128 + (p.aux_k16 > 0 ? kWChunkBytes : 0) +
+                      (p.center_n == 256 ? 3 * 64 * 128 : 0);
   return rows_layout(w_bytes, p.s_a, p.aux_k16 > 0, p.n_io).total + 1024;
 }
 
 namespace {
-template <bool kScale>
+template <bool kPar, bool kScale>
 cudaError_t launch_rows_variant(const ConvParams& p, int grid, size_t smem, cudaStream_t stream) {
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    e = cudaFuncSetAttribute(conv3x3_rows_kernel<kScale>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    e = cudaFuncSetAttribute(conv3x3_rows_kernel<kPar, kScale>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  conv3x3_rows_kernel<kScale><<<grid, kConvThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kRowsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv3x3_rows_kernel<kPar, kScale>, p);
 }
 }  // namespace
 
 cudaError_t launch_conv_rows(const ConvParams& p, int grid, cudaStream_t stream) {
   const size_t smem = conv_rows_smem_bytes(p);
-  return p.scale != nullptr ? launch_rows_variant<true>(p, grid, smem, stream)
-                            : launch_rows_variant<false>(p, grid, smem, stream);
+  const bool par = (p.center_n == 256), scale = (p.scale != nullptr);
+  if (par) return scale ? launch_rows_variant<true, true>(p, grid, smem, stream)
+                        : launch_rows_variant<true, false>(p, grid, smem, stream);
+  return scale ? launch_rows_variant<false, true>(p, grid, smem, stream)
+               : launch_rows_variant<false, false>(p, grid, smem, stream);
 }
 
 }  // namespace pnp

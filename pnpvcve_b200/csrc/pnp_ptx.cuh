@@ -53,6 +53,40 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   }
 }
 
+// One arrival per warp (barrier count = number of warps): every lane has finished its own work
+// (tcgen05.wait::ld + fence) before __syncwarp, lane 0 then speaks for the warp.  256 per-thread
+// arrivals per tile were a measurable load on the mbarrier unit.
+__device__ __forceinline__ void warp_arrive(uint32_t bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+
+// Patient variant for the many threads that merely wait for work (epilogue warps, TMA producer):
+// one lane polls with a hardware suspend-time hint and the warp re-converges.  Measured on B200
+// (profiles/r01_notes.md): with all 256 epilogue lanes spinning on try_wait, an already-complete
+// mbarrier wait of the MMA-issuing thread took ~375 cycles instead of ~125 and the N=192 MMAs
+// themselves ran ~25 % slower -- mbarrier polling competes for the shared-memory pipe.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int tag = 0) {
+  if ((threadIdx.x & 31) == 0) {
+    uint32_t spins = 0, ok = 0;
+    do {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar), "r"(parity), "r"(200u)      // suspend-time hint in ns
+          : "memory");
+      if (!ok && ++spins > (PNP_SPIN_LIMIT >> 4)) {
+        printf("pnp: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag,
+               (int)blockIdx.x, (int)threadIdx.x, parity);
+        __trap();
+      }
+    } while (!ok);
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------ fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -205,6 +239,38 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
+}
+
+// ------------------------------------------------------------------ flag hand-off in shared memory
+// A "scout" thread does the (slow, ~250 cycle) mbarrier waits and publishes progress counters; the
+// MMA-issuing thread only needs these ~30-cycle acquire loads on its critical path.
+__device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void spin_until_ge(uint32_t addr, uint32_t target, int tag) {
+  uint32_t spins = 0;
+  while (ld_acquire_shared(addr) < target) {
+    if (++spins > PNP_SPIN_LIMIT) {
+      printf("pnp: flag wait timed out (tag %d, block %d, target %u)\n", tag, (int)blockIdx.x, target);
+      __trap();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ programmatic dependent launch
+// launch_dependents: the next kernel in the stream (launched with the programmatic-serialization
+// attribute) may start its prologue; wait: block until the previous kernel has completed and its
+// memory is visible.  Everything that touches activations comes after griddep_wait().
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ misc

@@ -91,13 +91,13 @@ def pack_conv3x3(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=None, cen
                                     _ptr(dst), center_chunks, _stream()), "pnp_pack_conv3x3")
 
 
-def rowstack_bytes(tap_n=64, with_aux=False):
+def rowstack_bytes(tap_n=64, with_aux=False, with_par=False):
     """Size of a row-stacked weight pack (see pnp_pack_conv3x3_rowstack)."""
-    return 9 * tap_n * 128 + (CHUNK_BYTES if with_aux else 0)
+    return 9 * tap_n * 128 + (CHUNK_BYTES if with_aux else 0) + (3 * CHUNK_BYTES if with_par else 0)
 
 
-def new_wpack_rowstack(device, tap_n=64, with_aux=False):
-    n = (rowstack_bytes(tap_n, with_aux) + 1023) // 1024 * 1024
+def new_wpack_rowstack(device, tap_n=64, with_aux=False, with_par=False):
+    n = (rowstack_bytes(tap_n, with_aux, with_par) + 1023) // 1024 * 1024
     return torch.zeros(n, dtype=torch.uint8, device=device)
 
 
@@ -204,7 +204,8 @@ def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par
                     tuple(t.shape[2:]) != tuple(src.shape[1:3]):
                 raise ValueError(f"conv3x3: {nm} must be (N,3,H,W) matching src")
     d = fill_conv_desc(ConvDesc(), src, wpack, out, aux, idt, scale, bias, par, act, lq, outf, wlayout)
-    need = rowstack_bytes(d.tap_n, aux is not None) if wlayout == 1 else d.n_wchunks * CHUNK_BYTES
+    need = rowstack_bytes(d.tap_n, aux is not None, par is not None) if wlayout == 1 \
+        else d.n_wchunks * CHUNK_BYTES
     if wpack.numel() < need:
         raise ValueError("conv3x3: packed weight buffer too small for this configuration")
     lib = _lib.load()

@@ -149,20 +149,27 @@ def test_conv_variants_match_fp32_conv2d(dev, n, h, w, layout):
     ops.conv3x3(xs, wpm, out=out, wlayout=layout)
     assert_bf16_close(nchw(out), F.conv2d(x, bf(w_in[:, 3:67] + w_in[:, 67:131]), padding=1), "merged")
 
+    # 3x3 + three partition-modulated 1x1 convs, general (non one-hot) float partition map
+    par = torch.rand((n, 3, h, w), generator=g, device=dev) * \
+        (torch.rand((n, 3, h, w), generator=g, device=dev) > 0.5)
+    w1 = [bf(torch.randn((64, 64), generator=g, device=dev) * 0.1) for _ in range(3)]
     if layout == 0:
-        # 3x3 + three partition-modulated 1x1 convs, general (non one-hot) float partition map
-        par = torch.rand((n, 3, h, w), generator=g, device=dev) * \
-            (torch.rand((n, 3, h, w), generator=g, device=dev) > 0.5)
-        w1 = [bf(torch.randn((64, 64), generator=g, device=dev) * 0.1) for _ in range(3)]
         wpp = ops.new_wpack(12, dev)
         ops.pack_conv3x3(wt, wpp, center_chunks=4)
         for j in range(3):
             ops.pack_rows(w1[j], wpp, 64 * (j + 1))
-        ops.conv3x3(xs, wpp, out=out, scale=scale, bias=bias, par=par, act=ops.PNP_ACT_RELU)
-        ref = ref0 * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    else:
+        wpp = ops.new_wpack_rowstack(dev, with_par=True)
+        ops.pack_conv3x3_rowstack(wt, wpp)
         for j in range(3):
-            ref = ref + F.conv2d(x, w1[j].view(64, 64, 1, 1)) * par[:, j:j + 1]
-        assert_bf16_close(nchw(out), F.relu(ref), "par")
+            ops.pack_rows(w1[j], wpp[9 * ops.CHUNK_BYTES:], 64 * j)
+    ops.conv3x3(xs, wpp, out=out, scale=scale, bias=bias, par=par, act=ops.PNP_ACT_RELU, wlayout=layout)
+    ref = ref0 * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    for j in range(3):
+        ref = ref + F.conv2d(x, w1[j].view(64, 64, 1, 1)) * par[:, j:j + 1]
+    assert_bf16_close(nchw(out), F.relu(ref), "par")
+    ops.conv3x3(xs, wpp, out=out, bias=bias, par=par, act=ops.PNP_ACT_NONE, wlayout=layout)
+    assert_bf16_close(nchw(out), ref - ref0 * scale.view(1, -1, 1, 1) + ref0, "par without scale")
 
     # reconstruction tail: 64 -> 3, + lq, fp32 NCHW output
     wl = bf(torch.randn((3, 64, 3, 3), generator=g, device=dev) * 0.05)

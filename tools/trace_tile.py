@@ -11,20 +11,29 @@ if LAYOUT == 0:
     wp9 = ops.new_wpack(9, dev); ops.pack_conv3x3(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp9)
 else:
     wp9 = ops.new_wpack_rowstack(dev); ops.pack_conv3x3_rowstack(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp9)
-trace = torch.zeros(64 * 8, dtype=torch.int64, device=dev)
+trace = torch.zeros(2 * 64 * 8, dtype=torch.int64, device=dev)
 for _ in range(3): ops.conv3x3(x, wp9, out=out, wlayout=LAYOUT)
 torch.cuda.synchronize()
 os.environ["PNP_TRACE_PTR"] = str(trace.data_ptr())
-ops.conv3x3(x, wp9, out=out, wlayout=LAYOUT)
+PAR = len(sys.argv) > 2
+if PAR:
+    wp9 = ops.new_wpack_rowstack(dev, with_par=True); ops.pack_conv3x3_rowstack(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp9)
+    par = torch.rand((1, 3, h, w), device=dev)
+    ops.conv3x3(x, wp9, out=out, par=par, act=2, wlayout=1)
+else:
+    ops.conv3x3(x, wp9, out=out, wlayout=LAYOUT)
 torch.cuda.synchronize()
-t = trace.view(64, 8).cpu()
+t = trace[:512].view(64, 8).cpu()
+t2 = trace[512:].view(64, 8).cpu()
 t0 = int(t[0, 0])
 print("tile  mma_ready  mma_issued | epi_start  acc_full   epi_math   epi_bar   (cycles since first MMA ready; deltas in brackets)")
 prev = None
 for i in range(49):
     r = [int(v) - t0 for v in t[i, :8]]
     if LAYOUT == 1:
-        d = "" if prev is None else f"  [step period {r[0]-prev[0]:5d}  issue {r[1]-r[0]:4d}  gap {r[0]-prev[1]:4d} | epi period {r[2]-prev[2]:5d} wait {r[3]-r[2]:5d}  math {r[4]-r[3]:4d}  bar {r[5]-r[4]:4d}]"
+        d = "" if prev is None else f"  [step period {r[0]-prev[0]:5d}: dx0 +{r[6]-r[0]:4d}  dx1 +{r[7]-r[6]:4d}  lookahead waits +{r[2]-r[7]:4d}  dx2.. +{r[1]-r[2]:4d}  gap {r[0]-prev[1]:4d} | epi math {r[4]-r[3]:4d}  bar {r[5]-r[4]:4d}]"
+        w = [int(v) for v in t2[i, :3]]
+        d += f"  [wait a_full {w[1]-w[0]:4d}  acc_free {w[2]-w[1]:4d}]"
         print(f"{i:3d} {r[0]:9d} {r[1]:9d} | {r[2]:9d} {r[3]:9d} {r[4]:9d} {r[5]:9d}{d}")
         prev = r
         continue

@@ -24,7 +24,9 @@ if len(sys.argv) > 1:
     wr = ops.new_wpack_rowstack(dev); ops.pack_conv3x3_rowstack(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wr)
     ra = timeit(lambda: ops.conv3x3(x, wr, out=out, wlayout=1))
     rb = timeit(lambda: ops.conv3x3(x, wr, out=out, idt=idt, wlayout=1))
-    print(f"skip={os.environ.get('PNP_DEBUG_SKIP','0'):>2s}: rowstack plain {ra:6.1f} us   +id {rb:6.1f} us", flush=True)
+    wrp = ops.new_wpack_rowstack(dev, with_par=True); ops.pack_conv3x3_rowstack(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wrp)
+    rc = timeit(lambda: ops.conv3x3(x, wrp, out=out, par=par, act=2, wlayout=1))
+    print(f"skip={os.environ.get('PNP_DEBUG_SKIP','0'):>2s}: rowstack plain {ra:6.1f} us   +id {rb:6.1f} us   +par {rc:6.1f} us", flush=True)
     print(f"skip={os.environ.get('PNP_DEBUG_SKIP','0'):>2s}: plain {a:6.1f} us   +id {b:6.1f} us   +par {c:6.1f} us", flush=True)
 else:
     for bits in (0, 1, 2, 4, 3, 6, 7):
