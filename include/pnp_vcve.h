@@ -69,14 +69,16 @@ int pnp_lr_im2col(const float* lr, int64_t sn, int64_t sc, int64_t sy, void* dst
  *   pnp_pack_conv3x3: w is fp32 (E, out_ch, in_total, 3, 3); block = sum_e coef[e]*w[e] restricted to
  *     input channels [in_begin, in_begin+in_count) (+ the slice at in_begin2 if >= 0).  coef is a
  *     DEVICE pointer to E floats or NULL (E must then be 1).  Replaces the per-block, per-frame
- *     torch.mm expert mixing of Dynamic_conv2d_se.forward (sr_backbone_utils.py:198-199).
+ *     torch.mm expert mixing of Dynamic_conv2d_se.forward (sr_backbone_utils.py:198-199).  row_scale is a
+ *     DEVICE pointer to out_ch floats multiplied into the rows (the SE gain of sr_backbone_utils.py:207-208
+ *     folded into the kernel: (conv(x,W)+b)*g == conv(x, g*W) + g*b), or NULL.
  *   pnp_pack_rows: fp32 matrix (rows<=64, cols<=64; element strides) into packed rows
  *     row_offset.. of dst (used for the three 1x1 partition convs, sr_backbone_utils.py:285-287,
  *     stacked under the centre tap: rows 64.., 128.., 192..).
  *   pnp_pack_aux: first 3 input channels of w (out_ch, in_total, 3, 3) as one [64][tap*3+c] block.
  */
-int pnp_pack_conv3x3(const float* w, int n_experts, const float* coef, int out_ch, int in_total,
-                     int in_begin, int in_begin2, int in_count, void* dst, int center_chunks,
+int pnp_pack_conv3x3(const float* w, int n_experts, const float* coef, const float* row_scale, int out_ch,
+                     int in_total, int in_begin, int in_begin2, int in_count, void* dst, int center_chunks,
                      void* stream);
 int pnp_pack_rows(const float* w, int rows, int cols, int64_t row_stride, int64_t col_stride, void* dst,
                   int row_offset, void* stream);
@@ -84,9 +86,9 @@ int pnp_pack_rows(const float* w, int rows, int cols, int64_t row_stride, int64_
  * 128-byte rows, sub-block sb = 0,1,2 holding ky = 2 - sb, so that one source row can be multiplied
  * against the weights of the three output rows it feeds in a single N = 3*tap_n MMA.  tap_n is 64, or
  * 16 for the 64->3 tail; total 9*tap_n*128 bytes.  Same mixing arguments as pnp_pack_conv3x3. */
-int pnp_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, int out_ch, int in_total,
-                              int in_begin, int in_begin2, int in_count, void* dst, int tap_n,
-                              void* stream);
+int pnp_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, const float* row_scale,
+                              int out_ch, int in_total, int in_begin, int in_begin2, int in_count, void* dst,
+                              int tap_n, void* stream);
 int pnp_pack_aux(const float* w, int out_ch, int in_total, void* dst, void* stream);
 
 /*

@@ -92,7 +92,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 extern "C" {
 
-int pnp_abi_version(void) { return 1; }
+int pnp_abi_version(void) { return 2; }
 
 const char* pnp_last_error(void) { return g_err; }
 
@@ -133,8 +133,8 @@ int pnp_lr_im2col(const float* lr, int64_t sn, int64_t sc, int64_t sy, void* dst
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_lr_im2col");
 }
 
-int pnp_pack_conv3x3(const float* w, int n_experts, const float* coef, int out_ch, int in_total,
-                     int in_begin, int in_begin2, int in_count, void* dst, int center_chunks,
+int pnp_pack_conv3x3(const float* w, int n_experts, const float* coef, const float* row_scale, int out_ch,
+                     int in_total, int in_begin, int in_begin2, int in_count, void* dst, int center_chunks,
                      void* stream) {
   if (!w || !dst) return fail(PNP_ERR_ARG, "pnp_pack_conv3x3: null pointer");
   if (n_experts < 1 || (coef == nullptr && n_experts != 1) || out_ch < 1 || out_ch > 64 || in_count < 1 ||
@@ -145,14 +145,14 @@ int pnp_pack_conv3x3(const float* w, int n_experts, const float* coef, int out_c
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
-  cudaError_t e = pnp::launch_pack_conv3x3(w, n_experts, coef, out_ch, in_total, in_begin, in_begin2, in_count,
+  cudaError_t e = pnp::launch_pack_conv3x3(w, n_experts, coef, row_scale, out_ch, in_total, in_begin, in_begin2, in_count,
                                            dst, center_chunks, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_pack_conv3x3");
 }
 
-int pnp_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, int out_ch, int in_total,
-                              int in_begin, int in_begin2, int in_count, void* dst, int tap_n,
-                              void* stream) {
+int pnp_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, const float* row_scale,
+                              int out_ch, int in_total, int in_begin, int in_begin2, int in_count, void* dst,
+                              int tap_n, void* stream) {
   if (!w || !dst) return fail(PNP_ERR_ARG, "pnp_pack_conv3x3_rowstack: null pointer");
   if (n_experts < 1 || (coef == nullptr && n_experts != 1) || out_ch < 1 || (tap_n != 64 && tap_n != 16) ||
       out_ch > tap_n || in_count < 1 || in_count > 64 || in_begin < 0 || in_begin + in_count > in_total ||
@@ -161,7 +161,7 @@ int pnp_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, 
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
-  cudaError_t e = pnp::launch_pack_conv3x3_rowstack(w, n_experts, coef, out_ch, in_total, in_begin, in_begin2,
+  cudaError_t e = pnp::launch_pack_conv3x3_rowstack(w, n_experts, coef, row_scale, out_ch, in_total, in_begin, in_begin2,
                                                     in_count, dst, tap_n, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_pack_conv3x3_rowstack");
 }

@@ -155,8 +155,8 @@ __device__ __forceinline__ size_t packed_offset(int block, int row, int col) {
 
 __global__ void __launch_bounds__(256)
 pack_conv3x3_kernel(const float* __restrict__ w, int n_experts, const float* __restrict__ coef,
-                    int out_ch, int in_total, int in_begin, int in_begin2, int in_count,
-                    uint8_t* __restrict__ dst, int center_chunks) {
+                    const float* __restrict__ row_scale, int out_ch, int in_total, int in_begin, int in_begin2,
+                    int in_count, uint8_t* __restrict__ dst, int center_chunks) {
   // one thread per (tap, row<64, col<64)
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 9 * 64 * 64) return;
@@ -170,6 +170,7 @@ pack_conv3x3_kernel(const float* __restrict__ w, int n_experts, const float* __r
       if (in_begin2 >= 0) v += w[e * per_expert + ((size_t)row * in_total + in_begin2 + col) * 9 + tap];
       acc = fmaf(ce, v, acc);
     }
+    if (row_scale) acc *= row_scale[row];      // SE gain folded into the mixed kernel (per out channel)
   }
   const int block = (tap == 4) ? 0 : (center_chunks + (tap < 4 ? tap : tap - 1));
   *reinterpret_cast<__nv_bfloat16*>(dst + packed_offset(block, row, col)) = __float2bfloat16_rn(acc);
@@ -179,8 +180,8 @@ pack_conv3x3_kernel(const float* __restrict__ w, int n_experts, const float* __r
 // holding the weights of ky = 2 - sb (dy = +1, 0, -1); rows are 128-byte, 128B-swizzled.
 __global__ void __launch_bounds__(256)
 pack_conv3x3_rowstack_kernel(const float* __restrict__ w, int n_experts, const float* __restrict__ coef,
-                             int out_ch, int in_total, int in_begin, int in_begin2, int in_count,
-                             uint8_t* __restrict__ dst, int tap_n) {
+                             const float* __restrict__ row_scale, int out_ch, int in_total, int in_begin,
+                             int in_begin2, int in_count, uint8_t* __restrict__ dst, int tap_n) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int per_dx = 3 * tap_n * 64;
   if (idx >= 3 * per_dx) return;
@@ -198,6 +199,7 @@ pack_conv3x3_rowstack_kernel(const float* __restrict__ w, int n_experts, const f
       if (in_begin2 >= 0) v += w[e * per_expert + ((size_t)o * in_total + in_begin2 + col) * 9 + ky * 3 + kx];
       acc = fmaf(ce, v, acc);
     }
+    if (row_scale) acc *= row_scale[o];
   }
   const size_t off = (size_t)dxi * (3 * tap_n * 128) + (size_t)r * 128 + (size_t)((((col >> 3) ^ (r & 7)) << 4)) +
                      (size_t)(col & 7) * 2;
@@ -231,21 +233,21 @@ pack_aux_kernel(const float* __restrict__ w, int out_ch, int in_total, uint8_t* 
   *reinterpret_cast<__nv_bfloat16*>(dst + packed_offset(0, row, col)) = __float2bfloat16_rn(v);
 }
 
-cudaError_t launch_pack_conv3x3(const float* w, int n_experts, const float* coef, int out_ch, int in_total,
-                                int in_begin, int in_begin2, int in_count, void* dst, int center_chunks,
-                                cudaStream_t stream) {
+cudaError_t launch_pack_conv3x3(const float* w, int n_experts, const float* coef, const float* row_scale,
+                                int out_ch, int in_total, int in_begin, int in_begin2, int in_count, void* dst,
+                                int center_chunks, cudaStream_t stream) {
   pack_conv3x3_kernel<<<(9 * 64 * 64 + 255) / 256, 256, 0, stream>>>(
-      w, n_experts, coef, out_ch, in_total, in_begin, in_begin2, in_count, reinterpret_cast<uint8_t*>(dst),
+      w, n_experts, coef, row_scale, out_ch, in_total, in_begin, in_begin2, in_count, reinterpret_cast<uint8_t*>(dst),
       center_chunks);
   return cudaGetLastError();
 }
 
-cudaError_t launch_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, int out_ch,
-                                         int in_total, int in_begin, int in_begin2, int in_count, void* dst,
-                                         int tap_n, cudaStream_t stream) {
+cudaError_t launch_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef,
+                                         const float* row_scale, int out_ch, int in_total, int in_begin,
+                                         int in_begin2, int in_count, void* dst, int tap_n, cudaStream_t stream) {
   const int total = 3 * 3 * tap_n * 64;
   pack_conv3x3_rowstack_kernel<<<(total + 255) / 256, 256, 0, stream>>>(
-      w, n_experts, coef, out_ch, in_total, in_begin, in_begin2, in_count, reinterpret_cast<uint8_t*>(dst), tap_n);
+      w, n_experts, coef, row_scale, out_ch, in_total, in_begin, in_begin2, in_count, reinterpret_cast<uint8_t*>(dst), tap_n);
   return cudaGetLastError();
 }
 

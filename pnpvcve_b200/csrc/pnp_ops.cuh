@@ -12,12 +12,12 @@ cudaError_t launch_mv_warp(const void* src, const float* flow_x, const float* fl
                            cudaStream_t stream);
 cudaError_t launch_lr_im2col(const float* lr, long long sn, long long sc, long long sy, void* dst, int N,
                              int H, int W, int num_sms, cudaStream_t stream);
-cudaError_t launch_pack_conv3x3(const float* w, int n_experts, const float* coef, int out_ch, int in_total,
-                                int in_begin, int in_begin2, int in_count, void* dst, int center_chunks,
-                                cudaStream_t stream);
-cudaError_t launch_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, int out_ch,
-                                         int in_total, int in_begin, int in_begin2, int in_count, void* dst,
-                                         int tap_n, cudaStream_t stream);
+cudaError_t launch_pack_conv3x3(const float* w, int n_experts, const float* coef, const float* row_scale,
+                                int out_ch, int in_total, int in_begin, int in_begin2, int in_count, void* dst,
+                                int center_chunks, cudaStream_t stream);
+cudaError_t launch_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef,
+                                         const float* row_scale, int out_ch, int in_total, int in_begin,
+                                         int in_begin2, int in_count, void* dst, int tap_n, cudaStream_t stream);
 cudaError_t launch_pack_rows(const float* w, int rows, int cols, long long row_stride, long long col_stride,
                              void* dst, int row_offset, cudaStream_t stream);
 cudaError_t launch_pack_aux(const float* w, int out_ch, int in_total, void* dst, cudaStream_t stream);

@@ -172,13 +172,15 @@ class BaeEngine:
         self.mix_cache = {}
         return st
 
-    def _mixed_conv2(self, st, crf_value, coef_row, dev):
-        """Expert-mixed conv2 + stacked 1x1 partition convs for every block, per distinct CRF.
+    def _mixed_conv2(self, st, key, coef_row, gamma_row, dev):
+        """Expert-mixed conv2 (SE gain folded in) + stacked 1x1 partition convs for every block.
 
-        Dynamic_conv2d_se.forward (sr_backbone_utils.py:198-199) re-mixes per block and frame; the
-        mixture only depends on the frame's CRF, so it is cached per value.
+        Dynamic_conv2d_se.forward (sr_backbone_utils.py:198-208) re-mixes per block and frame and
+        multiplies the output by gamma; the mixture only depends on the frame's CRF and gamma on
+        its QP, so the packed kernels gamma_o * sum_e a_e W_e are cached per distinct (CRF, QP)
+        pair -- 3 pairs per clip in the IPB configs, at most ~15 in the CRF config.
         """
-        hit = self.mix_cache.get(crf_value)
+        hit = self.mix_cache.get(key)
         if hit is not None:
             return hit
         packs = {}
@@ -188,14 +190,15 @@ class BaeEngine:
                 # block launch A stays on the tap-major kernel (centre tap N=256): its row-stacked
                 # variant is correct but its single partition-accumulator hand-off is slower for now
                 buf = ops.new_wpack(12, dev)
-                ops.pack_conv3x3(st[name + "_conv2_w"][k], buf, coef=coef_row, center_chunks=4)
+                ops.pack_conv3x3(st[name + "_conv2_w"][k], buf, coef=coef_row, center_chunks=4,
+                                 row_scale=gamma_row)
                 for j, w1 in enumerate(st[name + "_1x1"][k]):
                     ops.pack_rows(w1, buf, 64 * (j + 1))
                 lst.append(buf)
             packs[name] = lst
         if len(self.mix_cache) > 64:
             self.mix_cache.clear()
-        self.mix_cache[crf_value] = packs
+        self.mix_cache[key] = packs
         return packs
 
     # ------------------------------------------------------------------ buffers
@@ -247,9 +250,10 @@ class BaeEngine:
         st = self._pack_static(dev)
         nb = st["nb"]
         # one D2H copy for everything the host needs (the reference syncs 2(T-1)n+1 times)
-        cond = torch.stack([slices.reshape(n, t).float(), base_QPs.reshape(n, t).float()], 0).cpu()
+        cond = torch.stack([slices.reshape(n, t).float(), base_QPs.reshape(n, t).float(),
+                            QPs.reshape(n, t).float()], 0).cpu()
         key_rows = keyframe_rows(cond[0])
-        crf_host = cond[1]
+        crf_host, qp_host = cond[1], cond[2]
 
         experts, gamma = ops.caa_heads(base_QPs.reshape(-1).float().contiguous(),
                                        QPs.reshape(-1).float().contiguous(), st["caa"], m.num_experts)
@@ -285,10 +289,9 @@ class BaeEngine:
             nonlocal launches
             f = b * t + i
             par = par_map[b:b + 1, i]
-            g = gamma[f]
             other = buf["xb"] if x is buf["xa"] else buf["xa"]
             for k in range(nb):
-                conv(stream, x, mixed[name][k], out=buf["t"], scale=g, bias=bias_tab[f, blk_off + k],
+                conv(stream, x, mixed[name][k], out=buf["t"], bias=bias_tab[f, blk_off + k],
                      par=par, act=PNP_ACT_RELU, label="block_a")
                 o = dst if k == nb - 1 else other
                 conv(stream, buf["t"], st[name + "_conv1_w"][k], out=o, idt=x,
@@ -301,7 +304,7 @@ class BaeEngine:
             # ---------------- backward-time propagation (iconvsr_ipb_par.py:67-100)
             for i in range(t - 1, -1, -1):
                 f = b * t + i
-                mixed = self._mixed_conv2(st, float(crf_host[b, i]), experts[f], dev)
+                mixed = self._mixed_conv2(st, (float(crf_host[b, i]), float(qp_host[b, i])), experts[f], gamma[f], dev)
                 ops.lr_im2col(lrs[b:b + 1, i], buf["lr64"])
                 launches += 1
                 x0 = buf["xa"]
@@ -329,7 +332,7 @@ class BaeEngine:
             # ---------------- forward-time propagation + reconstruction (:102-147)
             for i in range(t):
                 f = b * t + i
-                mixed = self._mixed_conv2(st, float(crf_host[b, i]), experts[f], dev)
+                mixed = self._mixed_conv2(st, (float(crf_host[b, i]), float(qp_host[b, i])), experts[f], gamma[f], dev)
                 ops.lr_im2col(lrs[b:b + 1, i], buf["lr64"])
                 launches += 1
                 x0 = buf["xa"]

@@ -77,7 +77,8 @@ def lr_im2col(lr, dst):
                                  _stream()), "pnp_lr_im2col")
 
 
-def pack_conv3x3(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=None, center_chunks=1):
+def pack_conv3x3(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=None, center_chunks=1,
+                 row_scale=None):
     """w fp32 (O,I,3,3) or (E,O,I,3,3) contiguous -> packed blocks in dst (uint8)."""
     if w.dtype != torch.float32 or not w.is_contiguous():
         raise ValueError("pack_conv3x3: w must be contiguous fp32")
@@ -87,7 +88,7 @@ def pack_conv3x3(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=None, cen
         e, o, i = w.shape[:3]
     in_count = i - in_begin if in_count is None else in_count
     lib = _lib.load()
-    _lib.check(lib.pnp_pack_conv3x3(_ptr(w), e, _ptr(coef), o, i, in_begin, in_begin2, in_count,
+    _lib.check(lib.pnp_pack_conv3x3(_ptr(w), e, _ptr(coef), _ptr(row_scale), o, i, in_begin, in_begin2, in_count,
                                     _ptr(dst), center_chunks, _stream()), "pnp_pack_conv3x3")
 
 
@@ -101,7 +102,8 @@ def new_wpack_rowstack(device, tap_n=64, with_aux=False, with_par=False):
     return torch.zeros(n, dtype=torch.uint8, device=device)
 
 
-def pack_conv3x3_rowstack(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=None, tap_n=64):
+def pack_conv3x3_rowstack(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=None, tap_n=64,
+                          row_scale=None):
     """w fp32 (O,I,3,3) or (E,O,I,3,3) -> row-stacked blocks [kx][ky=2,1,0][tap_n rows] in dst."""
     if w.dtype != torch.float32 or not w.is_contiguous():
         raise ValueError("pack_conv3x3_rowstack: w must be contiguous fp32")
@@ -111,7 +113,8 @@ def pack_conv3x3_rowstack(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=
         e, o, i = w.shape[:3]
     in_count = i - in_begin if in_count is None else in_count
     lib = _lib.load()
-    _lib.check(lib.pnp_pack_conv3x3_rowstack(_ptr(w), e, _ptr(coef), o, i, in_begin, in_begin2, in_count,
+    _lib.check(lib.pnp_pack_conv3x3_rowstack(_ptr(w), e, _ptr(coef), _ptr(row_scale), o, i, in_begin, in_begin2,
+                                             in_count,
                                              _ptr(dst), tap_n, _stream()), "pnp_pack_conv3x3_rowstack")
 
 

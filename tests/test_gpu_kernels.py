@@ -249,3 +249,17 @@ def test_caa_heads_match_oracle(dev):
     tab = ops.mix_bias(b2, experts, gamma)
     ref = torch.einsum("fe,bec->fbc", experts, b2) * gamma[:, None, :]
     assert (tab - ref).abs().max().item() < 1e-5
+
+
+def test_pack_row_scale_equals_output_gain(dev):
+    """SE gain folded at pack time: conv(x, g*W) == g * conv(x, W)  (sr_backbone_utils.py:207-208)."""
+    g = torch.Generator(device=dev).manual_seed(21)
+    w = bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05)
+    gain = torch.rand(64, generator=g, device=dev) * 2.0
+    x = bf(torch.randn((1, 64, 64, 128), generator=g, device=dev))
+    out = ops.new_feature(1, 64, 128, dev)
+    for layout in (0, 1):
+        wp = ops.new_wpack(9, dev) if layout == 0 else ops.new_wpack_rowstack(dev)
+        (ops.pack_conv3x3 if layout == 0 else ops.pack_conv3x3_rowstack)(w, wp, row_scale=gain)
+        ops.conv3x3(nhwc(x), wp, out=out, wlayout=layout)
+        assert_bf16_close(nchw(out), F.conv2d(x, bf(w * gain.view(-1, 1, 1, 1)), padding=1), "row_scale")

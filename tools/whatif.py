@@ -21,6 +21,11 @@ if len(sys.argv) > 1:
     a = timeit(lambda: ops.conv3x3(x, wp9, out=out))
     b = timeit(lambda: ops.conv3x3(x, wp9, out=out, idt=idt))
     c = timeit(lambda: ops.conv3x3(x, wp, out=out, par=par, act=2))
+    scale = torch.rand(64, device=dev) + 0.5; bias = torch.randn(64, device=dev)
+    c2 = timeit(lambda: ops.conv3x3(x, wp, out=out, par=par, scale=scale, bias=bias, act=2))
+    par1 = torch.nn.functional.one_hot(torch.randint(0, 3, (1, h // 8, w // 8), device=dev), 3).permute(0, 3, 1, 2).float().repeat_interleave(8, 2).repeat_interleave(8, 3).contiguous() / 255
+    c3 = timeit(lambda: ops.conv3x3(x, wp, out=out, par=par1, scale=scale, bias=bias, act=2))
+    print(f"tap-major +par+scale+bias {c2:6.1f} us ; with one-hot/255 partition map {c3:6.1f} us", flush=True)
     wr = ops.new_wpack_rowstack(dev); ops.pack_conv3x3_rowstack(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wr)
     ra = timeit(lambda: ops.conv3x3(x, wr, out=out, wlayout=1))
     rb = timeit(lambda: ops.conv3x3(x, wr, out=out, idt=idt, wlayout=1))
