@@ -275,26 +275,49 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     d2h = out_host.numel() * out_host.element_size()
 
-    def step_e2e(i):
-        src = host[0]
-        clip = {k: v.to(dev, non_blocking=True) for k, v in src.items()}
-        out = net(*synthetic.generator_args(clip))
-        out_host.copy_(out, non_blocking=True)
-        local = driver.frame_metrics(out)[0:1]
-        driver.gather_metrics(local, world, rank, world)
+    # Software-pipelined like a real serving loop: a copy stream uploads clip i+1 while clip i is
+    # enhanced, a second one downloads the frames of clip i-1.  Every step still pays its full H2D
+    # and D2H inside the timed region; only their overlap with compute is exploited.
+    main = torch.cuda.current_stream()
+    up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def upload():
+        with torch.cuda.stream(up):
+            clip = {k: v.to(dev, non_blocking=True) for k, v in host[0].items()}
+            ev = torch.cuda.Event()
+            ev.record(up)
+        return clip, ev
+
+    def run_e2e(n_steps):
+        nxt = upload()
+        for i in range(n_steps):
+            clip, ev = nxt
+            if i + 1 < n_steps:
+                nxt = upload()
+            main.wait_event(ev)
+            out = net(*synthetic.generator_args(clip))
+            for v in clip.values():
+                v.record_stream(main)
+            local = driver.frame_metrics(out)[0:1]
+            driver.gather_metrics(local, world, rank, world)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(down):
+                down.wait_event(done)
+                out_host.copy_(out, non_blocking=True)
+                out.record_stream(down)
+        main.wait_stream(down)
 
     del clips
     torch.cuda.empty_cache()
     with torch.no_grad():
         e2e_warm = min(args.warmup, 1) if args.frames >= 50 else args.warmup
-        for i in range(e2e_warm):
-            step_e2e(i)
+        run_e2e(max(e2e_warm, 1))
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2e_steps = args.steps
         f0.record()
-        for i in range(e2e_steps):
-            step_e2e(i)
+        run_e2e(e2e_steps)
         f1.record()
         barrier()
     ms2 = torch.tensor([f0.elapsed_time(f1)], device=dev)

@@ -88,7 +88,7 @@ int pnp_pack_rows(const float* w, int rows, int cols, int64_t row_stride, int64_
  * 16 for the 64->3 tail; total 9*tap_n*128 bytes.  Same mixing arguments as pnp_pack_conv3x3. */
 int pnp_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, const float* row_scale,
                               int out_ch, int in_total, int in_begin, int in_begin2, int in_count, void* dst,
-                              int tap_n, void* stream);
+                              int tap_n, int flip_ky, void* stream);
 int pnp_pack_aux(const float* w, int out_ch, int in_total, void* dst, void* stream);
 
 /*
@@ -145,6 +145,9 @@ typedef struct pnp_conv_desc {
                           followed by the 8192-byte aux block when aux is given, or by the three 1x1
                           partition convs as 192 packed rows (pnp_pack_rows, offsets 0/64/128 from there)
                           when par is given; par then excludes aux and idt) */
+  int32_t flip_y;      /* PNP_WLAYOUT_ROWSTACK only: process rows bottom-up.  The result is identical when wpack
+                          was packed with flip_ky = 1; alternating directions between dependent launches
+                          makes each launch read first what its predecessor wrote last (L2 hits). */
 } pnp_conv_desc;
 
 int pnp_conv3x3(const pnp_conv_desc* desc, void* stream);

@@ -36,7 +36,7 @@ class ConvDesc(_c.Structure):
         ("N", _c.c_int32), ("H", _c.c_int32), ("W", _c.c_int32),
         ("n_wchunks", _c.c_int32), ("center_n", _c.c_int32), ("tap_n", _c.c_int32),
         ("aux_k16", _c.c_int32), ("act", _c.c_int32), ("mode", _c.c_int32),
-        ("wlayout", _c.c_int32),
+        ("wlayout", _c.c_int32), ("flip_y", _c.c_int32),
     ]
 
 
@@ -48,7 +48,7 @@ _PROTOS = {
     "pnp_mv_warp": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
     "pnp_lr_im2col": (_i, [_vp, _i64, _i64, _i64, _vp, _i, _i, _i, _vp]),
     "pnp_pack_conv3x3": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
-    "pnp_pack_conv3x3_rowstack": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "pnp_pack_conv3x3_rowstack": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "pnp_pack_rows": (_i, [_vp, _i, _i, _i64, _i64, _vp, _i, _vp]),
     "pnp_pack_aux": (_i, [_vp, _i, _i, _vp, _vp]),
     "pnp_caa_heads": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),

@@ -92,7 +92,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 extern "C" {
 
-int pnp_abi_version(void) { return 2; }
+int pnp_abi_version(void) { return 3; }
 
 const char* pnp_last_error(void) { return g_err; }
 
@@ -152,7 +152,7 @@ int pnp_pack_conv3x3(const float* w, int n_experts, const float* coef, const flo
 
 int pnp_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, const float* row_scale,
                               int out_ch, int in_total, int in_begin, int in_begin2, int in_count, void* dst,
-                              int tap_n, void* stream) {
+                              int tap_n, int flip_ky, void* stream) {
   if (!w || !dst) return fail(PNP_ERR_ARG, "pnp_pack_conv3x3_rowstack: null pointer");
   if (n_experts < 1 || (coef == nullptr && n_experts != 1) || out_ch < 1 || (tap_n != 64 && tap_n != 16) ||
       out_ch > tap_n || in_count < 1 || in_count > 64 || in_begin < 0 || in_begin + in_count > in_total ||
@@ -162,7 +162,7 @@ int pnp_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, 
   int rc = device_info(&d);
   if (rc) return rc;
   cudaError_t e = pnp::launch_pack_conv3x3_rowstack(w, n_experts, coef, row_scale, out_ch, in_total, in_begin, in_begin2,
-                                                    in_count, dst, tap_n, static_cast<cudaStream_t>(stream));
+                                                    in_count, dst, tap_n, flip_ky != 0, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_pack_conv3x3_rowstack");
 }
 
@@ -285,6 +285,7 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   p.has_id = c->idt != nullptr;
   p.act = c->act;
   p.mode = last ? pnp::kModeLast : pnp::kModeBf16;
+  p.flip_y = (rowstack && c->flip_y) ? 1 : 0;
   p.base_off_mode = g_base_off_mode;
   {
     const char* dbg = getenv("PNP_DEBUG_SKIP");   // what-if profiling only; results are wrong when set

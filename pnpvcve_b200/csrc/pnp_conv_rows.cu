@@ -134,6 +134,11 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
   const int s_a = p.s_a;
   const int n_io = p.n_io;
   const bool last_mode = (p.mode == kModeLast);
+  // flip_y: the image is walked bottom-up (weights are packed with ky mirrored), so that a launch
+  // reads first what the previous launch wrote last -- those rows are still in L2.
+  const int y_flip_base = p.flip_y ? p.H - 1 : 0;
+  const int y_sign = p.flip_y ? -1 : 1;
+#define PNP_Y(yy) (y_flip_base + y_sign * (yy))
 
   if (threadIdx.x < 64) {
     misc->scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.0f;
@@ -201,7 +206,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
             mbar_arrive(fb);
           } else {
             mbar_arrive_expect_tx(fb, kRowBytes);
-            tma_load_4d(a_smem + ar.slot * kASlotBytes, &p.tm_src, fb, 0, x0 - 1, s.y_b + j, s.n);
+            tma_load_4d(a_smem + ar.slot * kASlotBytes, &p.tm_src, fb, 0, x0 - 1, PNP_Y(s.y_b + j), s.n);
           }
           if (j >= 0 && j < s.len) {       // per-output-row operands of row y_b + j
             if (p.aux_k16 > 0) {
@@ -213,7 +218,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
               aux_step[as] = sc;           // consumed in this very step (centre row)
               const uint32_t ab = smem_u32(&misc->aux_full[as]);
               mbar_arrive_expect_tx(ab, kTileBytes);
-              tma_load_4d(aux_smem + as * kTileBytes, &p.tm_aux, ab, 0, x0, s.y_b + j, s.n);
+              tma_load_4d(aux_smem + as * kTileBytes, &p.tm_aux, ab, 0, x0, PNP_Y(s.y_b + j), s.n);
             }
             ++ord;
           }
@@ -434,7 +439,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
     float dy_cur[kPar ? 32 : 1], dy_nxt[kPar ? 32 : 1];
     auto par_part = [&](const TileCur& c, float* dy) {
       const int x = c.s.strip * kTilePx + row;
-      const int y = c.s.y_b + c.o;
+      const int y = PNP_Y(c.s.y_b + c.o);
       float p0 = 0.f, p1 = 0.f, p2 = 0.f;
       if (x < p.W) {
         const float* pp = p.par + (long long)c.s.n * p.par_sn + (long long)y * p.par_sy + x;
@@ -468,7 +473,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
     auto load_id = [&](const TileCur& c, uint32_t slot) {
       const uint32_t ib = smem_u32(&misc->id_full[slot]);
       mbar_arrive_expect_tx(ib, kTileBytes);
-      tma_load_4d(io_smem + slot * kTileBytes, &p.tm_id, ib, 0, c.s.strip * kTilePx, c.s.y_b + c.o, c.s.n);
+      tma_load_4d(io_smem + slot * kTileBytes, &p.tm_id, ib, 0, c.s.strip * kTilePx, PNP_Y(c.s.y_b + c.o), c.s.n);
     };
     if (p.has_id && store_warp) {
       if (elect_one()) {
@@ -488,7 +493,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       const uint32_t ord = cur.ord;
       const int x = s.strip * kTilePx + row;
       const bool valid = x < p.W;
-      const int y = s.y_b + o;
+      const int y = PNP_Y(s.y_b + o);
       const uint32_t sc_last = cur.sc0 + (uint32_t)(min(o + 1, s.j_last) - s.j_first);
       const uint32_t slot = ord % kAccRing;
       const uint32_t taddr = lane_base + slot * tap_n;
@@ -521,9 +526,22 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         continue;
       }
       const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && ord < 64 && threadIdx.x == 64;
-      // the partition blend of the NEXT row comes first: its accumulators are ready a full step
-      // before this row's 3x3 result, and the MMA thread needs the region back early in that step
-      if (kPar && nxt.valid) par_part(nxt, dy_nxt);
+      // Partition path: the 1x1 accumulators of the NEXT row finish with the same step that completes
+      // this row's 3x3 result (they are issued last in that step), so both are fetched from TMEM in
+      // one batch behind one barrier wait; the blend of the next row is kept in registers (dy_nxt).
+      float pn0 = 0.f, pn1 = 0.f, pn2 = 0.f;
+      uint32_t sc_wait = sc_last;
+      if (kPar && nxt.valid) {
+        const int xn = nxt.s.strip * kTilePx + row;
+        if (xn < p.W) {
+          const float* pp = p.par + (long long)nxt.s.n * p.par_sn + (long long)PNP_Y(nxt.s.y_b + nxt.o) * p.par_sy + xn;
+          pn0 = __ldg(pp);
+          pn1 = __ldg(pp + p.par_sc);
+          pn2 = __ldg(pp + 2 * p.par_sc);
+        }
+        const uint32_t sc_centre_next = nxt.sc0 + (uint32_t)(nxt.o - nxt.s.j_first);
+        sc_wait = max(sc_last, sc_centre_next);          // differs only across strip segments
+      }
       const uint32_t s_io = ior.slot;
       if (store_warp) {
         if (elect_one()) {
@@ -541,7 +559,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       } else {
         named_bar_sync(1, 256);
       }
-      mbar_wait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> 3) & 1, 9);
+      mbar_wait(smem_u32(&misc->step_done[sc_wait & (kStepRing - 1)]), (sc_wait >> 3) & 1, 9);
       tc_fence_after();
       if (tr) p.trace[ord * 8 + 3] = clock64();
       uint8_t* rowp = sgen + L.io + s_io * kTileBytes + row * 128;
@@ -549,6 +567,19 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       if (p.debug_skip & 4) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      } else if (kPar && nxt.valid) {
+#pragma unroll
+        for (int gg = 0; gg < 2; ++gg) {
+          float a1[16], a2[16], a3[16];
+          const uint32_t col = kParCol + half * 32 + gg * 16;
+          tmem_ld16(taddr + half * 32 + gg * 16, v + gg * 16);
+          tmem_ld16(lane_base + col, a1);
+          tmem_ld16(lane_base + col + 64, a2);
+          tmem_ld16(lane_base + col + 128, a3);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dy_nxt[gg * 16 + j] = fmaf(pn2, a3[j], fmaf(pn1, a2[j], pn0 * a1[j]));
+        }
       } else {
         tmem_ld16(taddr + half * 32, v);
         tmem_ld16(taddr + half * 32 + 16, v + 16);
@@ -556,6 +587,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       }
       tc_fence_before();
       warp_arrive(smem_u32(&misc->acc_free[slot]));   // accumulator is in registers: slot reusable
+      if (kPar && nxt.valid) warp_arrive(smem_u32(&misc->par_free));   // ... and so is the 1x1 region
 #pragma unroll
       for (int gg = 0; gg < 2; ++gg) {
         const int g = half * 2 + gg;
@@ -637,6 +669,8 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
     tmem_dealloc(tmem_base, kTmemCols);
   }
 }
+
+#undef PNP_Y
 
 size_t conv_rows_smem_bytes(const ConvParams& p) {
   const int w_bytes = 3 * 3 * p.tap_n * 128 + (p.aux_k16 > 0 ? kWChunkBytes : 0) +

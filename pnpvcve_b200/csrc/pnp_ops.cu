@@ -188,7 +188,7 @@ pack_conv3x3_kernel(const float* __restrict__ w, int n_experts, const float* __r
 __global__ void __launch_bounds__(256)
 pack_conv3x3_rowstack_kernel(const float* __restrict__ w, int n_experts, const float* __restrict__ coef,
                              const float* __restrict__ row_scale, int out_ch, int in_total, int in_begin,
-                             int in_begin2, int in_count, uint8_t* __restrict__ dst, int tap_n) {
+                             int in_begin2, int in_count, uint8_t* __restrict__ dst, int tap_n, bool flip_ky) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int per_dx = 3 * tap_n * 64;
   if (idx >= 3 * per_dx) return;
@@ -196,7 +196,7 @@ pack_conv3x3_rowstack_kernel(const float* __restrict__ w, int n_experts, const f
   const int rem = idx - dxi * per_dx;
   const int col = rem & 63, r = rem >> 6;          // r = sb * tap_n + o
   const int sb = r / tap_n, o = r - sb * tap_n;
-  const int ky = 2 - sb, kx = dxi;
+  const int ky = flip_ky ? sb : 2 - sb, kx = dxi;    // mirrored for bottom-up traversal (flip_y)
   float acc = 0.f;
   if (o < out_ch && col < in_count) {
     const size_t per_expert = (size_t)out_ch * in_total * 9;
@@ -251,10 +251,11 @@ cudaError_t launch_pack_conv3x3(const float* w, int n_experts, const float* coef
 
 cudaError_t launch_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef,
                                          const float* row_scale, int out_ch, int in_total, int in_begin,
-                                         int in_begin2, int in_count, void* dst, int tap_n, cudaStream_t stream) {
+                                         int in_begin2, int in_count, void* dst, int tap_n, bool flip_ky,
+                                         cudaStream_t stream) {
   const int total = 3 * 3 * tap_n * 64;
   pack_conv3x3_rowstack_kernel<<<(total + 255) / 256, 256, 0, stream>>>(
-      w, n_experts, coef, row_scale, out_ch, in_total, in_begin, in_begin2, in_count, reinterpret_cast<uint8_t*>(dst), tap_n);
+      w, n_experts, coef, row_scale, out_ch, in_total, in_begin, in_begin2, in_count, reinterpret_cast<uint8_t*>(dst), tap_n, flip_ky);
   return cudaGetLastError();
 }
 

@@ -17,7 +17,8 @@ cudaError_t launch_pack_conv3x3(const float* w, int n_experts, const float* coef
                                 int center_chunks, cudaStream_t stream);
 cudaError_t launch_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef,
                                          const float* row_scale, int out_ch, int in_total, int in_begin,
-                                         int in_begin2, int in_count, void* dst, int tap_n, cudaStream_t stream);
+                                         int in_begin2, int in_count, void* dst, int tap_n, bool flip_ky,
+                                         cudaStream_t stream);
 cudaError_t launch_pack_rows(const float* w, int rows, int cols, long long row_stride, long long col_stride,
                              void* dst, int row_offset, cudaStream_t stream);
 cudaError_t launch_pack_aux(const float* w, int out_ch, int in_total, void* dst, cudaStream_t stream);

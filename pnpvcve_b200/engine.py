@@ -67,11 +67,11 @@ class _Launcher:
         self.seen = {}
 
     def __call__(self, stream, src, wpack, out=None, aux=None, idt=None, scale=None, bias=None,
-                 par=None, act=PNP_ACT_NONE, lq=None, outf=None, label=None):
+                 par=None, act=PNP_ACT_NONE, lq=None, outf=None, label=None, flip_y=False):
         # row-stacked weight layout (one source row feeds three output rows, N=192 MMAs) for every
         # conv except the partition-modulated block launch A
         ops.fill_conv_desc(self.desc, src, wpack, out, aux, idt, scale, bias, par, act, lq, outf,
-                           wlayout=0 if par is not None else 1)
+                           wlayout=0 if par is not None else 1, flip_y=flip_y)
         timed = self.prof is not None and label in self.prof
         if timed:                                  # bracket every prof_every-th launch of this label
             k = self.seen.get(label, 0)
@@ -146,8 +146,10 @@ class BaeEngine:
                 st["fwd_nb"] = pack(67)
             conv1_w, conv1_b, c2w, c2b, onebyone = [], [], [], [], []
             for blk in branch.main:
+                # block launch B walks the image bottom-up (flip_y): launch A wrote its bottom rows
+                # last, so B finds them in L2; B in turn writes the top rows last, where A starts
                 buf = ops.new_wpack_rowstack(dev)
-                ops.pack_conv3x3_rowstack(f32(blk.conv1.weight), buf)
+                ops.pack_conv3x3_rowstack(f32(blk.conv1.weight), buf, flip_ky=True)
                 conv1_w.append(buf)
                 conv1_b.append(f32(blk.conv1.bias))
                 c2w.append(f32(blk.conv2.weight))
@@ -295,7 +297,7 @@ class BaeEngine:
                      par=par, act=PNP_ACT_RELU, label="block_a")
                 o = dst if k == nb - 1 else other
                 conv(stream, buf["t"], st[name + "_conv1_w"][k], out=o, idt=x,
-                     bias=st[name + "_conv1_b"][k], act=PNP_ACT_NONE, label="block_b")
+                     bias=st[name + "_conv1_b"][k], act=PNP_ACT_NONE, label="block_b", flip_y=True)
                 x, other = o, x
                 launches += 2
 

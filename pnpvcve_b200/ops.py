@@ -103,7 +103,7 @@ def new_wpack_rowstack(device, tap_n=64, with_aux=False, with_par=False):
 
 
 def pack_conv3x3_rowstack(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=None, tap_n=64,
-                          row_scale=None):
+                          row_scale=None, flip_ky=False):
     """w fp32 (O,I,3,3) or (E,O,I,3,3) -> row-stacked blocks [kx][ky=2,1,0][tap_n rows] in dst."""
     if w.dtype != torch.float32 or not w.is_contiguous():
         raise ValueError("pack_conv3x3_rowstack: w must be contiguous fp32")
@@ -115,7 +115,7 @@ def pack_conv3x3_rowstack(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=
     lib = _lib.load()
     _lib.check(lib.pnp_pack_conv3x3_rowstack(_ptr(w), e, _ptr(coef), _ptr(row_scale), o, i, in_begin, in_begin2,
                                              in_count,
-                                             _ptr(dst), tap_n, _stream()), "pnp_pack_conv3x3_rowstack")
+                                             _ptr(dst), tap_n, int(flip_ky), _stream()), "pnp_pack_conv3x3_rowstack")
 
 
 def pack_rows(w2d, dst, row_offset):
@@ -160,7 +160,7 @@ def mix_bias(conv2_bias, experts, gamma):
 
 
 def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
-                   act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0):
+                   act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False):
     """Fill a ConvDesc in place (reusable across launches)."""
     n, h, w, _ = src.shape
     last = outf is not None
@@ -188,11 +188,12 @@ def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias
     d.act = act
     d.mode = PNP_CONV_LAST if last else PNP_CONV_BF16
     d.wlayout = wlayout
+    d.flip_y = 1 if flip_y else 0
     return d
 
 
 def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
-            act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0):
+            act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False):
     """Fused tcgen05 3x3 conv (see include/pnp_vcve.h: pnp_conv3x3)."""
     _feat_check(src, "src")
     for t, nm in ((out, "out"), (aux, "aux"), (idt, "idt")):
@@ -206,7 +207,7 @@ def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par
             if t.dim() != 4 or t.shape[1] != 3 or t.shape[0] != src.shape[0] or \
                     tuple(t.shape[2:]) != tuple(src.shape[1:3]):
                 raise ValueError(f"conv3x3: {nm} must be (N,3,H,W) matching src")
-    d = fill_conv_desc(ConvDesc(), src, wpack, out, aux, idt, scale, bias, par, act, lq, outf, wlayout)
+    d = fill_conv_desc(ConvDesc(), src, wpack, out, aux, idt, scale, bias, par, act, lq, outf, wlayout, flip_y)
     need = rowstack_bytes(d.tap_n, aux is not None, par is not None) if wlayout == 1 \
         else d.n_wchunks * CHUNK_BYTES
     if wpack.numel() < need:

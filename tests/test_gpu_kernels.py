@@ -263,3 +263,35 @@ def test_pack_row_scale_equals_output_gain(dev):
         (ops.pack_conv3x3 if layout == 0 else ops.pack_conv3x3_rowstack)(w, wp, row_scale=gain)
         ops.conv3x3(nhwc(x), wp, out=out, wlayout=layout)
         assert_bf16_close(nchw(out), F.conv2d(x, bf(w * gain.view(-1, 1, 1, 1)), padding=1), "row_scale")
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 68, 132), (2, 72, 200), (1, 376, 1244)])
+def test_conv_rowstack_bottom_up_equals_top_down(dev, n, h, w):
+    """flip_y + weights packed with mirrored ky: same convolution, rows accumulated in the other order
+    (fp32 sums differ in the last bit, so compare against conv2d, not bit for bit)."""
+    g = torch.Generator(device=dev).manual_seed(h + w)
+    x = nhwc(bf(torch.randn((n, 64, h, w), generator=g, device=dev)))
+    idt = nhwc(bf(torch.randn((n, 64, h, w), generator=g, device=dev)))
+    wt = bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05)
+    bias = torch.randn(64, generator=g, device=dev) * 0.1
+    down, up = ops.new_wpack_rowstack(dev), ops.new_wpack_rowstack(dev)
+    ops.pack_conv3x3_rowstack(wt, down)
+    ops.pack_conv3x3_rowstack(wt, up, flip_ky=True)
+    a, b = ops.new_feature(n, h, w, dev), ops.new_feature(n, h, w, dev)
+    ops.conv3x3(x, down, out=a, idt=idt, bias=bias, act=ops.PNP_ACT_LRELU, wlayout=1)
+    ops.conv3x3(x, up, out=b, idt=idt, bias=bias, act=ops.PNP_ACT_LRELU, wlayout=1, flip_y=True)
+    ref = F.leaky_relu(F.conv2d(nchw(x), wt, bias, padding=1) + nchw(idt), 0.1)
+    assert_bf16_close(nchw(a), ref, "top-down")
+    assert_bf16_close(nchw(b), ref, "bottom-up")
+    assert (a.float() - b.float()).abs().max().item() <= 0.07
+    # 64 -> 3 tail with fp32 output
+    wl = bf(torch.randn((3, 64, 3, 3), generator=g, device=dev) * 0.05)
+    lq = torch.rand((n, 3, h, w), generator=g, device=dev)
+    d16, u16 = ops.new_wpack_rowstack(dev, tap_n=16), ops.new_wpack_rowstack(dev, tap_n=16)
+    ops.pack_conv3x3_rowstack(wl, d16, tap_n=16)
+    ops.pack_conv3x3_rowstack(wl, u16, tap_n=16, flip_ky=True)
+    o1, o2 = torch.empty((n, 3, h, w), device=dev), torch.empty((n, 3, h, w), device=dev)
+    ops.conv3x3(x, d16, lq=lq, outf=o1, wlayout=1)
+    ops.conv3x3(x, u16, lq=lq, outf=o2, wlayout=1, flip_y=True)
+    ref = F.conv2d(nchw(x), wl, padding=1) + lq
+    assert (o1 - ref).abs().max().item() < 1e-4 and (o2 - ref).abs().max().item() < 1e-4

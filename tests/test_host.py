@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/pnp_vcve.h but not exported"
     assert sorted(_lib.EXPORTS) == syms
-    assert _lib.load().pnp_abi_version() == 2
+    assert _lib.load().pnp_abi_version() == 3
 
 
 def test_abi_argument_errors_without_gpu():
@@ -56,8 +56,9 @@ def test_abi_argument_errors_without_gpu():
 
 def test_conv_desc_matches_header_layout():
     d = _lib.ConvDesc()
-    assert ctypes.sizeof(d) == 7 * 8 + 4 * 8 + 4 * 8 + 4 * 8 + 9 * 4 + 4   # 8-byte aligned tail pad
+    assert ctypes.sizeof(d) == 7 * 8 + 4 * 8 + 4 * 8 + 4 * 8 + 11 * 4 + 4   # 8-byte aligned tail pad
     assert _lib.ConvDesc.N.offset == 152 and _lib.ConvDesc.mode.offset == 184
+    assert _lib.ConvDesc.wlayout.offset == 188 and _lib.ConvDesc.flip_y.offset == 192
 
 
 # ------------------------------------------------------------------ registry / boundary

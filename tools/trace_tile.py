@@ -17,9 +17,13 @@ torch.cuda.synchronize()
 os.environ["PNP_TRACE_PTR"] = str(trace.data_ptr())
 PAR = len(sys.argv) > 2
 if PAR:
-    wp9 = ops.new_wpack_rowstack(dev, with_par=True); ops.pack_conv3x3_rowstack(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp9)
+    if LAYOUT == 1:
+        wp9 = ops.new_wpack_rowstack(dev, with_par=True); ops.pack_conv3x3_rowstack(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp9)
+    else:
+        wp9 = ops.new_wpack(12, dev); ops.pack_conv3x3(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp9, center_chunks=4)
     par = torch.rand((1, 3, h, w), device=dev)
-    ops.conv3x3(x, wp9, out=out, par=par, act=2, wlayout=1)
+    bias = torch.randn(64, device=dev)
+    ops.conv3x3(x, wp9, out=out, par=par, bias=bias, act=2, wlayout=LAYOUT)
 else:
     ops.conv3x3(x, wp9, out=out, wlayout=LAYOUT)
 torch.cuda.synchronize()
