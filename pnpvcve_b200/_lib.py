@@ -69,6 +69,13 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.isfile(LIB_PATH):
+        # not a fallback: the same sm_100a library, compiled on demand when nvcc is at hand
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception:  # noqa: BLE001 - reported below
+            pass
+    if not os.path.isfile(LIB_PATH):
         raise PnpError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
             "g.build()'` (nvcc, sm_100a).  pnpvcve_b200 has no CPU / PyTorch fallback.")
