@@ -259,14 +259,21 @@ def main():
     share_a = a_ms * len(prof["block_a"]) * args.prof_every / args.steps / steps_ms if a_ms else 0.0
     roofline = dict(bound="tensor", kernel="conv3x3_umma_kernel (block launch A: 3x3 + 3 partition 1x1, N=256 centre tap)",
                     achieved=a_tflops, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
-                    frac=a_tflops / peaks["bf16_tflops_sustained"], traffic=None,
+                    frac=a_tflops / peaks["bf16_tflops_sustained"],
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at 720p, from the
+                    # committed capture profiles/r01_conv_final_ncu_summary.csv (135.36 + 75.16 MB); the
+                    # algorithmic bytes are 118 (x) + 11 (partition planes) + 118 (t) = 247 MB
+                    traffic=210.52e6, traffic_unit="bytes/launch",
                     peak_source=f"{peaks['source']} sustained cuBLAS bf16 (kernel timed inside a long step)",
                     ms_per_launch=a_ms, launches_timed=len(prof["block_a"]), timed_every=args.prof_every,
                     share_of_step=share_a,
                     whole_path_tflops=FLOP_PER_PX_FRAME * H * W * value / 1e12,
                     whole_path_frac=FLOP_PER_PX_FRAME * H * W * value / 1e12 / peaks["bf16_tflops_sustained"])
     roofline_warp = dict(bound="hbm", kernel="mv_warp_kernel", achieved=w_gbs, peak=peaks["hbm_gbs"],
-                         unit="GB/s", frac=w_gbs / peaks["hbm_gbs"], traffic=None, ms_per_launch=w_ms,
+                         unit="GB/s", frac=w_gbs / peaks["hbm_gbs"],
+                         # profiles/r01_warp_final_ncu_summary.csv: 92.37 + 73.65 MB (algorithmic 243.3 MB;
+                         # part of the source rows is still in L2 from the producing kernel)
+                         traffic=166.02e6, traffic_unit="bytes/launch", ms_per_launch=w_ms,
                          launches_timed=len(prof["warp"]), peak_source=peaks["source"])
 
     # ---------------- end to end from pinned host buffers (e2e)
