@@ -106,6 +106,26 @@ int pnp_mix_bias(const float* conv2_bias, int n_blocks, int n_experts, const flo
                  const float* gamma, int frames, float* out, void* stream);
 
 /*
+ * Side-information rasteriser ("next" row of the scope table): per-block motion-vector records ->
+ * dense motion fields and partition maps, bit-exact replacement of the per-record Python loop of
+ * LoadImageFromFileList_ipb.__call__ (mmedit/datasets/pipelines/loading_ipb.py:328-369) followed by
+ * RescaleToZeroOne on the partition maps (normalization.py:93-99) and FramesToTensor (formating.py:101-138).
+ *   records       : fp32 (R,10): direction, w, h, src_x, src_y, dst_x, dst_y, motion_x, motion_y, scale
+ *   frame_offsets : int32 (T+1): records of frame f are [frame_offsets[f], frame_offsets[f+1])
+ *   is_b          : int32 (T): 1 for B slices
+ *   p_target      : int32 (T): frame that receives the reversed direction>0 records of a non-B frame
+ *                   (the previous non-B frame, loading_ipb.py:351-355,369), -1 if there is none
+ *   owner_fwd/owner_bwd/part_mask : uint32 (T,H,W) workspaces, ZEROED by the caller
+ *   mvs (T,4,H,W), partitions (T,3,H,W) : fp32 outputs, fully overwritten
+ *   status        : device int32, OR-ed with 1 (block area not in {256,128,64}: KeyError in the reference)
+ *                   and 2 (reversed record without a target frame)
+ */
+int pnp_mv_rasterize(const float* records, const int32_t* frame_offsets, const int32_t* is_b,
+                     const int32_t* p_target, int T, int R, int H, int W, uint32_t* owner_fwd,
+                     uint32_t* owner_bwd, uint32_t* part_mask, float* mvs, float* partitions,
+                     int32_t* status, void* stream);
+
+/*
  * K2/K3/K5 -- fused 3x3 convolution on tcgen05 tensor cores (implicit GEMM, TMA fed, TMEM
  * accumulators).  One call replaces one F.conv2d of the reference plus the elementwise work
  * around it:

@@ -18,7 +18,7 @@ EXPORTS = [
     "pnp_abi_version", "pnp_last_error", "pnp_device_check", "pnp_set_base_offset_mode",
     "pnp_mv_warp", "pnp_lr_im2col", "pnp_pack_conv3x3", "pnp_pack_conv3x3_rowstack", "pnp_pack_rows",
     "pnp_pack_aux",
-    "pnp_caa_heads", "pnp_mix_bias", "pnp_conv3x3",
+    "pnp_caa_heads", "pnp_mix_bias", "pnp_mv_rasterize", "pnp_conv3x3",
 ]
 
 _c = ctypes
@@ -53,6 +53,7 @@ _PROTOS = {
     "pnp_pack_aux": (_i, [_vp, _i, _i, _vp, _vp]),
     "pnp_caa_heads": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "pnp_mix_bias": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "pnp_mv_rasterize": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pnp_conv3x3": (_i, [_c.POINTER(ConvDesc), _vp]),
 }
 

@@ -219,6 +219,23 @@ int pnp_mix_bias(const float* conv2_bias, int n_blocks, int n_experts, const flo
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_mix_bias");
 }
 
+int pnp_mv_rasterize(const float* records, const int32_t* frame_offsets, const int32_t* is_b,
+                     const int32_t* p_target, int T, int R, int H, int W, uint32_t* owner_fwd,
+                     uint32_t* owner_bwd, uint32_t* part_mask, float* mvs, float* partitions,
+                     int32_t* status, void* stream) {
+  if (!frame_offsets || !is_b || !p_target || !owner_fwd || !owner_bwd || !part_mask || !mvs || !partitions ||
+      !status || (R > 0 && !records))
+    return fail(PNP_ERR_ARG, "pnp_mv_rasterize: null pointer");
+  if (T < 1 || T > 65535 || R < 0 || H < 1 || H > 65535 || W < 1 || (long long)T * H * W >= (1LL << 31))
+    return fail(PNP_ERR_ARG, "pnp_mv_rasterize: bad shape");
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  cudaError_t e = pnp::launch_mv_rasterize(records, frame_offsets, is_b, p_target, T, R, H, W, owner_fwd, owner_bwd,
+                                           part_mask, mvs, partitions, status, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_mv_rasterize");
+}
+
 int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   if (!c) return fail(PNP_ERR_ARG, "pnp_conv3x3: null descriptor");
   if (!c->src || !c->wpack) return fail(PNP_ERR_ARG, "pnp_conv3x3: null src/wpack");

@@ -30,4 +30,8 @@ cudaError_t launch_mix_bias(const float* conv2_bias, long long block_stride, int
                             const float* experts, const float* gamma, int frames, float* out,
                             cudaStream_t stream);
 
+cudaError_t launch_mv_rasterize(const float* rec, const int* frame_off, const int* is_b, const int* p_target,
+                                int T, int R, int H, int W, unsigned* own_f, unsigned* own_b, unsigned* pmask,
+                                float* mvs, float* partitions, int* status, cudaStream_t stream);
+
 }  // namespace pnp

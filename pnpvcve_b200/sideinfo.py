@@ -1,0 +1,122 @@
+"""Compact codec side information -> dense generator inputs, on the GPU.
+
+The reference ships 7 dense fp32 planes per pixel and frame to the GPU (``mvs`` 4 + ``partitions`` 3:
+25.8 MB per 720p frame) after rasterising the per-block motion-vector records in a Python loop
+(mmedit/datasets/pipelines/loading_ipb.py:328-369, up to 14 400 iterations per 720p frame).  Here the
+records themselves (40 bytes per block) are uploaded and ``pnp_mv_rasterize`` produces exactly the
+tensors the generator expects -- same integer truncation, numpy slice wrapping, record-order overwrite,
+P-frame reversal into the previous non-B frame and partition one-hot/255 encoding.
+
+Record layout (loading_ipb.py:339): direction, w, h, src_x, src_y, dst_x, dst_y, motion_x, motion_y, scale.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+SLICE_ORD = {"I": 73, "P": 80, "B": 66}
+
+
+def p_targets(slice_types):
+    """Frame that receives the reversed (direction>0) records of each non-B frame.
+
+    loading_ipb.py:353-355,369: ``mvs[-p_offset]`` with ``p_offset = p_offset + 1 if B else 1`` updated
+    after every frame, i.e. the previous non-B frame; -1 when ``p_offset`` is still unbound (first frame)
+    or would point before the clip.
+    """
+    tgt, p_off = [], None
+    for f, st in enumerate(slice_types):
+        t = -1
+        if st != "B" and p_off is not None and f - p_off >= 0:
+            t = f - p_off
+        tgt.append(t)
+        p_off = (p_off + 1) if (st == "B" and p_off is not None) else 1
+    return tgt
+
+
+def rasterize_clip(records, frame_offsets, slice_types, h, w, device=None, check=True):
+    """records (R,10) fp32, frame_offsets (T+1,) int, slice_types: sequence of 'I'|'P'|'B'.
+
+    Returns (mvs (T,4,H,W), partitions (T,3,H,W)) fp32 on ``device`` -- the per-clip tensors of the
+    reference pipeline after ``FramesToTensor`` (add a leading batch dim for the generator).
+    ``check`` synchronises once and raises like the reference (KeyError for a block area outside
+    {256,128,64}; ValueError for a reversed record without a target frame).
+    """
+    dev = torch.device(device if device is not None else "cuda")
+    t = len(slice_types)
+    rec = torch.as_tensor(np.asarray(records, dtype=np.float32).reshape(-1, 10)).to(dev).contiguous()
+    offs = torch.as_tensor(np.asarray(frame_offsets, dtype=np.int32)).to(dev)
+    if offs.numel() != t + 1:
+        raise ValueError("frame_offsets must have T+1 entries")
+    is_b = torch.tensor([1 if s == "B" else 0 for s in slice_types], dtype=torch.int32, device=dev)
+    tgt = torch.tensor(p_targets(slice_types), dtype=torch.int32, device=dev)
+    work = torch.zeros((3, t, h, w), dtype=torch.int32, device=dev)        # owner fwd / bwd, partition bits
+    mvs = torch.empty((t, 4, h, w), dtype=torch.float32, device=dev)
+    par = torch.empty((t, 3, h, w), dtype=torch.float32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    vp = ctypes.c_void_p
+    with torch.cuda.device(dev):
+        stream = vp(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.pnp_mv_rasterize(vp(rec.data_ptr() if rec.numel() else 0), vp(offs.data_ptr()),
+                                        vp(is_b.data_ptr()), vp(tgt.data_ptr()), t, rec.shape[0], h, w,
+                                        vp(work[0].data_ptr()), vp(work[1].data_ptr()), vp(work[2].data_ptr()),
+                                        vp(mvs.data_ptr()), vp(par.data_ptr()), vp(status.data_ptr()), stream),
+                   "pnp_mv_rasterize")
+    if check:
+        st = int(status.item())
+        if st & 1:
+            raise KeyError("block area w*h not in {256, 128, 64} (partition_ch lookup, loading_ipb.py:361)")
+        if st & 2:
+            raise ValueError("reversed P-frame record without a previous non-B frame (p_offset unbound)")
+    return mvs, par
+
+
+def synthetic_records(h, w, pattern, seed=0, messy=False):
+    """Seeded per-frame record lists with the structure of an H.264 partition tree.
+
+    Every frame but I frames is tiled with 16x16 macroblocks split at random into 16x16 / 16x8 / 8x16 /
+    8x8 blocks (areas 256 / 128 / 64); motion in quarter pels with scale 4.  B frames carry forward and
+    (for a random subset) backward records, P frames forward records plus direction>0 records that the
+    loader reverses into the previous non-B frame.  ``messy`` adds what the loader tolerates: blocks
+    hanging over the frame edges (numpy slice wrapping), duplicates (overwrite order), direction 0 rows.
+    """
+    rng = np.random.RandomState(seed)
+    frames = []
+    for f, st in enumerate(pattern):
+        rows = []
+        if st != "I":
+            for y0 in range(0, h, 16):
+                for x0 in range(0, w, 16):
+                    split = rng.randint(0, 4)
+                    blocks = {0: [(0, 0, 16, 16)], 1: [(0, 0, 16, 8), (0, 8, 16, 8)],
+                              2: [(0, 0, 8, 16), (8, 0, 8, 16)],
+                              3: [(0, 0, 8, 8), (8, 0, 8, 8), (0, 8, 8, 8), (8, 8, 8, 8)]}[split]
+                    for (bx, by, bw, bh) in blocks:
+                        cx, cy = x0 + bx + bw // 2, y0 + by + bh // 2
+                        mx, my = rng.randint(-64, 65), rng.randint(-64, 65)
+                        sx, sy = cx + mx // 4, cy + my // 4
+                        rows.append([-1, bw, bh, sx, sy, cx, cy, mx, my, 4])
+                        if st == "B" and rng.rand() < 0.6:
+                            rows.append([1, bw, bh, cx - mx // 4, cy - my // 4, cx, cy, -mx, -my, 4])
+                        if st == "P" and f > 0 and rng.rand() < 0.5:
+                            rows.append([1, bw, bh, sx, sy, cx, cy, mx, my, 4])
+            if messy and rows:
+                for _ in range(12):
+                    r = list(rows[rng.randint(0, len(rows))])
+                    kind = rng.randint(0, 4)
+                    if kind == 0:          # hangs over the top/left edge: negative slice start wraps
+                        r[5], r[6] = rng.randint(-6, 4), rng.randint(-6, 4)
+                    elif kind == 1:        # hangs over the bottom/right edge: clamped
+                        r[5], r[6] = w - rng.randint(0, 6), h - rng.randint(0, 6)
+                    elif kind == 2:        # duplicate with another vector: later record wins
+                        r[7], r[8] = rng.randint(-64, 65), rng.randint(-64, 65)
+                    else:                  # direction 0: partition only
+                        r[0] = 0
+                    if r[0] > 0 and st == "P":
+                        r[3], r[4] = rng.randint(-8, w + 8), rng.randint(-8, h + 8)
+                    rows.append(r)
+        frames.append(np.asarray(rows, dtype=np.float32).reshape(-1, 10))
+    return frames

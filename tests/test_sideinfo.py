@@ -1,0 +1,117 @@
+"""MV / partition rasteriser: oracle vs. the reference's golden vectors (CPU), CUDA kernel vs. both (GPU)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mv_raster_oracle as R
+from pnpvcve_b200 import sideinfo
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["raster_64x96_ibbp", "raster_72x80_messy", "raster_128x128_ip"]
+
+
+def load_case(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    offs = g["offsets"]
+    recs = [g["records"][offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+    h, w = (int(v) for v in g["shape"])
+    return g, recs, [str(c) for c in g["pattern"]], h, w
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_loop_golden(name):
+    g, recs, pattern, h, w = load_case(name)
+    mv, par = R.rasterize_clip(recs, pattern, h, w)
+    assert np.array_equal(mv, g["mvs"]) and np.array_equal(par, g["partitions"])
+    assert set(np.unique(par)) <= {np.float32(0), np.float32(1) / np.float32(255)}
+
+
+def test_p_targets_follow_p_offset_rule():
+    assert sideinfo.p_targets("IBBPBBP") == [-1, -1, -1, 0, -1, -1, 3]
+    assert sideinfo.p_targets("IPPP") == [-1, 0, 1, 2]
+    assert sideinfo.p_targets("PBP") == [-1, -1, 0]
+
+
+def test_oracle_errors_like_reference():
+    bad_area = [np.zeros((0, 10), np.float32), np.array([[-1, 4, 4, 8, 8, 8, 8, 1, 1, 4]], np.float32)]
+    with pytest.raises(KeyError):
+        R.rasterize_clip(bad_area, ["I", "P"], 32, 32)
+    first_p = [np.array([[1, 8, 8, 8, 8, 8, 8, 1, 1, 4]], np.float32)]
+    with pytest.raises(UnboundLocalError):
+        R.rasterize_clip(first_p, ["P"], 32, 32)
+
+
+def test_synthetic_records_tile_the_frame():
+    recs = sideinfo.synthetic_records(64, 96, "IBP", seed=3)
+    assert recs[0].shape == (0, 10)
+    mv, par = R.rasterize_clip(recs, list("IBP"), 64, 96)
+    assert np.allclose(par[1].sum(0), 1.0 / 255.0)          # one-hot everywhere on coded frames
+    assert par[0].sum() == 0
+
+
+# ------------------------------------------------------------------ GPU
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_kernel_matches_reference_golden_bit_exact(dev, name):
+    g, recs, pattern, h, w = load_case(name)
+    mv, par = sideinfo.rasterize_clip(g["records"], g["offsets"], pattern, h, w, device=dev)
+    assert torch.equal(mv.cpu(), torch.from_numpy(g["mvs"]))
+    assert torch.equal(par.cpu(), torch.from_numpy(g["partitions"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w,pattern,messy", [(720, 1280, "IBBP", True), (376, 1244, "IP", True),
+                                                (180, 320, "IBBPBBPB", False)])
+def test_kernel_matches_oracle_at_full_sizes(dev, h, w, pattern, messy):
+    recs = sideinfo.synthetic_records(h, w, pattern, seed=h + w, messy=messy)
+    flat = np.concatenate(recs, 0)
+    offs = np.cumsum([0] + [len(r) for r in recs])
+    mv, par = sideinfo.rasterize_clip(flat, offs, list(pattern), h, w, device=dev)
+    emv, epar = R.rasterize_clip(recs, list(pattern), h, w)
+    assert torch.equal(mv.cpu(), torch.from_numpy(emv))
+    assert torch.equal(par.cpu(), torch.from_numpy(epar))
+
+
+@pytest.mark.gpu
+def test_kernel_reports_reference_errors(dev):
+    bad = np.array([[-1, 4, 4, 8, 8, 8, 8, 1, 1, 4]], np.float32)
+    with pytest.raises(KeyError):
+        sideinfo.rasterize_clip(bad, [0, 0, 1], ["I", "P"], 32, 32, device=dev)
+    first_p = np.array([[1, 8, 8, 8, 8, 8, 8, 1, 1, 4]], np.float32)
+    with pytest.raises(ValueError):
+        sideinfo.rasterize_clip(first_p, [0, 1], ["P"], 32, 32, device=dev)
+    mv, par = sideinfo.rasterize_clip(np.zeros((0, 10), np.float32), [0, 0], ["I"], 64, 64, device=dev)
+    assert mv.abs().max().item() == 0 and par.abs().max().item() == 0
+
+
+@pytest.mark.gpu
+def test_rasterised_side_info_drives_the_generator(dev):
+    """records -> pnp_mv_rasterize -> generator == dense reference-style inputs -> generator."""
+    import pnpvcve_b200 as P
+    from pnpvcve_b200 import synthetic, weights
+    from test_gpu_parity import GENERATOR_CFG
+    h, w, pattern = 64, 96, "IBBP"
+    recs = sideinfo.synthetic_records(h, w, pattern, seed=5)
+    emv, epar = R.rasterize_clip(recs, list(pattern), h, w)
+    flat = np.concatenate(recs, 0)
+    offs = np.cumsum([0] + [len(r) for r in recs])
+    mv, par = sideinfo.rasterize_clip(flat, offs, list(pattern), h, w, device=dev)
+    clip = synthetic.make_clip(h, w, len(pattern), seed=9, pattern="IBBP")
+    net = P.build_backbone(dict(GENERATOR_CFG))
+    net.load_state_dict(weights.random_state_dict(2), strict=True)
+    net = net.to(dev).eval()
+    args = [a.to(dev) for a in synthetic.generator_args(clip)]
+    with torch.no_grad():
+        a = net(args[0], args[1], args[2], mv[None], args[4], par[None])
+        b = net(args[0], args[1], args[2], torch.from_numpy(emv)[None].to(dev), args[4],
+                torch.from_numpy(epar)[None].to(dev))
+    assert torch.equal(a, b)
