@@ -3,8 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--frames T] [--impl ours|reference]
 
-A *step* is one synthetic REDS4-shape clip (1280x720, T frames, CRF cycling 15/25/35) per GPU through
-the registry-built generator.  N>1 is launched by torchrun (one process per GPU); clips are
+A *step* is one synthetic REDS4-shape clip (1280x720, T frames, CRF cycling 15/25/35; --clips batches
+more per step) per GPU through the registry-built generator.  N>1 is launched by torchrun (one process per GPU); clips are
 independent, so ranks share nothing on the data path (weak scaling) and only gather per-frame metrics.
 Rank 0 prints ONE JSON line:
 
@@ -154,7 +154,7 @@ def run_reference_arm(args):
 def workload_config(args, world):
     return dict(workload=f"C2 HR_davis_LR_128x128 BAE+CAA forward, synthetic REDS4-shape clip "
                          f"1280x720x{args.frames} frames, CRF 15/25/35 cycling, random-init weights",
-                frames_per_clip=args.frames, clips_per_gpu_per_step=1, height=H, width=W,
+                frames_per_clip=args.frames, clips_per_gpu_per_step=getattr(args, "clips", 1), height=H, width=W,
                 parallelism=f"clip-sharded x{world} (no data-path collective)",
                 l2="inputs (37 MB/frame) larger than L2; no flush needed")
 
@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=100)
+    ap.add_argument("--clips", type=int, default=1, help="clips per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prof-every", type=int, default=8,
@@ -208,8 +209,11 @@ def main():
     net = net.to(dev).eval()
     T = args.frames
     n_steps = args.warmup + args.steps
-    # one resident clip per CRF, reused across steps (generation is not part of the job)
-    clips = [make_device_clip(T, 2000 + 10 * rank + j, CRFS[j], dev) for j in range(len(CRFS))]
+    # resident batches of `args.clips` clips, one batch per CRF, reused across steps (generation is not
+    # part of the job)
+    nc = args.clips
+    clips = [synthetic.cat_clips([make_device_clip(T, 2000 + 10 * rank + 3 * k + j, CRFS[j], dev)
+                                  for k in range(nc)]) for j in range(len(CRFS))]
 
     def barrier():
         if world > 1:
@@ -217,10 +221,10 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident(i):
-        clip = clips[i % len(CRFS)]
+        clip = clips[i % len(clips)]
         out = net(*synthetic.generator_args(clip))
-        local = driver.frame_metrics(out)[0:1]
-        driver.gather_metrics(local, world, rank, world)          # the job's only collective
+        local = driver.frame_metrics(out)
+        driver.gather_metrics(local.mean(0, keepdim=True), world, rank, world)   # the job's only collective
         return out
 
     # ---------------- device-resident throughput (value)
@@ -246,7 +250,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    frames_total = world * args.steps * T
+    frames_total = world * args.steps * T * nc
     value = frames_total / (total_ms / 1e3)
 
     peaks = measured_peaks()
@@ -278,7 +282,7 @@ def main():
 
     # ---------------- end to end from pinned host buffers (e2e)
     host = [{k: v.cpu().pin_memory() for k, v in c.items()} for c in clips[:1]]
-    out_host = torch.empty((1, T, 3, H, W), dtype=torch.float32).pin_memory()
+    out_host = torch.empty((nc, T, 3, H, W), dtype=torch.float32).pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     d2h = out_host.numel() * out_host.element_size()
 
@@ -305,8 +309,8 @@ def main():
             out = net(*synthetic.generator_args(clip))
             for v in clip.values():
                 v.record_stream(main)
-            local = driver.frame_metrics(out)[0:1]
-            driver.gather_metrics(local, world, rank, world)
+            local = driver.frame_metrics(out)
+            driver.gather_metrics(local.mean(0, keepdim=True), world, rank, world)
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(down):
@@ -330,7 +334,7 @@ def main():
     ms2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps * T / (float(ms2.item()) / 1e3)
+    e2e_value = world * e2e_steps * T * nc / (float(ms2.item()) / 1e3)
 
     # ---------------- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample
     cpu_baseline = None

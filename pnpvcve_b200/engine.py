@@ -15,6 +15,7 @@ Restructures ``IconVSR_restore_wo_refill_mv_ipb_fast_domain_dynamic_with_par.for
   ``out += lq`` run in the conv epilogues.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -106,6 +107,10 @@ class BaeEngine:
         #: defeat programmatic dependent launch, so the bench samples instead of bracketing everything)
         self.prof = None
         self.prof_every = 1
+        #: clips of one call can be processed on several concurrent lanes (stream + work buffers each).
+        #: Measured (profiles/r01_notes.md): no gain at 720p (one CTA per SM fills the chip; 285 vs 289
+        #: frames/s) and +5 % at 320x180, where the host launch rate is the limit -- default 1.
+        self.max_lanes = int(os.environ.get("PNP_LANES", "1"))
 
     # ------------------------------------------------------------------ weights
     def _param_key(self):
@@ -204,23 +209,21 @@ class BaeEngine:
         return packs
 
     # ------------------------------------------------------------------ buffers
-    def _buffers(self, n, t, h, w, dev):
-        key = (n, t, h, w, dev)
+    def _buffers(self, n, t, h, w, dev, lanes):
+        key = (n, t, h, w, dev, lanes)
         if self.buf is not None and self.buf_key == key:
             return self.buf
         self.buf = None                                   # release before re-allocating
-        b = dict(
-            feats=torch.empty((n, t, h, w, 64), dtype=torch.bfloat16, device=dev),
-            lr64=ops.new_feature(1, h, w, dev, zero=True),
-            zero=ops.new_feature(1, h, w, dev, zero=True),
-            kw=ops.new_feature(1, h, w, dev),
-            pa=ops.new_feature(1, h, w, dev),
-            pb=ops.new_feature(1, h, w, dev),
-            xa=ops.new_feature(1, h, w, dev),
-            xb=ops.new_feature(1, h, w, dev),
-            t=ops.new_feature(1, h, w, dev),
-            hr=ops.new_feature(1, h, w, dev),
-        )
+        names = ("kw", "pa", "pb", "xa", "xb", "t", "hr")
+        lane_bufs = []
+        for _ in range(lanes):
+            lb = {k: ops.new_feature(1, h, w, dev) for k in names}
+            lb["lr64"] = ops.new_feature(1, h, w, dev, zero=True)
+            lb["zero"] = ops.new_feature(1, h, w, dev, zero=True)
+            lb["launcher"] = _Launcher()
+            lane_bufs.append(lb)
+        b = dict(feats=torch.empty((n, t, h, w, 64), dtype=torch.bfloat16, device=dev), lanes=lane_bufs,
+                 streams=[torch.cuda.Stream(device=dev) for _ in range(lanes)] if lanes > 1 else [])
         self.buf, self.buf_key = b, key
         return b
 
@@ -260,83 +263,96 @@ class BaeEngine:
         experts, gamma = ops.caa_heads(base_QPs.reshape(-1).float().contiguous(),
                                        QPs.reshape(-1).float().contiguous(), st["caa"], m.num_experts)
         bias_tab = ops.mix_bias(st["conv2_bias_all"], experts, gamma)       # (n*t, 2*nb, 64)
-        buf = self._buffers(n, t, h, w, dev)
-        feats = buf["feats"]
+        lanes = max(1, min(n, self.max_lanes))
+        bufs = self._buffers(n, t, h, w, dev, lanes)
+        feats = bufs["feats"]
         out = torch.empty((n, t, 3, h, w), dtype=torch.float32, device=dev)
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        conv = _Launcher(self.prof, self.prof_every)
         prof = self.prof
-        launches = 0
-        bwd_feats = None
-        if return_features:
-            bwd_feats = torch.empty_like(feats)
+        seen = {}
+        bwd_feats = torch.empty_like(feats) if return_features else None
+        counts = [0] * lanes
 
-        def warp(src, flow, dst):
-            timed = prof is not None and "warp" in prof
-            if timed:
-                k = conv.seen.get("warp", 0)
-                conv.seen["warp"] = k + 1
-                timed = (k % conv.prof_every) == 0
-            if timed:
-                e0 = torch.cuda.Event(enable_timing=True)
-                e1 = torch.cuda.Event(enable_timing=True)
-                e0.record()
-            ops.mv_warp(src, flow, dst)
-            if timed:
-                e1.record()
-                prof["warp"].append((e0, e1))
-
-        def stack(name, blk_off, b, i, x, dst, mixed):
-            """8 BAE blocks: x (in xa/xb) -> dst.  ResidualBlockNoBNDynamic_drt, sr_backbone_utils.py:304-333"""
-            nonlocal launches
-            f = b * t + i
-            par = par_map[b:b + 1, i]
-            other = buf["xb"] if x is buf["xa"] else buf["xa"]
-            for k in range(nb):
-                conv(stream, x, mixed[name][k], out=buf["t"], bias=bias_tab[f, blk_off + k],
-                     par=par, act=PNP_ACT_RELU, label="block_a")
-                o = dst if k == nb - 1 else other
-                conv(stream, buf["t"], st[name + "_conv1_w"][k], out=o, idt=x,
-                     bias=st[name + "_conv1_b"][k], act=PNP_ACT_NONE, label="block_b", flip_y=True)
-                x, other = o, x
-                launches += 2
-
+        # expert-mixed conv2 packs for every distinct (CRF, QP) pair of the call, packed up front on the
+        # caller's stream so that the clip lanes below only read them
+        mixed_of = {}
         for b in range(n):
+            for i in range(t):
+                key = (float(crf_host[b, i]), float(qp_host[b, i]))
+                if key not in mixed_of:
+                    f = b * t + i
+                    mixed_of[key] = self._mixed_conv2(st, key, experts[f], gamma[f], dev)
+
+        def clip_steps(b, lane):
+            """One clip on one lane (own stream + work buffers); yields after every frame step so that
+            the lanes interleave and one clip's kernel tails / prologues are filled by the other's."""
+            buf = bufs["lanes"][lane]
+            conv = buf["launcher"]
+            conv.prof, conv.prof_every, conv.seen = prof, self.prof_every, seen
+            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+            def warp(src, flow, dst):
+                timed = prof is not None and "warp" in prof
+                if timed:
+                    k = seen.get("warp", 0)
+                    seen["warp"] = k + 1
+                    timed = (k % conv.prof_every) == 0
+                if timed:
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                ops.mv_warp(src, flow, dst)
+                if timed:
+                    e1.record()
+                    prof["warp"].append((e0, e1))
+
+            def stack(name, blk_off, i, x, dst, mixed):
+                """8 BAE blocks: x (in xa/xb) -> dst.  ResidualBlockNoBNDynamic_drt, sr_backbone_utils.py:304-333"""
+                f = b * t + i
+                par = par_map[b:b + 1, i]
+                other = buf["xb"] if x is buf["xa"] else buf["xa"]
+                for k in range(nb):
+                    conv(stream, x, mixed[name][k], out=buf["t"], bias=bias_tab[f, blk_off + k],
+                         par=par, act=PNP_ACT_RELU, label="block_a")
+                    o = dst if k == nb - 1 else other
+                    conv(stream, buf["t"], st[name + "_conv1_w"][k], out=o, idt=x,
+                         bias=st[name + "_conv1_b"][k], act=PNP_ACT_NONE, label="block_b", flip_y=True)
+                    x, other = o, x
+                counts[lane] += 2 * nb
+
             bwd_key, fwd_key = key_schedule(key_rows[b])
             # ---------------- backward-time propagation (iconvsr_ipb_par.py:67-100)
             for i in range(t - 1, -1, -1):
-                f = b * t + i
-                mixed = self._mixed_conv2(st, (float(crf_host[b, i]), float(qp_host[b, i])), experts[f], gamma[f], dev)
+                mixed = mixed_of[(float(crf_host[b, i]), float(qp_host[b, i]))]
                 ops.lr_im2col(lrs[b:b + 1, i], buf["lr64"])
-                launches += 1
+                counts[lane] += 1
                 x0 = buf["xa"]
                 if i < t - 1:
                     kidx = bwd_key[i]
                     warp(feats[b, kidx].unsqueeze(0), mvs[b, i, 2:4], buf["kw"])
-                    launches += 1
+                    counts[lane] += 1
                     if kidx == i + 1:                     # align_key: neighbour is the warped key
                         conv(stream, buf["kw"], st["bwd_merged_aux"], out=x0, aux=buf["lr64"],
                              bias=st["bwd_in_bias"], act=PNP_ACT_LRELU, label="input")
-                        launches += 1
+                        counts[lane] += 1
                     else:
                         conv(stream, buf["kw"], st["bwd_key_aux"], out=buf["pa"], aux=buf["lr64"],
                              bias=st["bwd_in_bias"], act=PNP_ACT_NONE, label="input")
                         conv(stream, feats[b, i + 1].unsqueeze(0), st["bwd_nb"], out=x0, idt=buf["pa"],
                              act=PNP_ACT_LRELU, label="input")
-                        launches += 2
+                        counts[lane] += 2
                 else:                                     # zeros for key_warp / neighbour (:69-70)
                     conv(stream, buf["zero"], st["bwd_merged_aux"], out=x0, aux=buf["lr64"],
                          bias=st["bwd_in_bias"], act=PNP_ACT_LRELU, label="input")
-                    launches += 1
-                stack("bwd", 0, b, i, x0, feats[b, i].unsqueeze(0), mixed)
+                    counts[lane] += 1
+                stack("bwd", 0, i, x0, feats[b, i].unsqueeze(0), mixed)
+                yield
             if return_features:
                 bwd_feats[b].copy_(feats[b])
             # ---------------- forward-time propagation + reconstruction (:102-147)
             for i in range(t):
-                f = b * t + i
-                mixed = self._mixed_conv2(st, (float(crf_host[b, i]), float(qp_host[b, i])), experts[f], gamma[f], dev)
+                mixed = mixed_of[(float(crf_host[b, i]), float(qp_host[b, i]))]
                 ops.lr_im2col(lrs[b:b + 1, i], buf["lr64"])
-                launches += 1
+                counts[lane] += 1
                 x0 = buf["xa"]
                 cur = feats[b, i].unsqueeze(0)            # backward feature of frame i (outputs[i])
                 if i > 0:
@@ -344,26 +360,55 @@ class BaeEngine:
                     warp(feats[b, kidx].unsqueeze(0), mvs[b, i, 0:2], buf["kw"])
                     conv(stream, cur, st["fwd_bf_aux"], out=buf["pa"], aux=buf["lr64"],
                          bias=st["fwd_in_bias"], act=PNP_ACT_NONE, label="input")
-                    launches += 2
+                    counts[lane] += 2
                     if kidx == i - 1:
-                        conv(stream, buf["kw"], st["fwd_merged"], out=x0, idt=buf["pa"], act=PNP_ACT_LRELU, label="input")
-                        launches += 1
+                        conv(stream, buf["kw"], st["fwd_merged"], out=x0, idt=buf["pa"], act=PNP_ACT_LRELU,
+                             label="input")
+                        counts[lane] += 1
                     else:
                         conv(stream, buf["kw"], st["fwd_key"], out=buf["pb"], idt=buf["pa"],
                              act=PNP_ACT_NONE, label="input")
                         conv(stream, feats[b, i - 1].unsqueeze(0), st["fwd_nb"], out=x0, idt=buf["pb"],
                              act=PNP_ACT_LRELU, label="input")
-                        launches += 2
+                        counts[lane] += 2
                 else:
                     conv(stream, cur, st["fwd_bf_aux"], out=x0, aux=buf["lr64"], bias=st["fwd_in_bias"],
                          act=PNP_ACT_LRELU, label="input")
-                    launches += 1
-                stack("fwd", nb, b, i, x0, cur, mixed)
+                    counts[lane] += 1
+                stack("fwd", nb, i, x0, cur, mixed)
                 # out = conv_last(lrelu(conv_hr(x))) + lq   (:144-146)
                 conv(stream, cur, st["hr_w"], out=buf["hr"], bias=st["hr_b"], act=PNP_ACT_LRELU, label="hr")
                 conv(stream, buf["hr"], st["last_w"], bias=st["last_b"], lq=lrs[b:b + 1, i],
                      outf=out[b:b + 1, i], label="last")
-                launches += 2
+                counts[lane] += 2
+                yield
+
+        def lane_steps(lane):
+            for b in range(lane, n, lanes):               # clips of this lane, one after the other
+                yield from clip_steps(b, lane)
+
+        main = torch.cuda.current_stream()
+        if lanes == 1:
+            for _ in lane_steps(0):
+                pass
+        else:
+            streams = bufs["streams"]
+            gens = []
+            for lane in range(lanes):
+                streams[lane].wait_stream(main)
+                with torch.cuda.stream(streams[lane]):
+                    gens.append(lane_steps(lane))
+            live = list(range(lanes))
+            while live:
+                for lane in list(live):
+                    with torch.cuda.stream(streams[lane]):
+                        try:
+                            next(gens[lane])
+                        except StopIteration:
+                            live.remove(lane)
+            for lane in range(lanes):
+                main.wait_stream(streams[lane])
+        launches = sum(counts)
         self.launch_count = launches
         if return_features:
             return out, bwd_feats, feats
