@@ -45,12 +45,14 @@ int pnp_set_base_offset_mode(int mode);
  * Replaces flow_warp (mmedit/models/common/flow_warp.py:6-50) as called by VOSAlignment.forward
  * (mmedit/models/backbones/sr_backbones/iconvsr_mv.py:17-18): grid_sample(bilinear, zeros,
  * align_corners=True) of x + mv, including the reference's fp32 normalise/un-normalise sequence.
- *   src, dst : bf16 NHWC (H, W, 64), 16-byte aligned, distinct buffers
- *   flow_x/y : fp32 planes, element (y,x) at [y*flow_row_stride + x]   (a (2,H,W) slice of `mvs`)
- *   dbg_x0/y0: optional int32 (H*W) outputs of the integer north-west tap (floor), may be NULL
+ *   src, dst : bf16 NHWC (N, H, W, 64), 16-byte aligned, distinct buffers (N same-shape clips)
+ *   flow_x/y : fp32 planes, element (n,y,x) at [n*flow_image_stride + y*flow_row_stride + x]
+ *              (the (2,H,W) slices mvs[b0:b1, i, 2:4] or [.., 0:2] of the reference's `mvs`)
+ *   dbg_x0/y0: optional int32 (H*W) outputs of the integer north-west tap (floor), N == 1 only
  */
 int pnp_mv_warp(const void* src, const float* flow_x, const float* flow_y, int64_t flow_row_stride,
-                void* dst, int H, int W, int32_t* dbg_x0, int32_t* dbg_y0, void* stream);
+                int64_t flow_image_stride, void* dst, int N, int H, int W, int32_t* dbg_x0,
+                int32_t* dbg_y0, void* stream);
 
 /*
  * LR frames -> im2col'd bf16 operand (N, H, W, 64), channel k = tap*3 + c for k < 27, zero for

@@ -45,7 +45,7 @@ _PROTOS = {
     "pnp_last_error": (_c.c_char_p, []),
     "pnp_device_check": (_i, []),
     "pnp_set_base_offset_mode": (_i, [_i]),
-    "pnp_mv_warp": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
+    "pnp_mv_warp": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pnp_lr_im2col": (_i, [_vp, _i64, _i64, _i64, _vp, _i, _i, _i, _vp]),
     "pnp_pack_conv3x3": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "pnp_pack_conv3x3_rowstack": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),

@@ -92,7 +92,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 extern "C" {
 
-int pnp_abi_version(void) { return 3; }
+int pnp_abi_version(void) { return 4; }
 
 const char* pnp_last_error(void) { return g_err; }
 
@@ -108,17 +108,19 @@ int pnp_set_base_offset_mode(int mode) {
 }
 
 int pnp_mv_warp(const void* src, const float* flow_x, const float* flow_y, int64_t flow_row_stride,
-                void* dst, int H, int W, int32_t* dbg_x0, int32_t* dbg_y0, void* stream) {
+                int64_t flow_image_stride, void* dst, int N, int H, int W, int32_t* dbg_x0, int32_t* dbg_y0,
+                void* stream) {
   if (!src || !flow_x || !flow_y || !dst) return fail(PNP_ERR_ARG, "pnp_mv_warp: null pointer");
-  if (H <= 0 || W <= 0) return fail(PNP_ERR_ARG, "pnp_mv_warp: bad shape");
+  if (N <= 0 || H <= 0 || W <= 0) return fail(PNP_ERR_ARG, "pnp_mv_warp: bad shape");
   if (!aligned16(src) || !aligned16(dst) || src == dst)
     return fail(PNP_ERR_ARG, "pnp_mv_warp: src/dst must be distinct 16-byte aligned buffers");
-  if ((dbg_x0 == nullptr) != (dbg_y0 == nullptr)) return fail(PNP_ERR_ARG, "pnp_mv_warp: dbg pair");
+  if ((dbg_x0 == nullptr) != (dbg_y0 == nullptr) || (dbg_x0 && N != 1))
+    return fail(PNP_ERR_ARG, "pnp_mv_warp: dbg outputs come in pairs and need N == 1");
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
-  cudaError_t e = pnp::launch_mv_warp(src, flow_x, flow_y, flow_row_stride, dst, H, W, dbg_x0, dbg_y0, d->sms,
-                                      static_cast<cudaStream_t>(stream));
+  cudaError_t e = pnp::launch_mv_warp(src, flow_x, flow_y, flow_row_stride, flow_image_stride, dst, N, H, W, dbg_x0,
+                                      dbg_y0, d->sms, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_mv_warp");
 }
 

@@ -27,8 +27,13 @@ __device__ __forceinline__ float warp_coord(float pos, float mv, float size_m1_d
 // Now: 2-D grid (no divisions), 32-bit indexing, 4 threads per pixel x 32 bytes each, FMA blend.
 __global__ void __launch_bounds__(256)
 mv_warp_kernel(const uint4* __restrict__ src, const float* __restrict__ flow_x,
-               const float* __restrict__ flow_y, long long flow_sy, uint4* __restrict__ dst, int H, int W,
-               int* __restrict__ dbg_x0, int* __restrict__ dbg_y0) {
+               const float* __restrict__ flow_y, long long flow_sy, long long flow_sn, uint4* __restrict__ dst,
+               int H, int W, int* __restrict__ dbg_x0, int* __restrict__ dbg_y0) {
+  // blockIdx.z = image of the batch: same-shape clips with their own motion fields
+  src += (size_t)blockIdx.z * H * W * 8;
+  dst += (size_t)blockIdx.z * H * W * 8;
+  flow_x += (long long)blockIdx.z * flow_sn;
+  flow_y += (long long)blockIdx.z * flow_sn;
   const int y = blockIdx.y;
   const int x = blockIdx.x * 64 + (threadIdx.x >> 2);     // 64 pixels per block, 4 threads per pixel
   const int q = threadIdx.x & 3;                          // which 16-channel quarter (two uint4)
@@ -93,12 +98,12 @@ mv_warp_kernel(const uint4* __restrict__ src, const float* __restrict__ flow_x,
 }
 
 cudaError_t launch_mv_warp(const void* src, const float* flow_x, const float* flow_y, long long flow_sy,
-                           void* dst, int H, int W, int* dbg_x0, int* dbg_y0, int num_sms,
-                           cudaStream_t stream) {
+                           long long flow_sn, void* dst, int N, int H, int W, int* dbg_x0, int* dbg_y0,
+                           int num_sms, cudaStream_t stream) {
   (void)num_sms;
-  if ((long long)H * W >= (1LL << 27)) return cudaErrorInvalidValue;   // 32-bit pixel indexing
-  dim3 grid((W + 63) / 64, H);
-  mv_warp_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), flow_x, flow_y, flow_sy,
+  if ((long long)H * W >= (1LL << 27) || N > 65535) return cudaErrorInvalidValue;   // 32-bit pixel indexing
+  dim3 grid((W + 63) / 64, H, N);
+  mv_warp_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), flow_x, flow_y, flow_sy, flow_sn,
                                            reinterpret_cast<uint4*>(dst), H, W, dbg_x0, dbg_y0);
   return cudaGetLastError();
 }

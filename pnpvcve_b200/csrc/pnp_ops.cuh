@@ -8,8 +8,8 @@ namespace pnp {
 constexpr int kPackBlockBytes = 8192;
 
 cudaError_t launch_mv_warp(const void* src, const float* flow_x, const float* flow_y, long long flow_sy,
-                           void* dst, int H, int W, int* dbg_x0, int* dbg_y0, int num_sms,
-                           cudaStream_t stream);
+                           long long flow_sn, void* dst, int N, int H, int W, int* dbg_x0, int* dbg_y0,
+                           int num_sms, cudaStream_t stream);
 cudaError_t launch_lr_im2col(const float* lr, long long sn, long long sc, long long sy, void* dst, int N,
                              int H, int W, int num_sms, cudaStream_t stream);
 cudaError_t launch_pack_conv3x3(const float* w, int n_experts, const float* coef, const float* row_scale,

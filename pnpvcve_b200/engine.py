@@ -111,6 +111,9 @@ class BaeEngine:
         #: Measured (profiles/r01_notes.md): no gain at 720p (one CTA per SM fills the chip; 285 vs 289
         #: frames/s) and +5 % at 320x180, where the host launch rate is the limit -- default 1.
         self.max_lanes = int(os.environ.get("PNP_LANES", "1"))
+        #: batch runs of identically-conditioned clips into N-image launches (up to max_batch clips)
+        self.batch_clips = os.environ.get("PNP_BATCH_CLIPS", "1") != "0"
+        self.max_batch = 16
 
     # ------------------------------------------------------------------ weights
     def _param_key(self):
@@ -209,20 +212,21 @@ class BaeEngine:
         return packs
 
     # ------------------------------------------------------------------ buffers
-    def _buffers(self, n, t, h, w, dev, lanes):
-        key = (n, t, h, w, dev, lanes)
+    def _buffers(self, n, t, h, w, dev, lanes, maxn):
+        key = (n, t, h, w, dev, lanes, maxn)
         if self.buf is not None and self.buf_key == key:
             return self.buf
         self.buf = None                                   # release before re-allocating
         names = ("kw", "pa", "pb", "xa", "xb", "t", "hr")
         lane_bufs = []
         for _ in range(lanes):
-            lb = {k: ops.new_feature(1, h, w, dev) for k in names}
-            lb["lr64"] = ops.new_feature(1, h, w, dev, zero=True)
-            lb["zero"] = ops.new_feature(1, h, w, dev, zero=True)
+            lb = {k: ops.new_feature(maxn, h, w, dev) for k in names}
+            lb["lr64"] = ops.new_feature(maxn, h, w, dev, zero=True)
+            lb["zero"] = ops.new_feature(maxn, h, w, dev, zero=True)
             lb["launcher"] = _Launcher()
             lane_bufs.append(lb)
-        b = dict(feats=torch.empty((n, t, h, w, 64), dtype=torch.bfloat16, device=dev), lanes=lane_bufs,
+        # frame-major so that the features of a run of clips at one frame are one contiguous (N,H,W,64) block
+        b = dict(feats=torch.empty((t, n, h, w, 64), dtype=torch.bfloat16, device=dev), lanes=lane_bufs,
                  streams=[torch.cuda.Stream(device=dev) for _ in range(lanes)] if lanes > 1 else [])
         self.buf, self.buf_key = b, key
         return b
@@ -263,8 +267,20 @@ class BaeEngine:
         experts, gamma = ops.caa_heads(base_QPs.reshape(-1).float().contiguous(),
                                        QPs.reshape(-1).float().contiguous(), st["caa"], m.num_experts)
         bias_tab = ops.mix_bias(st["conv2_bias_all"], experts, gamma)       # (n*t, 2*nb, 64)
-        lanes = max(1, min(n, self.max_lanes))
-        bufs = self._buffers(n, t, h, w, dev, lanes)
+        # Clips with the same key-frame schedule and the same per-frame (CRF, QP) conditions use the same
+        # weights at every step, so a run of such clips is ONE launch sequence with N images per launch
+        # (the many-clip LR workload): fixed launch cost and the host launch rate are shared N ways.
+        sigs = [(tuple(key_rows[b]), tuple(crf_host[b].tolist()), tuple(qp_host[b].tolist())) for b in range(n)]
+        groups = []
+        for b in range(n):
+            if self.batch_clips and groups and sigs[b] == sigs[groups[-1][0]] and \
+                    groups[-1][1] - groups[-1][0] < self.max_batch:
+                groups[-1][1] = b + 1
+            else:
+                groups.append([b, b + 1])
+        maxn = max(g[1] - g[0] for g in groups)
+        lanes = max(1, min(len(groups), self.max_lanes))
+        bufs = self._buffers(n, t, h, w, dev, lanes, maxn)
         feats = bufs["feats"]
         out = torch.empty((n, t, 3, h, w), dtype=torch.float32, device=dev)
         prof = self.prof
@@ -282,10 +298,12 @@ class BaeEngine:
                     f = b * t + i
                     mixed_of[key] = self._mixed_conv2(st, key, experts[f], gamma[f], dev)
 
-        def clip_steps(b, lane):
-            """One clip on one lane (own stream + work buffers); yields after every frame step so that
-            the lanes interleave and one clip's kernel tails / prologues are filled by the other's."""
-            buf = bufs["lanes"][lane]
+        def clip_steps(b0, b1, lane):
+            """One run of identically-conditioned clips [b0, b1) on one lane (own stream + work buffers);
+            yields after every frame step so that lanes interleave."""
+            b = b0
+            nn = b1 - b0
+            buf = {k: (v[:nn] if isinstance(v, torch.Tensor) else v) for k, v in bufs["lanes"][lane].items()}
             conv = buf["launcher"]
             conv.prof, conv.prof_every, conv.seen = prof, self.prof_every, seen
             stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -308,7 +326,7 @@ class BaeEngine:
             def stack(name, blk_off, i, x, dst, mixed):
                 """8 BAE blocks: x (in xa/xb) -> dst.  ResidualBlockNoBNDynamic_drt, sr_backbone_utils.py:304-333"""
                 f = b * t + i
-                par = par_map[b:b + 1, i]
+                par = par_map[b0:b1, i]
                 other = buf["xb"] if x is buf["xa"] else buf["xa"]
                 for k in range(nb):
                     conv(stream, x, mixed[name][k], out=buf["t"], bias=bias_tab[f, blk_off + k],
@@ -323,12 +341,12 @@ class BaeEngine:
             # ---------------- backward-time propagation (iconvsr_ipb_par.py:67-100)
             for i in range(t - 1, -1, -1):
                 mixed = mixed_of[(float(crf_host[b, i]), float(qp_host[b, i]))]
-                ops.lr_im2col(lrs[b:b + 1, i], buf["lr64"])
+                ops.lr_im2col(lrs[b0:b1, i], buf["lr64"])
                 counts[lane] += 1
                 x0 = buf["xa"]
                 if i < t - 1:
                     kidx = bwd_key[i]
-                    warp(feats[b, kidx].unsqueeze(0), mvs[b, i, 2:4], buf["kw"])
+                    warp(feats[kidx, b0:b1], mvs[b0:b1, i, 2:4], buf["kw"])
                     counts[lane] += 1
                     if kidx == i + 1:                     # align_key: neighbour is the warped key
                         conv(stream, buf["kw"], st["bwd_merged_aux"], out=x0, aux=buf["lr64"],
@@ -337,27 +355,27 @@ class BaeEngine:
                     else:
                         conv(stream, buf["kw"], st["bwd_key_aux"], out=buf["pa"], aux=buf["lr64"],
                              bias=st["bwd_in_bias"], act=PNP_ACT_NONE, label="input")
-                        conv(stream, feats[b, i + 1].unsqueeze(0), st["bwd_nb"], out=x0, idt=buf["pa"],
+                        conv(stream, feats[i + 1, b0:b1], st["bwd_nb"], out=x0, idt=buf["pa"],
                              act=PNP_ACT_LRELU, label="input")
                         counts[lane] += 2
                 else:                                     # zeros for key_warp / neighbour (:69-70)
                     conv(stream, buf["zero"], st["bwd_merged_aux"], out=x0, aux=buf["lr64"],
                          bias=st["bwd_in_bias"], act=PNP_ACT_LRELU, label="input")
                     counts[lane] += 1
-                stack("bwd", 0, i, x0, feats[b, i].unsqueeze(0), mixed)
+                stack("bwd", 0, i, x0, feats[i, b0:b1], mixed)
                 yield
             if return_features:
-                bwd_feats[b].copy_(feats[b])
+                bwd_feats[:, b0:b1].copy_(feats[:, b0:b1])
             # ---------------- forward-time propagation + reconstruction (:102-147)
             for i in range(t):
                 mixed = mixed_of[(float(crf_host[b, i]), float(qp_host[b, i]))]
-                ops.lr_im2col(lrs[b:b + 1, i], buf["lr64"])
+                ops.lr_im2col(lrs[b0:b1, i], buf["lr64"])
                 counts[lane] += 1
                 x0 = buf["xa"]
-                cur = feats[b, i].unsqueeze(0)            # backward feature of frame i (outputs[i])
+                cur = feats[i, b0:b1]                     # backward feature of frame i (outputs[i])
                 if i > 0:
                     kidx = fwd_key[i]
-                    warp(feats[b, kidx].unsqueeze(0), mvs[b, i, 0:2], buf["kw"])
+                    warp(feats[kidx, b0:b1], mvs[b0:b1, i, 0:2], buf["kw"])
                     conv(stream, cur, st["fwd_bf_aux"], out=buf["pa"], aux=buf["lr64"],
                          bias=st["fwd_in_bias"], act=PNP_ACT_NONE, label="input")
                     counts[lane] += 2
@@ -368,7 +386,7 @@ class BaeEngine:
                     else:
                         conv(stream, buf["kw"], st["fwd_key"], out=buf["pb"], idt=buf["pa"],
                              act=PNP_ACT_NONE, label="input")
-                        conv(stream, feats[b, i - 1].unsqueeze(0), st["fwd_nb"], out=x0, idt=buf["pb"],
+                        conv(stream, feats[i - 1, b0:b1], st["fwd_nb"], out=x0, idt=buf["pb"],
                              act=PNP_ACT_LRELU, label="input")
                         counts[lane] += 2
                 else:
@@ -378,14 +396,14 @@ class BaeEngine:
                 stack("fwd", nb, i, x0, cur, mixed)
                 # out = conv_last(lrelu(conv_hr(x))) + lq   (:144-146)
                 conv(stream, cur, st["hr_w"], out=buf["hr"], bias=st["hr_b"], act=PNP_ACT_LRELU, label="hr")
-                conv(stream, buf["hr"], st["last_w"], bias=st["last_b"], lq=lrs[b:b + 1, i],
-                     outf=out[b:b + 1, i], label="last")
+                conv(stream, buf["hr"], st["last_w"], bias=st["last_b"], lq=lrs[b0:b1, i],
+                     outf=out[b0:b1, i], label="last")
                 counts[lane] += 2
                 yield
 
         def lane_steps(lane):
-            for b in range(lane, n, lanes):               # clips of this lane, one after the other
-                yield from clip_steps(b, lane)
+            for g in range(lane, len(groups), lanes):     # runs of this lane, one after the other
+                yield from clip_steps(groups[g][0], groups[g][1], lane)
 
         main = torch.cuda.current_stream()
         if lanes == 1:
@@ -411,5 +429,5 @@ class BaeEngine:
         launches = sum(counts)
         self.launch_count = launches
         if return_features:
-            return out, bwd_feats, feats
+            return out, bwd_feats.transpose(0, 1), feats.transpose(0, 1)     # (n, T, H, W, 64) views
         return out

@@ -47,21 +47,25 @@ def new_wpack(n_chunks, device):
 
 
 def mv_warp(src, flow, dst, debug=False):
-    """K1.  src/dst (1,H,W,64) bf16; flow (2,H,W) fp32 view (x then y).  Returns (x0,y0) if debug."""
+    """K1.  src/dst (N,H,W,64) bf16; flow (2,H,W) or (N,2,H,W) fp32 view (x then y).  Returns (x0,y0) if debug."""
     _feat_check(src, "src")
     _feat_check(dst, "dst")
     _plane_view_check(flow, "flow")
-    _, h, w, _ = src.shape
-    if flow.shape != (2, h, w) or src.shape[0] != 1 or dst.shape != src.shape:
-        raise ValueError(f"The spatial sizes of input ({(h, w)}) and flow ({tuple(flow.shape[1:])}) "
+    n, h, w, _ = src.shape
+    if flow.dim() == 3:
+        flow = flow.unsqueeze(0)
+    if tuple(flow.shape) != (n, 2, h, w) or dst.shape != src.shape:
+        raise ValueError(f"The spatial sizes of input ({(h, w)}) and flow ({tuple(flow.shape[-2:])}) "
                          "are not the same.")
     dx = dy = None
     if debug:
+        if n != 1:
+            raise ValueError("mv_warp: debug tap outputs need N == 1")
         dx = torch.empty((h, w), dtype=torch.int32, device=src.device)
         dy = torch.empty((h, w), dtype=torch.int32, device=src.device)
     lib = _lib.load()
-    _lib.check(lib.pnp_mv_warp(_ptr(src), _ptr(flow[0]), _ptr(flow[1]), flow.stride(1), _ptr(dst), h, w,
-                               _ptr(dx), _ptr(dy), _stream()), "pnp_mv_warp")
+    _lib.check(lib.pnp_mv_warp(_ptr(src), _ptr(flow[0, 0]), _ptr(flow[0, 1]), flow.stride(2), flow.stride(0),
+                               _ptr(dst), n, h, w, _ptr(dx), _ptr(dy), _stream()), "pnp_mv_warp")
     return (dx, dy) if debug else None
 
 

@@ -121,6 +121,25 @@ def test_generator_batch_equals_single_clips(dev):
     assert torch.equal(both[1:2], run(net, b, dev))
 
 
+def test_generator_batches_identically_conditioned_clips(dev):
+    """Clips with the same slice pattern / CRF / QPs share launches (N images per kernel); results must
+    equal the clips run alone, and the mixed batch [same, same, different] must split into two runs."""
+    sd = weights.random_state_dict(17)
+    a = synthetic.make_clip(64, 96, 5, seed=11, crf=25, pattern="IBBP", ipb=True)
+    b = synthetic.make_clip(64, 96, 5, seed=12, crf=25, pattern="IBBP", ipb=True)
+    c = synthetic.make_clip(64, 96, 5, seed=13, crf=35, pattern="IP", ipb=True)
+    net = build(sd, dev)
+    single = [run(net, x, dev) for x in (a, b, c)]
+    launches_single = net.gpu_launches
+    both = run(net, synthetic.cat_clips([a, b, c]), dev)
+    assert net.gpu_launches < 3 * launches_single                      # a and b shared their launches
+    for k in range(3):
+        assert torch.equal(both[k:k + 1], single[k])
+    net._engine.batch_clips = False
+    unb = run(net, synthetic.cat_clips([a, b, c]), dev)
+    assert torch.equal(unb, both)
+
+
 def test_generator_reflect_padding_and_size_errors(dev):
     sd = weights.random_state_dict(1, num_blocks=2)
     net = build(sd, dev, num_blocks=2)

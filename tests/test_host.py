@@ -38,14 +38,14 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/pnp_vcve.h but not exported"
     assert sorted(_lib.EXPORTS) == syms
-    assert _lib.load().pnp_abi_version() == 3
+    assert _lib.load().pnp_abi_version() == 4
 
 
 def test_abi_argument_errors_without_gpu():
     lib = _lib.load()
     assert lib.pnp_conv3x3(None, None) == -1                      # PNP_ERR_ARG
     assert b"null" in lib.pnp_last_error()
-    assert lib.pnp_mv_warp(None, None, None, 0, None, 4, 4, None, None, None) == -1
+    assert lib.pnp_mv_warp(None, None, None, 0, 0, None, 1, 4, 4, None, None, None) == -1
     assert lib.pnp_set_base_offset_mode(7) == -1
     assert lib.pnp_set_base_offset_mode(0) == 0
     if not torch.cuda.is_available():
