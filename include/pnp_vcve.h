@@ -174,6 +174,33 @@ typedef struct pnp_conv_desc {
 
 int pnp_conv3x3(const pnp_conv_desc* desc, void* stream);
 
+/*
+ * K3 fused -- one whole BAE residual block per launch (ResidualBlockNoBNDynamic_drt.forward,
+ * sr_backbone_utils.py:304-333), the intermediate activation never leaving the chip:
+ *   t   = relu( conv3x3(x, W2) + bias1 + sum_k par_k * conv1x1_k(x) )     bf16, on-chip only
+ *   out = x + conv3x3(t, W1) + bias2                                        bf16 NHWC
+ * Runs on CTA pairs (thread-block clusters of 2): one SM holds W2 + the 1x1s, its partner holds W1,
+ * rows of t travel through distributed shared memory.  Same numerics as pnp_conv3x3 launch A followed
+ * by launch B (t rounded to bf16 once, fp32 accumulation).
+ *   w_stage1: 98304 bytes = pnp_pack_conv3x3_rowstack(conv2 expert mix, row_scale = SE gain, tap_n 64)
+ *             followed by the three 1x1 partition convs as 192 packed rows (pnp_pack_rows at row offsets
+ *             0/64/128 from byte 73728) -- the PNP_WLAYOUT_ROWSTACK + par layout of pnp_conv3x3.
+ *   w_stage2: 73728 bytes = pnp_pack_conv3x3_rowstack(conv1, tap_n 64, flip_ky 0).
+ */
+typedef struct pnp_block_desc {
+  const void* x;          /* bf16 (N,H,W,64): block input and identity */
+  void* out;              /* bf16 (N,H,W,64); must not alias x */
+  const void* w_stage1;
+  const void* w_stage2;
+  const float* bias1;     /* [64] SE gain * mixed conv2 bias (pnp_mix_bias), or NULL */
+  const float* bias2;     /* [64] conv1 bias, or NULL */
+  const float* par;       /* fp32 (N,3,H,W) view of the partition map */
+  int64_t par_sn, par_sc, par_sy;
+  int32_t N, H, W;
+} pnp_block_desc;
+
+int pnp_resblock(const pnp_block_desc* desc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,7 @@ EXPORTS = [
     "pnp_abi_version", "pnp_last_error", "pnp_device_check", "pnp_set_base_offset_mode",
     "pnp_mv_warp", "pnp_lr_im2col", "pnp_pack_conv3x3", "pnp_pack_conv3x3_rowstack", "pnp_pack_rows",
     "pnp_pack_aux",
-    "pnp_caa_heads", "pnp_mix_bias", "pnp_mv_rasterize", "pnp_conv3x3",
+    "pnp_caa_heads", "pnp_mix_bias", "pnp_mv_rasterize", "pnp_conv3x3", "pnp_resblock",
 ]
 
 _c = ctypes
@@ -40,6 +40,15 @@ class ConvDesc(_c.Structure):
     ]
 
 
+class BlockDesc(_c.Structure):
+    """struct pnp_block_desc"""
+    _fields_ = [
+        ("x", _vp), ("out", _vp), ("w_stage1", _vp), ("w_stage2", _vp), ("bias1", _vp), ("bias2", _vp),
+        ("par", _vp), ("par_sn", _i64), ("par_sc", _i64), ("par_sy", _i64),
+        ("N", _c.c_int32), ("H", _c.c_int32), ("W", _c.c_int32),
+    ]
+
+
 _PROTOS = {
     "pnp_abi_version": (_i, []),
     "pnp_last_error": (_c.c_char_p, []),
@@ -55,6 +64,7 @@ _PROTOS = {
     "pnp_mix_bias": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "pnp_mv_rasterize": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pnp_conv3x3": (_i, [_c.POINTER(ConvDesc), _vp]),
+    "pnp_resblock": (_i, [_c.POINTER(BlockDesc), _vp]),
 }
 
 _lib = None

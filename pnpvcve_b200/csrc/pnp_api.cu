@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "../../include/pnp_vcve.h"
+#include "pnp_block.cuh"
 #include "pnp_conv.cuh"
 #include "pnp_ops.cuh"
 
@@ -92,7 +93,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 extern "C" {
 
-int pnp_abi_version(void) { return 4; }
+int pnp_abi_version(void) { return 5; }
 
 const char* pnp_last_error(void) { return g_err; }
 
@@ -339,6 +340,50 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   cudaError_t e = rowstack ? pnp::launch_conv_rows(p, grid, static_cast<cudaStream_t>(stream))
                            : pnp::launch_conv(p, grid, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_conv3x3");
+}
+
+int pnp_resblock(const pnp_block_desc* c, void* stream) {
+  if (!c) return fail(PNP_ERR_ARG, "pnp_resblock: null descriptor");
+  if (!c->x || !c->out || !c->w_stage1 || !c->w_stage2 || !c->par)
+    return fail(PNP_ERR_ARG, "pnp_resblock: null x/out/weights/par");
+  if (c->N < 1 || c->H < 1 || c->W < 1) return fail(PNP_ERR_ARG, "pnp_resblock: bad shape");
+  if (c->out == c->x) return fail(PNP_ERR_ARG, "pnp_resblock: out must not alias x (halo rows, identity)");
+  if (!aligned16(c->x) || !aligned16(c->out) || !aligned16(c->w_stage1) || !aligned16(c->w_stage2))
+    return fail(PNP_ERR_ARG, "pnp_resblock: pointers must be 16-byte aligned");
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  if (d->sms < 2) return fail(PNP_ERR_RESOURCE, "pnp_resblock: needs at least one SM pair");
+
+  pnp::BlockParams p;
+  memset(&p, 0, sizeof(p));
+  if ((rc = make_map(&p.tm_src, c->x, c->N, c->H, c->W, pnp::kHaloPx))) return rc;
+  if ((rc = make_map(&p.tm_out, c->out, c->N, c->H, c->W, pnp::kBlockOutPx))) return rc;
+  p.w0 = c->w_stage1;
+  p.w1 = c->w_stage2;
+  p.bias0 = c->bias1;
+  p.bias1 = c->bias2;
+  p.par = c->par;
+  p.par_sn = c->par_sn; p.par_sc = c->par_sc; p.par_sy = c->par_sy;
+  p.x = c->x;
+  p.H = c->H; p.W = c->W; p.N = c->N;
+  p.strips = (c->W + pnp::kBlockOutPx - 1) / pnp::kBlockOutPx;
+  const long long tiles = (long long)c->N * p.strips * c->H;
+  if (tiles > 0x7fffffffLL) return fail(PNP_ERR_ARG, "pnp_resblock: too many tiles");
+  p.tiles_total = (int)tiles;
+  int pairs = d->sms / 2 < p.tiles_total ? d->sms / 2 : p.tiles_total;
+  p.tiles_per_pair = (p.tiles_total + pairs - 1) / pairs;
+  pairs = (p.tiles_total + p.tiles_per_pair - 1) / p.tiles_per_pair;
+  p.s_a = 5;
+  p.n_t = 5;
+  {
+    const char* dbg = getenv("PNP_DEBUG_SKIP");   // what-if profiling only; results are wrong when set
+    p.debug_skip = dbg ? atoi(dbg) : 0;
+    const char* trc = getenv("PNP_TRACE_PTR");    // device pointer (decimal) of a >= 8 KB buffer
+    p.trace = trc ? reinterpret_cast<long long*>(strtoull(trc, nullptr, 10)) : nullptr;
+  }
+  cudaError_t e = pnp::launch_block(p, pairs, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_resblock");
 }
 
 }  // extern "C"

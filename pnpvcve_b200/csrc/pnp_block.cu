@@ -1,0 +1,640 @@
+// One BAE residual block per launch, fused across a CTA PAIR (thread-block cluster of 2).
+//
+// Replaces ResidualBlockNoBNDynamic_drt.forward (mmedit/models/common/sr_backbone_utils.py:304-333):
+//     t   = relu( conv3x3(x, g*Wmix) + g*bmix + sum_k par_k * conv1x1_k(x) )        (:307-311)
+//     out = x + conv3x3(t, W1) + b1                                                  (:313-316)
+// which pnp_conv.cu / pnp_conv_rows.cu run as two launches with `t` round-tripping through HBM (the
+// layer-by-layer form is HBM-bound: 590 MB per block at 720p).  Here `t` never leaves the chip:
+//
+//   * the two convolutions need 72 + 24 + 72 KB of resident weights and 5 + 3 + 5 TMEM accumulator
+//     slots -- more than one SM has -- so the block is split over the two SMs of a cluster:
+//       rank 0 ("stage 1"): TMA-loads source rows of x, row-stacked conv2 (N=192 MMAs into a ring of five
+//                64-column accumulators) + the three partition 1x1 convs (one N=192 group into a 192-column
+//                region), epilogue = bias + partition blend + ReLU -> bf16 row of `t` staged in its own
+//                shared memory and pushed into the partner's ring with cp.async.bulk (DSMEM);
+//       rank 1 ("stage 2"): row-stacked conv1 on the rows of `t` arriving in its ring, epilogue =
+//                bias + identity (x re-read through L2) -> TMA store of the output row.
+//   * a strip is 126 output pixels wide: stage 1 computes 128 pixels of `t` (x0-1 .. x0+126) from 130
+//     source pixels, stage 2 computes 128 outputs of which 126 are valid; pixels of `t` outside the image
+//     are forced to zero (they are conv1's zero padding).  At the top/bottom of a CTA's row range stage 1
+//     computes one extra row of `t` (halo recompute, ~2 % at 720p).
+//   * both CTAs walk the same (image, strip, row) ranges; hand-offs are mbarriers: t_full (bulk-copy
+//     complete_tx on the consumer), stage_free / t_free (remote arrives back to the producer).
+//   * each CTA keeps the warp roles of pnp_conv_rows.cu (TMA producer / MMA issuer / barrier scout /
+//     8 epilogue warps), but the epilogue is two independent groups of four warps working on alternate
+//     rows, so a row's epilogue may take two MMA steps.
+#include "pnp_block.cuh"
+#include "pnp_conv.cuh"
+#include "pnp_ptx.cuh"
+
+namespace pnp {
+
+namespace {
+
+constexpr int kRing0 = 5;        // stage-1 accumulator ring (5 x 64 TMEM columns)
+constexpr int kRing1 = 8;        // stage-2 accumulator ring (8 x 64 TMEM columns)
+constexpr int kParCol = 320;     // stage 1: TMEM column of the partition 1x1 accumulators (3 x 64)
+constexpr int kStepRing = 8;
+constexpr int kMaxSlots = 8;
+constexpr uint32_t kDxb = 3 * 64 * 128 / 16;   // descriptor units per dx block of a row-stacked pack
+constexpr uint32_t kSbb = 64 * 128 / 16;       // ... per dy sub-block
+
+struct PairMisc {
+  float bias[64];                  // stage 1: g*bmix; stage 2: conv1 bias
+  uint64_t w_full;
+  uint64_t a_full[kMaxSlots];      // stage 1: source rows (TMA); stage 2: rows of t (partner's bulk copies)
+  uint64_t step_done[kStepRing];   // tcgen05.commit after every step (one input row)
+  uint64_t acc_free[kMaxSlots];    // epilogue -> MMA: accumulator slot drained
+  uint64_t par_done[2];            // stage 1, by row parity: partition accumulators ready
+  uint64_t par_free[2];            // stage 1, by row parity: ... and read
+  uint64_t t_free[kMaxSlots];      // stage 1: the partner's MMAs are done with ring slot i (remote arrive)
+  uint64_t stage_free[2];          // stage 1: the copy out of staging tile g has landed (remote arrive)
+  uint32_t tmem_base;
+  uint32_t go_step;
+  uint32_t go_par;
+};
+static_assert(sizeof(PairMisc) <= 1024, "misc region overflow");
+
+struct PairLayout {
+  uint32_t misc, w, ring, stage, total;
+};
+
+__host__ __device__ inline PairLayout pair_layout(int role, int s_a, int n_t) {
+  PairLayout l;
+  l.misc = 0;
+  l.w = 1024;
+  l.ring = l.w + (role == 0 ? kBlockW0Bytes : kBlockW1Bytes);
+  l.stage = l.ring + (role == 0 ? s_a : n_t) * kASlotBytes;
+  l.total = l.stage + (role == 0 ? 2 : 4) * kTileBytes;
+  return l;
+}
+
+// A pair owns the output tiles [t_begin, t_end) in (image, strip, row) order; a segment is a maximal
+// run of consecutive rows of one strip.  `len` rows starting at y_b are produced from the input rows
+// y_b + j, j = j_first..j_last (the rows above/below exist unless the segment touches the image edge).
+struct Segment {
+  int n, strip, y_b, len, j_first, j_last;
+};
+
+__device__ __forceinline__ Segment make_seg(int n, int strip, int y_b, int len, int H) {
+  Segment s;
+  s.n = n;
+  s.strip = strip;
+  s.y_b = y_b;
+  s.len = len;
+  s.j_first = (y_b > 0) ? -1 : 0;
+  s.j_last = (y_b + len < H) ? len : len - 1;
+  return s;
+}
+
+// ext = false: segments of OUTPUT rows (stage 2; its input rows are rows of t).
+// ext = true : the rows of t stage 2 needs for that segment, i.e. the segment grown by its halo rows
+//              (stage 1; its input rows are rows of x).
+struct SegIter {
+  int t, t_end, H, strips, n, strip, y_b;
+  bool ext;
+  __device__ SegIter(const BlockParams& p, int b, int e, bool ext_)
+      : t(b), t_end(e), H(p.H), strips(p.strips), ext(ext_) {
+    const int col = b / p.H;
+    y_b = b - col * p.H;
+    n = col / p.strips;
+    strip = col - n * p.strips;
+  }
+  __device__ __forceinline__ bool valid() const { return t < t_end; }
+  __device__ __forceinline__ Segment get() const {
+    Segment s = make_seg(n, strip, y_b, min(H - y_b, t_end - t), H);
+    if (ext) s = make_seg(n, strip, y_b + s.j_first, s.j_last - s.j_first + 1, H);
+    return s;
+  }
+  __device__ __forceinline__ void next() {
+    t += min(H - y_b, t_end - t);
+    y_b = 0;
+    if (++strip == strips) {
+      strip = 0;
+      ++n;
+    }
+  }
+};
+
+struct Ring {
+  uint32_t slot, phase, size;
+  __device__ explicit Ring(uint32_t n) : slot(0), phase(0), size(n) {}
+  __device__ __forceinline__ void advance() {
+    if (++slot == size) {
+      slot = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+// flat cursor over the rows a CTA produces
+struct RowCur {
+  SegIter it;
+  Segment s;
+  int o;
+  uint32_t ord, sc0;
+  bool valid;
+  __device__ RowCur(const BlockParams& p, int b, int e, bool ext)
+      : it(p, b, e, ext), s{0, 0, 0, 0, 0, -1}, o(0), ord(0), sc0(0), valid(false) {
+    valid = it.valid();
+    if (valid) s = it.get();
+  }
+  __device__ __forceinline__ void next() {
+    ++ord;
+    if (++o < s.len) return;
+    sc0 += (uint32_t)(s.j_last - s.j_first + 1);
+    it.next();
+    valid = it.valid();
+    o = 0;
+    if (valid) s = it.get();
+  }
+  // step whose completion finishes the 3x3 accumulators of this row
+  __device__ __forceinline__ uint32_t sc_last() const { return sc0 + (uint32_t)(min(o + 1, s.j_last) - s.j_first); }
+};
+
+// ---------------------------------------------------------------------------------------- MMA issuer
+// Same issue discipline as pnp_conv_rows.cu (see the notes there): straight-line tcgen05.mma with
+// descriptor = base word + immediate, barriers of the next step polled through the scout's counter in
+// the middle of the current step, commits deferred behind the next step's first MMA.
+template <bool kPar, int kAccRing>
+__device__ __forceinline__ void mma_issue_loop(const BlockParams& p, PairMisc* misc, uint32_t w_smem,
+                                               uint32_t a_smem, uint32_t ring_slots, SegIter seg_it,
+                                               uint32_t tmem_base, int role) {
+  const uint32_t idesc0 = umma_idesc_bf16(128, 0);
+  const uint32_t idesc_step = (64u >> 3) << 17;
+  const uint32_t w_lo = umma_desc_lo(w_smem);
+  const uint32_t par_w_lo = w_lo + 3 * kDxb;
+  mbar_wait(smem_u32(&misc->w_full), 0, 4);
+  struct StepCtx {
+    bool valid;
+    int j, len, j_first;
+    uint32_t ord0, sc, a_slot;
+  };
+  Segment seg = seg_it.valid() ? seg_it.get() : Segment{0, 0, 0, 0, 0, -1};
+  Ring ar(ring_slots);
+  StepCtx cur{seg_it.valid(), seg.j_first, seg.len, seg.j_first, 0u, 0u, ar.slot};
+  auto advance = [&](StepCtx& c) {
+    ar.advance();
+    c.sc += 1;
+    c.a_slot = ar.slot;
+    if (c.j < seg.j_last) {
+      c.j += 1;
+      return;
+    }
+    const uint32_t next_ord0 = c.ord0 + (uint32_t)seg.len;
+    seg_it.next();
+    c.valid = seg_it.valid();
+    if (c.valid) {
+      seg = seg_it.get();
+      c.j = seg.j_first;
+      c.len = seg.len;
+      c.j_first = seg.j_first;
+      c.ord0 = next_ord0;
+    }
+  };
+  const uint32_t go_step = smem_u32(&misc->go_step), go_par = smem_u32(&misc->go_par);
+  bool pend = false;
+  uint32_t pend_bar = 0;
+  auto mma_range = [&](uint32_t slot_lo, int cnt, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+    const int n1 = min(cnt, kAccRing - (int)slot_lo);
+    umma_bf16_lo(tmem_base + slot_lo * 64, a_lo, kDescHiSw128, b_lo, kDescHiSw128, idesc0 + n1 * idesc_step, acc);
+    if (cnt > n1)
+      umma_bf16_lo(tmem_base, a_lo, kDescHiSw128, b_lo + n1 * kSbb, kDescHiSw128, idesc0 + (cnt - n1) * idesc_step,
+                   acc);
+  };
+  if (cur.valid) spin_until_ge(go_step, 1, 5);
+  tc_fence_after();
+  while (cur.valid) {
+    const bool tr = (p.trace != nullptr) && blockIdx.x < 2 && cur.sc < 128;
+    long long* trp = p.trace + (role * 128 + (int)cur.sc) * 4;
+    if (tr) trp[0] = clock64();
+    const int lo = max(cur.j - 1, 0);
+    const int hi = min(cur.j + 1, cur.len - 1);
+    const int cnt = hi - lo + 1;
+    const int new_from = (cur.j == cur.j_first) ? lo : cur.j + 1;   // rows first touched in this step
+    const int old_cnt = min(max(new_from - lo, 0), cnt);
+    const int new_cnt = cnt - old_cnt;
+    const bool centre = (cur.j >= 0 && cur.j < cur.len);
+    const uint32_t slot_lo = (cur.ord0 + lo) % kAccRing;
+    const uint32_t a_row = umma_desc_lo(a_smem + cur.a_slot * kASlotBytes);
+    const uint32_t b_row = w_lo + (uint32_t)(lo - (cur.j - 1)) * kSbb;   // first dy sub-block in range
+    const uint32_t cur_sc = cur.sc;
+    const uint32_t cur_od = cur.ord0 + (uint32_t)max(cur.j, 0);
+    StepCtx nxt = cur;
+    advance(nxt);
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      if (dx == 2) {
+        if (nxt.valid) spin_until_ge(go_step, nxt.sc + 1, 5);   // normally long satisfied
+        tc_fence_after();
+        if (tr) trp[1] = clock64();
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t a_lo = a_row + dx * 8 + 2 * k;
+        const uint32_t b_lo = b_row + dx * kDxb + 2 * k;
+        if (dx == 0 && k == 0) {
+          if (old_cnt > 0) mma_range(slot_lo, old_cnt, a_lo, b_lo, 1);
+          if (new_cnt > 0) mma_range((slot_lo + old_cnt) % kAccRing, new_cnt, a_lo, b_lo + old_cnt * kSbb, 0);
+          if (pend) {
+            umma_commit(pend_bar);
+            pend = false;
+          }
+        } else {
+          mma_range(slot_lo, cnt, a_lo, b_lo, 1);
+        }
+      }
+    }
+    if (kPar && centre) {
+      // partition 1x1 convs of this row of t: centre pixel column, N = 192, own TMEM region
+      spin_until_ge(go_par, cur_od + 1, 10);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16_lo(tmem_base + kParCol, a_row + 8 + 2 * k, kDescHiSw128, par_w_lo + 2 * k, kDescHiSw128,
+                     idesc0 + 3 * idesc_step, k > 0);
+      umma_commit(smem_u32(&misc->par_done[cur_od & 1]));
+    }
+    pend = true;
+    pend_bar = smem_u32(&misc->step_done[cur_sc & (kStepRing - 1)]);
+    if (tr) trp[2] = clock64();
+    cur = nxt;
+  }
+  if (pend) umma_commit(pend_bar);
+}
+
+// ---------------------------------------------------------------------------------------- barrier scout
+// Does every mbarrier wait the MMAs depend on and publishes plain counters (see pnp_conv_rows.cu).
+// Stage 2 additionally acknowledges each landed row of t to the producer (its staging tile is free).
+template <bool kPar, int kAccRing>
+__device__ __forceinline__ void scout_loop(const BlockParams& p, PairMisc* misc, uint32_t ring_slots, SegIter it,
+                                           uint32_t remote_stage_free) {
+  const uint32_t go_step = smem_u32(&misc->go_step), go_par = smem_u32(&misc->go_par);
+  Ring ar(ring_slots);
+  uint32_t sc = 0, ord0 = 0;
+  for (; it.valid(); it.next()) {
+    const Segment s = it.get();
+    for (int j = s.j_first; j <= s.j_last; ++j, ++sc, ar.advance()) {
+      mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
+      if (!kPar) mbar_arrive_remote(remote_stage_free + (sc & 1) * 8);
+      const int lo = max(j - 1, 0), hi = min(j + 1, s.len - 1);
+      const int new_from = (j == s.j_first) ? lo : j + 1;
+      for (int o = max(new_from, lo); o <= hi; ++o) {
+        const uint32_t od = ord0 + o;
+        mbar_wait(smem_u32(&misc->acc_free[od % kAccRing]), ((od / kAccRing) & 1) ^ 1, 6);
+      }
+      st_release_shared(go_step, sc + 1);
+      if (kPar && j >= 0 && j < s.len) {                  // the previous row's 1x1 results have been read
+        const uint32_t od = ord0 + j;
+        if (od >= 1) mbar_wait(smem_u32(&misc->par_free[(od - 1) & 1]), ((od - 1) >> 1) & 1, 10);
+        st_release_shared(go_par, od + 1);
+      }
+    }
+    ord0 += s.len;
+  }
+}
+
+}  // namespace
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kRowsThreads, 1)
+resblock_pair_kernel(const __grid_constant__ BlockParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - raw);
+  const int role = (int)cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const PairLayout L0 = pair_layout(0, p.s_a, p.n_t);
+  const PairLayout L1 = pair_layout(1, p.s_a, p.n_t);
+  const PairLayout L = role == 0 ? L0 : L1;
+  PairMisc* misc = reinterpret_cast<PairMisc*>(sgen + L.misc);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int t_begin = pair * p.tiles_per_pair;
+  const int t_end = min(p.tiles_total, t_begin + p.tiles_per_pair);
+  const uint32_t ring_slots = role == 0 ? p.s_a : p.n_t;
+  const int w_bytes = role == 0 ? kBlockW0Bytes : kBlockW1Bytes;
+
+  if (threadIdx.x < 64) {
+    const float* b = role == 0 ? p.bias0 : p.bias1;
+    misc->bias[threadIdx.x] = b ? b[threadIdx.x] : 0.0f;
+  }
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(smem_u32(&misc->w_full), 1);
+      for (int i = 0; i < kMaxSlots; ++i) {
+        mbar_init(smem_u32(&misc->a_full[i]), 1);
+        mbar_init(smem_u32(&misc->acc_free[i]), 4);     // the four warps of one epilogue group
+        mbar_init(smem_u32(&misc->t_free[i]), 1);
+      }
+      for (int i = 0; i < kStepRing; ++i) mbar_init(smem_u32(&misc->step_done[i]), 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(smem_u32(&misc->par_done[i]), 1);
+        mbar_init(smem_u32(&misc->par_free[i]), 4);
+        mbar_init(smem_u32(&misc->stage_free[i]), 1);
+      }
+      misc->go_step = 0;
+      misc->go_par = 0;
+      mbar_fence_init();
+      tma_prefetch_desc(role == 0 ? &p.tm_src : &p.tm_out);
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&misc->tmem_base), kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // the partner's barriers are initialised before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = misc->tmem_base;
+  griddep_launch_dependents();
+  griddep_wait();
+  const uint32_t w_smem = sbase + L.w;
+  const uint32_t ring_smem = sbase + L.ring;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t wbar = smem_u32(&misc->w_full);
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(role == 0 ? p.w0 : p.w1);
+      mbar_arrive_expect_tx(wbar, w_bytes);
+      for (int off = 0; off < w_bytes; off += kWChunkBytes) bulk_load_1d(w_smem + off, wsrc + off, kWChunkBytes, wbar);
+      if (role == 0) {
+        // ====================================================== stage 1: TMA producer of source rows
+        Ring ar(ring_slots);
+        uint32_t sc = 0;
+        for (SegIter it(p, t_begin, t_end, true); it.valid(); it.next()) {
+          const Segment s = it.get();
+          const int x0 = s.strip * kBlockOutPx;
+          for (int j = s.j_first; j <= s.j_last; ++j, ++sc, ar.advance()) {
+            if (sc >= ring_slots) {          // slot last used by step sc - ring_slots
+              const uint32_t ps = sc - ring_slots;
+              mbar_wait(smem_u32(&misc->step_done[ps & (kStepRing - 1)]), (ps >> 3) & 1, 1);
+            }
+            const uint32_t fb = smem_u32(&misc->a_full[ar.slot]);
+            if ((p.debug_skip & 1) && sc >= ring_slots) {
+              mbar_arrive(fb);
+            } else {
+              mbar_arrive_expect_tx(fb, kRowBytes);
+              tma_load_4d(ring_smem + ar.slot * kASlotBytes, &p.tm_src, fb, 0, x0 - 2, s.y_b + j, s.n);
+            }
+          }
+        }
+      } else {
+        // ====================================================== stage 2: ring-slot release relay
+        // a row of t may be overwritten once the MMAs of its step have completed
+        const uint32_t r_t_free = mapa_shared(smem_u32(&misc->t_free[0]), 0);
+        Ring tr(ring_slots);
+        uint32_t sc = 0;
+        for (SegIter it(p, t_begin, t_end, false); it.valid(); it.next()) {
+          const Segment s = it.get();
+          for (int j = s.j_first; j <= s.j_last; ++j, ++sc, tr.advance()) {
+            mbar_wait(smem_u32(&misc->step_done[sc & (kStepRing - 1)]), (sc >> 3) & 1, 2);
+            mbar_arrive_remote(r_t_free + tr.slot * 8);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      if (role == 0)
+        mma_issue_loop<true, kRing0>(p, misc, w_smem, ring_smem, ring_slots, SegIter(p, t_begin, t_end, true),
+                                     tmem_base, 0);
+      else
+        mma_issue_loop<false, kRing1>(p, misc, w_smem, ring_smem, ring_slots, SegIter(p, t_begin, t_end, false),
+                                      tmem_base, 1);
+    }
+  } else if (warp == 10) {
+    if (elect_one()) {
+      if (role == 0)
+        scout_loop<true, kRing0>(p, misc, ring_slots, SegIter(p, t_begin, t_end, true), 0u);
+      else
+        scout_loop<false, kRing1>(p, misc, ring_slots, SegIter(p, t_begin, t_end, false),
+                                  mapa_shared(smem_u32(&misc->stage_free[0]), 0));
+    }
+  } else {
+    // ============================================================ epilogue: two groups of four warps,
+    // group g owns the rows with ordinal = g (mod 2); thread = one pixel (TMEM lane), all 64 channels
+    const int q = warp & 3;
+    const int g = (warp - 2) >> 2;
+    const int m = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t sw = (uint32_t)(m & 7);
+    const bool lead = (warp == 2 + 4 * g);
+    const uint32_t bar_id = 1 + g;
+    uint32_t k = 0;                            // rows this group has finished
+    if (role == 0) {
+      // ---------------------------------------------------------- stage 1: t = relu(3x3 + bias + blend)
+      uint8_t* rowp = sgen + L0.stage + g * kTileBytes + m * 128;
+      const uint32_t stage_u32 = sbase + L0.stage + g * kTileBytes;
+      const uint32_t r_ring = mapa_shared(sbase + L1.ring, 1);
+      const uint32_t r_full = mapa_shared(smem_u32(&misc->a_full[0]), 1);
+      Ring tr(p.n_t), accr(kRing0);
+      for (RowCur cur(p, t_begin, t_end, true); cur.valid; cur.next(), tr.advance(), accr.advance()) {
+        if ((cur.ord & 1u) != (uint32_t)g) continue;
+        const Segment& s = cur.s;
+        const int px = s.strip * kBlockOutPx - 1 + m;
+        const int y = s.y_b + cur.o;
+        const bool in_img = (px >= 0) && (px < p.W);
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+        if (in_img) {
+          const float* pp = p.par + (long long)s.n * p.par_sn + (long long)y * p.par_sy + px;
+          p0 = __ldg(pp);
+          p1 = __ldg(pp + p.par_sc);
+          p2 = __ldg(pp + 2 * p.par_sc);
+        }
+        // partition blend + bias (the 1x1 accumulators of a row finish with its centre step)
+        float dy[64];
+        mbar_wait_warp(smem_u32(&misc->par_done[g]), k & 1, 11);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float a1[16], a2[16], a3[16];
+          tmem_ld16(lane_base + kParCol + c * 16, a1);
+          tmem_ld16(lane_base + kParCol + 64 + c * 16, a2);
+          tmem_ld16(lane_base + kParCol + 128 + c * 16, a3);
+          tmem_ld_wait();
+          const float4* bi4 = reinterpret_cast<const float4*>(&misc->bias[c * 16]);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bi = bi4[j4];
+            dy[c * 16 + 4 * j4 + 0] = fmaf(p2, a3[4 * j4 + 0], fmaf(p1, a2[4 * j4 + 0], fmaf(p0, a1[4 * j4 + 0], bi.x)));
+            dy[c * 16 + 4 * j4 + 1] = fmaf(p2, a3[4 * j4 + 1], fmaf(p1, a2[4 * j4 + 1], fmaf(p0, a1[4 * j4 + 1], bi.y)));
+            dy[c * 16 + 4 * j4 + 2] = fmaf(p2, a3[4 * j4 + 2], fmaf(p1, a2[4 * j4 + 2], fmaf(p0, a1[4 * j4 + 2], bi.z)));
+            dy[c * 16 + 4 * j4 + 3] = fmaf(p2, a3[4 * j4 + 3], fmaf(p1, a2[4 * j4 + 3], fmaf(p0, a1[4 * j4 + 3], bi.w)));
+          }
+        }
+        tc_fence_before();
+        warp_arrive(smem_u32(&misc->par_free[g]));
+        // 3x3 accumulators of the row
+        const uint32_t scl = cur.sc_last();
+        mbar_wait_warp(smem_u32(&misc->step_done[scl & (kStepRing - 1)]), (scl >> 3) & 1, 9);
+        tc_fence_after();
+        if (lead) {                            // the previous copy out of this group's staging tile has landed
+          if (lane == 0) mbar_wait_cluster(smem_u32(&misc->stage_free[g]), (k & 1) ^ 1, 12);
+          __syncwarp();
+        }
+        named_bar_sync(bar_id, 128);
+        const uint32_t taddr = lane_base + accr.slot * 64;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[32];
+          if (p.debug_skip & 4) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          } else {
+            tmem_ld16(taddr + h * 32, v);
+            tmem_ld16(taddr + h * 32 + 16, v + 16);
+            tmem_ld_wait();
+          }
+          if (h == 1) {
+            tc_fence_before();
+            warp_arrive(smem_u32(&misc->acc_free[accr.slot]));
+          }
+#pragma unroll
+          for (int gg = 0; gg < 2; ++gg) {
+            const int c2 = h * 2 + gg;         // 16-channel group
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float lo = fmaxf(v[gg * 16 + 2 * j] + dy[c2 * 16 + 2 * j], 0.f);
+              const float hi = fmaxf(v[gg * 16 + 2 * j + 1] + dy[c2 * 16 + 2 * j + 1], 0.f);
+              w[j] = in_img ? pack_bf16x2(lo, hi) : 0u;     // t outside the image is conv1's zero padding
+            }
+            *reinterpret_cast<uint4*>(rowp + (((2 * c2) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(rowp + (((2 * c2 + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (lead) {
+          if (elect_one()) {
+            mbar_wait_cluster(smem_u32(&misc->t_free[tr.slot]), tr.phase ^ 1, 13);
+            mbar_arrive_expect_tx_remote(r_full + tr.slot * 8, kTileBytes);
+            bulk_copy_to_cluster(r_ring + tr.slot * kASlotBytes, stage_u32, kTileBytes, r_full + tr.slot * 8);
+          }
+          __syncwarp();
+        }
+        ++k;
+      }
+    } else {
+      // ---------------------------------------------------------- stage 2: out = x + 3x3(t) + bias
+      const bool m_ok = m < kBlockOutPx;
+      Ring accr(kRing1);
+      for (RowCur cur(p, t_begin, t_end, false); cur.valid; cur.next(), accr.advance()) {
+        if ((cur.ord & 1u) != (uint32_t)g) continue;
+        const Segment& s = cur.s;
+        const int x0 = s.strip * kBlockOutPx;
+        const int px = x0 + m;
+        const int y = s.y_b + cur.o;
+        const bool valid = m_ok && px < p.W;
+        uint4 idv[8];
+        if (valid) {
+          const uint4* ip = reinterpret_cast<const uint4*>(
+              reinterpret_cast<const uint8_t*>(p.x) + (((long long)s.n * p.H + y) * p.W + px) * 128);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) idv[c] = ldg_nc_v4(ip + c);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) idv[c] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        const uint32_t s_io = g * 2 + (k & 1);
+        if (lead) {
+          if (elect_one()) tma_store_wait_read<1>();     // the store out of this staging tile (row k-2) has been read
+          __syncwarp();
+        }
+        named_bar_sync(bar_id, 128);
+        const uint32_t scl = cur.sc_last();
+        mbar_wait_warp(smem_u32(&misc->step_done[scl & (kStepRing - 1)]), (scl >> 3) & 1, 9);
+        tc_fence_after();
+        uint8_t* rowp = sgen + L1.stage + s_io * kTileBytes + m * 128;
+        const uint32_t taddr = lane_base + accr.slot * 64;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[32];
+          if (p.debug_skip & 4) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          } else {
+            tmem_ld16(taddr + h * 32, v);
+            tmem_ld16(taddr + h * 32 + 16, v + 16);
+            tmem_ld_wait();
+          }
+          if (h == 1) {
+            tc_fence_before();
+            warp_arrive(smem_u32(&misc->acc_free[accr.slot]));
+          }
+#pragma unroll
+          for (int gg = 0; gg < 2; ++gg) {
+            const int c2 = h * 2 + gg;
+            const float4* bi4 = reinterpret_cast<const float4*>(&misc->bias[c2 * 16]);
+            const uint4 i0 = idv[2 * c2], i1 = idv[2 * c2 + 1];
+            const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+            uint32_t w[8];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bi = bi4[j4];
+              const float* vv = v + gg * 16 + 4 * j4;
+              w[2 * j4] = pack_bf16x2(vv[0] + bi.x + bf16_lo(iw[2 * j4]), vv[1] + bi.y + bf16_hi(iw[2 * j4]));
+              w[2 * j4 + 1] =
+                  pack_bf16x2(vv[2] + bi.z + bf16_lo(iw[2 * j4 + 1]), vv[3] + bi.w + bf16_hi(iw[2 * j4 + 1]));
+            }
+            *reinterpret_cast<uint4*>(rowp + (((2 * c2) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(rowp + (((2 * c2 + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (lead) {
+          if (elect_one() && !(p.debug_skip & 2)) {
+            tma_store_4d(&p.tm_out, sbase + L1.stage + s_io * kTileBytes, 0, x0, y, s.n);
+            tma_store_commit();
+          }
+          __syncwarp();
+        }
+        ++k;
+      }
+      if (lead) {
+        if (elect_one()) tma_store_wait_all<0>();
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // no remote arrive / bulk copy may target a CTA that has exited
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+size_t block_smem_bytes(const BlockParams& p) {
+  const uint32_t a = pair_layout(0, p.s_a, p.n_t).total, b = pair_layout(1, p.s_a, p.n_t).total;
+  return (a > b ? a : b) + 1024;
+}
+
+cudaError_t launch_block(const BlockParams& p, int pairs, cudaStream_t stream) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    e = cudaFuncSetAttribute(resblock_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kRowsThreads);
+  cfg.dynamicSmemBytes = block_smem_bytes(p);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, resblock_pair_kernel, p);
+}
+
+}  // namespace pnp

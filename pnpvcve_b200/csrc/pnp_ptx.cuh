@@ -262,6 +262,69 @@ __device__ __forceinline__ void spin_until_ge(uint32_t addr, uint32_t target, in
   }
 }
 
+// ------------------------------------------------------------------ thread-block clusters / DSMEM
+// Used by the CTA-pair residual-block kernel (pnp_block.cu).  Measured on B200 (tools/dsmem_bench.cu,
+// profiles/r01_dsmem_bench.log): the SM-to-SM path moves 21.3 B/cycle with 512 contiguous bytes per
+// warp store or with cp.async.bulk, but only 10.7 B/cycle when each lane writes 16 B at a 128 B stride.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on an mbarrier of another CTA of the cluster (address from mapa_shared)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint32_t cluster_bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar),
+               "r"(bytes)
+               : "memory");
+}
+// wait on a LOCAL mbarrier whose arrivals come from another CTA (cluster-scope acquire)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int tag = 0) {
+  uint32_t spins = 0, ok = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > PNP_SPIN_LIMIT) {
+      printf("pnp: cluster mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag,
+             (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  } while (!ok);
+}
+// bulk copy own shared memory -> shared memory of another CTA; completes (complete_tx) on an mbarrier
+// of the destination CTA
+__device__ __forceinline__ void bulk_copy_to_cluster(uint32_t cluster_dst, uint32_t src, uint32_t bytes,
+                                                     uint32_t cluster_bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(cluster_dst), "r"(src), "r"(bytes), "r"(cluster_bar)
+      : "memory");
+}
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
 // ------------------------------------------------------------------ programmatic dependent launch
 // launch_dependents: the next kernel in the stream (launched with the programmatic-serialization
 // attribute) may start its prologue; wait: block until the previous kernel has completed and its

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import (PNP_ACT_LRELU, PNP_ACT_NONE, PNP_ACT_RELU, PNP_CONV_BF16,  # noqa: F401
-                   PNP_CONV_LAST, ConvDesc)
+                   PNP_CONV_LAST, BlockDesc, ConvDesc)
 
 CHUNK_BYTES = 8192
 
@@ -219,3 +219,40 @@ def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par
     lib = _lib.load()
     _lib.check(lib.pnp_conv3x3(ctypes.byref(d), _stream()), "pnp_conv3x3")
     return out if outf is None else outf
+
+
+BLOCK_W1_BYTES = 12 * CHUNK_BYTES      # stage 1: row-stacked conv2 mix (9 blocks) + three stacked 1x1 (3 blocks)
+BLOCK_W2_BYTES = 9 * CHUNK_BYTES       # stage 2: row-stacked conv1
+
+
+def fill_block_desc(d, x, out, w_stage1, w_stage2, bias1, bias2, par):
+    """Fill a BlockDesc in place (reusable across launches)."""
+    n, h, w, _ = x.shape
+    d.x, d.out = x.data_ptr(), out.data_ptr()
+    d.w_stage1, d.w_stage2 = w_stage1.data_ptr(), w_stage2.data_ptr()
+    d.bias1 = bias1.data_ptr() if bias1 is not None else None
+    d.bias2 = bias2.data_ptr() if bias2 is not None else None
+    d.par, d.par_sn, d.par_sc, d.par_sy = par.data_ptr(), par.stride(0), par.stride(1), par.stride(2)
+    d.N, d.H, d.W = n, h, w
+    return d
+
+
+def resblock(x, out, w_stage1, w_stage2, par, bias1=None, bias2=None):
+    """One fused BAE residual block (see include/pnp_vcve.h: pnp_resblock)."""
+    _feat_check(x, "x")
+    _feat_check(out, "out")
+    if out.shape != x.shape:
+        raise ValueError(f"resblock: out shape {tuple(out.shape)} != x {tuple(x.shape)}")
+    _plane_view_check(par, "par")
+    if par.dim() != 4 or par.shape[1] != 3 or par.shape[0] != x.shape[0] or \
+            tuple(par.shape[2:]) != tuple(x.shape[1:3]):
+        raise ValueError("resblock: par must be (N,3,H,W) matching x")
+    if w_stage1.numel() < BLOCK_W1_BYTES or w_stage2.numel() < BLOCK_W2_BYTES:
+        raise ValueError("resblock: packed weight buffer too small")
+    for b in (bias1, bias2):
+        if b is not None and (b.dtype != torch.float32 or b.numel() != 64 or not b.is_contiguous()):
+            raise ValueError("resblock: biases must be contiguous fp32 [64]")
+    d = fill_block_desc(BlockDesc(), x, out, w_stage1, w_stage2, bias1, bias2, par)
+    lib = _lib.load()
+    _lib.check(lib.pnp_resblock(ctypes.byref(d), _stream()), "pnp_resblock")
+    return out

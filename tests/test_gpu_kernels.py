@@ -295,3 +295,96 @@ def test_conv_rowstack_bottom_up_equals_top_down(dev, n, h, w):
     ops.conv3x3(x, u16, lq=lq, outf=o2, wlayout=1, flip_y=True)
     ref = F.conv2d(nchw(x), wl, padding=1) + lq
     assert (o1 - ref).abs().max().item() < 1e-4 and (o2 - ref).abs().max().item() < 1e-4
+
+
+# ------------------------------------------------------------------ fused residual block (CTA pair)
+def _block_weights(dev, g):
+    wt2 = bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05)
+    wt1 = bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05)
+    w1x1 = [bf(torch.randn((64, 64), generator=g, device=dev) * 0.1) for _ in range(3)]
+    b1 = torch.randn(64, generator=g, device=dev) * 0.1
+    b2 = torch.randn(64, generator=g, device=dev) * 0.1
+    ws1 = ops.new_wpack_rowstack(dev, with_par=True)
+    ops.pack_conv3x3_rowstack(wt2, ws1)
+    for j in range(3):
+        ops.pack_rows(w1x1[j], ws1[9 * ops.CHUNK_BYTES:], 64 * j)
+    ws2 = ops.new_wpack_rowstack(dev)
+    ops.pack_conv3x3_rowstack(wt1, ws2)
+    return wt2, wt1, w1x1, b1, b2, ws1, ws2
+
+
+def _block_reference(x, par, wt2, wt1, w1x1, b1, b2):
+    """ResidualBlockNoBNDynamic_drt.forward with t rounded to bf16 once (as both CUDA paths do)."""
+    t = F.conv2d(x, wt2, padding=1) + b1.view(1, -1, 1, 1)
+    for j in range(3):
+        t = t + F.conv2d(x, w1x1[j].view(64, 64, 1, 1)) * par[:, j:j + 1]
+    t = bf(F.relu(t))
+    return x + F.conv2d(t, wt1, padding=1) + b2.view(1, -1, 1, 1), t
+
+
+@pytest.mark.parametrize("n,h,w", SHAPES + [(1, 64, 126), (1, 70, 127), (3, 64, 253)])
+def test_resblock_pair_matches_fp32_reference(dev, n, h, w):
+    g = torch.Generator(device=dev).manual_seed(n * 100000 + h * 1000 + w + 1)
+    x = bf(torch.randn((n, 64, h, w), generator=g, device=dev))
+    par = torch.rand((n, 3, h, w), generator=g, device=dev) * \
+        (torch.rand((n, 3, h, w), generator=g, device=dev) > 0.5)
+    wt2, wt1, w1x1, b1, b2, ws1, ws2 = _block_weights(dev, g)
+    ref, t_ref = _block_reference(x, par, wt2, wt1, w1x1, b1, b2)
+    xs = nhwc(x)
+    out = torch.full_like(xs, float("nan"))
+    ops.resblock(xs, out, ws1, ws2, par, bias1=b1, bias2=b2)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all(), "unwritten or non-finite output pixels"
+    # t is rounded to bf16 before conv1: a one-ulp flip of t (|t| <~ 4) moves the output by <~ 2^-7 * 0.15
+    got = nchw(out)
+    tol = ref.abs() * 2.0 ** -7 + 1e-2
+    bad = (got - ref).abs() > tol
+    assert not bad.any(), f"{int(bad.sum())} of {bad.numel()} off, max {float((got - ref).abs().max())}"
+    assert (got - ref).abs().mean().item() < 2e-3
+    # and the two-launch path (pnp_conv3x3 launch A + launch B) agrees to the same degree
+    t2 = ops.new_feature(n, h, w, dev)
+    o2 = ops.new_feature(n, h, w, dev)
+    ops.conv3x3(xs, ws1, out=t2, bias=b1, par=par, act=ops.PNP_ACT_RELU, wlayout=1)
+    ops.conv3x3(t2, ws2, out=o2, idt=xs, bias=b2, wlayout=1)
+    assert (nchw(o2) - got).abs().max().item() <= 0.05
+    assert (nchw(o2) - got).abs().mean().item() < 1e-3
+
+
+def test_resblock_pair_720p_identity_and_shift(dev):
+    """Full REDS4 shape, exact properties: zero weights give out == x; a pure-shift conv2 followed by a
+    pure-shift conv1 moves the (non-negative) image by two pixels with zero fill -- bit for bit."""
+    g = torch.Generator(device=dev).manual_seed(9)
+    h, w = 720, 1280
+    x = nhwc(bf(torch.rand((1, 64, h, w), generator=g, device=dev)))
+    par = torch.zeros((1, 3, h, w), device=dev)
+    zero = torch.zeros((64, 64, 3, 3), device=dev)
+    ws1, ws2 = ops.new_wpack_rowstack(dev, with_par=True), ops.new_wpack_rowstack(dev)
+    ops.pack_conv3x3_rowstack(zero, ws1)
+    ops.pack_conv3x3_rowstack(zero, ws2)
+    out = ops.new_feature(1, h, w, dev)
+    ops.resblock(x, out, ws1, ws2, par)
+    assert torch.equal(out, x)
+    sh2 = torch.zeros((64, 64, 3, 3), device=dev)
+    sh2[:, :, 0, 2] = torch.eye(64, device=dev)          # t(y,x) = x(y-1,x+1)
+    sh1 = torch.zeros((64, 64, 3, 3), device=dev)
+    sh1[:, :, 2, 0] = torch.eye(64, device=dev)          # conv1(t)(y,x) = t(y+1,x-1)
+    ops.pack_conv3x3_rowstack(sh2, ws1)
+    ops.pack_conv3x3_rowstack(sh1, ws2)
+    ops.resblock(x, out, ws1, ws2, par)
+    # t(y+1,x-1) = x(y,x) wherever t's pixel (y+1,x-1) lies inside the image, else 0
+    exp = x.float() * 2.0
+    exp[:, h - 1, :, :] = x[:, h - 1].float()
+    exp[:, :, 0, :] = x[:, :, 0].float()
+    assert torch.equal(out, exp.to(torch.bfloat16))
+
+
+def test_resblock_rejects_bad_arguments(dev):
+    x = ops.new_feature(1, 64, 64, dev)
+    ws1, ws2 = ops.new_wpack_rowstack(dev, with_par=True), ops.new_wpack_rowstack(dev)
+    par = torch.zeros((1, 3, 64, 64), device=dev)
+    with pytest.raises(_lib.PnpError):
+        ops.resblock(x, x, ws1, ws2, par)                                  # aliasing
+    with pytest.raises(ValueError):
+        ops.resblock(x, ops.new_feature(1, 64, 64, dev), ws2, ws2, par)    # stage-1 pack too small
+    with pytest.raises(ValueError):
+        ops.resblock(x, ops.new_feature(1, 64, 64, dev), ws1, ws2, par[:, :2])

@@ -1,0 +1,75 @@
+"""Isolated timing of one BAE residual block at a given shape: fused CTA-pair kernel vs the two-launch path.
+   python tools/bench_block.py [H W [N]]      (diagnostic; PNP_TRACE=1 dumps the MMA threads' per-step clocks)"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pnpvcve_b200 import ops  # noqa: E402
+
+h, w = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (720, 1280)
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(0)
+x = torch.randn((n, h, w, 64), generator=g, device=dev).to(torch.bfloat16)
+par = (torch.rand((n, 3, h, w), generator=g, device=dev) > 0.66).float() / 255.0
+wt2 = torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05
+wt1 = torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05
+b = torch.randn(64, generator=g, device=dev) * 0.1
+ws1 = ops.new_wpack_rowstack(dev, with_par=True)
+ops.pack_conv3x3_rowstack(wt2, ws1)
+for j in range(3):
+    ops.pack_rows(torch.randn((64, 64), generator=g, device=dev) * 0.1, ws1[9 * ops.CHUNK_BYTES:], 64 * j)
+ws2 = ops.new_wpack_rowstack(dev)
+ops.pack_conv3x3_rowstack(wt1, ws2)
+wa = ops.new_wpack(12, dev)
+ops.pack_conv3x3(wt2, wa, center_chunks=4)
+t = ops.new_feature(n, h, w, dev)
+outs = [ops.new_feature(n, h, w, dev) for _ in range(2)]
+
+
+def fused(i):
+    ops.resblock(x if i % 2 == 0 else outs[0], outs[0] if i % 2 == 0 else outs[1], ws1, ws2, par, bias1=b, bias2=b)
+
+
+def two_launch(i):
+    ops.conv3x3(x, wa, out=t, bias=b, par=par, act=ops.PNP_ACT_RELU)
+    ops.conv3x3(t, ws2, out=outs[i % 2], idt=x, bias=b, wlayout=1)
+
+
+def rows_par(i):
+    ops.conv3x3(x, ws1, out=t, bias=b, par=par, act=ops.PNP_ACT_RELU, wlayout=1)
+
+
+def timeit(fn, iters=40):
+    for i in range(4):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+flop = 2.0 * (64 * 64 * 9 * 2 + 3 * 64 * 64) * n * h * w
+for name, fn in (("fused pair", fused), ("two launches", two_launch), ("rows kPar (launch A only)", rows_par)):
+    us = timeit(fn)
+    print(f"{name:28s} {us:8.1f} us   {flop / us * 1e-6:7.1f} TFLOP/s (block FLOPs)")
+
+if os.environ.get("PNP_TRACE"):
+    tr = torch.zeros(2 * 128 * 4, dtype=torch.int64, device=dev)
+    os.environ["PNP_TRACE_PTR"] = str(tr.data_ptr())
+    fused(0)
+    torch.cuda.synchronize()
+    del os.environ["PNP_TRACE_PTR"]
+    v = tr.view(2, 128, 4).cpu()
+    for role in range(2):
+        t0 = int(v[role, 0, 0])
+        print(f"role {role}: step  begin  go-check  end   (cycles since first step; delta to previous begin)")
+        for s in range(4, 40):
+            bgn = int(v[role, s, 0])
+            print(f"  {s:3d} {bgn - t0:8d} {int(v[role, s, 1]) - bgn:6d} {int(v[role, s, 2]) - bgn:6d}   d={bgn - int(v[role, s - 1, 0])}")
