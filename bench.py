@@ -232,7 +232,7 @@ def main():
         for i in range(args.warmup):
             step_resident(i)
         barrier()
-        net._engine.prof = {"block_a": [], "warp": [], "block_b": []}
+        net._engine.prof = {"block": [], "block_a": [], "warp": [], "block_b": []}
         net._engine.prof_every = args.prof_every
         sampler = ClockSampler(local_rank) if rank == 0 else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -356,7 +356,7 @@ def main():
                     clocks=clocks, e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d,
                                             d2h_bytes_per_step=d2h, steps=e2e_steps),
                     gpu_launches=launches * world, roofline=roofline, roofline_warp=roofline_warp,
-                    kernels_ms=dict(block_a=a_ms, block_b=b_ms, warp=w_ms), cpu_baseline=cpu_baseline)
+                    kernels_ms=dict(block=mean_event_ms(prof["block"]), block_a=a_ms, block_b=b_ms, warp=w_ms), cpu_baseline=cpu_baseline)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

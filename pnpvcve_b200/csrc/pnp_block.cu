@@ -31,6 +31,9 @@ namespace pnp {
 
 namespace {
 
+constexpr int kBlockThreads = 384;   // warps 0 TMA / relay, 1 MMA, 2 scout, 3 DSMEM copy issuer, 4-11 epilogue
+constexpr int kCtrlRegs = 104;        // setmaxnreg: the control warpgroup (warps 0-3) gives registers ...
+constexpr int kEpiRegs = 200;        // ... to the two epilogue warpgroups (launch allocation: 168 per thread)
 constexpr int kRing0 = 5;        // stage-1 accumulator ring (5 x 64 TMEM columns)
 constexpr int kRing1 = 8;        // stage-2 accumulator ring (8 x 64 TMEM columns)
 constexpr int kParCol = 320;     // stage 1: TMEM column of the partition 1x1 accumulators (3 x 64)
@@ -45,13 +48,13 @@ struct PairMisc {
   uint64_t a_full[kMaxSlots];      // stage 1: source rows (TMA); stage 2: rows of t (partner's bulk copies)
   uint64_t step_done[kStepRing];   // tcgen05.commit after every step (one input row)
   uint64_t acc_free[kMaxSlots];    // epilogue -> MMA: accumulator slot drained
-  uint64_t par_done[2];            // stage 1, by row parity: partition accumulators ready
-  uint64_t par_free[2];            // stage 1, by row parity: ... and read
   uint64_t t_free[kMaxSlots];      // stage 1: the partner's MMAs are done with ring slot i (remote arrive)
-  uint64_t stage_free[2];          // stage 1: the copy out of staging tile g has landed (remote arrive)
+  uint64_t stage_free[2];          // stage 1: the copy out of staging tile b has landed (remote arrive)
+  uint64_t staged[2];              // stage 1: all eight epilogue warps have written staging tile b
+  uint64_t par_done;               // stage 1: the partition accumulators of a row are complete (own commit)
   uint32_t tmem_base;
   uint32_t go_step;
-  uint32_t go_par;
+  uint32_t go_par;                 // stage 1: epilogue-warp reads of the partition region (8 per row of t)
 };
 static_assert(sizeof(PairMisc) <= 1024, "misc region overflow");
 
@@ -156,7 +159,7 @@ struct RowCur {
 // Same issue discipline as pnp_conv_rows.cu (see the notes there): straight-line tcgen05.mma with
 // descriptor = base word + immediate, barriers of the next step polled through the scout's counter in
 // the middle of the current step, commits deferred behind the next step's first MMA.
-template <bool kPar, int kAccRing>
+template <bool kPar, int kAccRing, bool kTrace>
 __device__ __forceinline__ void mma_issue_loop(const BlockParams& p, PairMisc* misc, uint32_t w_smem,
                                                uint32_t a_smem, uint32_t ring_slots, SegIter seg_it,
                                                uint32_t tmem_base, int role) {
@@ -205,8 +208,8 @@ __device__ __forceinline__ void mma_issue_loop(const BlockParams& p, PairMisc* m
   if (cur.valid) spin_until_ge(go_step, 1, 5);
   tc_fence_after();
   while (cur.valid) {
-    const bool tr = (p.trace != nullptr) && blockIdx.x < 2 && cur.sc < 128;
-    long long* trp = p.trace + (role * 128 + (int)cur.sc) * 4;
+    const bool tr = kTrace && blockIdx.x < 2 && cur.sc < 128;
+    long long* trp = p.trace + (role * 128 + (int)cur.sc) * 8;
     if (tr) trp[0] = clock64();
     const int lo = max(cur.j - 1, 0);
     const int hi = min(cur.j + 1, cur.len - 1);
@@ -247,13 +250,15 @@ __device__ __forceinline__ void mma_issue_loop(const BlockParams& p, PairMisc* m
     }
     if (kPar && centre) {
       // partition 1x1 convs of this row of t: centre pixel column, N = 192, own TMEM region
-      spin_until_ge(go_par, cur_od + 1, 10);
+      spin_until_ge(go_par, kEpilogueWarps * cur_od, 10);   // all eight warps have read row cur_od-1's region
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         umma_bf16_lo(tmem_base + kParCol, a_row + 8 + 2 * k, kDescHiSw128, par_w_lo + 2 * k, kDescHiSw128,
                      idesc0 + 3 * idesc_step, k > 0);
-      umma_commit(smem_u32(&misc->par_done[cur_od & 1]));
+      // own commit, not deferred: the epilogue's read of this region is on the only recurrence of the
+      // pipeline (the next row's 1x1 MMAs wait for it)
+      umma_commit(smem_u32(&misc->par_done));
     }
     pend = true;
     pend_bar = smem_u32(&misc->step_done[cur_sc & (kStepRing - 1)]);
@@ -269,7 +274,7 @@ __device__ __forceinline__ void mma_issue_loop(const BlockParams& p, PairMisc* m
 template <bool kPar, int kAccRing>
 __device__ __forceinline__ void scout_loop(const BlockParams& p, PairMisc* misc, uint32_t ring_slots, SegIter it,
                                            uint32_t remote_stage_free) {
-  const uint32_t go_step = smem_u32(&misc->go_step), go_par = smem_u32(&misc->go_par);
+  const uint32_t go_step = smem_u32(&misc->go_step);
   Ring ar(ring_slots);
   uint32_t sc = 0, ord0 = 0;
   for (; it.valid(); it.next()) {
@@ -284,11 +289,6 @@ __device__ __forceinline__ void scout_loop(const BlockParams& p, PairMisc* misc,
         mbar_wait(smem_u32(&misc->acc_free[od % kAccRing]), ((od / kAccRing) & 1) ^ 1, 6);
       }
       st_release_shared(go_step, sc + 1);
-      if (kPar && j >= 0 && j < s.len) {                  // the previous row's 1x1 results have been read
-        const uint32_t od = ord0 + j;
-        if (od >= 1) mbar_wait(smem_u32(&misc->par_free[(od - 1) & 1]), ((od - 1) >> 1) & 1, 10);
-        st_release_shared(go_par, od + 1);
-      }
     }
     ord0 += s.len;
   }
@@ -296,7 +296,8 @@ __device__ __forceinline__ void scout_loop(const BlockParams& p, PairMisc* misc,
 
 }  // namespace
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kRowsThreads, 1)
+template <bool kTrace>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kBlockThreads, 1)
 resblock_pair_kernel(const __grid_constant__ BlockParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -325,15 +326,15 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
       mbar_init(smem_u32(&misc->w_full), 1);
       for (int i = 0; i < kMaxSlots; ++i) {
         mbar_init(smem_u32(&misc->a_full[i]), 1);
-        mbar_init(smem_u32(&misc->acc_free[i]), 4);     // the four warps of one epilogue group
+        mbar_init(smem_u32(&misc->acc_free[i]), role == 0 ? 8 : 4);   // stage 1: all epilogue warps, stage 2: one group
         mbar_init(smem_u32(&misc->t_free[i]), 1);
       }
       for (int i = 0; i < kStepRing; ++i) mbar_init(smem_u32(&misc->step_done[i]), 1);
       for (int i = 0; i < 2; ++i) {
-        mbar_init(smem_u32(&misc->par_done[i]), 1);
-        mbar_init(smem_u32(&misc->par_free[i]), 4);
         mbar_init(smem_u32(&misc->stage_free[i]), 1);
+        mbar_init(smem_u32(&misc->staged[i]), kEpilogueWarps);
       }
+      mbar_init(smem_u32(&misc->par_done), 1);
       misc->go_step = 0;
       misc->go_par = 0;
       mbar_fence_init();
@@ -352,6 +353,8 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
   const uint32_t w_smem = sbase + L.w;
   const uint32_t ring_smem = sbase + L.ring;
 
+  if (warp < 4) {
+    setmaxnreg_dec<kCtrlRegs>();      // control warpgroup: hand registers to the epilogue warpgroups
   if (warp == 0) {
     if (elect_one()) {
       const uint32_t wbar = smem_u32(&misc->w_full);
@@ -397,13 +400,13 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
   } else if (warp == 1) {
     if (elect_one()) {
       if (role == 0)
-        mma_issue_loop<true, kRing0>(p, misc, w_smem, ring_smem, ring_slots, SegIter(p, t_begin, t_end, true),
+        mma_issue_loop<true, kRing0, kTrace>(p, misc, w_smem, ring_smem, ring_slots, SegIter(p, t_begin, t_end, true),
                                      tmem_base, 0);
       else
-        mma_issue_loop<false, kRing1>(p, misc, w_smem, ring_smem, ring_slots, SegIter(p, t_begin, t_end, false),
+        mma_issue_loop<false, kRing1, kTrace>(p, misc, w_smem, ring_smem, ring_slots, SegIter(p, t_begin, t_end, false),
                                       tmem_base, 1);
     }
-  } else if (warp == 10) {
+  } else if (warp == 2) {
     if (elect_one()) {
       if (role == 0)
         scout_loop<true, kRing0>(p, misc, ring_slots, SegIter(p, t_begin, t_end, true), 0u);
@@ -411,110 +414,181 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
         scout_loop<false, kRing1>(p, misc, ring_slots, SegIter(p, t_begin, t_end, false),
                                   mapa_shared(smem_u32(&misc->stage_free[0]), 0));
     }
+  } else if (warp == 3) {
+    // ============================================================ stage 1: DSMEM copy issuer
+    // Pushes every staged row of t into the partner's ring.  A thread of its own: the remote
+    // arrive.expect_tx + bulk copy took ~2000 cycles when the epilogue's store lane issued them.
+    if (role == 0 && elect_one()) {
+      const uint32_t r_ring = mapa_shared(sbase + L1.ring, 1);
+      const uint32_t r_full = mapa_shared(smem_u32(&misc->a_full[0]), 1);
+      Ring tr(p.n_t);
+      uint32_t ord = 0;
+      for (RowCur cur(p, t_begin, t_end, true); cur.valid; cur.next(), tr.advance(), ++ord) {
+        const uint32_t b = ord & 1;
+        mbar_wait(smem_u32(&misc->staged[b]), (ord >> 1) & 1, 14);
+        mbar_wait(smem_u32(&misc->t_free[tr.slot]), tr.phase ^ 1, 13);
+        mbar_arrive_expect_tx_remote(r_full + tr.slot * 8, kTileBytes);
+        bulk_copy_to_cluster(r_ring + tr.slot * kASlotBytes, sbase + L0.stage + b * kTileBytes, kTileBytes,
+                             r_full + tr.slot * 8);
+      }
+    }
+  }
   } else {
+    setmaxnreg_inc<kEpiRegs>();
     // ============================================================ epilogue: two groups of four warps,
     // group g owns the rows with ordinal = g (mod 2); thread = one pixel (TMEM lane), all 64 channels
     const int q = warp & 3;
-    const int g = (warp - 2) >> 2;
+    const int g = (warp - 4) >> 2;
     const int m = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t sw = (uint32_t)(m & 7);
-    const bool lead = (warp == 2 + 4 * g);
+    const bool lead = (warp == 4 + 4 * g);
     const uint32_t bar_id = 1 + g;
     uint32_t k = 0;                            // rows this group has finished
     if (role == 0) {
       // ---------------------------------------------------------- stage 1: t = relu(3x3 + bias + blend)
-      uint8_t* rowp = sgen + L0.stage + g * kTileBytes + m * 128;
-      const uint32_t stage_u32 = sbase + L0.stage + g * kTileBytes;
-      const uint32_t r_ring = mapa_shared(sbase + L1.ring, 1);
-      const uint32_t r_full = mapa_shared(smem_u32(&misc->a_full[0]), 1);
-      Ring tr(p.n_t), accr(kRing0);
-      for (RowCur cur(p, t_begin, t_end, true); cur.valid; cur.next(), tr.advance(), accr.advance()) {
-        if ((cur.ord & 1u) != (uint32_t)g) continue;
-        const Segment& s = cur.s;
-        const int px = s.strip * kBlockOutPx - 1 + m;
-        const int y = s.y_b + cur.o;
-        const bool in_img = (px >= 0) && (px < p.W);
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-        if (in_img) {
-          const float* pp = p.par + (long long)s.n * p.par_sn + (long long)y * p.par_sy + px;
-          p0 = __ldg(pp);
-          p1 = __ldg(pp + p.par_sc);
-          p2 = __ldg(pp + 2 * p.par_sc);
-        }
-        // partition blend + bias (the 1x1 accumulators of a row finish with its centre step)
-        float dy[64];
-        mbar_wait_warp(smem_u32(&misc->par_done[g]), k & 1, 11);
-        tc_fence_after();
+      // All eight warps work on every row: thread = (pixel, 32-channel half).  The 1x1 accumulators of row
+      // r+1 finish with the same step that completes the 3x3 result of row r (they are issued last in
+      // that step), so both are fetched in ONE TMEM batch behind one barrier wait and the partition region
+      // is handed back to the MMA thread (plain counter, no mbarrier / scout hop) ~200 cycles after it
+      // became readable; the blend of row r+1 waits in registers (dy_nxt) for that row's 3x3 result.
+      const int half = g;
+      const bool store_warp = (warp == 4);
+      const uint32_t go_par = smem_u32(&misc->go_par);
+      float dy_cur[32], dy_nxt[32];
+      // This thread's 32 bias values live in registers: the shared-memory pipe is ~85 % busy feeding the
+      // MMAs, so every LDS on the epilogue's critical path costs hundreds of cycles (measured: the blend
+      // took ~300 cycles per 8-channel chunk with the bias read from shared memory).
+      float bias_r[32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+      for (int j = 0; j < 32; ++j) bias_r[j] = misc->bias[half * 32 + j];
+      auto par_blend = [&](const float (&a1)[16], const float (&a2)[16], const float (&a3)[16], float q0, float q1,
+                           float q2, int c16, float* dy) {   // 16-channel chunk c16 of this thread's 32 channels
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          dy[c16 * 16 + j] = fmaf(q2, a3[j], fmaf(q1, a2[j], fmaf(q0, a1[j], bias_r[c16 * 16 + j])));
+      };
+      // partition accumulators -> blend in two TMEM round trips (48 live registers each); `after_last` runs
+      // once all loads have completed, before the last chunk's arithmetic
+      auto par_part = [&](float q0, float q1, float q2, float* dy, auto&& after_last) {
+#pragma unroll
+        for (int c16 = 0; c16 < 2; ++c16) {
           float a1[16], a2[16], a3[16];
-          tmem_ld16(lane_base + kParCol + c * 16, a1);
-          tmem_ld16(lane_base + kParCol + 64 + c * 16, a2);
-          tmem_ld16(lane_base + kParCol + 128 + c * 16, a3);
+          const uint32_t col = kParCol + half * 32 + c16 * 16;
+          tmem_ld16(lane_base + col, a1);
+          tmem_ld16(lane_base + col + 64, a2);
+          tmem_ld16(lane_base + col + 128, a3);
           tmem_ld_wait();
-          const float4* bi4 = reinterpret_cast<const float4*>(&misc->bias[c * 16]);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 bi = bi4[j4];
-            dy[c * 16 + 4 * j4 + 0] = fmaf(p2, a3[4 * j4 + 0], fmaf(p1, a2[4 * j4 + 0], fmaf(p0, a1[4 * j4 + 0], bi.x)));
-            dy[c * 16 + 4 * j4 + 1] = fmaf(p2, a3[4 * j4 + 1], fmaf(p1, a2[4 * j4 + 1], fmaf(p0, a1[4 * j4 + 1], bi.y)));
-            dy[c * 16 + 4 * j4 + 2] = fmaf(p2, a3[4 * j4 + 2], fmaf(p1, a2[4 * j4 + 2], fmaf(p0, a1[4 * j4 + 2], bi.z)));
-            dy[c * 16 + 4 * j4 + 3] = fmaf(p2, a3[4 * j4 + 3], fmaf(p1, a2[4 * j4 + 3], fmaf(p0, a1[4 * j4 + 3], bi.w)));
-          }
+          if (c16 == 1) after_last();
+          par_blend(a1, a2, a3, q0, q1, q2, c16, dy);
         }
-        tc_fence_before();
-        warp_arrive(smem_u32(&misc->par_free[g]));
-        // 3x3 accumulators of the row
-        const uint32_t scl = cur.sc_last();
-        mbar_wait_warp(smem_u32(&misc->step_done[scl & (kStepRing - 1)]), (scl >> 3) & 1, 9);
+      };
+      auto par_load = [&](const RowCur& c, float& q0, float& q1, float& q2) {
+        const int px = c.s.strip * kBlockOutPx - 1 + m;
+        q0 = q1 = q2 = 0.f;
+        if (px >= 0 && px < p.W) {
+          const float* pp = p.par + (long long)c.s.n * p.par_sn + (long long)(c.s.y_b + c.o) * p.par_sy + px;
+          q0 = __ldg(pp);
+          q1 = __ldg(pp + p.par_sc);
+          q2 = __ldg(pp + 2 * p.par_sc);
+        }
+      };
+      // Per-row facts the loop needs, computed from ONE heavy cursor that runs two rows ahead (it also
+      // fetches that row's partition values: they come from HBM, ~1000 cycles, and the blend needs them).
+      struct RowInfo {
+        int strip;
+        uint32_t sc_last, sc_centre;
+        bool valid;
+      };
+      RowCur look(p, t_begin, t_end, true);
+      float pq0 = 0.f, pq1 = 0.f, pq2 = 0.f;
+      auto fetch = [&](RowInfo& ri) {          // describe the row under `look`, load its partition values, advance
+        ri.valid = look.valid;
+        ri.strip = look.s.strip;
+        ri.sc_last = look.sc_last();
+        ri.sc_centre = look.sc0 + (uint32_t)(look.o - look.s.j_first);
+        pq0 = pq1 = pq2 = 0.f;
+        if (look.valid) {
+          par_load(look, pq0, pq1, pq2);
+          look.next();
+        }
+      };
+      RowInfo rc, rn, rl;
+      float pn0, pn1, pn2;
+      fetch(rc);
+      if (rc.valid) {                          // partition part of the very first row
+        const float q0 = pq0, q1 = pq1, q2 = pq2;
+        mbar_wait_warp(smem_u32(&misc->par_done), 0, 11);
         tc_fence_after();
-        if (lead) {                            // the previous copy out of this group's staging tile has landed
-          if (lane == 0) mbar_wait_cluster(smem_u32(&misc->stage_free[g]), (k & 1) ^ 1, 12);
-          __syncwarp();
-        }
-        named_bar_sync(bar_id, 128);
-        const uint32_t taddr = lane_base + accr.slot * 64;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float v[32];
-          if (p.debug_skip & 4) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          } else {
-            tmem_ld16(taddr + h * 32, v);
-            tmem_ld16(taddr + h * 32 + 16, v + 16);
-            tmem_ld_wait();
-          }
-          if (h == 1) {
+        par_part(q0, q1, q2, dy_cur, [&]() {
+          tc_fence_before();
+          warp_flag_add(go_par);
+        });
+      }
+      fetch(rn);
+      pn0 = pq0, pn1 = pq1, pn2 = pq2;
+      Ring accr(kRing0);
+      uint32_t ord = 0;
+      // one row: 3x3 result of row `rc` (+ dyc) -> t; partition blend of row `rn` -> dyn
+      auto row_body = [&](float* dyc, float* dyn) {
+        const bool etr = kTrace && blockIdx.x < 2 && store_warp && lane == 0 && ord < 128;
+        long long* etp = p.trace + (2 * 128 + (int)ord) * 8;
+        if (etr) etp[0] = clock64();
+        const int px = rc.strip * kBlockOutPx - 1 + m;
+        const bool in_img = (px >= 0) && (px < p.W);
+        const uint32_t taddr = lane_base + accr.slot * 64 + half * 32;
+        if (rn.valid) {                        // partition accumulators of the next row first: that region is
+          mbar_wait_warp(smem_u32(&misc->par_done), (ord + 1) & 1, 11);   // the one the MMA thread waits for
+          tc_fence_after();
+          if (etr) etp[2] = clock64();
+          par_part(pn0, pn1, pn2, dyn, [&]() {
             tc_fence_before();
-            warp_arrive(smem_u32(&misc->acc_free[accr.slot]));
-          }
-#pragma unroll
-          for (int gg = 0; gg < 2; ++gg) {
-            const int c2 = h * 2 + gg;         // 16-channel group
-            uint32_t w[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float lo = fmaxf(v[gg * 16 + 2 * j] + dy[c2 * 16 + 2 * j], 0.f);
-              const float hi = fmaxf(v[gg * 16 + 2 * j + 1] + dy[c2 * 16 + 2 * j + 1], 0.f);
-              w[j] = in_img ? pack_bf16x2(lo, hi) : 0u;     // t outside the image is conv1's zero padding
-            }
-            *reinterpret_cast<uint4*>(rowp + (((2 * c2) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(rowp + (((2 * c2 + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
-          }
+            warp_flag_add(go_par);
+            if (etr) etp[7] = clock64();
+          });
         }
+        mbar_wait_warp(smem_u32(&misc->step_done[rc.sc_last & (kStepRing - 1)]), (rc.sc_last >> 3) & 1, 9);
+        tc_fence_after();
+        float v[32];
+        tmem_ld16(taddr, v);
+        tmem_ld16(taddr + 16, v + 16);
+        tmem_ld_wait();
+        tc_fence_before();
+        warp_arrive_relaxed(smem_u32(&misc->acc_free[accr.slot]));
+        if (etr) etp[3] = clock64();
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float lo = fmaxf(v[2 * j] + dyc[2 * j], 0.f);
+          const float hi = fmaxf(v[2 * j + 1] + dyc[2 * j + 1], 0.f);
+          w[j] = in_img ? pack_bf16x2(lo, hi) : 0u;         // t outside the image is conv1's zero padding
+        }
+        // the copy out of this staging tile (row ord-2) landed long ago; the wait is a formality
+        mbar_wait_warp(smem_u32(&misc->stage_free[ord & 1]), ((ord >> 1) & 1) ^ 1, 12);
+        if (etr) etp[1] = clock64();
+        uint8_t* rowp = sgen + L0.stage + (ord & 1) * kTileBytes + m * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)            // 16-byte chunks 4*half .. 4*half+3 of the pixel's 128-byte row
+          *reinterpret_cast<uint4*>(rowp + (((4 * half + c) ^ sw) << 4)) =
+              make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
         fence_proxy_async_smem();
-        named_bar_sync(bar_id, 128);
-        if (lead) {
-          if (elect_one()) {
-            mbar_wait_cluster(smem_u32(&misc->t_free[tr.slot]), tr.phase ^ 1, 13);
-            mbar_arrive_expect_tx_remote(r_full + tr.slot * 8, kTileBytes);
-            bulk_copy_to_cluster(r_ring + tr.slot * kASlotBytes, stage_u32, kTileBytes, r_full + tr.slot * 8);
-          }
-          __syncwarp();
-        }
-        ++k;
+        warp_arrive(smem_u32(&misc->staged[ord & 1]));     // the copy warp pushes the tile to the partner
+        if (etr) etp[4] = clock64();
+        // shift the look-ahead pipeline
+        rc = rn;
+        fetch(rl);
+        rn = rl;
+        pn0 = pq0, pn1 = pq1, pn2 = pq2;
+        ++ord;
+        accr.advance();
+      };
+      // NOT unrolled by two for a register ping-pong: the kernel's hot code must stay inside the 32 KB
+      // L1.5 instruction cache (ncu: 40 % of this loop's stall samples were instruction-fetch misses when it
+      // did not); 32 register moves per row are cheaper.
+      while (rc.valid) {
+        row_body(dy_cur, dy_nxt);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dy_cur[j] = dy_nxt[j];
       }
     } else {
       // ---------------------------------------------------------- stage 2: out = x + 3x3(t) + bias
@@ -522,6 +596,9 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
       Ring accr(kRing1);
       for (RowCur cur(p, t_begin, t_end, false); cur.valid; cur.next(), accr.advance()) {
         if ((cur.ord & 1u) != (uint32_t)g) continue;
+        const bool etr = kTrace && blockIdx.x < 2 && lead && lane == 0 && k < 128;
+        long long* etp = p.trace + ((4 + g) * 128 + (int)k) * 8;
+        if (etr) etp[0] = clock64();
         const Segment& s = cur.s;
         const int x0 = s.strip * kBlockOutPx;
         const int px = x0 + m;
@@ -543,9 +620,11 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
           __syncwarp();
         }
         named_bar_sync(bar_id, 128);
+        if (etr) etp[1] = clock64();
         const uint32_t scl = cur.sc_last();
         mbar_wait_warp(smem_u32(&misc->step_done[scl & (kStepRing - 1)]), (scl >> 3) & 1, 9);
         tc_fence_after();
+        if (etr) etp[2] = clock64();
         uint8_t* rowp = sgen + L1.stage + s_io * kTileBytes + m * 128;
         const uint32_t taddr = lane_base + accr.slot * 64;
 #pragma unroll
@@ -561,7 +640,7 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
           }
           if (h == 1) {
             tc_fence_before();
-            warp_arrive(smem_u32(&misc->acc_free[accr.slot]));
+            warp_arrive_relaxed(smem_u32(&misc->acc_free[accr.slot]));
           }
 #pragma unroll
           for (int gg = 0; gg < 2; ++gg) {
@@ -584,6 +663,7 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
         }
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
+        if (etr) etp[3] = clock64();
         if (lead) {
           if (elect_one() && !(p.debug_skip & 2)) {
             tma_store_4d(&p.tm_out, sbase + L1.stage + s_io * kTileBytes, 0, x0, y, s.n);
@@ -614,19 +694,21 @@ size_t block_smem_bytes(const BlockParams& p) {
   return (a > b ? a : b) + 1024;
 }
 
-cudaError_t launch_block(const BlockParams& p, int pairs, cudaStream_t stream) {
+namespace {
+template <bool kTrace>
+cudaError_t launch_block_variant(const BlockParams& p, int pairs, cudaStream_t stream) {
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    e = cudaFuncSetAttribute(resblock_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    e = cudaFuncSetAttribute(resblock_pair_kernel<kTrace>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(kRowsThreads);
+  cfg.blockDim = dim3(kBlockThreads);
   cfg.dynamicSmemBytes = block_smem_bytes(p);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -634,7 +716,15 @@ cudaError_t launch_block(const BlockParams& p, int pairs, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, resblock_pair_kernel, p);
+  return cudaLaunchKernelEx(&cfg, resblock_pair_kernel<kTrace>, p);
+}
+}  // namespace
+
+// the tracing variant is a separate kernel so that its extra code never sits in the instruction cache
+// of production launches
+cudaError_t launch_block(const BlockParams& p, int pairs, cudaStream_t stream) {
+  return p.trace != nullptr ? launch_block_variant<true>(p, pairs, stream)
+                            : launch_block_variant<false>(p, pairs, stream);
 }
 
 }  // namespace pnp

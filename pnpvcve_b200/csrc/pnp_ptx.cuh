@@ -164,6 +164,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -252,6 +259,21 @@ __device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
   asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
+// counter variant: every lane has finished its reads, lane 0 adds 1 for the warp.
+// RELAXED on purpose: what is being handed over are TMEM reads that tcgen05.wait::ld has already
+// completed, and a release here would also wait for this thread's outstanding global loads (the
+// partition-map prefetch, ~1000 cycles from HBM) -- measured as a 400-1500 cycle stall per row.
+__device__ __forceinline__ void warp_flag_add(uint32_t addr) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0)
+    asm volatile("red.relaxed.cta.shared::cta.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+// same reasoning for "this TMEM accumulator has been read" arrivals
+__device__ __forceinline__ void warp_arrive_relaxed(uint32_t bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0)
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void spin_until_ge(uint32_t addr, uint32_t target, int tag) {
   uint32_t spins = 0;
   while (ld_acquire_shared(addr) < target) {
@@ -283,10 +305,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // arrive on an mbarrier of another CTA of the cluster (address from mapa_shared)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint32_t cluster_bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar),
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar),
                "r"(bytes)
                : "memory");
 }
@@ -334,6 +356,17 @@ __device__ __forceinline__ void griddep_launch_dependents() {
 }
 __device__ __forceinline__ void griddep_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ register re-allocation between warpgroups
+// (whole warpgroups of 4 consecutive warps must execute the same instruction)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // ------------------------------------------------------------------ misc

@@ -89,6 +89,29 @@ class _Launcher:
         if rc != 0:
             _lib.check(rc, "pnp_conv3x3")
 
+    def block(self, stream, x, out, w_stage1, w_stage2, bias1, bias2, par, label="block"):
+        """One fused residual block (pnp_resblock) with a reusable descriptor."""
+        if getattr(self, "bdesc", None) is None:
+            self.bdesc = ops.BlockDesc()
+            self.bref = ctypes.byref(self.bdesc)
+            self.bfn = self.lib.pnp_resblock
+        ops.fill_block_desc(self.bdesc, x, out, w_stage1, w_stage2, bias1, bias2, par)
+        timed = self.prof is not None and label in self.prof
+        if timed:
+            k = self.seen.get(label, 0)
+            self.seen[label] = k + 1
+            timed = (k % self.prof_every) == 0
+        if timed:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        rc = self.bfn(self.bref, stream)
+        if timed:
+            e1.record()
+            self.prof[label].append((e0, e1))
+        if rc != 0:
+            _lib.check(rc, "pnp_resblock")
+
 
 class BaeEngine:
     """Owns the packed weights and work buffers of one generator instance on one device."""
@@ -114,6 +137,9 @@ class BaeEngine:
         #: batch runs of identically-conditioned clips into N-image launches (up to max_batch clips)
         self.batch_clips = os.environ.get("PNP_BATCH_CLIPS", "1") != "0"
         self.max_batch = 16
+        #: run each BAE block as ONE launch of the CTA-pair kernel (pnp_resblock: the intermediate activation
+        #: stays on chip) instead of launch A + launch B of pnp_conv3x3
+        self.fused_block = os.environ.get("PNP_FUSED_BLOCK", "0") != "0"
 
     # ------------------------------------------------------------------ weights
     def _param_key(self):
@@ -152,19 +178,23 @@ class BaeEngine:
                 st["fwd_key"] = pack(3)
                 st["fwd_merged"] = pack(3, 67)
                 st["fwd_nb"] = pack(67)
-            conv1_w, conv1_b, c2w, c2b, onebyone = [], [], [], [], []
+            conv1_w, conv1_dn, conv1_b, c2w, c2b, onebyone = [], [], [], [], [], []
             for blk in branch.main:
                 # block launch B walks the image bottom-up (flip_y): launch A wrote its bottom rows
                 # last, so B finds them in L2; B in turn writes the top rows last, where A starts
                 buf = ops.new_wpack_rowstack(dev)
                 ops.pack_conv3x3_rowstack(f32(blk.conv1.weight), buf, flip_ky=True)
                 conv1_w.append(buf)
+                buf = ops.new_wpack_rowstack(dev)                      # top-down copy for the fused block kernel
+                ops.pack_conv3x3_rowstack(f32(blk.conv1.weight), buf)
+                conv1_dn.append(buf)
                 conv1_b.append(f32(blk.conv1.bias))
                 c2w.append(f32(blk.conv2.weight))
                 c2b.append(f32(blk.conv2.bias))
                 onebyone.append([f32(c.weight).view(64, 64) for c in
                                  (blk.conv16x16, blk.conv16x8, blk.conv8x8)])
             st[name + "_conv1_w"], st[name + "_conv1_b"] = conv1_w, conv1_b
+            st[name + "_conv1_dn"] = conv1_dn
             st[name + "_conv2_w"], st[name + "_1x1"] = c2w, onebyone
             st[name + "_conv2_bias"] = torch.stack(c2b, 0).contiguous()      # (nb, E, 64)
         st["conv2_bias_all"] = torch.cat([st["bwd_conv2_bias"], st["fwd_conv2_bias"]], 0).contiguous()
@@ -190,6 +220,7 @@ class BaeEngine:
         its QP, so the packed kernels gamma_o * sum_e a_e W_e are cached per distinct (CRF, QP)
         pair -- 3 pairs per clip in the IPB configs, at most ~15 in the CRF config.
         """
+        key = (key, self.fused_block)
         hit = self.mix_cache.get(key)
         if hit is not None:
             return hit
@@ -197,6 +228,14 @@ class BaeEngine:
         for name in ("bwd", "fwd"):
             lst = []
             for k in range(st["nb"]):
+                if self.fused_block:
+                    # stage-1 pack of pnp_resblock: row-stacked mix + the three 1x1 convs stacked behind it
+                    buf = ops.new_wpack_rowstack(dev, with_par=True)
+                    ops.pack_conv3x3_rowstack(st[name + "_conv2_w"][k], buf, coef=coef_row, row_scale=gamma_row)
+                    for j, w1 in enumerate(st[name + "_1x1"][k]):
+                        ops.pack_rows(w1, buf[9 * ops.CHUNK_BYTES:], 64 * j)
+                    lst.append(buf)
+                    continue
                 # block launch A stays on the tap-major kernel (centre tap N=256): its row-stacked
                 # variant is correct but its single partition-accumulator hand-off is slower for now
                 buf = ops.new_wpack(12, dev)
@@ -328,6 +367,14 @@ class BaeEngine:
                 f = b * t + i
                 par = par_map[b0:b1, i]
                 other = buf["xb"] if x is buf["xa"] else buf["xa"]
+                if self.fused_block:
+                    for k in range(nb):
+                        o = dst if k == nb - 1 else other
+                        conv.block(stream, x, o, mixed[name][k], st[name + "_conv1_dn"][k],
+                                   bias_tab[f, blk_off + k], st[name + "_conv1_b"][k], par)
+                        x, other = o, x
+                    counts[lane] += nb
+                    return
                 for k in range(nb):
                     conv(stream, x, mixed[name][k], out=buf["t"], bias=bias_tab[f, blk_off + k],
                          par=par, act=PNP_ACT_RELU, label="block_a")

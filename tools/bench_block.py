@@ -61,15 +61,25 @@ for name, fn in (("fused pair", fused), ("two launches", two_launch), ("rows kPa
     print(f"{name:28s} {us:8.1f} us   {flop / us * 1e-6:7.1f} TFLOP/s (block FLOPs)")
 
 if os.environ.get("PNP_TRACE"):
-    tr = torch.zeros(2 * 128 * 4, dtype=torch.int64, device=dev)
+    tr = torch.zeros(6 * 128 * 8, dtype=torch.int64, device=dev)
     os.environ["PNP_TRACE_PTR"] = str(tr.data_ptr())
     fused(0)
     torch.cuda.synchronize()
     del os.environ["PNP_TRACE_PTR"]
-    v = tr.view(2, 128, 4).cpu()
+    v = tr.view(6, 128, 8).cpu()
+    t0 = int(v[0, 0, 0])
+    lo, hi = 20, 34
     for role in range(2):
-        t0 = int(v[role, 0, 0])
-        print(f"role {role}: step  begin  go-check  end   (cycles since first step; delta to previous begin)")
-        for s in range(4, 40):
-            bgn = int(v[role, s, 0])
-            print(f"  {s:3d} {bgn - t0:8d} {int(v[role, s, 1]) - bgn:6d} {int(v[role, s, 2]) - bgn:6d}   d={bgn - int(v[role, s - 1, 0])}")
+        print(f"role {role} MMA thread: step  begin  +go-check  +end   (cycles since role-0 step 0; d = delta to previous begin)")
+        for s_ in range(lo, hi):
+            bgn = int(v[role, s_, 0])
+            print(f"  {s_:3d} {bgn - t0:8d} {int(v[role, s_, 1]) - bgn:6d} {int(v[role, s_, 2]) - bgn:6d}   d={bgn - int(v[role, s_ - 1, 0])}")
+    print("role 0 epilogue (8 warps): row  begin | +stage_free +step_done +tmem_read +staged | +par_released")
+    for k_ in range(lo, hi):
+        r = v[2, k_]
+        print(f"  {k_:3d} {int(r[0]) - t0:8d} | " + " ".join(f"{int(r[i]) - int(r[0]):6d}" for i in (1, 2, 3, 4, 7)))
+    for g_ in range(2):
+        print(f"role 1 epilogue group {g_}: row  begin | +slot_free +step_done +staged")
+        for k_ in range(lo // 2, hi // 2):
+            r = v[4 + g_, k_]
+            print(f"  {2 * k_ + g_:3d} {int(r[0]) - t0:8d} | " + " ".join(f"{int(r[i]) - int(r[0]):6d}" for i in range(1, 4)))
