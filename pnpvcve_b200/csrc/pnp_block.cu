@@ -271,7 +271,7 @@ __device__ __forceinline__ void mma_issue_loop(const BlockParams& p, PairMisc* m
 // ---------------------------------------------------------------------------------------- barrier scout
 // Does every mbarrier wait the MMAs depend on and publishes plain counters (see pnp_conv_rows.cu).
 // Stage 2 additionally acknowledges each landed row of t to the producer (its staging tile is free).
-template <bool kPar, int kAccRing>
+template <bool kPar, int kAccRing, bool kTrace>
 __device__ __forceinline__ void scout_loop(const BlockParams& p, PairMisc* misc, uint32_t ring_slots, SegIter it,
                                            uint32_t remote_stage_free) {
   const uint32_t go_step = smem_u32(&misc->go_step);
@@ -280,7 +280,11 @@ __device__ __forceinline__ void scout_loop(const BlockParams& p, PairMisc* misc,
   for (; it.valid(); it.next()) {
     const Segment s = it.get();
     for (int j = s.j_first; j <= s.j_last; ++j, ++sc, ar.advance()) {
+      const bool tr = kTrace && blockIdx.x < 2 && sc < 128;
+      long long* trp = p.trace + ((kPar ? 0 : 1) * 128 + (int)sc) * 8;
+      if (tr) trp[3] = clock64();
       mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
+      if (tr) trp[4] = clock64();
       if (!kPar) mbar_arrive_remote(remote_stage_free + (sc & 1) * 8);
       const int lo = max(j - 1, 0), hi = min(j + 1, s.len - 1);
       const int new_from = (j == s.j_first) ? lo : j + 1;
@@ -288,6 +292,7 @@ __device__ __forceinline__ void scout_loop(const BlockParams& p, PairMisc* misc,
         const uint32_t od = ord0 + o;
         mbar_wait(smem_u32(&misc->acc_free[od % kAccRing]), ((od / kAccRing) & 1) ^ 1, 6);
       }
+      if (tr) trp[5] = clock64();
       st_release_shared(go_step, sc + 1);
     }
     ord0 += s.len;
@@ -350,6 +355,10 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
   const uint32_t tmem_base = misc->tmem_base;
   griddep_launch_dependents();
   griddep_wait();
+  if (kTrace && threadIdx.x == 0) {
+    if (blockIdx.x == 0) p.trace[6 * 128 * 8] = clock64();
+    p.trace[6 * 128 * 8 + 8 + blockIdx.x * 2] = (long long)globaltimer_ns();
+  }
   const uint32_t w_smem = sbase + L.w;
   const uint32_t ring_smem = sbase + L.ring;
 
@@ -409,9 +418,9 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
   } else if (warp == 2) {
     if (elect_one()) {
       if (role == 0)
-        scout_loop<true, kRing0>(p, misc, ring_slots, SegIter(p, t_begin, t_end, true), 0u);
+        scout_loop<true, kRing0, kTrace>(p, misc, ring_slots, SegIter(p, t_begin, t_end, true), 0u);
       else
-        scout_loop<false, kRing1>(p, misc, ring_slots, SegIter(p, t_begin, t_end, false),
+        scout_loop<false, kRing1, kTrace>(p, misc, ring_slots, SegIter(p, t_begin, t_end, false),
                                   mapa_shared(smem_u32(&misc->stage_free[0]), 0));
     }
   } else if (warp == 3) {
@@ -682,6 +691,10 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (kTrace && threadIdx.x == 0) {
+    if (blockIdx.x == 0) p.trace[6 * 128 * 8 + 1] = clock64();
+    p.trace[6 * 128 * 8 + 8 + blockIdx.x * 2 + 1] = (long long)globaltimer_ns();
+  }
   cluster_sync_all();            // no remote arrive / bulk copy may target a CTA that has exited
   if (warp == 0) {
     tc_fence_after();

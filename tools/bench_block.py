@@ -56,24 +56,39 @@ def timeit(fn, iters=40):
 
 
 flop = 2.0 * (64 * 64 * 9 * 2 + 3 * 64 * 64) * n * h * w
-for name, fn in (("fused pair", fused), ("two launches", two_launch), ("rows kPar (launch A only)", rows_par)):
-    us = timeit(fn)
+import subprocess  # noqa: E402
+smi = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-lms", "100"],
+                       stdout=subprocess.PIPE, text=True)
+for name, fn in (("fused pair", lambda i: fused(i)), ("fused pair x400", None), ("two launches", two_launch), ("rows kPar (launch A only)", rows_par)):
+    us = timeit(fn) if fn is not None else timeit(fused, iters=400)
     print(f"{name:28s} {us:8.1f} us   {flop / us * 1e-6:7.1f} TFLOP/s (block FLOPs)")
 
+smi.terminate()
+clk = [ln.split(",")[0].strip() for ln in smi.communicate()[0].strip().splitlines()]
+print("SM clock samples (MHz) during the timing loops:", " ".join(clk[:60]))
 if os.environ.get("PNP_TRACE"):
-    tr = torch.zeros(6 * 128 * 8, dtype=torch.int64, device=dev)
+    tr = torch.zeros(6 * 128 * 8 + 8 + 2 * 148, dtype=torch.int64, device=dev)
     os.environ["PNP_TRACE_PTR"] = str(tr.data_ptr())
-    fused(0)
+    for i_ in range(6):
+        fused(i_)
     torch.cuda.synchronize()
     del os.environ["PNP_TRACE_PTR"]
-    v = tr.view(6, 128, 8).cpu()
+    print('CTA 0 body cycles:', int(tr[6 * 128 * 8 + 1] - tr[6 * 128 * 8]))
+    gt = tr[6 * 128 * 8 + 8:].view(148, 2).cpu()
+    g0 = int(gt[:, 0].min())
+    print('per-CTA (start, end) in us since first CTA start:')
+    print(' '.join(f'{(int(a) - g0) / 1e3:.0f}-{(int(b) - g0) / 1e3:.0f}' for a, b in gt.tolist()))
+    dur = sorted((int(b) - int(a)) / 1e3 for a, b in gt.tolist() if b > a)
+    print('CTA durations us: min %.0f median %.0f max %.0f' % (dur[0], dur[len(dur) // 2], dur[-1]))
+    v = tr[:6 * 128 * 8].view(6, 128, 8).cpu()
     t0 = int(v[0, 0, 0])
     lo, hi = 20, 34
     for role in range(2):
         print(f"role {role} MMA thread: step  begin  +go-check  +end   (cycles since role-0 step 0; d = delta to previous begin)")
         for s_ in range(lo, hi):
             bgn = int(v[role, s_, 0])
-            print(f"  {s_:3d} {bgn - t0:8d} {int(v[role, s_, 1]) - bgn:6d} {int(v[role, s_, 2]) - bgn:6d}   d={bgn - int(v[role, s_ - 1, 0])}")
+            print(f"  {s_:3d} {bgn - t0:8d} {int(v[role, s_, 1]) - bgn:6d} {int(v[role, s_, 2]) - bgn:6d}   d={bgn - int(v[role, s_ - 1, 0])}"
+                  f"   scout(step {s_ + 1}): begin {int(v[role, s_ + 1, 3]) - bgn:6d} input-row {int(v[role, s_ + 1, 4]) - bgn:6d} acc-free {int(v[role, s_ + 1, 5]) - bgn:6d}")
     print("role 0 epilogue (8 warps): row  begin | +stage_free +step_done +tmem_read +staged | +par_released")
     for k_ in range(lo, hi):
         r = v[2, k_]
