@@ -89,12 +89,12 @@ if os.environ.get("PNP_TRACE"):
             bgn = int(v[role, s_, 0])
             print(f"  {s_:3d} {bgn - t0:8d} {int(v[role, s_, 1]) - bgn:6d} {int(v[role, s_, 2]) - bgn:6d}   d={bgn - int(v[role, s_ - 1, 0])}"
                   f"   scout(step {s_ + 1}): begin {int(v[role, s_ + 1, 3]) - bgn:6d} input-row {int(v[role, s_ + 1, 4]) - bgn:6d} acc-free {int(v[role, s_ + 1, 5]) - bgn:6d}")
-    print("role 0 epilogue (8 warps): row  begin | +stage_free +step_done +tmem_read +staged | +par_released")
+    for wv in (2, 3):
+        print(f"role 0 epilogue warp {wv + 2}: row  begin | +acc_ready +par_released +staged")
+        for k_ in range(lo, hi):
+            r = v[wv, k_]
+            print(f"  {k_:3d} {int(r[0]) - t0:8d} | " + " ".join(f"{int(r[i]) - int(r[0]):6d}" for i in (1, 3, 2)))
+    print("role 1 epilogue: row  begin | +acc_ready +staged")
     for k_ in range(lo, hi):
-        r = v[2, k_]
-        print(f"  {k_:3d} {int(r[0]) - t0:8d} | " + " ".join(f"{int(r[i]) - int(r[0]):6d}" for i in (1, 2, 3, 4, 7)))
-    for g_ in range(2):
-        print(f"role 1 epilogue group {g_}: row  begin | +slot_free +step_done +staged")
-        for k_ in range(lo // 2, hi // 2):
-            r = v[4 + g_, k_]
-            print(f"  {2 * k_ + g_:3d} {int(r[0]) - t0:8d} | " + " ".join(f"{int(r[i]) - int(r[0]):6d}" for i in range(1, 4)))
+        r = v[4, k_]
+        print(f"  {k_:3d} {int(r[0]) - t0:8d} | " + " ".join(f"{int(r[i]) - int(r[0]):6d}" for i in range(1, 3)))

@@ -17,8 +17,8 @@
 
 using namespace pnp;
 
-__global__ void __launch_bounds__(384, 1)
-interf_kernel(int steps, int mask, int pace, const uint8_t* gsrc, long long* out_cycles, float* sink) {
+__global__ void __launch_bounds__(640, 1)
+interf_kernel(int steps, int mask, int pace, int nread, const uint8_t* gsrc, long long* out_cycles, float* sink) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar, done_bar[8], ld_bar, never_bar;
   __shared__ uint32_t tmem_slot;
@@ -65,7 +65,11 @@ interf_kernel(int steps, int mask, int pace, const uint8_t* gsrc, long long* out
       const long long t0 = clock64();
       bool pend = false;
       uint32_t pend_bar = 0;
-      for (int s = 0; s < steps; ++s) {
+      if (mask & 64) {
+        while (clock64() - t0 < 400000) {
+        }
+      }
+      for (int s = 0; s < ((mask & 64) ? 0 : steps); ++s) {
         const uint32_t slot = (uint32_t)(s & 3) * 64;
         const uint32_t a_row = a_lo0 + (uint32_t)(s & 3) * 1088;
         umma_bf16_lo(tmem + slot, a_row, kDescHiSw128, b_lo0, kDescHiSw128, id128, 1);
@@ -97,14 +101,31 @@ interf_kernel(int steps, int mask, int pace, const uint8_t* gsrc, long long* out
         phase ^= 1;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + nread) {
     const int q = warp & 3;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     float acc = 0.f;
     long long t_next = clock64();
+    long long ld_cycles = 0;
+    int ld_batches = 0;
     uint8_t* rowp = sgen + 170 * 1024 + (q * 32 + lane) * 128;
     const uint32_t swz = (uint32_t)(lane & 7);
     const int half = (warp - 4) >> 2;
+    if (mask & 128) {                       // pure ALU pressure on every sub-partition (no memory ops)
+      float x0 = acc + 1.f, x1 = 2.f, x2 = 3.f, x3 = 4.f;
+      int it = 0;
+      do {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          x0 = fmaf(x0, 1.0001f, 0.5f);
+          x1 = fmaf(x1, 1.0002f, 0.25f);
+          x2 = fmaf(x2, 0.9999f, 0.125f);
+          x3 = fmaf(x3, 0.9998f, 0.0625f);
+        }
+        ++it;
+      } while ((it & 7) != 0 || ld_acquire_shared(stop_addr) == 0);
+      acc += x0 + x1 + x2 + x3;
+    }
     while (ld_acquire_shared(stop_addr) == 0) {
       while (clock64() < t_next) {
         if (mask & 32) {
@@ -114,6 +135,7 @@ interf_kernel(int steps, int mask, int pace, const uint8_t* gsrc, long long* out
       }
       t_next += pace;
       if (mask & 2) {
+        const long long l0 = clock64();
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           float v[64];
@@ -125,6 +147,8 @@ interf_kernel(int steps, int mask, int pace, const uint8_t* gsrc, long long* out
 #pragma unroll
           for (int j = 0; j < 64; ++j) acc += v[j];
         }
+        ld_cycles += clock64() - l0;
+        ++ld_batches;
       }
       if (mask & 16) {
 #pragma unroll
@@ -145,6 +169,7 @@ interf_kernel(int steps, int mask, int pace, const uint8_t* gsrc, long long* out
       }
     }
     if (acc == 123.456f) sink[threadIdx.x] = acc;
+    if (blockIdx.x == 0 && threadIdx.x == 128 && ld_batches > 0) out_cycles[255] = ld_cycles / ld_batches;
   }
   tc_fence_before();
   __syncthreads();
@@ -160,32 +185,36 @@ int main() {
   long long* d;
   float* sink;
   uint8_t* gsrc;
-  cudaMalloc(&d, sizeof(long long) * sms);
+  cudaMalloc(&d, sizeof(long long) * 256);
+  cudaMemset(d, 0, sizeof(long long) * 256);
   cudaMalloc(&sink, 4096);
   cudaMalloc(&gsrc, (size_t)sms * 16640);
   cudaMemset(gsrc, 0x3c, (size_t)sms * 16640);
   cudaFuncSetAttribute(interf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
   const int steps = 400;
-  const int masks[] = {0, 1, 2, 4, 8, 16, 32, 2 | 4 | 8, 1 | 2 | 4 | 8, 1 | 2 | 4 | 8 | 16 | 32};
-  for (int pace : {1200, 600}) {
+  const int masks[] = {0, 128};
+  for (int nread : {4, 8, 16}) {
+    const int pace = 1200;
     for (int mask : masks) {
       double best = 1e30;
+      long long ld = 0;
       for (int rep = 0; rep < 3; ++rep) {
-        interf_kernel<<<sms, 384, 210 * 1024>>>(steps, mask, pace, gsrc, d, sink);
+        interf_kernel<<<sms, 640, 210 * 1024>>>(steps, mask, pace, nread, gsrc, d, sink);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
           printf("mask %d: %s\n", mask, cudaGetErrorString(e));
           return 1;
         }
         long long h[256];
-        cudaMemcpy(h, d, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
+        cudaMemcpy(h, d, sizeof(long long) * 256, cudaMemcpyDeviceToHost);
         double mean = 0;
         for (int i = 0; i < sms; ++i) mean += (double)h[i];
         mean /= sms;
         if (mean < best) best = mean;
+        ld = h[255];
       }
-      printf("pace %4d mask %2d: %7.1f cycles/step  (%5.1f per MMA; ideal 12 x 98.6 = 1183)\n", pace, mask,
-             best / steps, best / steps / 12.0);
+      printf("readers %2d mask %2d: %7.1f cycles/step  (%5.1f per MMA; ideal 12 x 98.6 = 1183); 128-value TMEM read batch: %lld cycles\n",
+             nread, mask, best / steps, best / steps / 12.0, ld);
     }
   }
   return 0;
