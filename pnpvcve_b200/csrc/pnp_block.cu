@@ -31,10 +31,14 @@ namespace pnp {
 
 namespace {
 
-constexpr int kEpiWarps = 16;
-constexpr int kBlockThreads = 640;   // warps 0 TMA / relay, 1 MMA, 2 scout, 3 copy / store issuer, 4-19 epilogue
-constexpr int kCtrlRegs = 128;       // setmaxnreg: the control warpgroup (warps 0-3) takes registers ...
-constexpr int kEpiRegs = 88;         // ... from the four epilogue warpgroups (launch allocation: 96 per thread)
+// Eight epilogue warps, not sixteen: measured (tools/umma_interf.cu, profiles/r01_umma_interf_alu.log) the warp
+// scheduler does not favour the MMA-issuing thread -- four ALU-busy warps on its sub-partition slow MMA issue
+// 4.2x, two by 19 %, one not at all.
+constexpr int kEpiWarps = 8;
+constexpr int kEpiCh = 64 / (kEpiWarps / 4);   // channels per epilogue thread
+constexpr int kBlockThreads = 128 + 32 * kEpiWarps;   // warps 0 TMA / relay, 1 MMA, 2 scout, 3 copy / store issuer, 4.. epilogue
+constexpr int kCtrlRegs = 128;       // setmaxnreg: the control warpgroup (warps 0-3) ...
+constexpr int kEpiRegs = 184;        // ... vs the epilogue warpgroups (launch allocation: 168 per thread)
 constexpr int kRing0 = 5;        // stage-1 accumulator ring (5 x 64 TMEM columns)
 constexpr int kRing1 = 8;        // stage-2 accumulator ring (8 x 64 TMEM columns)
 constexpr int kParCol = 320;     // stage 1: TMEM column of the partition 1x1 accumulators (3 x 64)
@@ -160,6 +164,59 @@ struct RowCur {
 // Same issue discipline as pnp_conv_rows.cu (see the notes there): straight-line tcgen05.mma with
 // descriptor = base word + immediate, barriers of the next step polled through the scout's counter in
 // the middle of the current step, commits deferred behind the next step's first MMA.
+// One INTERIOR step (source row j with 1 <= j <= len-2: three output rows, two already touched, one new;
+// next step in the same segment) as straight-line code.  The MMA-issuing thread shares its sub-partition's
+// scheduler with epilogue warps and is not favoured by it (tools/umma_interf.cu), so every instruction it
+// does not execute is tensor-pipe time: all offsets are immediates, the only runtime inputs are the A-row
+// descriptor word, the accumulator column of the window and the flags to poll.  N1 = rows of the 3-row
+// window before the accumulator ring wraps (3 = no wrap).
+template <bool kPar, int N1>
+__device__ __forceinline__ void mma_fast_step(uint32_t tmem_base, uint32_t win_col, uint32_t a_row, uint32_t w_lo,
+                                              uint32_t go_step, uint32_t next_target, uint32_t go_par,
+                                              uint32_t par_target, uint32_t pend_bar, uint32_t par_done_bar) {
+  constexpr uint32_t kI64 = umma_idesc_bf16(128, 64), kI128 = umma_idesc_bf16(128, 128),
+                     kI192 = umma_idesc_bf16(128, 192);
+  const uint32_t d0 = tmem_base + win_col;
+  // first MMA of the step: rows 0,1 of the window accumulate, row 2 is overwritten
+  if (N1 >= 2) {
+    umma_bf16_lo(d0, a_row, kDescHiSw128, w_lo, kDescHiSw128, kI128, 1);
+    umma_bf16_lo(N1 == 3 ? d0 + 128 : tmem_base, a_row, kDescHiSw128, w_lo + 2 * kSbb, kDescHiSw128, kI64, 0);
+  } else {
+    umma_bf16_lo(d0, a_row, kDescHiSw128, w_lo, kDescHiSw128, kI64, 1);
+    umma_bf16_lo(tmem_base, a_row, kDescHiSw128, w_lo + kSbb, kDescHiSw128, kI64, 1);
+    umma_bf16_lo(tmem_base + 64, a_row, kDescHiSw128, w_lo + 2 * kSbb, kDescHiSw128, kI64, 0);
+  }
+  if (pend_bar != 0) umma_commit(pend_bar);   // the previous step's commit rides behind this step's first MMA
+#pragma unroll
+  for (int dx = 0; dx < 3; ++dx) {
+    if (dx == 2) {
+      spin_until_ge(go_step, next_target, 5);  // barriers of the NEXT step; normally long satisfied
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (dx == 0 && k == 0) continue;
+      const uint32_t a_lo = a_row + dx * 8 + 2 * k;
+      const uint32_t b_lo = w_lo + dx * kDxb + 2 * k;
+      if (N1 == 3) {
+        umma_bf16_lo(d0, a_lo, kDescHiSw128, b_lo, kDescHiSw128, kI192, 1);
+      } else {
+        umma_bf16_lo(d0, a_lo, kDescHiSw128, b_lo, kDescHiSw128, N1 == 2 ? kI128 : kI64, 1);
+        umma_bf16_lo(tmem_base, a_lo, kDescHiSw128, b_lo + N1 * kSbb, kDescHiSw128, N1 == 2 ? kI64 : kI128, 1);
+      }
+    }
+  }
+  if (kPar) {
+    spin_until_ge(go_par, par_target, 10);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16_lo(tmem_base + kParCol, a_row + 8 + 2 * k, kDescHiSw128, w_lo + 3 * kDxb + 2 * k, kDescHiSw128, kI192,
+                   k > 0);
+    umma_commit(par_done_bar);
+  }
+}
+
 template <bool kPar, int kAccRing, bool kTrace>
 __device__ __forceinline__ void mma_issue_loop(const BlockParams& p, PairMisc* misc, uint32_t w_smem,
                                                uint32_t a_smem, uint32_t ring_slots, SegIter seg_it,
@@ -208,10 +265,32 @@ __device__ __forceinline__ void mma_issue_loop(const BlockParams& p, PairMisc* m
   };
   if (cur.valid) spin_until_ge(go_step, 1, 5);
   tc_fence_after();
+  const uint32_t par_done_bar = smem_u32(&misc->par_done);
   while (cur.valid) {
     const bool tr = kTrace && blockIdx.x < 2 && cur.sc < 128;
     long long* trp = p.trace + (role * 128 + (int)cur.sc) * 8;
     if (tr) trp[0] = clock64();
+    if (cur.j >= 1 && cur.j + 2 <= cur.len) {
+      // interior step: see mma_fast_step
+      const uint32_t s0 = (cur.ord0 + (uint32_t)(cur.j - 1)) % kAccRing;
+      const uint32_t a_row = umma_desc_lo(a_smem + cur.a_slot * kASlotBytes);
+      const uint32_t pb = pend ? pend_bar : 0u;
+      const uint32_t par_target = kEpiWarps * (cur.ord0 + (uint32_t)cur.j);
+      if (s0 + 3 <= kAccRing)
+        mma_fast_step<kPar, 3>(tmem_base, s0 * 64, a_row, w_lo, go_step, cur.sc + 2, go_par, par_target, pb, par_done_bar);
+      else if (s0 + 2 == kAccRing)
+        mma_fast_step<kPar, 2>(tmem_base, s0 * 64, a_row, w_lo, go_step, cur.sc + 2, go_par, par_target, pb, par_done_bar);
+      else
+        mma_fast_step<kPar, 1>(tmem_base, s0 * 64, a_row, w_lo, go_step, cur.sc + 2, go_par, par_target, pb, par_done_bar);
+      pend = true;
+      pend_bar = smem_u32(&misc->step_done[cur.sc & (kStepRing - 1)]);
+      if (tr) trp[2] = clock64();
+      ar.advance();
+      cur.sc += 1;
+      cur.a_slot = ar.slot;
+      cur.j += 1;
+      continue;
+    }
     const int lo = max(cur.j - 1, 0);
     const int hi = min(cur.j + 1, cur.len - 1);
     const int cnt = hi - lo + 1;
@@ -259,7 +338,7 @@ __device__ __forceinline__ void mma_issue_loop(const BlockParams& p, PairMisc* m
                      idesc0 + 3 * idesc_step, k > 0);
       // own commit, not deferred: the epilogue's read of this region is on the only recurrence of the
       // pipeline (the next row's 1x1 MMAs wait for it)
-      umma_commit(smem_u32(&misc->par_done));
+      umma_commit(par_done_bar);
     }
     pend = true;
     pend_bar = smem_u32(&misc->step_done[cur_sc & (kStepRing - 1)]);
@@ -364,7 +443,7 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
   const uint32_t ring_smem = sbase + L.ring;
 
   if (warp < 4) {
-    setmaxnreg_inc<kCtrlRegs>();      // control warpgroup: registers released by the epilogue warpgroups
+    setmaxnreg_dec<kCtrlRegs>();      // control warpgroup: hands registers to the epilogue warpgroups
   if (warp == 0) {
     if (elect_one()) {
       const uint32_t wbar = smem_u32(&misc->w_full);
@@ -461,7 +540,7 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
     }
   }
   } else {
-    setmaxnreg_dec<kEpiRegs>();
+    setmaxnreg_inc<kEpiRegs>();
     // ============================================================ epilogue: sixteen warps, thread = one pixel
     // (TMEM lane) x 16 channels.  Small on purpose: ncu showed the earlier 8-warp / 4-warp epilogues (32 / 64
     // channels per thread, ~800 straight-line instructions per row) spending 40 % of their samples on
@@ -469,14 +548,15 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
     // This one is ~150 instructions, all four warps of a sub-partition run the same code in phase, and the
     // per-row latency is short enough for ONE team to keep up with the MMA steps.
     const int q = warp & 3;
-    const int cq = (warp - 4) >> 2;            // channel quarter: channels 16 cq .. 16 cq + 15
+    const int cq = (warp - 4) >> 2;            // channel group: channels kEpiCh*cq .. kEpiCh*cq + kEpiCh-1
     const int m = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t sw = (uint32_t)(m & 7);
-    const bool lead = (warp == 4);
-    float bias_r[16];
+    constexpr int kChunk = 16;                 // channels per partition-accumulator round trip
+    constexpr int kChunks = kEpiCh / kChunk;
+    float bias_r[kEpiCh];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) bias_r[j] = misc->bias[cq * 16 + j];
+    for (int j = 0; j < kEpiCh; ++j) bias_r[j] = misc->bias[cq * kEpiCh + j];
     if (role == 0) {
       // ---------------------------------------------------------- stage 1: t = relu(3x3 + bias + blend)
       // Iteration k: the step that completes the 3x3 result of row k also carries the 1x1 accumulators of row
@@ -495,14 +575,33 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
           q2 = __ldg(pp + 2 * p.par_sc);
         }
       };
-      float dy[16];
-      auto blend8 = [&](const float (&a1)[8], const float (&a2)[8], const float (&a3)[8], float q0, float q1, float q2,
-                        int h) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dy[h * 8 + j] = fmaf(q2, a3[j], fmaf(q1, a2[j], fmaf(q0, a1[j], bias_r[h * 8 + j])));
+      float dy[kEpiCh];
+      const uint32_t par_col = lane_base + kParCol + cq * kEpiCh;
+      auto par_ld = [&](int c, float (&a1)[kChunk], float (&a2)[kChunk], float (&a3)[kChunk]) {
+        tmem_ld16(par_col + c * kChunk, a1);
+        tmem_ld16(par_col + 64 + c * kChunk, a2);
+        tmem_ld16(par_col + 128 + c * kChunk, a3);
       };
-      const uint32_t par_col = lane_base + kParCol + cq * 16;
+      auto blend = [&](const float (&a1)[kChunk], const float (&a2)[kChunk], const float (&a3)[kChunk], float q0,
+                       float q1, float q2, int c) {
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j)
+          dy[c * kChunk + j] = fmaf(q2, a3[j], fmaf(q1, a2[j], fmaf(q0, a1[j], bias_r[c * kChunk + j])));
+      };
+      // whole partition part of one row (first row of a segment: nothing else to read with it)
+      auto par_row = [&](float q0, float q1, float q2) {
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          float a1[kChunk], a2[kChunk], a3[kChunk];
+          par_ld(c, a1, a2, a3);
+          tmem_ld_wait();
+          if (c == kChunks - 1) {
+            tc_fence_before();
+            warp_flag_add(go_par);
+          }
+          blend(a1, a2, a3, q0, q1, q2, c);
+        }
+      };
       RowCur cur(p, t_begin, t_end, true);     // row k
       RowCur look = cur;                       // runs ahead: fetches partition values one row early
       float n0, n1, n2;
@@ -511,22 +610,10 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
         par_load(look, q0, q1, q2);            // row 0
         if (look.valid) look.next();
         par_load(look, n0, n1, n2);            // row 1
-        if (cur.valid) {                       // partition part of row 0
+        if (cur.valid) {
           mbar_wait_warp(smem_u32(&misc->par_done), 0, 11);
           tc_fence_after();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float a1[8], a2[8], a3[8];
-            tmem_ld8(par_col + h * 8, a1);
-            tmem_ld8(par_col + 64 + h * 8, a2);
-            tmem_ld8(par_col + 128 + h * 8, a3);
-            tmem_ld_wait();
-            if (h == 1) {
-              tc_fence_before();
-              warp_flag_add(go_par);
-            }
-            blend8(a1, a2, a3, q0, q1, q2, h);
-          }
+          par_row(q0, q1, q2);
         }
       }
       uint32_t k = 0;
@@ -547,64 +634,62 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
         }
         tc_fence_after();
         if (etr) etp[1] = clock64();
-        float v[16];
-        uint32_t w[8];
-        const uint32_t acc_col = lane_base + slot * 64 + cq * 16;
-        if (same_seg) {
-          // 3x3 result of row k and the first half of row k+1's partition accumulators in one round trip
-          float a1[8], a2[8], a3[8];
-          tmem_ld16(acc_col, v);
-          tmem_ld8(par_col, a1);
-          tmem_ld8(par_col + 64, a2);
-          tmem_ld8(par_col + 128, a3);
-          tmem_ld_wait();
+        uint32_t w[kEpiCh / 2];
+        const uint32_t acc_col = lane_base + slot * 64 + cq * kEpiCh;
+        {
+          float v[kEpiCh];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2_relu(v[2 * j] + dy[2 * j], v[2 * j + 1] + dy[2 * j + 1]);
-          blend8(a1, a2, a3, n0, n1, n2, 0);   // dy of row k is dead from here on
-          tmem_ld8(par_col + 8, a1);
-          tmem_ld8(par_col + 72, a2);
-          tmem_ld8(par_col + 136, a3);
-          tmem_ld_wait();
-          tc_fence_before();
-          warp_flag_add(go_par);               // region handed back ~2 TMEM round trips after it became readable
-          if (etr) etp[3] = clock64();
-          blend8(a1, a2, a3, n0, n1, n2, 1);
-        } else {
-          tmem_ld16(acc_col, v);
-          tmem_ld_wait();
-          tc_fence_before();
+          for (int g = 0; g < kEpiCh / 16; ++g) tmem_ld16(acc_col + g * 16, v + g * 16);
+          if (same_seg) {
+            // 3x3 result of row k and the first chunk of row k+1's partition accumulators in one round trip
+            float a1[kChunk], a2[kChunk], a3[kChunk];
+            par_ld(0, a1, a2, a3);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2_relu(v[2 * j] + dy[2 * j], v[2 * j + 1] + dy[2 * j + 1]);
+            for (int j = 0; j < kEpiCh / 2; ++j) w[j] = pack_bf16x2_relu(v[2 * j] + dy[2 * j], v[2 * j + 1] + dy[2 * j + 1]);
+            if (kChunks == 1) {
+              tc_fence_before();
+              warp_flag_add(go_par);
+              if (etr) etp[3] = clock64();
+            }
+            blend(a1, a2, a3, n0, n1, n2, 0);  // dy of row k is dead from here on
+#pragma unroll
+            for (int c = 1; c < kChunks; ++c) {
+              par_ld(c, a1, a2, a3);
+              tmem_ld_wait();
+              if (c == kChunks - 1) {          // region handed back a few TMEM round trips after it became readable
+                tc_fence_before();
+                warp_flag_add(go_par);
+                if (etr) etp[3] = clock64();
+              }
+              blend(a1, a2, a3, n0, n1, n2, c);
+            }
+          } else {
+            tmem_ld_wait();
+            tc_fence_before();
+#pragma unroll
+            for (int j = 0; j < kEpiCh / 2; ++j) w[j] = pack_bf16x2_relu(v[2 * j] + dy[2 * j], v[2 * j + 1] + dy[2 * j + 1]);
+          }
         }
         warp_arrive_relaxed(smem_u32(&misc->acc_free[slot]));
         if (!in_img) {                         // t outside the image is conv1's zero padding
 #pragma unroll
-          for (int j = 0; j < 8; ++j) w[j] = 0u;
+          for (int j = 0; j < kEpiCh / 2; ++j) w[j] = 0u;
         }
         // the copy out of this staging tile (row k-2) landed long ago; the wait is a formality
         mbar_wait_warp(smem_u32(&misc->stage_free[k & 1]), ((k >> 1) & 1) ^ 1, 12);
         uint8_t* rowp = sgen + L0.stage + (k & 1) * kTileBytes + m * 128;
-        *reinterpret_cast<uint4*>(rowp + (((2 * cq) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(rowp + (((2 * cq + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+#pragma unroll
+        for (int c = 0; c < kEpiCh / 8; ++c)   // 16-byte chunks of the pixel's 128-byte row
+          *reinterpret_cast<uint4*>(rowp + (((cq * (kEpiCh / 8) + c) ^ sw) << 4)) =
+              make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
         fence_proxy_async_smem();
         warp_arrive(smem_u32(&misc->staged[k & 1]));       // warp 3 pushes the tile to the partner
         if (etr) etp[2] = clock64();
         if (has_next && !same_seg) {           // first row of a new segment: its 1x1 MMAs come with a later step
           mbar_wait_warp(smem_u32(&misc->par_done), (k + 1) & 1, 11);
           tc_fence_after();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float a1[8], a2[8], a3[8];
-            tmem_ld8(par_col + h * 8, a1);
-            tmem_ld8(par_col + 64 + h * 8, a2);
-            tmem_ld8(par_col + 128 + h * 8, a3);
-            tmem_ld_wait();
-            if (h == 1) {
-              tc_fence_before();
-              warp_flag_add(go_par);
-            }
-            blend8(a1, a2, a3, n0, n1, n2, h);
-          }
+          par_row(n0, n1, n2);
         }
         if (has_next) {
           look.next();
@@ -619,39 +704,50 @@ resblock_pair_kernel(const __grid_constant__ BlockParams p) {
       const bool m_ok = m < kBlockOutPx;
       uint32_t k = 0, slot = 0;
       for (RowCur cur(p, t_begin, t_end, false); cur.valid; cur.next(), ++k) {
-        const bool etr = kTrace && blockIdx.x < 2 && lead && lane == 0 && k < 128;
+        const bool etr = kTrace && blockIdx.x < 2 && warp == 4 && lane == 0 && k < 128;
         long long* etp = p.trace + (4 * 128 + (int)k) * 8;
         if (etr) etp[0] = clock64();
         const Segment& s = cur.s;
         const int px = s.strip * kBlockOutPx + m;
         const int y = s.y_b + cur.o;
         const bool valid = m_ok && px < p.W;
-        uint4 i0 = make_uint4(0u, 0u, 0u, 0u), i1 = i0;
+        uint4 idv[kEpiCh / 8];
+#pragma unroll
+        for (int c = 0; c < kEpiCh / 8; ++c) idv[c] = make_uint4(0u, 0u, 0u, 0u);
         if (valid) {
-          const uint4* ip = reinterpret_cast<const uint4*>(
-              reinterpret_cast<const uint8_t*>(p.x) + (((long long)s.n * p.H + y) * p.W + px) * 128 + cq * 32);
-          i0 = ldg_nc_v4(ip);
-          i1 = ldg_nc_v4(ip + 1);
+          const uint4* ip = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) +
+                                                           (((long long)s.n * p.H + y) * p.W + px) * 128 +
+                                                           cq * (kEpiCh * 2));
+#pragma unroll
+          for (int c = 0; c < kEpiCh / 8; ++c) idv[c] = ldg_nc_v4(ip + c);
         }
         const uint32_t scl = cur.sc_last();
         mbar_wait_warp(smem_u32(&misc->step_done[scl & (kStepRing - 1)]), (scl >> 3) & 1, 9);
         tc_fence_after();
         if (etr) etp[1] = clock64();
-        float v[16];
-        tmem_ld16(lane_base + slot * 64 + cq * 16, v);
+        float v[kEpiCh];
+#pragma unroll
+        for (int g = 0; g < kEpiCh / 16; ++g) tmem_ld16(lane_base + slot * 64 + cq * kEpiCh + g * 16, v + g * 16);
         tmem_ld_wait();
         tc_fence_before();
         warp_arrive_relaxed(smem_u32(&misc->acc_free[slot]));
-        const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-        uint32_t w[8];
+        uint32_t w[kEpiCh / 2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          w[j] = pack_bf16x2(v[2 * j] + bias_r[2 * j] + bf16_lo(iw[j]), v[2 * j + 1] + bias_r[2 * j + 1] + bf16_hi(iw[j]));
+        for (int c = 0; c < kEpiCh / 8; ++c) {
+          const uint32_t iw[4] = {idv[c].x, idv[c].y, idv[c].z, idv[c].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int e = 8 * c + 2 * j;
+            w[4 * c + j] = pack_bf16x2(v[e] + bias_r[e] + bf16_lo(iw[j]), v[e + 1] + bias_r[e + 1] + bf16_hi(iw[j]));
+          }
+        }
         // the TMA store out of this staging tile (row k-2) has been read; formality
         mbar_wait_warp(smem_u32(&misc->stage_free[k & 1]), ((k >> 1) & 1) ^ 1, 12);
         uint8_t* rowp = sgen + L1.stage + (k & 1) * kTileBytes + m * 128;
-        *reinterpret_cast<uint4*>(rowp + (((2 * cq) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(rowp + (((2 * cq + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+#pragma unroll
+        for (int c = 0; c < kEpiCh / 8; ++c)
+          *reinterpret_cast<uint4*>(rowp + (((cq * (kEpiCh / 8) + c) ^ sw) << 4)) =
+              make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
         fence_proxy_async_smem();
         warp_arrive(smem_u32(&misc->staged[k & 1]));       // warp 3 issues the TMA store
         if (etr) etp[2] = clock64();
