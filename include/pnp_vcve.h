@@ -170,6 +170,10 @@ typedef struct pnp_conv_desc {
   int32_t flip_y;      /* PNP_WLAYOUT_ROWSTACK only: process rows bottom-up.  The result is identical when wpack
                           was packed with flip_ky = 1; alternating directions between dependent launches
                           makes each launch read first what its predecessor wrote last (L2 hits). */
+  int32_t wpack_stable; /* 1: wpack was NOT written by the operation immediately preceding this launch in the stream
+                          (weights are packed once per checkpoint / clip, long before the frame loop), so the
+                          kernel may fetch it while the previous kernel is still draining (programmatic dependent
+                          launch).  0: fetch it only after the previous kernel has completed. */
 } pnp_conv_desc;
 
 int pnp_conv3x3(const pnp_conv_desc* desc, void* stream);

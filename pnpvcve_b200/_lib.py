@@ -7,7 +7,9 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpnpvcve.so")
+#: PNP_LIB_PATH selects another BUILD of the same library (A/B timing of kernel revisions in tools/); it is
+#: not a fallback -- whatever it names must export the same C ABI
+LIB_PATH = os.environ.get("PNP_LIB_PATH") or os.path.join(HERE, "libpnpvcve.so")
 
 PNP_CONV_BF16, PNP_CONV_LAST = 0, 1
 PNP_ACT_NONE, PNP_ACT_LRELU, PNP_ACT_RELU = 0, 1, 2
@@ -36,7 +38,7 @@ class ConvDesc(_c.Structure):
         ("N", _c.c_int32), ("H", _c.c_int32), ("W", _c.c_int32),
         ("n_wchunks", _c.c_int32), ("center_n", _c.c_int32), ("tap_n", _c.c_int32),
         ("aux_k16", _c.c_int32), ("act", _c.c_int32), ("mode", _c.c_int32),
-        ("wlayout", _c.c_int32), ("flip_y", _c.c_int32),
+        ("wlayout", _c.c_int32), ("flip_y", _c.c_int32), ("wpack_stable", _c.c_int32),
     ]
 
 

@@ -93,7 +93,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 extern "C" {
 
-int pnp_abi_version(void) { return 5; }
+int pnp_abi_version(void) { return 6; }
 
 const char* pnp_last_error(void) { return g_err; }
 
@@ -306,6 +306,7 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   p.act = c->act;
   p.mode = last ? pnp::kModeLast : pnp::kModeBf16;
   p.flip_y = (rowstack && c->flip_y) ? 1 : 0;
+  p.w_stable = c->wpack_stable ? 1 : 0;
   p.base_off_mode = g_base_off_mode;
   {
     const char* dbg = getenv("PNP_DEBUG_SKIP");   // what-if profiling only; results are wrong when set
@@ -324,6 +325,7 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
     return w_bytes + (c->aux ? 2 * pnp::kTileBytes : 0) + (long long)n_io * pnp::kTileBytes;
   };
   p.n_io = 2;
+  if (rowstack && c->par) p.n_io = 3;   // the next row's 1x1 blend is parked in its staging slot one row early
   if (c->idt) {
     p.n_io = 4;
     while (p.n_io > 2 && (budget - fixed_bytes(p.n_io)) / pnp::kASlotBytes < 5) --p.n_io;

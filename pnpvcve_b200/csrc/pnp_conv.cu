@@ -161,8 +161,30 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
   // the tail of the previous kernel in the stream; nothing below touches global memory before the
   // previous kernel has completed (packed weights may have been written by the kernel just before).
   griddep_launch_dependents();
+  const uint32_t w_smem_early = sbase + L.w;
+  auto load_weights = [&]() {                 // one elected lane of warp 0
+    const uint32_t wbar = smem_u32(&misc->w_full);
+    mbar_arrive_expect_tx(wbar, p.n_wchunks * kWChunkBytes);
+    for (int c = 0; c < p.n_wchunks; ++c)
+      bulk_load_1d(w_smem_early + c * kWChunkBytes,
+                   reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)c * kWChunkBytes, kWChunkBytes, wbar);
+  };
+  // stable weights (packed long before this launch) are fetched while the previous kernel drains
+  if (p.w_stable && warp == 0) {
+    if (elect_one()) load_weights();
+    __syncwarp();
+  }
   griddep_wait();
 
+  // patient waits for threads that merely wait for work (see pnp_conv_rows.cu); debug bit 32 = patient polling
+  const bool hot_waits = (p.debug_skip & 32) == 0;
+  const uint32_t hint_ns = (p.debug_skip & 64) ? 40u : 200u;
+  auto pwait = [&](uint32_t bar, uint32_t parity, int tag) {      // one elected lane
+    if (hot_waits) mbar_wait(bar, parity, tag); else mbar_wait_patient(bar, parity, tag, hint_ns);
+  };
+  auto ewait = [&](uint32_t bar, uint32_t parity, int tag) {      // whole (converged) warp
+    if (hot_waits) mbar_wait(bar, parity, tag); else mbar_wait_warp(bar, parity, tag, hint_ns);
+  };
   const uint32_t w_smem = sbase + L.w;
   const uint32_t a_smem = sbase + L.a;
   const uint32_t aux_smem = sbase + L.aux;
@@ -171,18 +193,13 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
   if (warp == 0) {
     // ============================================================ TMA producer (one elected lane)
     if (elect_one()) {
-      const uint32_t wbar = smem_u32(&misc->w_full);
-      mbar_arrive_expect_tx(wbar, p.n_wchunks * kWChunkBytes);
-      for (int c = 0; c < p.n_wchunks; ++c)
-        bulk_load_1d(w_smem + c * kWChunkBytes,
-                     reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)c * kWChunkBytes, kWChunkBytes,
-                     wbar);
+      if (!p.w_stable) load_weights();
       Ring ar(s_a), ior(n_io);
       uint32_t loads = 0;
       int it = 0;
       for (TileIter c(p, t_begin, t_end); c.valid(); c.next(), ++it) {
         for (int r = c.first() ? c.y - 1 : c.y + 1; r <= c.y + 1; ++r, ++loads, ar.advance()) {
-          mbar_wait(smem_u32(&misc->a_empty[ar.slot]), ar.phase ^ 1, 1);
+          pwait(smem_u32(&misc->a_empty[ar.slot]), ar.phase ^ 1, 1);
           const uint32_t fb = smem_u32(&misc->a_full[ar.slot]);
           if ((p.debug_skip & 1) && loads >= (uint32_t)s_a) {
             mbar_arrive(fb);
@@ -193,13 +210,13 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
         }
         if (p.aux_k16 > 0) {
           const uint32_t s = it & 1, ph = (it >> 1) & 1;
-          mbar_wait(smem_u32(&misc->aux_empty[s]), ph ^ 1, 2);
+          pwait(smem_u32(&misc->aux_empty[s]), ph ^ 1, 2);
           const uint32_t fb = smem_u32(&misc->aux_full[s]);
           mbar_arrive_expect_tx(fb, kTileBytes);
           tma_load_4d(aux_smem + s * kTileBytes, &p.tm_aux, fb, 0, c.x0(), c.y, c.n);
         }
         if (p.has_id) {
-          mbar_wait(smem_u32(&misc->io_empty[ior.slot]), ior.phase ^ 1, 3);
+          pwait(smem_u32(&misc->io_empty[ior.slot]), ior.phase ^ 1, 3);
           const uint32_t fb = smem_u32(&misc->id_full[ior.slot]);
           mbar_arrive_expect_tx(fb, kTileBytes);
           tma_load_4d(io_smem + ior.slot * kTileBytes, &p.tm_id, fb, 0, c.x0(), c.y, c.n);
@@ -373,7 +390,7 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
           r1 = __ldg(lp + p.lq_sc);
           r2 = __ldg(lp + 2 * p.lq_sc);
         }
-        mbar_wait(smem_u32(&misc->acc_full[b]), (it >> 1) & 1, 9);
+        ewait(smem_u32(&misc->acc_full[b]), (it >> 1) & 1, 9);
         tc_fence_after();
         float v[16];
         if (half == 0) {
@@ -413,11 +430,11 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
       }
       if (it >= 2) rel.advance();
       if (p.has_id) {
-        mbar_wait(smem_u32(&misc->id_full[s_io]), ior.phase, 8);
+        ewait(smem_u32(&misc->id_full[s_io]), ior.phase, 8);
       } else {
         named_bar_sync(1, 256);             // n_io == 2: tile it-2's store has drained this slot
       }
-      mbar_wait(smem_u32(&misc->acc_full[b]), (it >> 1) & 1, 9);
+      ewait(smem_u32(&misc->acc_full[b]), (it >> 1) & 1, 9);
       tc_fence_after();
       if (tr) p.trace[it * 8 + 3] = clock64();
       uint8_t* rowp = sgen + L.io + s_io * kTileBytes + row * 128;

@@ -46,6 +46,7 @@ struct ConvParams {
   int act;
   int mode;
   int flip_y;           // row-stacked kernel: walk the image bottom-up (weights packed with ky mirrored)
+  int w_stable;         // weights may be fetched before the previous kernel in the stream has completed
   int s_a;              // A ring slots
   int n_io;             // id/out staging slots
   long long* trace;      // optional device buffer for per-tile clock64 stamps of CTA 0 (diagnostics)

@@ -15,6 +15,8 @@
 // partition-modulated 1x1 convs are one extra N=192 MMA group on the centre row into a dedicated
 // 192-column TMEM region; the epilogue folds sum_k par_k * conv1x1_k(x) into registers one step
 // ahead of the 3x3 result (accumulator ring shrinks to 5 x 64 columns to make room).
+#include <type_traits>
+
 #include "pnp_conv.cuh"
 #include "pnp_ptx.cuh"
 
@@ -49,13 +51,12 @@ struct RowsMisc {
   uint64_t step_done[kStepRing];   // tcgen05.commit after every step (one source row)
   uint64_t acc_free[kAccRingMax];  // epilogue -> MMA: accumulator slot drained
   uint64_t par_done;               // MMA -> epilogue: partition 1x1 accumulators of a row are ready
-  uint64_t par_free;               // epilogue -> MMA: ... and have been read
   uint64_t aux_full[2];
   uint64_t id_full[kMaxIoSlots];
   uint64_t io_empty[kMaxIoSlots];
   uint32_t tmem_base;
   uint32_t go_step;                // scout -> MMA: steps whose barriers have all completed
-  uint32_t go_par;                 // scout -> MMA: rows whose partition accumulators may be overwritten
+  uint32_t go_par;                 // epilogue -> MMA: epilogue-warp reads of the partition region (8 per row)
 };
 static_assert(sizeof(RowsMisc) <= 1024, "misc region overflow");
 
@@ -152,7 +153,6 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       for (int i = 0; i < kStepRing; ++i) mbar_init(smem_u32(&misc->step_done[i]), 1);
       for (int i = 0; i < kAccRingMax; ++i) mbar_init(smem_u32(&misc->acc_free[i]), kEpilogueWarps);
       mbar_init(smem_u32(&misc->par_done), 1);
-      mbar_init(smem_u32(&misc->par_free), kEpilogueWarps);
       for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&misc->aux_full[i]), 1);
       for (int i = 0; i < kMaxIoSlots; ++i) {
         mbar_init(smem_u32(&misc->id_full[i]), 1);
@@ -175,7 +175,36 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
   // the tail of the previous kernel in the stream; nothing below touches global memory before the
   // previous kernel has completed (packed weights may have been written by the kernel just before).
   griddep_launch_dependents();
+  const uint32_t w_smem_early = sbase + L.w;
+  auto load_weights = [&]() {                 // one elected lane of warp 0
+    const uint32_t wbar = smem_u32(&misc->w_full);
+    mbar_arrive_expect_tx(wbar, w_bytes);
+    for (int off = 0; off < w_bytes; off += kWChunkBytes) {
+      const int n = min(kWChunkBytes, w_bytes - off);
+      bulk_load_1d(w_smem_early + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, n, wbar);
+    }
+  };
+  // stable weights (packed long before this launch) are fetched while the previous kernel drains
+  if (p.w_stable && warp == 0) {
+    if (elect_one()) load_weights();
+    __syncwarp();
+  }
   griddep_wait();
+  if (p.trace != nullptr && threadIdx.x == 0) {            // per-CTA body start (cycles, ns): stored, not kept live
+    p.trace[2048 + blockIdx.x] = -clock64();
+    p.trace[2208 + blockIdx.x] = (long long)globaltimer_ns();
+  }
+  // Threads that merely wait for work poll patiently (one lane per warp, hardware suspend hint): hot
+  // try_wait loops of 256 epilogue lanes compete with the MMA operand fetch for the shared-memory pipe
+  // (measured: N=192 MMAs ~25 % slower).  debug bit 32 selects patient polling, bit 64 shortens the hint.
+  const bool hot_waits = (p.debug_skip & 32) == 0;
+  const uint32_t hint_ns = (p.debug_skip & 64) ? 40u : 200u;
+  auto pwait = [&](uint32_t bar, uint32_t parity, int tag) {      // one elected lane
+    if (hot_waits) mbar_wait(bar, parity, tag); else mbar_wait_patient(bar, parity, tag, hint_ns);
+  };
+  auto ewait = [&](uint32_t bar, uint32_t parity, int tag) {      // whole (converged) warp
+    if (hot_waits) mbar_wait(bar, parity, tag); else mbar_wait_warp(bar, parity, tag, hint_ns);
+  };
   const uint32_t w_smem = sbase + L.w;
   const uint32_t a_smem = sbase + L.a;
   const uint32_t aux_smem = sbase + L.aux;
@@ -184,12 +213,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
   if (warp == 0) {
     // ============================================================ TMA producer (one elected lane)
     if (elect_one()) {
-      const uint32_t wbar = smem_u32(&misc->w_full);
-      mbar_arrive_expect_tx(wbar, w_bytes);
-      for (int off = 0; off < w_bytes; off += kWChunkBytes) {
-        const int n = min(kWChunkBytes, w_bytes - off);
-        bulk_load_1d(w_smem + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, n, wbar);
-      }
+      if (!p.w_stable) load_weights();
       Ring ar(s_a);
       uint32_t sc = 0, ord = 0;            // step counter, output-row ordinal
       uint32_t aux_step[2] = {0, 0};       // step in which each aux slot was last consumed
@@ -199,7 +223,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         for (int j = s.j_first; j <= s.j_last; ++j, ++sc, ar.advance()) {
           if (sc >= (uint32_t)s_a) {       // slot last used by step sc - s_a
             const uint32_t ps = sc - s_a;
-            mbar_wait(smem_u32(&misc->step_done[ps & (kStepRing - 1)]), (ps >> 3) & 1, 1);
+            pwait(smem_u32(&misc->step_done[ps & (kStepRing - 1)]), (ps >> 3) & 1, 1);
           }
           const uint32_t fb = smem_u32(&misc->a_full[ar.slot]);
           if ((p.debug_skip & 1) && sc >= (uint32_t)s_a) {
@@ -213,7 +237,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
               const uint32_t as = ord & 1;
               if (ord >= 2) {
                 const uint32_t ps = aux_step[as];
-                mbar_wait(smem_u32(&misc->step_done[ps & (kStepRing - 1)]), (ps >> 3) & 1, 2);
+                pwait(smem_u32(&misc->step_done[ps & (kStepRing - 1)]), (ps >> 3) & 1, 2);
               }
               aux_step[as] = sc;           // consumed in this very step (centre row)
               const uint32_t ab = smem_u32(&misc->aux_full[as]);
@@ -281,18 +305,31 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       bool pend = false;
       uint32_t pend_bar = 0;
 
-      // MMAs of one (dx,k) over `cnt` consecutive accumulator slots starting at slot_lo (wraps)
-      auto mma_range = [&](uint32_t slot_lo, int cnt, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
-        const int n1 = min(cnt, kAccRing - (int)slot_lo);
-        umma_bf16_lo(tmem_base + slot_lo * tap_n, a_lo, kDescHiSw128, b_lo, kDescHiSw128, idesc0 + n1 * idesc_step, acc);
-        if (cnt > n1)
-          umma_bf16_lo(tmem_base, a_lo, kDescHiSw128, b_lo + n1 * sbb, kDescHiSw128, idesc0 + (cnt - n1) * idesc_step, acc);
+      // MMAs of one (dx,k) over `cnt` consecutive accumulator slots starting at slot_lo.  kWrap: the
+      // range may run over the end of the ring and is issued as two MMAs.  The two cases are separate
+      // straight-line bodies selected by ONE branch per step: a predicated-off tcgen05.mma is not free
+      // (measured: steps with 12 squashed second halves took ~1790 cycles, steps whose ranges really
+      // wrap -- 24 executed MMAs -- only ~1570).
+      auto mma_range = [&](auto wrap_tag, uint32_t slot_lo, int cnt, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+        constexpr bool kWrap = decltype(wrap_tag)::value;
+        if constexpr (!kWrap) {
+          umma_bf16_lo(tmem_base + slot_lo * tap_n, a_lo, kDescHiSw128, b_lo, kDescHiSw128, idesc0 + cnt * idesc_step, acc);
+        } else {
+          const int n1 = min(cnt, kAccRing - (int)slot_lo);
+          umma_bf16_lo(tmem_base + slot_lo * tap_n, a_lo, kDescHiSw128, b_lo, kDescHiSw128, idesc0 + n1 * idesc_step, acc);
+          if (cnt > n1)
+            umma_bf16_lo(tmem_base, a_lo, kDescHiSw128, b_lo + n1 * sbb, kDescHiSw128, idesc0 + (cnt - n1) * idesc_step, acc);
+        }
       };
 
-      if (cur.valid) spin_until_ge(go_step, 1, 5);
+      // last value read from go_step: the scout usually runs several steps ahead (A ring depth, free
+      // accumulator slots), so most steps need no shared-memory poll and no fence at all
+      uint32_t go_seen = 0;
+      const bool dbg_nopoll = (p.debug_skip & 8) != 0, dbg_nofence = (p.debug_skip & 16) != 0;
+      if (cur.valid) go_seen = spin_until_ge_v(go_step, 1, 5);
       tc_fence_after();
       while (cur.valid) {
-        const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && cur.sc < 64;
+        const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && cur.sc < 64 && !(p.debug_skip & 128);
         if (tr) p.trace[cur.sc * 8 + 0] = clock64();
         int lo, cnt, old_cnt;
         ranges(cur, lo, cnt, old_cnt);
@@ -305,35 +342,44 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         const uint32_t cur_od = cur.ord0 + (uint32_t)max(cur.j, 0);
         StepCtx nxt = cur;
         advance(nxt);
+        auto step_body = [&](auto wrap_tag) {
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          if (tr && dx == 1) p.trace[cur_sc * 8 + 6] = clock64();
-          if (dx == 2) {
-            // barriers of the NEXT step, checked while ~8 MMAs of this step are still queued
-            if (tr) p.trace[cur_sc * 8 + 7] = clock64();
-            if (nxt.valid) spin_until_ge(go_step, nxt.sc + 1, 5);   // normally long satisfied
-            tc_fence_after();
-            if (tr) p.trace[cur_sc * 8 + 2] = clock64();   // (slot 2 is otherwise the epilogue's)
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t a_lo = a_row + dx * 8 + 2 * k;
-            const uint32_t b_lo = b_row + dx * dxb + 2 * k;
-            if (dx == 0 && k == 0) {
-              // first MMA of the step: rows touched before accumulate, new rows are overwritten
-              if (old_cnt > 0) mma_range(slot_lo, old_cnt, a_lo, b_lo, 1);
-              if (new_cnt > 0)
-                mma_range((slot_lo + old_cnt) % kAccRing, new_cnt, a_lo, b_lo + old_cnt * sbb, 0);
-              if (pend) {
-                // the previous step's commit rides behind this step's first MMA
-                umma_commit(pend_bar);
-                pend = false;
+          for (int dx = 0; dx < 3; ++dx) {
+            if (tr && dx == 1) p.trace[cur_sc * 8 + 6] = clock64();
+            if (dx == 2) {
+              // barriers of the NEXT step, checked while ~8 MMAs of this step are still queued
+              if (tr) p.trace[cur_sc * 8 + 7] = clock64();
+              if (nxt.valid && go_seen < nxt.sc + 1 && !dbg_nopoll) {
+                go_seen = spin_until_ge_v(go_step, nxt.sc + 1, 5);
+                if (!dbg_nofence) tc_fence_after();
               }
-            } else {
-              mma_range(slot_lo, cnt, a_lo, b_lo, 1);
+              if (tr) p.trace[cur_sc * 8 + 2] = clock64();   // (slot 2 is otherwise the epilogue's)
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t a_lo = a_row + dx * 8 + 2 * k;
+              const uint32_t b_lo = b_row + dx * dxb + 2 * k;
+              if (dx == 0 && k == 0) {
+                // first MMA of the step: rows touched before accumulate, new rows are overwritten
+                if (old_cnt > 0) mma_range(wrap_tag, slot_lo, old_cnt, a_lo, b_lo, 1);
+                if (new_cnt > 0)
+                  mma_range(wrap_tag, (slot_lo + old_cnt) % kAccRing, new_cnt, a_lo, b_lo + old_cnt * sbb, 0);
+                if (pend) {
+                  // the previous step's commit rides behind this step's first MMA
+                  umma_commit(pend_bar);
+                  pend = false;
+                }
+              } else {
+                mma_range(wrap_tag, slot_lo, cnt, a_lo, b_lo, 1);
+              }
+              if (tr) p.trace[1024 + cur_sc * 16 + dx * 4 + k] = clock64();
             }
           }
-        }
+        };
+        if (slot_lo + (uint32_t)cnt > (uint32_t)kAccRing)
+          step_body(std::true_type{});
+        else
+          step_body(std::false_type{});
         if (p.aux_k16 > 0 && centre) {
           const uint32_t a_lo = umma_desc_lo(aux_smem + (cur_od & 1) * kTileBytes);
           for (int k = 0; k < p.aux_k16; ++k)
@@ -344,7 +390,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
           // Partition 1x1 convs of this row: centre pixel column (dx index 1), N = 192, own TMEM
           // region.  Issued LAST in the step: the epilogue then has a whole step to read the region
           // before the next row needs it (issued first, the hand-back sat on the critical path).
-          spin_until_ge(go_par, cur_od + 1, 10);
+          spin_until_ge(go_par, kEpilogueWarps * cur_od, 10);   // every epilogue warp has read row cur_od-1's region
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -365,7 +411,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
     // mbarrier wait the MMAs depend on (an already-complete try_wait costs 220-290 cycles in this
     // kernel) and publishes plain progress counters the MMA thread can poll in ~30 cycles.
     if (elect_one()) {
-      const uint32_t go_step = smem_u32(&misc->go_step), go_par = smem_u32(&misc->go_par);
+      const uint32_t go_step = smem_u32(&misc->go_step);
       Ring ar(s_a);
       uint32_t sc = 0, ord0 = 0;
       for (SegIter it(p, t_begin, t_end); it.valid();) {
@@ -384,11 +430,6 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
             mbar_wait(smem_u32(&misc->aux_full[od & 1]), (od >> 1) & 1, 7);
           }
           st_release_shared(go_step, sc + 1);
-          if (kPar && centre) {                                    // previous row's 1x1 results read
-            const uint32_t od = ord0 + j;
-            if (od >= 1) mbar_wait(smem_u32(&misc->par_free), (od - 1) & 1, 10);
-            st_release_shared(go_par, od + 1);
-          }
         }
         ord0 += s.len;
         it.next(s);
@@ -404,6 +445,8 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     // non-partition variants keep the per-channel constants of this warp's 32 channels in registers;
     // the partition variant needs those registers for the 1x1 blend and re-reads them as float4
+    // non-partition variants keep the per-channel constants of this warp's 32 channels in registers;
+    // the partition variant is short of registers (1x1 blend) and re-reads them as float4
     float bias_r[kPar ? 1 : 32], scale_r[(kScale && !kPar) ? 32 : 1];
     if (!kPar) {
 #pragma unroll
@@ -434,21 +477,11 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       if (c.valid) c.s = c.it.get();
     };
 
-    // sum_k par_k * conv1x1_k(x) for the row at `c`: read the 3 x 32 columns of this warp's channel
-    // half from the partition accumulators, blend with the pixel's partition values, free the region
-    float dy_cur[kPar ? 32 : 1], dy_nxt[kPar ? 32 : 1];
-    auto par_part = [&](const TileCur& c, float* dy) {
-      const int x = c.s.strip * kTilePx + row;
-      const int y = PNP_Y(c.s.y_b + c.o);
-      float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-      if (x < p.W) {
-        const float* pp = p.par + (long long)c.s.n * p.par_sn + (long long)y * p.par_sy + x;
-        p0 = __ldg(pp);
-        p1 = __ldg(pp + p.par_sc);
-        p2 = __ldg(pp + 2 * p.par_sc);
-      }
-      mbar_wait(smem_u32(&misc->par_done), c.ord & 1, 11);
-      tc_fence_after();
+    // sum_k par_k * conv1x1_k(x) of a row: read the 3 x 32 columns of this warp's channel half from the
+    // partition accumulators, blend with the pixel's partition values and park the result (bf16) in the
+    // row's output staging slot -- in exactly the bytes this thread overwrites with the final value one
+    // row later, so no register state is carried from row to row and no other thread is involved.
+    auto blend_store = [&](uint8_t* slot_row, float q0, float q1, float q2) {
 #pragma unroll
       for (int gg = 0; gg < 2; ++gg) {
         float a1[16], a2[16], a3[16];
@@ -457,13 +490,44 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         tmem_ld16(lane_base + col + 64, a2);
         tmem_ld16(lane_base + col + 128, a3);
         tmem_ld_wait();
+        uint32_t w[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dy[gg * 16 + j] = fmaf(p2, a3[j], fmaf(p1, a2[j], p0 * a1[j]));
+        for (int j = 0; j < 8; ++j)
+          w[j] = pack_bf16x2(fmaf(q2, a3[2 * j], fmaf(q1, a2[2 * j], q0 * a1[2 * j])),
+                             fmaf(q2, a3[2 * j + 1], fmaf(q1, a2[2 * j + 1], q0 * a1[2 * j + 1])));
+        const int g = half * 2 + gg;
+        *reinterpret_cast<uint4*>(slot_row + (((2 * g) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(slot_row + (((2 * g + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
       }
-      tc_fence_before();
-      warp_arrive(smem_u32(&misc->par_free));
     };
-    if (kPar && cur.valid) par_part(cur, dy_cur);
+    auto par_load = [&](const TileCur& c, float& q0, float& q1, float& q2) {
+      const int x = c.s.strip * kTilePx + row;
+      q0 = q1 = q2 = 0.f;
+      if (x < p.W) {
+        const float* pp = p.par + (long long)c.s.n * p.par_sn + (long long)PNP_Y(c.s.y_b + c.o) * p.par_sy + x;
+        q0 = __ldg(pp);
+        q1 = __ldg(pp + p.par_sc);
+        q2 = __ldg(pp + 2 * p.par_sc);
+      }
+    };
+    // partition values are fetched TWO rows ahead: the epilogue is the hand-back path of the single 1x1
+    // accumulator region, so a global-load latency per row (measured: 1300-2400 cycles of "math") would
+    // bound the whole pipeline.  pn* = values of the row after `cur`, loaded one iteration earlier.
+    float pn0 = 0.f, pn1 = 0.f, pn2 = 0.f;
+    if (kPar && cur.valid) {                 // first row of this CTA: staging slot 0 is free
+      float q0, q1, q2;
+      par_load(cur, q0, q1, q2);
+      {
+        TileCur n1 = cur;
+        tile_next(n1);
+        if (n1.valid) par_load(n1, pn0, pn1, pn2);
+      }
+      ewait(smem_u32(&misc->par_done), cur.ord & 1, 11);
+      tc_fence_after();
+      blend_store(sgen + L.io + row * 128, q0, q1, q2);
+      tc_fence_before();
+      warp_flag_add(smem_u32(&misc->go_par));
+    }
 
     // Identity tiles are fetched by the epilogue's own store lane: it is the one who knows when a
     // staging slot has been drained (wait_group.read), so the TMA producer never blocks on them and
@@ -507,7 +571,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
           r1 = __ldg(lp + p.lq_sc);
           r2 = __ldg(lp + 2 * p.lq_sc);
         }
-        mbar_wait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> 3) & 1, 9);
+        ewait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> 3) & 1, 9);
         tc_fence_after();
         float v[16];
         if (half == 0) {
@@ -525,22 +589,15 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         cur = nxt;
         continue;
       }
-      const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && ord < 64 && threadIdx.x == 64;
+      const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && ord < 64 && threadIdx.x == 64 && !(p.debug_skip & 128);
       // Partition path: the 1x1 accumulators of the NEXT row finish with the same step that completes
       // this row's 3x3 result (they are issued last in that step), so both are fetched from TMEM in
-      // one batch behind one barrier wait; the blend of the next row is kept in registers (dy_nxt).
-      float pn0 = 0.f, pn1 = 0.f, pn2 = 0.f;
-      uint32_t sc_wait = sc_last;
+      // one batch behind one barrier wait; the blend of the next row is parked in its staging slot.
+      float pf0 = 0.f, pf1 = 0.f, pf2 = 0.f;   // partition values of the row after next
       if (kPar && nxt.valid) {
-        const int xn = nxt.s.strip * kTilePx + row;
-        if (xn < p.W) {
-          const float* pp = p.par + (long long)nxt.s.n * p.par_sn + (long long)PNP_Y(nxt.s.y_b + nxt.o) * p.par_sy + xn;
-          pn0 = __ldg(pp);
-          pn1 = __ldg(pp + p.par_sc);
-          pn2 = __ldg(pp + 2 * p.par_sc);
-        }
-        const uint32_t sc_centre_next = nxt.sc0 + (uint32_t)(nxt.o - nxt.s.j_first);
-        sc_wait = max(sc_last, sc_centre_next);          // differs only across strip segments
+        TileCur n2 = nxt;
+        tile_next(n2);
+        if (n2.valid) par_load(n2, pf0, pf1, pf2);
       }
       const uint32_t s_io = ior.slot;
       if (store_warp) {
@@ -555,11 +612,18 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         __syncwarp();
       }
       if (p.has_id) {
-        mbar_wait(smem_u32(&misc->id_full[s_io]), ior.phase, 8);
+        ewait(smem_u32(&misc->id_full[s_io]), ior.phase, 8);
       } else {
         named_bar_sync(1, 256);
       }
-      mbar_wait(smem_u32(&misc->step_done[sc_wait & (kStepRing - 1)]), (sc_wait >> 3) & 1, 9);
+      if (kPar && nxt.valid) {
+        // par_done of the next row is committed right behind its four 1x1 MMAs, which are the LAST MMAs of
+        // the step that also completes this row's 3x3 result (a commit covers everything issued before
+        // it), whereas that step's own step_done commit is deferred into the following step
+        ewait(smem_u32(&misc->par_done), (ord + 1) & 1, 11);
+      } else {
+        ewait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> 3) & 1, 9);
+      }
       tc_fence_after();
       if (tr) p.trace[ord * 8 + 3] = clock64();
       uint8_t* rowp = sgen + L.io + s_io * kTileBytes + row * 128;
@@ -567,27 +631,21 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       if (p.debug_skip & 4) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      } else if (kPar && nxt.valid) {
-#pragma unroll
-        for (int gg = 0; gg < 2; ++gg) {
-          float a1[16], a2[16], a3[16];
-          const uint32_t col = kParCol + half * 32 + gg * 16;
-          tmem_ld16(taddr + half * 32 + gg * 16, v + gg * 16);
-          tmem_ld16(lane_base + col, a1);
-          tmem_ld16(lane_base + col + 64, a2);
-          tmem_ld16(lane_base + col + 128, a3);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) dy_nxt[gg * 16 + j] = fmaf(pn2, a3[j], fmaf(pn1, a2[j], pn0 * a1[j]));
-        }
       } else {
         tmem_ld16(taddr + half * 32, v);
         tmem_ld16(taddr + half * 32 + 16, v + 16);
-        tmem_ld_wait();
+        if (kPar && nxt.valid) {
+          // the NEXT row's 1x1 results (complete with the same step): blend into the next staging slot,
+          // which the store of row ord-2 has drained (wait_group.read<1> + named barrier 1 above, n_io >= 3)
+          const uint32_t s_nx = (s_io + 1 == (uint32_t)n_io) ? 0u : s_io + 1;
+          blend_store(sgen + L.io + s_nx * kTileBytes + row * 128, pn0, pn1, pn2);
+        } else {
+          tmem_ld_wait();
+        }
       }
       tc_fence_before();
       warp_arrive(smem_u32(&misc->acc_free[slot]));   // accumulator is in registers: slot reusable
-      if (kPar && nxt.valid) warp_arrive(smem_u32(&misc->par_free));   // ... and so is the 1x1 region
+      if (kPar && nxt.valid) warp_flag_add(smem_u32(&misc->go_par));   // ... and so is the 1x1 region
 #pragma unroll
       for (int gg = 0; gg < 2; ++gg) {
         const int g = half * 2 + gg;
@@ -599,19 +657,19 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 sc = kScale ? sc4[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
             const float4 bi = bi4[j4];
-            vv[4 * j4 + 0] = fmaf(vv[4 * j4 + 0], sc.x, bi.x) + dy_cur[gg * 16 + 4 * j4 + 0];
-            vv[4 * j4 + 1] = fmaf(vv[4 * j4 + 1], sc.y, bi.y) + dy_cur[gg * 16 + 4 * j4 + 1];
-            vv[4 * j4 + 2] = fmaf(vv[4 * j4 + 2], sc.z, bi.z) + dy_cur[gg * 16 + 4 * j4 + 2];
-            vv[4 * j4 + 3] = fmaf(vv[4 * j4 + 3], sc.w, bi.w) + dy_cur[gg * 16 + 4 * j4 + 3];
+            vv[4 * j4 + 0] = fmaf(vv[4 * j4 + 0], sc.x, bi.x);
+            vv[4 * j4 + 1] = fmaf(vv[4 * j4 + 1], sc.y, bi.y);
+            vv[4 * j4 + 2] = fmaf(vv[4 * j4 + 2], sc.z, bi.z);
+            vv[4 * j4 + 3] = fmaf(vv[4 * j4 + 3], sc.w, bi.w);
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            vv[j] = (kScale && !kPar) ? fmaf(vv[j], scale_r[gg * 16 + j], bias_r[gg * 16 + j]) : vv[j] + bias_r[gg * 16 + j];
+            vv[j] = kScale ? fmaf(vv[j], scale_r[gg * 16 + j], bias_r[gg * 16 + j]) : vv[j] + bias_r[gg * 16 + j];
         }
         uint4* c0 = reinterpret_cast<uint4*>(rowp + (((2 * g) ^ sw) << 4));
         uint4* c1 = reinterpret_cast<uint4*>(rowp + (((2 * g + 1) ^ sw) << 4));
-        if (p.has_id) {
+        if (p.has_id || kPar) {              // identity tile (TMA) or this row's parked 1x1 blend
           const uint4 i0 = *c0, i1 = *c1;
           const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
 #pragma unroll
@@ -651,8 +709,9 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       }
       ior.advance();
       if (kPar) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dy_cur[j] = dy_nxt[j];
+        pn0 = pf0;
+        pn1 = pf1;
+        pn2 = pf2;
       }
       cur = nxt;
     }
@@ -664,6 +723,10 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (p.trace != nullptr && threadIdx.x == 0) {            // per-CTA body cycles, start and end time (ns)
+    p.trace[2048 + blockIdx.x] += clock64();
+    p.trace[2368 + blockIdx.x] = (long long)globaltimer_ns();
+  }
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);

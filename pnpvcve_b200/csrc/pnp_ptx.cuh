@@ -66,24 +66,26 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar) {
 // (profiles/r01_notes.md): with all 256 epilogue lanes spinning on try_wait, an already-complete
 // mbarrier wait of the MMA-issuing thread took ~375 cycles instead of ~125 and the N=192 MMAs
 // themselves ran ~25 % slower -- mbarrier polling competes for the shared-memory pipe.
-__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int tag = 0) {
-  if ((threadIdx.x & 31) == 0) {
-    uint32_t spins = 0, ok = 0;
-    do {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(ok)
-          : "r"(bar), "r"(parity), "r"(200u)      // suspend-time hint in ns
-          : "memory");
-      if (!ok && ++spins > (PNP_SPIN_LIMIT >> 4)) {
-        printf("pnp: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag,
-               (int)blockIdx.x, (int)threadIdx.x, parity);
-        __trap();
-      }
-    } while (!ok);
-  }
+// single-thread form (the caller is one elected lane, or wants every lane to poll patiently)
+__device__ __forceinline__ void mbar_wait_patient(uint32_t bar, uint32_t parity, int tag = 0, uint32_t hint_ns = 200u) {
+  uint32_t spins = 0, ok = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)      // suspend-time hint in ns
+        : "memory");
+    if (!ok && ++spins > (PNP_SPIN_LIMIT >> 4)) {
+      printf("pnp: mbarrier wait timed out (tag %d, block %d, thread %d, parity %u)\n", tag,
+             (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int tag = 0, uint32_t hint_ns = 200u) {
+  if ((threadIdx.x & 31) == 0) mbar_wait_patient(bar, parity, tag, hint_ns);
   __syncwarp();
 }
 
@@ -295,6 +297,18 @@ __device__ __forceinline__ void spin_until_ge(uint32_t addr, uint32_t target, in
       __trap();
     }
   }
+}
+
+// same, returning the value that satisfied the wait (callers cache it and skip later polls)
+__device__ __forceinline__ uint32_t spin_until_ge_v(uint32_t addr, uint32_t target, int tag) {
+  uint32_t spins = 0, v;
+  while ((v = ld_acquire_shared(addr)) < target) {
+    if (++spins > PNP_SPIN_LIMIT) {
+      printf("pnp: flag wait timed out (tag %d, block %d, target %u)\n", tag, (int)blockIdx.x, target);
+      __trap();
+    }
+  }
+  return v;
 }
 
 // ------------------------------------------------------------------ thread-block clusters / DSMEM

@@ -64,6 +64,7 @@ class _Launcher:
         self.desc = ops.ConvDesc()
         self.ref = ctypes.byref(self.desc)
         self.prof = prof          # None or {label: [(start_event, end_event), ...]}
+        self.rows_par = False     # block launch A on the row-stacked kernel (weights packed accordingly)
         self.prof_every = max(int(prof_every), 1)
         self.seen = {}
 
@@ -71,8 +72,11 @@ class _Launcher:
                  par=None, act=PNP_ACT_NONE, lq=None, outf=None, label=None, flip_y=False):
         # row-stacked weight layout (one source row feeds three output rows, N=192 MMAs) for every
         # conv except the partition-modulated block launch A
+        # wpack_stable: every pack kernel of the call ran before the frame loop started (the launch
+        # right before a conv is always lr_im2col, the warp or another conv)
         ops.fill_conv_desc(self.desc, src, wpack, out, aux, idt, scale, bias, par, act, lq, outf,
-                           wlayout=0 if par is not None else 1, flip_y=flip_y)
+                           wlayout=0 if (par is not None and not self.rows_par) else 1, flip_y=flip_y,
+                           wpack_stable=True)
         timed = self.prof is not None and label in self.prof
         if timed:                                  # bracket every prof_every-th launch of this label
             k = self.seen.get(label, 0)
@@ -140,6 +144,8 @@ class BaeEngine:
         #: run each BAE block as ONE launch of the CTA-pair kernel (pnp_resblock: the intermediate activation
         #: stays on chip) instead of launch A + launch B of pnp_conv3x3
         self.fused_block = os.environ.get("PNP_FUSED_BLOCK", "0") != "0"
+        #: block launch A (3x3 + three partition 1x1s) on the row-stacked kernel instead of the tap-major one
+        self.rows_par = os.environ.get("PNP_ROWS_PAR", "0") != "0"
 
     # ------------------------------------------------------------------ weights
     def _param_key(self):
@@ -220,7 +226,7 @@ class BaeEngine:
         its QP, so the packed kernels gamma_o * sum_e a_e W_e are cached per distinct (CRF, QP)
         pair -- 3 pairs per clip in the IPB configs, at most ~15 in the CRF config.
         """
-        key = (key, self.fused_block)
+        key = (key, self.fused_block, self.rows_par)
         hit = self.mix_cache.get(key)
         if hit is not None:
             return hit
@@ -228,8 +234,8 @@ class BaeEngine:
         for name in ("bwd", "fwd"):
             lst = []
             for k in range(st["nb"]):
-                if self.fused_block:
-                    # stage-1 pack of pnp_resblock: row-stacked mix + the three 1x1 convs stacked behind it
+                if self.fused_block or self.rows_par:
+                    # stage-1 pack of pnp_resblock / row-stacked launch A: row-stacked mix + the three 1x1 convs stacked behind it
                     buf = ops.new_wpack_rowstack(dev, with_par=True)
                     ops.pack_conv3x3_rowstack(st[name + "_conv2_w"][k], buf, coef=coef_row, row_scale=gamma_row)
                     for j, w1 in enumerate(st[name + "_1x1"][k]):
@@ -345,6 +351,7 @@ class BaeEngine:
             buf = {k: (v[:nn] if isinstance(v, torch.Tensor) else v) for k, v in bufs["lanes"][lane].items()}
             conv = buf["launcher"]
             conv.prof, conv.prof_every, conv.seen = prof, self.prof_every, seen
+            conv.rows_par = self.rows_par
             stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
             def warp(src, flow, dst):
@@ -384,10 +391,18 @@ class BaeEngine:
                     x, other = o, x
                 counts[lane] += 2 * nb
 
+            def phase(name):
+                """prof["phases"]: one event per phase boundary of a frame step (4 per frame, negligible)"""
+                if prof is not None and "phases" in prof:
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record()
+                    prof["phases"].append((name, ev))
+
             bwd_key, fwd_key = key_schedule(key_rows[b])
             # ---------------- backward-time propagation (iconvsr_ipb_par.py:67-100)
             for i in range(t - 1, -1, -1):
                 mixed = mixed_of[(float(crf_host[b, i]), float(qp_host[b, i]))]
+                phase("bwd_start")
                 ops.lr_im2col(lrs[b0:b1, i], buf["lr64"])
                 counts[lane] += 1
                 x0 = buf["xa"]
@@ -409,13 +424,16 @@ class BaeEngine:
                     conv(stream, buf["zero"], st["bwd_merged_aux"], out=x0, aux=buf["lr64"],
                          bias=st["bwd_in_bias"], act=PNP_ACT_LRELU, label="input")
                     counts[lane] += 1
+                phase("bwd_input_done")
                 stack("bwd", 0, i, x0, feats[i, b0:b1], mixed)
+                phase("bwd_stack_done")
                 yield
             if return_features:
                 bwd_feats[:, b0:b1].copy_(feats[:, b0:b1])
             # ---------------- forward-time propagation + reconstruction (:102-147)
             for i in range(t):
                 mixed = mixed_of[(float(crf_host[b, i]), float(qp_host[b, i]))]
+                phase("fwd_start")
                 ops.lr_im2col(lrs[b0:b1, i], buf["lr64"])
                 counts[lane] += 1
                 x0 = buf["xa"]
@@ -440,12 +458,15 @@ class BaeEngine:
                     conv(stream, cur, st["fwd_bf_aux"], out=x0, aux=buf["lr64"], bias=st["fwd_in_bias"],
                          act=PNP_ACT_LRELU, label="input")
                     counts[lane] += 1
+                phase("fwd_input_done")
                 stack("fwd", nb, i, x0, cur, mixed)
+                phase("fwd_stack_done")
                 # out = conv_last(lrelu(conv_hr(x))) + lq   (:144-146)
                 conv(stream, cur, st["hr_w"], out=buf["hr"], bias=st["hr_b"], act=PNP_ACT_LRELU, label="hr")
                 conv(stream, buf["hr"], st["last_w"], bias=st["last_b"], lq=lrs[b0:b1, i],
                      outf=out[b0:b1, i], label="last")
                 counts[lane] += 2
+                phase("fwd_head_done")
                 yield
 
         def lane_steps(lane):

@@ -164,7 +164,7 @@ def mix_bias(conv2_bias, experts, gamma):
 
 
 def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
-                   act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False):
+                   act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False, wpack_stable=False):
     """Fill a ConvDesc in place (reusable across launches)."""
     n, h, w, _ = src.shape
     last = outf is not None
@@ -193,11 +193,12 @@ def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias
     d.mode = PNP_CONV_LAST if last else PNP_CONV_BF16
     d.wlayout = wlayout
     d.flip_y = 1 if flip_y else 0
+    d.wpack_stable = 1 if wpack_stable else 0
     return d
 
 
 def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
-            act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False):
+            act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False, wpack_stable=False):
     """Fused tcgen05 3x3 conv (see include/pnp_vcve.h: pnp_conv3x3)."""
     _feat_check(src, "src")
     for t, nm in ((out, "out"), (aux, "aux"), (idt, "idt")):
@@ -211,7 +212,8 @@ def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par
             if t.dim() != 4 or t.shape[1] != 3 or t.shape[0] != src.shape[0] or \
                     tuple(t.shape[2:]) != tuple(src.shape[1:3]):
                 raise ValueError(f"conv3x3: {nm} must be (N,3,H,W) matching src")
-    d = fill_conv_desc(ConvDesc(), src, wpack, out, aux, idt, scale, bias, par, act, lq, outf, wlayout, flip_y)
+    d = fill_conv_desc(ConvDesc(), src, wpack, out, aux, idt, scale, bias, par, act, lq, outf, wlayout, flip_y,
+                       wpack_stable)
     need = rowstack_bytes(d.tap_n, aux is not None, par is not None) if wlayout == 1 \
         else d.n_wchunks * CHUNK_BYTES
     if wpack.numel() < need:

@@ -33,9 +33,11 @@ def nchw(x):
     return x.float().permute(0, 3, 1, 2).contiguous()
 
 
-def assert_bf16_close(got, ref, what):
-    """within one bf16 rounding step of the fp32 reference result"""
+def assert_bf16_close(got, ref, what, extra=None):
+    """within one bf16 rounding step of the fp32 reference result (+ an optional per-element allowance)"""
     tol = ref.abs() * 2.0 ** -7 + 2e-3
+    if extra is not None:
+        tol = tol + extra
     bad = (got - ref).abs() > tol
     assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.numel()} off, max {float((got - ref).abs().max())}"
 
@@ -165,11 +167,16 @@ def test_conv_variants_match_fp32_conv2d(dev, n, h, w, layout):
             ops.pack_rows(w1[j], wpp[9 * ops.CHUNK_BYTES:], 64 * j)
     ops.conv3x3(xs, wpp, out=out, scale=scale, bias=bias, par=par, act=ops.PNP_ACT_RELU, wlayout=layout)
     ref = ref0 * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    dyres = torch.zeros_like(ref0)
     for j in range(3):
-        ref = ref + F.conv2d(x, w1[j].view(64, 64, 1, 1)) * par[:, j:j + 1]
-    assert_bf16_close(nchw(out), F.relu(ref), "par")
+        dyres = dyres + F.conv2d(x, w1[j].view(64, 64, 1, 1)) * par[:, j:j + 1]
+    ref = ref + dyres
+    # the row-stacked kernel parks the 1x1 blend in bf16 before adding it: one more rounding of that addend
+    # (this test's partition values are O(1); the real maps are {0, 1/255}, where it is ~1e-5)
+    extra = dyres.abs() * 2.0 ** -8 if layout == 1 else None
+    assert_bf16_close(nchw(out), F.relu(ref), "par", extra)
     ops.conv3x3(xs, wpp, out=out, bias=bias, par=par, act=ops.PNP_ACT_NONE, wlayout=layout)
-    assert_bf16_close(nchw(out), ref - ref0 * scale.view(1, -1, 1, 1) + ref0, "par without scale")
+    assert_bf16_close(nchw(out), ref - ref0 * scale.view(1, -1, 1, 1) + ref0, "par without scale", extra)
 
     # reconstruction tail: 64 -> 3, + lq, fp32 NCHW output
     wl = bf(torch.randn((3, 64, 3, 3), generator=g, device=dev) * 0.05)
@@ -346,8 +353,10 @@ def test_resblock_pair_matches_fp32_reference(dev, n, h, w):
     o2 = ops.new_feature(n, h, w, dev)
     ops.conv3x3(xs, ws1, out=t2, bias=b1, par=par, act=ops.PNP_ACT_RELU, wlayout=1)
     ops.conv3x3(t2, ws2, out=o2, idt=xs, bias=b2, wlayout=1)
+    # (the row-stacked launch A parks the 1x1 blend in bf16 before adding it -- one more rounding of an
+    # addend that is O(1) with this test's partition values, ~1e-5 with the real {0, 1/255} maps)
     assert (nchw(o2) - got).abs().max().item() <= 0.05
-    assert (nchw(o2) - got).abs().mean().item() < 1e-3
+    assert (nchw(o2) - got).abs().mean().item() < 2e-3
 
 
 def test_resblock_pair_720p_identity_and_shift(dev):

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/pnp_vcve.h but not exported"
     assert sorted(_lib.EXPORTS) == syms
-    assert _lib.load().pnp_abi_version() == 5
+    assert _lib.load().pnp_abi_version() == 6
 
 
 def test_abi_argument_errors_without_gpu():

@@ -11,11 +11,13 @@ if LAYOUT == 0:
     wp9 = ops.new_wpack(9, dev); ops.pack_conv3x3(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp9)
 else:
     wp9 = ops.new_wpack_rowstack(dev); ops.pack_conv3x3_rowstack(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp9)
-trace = torch.zeros(2 * 64 * 8, dtype=torch.int64, device=dev)
+trace = torch.zeros(2 * 64 * 8 + 64 * 16 + 3 * 160, dtype=torch.int64, device=dev)
 for _ in range(3): ops.conv3x3(x, wp9, out=out, wlayout=LAYOUT)
 torch.cuda.synchronize()
 os.environ["PNP_TRACE_PTR"] = str(trace.data_ptr())
-PAR = len(sys.argv) > 2
+PAR = len(sys.argv) > 2 and sys.argv[2] == 'par'
+IDT = len(sys.argv) > 2 and sys.argv[2] == 'id'
+idt = torch.randn((1, h, w, 64), device=dev).to(torch.bfloat16)
 if PAR:
     if LAYOUT == 1:
         wp9 = ops.new_wpack_rowstack(dev, with_par=True); ops.pack_conv3x3_rowstack(torch.randn((64, 64, 3, 3), device=dev) * 0.05, wp9)
@@ -24,11 +26,16 @@ if PAR:
     par = torch.rand((1, 3, h, w), device=dev)
     bias = torch.randn(64, device=dev)
     ops.conv3x3(x, wp9, out=out, par=par, bias=bias, act=2, wlayout=LAYOUT)
+elif IDT:
+    ops.conv3x3(x, wp9, out=out, idt=idt, wlayout=LAYOUT)
 else:
     ops.conv3x3(x, wp9, out=out, wlayout=LAYOUT)
 torch.cuda.synchronize()
 t = trace[:512].view(64, 8).cpu()
-t2 = trace[512:].view(64, 8).cpu()
+t2 = trace[512:1024].view(64, 8).cpu()
+t3 = trace[1024:2048].view(64, 16).cpu()
+body = trace[2048:2048 + 148].cpu()
+g0 = trace[2208:2208 + 147].cpu(); g1 = trace[2368:2368 + 147].cpu()
 t0 = int(t[0, 0])
 print("tile  mma_ready  mma_issued | epi_start  acc_full   epi_math   epi_bar   (cycles since first MMA ready; deltas in brackets)")
 prev = None
@@ -44,3 +51,21 @@ for i in range(49):
     d = "" if prev is None else f"  [period {r[0]-prev[0]:5d}  issue {r[1]-r[0]:4d} (4 MMAs +{r[6]-r[0]:4d}, 20 MMAs +{r[7]-r[0]:4d})  gap {r[0]-prev[1]:4d}  accwait {r[3]-r[2]:5d}  math {r[4]-r[3]:4d}  bar {r[5]-r[4]:4d}]"
     print(f"{i:3d} {r[0]:9d} {r[1]:9d} | {r[2]:9d} {r[3]:9d} {r[4]:9d} {r[5]:9d}{d}")
     prev = r
+
+if LAYOUT == 1:
+    print("per-MMA issue stamps (cycles since step start), steps 8..20; columns = dx*4+k")
+    for i in list(range(0, 4)) + list(range(8, 21)):
+        base = int(t[i, 0])
+        print(f"{i:3d} " + " ".join(f"{int(v) - base:5d}" for v in t3[i, :12]))
+
+if LAYOUT == 1:
+    print(f"CTA body cycles: traced CTA0 {int(body[0])}, others min {int(body[1:].min())} median {int(body[1:].median())} max {int(body[1:].max())}")
+    span = int(g1.max() - g0.min()); med = int((g1 - g0).median())
+    print(f"body ns: median {med}, first start -> last end {span} ns, start skew {int(g0.max() - g0.min())} ns, end skew {int(g1.max() - g1.min())} ns; clock ~ {int(body[1:147].median()) / med:.3f} GHz")
+    # steady-state launch-to-launch period for comparison
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    del os.environ["PNP_TRACE_PTR"]
+    e0.record()
+    for _ in range(50): ops.conv3x3(x, wp9, out=out, idt=idt if IDT else None, wlayout=LAYOUT)
+    e1.record(); torch.cuda.synchronize()
+    print(f"back-to-back launches: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us per launch")

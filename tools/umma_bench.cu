@@ -83,7 +83,7 @@ bench_kernel(int n, int n_acc, int per_group, int reps, int a_span, int b_span, 
 // Replica of one CTA of the row-stacked conv kernel's MMA thread: per step [N=128 acc + N=64 overwrite],
 // optional deferred commit, 11 x N=192, optional `gap_waits` already-complete mbarrier waits between steps.
 __global__ void __launch_bounds__(128, 1)
-step_kernel(int steps, int use_commit, int gap_waits, int spin_warps, long long* out_cycles) {
+step_kernel(int steps, int use_commit, int gap_waits, int spin_warps, long long* out_cycles, int fill = 0) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar, done_bar[8], ready_bar;
   __shared__ uint32_t tmem_slot;
@@ -101,6 +101,15 @@ step_kernel(int steps, int use_commit, int gap_waits, int spin_warps, long long*
     __syncwarp();
     tmem_alloc(smem_u32(&tmem_slot), 512);
   }
+  // fill: 0 = whatever the SM holds, 1 = constant, 2 = pseudo-random bf16 in (-2,2) (data-dependent power?)
+  if (fill)
+    for (int i = threadIdx.x; i < 190 * 1024 / 4; i += blockDim.x) {
+      uint32_t h = (uint32_t)i * 2654435761u;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      const uint32_t v = (h & 0x807F807Fu) | 0x3F003F00u | ((h >> 3) & 0x00800080u);
+      reinterpret_cast<uint32_t*>(smem_raw + (sbase - raw))[i] = fill == 2 ? v : 0x3c003c00u;
+    }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -247,19 +256,22 @@ int main() {
     printf("\n");
   }
   cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  struct SP { int commit, gaps, spin; const char* what; };
+  struct SP { int commit, gaps, spin; const char* what; int fill; };
   const SP sps[] = {{0, 0, 0, "steps: no commit, no gap"},       {1, 0, 0, "steps: deferred commit, no gap"},
+                    {1, 0, 0, "steps: deferred commit, no gap, CONSTANT operands", 1},
+                    {1, 0, 0, "steps: deferred commit, no gap, RANDOM operands", 2},
+                    {1, 0, 2, "steps: deferred commit, no gap, random, 2 polling warps", 2},
                     {0, 4, 0, "steps: no commit, 4 waits gap"},  {1, 4, 0, "steps: deferred commit, 4 waits gap"},
                     {1, 4, 2, "steps: commit + gap + 2 polling warps"}, {1, 2, 0, "steps: deferred commit, 2 waits gap"}};
   for (const SP& sp : sps) {
-    step_kernel<<<sms, 128, 200 * 1024>>>(200, sp.commit, sp.gaps, sp.spin, d);
+    step_kernel<<<sms, 128, 200 * 1024>>>(200, sp.commit, sp.gaps, sp.spin, d, sp.fill);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: %s\n", sp.what, cudaGetErrorString(e)); return 1; }
     long long h[256];
     cudaMemcpy(h, d, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
     double mean = 0;
     for (int i = 0; i < sms; ++i) mean += (double)h[i];
-    printf("%-48s %7.0f cycles/step (ideal 12 x 98.6 + 18 = 1201)\n", sp.what, mean / sms / 200.0);
+    printf("%-58s %7.0f cycles/step (ideal 12 x 98.6 + 18 = 1201)\n", sp.what, mean / sms / 200.0);
   }
   const int reps = 200;
   for (const Pat& p : pats) {
