@@ -134,7 +134,7 @@ int pnp_mv_rasterize(const float* records, const int32_t* frame_offsets, const i
  *   acc  = conv3x3(src, W) [+ conv1x1(aux, Waux)]
  *   v    = acc * scale + bias [+ sum_k par_k * conv1x1_k(src)] [+ idt]      (fp32)
  *   out  = act(v)                       -> bf16 NHWC               (mode PNP_CONV_BF16)
- *   outf = v[0:3] + lq                  -> fp32 NCHW view          (mode PNP_CONV_LAST)
+ *   outf = v[0:3] + lq (or up4(lq))     -> fp32 NCHW view          (mode PNP_CONV_LAST)
  * Reference call sites: ResidualBlockNoBNDynamic_drt.forward (sr_backbone_utils.py:304-333),
  * input_conv (basicvsr_net.py:484,515), conv_hr/conv_last (iconvsr_ipb_par.py:144-146).
  */
@@ -170,6 +170,13 @@ typedef struct pnp_conv_desc {
   int32_t flip_y;      /* PNP_WLAYOUT_ROWSTACK only: process rows bottom-up.  The result is identical when wpack
                           was packed with flip_ky = 1; alternating directions between dependent launches
                           makes each launch read first what its predecessor wrote last (L2 hits). */
+  int64_t out_spx, out_sy, out_sn; /* element strides of `out` between pixels / rows / images; all 0 = contiguous
+                          (64, 64*W, 64*H*W).  A strided view makes the TMA store a scatter: launch g of a
+                          PixelShufflePack (upsample.py:46-49, scale 2) writes its 64 channels to
+                          up[:, i::2, j::2, :] -- the pixel shuffle is the store epilogue.  Multiples of 8. */
+  int32_t lq_up4;      /* PNP_CONV_LAST: 1 = `lq` is the (N,3,H/4,W/4) low-resolution frame and the epilogue adds its
+                          x4 bilinear upsampling (nn.Upsample(scale_factor=4, mode='bilinear', align_corners=False),
+                          iconvsr_ipb_par.py:41,140-141) instead of lq itself; row-stacked layout only */
   int32_t wpack_stable; /* 1: wpack was NOT written by the operation immediately preceding this launch in the stream
                           (weights are packed once per checkpoint / clip, long before the frame loop), so the
                           kernel may fetch it while the previous kernel is still draining (programmatic dependent

@@ -230,11 +230,11 @@ def resblocks(sd, branch, x_in, par, w_experts, gamma, num_blocks=NUM_BLOCKS):
 # --------------------------------------------------------------------------------------
 @torch.no_grad()
 def generator_forward(sd, lrs, QPs, slices, mvs, base_QPs, par_map, num_blocks=NUM_BLOCKS,
-                      return_features=False):
+                      return_features=False, vsr=False):
     """IconVSR_restore_wo_refill_mv_ipb_fast_domain_dynamic_with_par.forward
 
     iconvsr_ipb_par.py:44-149 with the config kwargs of configs/HR_davis_LR_128x128.py:6-25
-    (with_cat, use_base_qp, with_bias+with_se, align_key, vsr=False).  ``sd`` is the reference's
+    (with_cat, use_base_qp, with_bias+with_se, align_key; vsr selects the x4 tail).  ``sd`` is the reference's
     ``state_dict``.  Returns (n,t,3,Hp,Wp) -- padded, NOT cropped (reference quirk).
     """
     sd = {k: v.to(lrs.device, torch.float32) for k, v in sd.items()}
@@ -289,6 +289,16 @@ def generator_forward(sd, lrs, QPs, slices, mvs, base_QPs, par_map, num_blocks=N
             x = resblocks(sd, "forward", feat, par_map[b:b + 1, i], experts[b, i], gammas[b, i],
                           num_blocks)
             outputs[b][i] = x
+            if vsr:                                   # x4 tail, :135-142 (PixelShufflePack: common/upsample.py:46-49)
+                o = x
+                for name in ("upsample1", "upsample2"):
+                    o = F.conv2d(o, sd[name + ".upsample_conv.weight"], sd[name + ".upsample_conv.bias"], padding=1)
+                    o = F.leaky_relu(F.pixel_shuffle(o, 2), 0.1)
+                o = F.leaky_relu(F.conv2d(o, sd["conv_hr.weight"], sd["conv_hr.bias"], padding=1), 0.1)
+                o = F.conv2d(o, sd["conv_last.weight"], sd["conv_last.bias"], padding=1)
+                base = F.interpolate(lr, scale_factor=4, mode="bilinear", align_corners=False)   # :41
+                frames.append(o + base)
+                continue
             o = F.leaky_relu(F.conv2d(x, sd["conv_hr.weight"], sd["conv_hr.bias"], padding=1), 0.1)
             o = F.conv2d(o, sd["conv_last.weight"], sd["conv_last.bias"], padding=1)
             frames.append(o + lr)                     # :144-147

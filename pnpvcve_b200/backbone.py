@@ -7,7 +7,8 @@ Boundary being mirrored (all paths relative to the reference tree):
     from ``configs/HR_davis_LR_128x128*.py`` generator dicts;
   * call: ``generator(lq, QPs, slices, mvs, base_QPs, par_map)`` positionally
     (mmedit/models/restorers/basicvsr.py:179, basic_restorer.py:113,160);
-  * return: new fp32 ``(n, T, 3, Hp, Wp)`` tensor, H/W rounded up to x4 and NOT cropped;
+  * return: new fp32 ``(n, T, 3, Hp, Wp)`` tensor, H/W rounded up to x4 and NOT cropped
+    (``(n, T, 3, 4Hp, 4Wp)`` with ``vsr=True``: PixelShufflePack x2 + bilinear x4 base, :36-41,135-142);
   * ``init_weights(pretrained, strict)``: iconvsr.py:510-523;
   * ``state_dict`` keys: SURVEY.md section 8(b) (see ``pnpvcve_b200.weights``).
 
@@ -86,9 +87,19 @@ class _GainPredictor(_Holder):
                                 nn.Linear(channel // reduction, channel, bias=False))
 
 
+class _PixelShufflePack(_Holder):
+    """PixelShufflePack parameters (common/upsample.py:27-41): conv 64 -> 64*r*r, 3x3; default_init_weights(self, 1)."""
+
+    def __init__(self, cin, cout, scale):
+        super().__init__()
+        self.upsample_conv = nn.Conv2d(cin, cout * scale * scale, 3, padding=1)
+        nn.init.kaiming_normal_(self.upsample_conv.weight, a=0, mode="fan_in", nonlinearity="relu")
+        nn.init.zeros_(self.upsample_conv.bias)
+
+
 _REQUIRED = dict(mid_channels=64, num_group=1, expert_softmax=True, use_base_qp=True, with_bias=True,
                  with_se=True, one_layer=True, blocktype="drt", channel_first=True, sparse_val=False,
-                 vsr=False, align_key=True, with_cat=True, deform="vos", flow_inter="bilinear")
+                 align_key=True, with_cat=True, deform="vos", flow_inter="bilinear")
 
 
 @BACKBONES.register_module()
@@ -111,7 +122,7 @@ class IconVSR_restore_wo_refill_mv_ipb_fast_domain_dynamic_with_par(nn.Module):
         given = dict(mid_channels=mid_channels, num_group=num_group, expert_softmax=expert_softmax,
                      use_base_qp=use_base_qp, with_bias=with_bias, with_se=with_se,
                      one_layer=one_layer, blocktype=blocktype, channel_first=channel_first,
-                     sparse_val=sparse_val, vsr=vsr, align_key=align_key, with_cat=with_cat,
+                     sparse_val=sparse_val, align_key=align_key, with_cat=with_cat,
                      deform=deform, flow_inter=flow_inter)
         bad = {k: v for k, v in given.items() if v != _REQUIRED[k]}
         if bad:
@@ -138,6 +149,9 @@ class IconVSR_restore_wo_refill_mv_ipb_fast_domain_dynamic_with_par(nn.Module):
                                                     self.num_experts, init_weight)
         self.conv_hr = nn.Conv2d(64, 64, 3, 1, 1)
         self.conv_last = nn.Conv2d(64, 3, 3, 1, 1)
+        if vsr:   # x4 tail: PixelShufflePack x2, bilinear base (iconvsr_ipb_par.py:36-41); img_upsample has no parameters
+            self.upsample1 = _PixelShufflePack(mid_channels, mid_channels, 2)
+            self.upsample2 = _PixelShufflePack(mid_channels, 64, 2)
         self._engine = BaeEngine(self)
 
     # ------------------------------------------------------------------ reference API

@@ -1,4 +1,5 @@
 // extern "C" surface of libpnpvcve.so (declared in include/pnp_vcve.h).
+#include <cstddef>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -70,11 +71,18 @@ EncodeTiledFn encode_fn() {
 }
 
 // (64, W, H, N) bf16 NHWC tensor, box (64, box_w, 1, 1), 128-byte swizzle, zero fill out of range.
-int make_map(CUtensorMap* m, const void* base, int N, int H, int W, int box_w) {
+// spx/sy/sn: element strides between pixels / rows / images (0 = contiguous NHWC).
+int make_map(CUtensorMap* m, const void* base, int N, int H, int W, int box_w, long long spx = 0, long long sy = 0,
+             long long sn = 0) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(PNP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+  if (spx != 0) {
+    strides[0] = (cuuint64_t)spx * 2;
+    strides[1] = (cuuint64_t)sy * 2;
+    strides[2] = (cuuint64_t)sn * 2;
+  }
   cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
@@ -93,6 +101,9 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 extern "C" {
 
+static_assert(sizeof(pnp_conv_desc) == 232 && offsetof(pnp_conv_desc, out_spx) == 200 &&
+                  offsetof(pnp_conv_desc, wpack_stable) == 228,
+              "pnp_conv_desc layout is part of the ABI (mirrored by pnpvcve_b200/_lib.py: ConvDesc)");
 int pnp_abi_version(void) { return 6; }
 
 const char* pnp_last_error(void) { return g_err; }
@@ -267,6 +278,12 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   if (!rowstack && c->n_wchunks != need_chunks)
     return fail(PNP_ERR_ARG, "pnp_conv3x3: n_wchunks does not match the layout");
   if (c->act < 0 || c->act > 2) return fail(PNP_ERR_ARG, "pnp_conv3x3: bad act");
+  const bool strided_out = c->out_spx != 0 || c->out_sy != 0 || c->out_sn != 0;
+  if (strided_out && (last || c->out_spx < 64 || c->out_sy < c->out_spx * c->W || (c->N > 1 && c->out_sn < c->out_sy * c->H) ||
+                      ((c->out_spx | c->out_sy | c->out_sn) & 7)))
+    return fail(PNP_ERR_ARG, "pnp_conv3x3: out strides must be non-overlapping multiples of 8 elements (PNP_CONV_BF16 only)");
+  if (c->lq_up4 && (!last || !rowstack || (c->H & 3) || (c->W & 3)))
+    return fail(PNP_ERR_ARG, "pnp_conv3x3: lq_up4 needs PNP_CONV_LAST, the row-stacked layout and H, W multiples of 4");
   if (!aligned16(c->src) || !aligned16(c->wpack) || (c->aux && !aligned16(c->aux)) ||
       (c->idt && !aligned16(c->idt)) || (c->out && !aligned16(c->out)))
     return fail(PNP_ERR_ARG, "pnp_conv3x3: pointers must be 16-byte aligned");
@@ -279,7 +296,8 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   if ((rc = make_map(&p.tm_src, c->src, c->N, c->H, c->W, pnp::kHaloPx))) return rc;
   if (c->aux && (rc = make_map(&p.tm_aux, c->aux, c->N, c->H, c->W, pnp::kTilePx))) return rc;
   if (c->idt && (rc = make_map(&p.tm_id, c->idt, c->N, c->H, c->W, pnp::kTilePx))) return rc;
-  if (!last && (rc = make_map(&p.tm_out, c->out, c->N, c->H, c->W, pnp::kTilePx))) return rc;
+  if (!last && (rc = make_map(&p.tm_out, c->out, c->N, c->H, c->W, pnp::kTilePx, c->out_spx, c->out_sy, c->out_sn)))
+    return rc;
   if (last) p.tm_out = p.tm_src;  // never used; keeps the prefetch harmless
   p.wpack = c->wpack;
   p.scale = c->scale;
@@ -307,6 +325,7 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   p.mode = last ? pnp::kModeLast : pnp::kModeBf16;
   p.flip_y = (rowstack && c->flip_y) ? 1 : 0;
   p.w_stable = c->wpack_stable ? 1 : 0;
+  p.lq_up4 = c->lq_up4 ? 1 : 0;
   p.base_off_mode = g_base_off_mode;
   {
     const char* dbg = getenv("PNP_DEBUG_SKIP");   // what-if profiling only; results are wrong when set

@@ -566,10 +566,34 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       if (last_mode) {
         float r0 = 0.f, r1 = 0.f, r2 = 0.f;
         if (valid && half == 0) {
-          const float* lp = p.lq + (long long)s.n * p.lq_sn + (long long)y * p.lq_sy + x;
-          r0 = __ldg(lp);
-          r1 = __ldg(lp + p.lq_sc);
-          r2 = __ldg(lp + 2 * p.lq_sc);
+          if (p.lq_up4) {
+            // base = nn.Upsample(scale_factor=4, mode='bilinear', align_corners=False)(lr), iconvsr_ipb_par.py:41,
+            // 140-141, fused: ATen's source index scale*(dst+0.5)-0.5 clamped at 0, i1 = i0 + (i0 < size-1),
+            // lambda1 = src - i0, row blend of the two column blends
+            const int hl = p.H >> 2, wl = p.W >> 2;
+            const float sy = fmaxf(0.25f * ((float)y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.25f * ((float)x + 0.5f) - 0.5f, 0.f);
+            const int y0 = (int)sy, x0 = (int)sx;
+            const int y1 = y0 + (y0 < hl - 1 ? 1 : 0), x1 = x0 + (x0 < wl - 1 ? 1 : 0);
+            const float ly1 = sy - (float)y0, lx1 = sx - (float)x0;
+            const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+            const float* b0 = p.lq + (long long)s.n * p.lq_sn + (long long)y0 * p.lq_sy;
+            const float* b1 = p.lq + (long long)s.n * p.lq_sn + (long long)y1 * p.lq_sy;
+            float r[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float* c0 = b0 + c * p.lq_sc;
+              const float* c1 = b1 + c * p.lq_sc;
+              r[c] = ly0 * (lx0 * __ldg(c0 + x0) + lx1 * __ldg(c0 + x1)) + ly1 * (lx0 * __ldg(c1 + x0) + lx1 * __ldg(c1 + x1));
+            }
+            r0 = r[0];
+            r1 = r[1];
+            r2 = r[2];
+          } else {
+            const float* lp = p.lq + (long long)s.n * p.lq_sn + (long long)y * p.lq_sy + x;
+            r0 = __ldg(lp);
+            r1 = __ldg(lp + p.lq_sc);
+            r2 = __ldg(lp + 2 * p.lq_sc);
+          }
         }
         ewait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> 3) & 1, 9);
         tc_fence_after();

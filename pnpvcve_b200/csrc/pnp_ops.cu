@@ -1,5 +1,7 @@
 // Memory-bound kernels of the BAE path: MV-guided warp (K1), LR im2col packing, weight packing with
 // expert mixing (K4) and the CAA heads.
+#include <cstdlib>
+
 #include "pnp_ops.cuh"
 #include "pnp_ptx.cuh"
 
@@ -22,24 +24,10 @@ __device__ __forceinline__ float warp_coord(float pos, float mv, float size_m1_d
   return __fmul_rn(__fmul_rn(__fadd_rn(nrm, 1.0f), 0.5f), size_m1);    // ((c+1)/2)*(s-1)
 }
 
-// The first version of this kernel spent ~550 SASS instructions per 48 bytes moved (64-bit index
-// divisions, per-tap rounded mul/add chains) and was issue-bound at ~45 % of the HBM roofline.
-// Now: 2-D grid (no divisions), 32-bit indexing, 4 threads per pixel x 32 bytes each, FMA blend.
-__global__ void __launch_bounds__(256)
-mv_warp_kernel(const uint4* __restrict__ src, const float* __restrict__ flow_x,
-               const float* __restrict__ flow_y, long long flow_sy, long long flow_sn, uint4* __restrict__ dst,
-               int H, int W, int* __restrict__ dbg_x0, int* __restrict__ dbg_y0) {
-  // blockIdx.z = image of the batch: same-shape clips with their own motion fields
-  src += (size_t)blockIdx.z * H * W * 8;
-  dst += (size_t)blockIdx.z * H * W * 8;
-  flow_x += (long long)blockIdx.z * flow_sn;
-  flow_y += (long long)blockIdx.z * flow_sn;
-  const int y = blockIdx.y;
-  const int x = blockIdx.x * 64 + (threadIdx.x >> 2);     // 64 pixels per block, 4 threads per pixel
-  const int q = threadIdx.x & 3;                          // which 16-channel quarter (two uint4)
-  if (x >= W) return;
-  const float fx = __ldg(flow_x + (long long)y * flow_sy + x);
-  const float fy = __ldg(flow_y + (long long)y * flow_sy + x);
+// One pixel quarter (16 channels = 32 bytes) of the warp: coordinates, 4 taps, fp32 blend, store.
+__device__ __forceinline__ void warp_pixel_quarter(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                   float fx, float fy, int x, int y, int q, int H, int W,
+                                                   int* __restrict__ dbg_x0, int* __restrict__ dbg_y0) {
   const float ix = warp_coord((float)x, fx, (float)max(W - 1, 1), (float)(W - 1));
   const float iy = warp_coord((float)y, fy, (float)max(H - 1, 1), (float)(H - 1));
   const float x0f = floorf(ix), y0f = floorf(iy);
@@ -97,14 +85,71 @@ mv_warp_kernel(const uint4* __restrict__ src, const float* __restrict__ flow_x,
   op[1] = o[1];
 }
 
+// The first version of this kernel spent ~550 SASS instructions per 48 bytes moved (64-bit index
+// divisions, per-tap rounded mul/add chains) and was issue-bound at ~45 % of the HBM roofline.
+// Second version: 2-D grid (no divisions), 32-bit indexing, 4 threads per pixel x 32 bytes each, FMA
+// blend, one block = 64 pixels of ONE row -- every source row was then fetched from L2 by two blocks
+// (rows y0 and y0+1 of vertically adjacent outputs), i.e. ~2x the source bytes over the L2->SM path.
+// Now: one block = a kTileW x kTileH pixel tile walked two rows at a time, so the second tap row of one
+// iteration is the first tap row of the next and is found in L1; with the codec's block-constant motion
+// vectors a tile reads a (kTileW+1) x (kTileH+1) window once.
+template <int kTileW, int kTileH>
+__global__ void __launch_bounds__(256)
+mv_warp_kernel(const uint4* __restrict__ src, const float* __restrict__ flow_x,
+               const float* __restrict__ flow_y, long long flow_sy, long long flow_sn, uint4* __restrict__ dst,
+               int H, int W, int* __restrict__ dbg_x0, int* __restrict__ dbg_y0) {
+  constexpr int kRowsPerIter = 64 / kTileW;               // 256 threads = 64 pixels x 4 quarters per iteration
+  static_assert(kTileW * kRowsPerIter == 64 && kTileH % kRowsPerIter == 0, "tile shape");
+  // blockIdx.z = image of the batch: same-shape clips with their own motion fields
+  src += (size_t)blockIdx.z * H * W * 8;
+  dst += (size_t)blockIdx.z * H * W * 8;
+  flow_x += (long long)blockIdx.z * flow_sn;
+  flow_y += (long long)blockIdx.z * flow_sn;
+  const int q = threadIdx.x & 3;                          // which 16-channel quarter (two uint4)
+  const int px = threadIdx.x >> 2;                        // 0..63
+  const int x = blockIdx.x * kTileW + (px % kTileW);
+  const int ry = px / kTileW;
+  if (x >= W) return;
+  const int y_base = blockIdx.y * kTileH + ry;
+  // all motion vectors of this thread's pixels first (independent loads), then the gathers
+  float fx[kTileH / kRowsPerIter], fy[kTileH / kRowsPerIter];
+#pragma unroll
+  for (int it = 0; it < kTileH / kRowsPerIter; ++it) {
+    const int y = y_base + it * kRowsPerIter;
+    fx[it] = (y < H) ? __ldg(flow_x + (long long)y * flow_sy + x) : 0.f;
+    fy[it] = (y < H) ? __ldg(flow_y + (long long)y * flow_sy + x) : 0.f;
+  }
+#pragma unroll
+  for (int it = 0; it < kTileH / kRowsPerIter; ++it) {
+    const int y = y_base + it * kRowsPerIter;
+    if (y < H) warp_pixel_quarter(src, dst, fx[it], fy[it], x, y, q, H, W, dbg_x0, dbg_y0);
+  }
+}
+
 cudaError_t launch_mv_warp(const void* src, const float* flow_x, const float* flow_y, long long flow_sy,
                            long long flow_sn, void* dst, int N, int H, int W, int* dbg_x0, int* dbg_y0,
                            int num_sms, cudaStream_t stream) {
   (void)num_sms;
   if ((long long)H * W >= (1LL << 27) || N > 65535) return cudaErrorInvalidValue;   // 32-bit pixel indexing
-  dim3 grid((W + 63) / 64, H, N);
-  mv_warp_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), flow_x, flow_y, flow_sy, flow_sn,
-                                           reinterpret_cast<uint4*>(dst), H, W, dbg_x0, dbg_y0);
+  static int variant = -1;                                // diagnostic: PNP_WARP_TILE = 0 (64x1), 1 (32x8), 2 (16x8), 3 (64x4)
+  if (variant < 0) {
+    const char* v = getenv("PNP_WARP_TILE");
+    variant = v ? atoi(v) : 1;
+  }
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#define PNP_WARP_LAUNCH(TW, TH)                                                                              \
+  mv_warp_kernel<TW, TH><<<dim3((W + TW - 1) / TW, (H + TH - 1) / TH, N), 256, 0, stream>>>(s, flow_x, flow_y, flow_sy, \
+                                                                                           flow_sn, d, H, W, dbg_x0, dbg_y0)
+  switch (variant) {
+    case 0: PNP_WARP_LAUNCH(64, 1); break;
+    case 2: PNP_WARP_LAUNCH(16, 8); break;
+    case 3: PNP_WARP_LAUNCH(64, 4); break;
+    case 4: PNP_WARP_LAUNCH(32, 16); break;
+    case 5: PNP_WARP_LAUNCH(32, 4); break;
+    default: PNP_WARP_LAUNCH(32, 8); break;
+  }
+#undef PNP_WARP_LAUNCH
   return cudaGetLastError();
 }
 

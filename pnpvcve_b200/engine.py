@@ -69,14 +69,14 @@ class _Launcher:
         self.seen = {}
 
     def __call__(self, stream, src, wpack, out=None, aux=None, idt=None, scale=None, bias=None,
-                 par=None, act=PNP_ACT_NONE, lq=None, outf=None, label=None, flip_y=False):
+                 par=None, act=PNP_ACT_NONE, lq=None, outf=None, label=None, flip_y=False, lq_up4=False):
         # row-stacked weight layout (one source row feeds three output rows, N=192 MMAs) for every
         # conv except the partition-modulated block launch A
         # wpack_stable: every pack kernel of the call ran before the frame loop started (the launch
         # right before a conv is always lr_im2col, the warp or another conv)
         ops.fill_conv_desc(self.desc, src, wpack, out, aux, idt, scale, bias, par, act, lq, outf,
                            wlayout=0 if (par is not None and not self.rows_par) else 1, flip_y=flip_y,
-                           wpack_stable=True)
+                           wpack_stable=True, lq_up4=lq_up4)
         timed = self.prof is not None and label in self.prof
         if timed:                                  # bracket every prof_every-th launch of this label
             k = self.seen.get(label, 0)
@@ -210,6 +210,20 @@ class BaeEngine:
         last = ops.new_wpack_rowstack(dev, tap_n=16)
         ops.pack_conv3x3_rowstack(f32(m.conv_last.weight), last, tap_n=16)
         st["last_w"], st["last_b"] = last, f32(m.conv_last.bias)
+        if m.vsr:
+            # PixelShufflePack (common/upsample.py:46-49): conv 64 -> 256 then pixel_shuffle(2), i.e. output
+            # channel c*4 + 2*i + j lands at (c, 2y+i, 2x+j).  Sliced by g = 2*i + j this is four 64 -> 64
+            # convs whose 64 channels are one NHWC pixel of the upsampled map: the shuffle becomes the
+            # (strided) store of launch g and LeakyReLU stays in its epilogue.
+            for name, mod in (("up1", m.upsample1), ("up2", m.upsample2)):
+                w_up, b_up = f32(mod.upsample_conv.weight), f32(mod.upsample_conv.bias)
+                packs, biases = [], []
+                for g in range(4):
+                    buf = ops.new_wpack_rowstack(dev)
+                    ops.pack_conv3x3_rowstack(w_up[g::4].contiguous(), buf)
+                    packs.append(buf)
+                    biases.append(b_up[g::4].contiguous())
+                st[name + "_w"], st[name + "_b"] = packs, biases
         st["caa"] = dict(b0w=f32(m.BasePredictor.BaseNet[0].weight), b0b=f32(m.BasePredictor.BaseNet[0].bias),
                          b2w=f32(m.BasePredictor.BaseNet[2].weight), b2b=f32(m.BasePredictor.BaseNet[2].bias),
                          s0w=f32(m.BiasePredictor.fc[0].weight), s2w=f32(m.BiasePredictor.fc[2].weight))
@@ -258,7 +272,7 @@ class BaeEngine:
 
     # ------------------------------------------------------------------ buffers
     def _buffers(self, n, t, h, w, dev, lanes, maxn):
-        key = (n, t, h, w, dev, lanes, maxn)
+        key = (n, t, h, w, dev, lanes, maxn, bool(self.m.vsr))
         if self.buf is not None and self.buf_key == key:
             return self.buf
         self.buf = None                                   # release before re-allocating
@@ -268,6 +282,10 @@ class BaeEngine:
             lb = {k: ops.new_feature(maxn, h, w, dev) for k in names}
             lb["lr64"] = ops.new_feature(maxn, h, w, dev, zero=True)
             lb["zero"] = ops.new_feature(maxn, h, w, dev, zero=True)
+            if self.m.vsr:      # x4 tail: 2Hx2W and 4Hx4W feature maps of one frame
+                lb["u1"] = ops.new_feature(maxn, 2 * h, 2 * w, dev)
+                lb["u2"] = ops.new_feature(maxn, 4 * h, 4 * w, dev)
+                lb["hr4"] = ops.new_feature(maxn, 4 * h, 4 * w, dev)
             lb["launcher"] = _Launcher()
             lane_bufs.append(lb)
         # frame-major so that the features of a run of clips at one frame are one contiguous (N,H,W,64) block
@@ -327,7 +345,8 @@ class BaeEngine:
         lanes = max(1, min(len(groups), self.max_lanes))
         bufs = self._buffers(n, t, h, w, dev, lanes, maxn)
         feats = bufs["feats"]
-        out = torch.empty((n, t, 3, h, w), dtype=torch.float32, device=dev)
+        up = 4 if m.vsr else 1
+        out = torch.empty((n, t, 3, up * h, up * w), dtype=torch.float32, device=dev)
         prof = self.prof
         seen = {}
         bwd_feats = torch.empty_like(feats) if return_features else None
@@ -461,11 +480,24 @@ class BaeEngine:
                 phase("fwd_input_done")
                 stack("fwd", nb, i, x0, cur, mixed)
                 phase("fwd_stack_done")
-                # out = conv_last(lrelu(conv_hr(x))) + lq   (:144-146)
-                conv(stream, cur, st["hr_w"], out=buf["hr"], bias=st["hr_b"], act=PNP_ACT_LRELU, label="hr")
-                conv(stream, buf["hr"], st["last_w"], bias=st["last_b"], lq=lrs[b0:b1, i],
-                     outf=out[b0:b1, i], label="last")
-                counts[lane] += 2
+                if m.vsr:
+                    # x4 tail (:135-142): lrelu(upsample1) -> lrelu(upsample2) -> lrelu(conv_hr) -> conv_last
+                    # + bilinear x4 of the LR frame.  Pixel shuffle = strided store of launch g, the bilinear
+                    # base is computed inside conv_last's epilogue from the LR frame.
+                    for src_f, dst_f, name in ((cur, buf["u1"], "up1"), (buf["u1"], buf["u2"], "up2")):
+                        for g in range(4):
+                            conv(stream, src_f, st[name + "_w"][g], out=dst_f[:, g >> 1::2, g & 1::2, :],
+                                 bias=st[name + "_b"][g], act=PNP_ACT_LRELU, label="up")
+                    conv(stream, buf["u2"], st["hr_w"], out=buf["hr4"], bias=st["hr_b"], act=PNP_ACT_LRELU, label="hr")
+                    conv(stream, buf["hr4"], st["last_w"], bias=st["last_b"], lq=lrs[b0:b1, i],
+                         outf=out[b0:b1, i], label="last", lq_up4=True)
+                    counts[lane] += 10
+                else:
+                    # out = conv_last(lrelu(conv_hr(x))) + lq   (:144-146)
+                    conv(stream, cur, st["hr_w"], out=buf["hr"], bias=st["hr_b"], act=PNP_ACT_LRELU, label="hr")
+                    conv(stream, buf["hr"], st["last_w"], bias=st["last_b"], lq=lrs[b0:b1, i],
+                         outf=out[b0:b1, i], label="last")
+                    counts[lane] += 2
                 phase("fwd_head_done")
                 yield
 

@@ -23,8 +23,11 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
-def _feat_check(t, name):
-    if t.dtype != torch.bfloat16 or t.dim() != 4 or t.shape[-1] != 64 or not t.is_contiguous():
+def _feat_check(t, name, strided=False):
+    ok = t.dtype == torch.bfloat16 and t.dim() == 4 and t.shape[-1] == 64
+    if ok and not t.is_contiguous():
+        ok = strided and t.stride(3) == 1 and all(st % 8 == 0 and st > 0 for st in t.stride()[:3])
+    if not ok:
         raise ValueError(f"{name} must be a contiguous bf16 (N,H,W,64) tensor, got "
                          f"{tuple(t.shape)} {t.dtype}")
     if not t.is_cuda:
@@ -164,13 +167,20 @@ def mix_bias(conv2_bias, experts, gamma):
 
 
 def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
-                   act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False, wpack_stable=False):
-    """Fill a ConvDesc in place (reusable across launches)."""
+                   act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False, wpack_stable=False,
+                   lq_up4=False):
+    """Fill a ConvDesc in place (reusable across launches).  `out` may be a strided (N,H,W,64) view with
+    unit channel stride (e.g. up[:, i::2, j::2, :]: pixel shuffle as the store epilogue)."""
     n, h, w, _ = src.shape
     last = outf is not None
     d.src, d.aux, d.idt = src.data_ptr(), (aux.data_ptr() if aux is not None else None), \
         (idt.data_ptr() if idt is not None else None)
     d.out = out.data_ptr() if out is not None else None
+    if out is not None and not out.is_contiguous():
+        d.out_sn, d.out_sy, d.out_spx = out.stride(0), out.stride(1), out.stride(2)
+    else:
+        d.out_sn = d.out_sy = d.out_spx = 0
+    d.lq_up4 = 1 if lq_up4 else 0
     d.wpack = wpack.data_ptr()
     d.scale = scale.data_ptr() if scale is not None else None
     d.bias = bias.data_ptr() if bias is not None else None
@@ -198,22 +208,26 @@ def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias
 
 
 def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
-            act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False, wpack_stable=False):
-    """Fused tcgen05 3x3 conv (see include/pnp_vcve.h: pnp_conv3x3)."""
+            act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False, wpack_stable=False, lq_up4=False):
+    """Fused tcgen05 3x3 conv (see include/pnp_vcve.h: pnp_conv3x3).  `out` may be a strided view with unit
+    channel stride (pixel shuffle as the store epilogue); lq_up4: lq is the (N,3,H/4,W/4) frame whose x4
+    bilinear upsampling is added."""
     _feat_check(src, "src")
     for t, nm in ((out, "out"), (aux, "aux"), (idt, "idt")):
         if t is not None:
-            _feat_check(t, nm)
+            _feat_check(t, nm, strided=(nm == "out"))
             if t.shape != src.shape:
                 raise ValueError(f"conv3x3: {nm} shape {tuple(t.shape)} != src {tuple(src.shape)}")
     for t, nm in ((par, "par"), (lq, "lq"), (outf, "outf")):
         if t is not None:
             _plane_view_check(t, nm)
-            if t.dim() != 4 or t.shape[1] != 3 or t.shape[0] != src.shape[0] or \
-                    tuple(t.shape[2:]) != tuple(src.shape[1:3]):
-                raise ValueError(f"conv3x3: {nm} must be (N,3,H,W) matching src")
+            hw = tuple(src.shape[1:3])
+            if nm == "lq" and lq_up4:
+                hw = (src.shape[1] // 4, src.shape[2] // 4)
+            if t.dim() != 4 or t.shape[1] != 3 or t.shape[0] != src.shape[0] or tuple(t.shape[2:]) != hw:
+                raise ValueError(f"conv3x3: {nm} must be (N,3,H,W) matching src" + (" / 4" if hw[0] != src.shape[1] else ""))
     d = fill_conv_desc(ConvDesc(), src, wpack, out, aux, idt, scale, bias, par, act, lq, outf, wlayout, flip_y,
-                       wpack_stable)
+                       wpack_stable, lq_up4)
     need = rowstack_bytes(d.tap_n, aux is not None, par is not None) if wlayout == 1 \
         else d.n_wchunks * CHUNK_BYTES
     if wpack.numel() < need:

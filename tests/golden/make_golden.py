@@ -42,6 +42,9 @@ CASES = {
         dict(h=64, w=64, t=1, seed=3300, crf=35, mv_qpel=32, ipb=False, pattern="IBBP")]),
     "edge_68x132_t3": dict(weight_seed=5, num_blocks=8, clips=[
         dict(h=68, w=132, t=3, seed=3400, crf=15, mv_qpel=64, ipb=True, pattern="IBBP")]),
+    # vsr=True: PixelShufflePack x2 + bilinear x4 base tail (iconvsr_ipb_par.py:36-41,135-142); output is 4H x 4W
+    "vsr_64x96_t3": dict(weight_seed=6, num_blocks=8, vsr=True, clips=[
+        dict(h=64, w=96, t=3, seed=3500, crf=25, mv_qpel=32, ipb=True, pattern="IBBP")]),
 }
 
 
@@ -58,10 +61,18 @@ def build_inputs(case):
 
 def main():
     torch.set_num_threads(os.cpu_count())
+    only = set(sys.argv[1:])           # optional: regenerate just these cases (cases.json is merged)
     meta = {}
+    cases_path = os.path.join(HERE, "cases.json")
+    if only and os.path.isfile(cases_path):
+        with open(cases_path) as f:
+            meta = json.load(f)
     for name, case in CASES.items():
-        net = refshim.build_reference(seed=0, num_blocks=case["num_blocks"])
-        sd = weights.random_state_dict(case["weight_seed"], num_blocks=case["num_blocks"])
+        if only and name not in only:
+            continue
+        vsr = bool(case.get("vsr", False))
+        net = refshim.build_reference(seed=0, num_blocks=case["num_blocks"], vsr=vsr)
+        sd = weights.random_state_dict(case["weight_seed"], num_blocks=case["num_blocks"], vsr=vsr)
         net.load_state_dict(sd, strict=True)
         clip = build_inputs(case)
         with torch.no_grad():
@@ -76,6 +87,10 @@ def main():
         meta[name] = case
         print(name, tuple(out.shape), float(out.min()), float(out.max()))
 
+    if only and "warp_720p" not in only:
+        with open(cases_path, "w") as f:
+            json.dump(meta, f, indent=1, sort_keys=True)
+        return
     # reference flow_warp on a 720p plane
     fw = sys.modules["mmedit.models.common.flow_warp"].flow_warp
     g = torch.Generator().manual_seed(4242)

@@ -24,7 +24,7 @@ def build_case(name):
         t = clip["lq"].shape[1]
         half = clip["lq"][:, : t // 2]
         clip["lq"] = torch.cat([half, half.flip(1)], dim=1).contiguous()
-    sd = weights.random_state_dict(case["weight_seed"], num_blocks=case["num_blocks"])
+    sd = weights.random_state_dict(case["weight_seed"], num_blocks=case["num_blocks"], vsr=bool(case.get("vsr")))
     gold = np.load(os.path.join(GOLDEN, name + ".npz"))
     return sd, clip, gold
 

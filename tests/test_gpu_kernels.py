@@ -304,6 +304,42 @@ def test_conv_rowstack_bottom_up_equals_top_down(dev, n, h, w):
     assert (o1 - ref).abs().max().item() < 1e-4 and (o2 - ref).abs().max().item() < 1e-4
 
 
+# ------------------------------------------------------------------ x4 tail epilogues (vsr=True)
+@pytest.mark.parametrize("n,h,w", [(1, 64, 64), (2, 36, 132)])
+def test_pixel_shuffle_store_and_bilinear_base_epilogues(dev, n, h, w):
+    """PixelShufflePack (common/upsample.py:46-49) as four 64->64 launches with strided stores, and conv_last
+    with the x4 bilinear base of the LR frame added in its epilogue (iconvsr_ipb_par.py:139-141)."""
+    g = torch.Generator(device=dev).manual_seed(n * 1000 + h + w)
+    x = bf(torch.randn((n, 64, h, w), generator=g, device=dev))
+    w_up = bf(torch.randn((256, 64, 3, 3), generator=g, device=dev) * 0.05)
+    b_up = torch.randn(256, generator=g, device=dev) * 0.1
+    up = torch.full((n, 2 * h, 2 * w, 64), float("nan"), dtype=torch.bfloat16, device=dev)
+    for k in range(4):
+        wp = ops.new_wpack_rowstack(dev)
+        ops.pack_conv3x3_rowstack(w_up[k::4].contiguous(), wp)
+        ops.conv3x3(nhwc(x), wp, out=up[:, k >> 1::2, k & 1::2, :], bias=b_up[k::4].contiguous(),
+                    act=ops.PNP_ACT_LRELU, wlayout=1)
+    ref = F.leaky_relu(F.pixel_shuffle(F.conv2d(x, w_up, b_up, padding=1), 2), 0.1)
+    assert torch.isfinite(up.float()).all(), "pixels not covered by the four strided stores"
+    assert_bf16_close(nchw(up), ref, "pixel shuffle store")
+
+    hh, ww = 4 * h, 4 * w
+    y = bf(torch.randn((n, 64, hh, ww), generator=g, device=dev))
+    wl = bf(torch.randn((3, 64, 3, 3), generator=g, device=dev) * 0.05)
+    bl = torch.randn(3, generator=g, device=dev) * 0.1
+    lr = torch.rand((n, 3, h, w), generator=g, device=dev)
+    wpl = ops.new_wpack_rowstack(dev, tap_n=16)
+    ops.pack_conv3x3_rowstack(wl, wpl, tap_n=16)
+    outf = torch.empty((n, 3, hh, ww), device=dev)
+    ops.conv3x3(nhwc(y), wpl, bias=bl, lq=lr, outf=outf, wlayout=1, lq_up4=True)
+    base = F.interpolate(lr, scale_factor=4, mode="bilinear", align_corners=False)
+    assert (outf - (F.conv2d(y, wl, bl, padding=1) + base)).abs().max().item() < 1e-4
+    with pytest.raises(Exception):       # tap-major layout has no fused upsampling
+        wt = ops.new_wpack(10, dev)
+        ops.pack_conv3x3(wl, wt)
+        ops.conv3x3(nhwc(y), wt, bias=bl, lq=lr, outf=outf, wlayout=0, lq_up4=True)
+
+
 # ------------------------------------------------------------------ fused residual block (CTA pair)
 def _block_weights(dev, g):
     wt2 = bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05)

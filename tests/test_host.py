@@ -56,9 +56,12 @@ def test_abi_argument_errors_without_gpu():
 
 def test_conv_desc_matches_header_layout():
     d = _lib.ConvDesc()
-    assert ctypes.sizeof(d) == 7 * 8 + 4 * 8 + 4 * 8 + 4 * 8 + 11 * 4 + 4   # 8-byte aligned tail pad
+    # 7 pointers, 3 x (pointer + 3 strides), 11 int32 (+4 pad), 3 int64 out strides, 2 int32
+    assert ctypes.sizeof(d) == 7 * 8 + 4 * 8 + 4 * 8 + 4 * 8 + 11 * 4 + 4 + 3 * 8 + 2 * 4
     assert _lib.ConvDesc.N.offset == 152 and _lib.ConvDesc.mode.offset == 184
     assert _lib.ConvDesc.wlayout.offset == 188 and _lib.ConvDesc.flip_y.offset == 192
+    assert _lib.ConvDesc.out_spx.offset == 200 and _lib.ConvDesc.out_sn.offset == 216
+    assert _lib.ConvDesc.lq_up4.offset == 224 and _lib.ConvDesc.wpack_stable.offset == 228
 
 
 # ------------------------------------------------------------------ registry / boundary
@@ -74,7 +77,12 @@ def test_registry_builds_generator_and_state_dict_layout():
     net.load_state_dict(weights.random_state_dict(0), strict=True)
     with pytest.raises(KeyError):
         P.build_backbone(dict(CFG, type="NoSuchBackbone"))
-    for bad in (dict(vsr=True), dict(blocktype="sft"), dict(with_se=False), dict(deform="fvc"),
+    # vsr=True (x4 tail) is supported: two PixelShufflePack holders with the reference's key names
+    vsr_net = P.build_backbone(dict(CFG, vsr=True))
+    vsr_shapes = weights.state_dict_shapes(vsr=True)
+    assert {k: tuple(v.shape) for k, v in vsr_net.state_dict().items()} == vsr_shapes
+    assert set(vsr_shapes) - set(shapes) == {f"upsample{i}.upsample_conv.{p}" for i in (1, 2) for p in ("weight", "bias")}
+    for bad in (dict(blocktype="sft"), dict(with_se=False), dict(deform="fvc"),
                 dict(sparse_val=True), dict(mid_channels=32)):
         with pytest.raises(NotImplementedError):
             P.build_backbone(dict(CFG, **bad))
