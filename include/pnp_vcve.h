@@ -177,6 +177,9 @@ typedef struct pnp_conv_desc {
   int32_t lq_up4;      /* PNP_CONV_LAST: 1 = `lq` is the (N,3,H/4,W/4) low-resolution frame and the epilogue adds its
                           x4 bilinear upsampling (nn.Upsample(scale_factor=4, mode='bilinear', align_corners=False),
                           iconvsr_ipb_par.py:41,140-141) instead of lq itself; row-stacked layout only */
+  int32_t par_sparse;  /* 1: the reference's eval-mode sparse_val=True path (sr_backbone_utils.py:294-302): the 1x1 conv of
+                          the LAST partition class whose map is non-zero at the pixel, divided by 255 -- the
+                          map's value is not used.  0: dense sum_k par_k * conv1x1_k(src). */
   int32_t wpack_stable; /* 1: wpack was NOT written by the operation immediately preceding this launch in the stream
                           (weights are packed once per checkpoint / clip, long before the frame loop), so the
                           kernel may fetch it while the previous kernel is still draining (programmatic dependent

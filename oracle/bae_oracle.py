@@ -195,22 +195,41 @@ def dynamic_conv_se(x, weight, bias, w_experts, gamma):
     return out * gamma.view(1, -1, 1, 1)
 
 
-def bae_block(sd, prefix, x, par, w_experts, gamma):
-    """ResidualBlockNoBNDynamic_drt.forward (channel_first, one_layer, with_se, dense par).
+def sparse_dyres(sd, prefix, x, par):
+    """ResidualBlockNoBNDynamic_drt.sparse_conv (sr_backbone_utils.py:294-302) with the index lists of
+    generate_indices(..., 1) (basicvsr_net.py:456-466, :511-514): for every partition class the 1x1 conv is
+    evaluated only at the pixels whose mask is NON-ZERO (gather -> mm -> scatter), scattered results
+    OVERWRITE each other in the order 16x16, 16x8, 8x8, and the sum is divided by 255 -- the mask VALUE
+    is never used.  x (1,64,h,w), par (1,3,1,h,w)."""
+    dyres = torch.zeros_like(x)
+    for k, name in enumerate(("conv16x16", "conv16x8", "conv8x8")):
+        idx = torch.nonzero(par[:, k].squeeze())                 # (m, 2) row-major pixel list
+        hi, wi = idx[:, 0], idx[:, 1]
+        roi = x[0, :, hi, wi]                                    # mask_roi: (64, m)
+        dyres[0, :, hi, wi] = torch.mm(sd[prefix + name + ".weight"].view(64, -1), roi)   # mask_roi_back
+    return dyres / 255
+
+
+def bae_block(sd, prefix, x, par, w_experts, gamma, sparse=False):
+    """ResidualBlockNoBNDynamic_drt.forward (channel_first, one_layer, with_se; dense par, or the
+    eval-mode sparse_val=True path).
 
     sr_backbone_utils.py:304-333.  x (1,64,h,w), par (1,3,1,h,w).
     """
     identity = x
-    dyres = (F.conv2d(x, sd[prefix + "conv16x16.weight"]) * par[:, 0]
-             + F.conv2d(x, sd[prefix + "conv16x8.weight"]) * par[:, 1]
-             + F.conv2d(x, sd[prefix + "conv8x8.weight"]) * par[:, 2])
+    if sparse:
+        dyres = sparse_dyres(sd, prefix, x, par)
+    else:
+        dyres = (F.conv2d(x, sd[prefix + "conv16x16.weight"]) * par[:, 0]
+                 + F.conv2d(x, sd[prefix + "conv16x8.weight"]) * par[:, 1]
+                 + F.conv2d(x, sd[prefix + "conv8x8.weight"]) * par[:, 2])
     t = dynamic_conv_se(x, sd[prefix + "conv2.weight"], sd[prefix + "conv2.bias"], w_experts, gamma)
     out = F.relu(t + dyres)
     out = F.conv2d(out, sd[prefix + "conv1.weight"], sd[prefix + "conv1.bias"], padding=1)
     return identity + out * 1.0
 
 
-def resblocks(sd, branch, x_in, par, w_experts, gamma, num_blocks=NUM_BLOCKS):
+def resblocks(sd, branch, x_in, par, w_experts, gamma, num_blocks=NUM_BLOCKS, sparse=False):
     """ResidualBlocksWithInputConvDynamic_drt.forward, basicvsr_net.py:506-519.
 
     x_in (1,131|195,h,w); par (1,3,h,w) -> viewed (1,3,1,h,w); returns (1,64,h,w).
@@ -221,7 +240,7 @@ def resblocks(sd, branch, x_in, par, w_experts, gamma, num_blocks=NUM_BLOCKS):
     x = F.leaky_relu(F.conv2d(x_in, sd[p + "input_conv.0.weight"], sd[p + "input_conv.0.bias"],
                               padding=1), negative_slope=0.1)
     for k in range(num_blocks):
-        x = bae_block(sd, f"{p}main.{k}.", x, par5, w_experts, gamma)
+        x = bae_block(sd, f"{p}main.{k}.", x, par5, w_experts, gamma, sparse)
     return x
 
 
@@ -230,7 +249,7 @@ def resblocks(sd, branch, x_in, par, w_experts, gamma, num_blocks=NUM_BLOCKS):
 # --------------------------------------------------------------------------------------
 @torch.no_grad()
 def generator_forward(sd, lrs, QPs, slices, mvs, base_QPs, par_map, num_blocks=NUM_BLOCKS,
-                      return_features=False, vsr=False):
+                      return_features=False, vsr=False, sparse_val=False):
     """IconVSR_restore_wo_refill_mv_ipb_fast_domain_dynamic_with_par.forward
 
     iconvsr_ipb_par.py:44-149 with the config kwargs of configs/HR_davis_LR_128x128.py:6-25
@@ -269,7 +288,7 @@ def generator_forward(sd, lrs, QPs, slices, mvs, base_QPs, par_map, num_blocks=N
                 key_warp, neighbor = zeros, zeros
             feat = torch.cat([lr, key_warp, neighbor], dim=1)
             outputs[b][i] = resblocks(sd, "backward", feat, par_map[b:b + 1, i], experts[b, i],
-                                      gammas[b, i], num_blocks)
+                                      gammas[b, i], num_blocks, sparse_val)
     bwd_feats = [[o.clone() for o in row] for row in outputs] if return_features else None
     outs = []
     for b in range(n):
@@ -287,7 +306,7 @@ def generator_forward(sd, lrs, QPs, slices, mvs, base_QPs, par_map, num_blocks=N
                 key_warp, neighbor = zeros, zeros
             feat = torch.cat([lr, key_warp, neighbor, outputs[b][i]], dim=1)
             x = resblocks(sd, "forward", feat, par_map[b:b + 1, i], experts[b, i], gammas[b, i],
-                          num_blocks)
+                          num_blocks, sparse_val)
             outputs[b][i] = x
             if vsr:                                   # x4 tail, :135-142 (PixelShufflePack: common/upsample.py:46-49)
                 o = x

@@ -39,7 +39,7 @@ class ConvDesc(_c.Structure):
         ("n_wchunks", _c.c_int32), ("center_n", _c.c_int32), ("tap_n", _c.c_int32),
         ("aux_k16", _c.c_int32), ("act", _c.c_int32), ("mode", _c.c_int32),
         ("wlayout", _c.c_int32), ("flip_y", _c.c_int32),
-        ("out_spx", _i64), ("out_sy", _i64), ("out_sn", _i64), ("lq_up4", _c.c_int32), ("wpack_stable", _c.c_int32),
+        ("out_spx", _i64), ("out_sy", _i64), ("out_sn", _i64), ("lq_up4", _c.c_int32), ("par_sparse", _c.c_int32), ("wpack_stable", _c.c_int32),
     ]
 
 

@@ -98,7 +98,7 @@ class _PixelShufflePack(_Holder):
 
 
 _REQUIRED = dict(mid_channels=64, num_group=1, expert_softmax=True, use_base_qp=True, with_bias=True,
-                 with_se=True, one_layer=True, blocktype="drt", channel_first=True, sparse_val=False,
+                 with_se=True, one_layer=True, blocktype="drt", channel_first=True,
                  align_key=True, with_cat=True, deform="vos", flow_inter="bilinear")
 
 
@@ -122,7 +122,7 @@ class IconVSR_restore_wo_refill_mv_ipb_fast_domain_dynamic_with_par(nn.Module):
         given = dict(mid_channels=mid_channels, num_group=num_group, expert_softmax=expert_softmax,
                      use_base_qp=use_base_qp, with_bias=with_bias, with_se=with_se,
                      one_layer=one_layer, blocktype=blocktype, channel_first=channel_first,
-                     sparse_val=sparse_val, align_key=align_key, with_cat=with_cat,
+                     align_key=align_key, with_cat=with_cat,
                      deform=deform, flow_inter=flow_inter)
         bad = {k: v for k, v in given.items() if v != _REQUIRED[k]}
         if bad:
@@ -139,6 +139,10 @@ class IconVSR_restore_wo_refill_mv_ipb_fast_domain_dynamic_with_par(nn.Module):
         self.flow_inter = flow_inter
         self.with_cat, self.use_base_qp, self.with_bias = with_cat, use_base_qp, with_bias
         self.with_par, self.vsr, self.align_key = with_par, vsr, align_key
+        #: the reference's eval-mode "sparse conv" (sr_backbone_utils.py:294-302,307-308): per pixel the 1x1 conv of the
+        #: last partition class with a non-zero mask, / 255.  Defined per image (the reference's index lists only
+        #: work for n == 1: basicvsr_net.py:458 squeezes the batch away).
+        self.sparse_val = bool(sparse_val)
         self.is_mirror_extended = False
 
         self.BiasePredictor = _GainPredictor(mid_channels)

@@ -101,8 +101,8 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 extern "C" {
 
-static_assert(sizeof(pnp_conv_desc) == 232 && offsetof(pnp_conv_desc, out_spx) == 200 &&
-                  offsetof(pnp_conv_desc, wpack_stable) == 228,
+static_assert(sizeof(pnp_conv_desc) == 240 && offsetof(pnp_conv_desc, out_spx) == 200 &&
+                  offsetof(pnp_conv_desc, wpack_stable) == 232,
               "pnp_conv_desc layout is part of the ABI (mirrored by pnpvcve_b200/_lib.py: ConvDesc)");
 int pnp_abi_version(void) { return 6; }
 
@@ -326,6 +326,7 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   p.flip_y = (rowstack && c->flip_y) ? 1 : 0;
   p.w_stable = c->wpack_stable ? 1 : 0;
   p.lq_up4 = c->lq_up4 ? 1 : 0;
+  p.par_sparse = (c->par && c->par_sparse) ? 1 : 0;
   p.base_off_mode = g_base_off_mode;
   {
     const char* dbg = getenv("PNP_DEBUG_SKIP");   // what-if profiling only; results are wrong when set

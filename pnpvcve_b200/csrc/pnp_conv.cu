@@ -413,6 +413,7 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
         p0 = __ldg(pp);
         p1 = __ldg(pp + p.par_sc);
         p2 = __ldg(pp + 2 * p.par_sc);
+        if (p.par_sparse) par_sparse_select(p0, p1, p2);
       }
       const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && it < 64 && threadIdx.x == 64;
       if (tr) p.trace[it * 8 + 2] = clock64();
@@ -457,9 +458,13 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             v[j] = kScale ? fmaf(v[j], scale_r[gg * 16 + j], bias_r[gg * 16 + j]) : v[j] + bias_r[gg * 16 + j];
-            v[j] = fmaf(p0, a1[j], v[j]);
-            v[j] = fmaf(p1, a2[j], v[j]);
-            v[j] = fmaf(p2, a3[j], v[j]);
+            if (p.par_sparse) {             // exactly one selector is 1 (or none): W_k x / 255, true division
+              v[j] += __fdiv_rn(p0 * a1[j] + p1 * a2[j] + p2 * a3[j], 255.0f);
+            } else {
+              v[j] = fmaf(p0, a1[j], v[j]);
+              v[j] = fmaf(p1, a2[j], v[j]);
+              v[j] = fmaf(p2, a3[j], v[j]);
+            }
           }
         } else {
           tmem_ld_wait();

@@ -46,6 +46,7 @@ struct ConvParams {
   int act;
   int mode;
   int flip_y;           // row-stacked kernel: walk the image bottom-up (weights packed with ky mirrored)
+  int par_sparse;       // partition blend: last non-zero class only, / 255 (the reference's sparse_val eval path)
   int lq_up4;           // kModeLast: lq is the (H/4, W/4) frame, the epilogue adds its x4 bilinear upsampling
   int w_stable;         // weights may be fetched before the previous kernel in the stream has completed
   int s_a;              // A ring slots
@@ -54,6 +55,16 @@ struct ConvParams {
   int debug_skip;        // what-if profiling bits (results are WRONG): 1 skip row loads, 2 skip output staging/store, 4 skip TMEM loads
   int base_off_mode;    // 0: descriptor base_offset = 0 (measured-correct on B200); 1: (addr>>7)&7
 };
+
+// sparse_val eval path of the reference (sr_backbone_utils.py:294-302, basicvsr_net.py:511-514): per class the
+// 1x1 result is scattered to the pixels whose mask is non-zero, later classes overwrite earlier ones.  Turns the
+// three map values into 0/1 selectors of the surviving class.
+__device__ __forceinline__ void par_sparse_select(float& p0, float& p1, float& p2) {
+  const bool n2 = p2 != 0.f, n1 = p1 != 0.f, n0 = p0 != 0.f;
+  p2 = n2 ? 1.f : 0.f;
+  p1 = (!n2 && n1) ? 1.f : 0.f;
+  p0 = (!n2 && !n1 && n0) ? 1.f : 0.f;
+}
 
 size_t conv_smem_bytes(const ConvParams& p);
 cudaError_t launch_conv(const ConvParams& p, int grid, cudaStream_t stream);

@@ -65,6 +65,7 @@ class _Launcher:
         self.ref = ctypes.byref(self.desc)
         self.prof = prof          # None or {label: [(start_event, end_event), ...]}
         self.rows_par = False     # block launch A on the row-stacked kernel (weights packed accordingly)
+        self.par_sparse = False   # sparse_val=True: last non-zero partition class only, / 255
         self.prof_every = max(int(prof_every), 1)
         self.seen = {}
 
@@ -76,7 +77,7 @@ class _Launcher:
         # right before a conv is always lr_im2col, the warp or another conv)
         ops.fill_conv_desc(self.desc, src, wpack, out, aux, idt, scale, bias, par, act, lq, outf,
                            wlayout=0 if (par is not None and not self.rows_par) else 1, flip_y=flip_y,
-                           wpack_stable=True, lq_up4=lq_up4)
+                           wpack_stable=True, lq_up4=lq_up4, par_sparse=self.par_sparse)
         timed = self.prof is not None and label in self.prof
         if timed:                                  # bracket every prof_every-th launch of this label
             k = self.seen.get(label, 0)
@@ -371,6 +372,7 @@ class BaeEngine:
             conv = buf["launcher"]
             conv.prof, conv.prof_every, conv.seen = prof, self.prof_every, seen
             conv.rows_par = self.rows_par
+            conv.par_sparse = bool(m.sparse_val)
             stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
             def warp(src, flow, dst):
@@ -394,6 +396,8 @@ class BaeEngine:
                 par = par_map[b0:b1, i]
                 other = buf["xb"] if x is buf["xa"] else buf["xa"]
                 if self.fused_block:
+                    if m.sparse_val:
+                        raise NotImplementedError("PNP_FUSED_BLOCK has no sparse_val path; unset it")
                     for k in range(nb):
                         o = dst if k == nb - 1 else other
                         conv.block(stream, x, o, mixed[name][k], st[name + "_conv1_dn"][k],

@@ -168,7 +168,7 @@ def mix_bias(conv2_bias, experts, gamma):
 
 def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
                    act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False, wpack_stable=False,
-                   lq_up4=False):
+                   lq_up4=False, par_sparse=False):
     """Fill a ConvDesc in place (reusable across launches).  `out` may be a strided (N,H,W,64) view with
     unit channel stride (e.g. up[:, i::2, j::2, :]: pixel shuffle as the store epilogue)."""
     n, h, w, _ = src.shape
@@ -181,6 +181,7 @@ def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias
     else:
         d.out_sn = d.out_sy = d.out_spx = 0
     d.lq_up4 = 1 if lq_up4 else 0
+    d.par_sparse = 1 if (par_sparse and par is not None) else 0
     d.wpack = wpack.data_ptr()
     d.scale = scale.data_ptr() if scale is not None else None
     d.bias = bias.data_ptr() if bias is not None else None
@@ -208,7 +209,8 @@ def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias
 
 
 def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
-            act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False, wpack_stable=False, lq_up4=False):
+            act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False, wpack_stable=False, lq_up4=False,
+            par_sparse=False):
     """Fused tcgen05 3x3 conv (see include/pnp_vcve.h: pnp_conv3x3).  `out` may be a strided view with unit
     channel stride (pixel shuffle as the store epilogue); lq_up4: lq is the (N,3,H/4,W/4) frame whose x4
     bilinear upsampling is added."""
@@ -227,7 +229,7 @@ def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par
             if t.dim() != 4 or t.shape[1] != 3 or t.shape[0] != src.shape[0] or tuple(t.shape[2:]) != hw:
                 raise ValueError(f"conv3x3: {nm} must be (N,3,H,W) matching src" + (" / 4" if hw[0] != src.shape[1] else ""))
     d = fill_conv_desc(ConvDesc(), src, wpack, out, aux, idt, scale, bias, par, act, lq, outf, wlayout, flip_y,
-                       wpack_stable, lq_up4)
+                       wpack_stable, lq_up4, par_sparse)
     need = rowstack_bytes(d.tap_n, aux is not None, par is not None) if wlayout == 1 \
         else d.n_wchunks * CHUNK_BYTES
     if wpack.numel() < need:

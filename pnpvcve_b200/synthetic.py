@@ -67,6 +67,20 @@ def make_clip(h, w, t, seed, crf=25, mv_qpel=64, ipb=False, pattern="IBBP", devi
     return dict(lq=lq, QPs=qps, slices=slices, mvs=mvs, base_QPs=base, partitions=par)
 
 
+def overlap_partitions(clip, seed, block=8):
+    """Make the partition maps overlap and carry other values than 1/255 (in place): the dense path uses the
+    VALUES, the reference's sparse_val path only whether they are non-zero and which class comes last."""
+    par = clip["partitions"]
+    n, t, _, h, w = par.shape
+    g = torch.Generator().manual_seed(int(seed))
+    hb, wb = (h + block - 1) // block, (w + block - 1) // block
+    extra = (torch.rand((n, t, 3, hb, wb), generator=g) > 0.6).float() * \
+        torch.randint(1, 4, (n, t, 3, hb, wb), generator=g).float() / 255.0
+    extra = extra.repeat_interleave(block, dim=3).repeat_interleave(block, dim=4)[..., :h, :w]
+    clip["partitions"] = (par + extra.to(par.device)).contiguous()
+    return clip
+
+
 def make_config_clip(name, clip_idx=0, t=None, crf=25, device="cpu", pattern=None):
     c = CONFIGS[name]
     pat = pattern or ("IP" if name == "C5" else "IBBP")

@@ -43,6 +43,12 @@ CASES = {
     "edge_68x132_t3": dict(weight_seed=5, num_blocks=8, clips=[
         dict(h=68, w=132, t=3, seed=3400, crf=15, mv_qpel=64, ipb=True, pattern="IBBP")]),
     # vsr=True: PixelShufflePack x2 + bilinear x4 base tail (iconvsr_ipb_par.py:36-41,135-142); output is 4H x 4W
+    # sparse_val=True eval path (sr_backbone_utils.py:294-302) on overlapping, non-1/255 partition maps; and the
+    # dense path on the same maps (the values matter there)
+    "sparse_64x64_t3": dict(weight_seed=7, num_blocks=8, sparse_val=True, par_overlap=77, clips=[
+        dict(h=64, w=64, t=3, seed=3600, crf=35, mv_qpel=32, ipb=True, pattern="IBBP")]),
+    "densepar_64x64_t3": dict(weight_seed=7, num_blocks=8, par_overlap=77, clips=[
+        dict(h=64, w=64, t=3, seed=3600, crf=35, mv_qpel=32, ipb=True, pattern="IBBP")]),
     "vsr_64x96_t3": dict(weight_seed=6, num_blocks=8, vsr=True, clips=[
         dict(h=64, w=96, t=3, seed=3500, crf=25, mv_qpel=32, ipb=True, pattern="IBBP")]),
 }
@@ -51,6 +57,8 @@ CASES = {
 def build_inputs(case):
     clips = [synthetic.make_clip(**kw) for kw in case["clips"]]
     clip = synthetic.cat_clips(clips)
+    if case.get("par_overlap"):
+        synthetic.overlap_partitions(clip, case["par_overlap"])
     if case.get("mirror"):
         # even-T exact mirror: frame i == frame t-1-i (iconvsr.py:396-410)
         t = clip["lq"].shape[1]
@@ -71,7 +79,8 @@ def main():
         if only and name not in only:
             continue
         vsr = bool(case.get("vsr", False))
-        net = refshim.build_reference(seed=0, num_blocks=case["num_blocks"], vsr=vsr)
+        net = refshim.build_reference(seed=0, num_blocks=case["num_blocks"], vsr=vsr,
+                                      sparse_val=bool(case.get("sparse_val", False)))
         sd = weights.random_state_dict(case["weight_seed"], num_blocks=case["num_blocks"], vsr=vsr)
         net.load_state_dict(sd, strict=True)
         clip = build_inputs(case)

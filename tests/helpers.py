@@ -20,6 +20,8 @@ def build_case(name):
     case = golden_cases()[name]
     clips = [synthetic.make_clip(**kw) for kw in case["clips"]]
     clip = synthetic.cat_clips(clips)
+    if case.get("par_overlap"):
+        synthetic.overlap_partitions(clip, case["par_overlap"])
     if case.get("mirror"):
         t = clip["lq"].shape[1]
         half = clip["lq"][:, : t // 2]

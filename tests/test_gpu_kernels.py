@@ -304,6 +304,46 @@ def test_conv_rowstack_bottom_up_equals_top_down(dev, n, h, w):
     assert (o1 - ref).abs().max().item() < 1e-4 and (o2 - ref).abs().max().item() < 1e-4
 
 
+# ------------------------------------------------------------------ sparse_val partition path
+@pytest.mark.parametrize("layout", [0, 1], ids=["tapmajor", "rowstack"])
+def test_conv_par_sparse_selects_last_nonzero_class(dev, layout):
+    """sparse_val eval path (sr_backbone_utils.py:294-302): W_k x / 255 of the LAST class whose map is non-zero,
+    whatever the map's value; pixels with all-zero maps get nothing.  1x1 weights are large here so that the
+    term is O(1) and a wrong class / a dense blend would be far outside the tolerance."""
+    n, h, w = 2, 40, 136
+    g = torch.Generator(device=dev).manual_seed(11)
+    x = bf(torch.randn((n, 64, h, w), generator=g, device=dev))
+    wt = bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05)
+    w1 = [bf(torch.randn((64, 64), generator=g, device=dev) * 20.0) for _ in range(3)]
+    bias = torch.randn(64, generator=g, device=dev) * 0.1
+    par = (torch.rand((n, 3, h, w), generator=g, device=dev) > 0.6).float() * \
+        torch.randint(1, 4, (n, 3, h, w), generator=g, device=dev).float() / 255.0
+    if layout == 0:
+        wpp = ops.new_wpack(12, dev)
+        ops.pack_conv3x3(wt, wpp, center_chunks=4)
+        for j in range(3):
+            ops.pack_rows(w1[j], wpp, 64 * (j + 1))
+    else:
+        wpp = ops.new_wpack_rowstack(dev, with_par=True)
+        ops.pack_conv3x3_rowstack(wt, wpp)
+        for j in range(3):
+            ops.pack_rows(w1[j], wpp[9 * ops.CHUNK_BYTES:], 64 * j)
+    out = ops.new_feature(n, h, w, dev)
+    ops.conv3x3(nhwc(x), wpp, out=out, bias=bias, par=par, act=ops.PNP_ACT_NONE, wlayout=layout, par_sparse=True)
+    dy = torch.zeros_like(x)
+    for j in range(3):                                   # later classes overwrite earlier ones
+        m = (par[:, j:j + 1] != 0)
+        dy = torch.where(m, F.conv2d(x, w1[j].view(64, 64, 1, 1)), dy)
+    dy = dy / 255
+    ref = F.conv2d(x, wt, bias, padding=1) + dy
+    assert dy.abs().mean().item() > 0.1                  # the term under test is not negligible
+    extra = dy.abs() * 2.0 ** -8 if layout == 1 else None
+    assert_bf16_close(nchw(out), ref, "par_sparse", extra)
+    # and it is NOT what the dense blend gives on these maps
+    ops.conv3x3(nhwc(x), wpp, out=out, bias=bias, par=par, act=ops.PNP_ACT_NONE, wlayout=layout)
+    assert (nchw(out) - ref).abs().max().item() > 0.05
+
+
 # ------------------------------------------------------------------ x4 tail epilogues (vsr=True)
 @pytest.mark.parametrize("n,h,w", [(1, 64, 64), (2, 36, 132)])
 def test_pixel_shuffle_store_and_bilinear_base_epilogues(dev, n, h, w):

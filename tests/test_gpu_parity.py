@@ -49,7 +49,8 @@ CASES = [c for c in golden_cases() if c != "warp_720p"]
 @pytest.mark.parametrize("name", CASES)
 def test_generator_matches_reference_golden(dev, name):
     sd, clip, gold = build_case(name)
-    net = build(sd, dev, vsr=bool(golden_cases()[name].get("vsr")))
+    case = golden_cases()[name]
+    net = build(sd, dev, vsr=bool(case.get("vsr")), sparse_val=bool(case.get("sparse_val")))
     out = run(net, clip, dev)
     assert out.dtype == torch.float32 and out.is_cuda
     err = check_against_golden(out, gold, tol=TOL)
@@ -163,6 +164,6 @@ def test_generator_reflect_padding_and_size_errors(dev):
 
 def test_unsupported_kwargs_raise():
     with pytest.raises(NotImplementedError):
-        P.build_backbone(dict(GENERATOR_CFG, sparse_val=True))
+        P.build_backbone(dict(GENERATOR_CFG, with_se=False))
     with pytest.raises(NotImplementedError):
         P.build_backbone(dict(GENERATOR_CFG, blocktype="sft"))

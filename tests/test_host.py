@@ -57,11 +57,12 @@ def test_abi_argument_errors_without_gpu():
 def test_conv_desc_matches_header_layout():
     d = _lib.ConvDesc()
     # 7 pointers, 3 x (pointer + 3 strides), 11 int32 (+4 pad), 3 int64 out strides, 2 int32
-    assert ctypes.sizeof(d) == 7 * 8 + 4 * 8 + 4 * 8 + 4 * 8 + 11 * 4 + 4 + 3 * 8 + 2 * 4
+    assert ctypes.sizeof(d) == 7 * 8 + 4 * 8 + 4 * 8 + 4 * 8 + 11 * 4 + 4 + 3 * 8 + 3 * 4 + 4
     assert _lib.ConvDesc.N.offset == 152 and _lib.ConvDesc.mode.offset == 184
     assert _lib.ConvDesc.wlayout.offset == 188 and _lib.ConvDesc.flip_y.offset == 192
     assert _lib.ConvDesc.out_spx.offset == 200 and _lib.ConvDesc.out_sn.offset == 216
-    assert _lib.ConvDesc.lq_up4.offset == 224 and _lib.ConvDesc.wpack_stable.offset == 228
+    assert _lib.ConvDesc.lq_up4.offset == 224 and _lib.ConvDesc.par_sparse.offset == 228
+    assert _lib.ConvDesc.wpack_stable.offset == 232
 
 
 # ------------------------------------------------------------------ registry / boundary
@@ -83,7 +84,7 @@ def test_registry_builds_generator_and_state_dict_layout():
     assert {k: tuple(v.shape) for k, v in vsr_net.state_dict().items()} == vsr_shapes
     assert set(vsr_shapes) - set(shapes) == {f"upsample{i}.upsample_conv.{p}" for i in (1, 2) for p in ("weight", "bias")}
     for bad in (dict(blocktype="sft"), dict(with_se=False), dict(deform="fvc"),
-                dict(sparse_val=True), dict(mid_channels=32)):
+                dict(one_layer=False), dict(mid_channels=32)):
         with pytest.raises(NotImplementedError):
             P.build_backbone(dict(CFG, **bad))
 

@@ -16,7 +16,9 @@ CASES = [c for c in golden_cases() if c != "warp_720p"]
 @pytest.mark.parametrize("name", CASES)
 def test_oracle_matches_reference_golden(name):
     sd, clip, gold = build_case(name)
-    out = O.generator_forward(sd, *synthetic.generator_args(clip), vsr=bool(golden_cases()[name].get("vsr")))
+    case = golden_cases()[name]
+    out = O.generator_forward(sd, *synthetic.generator_args(clip), vsr=bool(case.get("vsr")),
+                              sparse_val=bool(case.get("sparse_val")))
     err = check_against_golden(out, gold, tol=2e-6)
     assert err < 2e-6
 
