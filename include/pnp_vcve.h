@@ -128,6 +128,24 @@ int pnp_mv_rasterize(const float* records, const int32_t* frame_offsets, const i
                      int32_t* status, void* stream);
 
 /*
+ * Per-frame quality metrics of the reference's test loop, computed where the frames are ("next" row of the scope
+ * table): BasicVSR.evaluate (mmedit/models/restorers/basicvsr.py:119-153) copies every frame to the host, quantises
+ * it with tensor2img (mmedit/core/misc.py:9-74: clamp [0,1], x255, round half to even, uint8) and calls psnr / ssim
+ * (mmedit/core/evaluation/metrics.py:170-215, 262-355; convert_to=None).
+ *   a, b        : fp32 (F,3,H,W) views, unit x stride; *_sf/_sc/_sy = frame / channel / row strides in elements
+ *   sse[F]      : EXACT integer sum over the cropped frame and the 3 channels of (a8 - b8)^2;
+ *                 psnr = 20 log10(255 / sqrt(sse / (3 (H-2c) (W-2c)))), +inf when sse == 0
+ *   ssim_sum[3F]: float64 sum of the SSIM map (11x11 Gaussian window, sigma 1.5, valid positions of the cropped frame)
+ *                 of channel k at [3 f + k]; ssim = mean_k(sum_k / ((H-2c-10) (W-2c-10))).  Reference quirk, kept: with
+ *                 crop_border != 0 only the first channel of the BGR image -- input channel 2 -- is evaluated
+ *                 (metrics.py:347-352 index with a trailing None), and only [3 f] is written.
+ * Both outputs are zeroed by the call.  H - 2 crop_border and W - 2 crop_border must be >= 11.
+ */
+int pnp_frame_quality(const float* a, int64_t a_sf, int64_t a_sc, int64_t a_sy, const float* b, int64_t b_sf,
+                      int64_t b_sc, int64_t b_sy, int F, int H, int W, int crop_border, unsigned long long* sse,
+                      double* ssim_sum, void* stream);
+
+/*
  * K2/K3/K5 -- fused 3x3 convolution on tcgen05 tensor cores (implicit GEMM, TMA fed, TMEM
  * accumulators).  One call replaces one F.conv2d of the reference plus the elementwise work
  * around it:

@@ -20,7 +20,7 @@ EXPORTS = [
     "pnp_abi_version", "pnp_last_error", "pnp_device_check", "pnp_set_base_offset_mode",
     "pnp_mv_warp", "pnp_lr_im2col", "pnp_pack_conv3x3", "pnp_pack_conv3x3_rowstack", "pnp_pack_rows",
     "pnp_pack_aux",
-    "pnp_caa_heads", "pnp_mix_bias", "pnp_mv_rasterize", "pnp_conv3x3", "pnp_resblock",
+    "pnp_caa_heads", "pnp_mix_bias", "pnp_mv_rasterize", "pnp_conv3x3", "pnp_resblock", "pnp_frame_quality",
 ]
 
 _c = ctypes
@@ -68,6 +68,7 @@ _PROTOS = {
     "pnp_mv_rasterize": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pnp_conv3x3": (_i, [_c.POINTER(ConvDesc), _vp]),
     "pnp_resblock": (_i, [_c.POINTER(BlockDesc), _vp]),
+    "pnp_frame_quality": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -1,4 +1,5 @@
 // extern "C" surface of libpnpvcve.so (declared in include/pnp_vcve.h).
+#include <cmath>
 #include <cstddef>
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -248,6 +249,29 @@ int pnp_mv_rasterize(const float* records, const int32_t* frame_offsets, const i
   cudaError_t e = pnp::launch_mv_rasterize(records, frame_offsets, is_b, p_target, T, R, H, W, owner_fwd, owner_bwd,
                                            part_mask, mvs, partitions, status, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_mv_rasterize");
+}
+
+int pnp_frame_quality(const float* a, int64_t a_sf, int64_t a_sc, int64_t a_sy, const float* b, int64_t b_sf,
+                      int64_t b_sc, int64_t b_sy, int F, int H, int W, int crop_border, unsigned long long* sse,
+                      double* ssim_sum, void* stream) {
+  if (!a || !b || !sse || !ssim_sum) return fail(PNP_ERR_ARG, "pnp_frame_quality: null pointer");
+  if (F < 1 || crop_border < 0 || H - 2 * crop_border < 11 || W - 2 * crop_border < 11)
+    return fail(PNP_ERR_ARG, "pnp_frame_quality: the cropped frame must be at least 11 x 11");
+  if ((long long)F * 3 > 65535) return fail(PNP_ERR_ARG, "pnp_frame_quality: at most 21845 frames per call");
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  // cv2.getGaussianKernel(11, 1.5): exp(-(i-5)^2 / (2 sigma^2)), normalised to sum 1 (float64)
+  double g[11], s = 0.0;
+  for (int i = 0; i < 11; ++i) {
+    g[i] = exp(-((double)(i - 5) * (i - 5)) / (2.0 * 1.5 * 1.5));
+    s += g[i];
+  }
+  for (int i = 0; i < 11; ++i) g[i] /= s;
+  const int ch_first = crop_border != 0 ? 2 : 0, n_ch = crop_border != 0 ? 1 : 3;
+  cudaError_t e = pnp::launch_frame_quality(a, a_sf, a_sc, a_sy, b, b_sf, b_sc, b_sy, F, H, W, crop_border, ch_first,
+                                            n_ch, g, sse, ssim_sum, d->sms, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_frame_quality");
 }
 
 int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {

@@ -458,13 +458,9 @@ conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             v[j] = kScale ? fmaf(v[j], scale_r[gg * 16 + j], bias_r[gg * 16 + j]) : v[j] + bias_r[gg * 16 + j];
-            if (p.par_sparse) {             // exactly one selector is 1 (or none): W_k x / 255, true division
-              v[j] += __fdiv_rn(p0 * a1[j] + p1 * a2[j] + p2 * a3[j], 255.0f);
-            } else {
-              v[j] = fmaf(p0, a1[j], v[j]);
-              v[j] = fmaf(p1, a2[j], v[j]);
-              v[j] = fmaf(p2, a3[j], v[j]);
-            }
+            v[j] = fmaf(p0, a1[j], v[j]);
+            v[j] = fmaf(p1, a2[j], v[j]);
+            v[j] = fmaf(p2, a3[j], v[j]);
           }
         } else {
           tmem_ld_wait();

@@ -491,17 +491,10 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         tmem_ld16(lane_base + col + 128, a3);
         tmem_ld_wait();
         uint32_t w[8];
-        if (p.par_sparse) {                // at most one selector is 1: W_k x / 255, true division like the reference
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            w[j] = pack_bf16x2(__fdiv_rn(q2 * a3[2 * j] + q1 * a2[2 * j] + q0 * a1[2 * j], 255.0f),
-                               __fdiv_rn(q2 * a3[2 * j + 1] + q1 * a2[2 * j + 1] + q0 * a1[2 * j + 1], 255.0f));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            w[j] = pack_bf16x2(fmaf(q2, a3[2 * j], fmaf(q1, a2[2 * j], q0 * a1[2 * j])),
-                               fmaf(q2, a3[2 * j + 1], fmaf(q1, a2[2 * j + 1], q0 * a1[2 * j + 1])));
-        }
+        for (int j = 0; j < 8; ++j)
+          w[j] = pack_bf16x2(fmaf(q2, a3[2 * j], fmaf(q1, a2[2 * j], q0 * a1[2 * j])),
+                             fmaf(q2, a3[2 * j + 1], fmaf(q1, a2[2 * j + 1], q0 * a1[2 * j + 1])));
         const int g = half * 2 + gg;
         *reinterpret_cast<uint4*>(slot_row + (((2 * g) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<uint4*>(slot_row + (((2 * g + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
@@ -515,7 +508,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         q0 = __ldg(pp);
         q1 = __ldg(pp + p.par_sc);
         q2 = __ldg(pp + 2 * p.par_sc);
-        if (p.par_sparse) par_sparse_select(q0, q1, q2);   // 0/1 selector of the surviving class
+        if (p.par_sparse) par_sparse_select(q0, q1, q2);   // 1/255 for the surviving class, 0 for the others
       }
     };
     // partition values are fetched TWO rows ahead: the epilogue is the hand-back path of the single 1x1

@@ -30,6 +30,11 @@ cudaError_t launch_mix_bias(const float* conv2_bias, long long block_stride, int
                             const float* experts, const float* gamma, int frames, float* out,
                             cudaStream_t stream);
 
+cudaError_t launch_frame_quality(const float* a, long long a_sf, long long a_sc, long long a_sy, const float* b,
+                                 long long b_sf, long long b_sc, long long b_sy, int F, int H, int W, int crop,
+                                 int ch_first, int n_ch, const double* gauss11, unsigned long long* sse,
+                                 double* ssim_sum, int num_sms, cudaStream_t stream);
+
 cudaError_t launch_mv_rasterize(const float* rec, const int* frame_off, const int* is_b, const int* p_target,
                                 int T, int R, int H, int W, unsigned* own_f, unsigned* own_b, unsigned* pmask,
                                 float* mvs, float* partitions, int* status, cudaStream_t stream);

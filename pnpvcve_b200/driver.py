@@ -37,14 +37,15 @@ def gather_metrics(local, num_clips, rank, world, group=None):
     """
     per = clips_per_rank(num_clips, world)
     t = local.shape[1] if local.dim() == 3 else 0
-    padded = torch.full((per, t, N_METRICS), float("nan"), dtype=torch.float32, device=local.device)
+    nm = local.shape[2] if local.dim() == 3 else N_METRICS      # any per-frame metric vector (e.g. + PSNR, SSIM)
+    padded = torch.full((per, t, nm), float("nan"), dtype=torch.float32, device=local.device)
     padded[: local.shape[0]] = local
     if world == 1:
         parts = [padded]
     else:
         parts = [torch.empty_like(padded) for _ in range(world)]
         dist.all_gather(parts, padded, group=group)
-    full = torch.empty((num_clips, t, N_METRICS), dtype=torch.float32, device=local.device)
+    full = torch.empty((num_clips, t, nm), dtype=torch.float32, device=local.device)
     for r in range(world):
         idx = shard_clips(num_clips, r, world)
         if idx:

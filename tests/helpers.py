@@ -52,3 +52,17 @@ def warp_case():
     flow = flow_b.repeat_interleave(8, 2).repeat_interleave(8, 3)
     gold = np.load(os.path.join(GOLDEN, "warp_720p.npz"))
     return x, flow, gold
+
+
+def metric_cases():
+    """name -> (out (3,H,W) fp32, gt (3,H,W) fp32, crop_border) for the PSNR / SSIM golden values
+    (tests/golden/metrics_cases.npz, written by tests/golden/make_golden_metrics.py from the reference's functions)."""
+    cases = {}
+    for name, (h, w, seed, noise, crop) in dict(a_64x80=(64, 80, 1, 0.02, 0), b_72x96_crop4=(72, 96, 2, 0.05, 4),
+                                                c_40x56_hard=(40, 56, 3, 0.3, 2), d_equal=(32, 48, 4, 0.0, 0)).items():
+        g = torch.Generator().manual_seed(seed)
+        gt = torch.rand((3, h, w), generator=g) * 1.1 - 0.05
+        gt = torch.nn.functional.avg_pool2d(gt[None], 3, 1, 1)[0] * 1.2 - 0.05          # some structure
+        out = gt + noise * torch.randn((3, h, w), generator=g)
+        cases[name] = (out.contiguous(), gt.contiguous(), crop)
+    return cases
