@@ -482,6 +482,8 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
     // row's output staging slot -- in exactly the bytes this thread overwrites with the final value one
     // row later, so no register state is carried from row to row and no other thread is involved.
     auto blend_store = [&](uint8_t* slot_row, float q0, float q1, float q2) {
+      // (the values were prefetched rows ago; they are first touched here, behind the barrier wait)
+      if (p.par_sparse) par_sparse_select(q0, q1, q2);   // 1/255 for the surviving class, 0 for the others
 #pragma unroll
       for (int gg = 0; gg < 2; ++gg) {
         float a1[16], a2[16], a3[16];
@@ -508,7 +510,6 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         q0 = __ldg(pp);
         q1 = __ldg(pp + p.par_sc);
         q2 = __ldg(pp + 2 * p.par_sc);
-        if (p.par_sparse) par_sparse_select(q0, q1, q2);   // 1/255 for the surviving class, 0 for the others
       }
     };
     // partition values are fetched TWO rows ahead: the epilogue is the hand-back path of the single 1x1
