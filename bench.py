@@ -147,7 +147,7 @@ def run_reference_arm(args):
                 cpu_baseline=dict(value=value, unit="frames/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -171,7 +171,27 @@ def mean_event_ms(pairs):
     return sum(a.elapsed_time(b) for a, b in pairs) / max(len(pairs), 1)
 
 
+#: the ONE JSON line goes to the process's original stdout; everything else that native libraries print there
+#: (NCCL announces its version on stdout on some boxes) is sent to stderr
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -255,10 +275,19 @@ def main():
             step_resident(args.warmup + i)
         p1.record()
         barrier()
-        clocks = sampler.stop() if sampler else None
         prof = net._engine.prof
-        net._engine.prof = None
         prof_step_ms = p0.elapsed_time(p1) / prof_steps
+        # ... and one more step with events only at the phase boundaries of a frame (7 per frame instead of ~12 per
+        # block): the 8-block stacks are timed undisturbed, which gives the in-situ duration of a launch A + launch B pair
+        net._engine.prof = {"phases": []}
+        step_resident(args.warmup)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        phases = net._engine.prof["phases"]
+        net._engine.prof = None
+        stack_us = [a.elapsed_time(b) * 1e3 for (n0, a), (n1, b) in zip(phases[:-1], phases[1:])
+                    if n0.endswith("input_done") and n1.endswith("stack_done")]
+        pair_us = sum(stack_us) / len(stack_us) / GEN_CFG["num_blocks"] if stack_us else 0.0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -279,19 +308,26 @@ def main():
                     achieved=a_tflops, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
                     frac=a_tflops / peaks["bf16_tflops_sustained"],
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at 720p, from the
-                    # committed capture profiles/r01_conv_final_ncu_summary.csv (135.36 + 75.16 MB); the
+                    # committed capture profiles/r01b_kernels_ncu_summary.csv (135.31 + 74.77 MB); the
                     # algorithmic bytes are 118 (x) + 11 (partition planes) + 118 (t) = 247 MB
-                    traffic=210.52e6, traffic_unit="bytes/launch",
+                    traffic=210.07e6, traffic_unit="bytes/launch",
                     peak_source=f"{peaks['source']} sustained cuBLAS bf16 (kernel timed inside a long step)",
                     ms_per_launch=a_ms, launches_timed=len(prof["block_a"]), timed_every=args.prof_every,
                     share_of_step=share_a,
+                    # launch A + launch B of one BAE block, from phase-boundary events around the undisturbed 8-block stacks
+                    block_pair=dict(us=pair_us, tflops=(FLOP_BLOCK_A_PER_PX + 2 * 64 * 64 * 9) * H * W / (pair_us * 1e-6) / 1e12
+                                    if pair_us else 0.0,
+                                    frac=(FLOP_BLOCK_A_PER_PX + 2 * 64 * 64 * 9) * H * W / (pair_us * 1e-6) / 1e12
+                                    / peaks["bf16_tflops_sustained"] if pair_us else 0.0,
+                                    note="bracketing single launches defeats programmatic dependent launch, so ms_per_launch "
+                                         "is an upper bound; this is the in-situ time of the A+B pair"),
                     whole_path_tflops=FLOP_PER_PX_FRAME * H * W * value / 1e12,
                     whole_path_frac=FLOP_PER_PX_FRAME * H * W * value / 1e12 / peaks["bf16_tflops_sustained"])
     roofline_warp = dict(bound="hbm", kernel="mv_warp_kernel", achieved=w_gbs, peak=peaks["hbm_gbs"],
                          unit="GB/s", frac=w_gbs / peaks["hbm_gbs"],
-                         # profiles/r01_warp_final_ncu_summary.csv: 92.37 + 73.65 MB (algorithmic 243.3 MB;
+                         # profiles/r01b_kernels_ncu_summary.csv: 92.39 + 72.20 MB (algorithmic 243.3 MB;
                          # part of the source rows is still in L2 from the producing kernel)
-                         traffic=166.02e6, traffic_unit="bytes/launch", ms_per_launch=w_ms,
+                         traffic=164.60e6, traffic_unit="bytes/launch", ms_per_launch=w_ms,
                          launches_timed=len(prof["warp"]), peak_source=peaks["source"])
 
     # ---------------- end to end from pinned host buffers (e2e)
@@ -371,7 +407,7 @@ def main():
                                             d2h_bytes_per_step=d2h, steps=e2e_steps),
                     gpu_launches=launches * world, roofline=roofline, roofline_warp=roofline_warp,
                     kernels_ms=dict(block=mean_event_ms(prof["block"]), block_a=a_ms, block_b=b_ms, warp=w_ms), cpu_baseline=cpu_baseline)
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
