@@ -54,19 +54,29 @@ def gather_metrics(local, num_clips, rank, world, group=None):
 
 
 @torch.no_grad()
-def enhance_clips(net, clips, rank=0, world=1, refs=None):
+def enhance_clips(net, clips, rank=0, world=1, refs=None, gts=None, crop_border=0):
     """Run this rank's share of ``clips`` (list of dicts as produced by pnpvcve_b200.synthetic).
 
-    Returns (outputs for the local clips, gathered metrics for all clips).
+    Returns (outputs for the local clips, gathered metrics for all clips).  With ``gts`` (ground-truth clips,
+    (1,T,3,H,W) each) the per-frame metric vector is [max-abs, mse, PSNR, SSIM]: PSNR / SSIM as BasicVSR.evaluate
+    computes them (mmedit/models/restorers/basicvsr.py:119-153), but on the device (pnpvcve_b200.metrics) -- the
+    reference's test loop copies every frame to the host and pickles per-clip results through two all_gathers
+    (mmedit/apis/test.py:190-234); here nothing leaves the GPU before the single fixed-shape gather.
     """
     from .synthetic import generator_args
+    from . import metrics as _metrics
     mine = shard_clips(len(clips), rank, world)
     outs, mets = [], []
     for c in mine:
         out = net(*generator_args(clips[c]))
         outs.append(out)
-        mets.append(frame_metrics(out, None if refs is None else refs[c])[0])
+        m = frame_metrics(out, None if refs is None else refs[c])[0]
+        if gts is not None:
+            q = _metrics.frame_quality(out, gts[c].to(out.device), crop_border)
+            m = torch.cat([m, q["psnr"][0].float()[:, None], q["ssim"][0].float()[:, None]], dim=1)
+        mets.append(m)
     t = clips[0]["lq"].shape[1]
     dev = clips[0]["lq"].device
-    local = torch.stack(mets, 0) if mets else torch.empty((0, t, N_METRICS), device=dev)
+    nm = N_METRICS + (2 if gts is not None else 0)
+    local = torch.stack(mets, 0) if mets else torch.empty((0, t, nm), device=dev)
     return outs, gather_metrics(local, len(clips), rank, world)

@@ -78,3 +78,24 @@ def test_frame_quality_sequence_720p_views_and_evaluate():
     assert abs(ev["PSNR"].item() - q["psnr"].mean().item()) < 1e-12
     with pytest.raises(Exception):
         metrics.frame_quality(out[..., :12, :12], gt[..., :12, :12], crop_border=1)   # cropped frame < 11 x 11
+
+
+@pytest.mark.gpu
+def test_driver_gathers_psnr_ssim_per_frame():
+    """enhance_clips with ground truth: [max-abs, mse, PSNR, SSIM] per frame through the fixed-shape gather."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pnpvcve_b200 as P
+    from pnpvcve_b200 import driver, metrics, synthetic, weights
+    from test_gpu_parity import GENERATOR_CFG
+    dev = torch.device("cuda:0")
+    net = P.build_backbone(dict(GENERATOR_CFG, num_blocks=2))
+    net.load_state_dict(weights.random_state_dict(3, num_blocks=2), strict=True)
+    net = net.to(dev).eval()
+    clips = [{k: v.to(dev) for k, v in synthetic.make_clip(64, 96, 3, seed=50 + i).items()} for i in range(2)]
+    gts = [(c["lq"] * 0.9 + 0.05) for c in clips]
+    outs, met = driver.enhance_clips(net, clips, gts=gts)
+    assert met.shape == (2, 3, 4)
+    q = metrics.frame_quality(outs[1], gts[1])
+    assert torch.allclose(met[1, :, 2].double(), q["psnr"][0], atol=1e-4)
+    assert torch.allclose(met[1, :, 3].double(), q["ssim"][0], atol=1e-6)
