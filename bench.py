@@ -349,7 +349,24 @@ def main():
             ev.record(up)
         return clip, ev
 
+    streamer = driver.ClipStreamer(net, dev, chunk=10) if nc == 1 else None
+
+    def run_e2e_streamed(n_steps):
+        """The public host-clip API (driver.ClipStreamer): frames are uploaded in chunks in the order the backward-time
+        pass reads them, finished frames are downloaded chunk by chunk; every step still copies all of its inputs from
+        pinned host memory and all of its frames back inside the timed region."""
+        ticket = streamer.upload(host[0])
+        for i in range(n_steps):
+            nxt = streamer.upload(host[0]) if i + 1 < n_steps else None
+            out = streamer.run(ticket, out_host)
+            local = driver.frame_metrics(out)
+            driver.gather_metrics(local.mean(0, keepdim=True), world, rank, world)
+            ticket = nxt
+        streamer.finish()
+
     def run_e2e(n_steps):
+        if streamer is not None:
+            return run_e2e_streamed(n_steps)
         nxt = upload()
         for i in range(n_steps):
             clip, ev = nxt
@@ -404,7 +421,9 @@ def main():
                     warmup=args.warmup, ms_per_step=steps_ms, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="bf16", data="synthetic", config=workload_config(args, world),
                     clocks=clocks, e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d,
-                                            d2h_bytes_per_step=d2h, steps=e2e_steps),
+                                            d2h_bytes_per_step=d2h, steps=e2e_steps,
+                                            api="pnpvcve_b200.driver.ClipStreamer (chunked H2D/D2H overlapped with the kernels)"
+                                            if streamer is not None else "net(...) per clip, whole-clip copies on side streams"),
                     gpu_launches=launches * world, roofline=roofline, roofline_warp=roofline_warp,
                     kernels_ms=dict(block=mean_event_ms(prof["block"]), block_a=a_ms, block_b=b_ms, warp=w_ms), cpu_baseline=cpu_baseline)
         _emit(line)

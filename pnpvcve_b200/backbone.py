@@ -183,6 +183,17 @@ class IconVSR_restore_wo_refill_mv_ipb_fast_domain_dynamic_with_par(nn.Module):
             raise RuntimeError("pnpvcve_b200 runs on sm_100 CUDA devices only; there is no CPU fallback")
         return self._engine.forward(lrs, QPs, slices, mvs, base_QPs, par_map)
 
+    def forward_streamed(self, lrs, QPs, slices, mvs, base_QPs, par_map, cond_host=None, frame_ready=None,
+                         frame_done=None, out=None):
+        """Same computation as ``forward`` for a clip that is still arriving / already leaving: ``frame_ready(i)`` is
+        called before frame i's inputs are first read (backward-time order T-1 .. 0), ``frame_done(i, out)`` after
+        frame i of the output has been enqueued, ``cond_host`` = host copies of (slices, base_QPs, QPs) saves the one
+        device->host copy.  Used by ``pnpvcve_b200.driver.stream_clips`` to overlap H2D / D2H with the kernels."""
+        if not lrs.is_cuda:
+            raise RuntimeError("pnpvcve_b200 runs on sm_100 CUDA devices only; there is no CPU fallback")
+        return self._engine.forward(lrs, QPs, slices, mvs, base_QPs, par_map, cond_host=cond_host,
+                                    frame_ready=frame_ready, frame_done=frame_done, out=out)
+
     def forward_with_features(self, lrs, QPs, slices, mvs, base_QPs, par_map):
         """Test hook: also returns the backward / forward propagation features (bf16 NHWC)."""
         return self._engine.forward(lrs, QPs, slices, mvs, base_QPs, par_map, return_features=True)

@@ -80,3 +80,122 @@ def enhance_clips(net, clips, rank=0, world=1, refs=None, gts=None, crop_border=
     nm = N_METRICS + (2 if gts is not None else 0)
     local = torch.stack(mets, 0) if mets else torch.empty((0, t, nm), device=dev)
     return outs, gather_metrics(local, len(clips), rank, world)
+
+
+# ------------------------------------------------------------------------------------------------
+# host-resident clips: chunked upload / download overlapped with the kernels
+# ------------------------------------------------------------------------------------------------
+class ClipStreamer:
+    """Enhances clips that live in PINNED HOST memory and returns the frames to pinned host memory.
+
+    The reference's test loop uploads a whole clip, runs the generator, then copies every frame back
+    (mmedit/apis/test.py:38-60, restorers/basicvsr.py:176-182).  Here the clip is uploaded in chunks of frames in
+    the order the backward-time pass consumes them (last frame first) on a copy stream, the generator waits per
+    chunk (``forward_streamed``), and finished frames go back to the host chunk by chunk on a second copy stream
+    while later frames are still being computed; the upload of clip k+1 overlaps the kernels of clip k (two sets of
+    device buffers).  Every clip still pays its full H2D and D2H -- they are just never exposed, except the first
+    chunk in and the last chunk out.  One clip (n = 1) per call.
+    """
+
+    BIG = ("lq", "mvs", "partitions")
+    SMALL = ("QPs", "slices", "base_QPs")
+
+    def __init__(self, net, device, chunk=10):
+        self.net, self.dev, self.chunk = net, torch.device(device), int(chunk)
+        self.up = torch.cuda.Stream(device=self.dev)
+        self.down = torch.cuda.Stream(device=self.dev)
+        self.slots = [None, None]          # double-buffered device copies of the inputs
+        self.outs = [None, None]           # ... and result buffers: (tensor, event "its last download has finished")
+        self.turn = 0
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def _chunks(self, t):
+        return [(a, min(a + self.chunk, t)) for a in range(0, t, self.chunk)]
+
+    def upload(self, host_clip):
+        """Enqueue the upload of one clip; returns a ticket for ``run``."""
+        t = host_clip["lq"].shape[1]
+        slot = self.turn
+        self.turn ^= 1
+        key = tuple((k, tuple(v.shape)) for k, v in sorted(host_clip.items()))
+        if self.slots[slot] is None or self.slots[slot][0] != key:
+            self.slots[slot] = (key, {k: torch.empty(v.shape, dtype=v.dtype, device=self.dev) for k, v in host_clip.items()},
+                                None)
+        dclip = self.slots[slot][1]
+        busy = self.slots[slot][2]         # kernels of the clip that last used these buffers
+        events = {}
+        with torch.cuda.stream(self.up):
+            if busy is not None:
+                self.up.wait_event(busy)
+            for k in self.SMALL:
+                dclip[k].copy_(host_clip[k], non_blocking=True)
+            for a, b in reversed(self._chunks(t)):
+                for k in self.BIG:
+                    dclip[k][:, a:b].copy_(host_clip[k][:, a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.up)
+                events[(a, b)] = ev
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in host_clip.values())
+        return dict(slot=slot, dclip=dclip, events=events, t=t,
+                    cond=(host_clip["slices"], host_clip["base_QPs"], host_clip["QPs"]))
+
+    @torch.no_grad()
+    def run(self, ticket, out_host):
+        """Enqueue the kernels of an uploaded clip and the chunked download of its frames into ``out_host``."""
+        main = torch.cuda.current_stream(self.dev)
+        t, dclip, events = ticket["t"], ticket["dclip"], ticket["events"]
+        chunks = self._chunks(t)
+        waited = set()
+
+        def frame_ready(i):
+            c = chunks[i // self.chunk]
+            if c not in waited:
+                waited.add(c)
+                main.wait_event(events[c])
+
+        def frame_done(i, out):
+            a, b = chunks[i // self.chunk]
+            if i == b - 1:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(self.down):
+                    self.down.wait_event(ev)
+                    out_host[:, a:b].copy_(out[:, a:b], non_blocking=True)
+
+        main.wait_event(events[chunks[-1]])          # small tensors + the first chunk the kernels need
+        waited.add(chunks[-1])
+        from .synthetic import generator_args
+        # result buffers are owned here and recycled under events: a fresh torch.empty per clip that another stream
+        # still reads (record_stream) keeps the caching allocator from reusing the block and ends in cudaMalloc stalls
+        slot = ticket["slot"]
+        if self.outs[slot] is not None and tuple(self.outs[slot][0].shape[:2]) == tuple(out_host.shape[:2]) and \
+                tuple(self.outs[slot][0].shape[2:]) == tuple(out_host.shape[2:]):
+            obuf, free_ev = self.outs[slot]
+            main.wait_event(free_ev)
+        else:
+            obuf = torch.empty(out_host.shape, dtype=torch.float32, device=self.dev)
+        out = self.net.forward_streamed(*generator_args(dclip), cond_host=ticket["cond"], frame_ready=frame_ready,
+                                        frame_done=frame_done, out=obuf)
+        free_ev = torch.cuda.Event()
+        free_ev.record(self.down)                    # behind the last chunk's download
+        self.outs[slot] = (obuf, free_ev)
+        done = torch.cuda.Event()
+        done.record(main)
+        self.slots[ticket["slot"]] = (self.slots[ticket["slot"]][0], dclip, done)
+        self.d2h_bytes = out.numel() * out.element_size()
+        return out
+
+    def finish(self):
+        torch.cuda.current_stream(self.dev).wait_stream(self.down)
+
+
+def stream_clips(net, host_clips, out_hosts, device, chunk=10):
+    """Enhance a sequence of pinned host clips into pinned host outputs (see ClipStreamer); returns the streamer."""
+    s = ClipStreamer(net, device, chunk)
+    ticket = s.upload(host_clips[0])
+    for k in range(len(host_clips)):
+        nxt = s.upload(host_clips[k + 1]) if k + 1 < len(host_clips) else None
+        s.run(ticket, out_hosts[k])
+        ticket = nxt
+    s.finish()
+    return s

@@ -297,7 +297,13 @@ class BaeEngine:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, lrs, QPs, slices, mvs, base_QPs, par_map, return_features=False):
+    def forward(self, lrs, QPs, slices, mvs, base_QPs, par_map, return_features=False, cond_host=None,
+                frame_ready=None, frame_done=None, out=None):
+        """cond_host: optional host copies (slices, base_QPs, QPs), each (n,T) -- skips the one device->host copy.
+        frame_ready(i): called (host side) before frame i's lq / mvs / par_map are first read, in the backward-time
+        pass (i = T-1 .. 0); frame_done(i, out): called after frame i's output has been enqueued.  Both let a caller
+        stream a clip in and out in chunks (driver.stream_clips): they typically enqueue an event wait / record.
+        out: optional preallocated fp32 (n,T,3,Hout,Wout) result buffer (the caller guarantees nobody still reads it)."""
         m = self.m
         dev = lrs.device
         _lib.require_device()
@@ -305,6 +311,11 @@ class BaeEngine:
         assert h_in >= 64 and w_in >= 64, (
             f"The height and width of inputs should be at least 64, but got {h_in} and {w_in}.")
         pad_h, pad_w = (4 - h_in % 4) % 4, (4 - w_in % 4) % 4
+        if frame_ready is not None and (pad_h or pad_w or not (lrs.is_contiguous() and mvs.is_contiguous()
+                                                              and par_map.is_contiguous())):
+            for i in range(t):                            # whole-tensor copies below: everything must have arrived
+                frame_ready(i)
+            frame_ready = None
         if pad_h or pad_w:                                # spatial_padding, iconvsr.py:371-394
             lrs = F.pad(lrs.reshape(-1, c, h_in, w_in), [0, pad_w, 0, pad_h], mode="reflect")
             lrs = lrs.view(n, t, c, h_in + pad_h, w_in + pad_w)
@@ -323,8 +334,11 @@ class BaeEngine:
         st = self._pack_static(dev)
         nb = st["nb"]
         # one D2H copy for everything the host needs (the reference syncs 2(T-1)n+1 times)
-        cond = torch.stack([slices.reshape(n, t).float(), base_QPs.reshape(n, t).float(),
-                            QPs.reshape(n, t).float()], 0).cpu()
+        if cond_host is not None:
+            cond = torch.stack([torch.as_tensor(c, dtype=torch.float32).reshape(n, t).cpu() for c in cond_host], 0)
+        else:
+            cond = torch.stack([slices.reshape(n, t).float(), base_QPs.reshape(n, t).float(),
+                                QPs.reshape(n, t).float()], 0).cpu()
         key_rows = keyframe_rows(cond[0])
         crf_host, qp_host = cond[1], cond[2]
 
@@ -347,7 +361,11 @@ class BaeEngine:
         bufs = self._buffers(n, t, h, w, dev, lanes, maxn)
         feats = bufs["feats"]
         up = 4 if m.vsr else 1
-        out = torch.empty((n, t, 3, up * h, up * w), dtype=torch.float32, device=dev)
+        if out is None:
+            out = torch.empty((n, t, 3, up * h, up * w), dtype=torch.float32, device=dev)
+        elif tuple(out.shape) != (n, t, 3, up * h, up * w) or out.dtype != torch.float32 or out.device != dev or \
+                not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous fp32 {(n, t, 3, up * h, up * w)} tensor on {dev}")
         prof = self.prof
         seen = {}
         bwd_feats = torch.empty_like(feats) if return_features else None
@@ -425,6 +443,8 @@ class BaeEngine:
             # ---------------- backward-time propagation (iconvsr_ipb_par.py:67-100)
             for i in range(t - 1, -1, -1):
                 mixed = mixed_of[(float(crf_host[b, i]), float(qp_host[b, i]))]
+                if frame_ready is not None:
+                    frame_ready(i)
                 phase("bwd_start")
                 ops.lr_im2col(lrs[b0:b1, i], buf["lr64"])
                 counts[lane] += 1
@@ -503,6 +523,8 @@ class BaeEngine:
                          outf=out[b0:b1, i], label="last")
                     counts[lane] += 2
                 phase("fwd_head_done")
+                if frame_done is not None and b1 == n:
+                    frame_done(i, out)
                 yield
 
         def lane_steps(lane):

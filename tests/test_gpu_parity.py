@@ -167,3 +167,21 @@ def test_unsupported_kwargs_raise():
         P.build_backbone(dict(GENERATOR_CFG, with_se=False))
     with pytest.raises(NotImplementedError):
         P.build_backbone(dict(GENERATOR_CFG, blocktype="sft"))
+
+
+def test_clip_streamer_equals_plain_forward(dev):
+    """Host-resident clips through driver.ClipStreamer (chunked H2D in backward-time order, chunked D2H, recycled
+    device buffers) give bit-identical frames to the plain call -- the streaming hooks only reorder copies."""
+    from pnpvcve_b200 import driver
+    sd = weights.random_state_dict(9, num_blocks=2)
+    net = build(sd, dev, num_blocks=2)
+    clips = [synthetic.make_clip(64, 96, 13, seed=600 + i, crf=(15, 35)[i % 2]) for i in range(3)]
+    refs = [run(net, c, dev).cpu() for c in clips]
+    hosts = [{k: v.pin_memory() for k, v in c.items()} for c in clips]
+    outs = [torch.empty_like(r).pin_memory() for r in refs]
+    st = driver.stream_clips(net, hosts, outs, dev, chunk=5)
+    torch.cuda.synchronize()
+    for o, r in zip(outs, refs):
+        assert torch.equal(o, r)
+    assert st.h2d_bytes == sum(v.numel() * v.element_size() for v in hosts[0].values())
+    assert st.d2h_bytes == refs[0].numel() * 4
