@@ -304,13 +304,13 @@ def main():
     steps_ms = total_ms / args.steps
     # share of the (profiled) step spent in this kernel: bracketed launches x sampling stride / profiled step time
     share_a = a_ms * len(prof["block_a"]) * args.prof_every / prof_steps / prof_step_ms if a_ms else 0.0
-    roofline = dict(bound="tensor", kernel="conv3x3_umma_kernel (block launch A: 3x3 + 3 partition 1x1, N=256 centre tap)",
+    roofline = dict(bound="tensor", kernel="conv3x3_rows_kernel<1,0> (block launch A: row-stacked 3x3 + three partition 1x1 convs, N=192 MMAs, split-role epilogue)",
                     achieved=a_tflops, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
                     frac=a_tflops / peaks["bf16_tflops_sustained"],
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at 720p, from the
-                    # committed capture profiles/r01b_kernels_ncu_summary.csv (135.31 + 74.77 MB); the
+                    # committed capture profiles/r01c_kernels_ncu_summary.csv (135.55 + 74.66 MB); the
                     # algorithmic bytes are 118 (x) + 11 (partition planes) + 118 (t) = 247 MB
-                    traffic=210.07e6, traffic_unit="bytes/launch",
+                    traffic=210.21e6, traffic_unit="bytes/launch",
                     peak_source=f"{peaks['source']} sustained cuBLAS bf16 (kernel timed inside a long step)",
                     ms_per_launch=a_ms, launches_timed=len(prof["block_a"]), timed_every=args.prof_every,
                     share_of_step=share_a,
@@ -325,9 +325,9 @@ def main():
                     whole_path_frac=FLOP_PER_PX_FRAME * H * W * value / 1e12 / peaks["bf16_tflops_sustained"])
     roofline_warp = dict(bound="hbm", kernel="mv_warp_kernel", achieved=w_gbs, peak=peaks["hbm_gbs"],
                          unit="GB/s", frac=w_gbs / peaks["hbm_gbs"],
-                         # profiles/r01b_kernels_ncu_summary.csv: 92.39 + 72.20 MB (algorithmic 243.3 MB;
+                         # profiles/r01c_kernels_ncu_summary.csv: 92.36 + 71.24 MB (algorithmic 243.3 MB;
                          # part of the source rows is still in L2 from the producing kernel)
-                         traffic=164.60e6, traffic_unit="bytes/launch", ms_per_launch=w_ms,
+                         traffic=163.61e6, traffic_unit="bytes/launch", ms_per_launch=w_ms,
                          launches_timed=len(prof["warp"]), peak_source=peaks["source"])
 
     # ---------------- end to end from pinned host buffers (e2e)
@@ -389,7 +389,9 @@ def main():
     del clips
     torch.cuda.empty_cache()
     with torch.no_grad():
-        e2e_warm = min(args.warmup, 1) if args.frames >= 50 else args.warmup
+        # two warm-up steps: the streamer double-buffers its device copies, so the second step still allocates
+        # (GB-sized cudaMallocs inside the timed region made this number swing between 230 and 300 frames/s)
+        e2e_warm = min(args.warmup, 2) if args.frames >= 50 else args.warmup
         run_e2e(max(e2e_warm, 1))
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -351,6 +351,10 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   p.w_stable = c->wpack_stable ? 1 : 0;
   p.lq_up4 = c->lq_up4 ? 1 : 0;
   p.par_sparse = (c->par && c->par_sparse) ? 1 : 0;
+  {
+    const char* sp = getenv("PNP_PAR_SPLIT");     // diagnostic switch for the row-stacked partition variant (default on)
+    p.par_split = (rowstack && c->par && !(sp && atoi(sp) == 0)) ? 1 : 0;
+  }
   p.base_off_mode = g_base_off_mode;
   {
     const char* dbg = getenv("PNP_DEBUG_SKIP");   // what-if profiling only; results are wrong when set

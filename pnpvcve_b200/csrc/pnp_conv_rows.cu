@@ -56,7 +56,9 @@ struct RowsMisc {
   uint64_t io_empty[kMaxIoSlots];
   uint32_t tmem_base;
   uint32_t go_step;                // scout -> MMA: steps whose barriers have all completed
-  uint32_t go_par;                 // epilogue -> MMA: epilogue-warp reads of the partition region (8 per row)
+  uint32_t go_par;                 // epilogue -> MMA: epilogue-warp reads of the partition region (8 or 4 per row)
+  uint32_t slot_free;              // split roles: output rows whose TMA stores have finished reading their staging slot
+  uint64_t dy_full[kMaxIoSlots];   // split roles: region readers -> main epilogue: the row's 1x1 blend is parked
 };
 static_assert(sizeof(RowsMisc) <= 1024, "misc region overflow");
 
@@ -151,7 +153,10 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       mbar_init(smem_u32(&misc->w_full), 1);
       for (int i = 0; i < kMaxASlots; ++i) mbar_init(smem_u32(&misc->a_full[i]), 1);
       for (int i = 0; i < kStepRing; ++i) mbar_init(smem_u32(&misc->step_done[i]), 1);
-      for (int i = 0; i < kAccRingMax; ++i) mbar_init(smem_u32(&misc->acc_free[i]), kEpilogueWarps);
+      const int acc_readers = (kPar && p.par_split) ? 4 : kEpilogueWarps;
+      for (int i = 0; i < kAccRingMax; ++i) mbar_init(smem_u32(&misc->acc_free[i]), acc_readers);
+      for (int i = 0; i < kMaxIoSlots; ++i) mbar_init(smem_u32(&misc->dy_full[i]), 4);
+      misc->slot_free = 0;
       mbar_init(smem_u32(&misc->par_done), 1);
       for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&misc->aux_full[i]), 1);
       for (int i = 0; i < kMaxIoSlots; ++i) {
@@ -390,7 +395,8 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
           // Partition 1x1 convs of this row: centre pixel column (dx index 1), N = 192, own TMEM
           // region.  Issued LAST in the step: the epilogue then has a whole step to read the region
           // before the next row needs it (issued first, the hand-back sat on the critical path).
-          spin_until_ge(go_par, kEpilogueWarps * cur_od, 10);   // every epilogue warp has read row cur_od-1's region
+          // every reader warp has pulled row cur_od-1's region into registers
+          spin_until_ge(go_par, (p.par_split ? 4u : (uint32_t)kEpilogueWarps) * cur_od, 10);
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -512,6 +518,137 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         q2 = __ldg(pp + 2 * p.par_sc);
       }
     };
+    // ---------------------------------------------------------------------------------------------------
+    // Split roles (kPar, p.par_split): warps 6..9 do nothing but drain the single 1x1 accumulator region --
+    // wait for par_done, pull the 192 columns of their lane quarter into registers, hand the region back, blend
+    // and park the result in the row's staging slot -- while warps 2..5 finish rows (all 64 channels of their 32
+    // pixels).  The region's hand-back loop (commit -> reader -> release -> next 1x1 MMAs) then no longer
+    // contains the main epilogue's loop top, store bookkeeping and row arithmetic.
+    // ---------------------------------------------------------------------------------------------------
+    if (kPar && p.par_split) {
+      const uint32_t slot_free = smem_u32(&misc->slot_free);
+      if (warp >= 6) {
+        float pn0 = 0.f, pn1 = 0.f, pn2 = 0.f;
+        if (cur.valid) par_load(cur, pn0, pn1, pn2);
+        Ring sl(n_io);
+        while (cur.valid) {
+          TileCur nxt = cur;
+          tile_next(nxt);
+          float pf0 = 0.f, pf1 = 0.f, pf2 = 0.f;
+          if (nxt.valid) par_load(nxt, pf0, pf1, pf2);      // one row ahead: consumed a whole step later
+          mbar_wait(smem_u32(&misc->par_done), cur.ord & 1, 11);   // (one poller per warp measured no better)
+          tc_fence_after();
+          if (p.par_sparse) par_sparse_select(pn0, pn1, pn2);
+          uint32_t wv[32];
+          // two batches of 32 channels x 3 classes: six tcgen05.ld in flight per wait
+#pragma unroll
+          for (int b2 = 0; b2 < 2; ++b2) {
+            float a1[32], a2[32], a3[32];
+            const uint32_t col = kParCol + b2 * 32;
+            tmem_ld16(lane_base + col, a1);
+            tmem_ld16(lane_base + col + 16, a1 + 16);
+            tmem_ld16(lane_base + col + 64, a2);
+            tmem_ld16(lane_base + col + 80, a2 + 16);
+            tmem_ld16(lane_base + col + 128, a3);
+            tmem_ld16(lane_base + col + 144, a3 + 16);
+            tmem_ld_wait();
+            if (b2 == 1) {                                   // everything is in registers: hand the region back first
+              tc_fence_before();
+              warp_flag_add(smem_u32(&misc->go_par));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              wv[b2 * 16 + j] = pack_bf16x2(fmaf(pn2, a3[2 * j], fmaf(pn1, a2[2 * j], pn0 * a1[2 * j])),
+                                            fmaf(pn2, a3[2 * j + 1], fmaf(pn1, a2[2 * j + 1], pn0 * a1[2 * j + 1])));
+          }
+          // the row's staging slot was last used by row ord - n_io: its TMA store must have finished reading
+          if (cur.ord >= (uint32_t)n_io) spin_until_ge(slot_free, cur.ord - (uint32_t)n_io + 1, 12);
+          uint8_t* rowp = sgen + L.io + sl.slot * kTileBytes + row * 128;
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8)
+            *reinterpret_cast<uint4*>(rowp + ((c8 ^ sw) << 4)) =
+                make_uint4(wv[4 * c8], wv[4 * c8 + 1], wv[4 * c8 + 2], wv[4 * c8 + 3]);
+          warp_arrive(smem_u32(&misc->dy_full[sl.slot]));    // release: the parked values are visible to warps 2..5
+          sl.advance();
+          pn0 = pf0;
+          pn1 = pf1;
+          pn2 = pf2;
+          cur = nxt;
+        }
+      } else {
+        Ring ior(n_io);
+        while (cur.valid) {
+          const Segment& s = cur.s;
+          const uint32_t ord = cur.ord;
+          const int y = PNP_Y(s.y_b + cur.o);
+          const uint32_t sc_last = cur.sc0 + (uint32_t)(min(cur.o + 1, s.j_last) - s.j_first);
+          const uint32_t slot = ord % kAccRing;
+          const uint32_t taddr = lane_base + slot * tap_n;
+          if (store_warp) {
+            if (elect_one()) {
+              tma_store_wait_read<1>();                      // stores of rows <= ord-2 no longer read shared memory
+              if (ord >= 1) st_release_shared(slot_free, ord - 1);
+            }
+            __syncwarp();
+          }
+          mbar_wait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> 3) & 1, 9);
+          tc_fence_after();
+          float v[64];
+#pragma unroll
+          for (int b4 = 0; b4 < 4; ++b4) tmem_ld16(taddr + b4 * 16, v + b4 * 16);
+          tmem_ld_wait();
+          tc_fence_before();
+          warp_arrive(smem_u32(&misc->acc_free[slot]));      // accumulator is in registers: slot reusable
+          mbar_wait(smem_u32(&misc->dy_full[ior.slot]), ior.phase, 13);
+          uint8_t* rowp = sgen + L.io + ior.slot * kTileBytes + row * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float* vv = v + g * 16;
+            const float4* sc4 = reinterpret_cast<const float4*>(&misc->scale[g * 16]);
+            const float4* bi4 = reinterpret_cast<const float4*>(&misc->bias[g * 16]);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 sc = kScale ? sc4[j4] : make_float4(1.f, 1.f, 1.f, 1.f);
+              const float4 bi = bi4[j4];
+              vv[4 * j4 + 0] = fmaf(vv[4 * j4 + 0], sc.x, bi.x);
+              vv[4 * j4 + 1] = fmaf(vv[4 * j4 + 1], sc.y, bi.y);
+              vv[4 * j4 + 2] = fmaf(vv[4 * j4 + 2], sc.z, bi.z);
+              vv[4 * j4 + 3] = fmaf(vv[4 * j4 + 3], sc.w, bi.w);
+            }
+            uint4* c0 = reinterpret_cast<uint4*>(rowp + (((2 * g) ^ sw) << 4));
+            uint4* c1 = reinterpret_cast<uint4*>(rowp + (((2 * g + 1) ^ sw) << 4));
+            const uint4 i0 = *c0, i1 = *c1;                  // the row's parked 1x1 blend
+            const uint32_t iw[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              vv[2 * j] += bf16_lo(iw[j]);
+              vv[2 * j + 1] += bf16_hi(iw[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) vv[j] = act_fn(vv[j], p.act);
+            *c0 = make_uint4(pack_bf16x2(vv[0], vv[1]), pack_bf16x2(vv[2], vv[3]), pack_bf16x2(vv[4], vv[5]),
+                             pack_bf16x2(vv[6], vv[7]));
+            *c1 = make_uint4(pack_bf16x2(vv[8], vv[9]), pack_bf16x2(vv[10], vv[11]), pack_bf16x2(vv[12], vv[13]),
+                             pack_bf16x2(vv[14], vv[15]));
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (store_warp) {
+            if (elect_one()) {
+              tma_store_4d(&p.tm_out, io_smem + ior.slot * kTileBytes, 0, s.strip * kTilePx, y, s.n);
+              tma_store_commit();
+            }
+            __syncwarp();
+          }
+          ior.advance();
+          tile_next(cur);
+        }
+        if (store_warp) {
+          if (elect_one()) tma_store_wait_all<0>();
+          __syncwarp();
+        }
+      }
+    } else {
     // partition values are fetched TWO rows ahead: the epilogue is the hand-back path of the single 1x1
     // accumulator region, so a global-load latency per row (measured: 1300-2400 cycles of "math") would
     // bound the whole pipeline.  pn* = values of the row after `cur`, loaded one iteration earlier.
@@ -745,6 +882,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       if (elect_one()) tma_store_wait_all<0>();
       __syncwarp();
     }
+    }   // !(kPar && p.par_split)
   }
 
   tc_fence_before();

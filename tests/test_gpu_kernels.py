@@ -1,4 +1,6 @@
 """Kernel-level parity on a real B200, every call going through the C ABI (libpnpvcve.so)."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -177,6 +179,15 @@ def test_conv_variants_match_fp32_conv2d(dev, n, h, w, layout):
     assert_bf16_close(nchw(out), F.relu(ref), "par", extra)
     ops.conv3x3(xs, wpp, out=out, bias=bias, par=par, act=ops.PNP_ACT_NONE, wlayout=layout)
     assert_bf16_close(nchw(out), ref - ref0 * scale.view(1, -1, 1, 1) + ref0, "par without scale", extra)
+    if layout == 1:      # the single-role epilogue of the row-stacked partition variant (diagnostic switch)
+        os.environ["PNP_PAR_SPLIT"] = "0"
+        try:
+            out.zero_()
+            ops.conv3x3(xs, wpp, out=out, bias=bias, par=par, act=ops.PNP_ACT_NONE, wlayout=layout)
+            torch.cuda.synchronize()
+        finally:
+            del os.environ["PNP_PAR_SPLIT"]
+        assert_bf16_close(nchw(out), ref - ref0 * scale.view(1, -1, 1, 1) + ref0, "par, single-role epilogue", extra)
 
     # reconstruction tail: 64 -> 3, + lq, fp32 NCHW output
     wl = bf(torch.randn((3, 64, 3, 3), generator=g, device=dev) * 0.05)
