@@ -69,3 +69,22 @@ if LAYOUT == 1:
     for _ in range(50): ops.conv3x3(x, wp9, out=out, idt=idt if IDT else None, wlayout=LAYOUT)
     e1.record(); torch.cuda.synchronize()
     print(f"back-to-back launches: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us per launch")
+if LAYOUT == 1 and os.environ.get("PNP_SKEW"):
+    import numpy as np
+    dur = (g1 - g0).numpy(); end = (g1 - g0.min()).numpy(); start = (g0 - g0.min()).numpy()
+    tiles_per = 49
+    def steps(c):
+        t0, t1 = c * tiles_per, min(7200, (c + 1) * tiles_per)
+        n = 0; t = t0
+        while t < t1:
+            col, y = divmod(t, 720)
+            ln = min(720 - y, t1 - t)
+            n += ln + (1 if y > 0 else 0) + (1 if y + ln < 720 else 0)
+            t += ln
+        return n
+    st = np.array([steps(c) for c in range(147)])
+    print("steps per CTA: min", st.min(), "max", st.max(), "; body ns by step count:", {int(s): int(np.median(dur[st == s])) for s in sorted(set(st))})
+    order = np.argsort(end)
+    print("earliest 8 ends (cta, steps, end ns):", [(int(c), int(st[c]), int(end[c])) for c in order[:8]])
+    print("latest 8 ends   (cta, steps, end ns):", [(int(c), int(st[c]), int(end[c])) for c in order[-8:]])
+    print("ns per step by CTA index decile:", [int(np.median((dur / st)[i:i + 15])) for i in range(0, 147, 15)])
