@@ -102,12 +102,15 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_oracle_step(sd, clip):
+def cpu_oracle_step(sd, clip, keep=None):
     from oracle import bae_oracle
     from pnpvcve_b200 import synthetic
     t0 = time.perf_counter()
-    bae_oracle.generator_forward(sd, *synthetic.generator_args(clip))
-    return time.perf_counter() - t0
+    out = bae_oracle.generator_forward(sd, *synthetic.generator_args(clip))
+    dt = time.perf_counter() - t0
+    if keep is not None:
+        keep.append(out)
+    return dt
 
 
 def cpu_sample_shape(budget_s, n_steps):
@@ -407,13 +410,21 @@ def main():
 
     # ---------------- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample
     cpu_baseline = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         h, w = cpu_sample_shape(30.0, 1)
         sd = weights.random_state_dict(0)
         clip = synthetic.make_clip(h, w, 2, seed=2000, crf=25, mv_qpel=64)
-        dt = cpu_oracle_step(sd, clip)
+        kept = []
+        dt = cpu_oracle_step(sd, clip, keep=kept)
+        # the oracle's frames of that sample double as the checker of the CUDA path on the same inputs (max-abs on
+        # [0,1] frames, tolerance 2e-3 of north_star) -- the sample is 720p whenever the budget allows
+        with torch.no_grad():
+            got = net(*[a.to(dev) for a in synthetic.generator_args(clip)]).float().cpu()
+        parity = dict(max_abs_err=float((got - kept[0]).abs().max()), tolerance=2e-3,
+                      sample=f"2 frames of a {w}x{h} synthetic clip, CUDA path vs CPU oracle port")
         cpu_baseline = dict(value=2 * (h * w) / float(H * W) / dt, unit="frames/s", cores=cores, kind="port",
                             sample=f"oracle port (PyTorch fp32, {cores} threads), 2 frames of a {w}x{h} "
                                    f"synthetic clip, one timed run after a 128x128 warm-up, 720p-equivalent")
@@ -427,7 +438,8 @@ def main():
                                             api="pnpvcve_b200.driver.ClipStreamer (chunked H2D/D2H overlapped with the kernels)"
                                             if streamer is not None else "net(...) per clip, whole-clip copies on side streams"),
                     gpu_launches=launches * world, roofline=roofline, roofline_warp=roofline_warp,
-                    kernels_ms=dict(block=mean_event_ms(prof["block"]), block_a=a_ms, block_b=b_ms, warp=w_ms), cpu_baseline=cpu_baseline)
+                    kernels_ms=dict(block=mean_event_ms(prof["block"]), block_a=a_ms, block_b=b_ms, warp=w_ms),
+                    cpu_baseline=cpu_baseline, parity=parity)
         _emit(line)
     if world > 1:
         dist.barrier()

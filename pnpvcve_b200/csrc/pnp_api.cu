@@ -387,6 +387,15 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   if (rowstack && c->idt && p.n_io < 3)
     return fail(PNP_ERR_RESOURCE, "pnp_conv3x3: row-stacked layout with idt needs 3 staging slots (drop aux)");
   p.s_a = (int)slots;
+  if (const char* ov = getenv("PNP_RINGS")) {     // diagnostic: "<n_io>,<s_a>" override of the shared-memory split
+    int nio = 0, sa = 0;
+    if (sscanf(ov, "%d,%d", &nio, &sa) == 2 && nio >= 2 && nio <= pnp::kMaxIoSlots && sa >= 4 && sa <= pnp::kMaxASlots &&
+        fixed_bytes(nio) + (long long)sa * pnp::kASlotBytes <= budget && !(rowstack && c->idt && nio < 3) &&
+        !(rowstack && c->par && nio != 3)) {
+      p.n_io = nio;
+      p.s_a = sa;
+    }
+  }
   cudaError_t e = rowstack ? pnp::launch_conv_rows(p, grid, static_cast<cudaStream_t>(stream))
                            : pnp::launch_conv(p, grid, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_conv3x3");
