@@ -202,6 +202,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
   // Threads that merely wait for work poll patiently (one lane per warp, hardware suspend hint): hot
   // try_wait loops of 256 epilogue lanes compete with the MMA operand fetch for the shared-memory pipe
   // (measured: N=192 MMAs ~25 % slower).  debug bit 32 selects patient polling, bit 64 shortens the hint.
+  const bool par_defer = kPar && p.par_split && (p.debug_skip & 1024);    // diagnostic, see the MMA issuer
   const bool hot_waits = (p.debug_skip & 32) == 0;
   const uint32_t hint_ns = (p.debug_skip & 64) ? 40u : 200u;
   auto pwait = [&](uint32_t bar, uint32_t parity, int tag) {      // one elected lane
@@ -227,7 +228,8 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         const int x0 = s.strip * kTilePx;
         for (int j = s.j_first; j <= s.j_last; ++j, ++sc, ar.advance()) {
           if (sc >= (uint32_t)s_a) {       // slot last used by step sc - s_a
-            const uint32_t ps = sc - s_a;
+            // with deferred 1x1 MMAs the row of step ps is still read during step ps + 1
+            const uint32_t ps = sc - s_a + (par_defer ? 1u : 0u);
             pwait(smem_u32(&misc->step_done[ps & (kStepRing - 1)]), (ps >> 3) & 1, 1);
           }
           const uint32_t fb = smem_u32(&misc->a_full[ar.slot]);
@@ -327,6 +329,20 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         }
       };
 
+      // the four 1x1 MMAs of output row `od` (source row descriptor a_row_) + their own commit
+      bool ppend = false;
+      uint32_t pp_arow = 0, pp_od = 0;
+      auto issue_par = [&](uint32_t a_row_, uint32_t od) {
+        // every reader warp has pulled row od-1's region into registers
+        spin_until_ge(go_par, (p.par_split ? 4u : (uint32_t)kEpilogueWarps) * od, 10);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_lo(tmem_base + kParCol, a_row_ + 8 + 2 * k, kDescHiSw128, par_w_lo + 2 * k, kDescHiSw128,
+                       idesc0 + 3 * idesc_step, k > 0);
+        umma_commit(smem_u32(&misc->par_done));
+      };
+
       // last value read from go_step: the scout usually runs several steps ahead (A ring depth, free
       // accumulator slots), so most steps need no shared-memory poll and no fence at all
       uint32_t go_seen = 0;
@@ -350,6 +366,10 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         auto step_body = [&](auto wrap_tag) {
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
+            if (kPar && dx == 1 && ppend) {       // previous row's 1x1 convs, behind this step's dx = 0 group
+              issue_par(pp_arow, pp_od);
+              ppend = false;
+            }
             if (tr && dx == 1) p.trace[cur_sc * 8 + 6] = clock64();
             if (dx == 2) {
               // barriers of the NEXT step, checked while ~8 MMAs of this step are still queued
@@ -392,23 +412,24 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
                          aux_w_lo + 2 * k, kDescHiSw128, idesc0 + idesc_step, 1);
         }
         if (kPar && centre) {
-          // Partition 1x1 convs of this row: centre pixel column (dx index 1), N = 192, own TMEM
-          // region.  Issued LAST in the step: the epilogue then has a whole step to read the region
-          // before the next row needs it (issued first, the hand-back sat on the critical path).
-          // every reader warp has pulled row cur_od-1's region into registers
-          spin_until_ge(go_par, (p.par_split ? 4u : (uint32_t)kEpilogueWarps) * cur_od, 10);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_lo(tmem_base + kParCol, a_row + 8 + 2 * k, kDescHiSw128, par_w_lo + 2 * k, kDescHiSw128,
-                         idesc0 + 3 * idesc_step, k > 0);
-          umma_commit(smem_u32(&misc->par_done));
+          // Partition 1x1 convs of this row: centre pixel column (dx index 1), N = 192, own TMEM region.
+          // Issued at the end of their own step.  Deferring them behind the dx = 0 group of the NEXT step (debug
+          // bit 1024: the wait for the region then comes a third of a step later) measured no difference once the
+          // region had its own reader warps (73.9 us either way): the step is bound by shared-memory wavefronts.
+          if (par_defer) {
+            ppend = true;
+            pp_arow = a_row;
+            pp_od = cur_od;
+          } else {
+            issue_par(a_row, cur_od);
+          }
         }
         pend = true;
         pend_bar = smem_u32(&misc->step_done[cur_sc & (kStepRing - 1)]);
         if (tr) p.trace[cur_sc * 8 + 1] = clock64();
         cur = nxt;
       }
+      if (kPar && ppend) issue_par(pp_arow, pp_od);      // the last row's 1x1 convs
       if (pend) umma_commit(pend_bar);
     }
   } else if (warp == 10) {
