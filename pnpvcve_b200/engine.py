@@ -409,6 +409,8 @@ class BaeEngine:
                     e1.record()
                     prof["warp"].append((e0, e1))
 
+            fast, wptr_cache = {}, {}       # per clip run: pre-filled block descriptors, weight pointers per mix
+
             def stack(name, blk_off, i, x, dst, mixed):
                 """8 BAE blocks: x (in xa/xb) -> dst.  ResidualBlockNoBNDynamic_drt, sr_backbone_utils.py:304-333"""
                 f = b * t + i
@@ -423,6 +425,46 @@ class BaeEngine:
                                    bias_tab[f, blk_off + k], st[name + "_conv1_b"][k], par)
                         x, other = o, x
                     counts[lane] += nb
+                    return
+                if prof is None or not ("block_a" in prof or "block_b" in prof):
+                    # Fast path (32 of a frame's ~42 launches): the two descriptors of every block are filled once per
+                    # clip run; per launch only the pointers that change are patched -- filling a 40-field ctypes
+                    # descriptor and slicing the bias table per launch cost ~16 us of host time per launch, 40 % of the
+                    # GPU time on a slow host.
+                    key = (name, par.stride(0), par.stride(1), par.stride(2))
+                    descs = fast.get(key)
+                    if descs is None:
+                        descs = []
+                        for k in range(nb):
+                            da, db = ops.ConvDesc(), ops.ConvDesc()
+                            ops.fill_conv_desc(da, x, mixed[name][k], buf["t"], None, None, None, bias_tab[f, blk_off + k],
+                                               par, PNP_ACT_RELU, None, None, wlayout=0 if not conv.rows_par else 1,
+                                               wpack_stable=True, par_sparse=conv.par_sparse)
+                            ops.fill_conv_desc(db, buf["t"], st[name + "_conv1_w"][k], other, None, x, None,
+                                               st[name + "_conv1_b"][k], None, PNP_ACT_NONE, None, None, wlayout=1,
+                                               flip_y=True, wpack_stable=True)
+                            descs.append((da, ctypes.byref(da), db, ctypes.byref(db)))
+                        fast[key] = descs
+                    wptrs = wptr_cache.get(id(mixed[name]))
+                    if wptrs is None:
+                        wptrs = wptr_cache[id(mixed[name])] = [wk.data_ptr() for wk in mixed[name]]
+                    x_ptr, o_ptr, dst_ptr = x.data_ptr(), other.data_ptr(), dst.data_ptr()
+                    par_ptr = par.data_ptr()
+                    bias_ptr = bias_tab.data_ptr() + (f * bias_tab.shape[1] + blk_off) * 256     # 64 fp32 per row
+                    fn = conv.fn
+                    for k in range(nb):
+                        da, ra, db, rb = descs[k]
+                        da.src, da.wpack, da.bias, da.par = x_ptr, wptrs[k], bias_ptr + 256 * k, par_ptr
+                        rc = fn(ra, stream)
+                        if rc != 0:
+                            _lib.check(rc, "pnp_conv3x3")
+                        nxt_ptr = dst_ptr if k == nb - 1 else o_ptr
+                        db.out, db.idt = nxt_ptr, x_ptr
+                        rc = fn(rb, stream)
+                        if rc != 0:
+                            _lib.check(rc, "pnp_conv3x3")
+                        x_ptr, o_ptr = nxt_ptr, x_ptr
+                    counts[lane] += 2 * nb
                     return
                 for k in range(nb):
                     conv(stream, x, mixed[name][k], out=buf["t"], bias=bias_tab[f, blk_off + k],
