@@ -185,3 +185,20 @@ def test_clip_streamer_equals_plain_forward(dev):
         assert torch.equal(o, r)
     assert st.h2d_bytes == sum(v.numel() * v.element_size() for v in hosts[0].values())
     assert st.d2h_bytes == refs[0].numel() * 4
+
+
+def test_profiled_launch_path_equals_fast_path(dev):
+    """bench.py's profile pass brackets block launches with events and therefore takes the per-launch descriptor path;
+    the default path patches pre-filled descriptors.  Same kernels, same arguments: bit-identical frames."""
+    sd = weights.random_state_dict(11, num_blocks=3)
+    net = build(sd, dev, num_blocks=3)
+    clip = synthetic.make_clip(72, 136, 5, seed=700, crf=25, ipb=True)
+    fast = run(net, clip, dev).clone()
+    net._engine.prof = {"block_a": [], "block_b": [], "warp": [], "phases": []}
+    net._engine.prof_every = 2
+    try:
+        slow = run(net, clip, dev)
+        assert len(net._engine.prof["block_a"]) > 0 and len(net._engine.prof["phases"]) > 0
+    finally:
+        net._engine.prof = None
+    assert torch.equal(fast, slow)
