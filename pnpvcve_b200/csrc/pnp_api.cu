@@ -352,6 +352,11 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   p.lq_up4 = c->lq_up4 ? 1 : 0;
   p.par_sparse = (c->par && c->par_sparse) ? 1 : 0;
   {
+    // diagnostic: block launch B (row-stacked, identity, bottom-up) reads t and x for the last time
+    const char* hp = getenv("PNP_L2_HINTS");
+    p.l2_dead_reads = (hp && atoi(hp) != 0 && rowstack && c->idt && c->flip_y) ? 1 : 0;
+  }
+  {
     const char* sp = getenv("PNP_PAR_SPLIT");     // diagnostic switch for the row-stacked partition variant (default on)
     p.par_split = (rowstack && c->par && !(sp && atoi(sp) == 0)) ? 1 : 0;
   }

@@ -46,6 +46,7 @@ struct ConvParams {
   int act;
   int mode;
   int flip_y;           // row-stacked kernel: walk the image bottom-up (weights packed with ky mirrored)
+  int l2_dead_reads;    // row-stacked kernel: src and identity are dead after this launch -> L2 evict_first on their loads
   int par_split;        // row-stacked partition variant: dedicated reader warps for the 1x1 accumulator region
   int par_sparse;       // partition blend: last non-zero class only, / 255 (the reference's sparse_val eval path)
   int lq_up4;           // kModeLast: lq is the (H/4, W/4) frame, the epilogue adds its x4 bilinear upsampling

@@ -220,6 +220,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
     // ============================================================ TMA producer (one elected lane)
     if (elect_one()) {
       if (!p.w_stable) load_weights();
+      const uint64_t pol_dead = l2_policy_evict_first();
       Ring ar(s_a);
       uint32_t sc = 0, ord = 0;            // step counter, output-row ordinal
       uint32_t aux_step[2] = {0, 0};       // step in which each aux slot was last consumed
@@ -237,7 +238,10 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
             mbar_arrive(fb);
           } else {
             mbar_arrive_expect_tx(fb, kRowBytes);
-            tma_load_4d(a_smem + ar.slot * kASlotBytes, &p.tm_src, fb, 0, x0 - 1, PNP_Y(s.y_b + j), s.n);
+            if (p.l2_dead_reads)
+              tma_load_4d_hint(a_smem + ar.slot * kASlotBytes, &p.tm_src, fb, 0, x0 - 1, PNP_Y(s.y_b + j), s.n, pol_dead);
+            else
+              tma_load_4d(a_smem + ar.slot * kASlotBytes, &p.tm_src, fb, 0, x0 - 1, PNP_Y(s.y_b + j), s.n);
           }
           if (j >= 0 && j < s.len) {       // per-output-row operands of row y_b + j
             if (p.aux_k16 > 0) {
@@ -697,7 +701,11 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
     auto load_id = [&](const TileCur& c, uint32_t slot) {
       const uint32_t ib = smem_u32(&misc->id_full[slot]);
       mbar_arrive_expect_tx(ib, kTileBytes);
-      tma_load_4d(io_smem + slot * kTileBytes, &p.tm_id, ib, 0, c.s.strip * kTilePx, PNP_Y(c.s.y_b + c.o), c.s.n);
+      if (p.l2_dead_reads)
+        tma_load_4d_hint(io_smem + slot * kTileBytes, &p.tm_id, ib, 0, c.s.strip * kTilePx, PNP_Y(c.s.y_b + c.o), c.s.n,
+                         l2_policy_evict_first());
+      else
+        tma_load_4d(io_smem + slot * kTileBytes, &p.tm_id, ib, 0, c.s.strip * kTilePx, PNP_Y(c.s.y_b + c.o), c.s.n);
     };
     if (p.has_id && store_warp) {
       if (elect_one()) {
