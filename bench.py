@@ -8,14 +8,18 @@ more per step) per GPU through the registry-built generator.  N>1 is launched by
 independent, so ranks share nothing on the data path (weak scaling) and only gather per-frame metrics.
 Rank 0 prints ONE JSON line:
 
-  value        frames/s with the clip already resident in HBM (CUDA events, max over ranks)
-  e2e          same through the public API from pinned HOST buffers: H2D of every input and D2H of
-               the enhanced frames inside the timed region
-  roofline     dominant kernel (fused 3x3 conv + three partition 1x1 convs): algorithmic FLOPs per
-               launch / mean launch duration (CUDA events bracketing those launches in the timed
-               steps) against the measured bf16 peak of MEASURED_PEAKS.json
+  value        frames/s with the clip already resident in HBM (CUDA events around the steps, NO events inside
+               them, max over ranks)
+  e2e          same from pinned HOST buffers through the public host-clip API (driver.ClipStreamer): H2D of
+               every input and D2H of the enhanced frames inside the timed region, overlapped with the kernels
+  roofline     dominant kernel (block launch A: 3x3 conv + three partition 1x1 convs): algorithmic FLOPs per
+               launch / mean launch duration, CUDA events bracketing every 8th such launch in a separate pass of
+               the same steps (an upper bound: the bracketed launch loses its programmatic-dependent-launch
+               overlap), against the measured sustained bf16 peak of MEASURED_PEAKS.json; block_pair = in-situ
+               time of a launch A + launch B pair from phase-boundary events around the undisturbed stacks
   roofline_warp  K1 (HBM bound), algorithmic bytes 264 B/px
   cpu_baseline the oracle port of the reference on this box's host cores, bounded sample
+  parity       max-abs error of the CUDA path against that oracle sample (same inputs, tolerance 2e-3)
 
 --impl reference times the reference's own algorithm (oracle port, PyTorch CPU, all host threads) on
 the same metric.  The oracle is only ever the thing measured beside us, never part of the product.
