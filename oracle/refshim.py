@@ -201,3 +201,65 @@ def build_reference(seed=0, **overrides):
     net = cls(**kw)
     net.eval()
     return net
+
+
+_restorer = None
+
+
+def load_restorer():
+    """The reference's own MODEL wrapper ``BasicVSR`` (mmedit/models/restorers/basicvsr.py, basic_restorer.py, base.py,
+    builder.py -- loaded unmodified), its ``MODELS`` registry and its ``build_model``.  ``mmedit.core`` is replaced by a
+    namespace holding the reference's own ``psnr`` / ``ssim`` / ``tensor2img`` functions (their sources are executed from
+    the reference files; the modules themselves import cv2-free parts of mmcv that the stub does not provide).  Used by
+    tests/test_restorer_dropin.py to drive the B200 generator through the reference's L2 -> L1 call."""
+    global _restorer
+    if _restorer is not None:
+        return _restorer
+    import ast
+    import math
+
+    import numpy as np
+    load_reference()
+    mmcv = sys.modules["mmcv"]
+    runner = sys.modules["mmcv.runner"]
+
+    def auto_fp16(apply_to=None, out_fp32=False):     # mmcv.runner.auto_fp16 is the identity unless fp16_enabled
+        def deco(fn):
+            return fn
+        return deco
+
+    runner.auto_fp16 = auto_fp16
+    mmcv.imwrite = lambda *a, **k: None
+
+    def load_functions(relpath, names, ns):
+        path = os.path.join(REFERENCE_ROOT, relpath)
+        tree = ast.parse(open(path).read())
+        for node in tree.body:
+            if isinstance(node, ast.FunctionDef) and node.name in names:
+                exec(compile(ast.Module([node], []), path + ":" + node.name, "exec"), ns)
+        return ns
+
+    try:
+        import cv2
+    except ImportError:  # psnr does not need it
+        cv2 = None
+    ns = dict(np=np, cv2=cv2, torch=torch, math=math, make_grid=None, mmcv=None)
+    load_functions("mmedit/core/evaluation/metrics.py", {"reorder_image", "psnr", "_ssim", "ssim"}, ns)
+    load_functions("mmedit/core/misc.py", {"tensor2img"}, ns)
+    core = types.ModuleType("mmedit.core")
+    core.psnr, core.ssim, core.tensor2img = ns["psnr"], ns["ssim"], ns["tensor2img"]
+    sys.modules["mmedit.core"] = core
+    sys.modules["mmedit"].core = core
+
+    _load_file("mmedit.models.base", "mmedit/models/base.py")
+    builder = _load_file("mmedit.models.builder", "mmedit/models/builder.py")
+    _namespace("mmedit.models.losses", "mmedit/models/losses")
+    _load_file("mmedit.models.losses.utils", "mmedit/models/losses/utils.py")
+    _load_file("mmedit.models.losses.pixelwise_loss", "mmedit/models/losses/pixelwise_loss.py")
+    _namespace("mmedit.models.restorers", "mmedit/models/restorers")
+    _load_file("mmedit.models.restorers.basic_restorer", "mmedit/models/restorers/basic_restorer.py")
+    vsr = _load_file("mmedit.models.restorers.basicvsr", "mmedit/models/restorers/basicvsr.py")
+    reg = sys.modules["mmedit.models.registry"]
+    _restorer = dict(BasicVSR=vsr.BasicVSR, MODELS=reg.MODELS, BACKBONES=reg.BACKBONES,
+                     build_model=builder.build_model, build_backbone=builder.build_backbone)
+    return _restorer

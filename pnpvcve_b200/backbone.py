@@ -158,6 +158,22 @@ class IconVSR_restore_wo_refill_mv_ipb_fast_domain_dynamic_with_par(nn.Module):
             self.upsample2 = _PixelShufflePack(mid_channels, 64, 2)
         self._engine = BaeEngine(self)
 
+    # packed weights follow the parameters: every path that rewrites them drops the engine's caches
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._engine.invalidate()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        res = super().load_state_dict(*args, **kwargs)
+        self._engine.invalidate()
+        return res
+
+    def invalidate_packed_weights(self):
+        """Call after writing parameters through ``.data`` (EMA swaps, ``p.data.copy_``): such writes do not bump
+        the parameter version the packed-weight cache is keyed on."""
+        self._engine.invalidate()
+
     # ------------------------------------------------------------------ reference API
     def init_weights(self, pretrained=None, strict=True):
         """iconvsr.py:510-523: str -> load checkpoint, None -> keep init, anything else -> TypeError."""

@@ -129,6 +129,7 @@ class BaeEngine:
         self.buf_key = None
         self.buf = None
         self.launch_count = 0
+        self._done = None         # (device, event recorded behind the last forward)
         #: set to {label: []} (labels: "block_a", "block_b", "input", "hr", "last", "warp") to have the
         #: next forward bracket those launches with CUDA events on the launching stream (bench.py);
         #: prof_every = N brackets only every N-th launch of a label (event records between kernels
@@ -151,7 +152,23 @@ class BaeEngine:
 
     # ------------------------------------------------------------------ weights
     def _param_key(self):
-        return tuple((id(p), p._version, p.device) for p in self.m.parameters())
+        # data_ptr: updates through ``p.data`` (``p.data = ...``, EMA weight swaps) re-seat the storage without
+        # bumping ``_version``; in-place writes through ``.data`` (``p.data.copy_``) change neither -- call
+        # ``invalidate()`` (the module does it from ``load_state_dict`` / ``_apply``) after such updates
+        return tuple((id(p), p._version, p.device, p.data_ptr()) for p in self.m.parameters())
+
+    def invalidate(self):
+        """Drop the packed / expert-mixed weights (re-packed by the next forward)."""
+        self.static = self.static_key = None
+        self.mix_cache = {}
+
+    # Copies and pickles of the owning module get a FRESH engine: packed weights, work buffers, streams, ctypes
+    # descriptors and events are per-process, per-device resources and are rebuilt on first use.
+    def __getstate__(self):
+        return {"m": self.m}
+
+    def __setstate__(self, state):
+        self.__init__(state["m"])
 
     def _pack_static(self, dev):
         """Weights that do not depend on the clip: packed once per checkpoint."""
@@ -298,8 +315,26 @@ class BaeEngine:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, lrs, QPs, slices, mvs, base_QPs, par_map, return_features=False, cond_host=None,
-                frame_ready=None, frame_done=None, out=None):
+    def forward(self, lrs, *args, **kwargs):
+        """Runs ``_forward`` with ``lrs.device`` as the current CUDA device (every launch of libpnpvcve goes to the
+        current device / its current stream; the reference accepts a module on a non-current device) and orders the
+        call behind the previous one: the work buffers are reused, so a call from another stream waits for the event
+        the previous call recorded."""
+        dev = lrs.device
+        if dev.type != "cuda":
+            raise RuntimeError("pnpvcve_b200 runs on sm_100 CUDA devices only; there is no CPU fallback")
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            if self._done is not None and self._done[0] == dev:
+                stream.wait_event(self._done[1])
+            res = self._forward(lrs, *args, **kwargs)
+            ev = self._done[1] if (self._done is not None and self._done[0] == dev) else torch.cuda.Event()
+            ev.record(stream)
+            self._done = (dev, ev)
+        return res
+
+    def _forward(self, lrs, QPs, slices, mvs, base_QPs, par_map, return_features=False, cond_host=None,
+                 frame_ready=None, frame_done=None, out=None):
         """cond_host: optional host copies (slices, base_QPs, QPs), each (n,T) -- skips the one device->host copy.
         frame_ready(i): called (host side) before frame i's lq / mvs / par_map are first read, in the backward-time
         pass (i = T-1 .. 0); frame_done(i, out): called after frame i's output has been enqueued.  Both let a caller
@@ -391,7 +426,9 @@ class BaeEngine:
             conv = buf["launcher"]
             conv.prof, conv.prof_every, conv.seen = prof, self.prof_every, seen
             conv.rows_par = self.rows_par
-            conv.par_sparse = bool(m.sparse_val)
+            # the reference takes the sparse path only in eval mode (sr_backbone_utils.py:307: `self.sparse_val and
+            # not self.training`); a module left in train() under no_grad computes the dense blend
+            conv.par_sparse = bool(m.sparse_val) and not m.training
             stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
             def warp(src, flow, dst):
@@ -417,7 +454,7 @@ class BaeEngine:
                 par = par_map[b0:b1, i]
                 other = buf["xb"] if x is buf["xa"] else buf["xa"]
                 if self.fused_block:
-                    if m.sparse_val:
+                    if conv.par_sparse:
                         raise NotImplementedError("PNP_FUSED_BLOCK has no sparse_val path; unset it")
                     for k in range(nb):
                         o = dst if k == nb - 1 else other

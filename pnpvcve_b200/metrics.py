@@ -38,8 +38,10 @@ def frame_quality(out, gt, crop_border=0):
     sse = torch.empty(f, dtype=torch.int64, device=out.device)
     ssum = torch.empty((f, 3), dtype=torch.float64, device=out.device)
     lib = _lib.load()
-    _lib.check(lib.pnp_frame_quality(_ptr(a), a.stride(0), a.stride(1), a.stride(2), _ptr(b), b.stride(0), b.stride(1),
-                                     b.stride(2), f, h, w, c, _ptr(sse), _ptr(ssum), _stream()), "pnp_frame_quality")
+    with torch.cuda.device(out.device):
+        rc = lib.pnp_frame_quality(_ptr(a), a.stride(0), a.stride(1), a.stride(2), _ptr(b), b.stride(0), b.stride(1),
+                                     b.stride(2), f, h, w, c, _ptr(sse), _ptr(ssum), _stream())
+    _lib.check(rc, "pnp_frame_quality")
     npix = 3 * (h - 2 * c) * (w - 2 * c)
     mse = sse.to(torch.float64) / npix
     psnr = torch.where(sse == 0, torch.full_like(mse, math.inf), 20.0 * torch.log10(255.0 / torch.sqrt(mse)))

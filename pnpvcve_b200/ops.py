@@ -19,6 +19,22 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_device_of(fn):
+    """Public wrappers launch on the device of their first tensor argument (libpnpvcve launches on the CURRENT
+    device / its current stream); the context switch is skipped when that device is already current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(t, *args, **kwargs):
+        if not t.is_cuda:
+            raise ValueError(f"{fn.__name__}: CUDA tensors only (there is no CPU path)")
+        if t.device.index == torch.cuda.current_device():
+            return fn(t, *args, **kwargs)
+        with torch.cuda.device(t.device):
+            return fn(t, *args, **kwargs)
+    return wrapped
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -49,6 +65,7 @@ def new_wpack(n_chunks, device):
     return torch.zeros(n_chunks * CHUNK_BYTES, dtype=torch.uint8, device=device)
 
 
+@_on_device_of
 def mv_warp(src, flow, dst, debug=False):
     """K1.  src/dst (N,H,W,64) bf16; flow (2,H,W) or (N,2,H,W) fp32 view (x then y).  Returns (x0,y0) if debug."""
     _feat_check(src, "src")
@@ -72,6 +89,7 @@ def mv_warp(src, flow, dst, debug=False):
     return (dx, dy) if debug else None
 
 
+@_on_device_of
 def lr_im2col(lr, dst):
     """lr (N,3,H,W) fp32 view -> dst (N,H,W,64) bf16 (channels 0..31 written)."""
     _plane_view_check(lr, "lr")
@@ -84,6 +102,7 @@ def lr_im2col(lr, dst):
                                  _stream()), "pnp_lr_im2col")
 
 
+@_on_device_of
 def pack_conv3x3(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=None, center_chunks=1,
                  row_scale=None):
     """w fp32 (O,I,3,3) or (E,O,I,3,3) contiguous -> packed blocks in dst (uint8)."""
@@ -109,6 +128,7 @@ def new_wpack_rowstack(device, tap_n=64, with_aux=False, with_par=False):
     return torch.zeros(n, dtype=torch.uint8, device=device)
 
 
+@_on_device_of
 def pack_conv3x3_rowstack(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=None, tap_n=64,
                           row_scale=None, flip_ky=False):
     """w fp32 (O,I,3,3) or (E,O,I,3,3) -> row-stacked blocks [kx][ky=2,1,0][tap_n rows] in dst."""
@@ -125,6 +145,7 @@ def pack_conv3x3_rowstack(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=
                                              _ptr(dst), tap_n, int(flip_ky), _stream()), "pnp_pack_conv3x3_rowstack")
 
 
+@_on_device_of
 def pack_rows(w2d, dst, row_offset):
     """fp32 (rows<=64, cols<=64) view -> packed rows row_offset.. of dst."""
     if w2d.dtype != torch.float32 or w2d.dim() != 2:
@@ -134,6 +155,7 @@ def pack_rows(w2d, dst, row_offset):
                                  _ptr(dst), row_offset, _stream()), "pnp_pack_rows")
 
 
+@_on_device_of
 def pack_aux(w, dst):
     if w.dtype != torch.float32 or not w.is_contiguous() or w.dim() != 4:
         raise ValueError("pack_aux: w must be contiguous fp32 (O,I,3,3)")
@@ -141,6 +163,7 @@ def pack_aux(w, dst):
     _lib.check(lib.pnp_pack_aux(_ptr(w), w.shape[0], w.shape[1], _ptr(dst), _stream()), "pnp_pack_aux")
 
 
+@_on_device_of
 def caa_heads(base_qp, qp, params, n_experts):
     """base_qp/qp: fp32 (F,) -> experts (F,E), gamma (F,64).  params: dict of the six CAA tensors."""
     f = base_qp.numel()
@@ -155,6 +178,7 @@ def caa_heads(base_qp, qp, params, n_experts):
     return experts, gamma
 
 
+@_on_device_of
 def mix_bias(conv2_bias, experts, gamma):
     """conv2_bias (B,E,64), experts (F,E), gamma (F,64) -> (F,B,64)."""
     b, e, _ = conv2_bias.shape
@@ -208,6 +232,7 @@ def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias
     return d
 
 
+@_on_device_of
 def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
             act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False, wpack_stable=False, lq_up4=False,
             par_sparse=False):
@@ -255,6 +280,7 @@ def fill_block_desc(d, x, out, w_stage1, w_stage2, bias1, bias2, par):
     return d
 
 
+@_on_device_of
 def resblock(x, out, w_stage1, w_stage2, par, bias1=None, bias2=None):
     """One fused BAE residual block (see include/pnp_vcve.h: pnp_resblock)."""
     _feat_check(x, "x")

@@ -31,13 +31,32 @@ def build_case(name):
     return sd, clip, gold
 
 
-def check_against_golden(out, gold, tol):
-    """max-abs error on the stored lattice + relative error of the float64 frame sums."""
+def residual_base(lq, vsr):
+    """The frame the generator adds its conv output to: the reflect-padded LR frame (iconvsr.py:371-394,
+    iconvsr_ipb_par.py:146) or, with vsr, its x4 bilinear upsampling (:41,140-141)."""
+    n, t, c, h, w = lq.shape
+    ph, pw = (4 - h % 4) % 4, (4 - w % 4) % 4
+    x = torch.nn.functional.pad(lq.reshape(-1, c, h, w), [0, pw, 0, ph], mode="reflect")
+    if vsr:
+        x = torch.nn.functional.interpolate(x, scale_factor=4, mode="bilinear", align_corners=False)
+    return x.view(n, t, c, *x.shape[-2:])
+
+
+def check_against_golden(out, gold, tol, lq=None, vsr=False):
+    """max-abs error on the stored fp32 lattice, on every other pixel (fp16 residuals: + 4e-5 of quantisation) when
+    ``lq`` is given, and relative error of the float64 frame sums."""
     out = out.detach().float().cpu()
     assert tuple(out.shape) == tuple(int(v) for v in gold["shape"])
     lat = torch.from_numpy(gold["lattice"])
     err = (out[..., ::2, ::2] - lat).abs().max().item()
     assert err <= tol, f"lattice max-abs {err:.3e} > {tol:.1e}"
+    if lq is not None:
+        res = out - residual_base(lq.float().cpu(), vsr)
+        off = torch.from_numpy(gold["off_lattice_f16"].astype(np.float32))
+        got = torch.stack([res[..., 0::2, 1::2], res[..., 1::2, 0::2], res[..., 1::2, 1::2]])
+        err_off = (got - off).abs().max().item()
+        assert err_off <= tol + 4e-5, f"off-lattice max-abs {err_off:.3e} > {tol:.1e} + 4e-5"
+        err = max(err, err_off - 4e-5)
     fs = out.double().sum(dim=(2, 3, 4)).numpy()
     npix = out.shape[2] * out.shape[3] * out.shape[4]
     sum_err = np.abs(fs - gold["frame_sum"]).max() / npix

@@ -53,7 +53,7 @@ def test_generator_matches_reference_golden(dev, name):
     net = build(sd, dev, vsr=bool(case.get("vsr")), sparse_val=bool(case.get("sparse_val")))
     out = run(net, clip, dev)
     assert out.dtype == torch.float32 and out.is_cuda
-    err = check_against_golden(out, gold, tol=TOL)
+    err = check_against_golden(out, gold, tol=TOL, lq=clip["lq"], vsr=bool(case.get("vsr")))
     assert net.gpu_launches > 0
     print(f"{name}: max-abs vs reference golden {err:.2e}")
 

@@ -19,7 +19,7 @@ def test_oracle_matches_reference_golden(name):
     case = golden_cases()[name]
     out = O.generator_forward(sd, *synthetic.generator_args(clip), vsr=bool(case.get("vsr")),
                               sparse_val=bool(case.get("sparse_val")))
-    err = check_against_golden(out, gold, tol=2e-6)
+    err = check_against_golden(out, gold, tol=2e-6, lq=clip["lq"], vsr=bool(case.get("vsr")))
     assert err < 2e-6
 
 
