@@ -1,10 +1,15 @@
 #!/usr/bin/env python
 """Benchmark of the BAE+CAA enhancement hot path (BASELINE.json: 720p enhanced frames/s + roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames T] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2|C3|C4|C5] [--frames T] [--clips n]
+                    [--impl ours|reference]
 
-A *step* is one synthetic REDS4-shape clip (1280x720, T frames, CRF cycling 15/25/35; --clips batches
-more per step) per GPU through the registry-built generator.  N>1 is launched by torchrun (one process per GPU); clips are
+A *step* is one batch of synthetic clips of the selected BASELINE.json config per GPU through the registry-built
+generator: C2 (default at N=1) one REDS4-shape clip 1280x720x100, per-frame random QPs, CRF cycling 15/25/35 over the
+steps; C3 (default at N>1, the config BASELINE.json quotes for 1/2/4/8 GPUs) the same with slice-type (IPB) conditioning;
+C4 sixteen 320x180x100 LR clips with MIXED CRFs in one call; C5 sixteen KITTI-shape 1244x376 frame pairs.  The N=1 line
+also carries `other_configs`: short resident runs of the configs that are not the selected one (frames/s, Mpx/s, and
+max-abs error of a sample against the CPU oracle port).  N>1 is launched by torchrun (one process per GPU); clips are
 independent, so ranks share nothing on the data path (weak scaling) and only gather per-frame metrics.
 Rank 0 prints ONE JSON line:
 
@@ -37,8 +42,35 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W = 720, 1280
+H, W = 720, 1280                            # the selected config's frame size (set by select_config)
 CRFS = (15, 25, 35)
+#: BASELINE.json configs 2-5 (config 1 is the CPU-runnable case of the parity tests)
+CONFIGS = {
+    "C2": dict(h=720, w=1280, t=100, ipb=False, clips=1, mv_qpel=64, pattern="IBBP", tag="720p",
+               desc="C2 HR_davis_LR_128x128 BAE+CAA forward, synthetic REDS4-shape clips 1280x720, per-frame random QPs"),
+    "C3": dict(h=720, w=1280, t=100, ipb=True, clips=1, mv_qpel=64, pattern="IBBP", tag="720p",
+               desc="C3 HR_davis_LR_128x128_IPB (slice-type I/P/B conditioning) BAE+CAA forward, synthetic 720p clips 1280x720"),
+    "C4": dict(h=180, w=320, t=100, ipb=True, clips=16, mv_qpel=32, pattern="IBBP", tag="lr_320x180",
+               desc="C4 HR_davis_LR_128x128_IPB_LR_test BAE+CAA forward, synthetic LR clips 320x180, many clips per call with mixed CRFs"),
+    "C5": dict(h=376, w=1244, t=2, ipb=True, clips=16, mv_qpel=64, pattern="IP", tag="kitti_1244x376",
+               desc="C5 HR_davis_LR_128x128_IPB BAE+CAA forward, synthetic KITTI-shape frame pairs 1242x375 pre-padded to 1244x376"),
+}
+CFG = dict(CONFIGS["C2"], name="C2")
+
+
+def select_config(args):
+    """Fix the workload: --config (default C2 at N=1, C3 at N>1), --frames / --clips override its T / clips per step."""
+    global H, W, CFG, METRIC
+    name = args.config or ("C2" if args.gpus <= 1 else "C3")
+    CFG = dict(CONFIGS[name], name=name)
+    if args.frames:
+        CFG["t"] = args.frames
+    if args.clips:
+        CFG["clips"] = args.clips
+    args.frames, args.clips = CFG["t"], CFG["clips"]
+    H, W = CFG["h"], CFG["w"]
+    METRIC = "enhanced_frames_per_sec_" + CFG["tag"]
+    return CFG
 FLOP_PER_PX_FRAME = 3205248                 # SURVEY.md section 8(d): dense convs, 2 FLOP per MAC
 FLOP_BLOCK_A_PER_PX = 2 * (64 * 64 * 9 + 3 * 64 * 64)
 WARP_BYTES_PER_PX = 2 * 64 * 2 + 8          # bf16 features in + out, fp32 2-channel flow
@@ -117,40 +149,65 @@ def cpu_oracle_step(sd, clip, keep=None):
     return dt
 
 
-def cpu_sample_shape(budget_s, n_steps):
-    """Pick the sample (2 frames, 720p or a centred crop of it) so n_steps steps fit the budget."""
+def cpu_px_rate():
+    """Pixels x frames per second of the oracle port on this host (probe on 128x128, scaled for large frames)."""
     from pnpvcve_b200 import synthetic, weights
     sd = weights.random_state_dict(0)
     probe = synthetic.make_clip(128, 128, 2, seed=1)
     cpu_oracle_step(sd, probe)                                   # page in / thread pool warm-up
     dt = cpu_oracle_step(sd, probe)
-    px_per_s = 2 * 128 * 128 / dt * 0.45                         # large frames run ~2x slower per pixel
-    for (h, w) in ((720, 1280), (360, 640), (180, 320)):
-        if n_steps * (2 * h * w / px_per_s) <= budget_s:
-            return h, w
-    return 128, 128
+    return 2 * 128 * 128 / dt * 0.45                             # large frames run ~2x slower per pixel
+
+
+def cpu_sample(budget_s, n_steps, cfg=None):
+    """The bounded sample of the workload one CPU step runs: (h, w, frames).  The config's own frame size with 2 frames
+    (I,B / I,P) or 1 frame (I) whenever n_steps of it fit the budget -- otherwise a centred crop, and the caller says so."""
+    cfg = cfg or CFG
+    rate = cpu_px_rate()
+    for (h, w) in ((cfg["h"], cfg["w"]), (cfg["h"] // 2, cfg["w"] // 2), (cfg["h"] // 4, cfg["w"] // 4)):
+        h, w = max(64, h // 4 * 4), max(64, w // 4 * 4)
+        for frames in (2, 1):
+            if n_steps * (frames * h * w / rate) <= budget_s:
+                return h, w, frames
+    return 64, 64, 1
+
+
+def make_cpu_clip(cfg, h, w, frames, crf=25):
+    from pnpvcve_b200 import synthetic
+    return synthetic.make_clip(h, w, frames, seed=2000, crf=crf, mv_qpel=cfg["mv_qpel"], ipb=cfg["ipb"],
+                               pattern=cfg["pattern"])
+
+
+def sample_text(cfg, h, w, frames):
+    full = (h, w) == (cfg["h"], cfg["w"])
+    return (f"{frames} frame{'s' if frames > 1 else ''} of a {w}x{h} synthetic clip"
+            + ("" if full else f" (crop of the {cfg['w']}x{cfg['h']} workload; value scaled by pixel count)"))
 
 
 def run_reference_arm(args):
     """--impl reference: rank 0 only; other ranks exit without work."""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    from pnpvcve_b200 import synthetic, weights
+    from pnpvcve_b200 import weights
+    cfg = select_config(args)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    h, w = cpu_sample_shape(150.0, args.steps + args.warmup)
+    h, w, frames = cpu_sample(200.0, args.steps + args.warmup)
     sd = weights.random_state_dict(0)
-    clip = synthetic.make_clip(h, w, 2, seed=2000, crf=25, mv_qpel=64)
+    clip = make_cpu_clip(cfg, h, w, frames)
     for _ in range(args.warmup):
         cpu_oracle_step(sd, clip)
     times = [cpu_oracle_step(sd, clip) for _ in range(args.steps)]
     total = sum(times)
-    value = args.steps * 2 * (h * w) / float(H * W) / total      # 720p-equivalent frames / s
-    sample = f"2 frames (I,B) of a {w}x{h} synthetic clip per step, 720p-equivalent frames/s"
+    value = args.steps * frames * (h * w) / float(H * W) / total      # frames of the config's size per second
+    sample = f"oracle port (PyTorch fp32, {cores} threads), per step " + sample_text(cfg, h, w, frames)
+    config = workload_config(args, 1)
+    # what this arm REALLY ran per step (a bounded sample of the workload above, tier rule 4)
+    config.update(sample=sample_text(cfg, h, w, frames), sample_height=h, sample_width=w, sample_frames=frames)
     line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * total / args.steps, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=workload_config(args, 1),
+                config=config,
                 cpu_baseline=dict(value=value, unit="frames/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
@@ -159,23 +216,55 @@ def run_reference_arm(args):
 
 
 def workload_config(args, world):
-    return dict(workload=f"C2 HR_davis_LR_128x128 BAE+CAA forward, synthetic REDS4-shape clip "
-                         f"1280x720x{args.frames} frames, CRF 15/25/35 cycling, random-init weights",
-                frames_per_clip=args.frames, clips_per_gpu_per_step=getattr(args, "clips", 1), height=H, width=W,
+    return dict(workload=f"{CFG['desc']}, {args.clips} clip(s) x {args.frames} frames per GPU per step, "
+                         f"CRF 15/25/35 {'mixed inside the batch' if args.clips > 1 else 'cycling over the steps'}, "
+                         "random-init weights",
+                config=CFG["name"], frames_per_clip=args.frames, clips_per_gpu_per_step=args.clips, height=H, width=W,
+                conditioning="slice type (IPB)" if CFG["ipb"] else "per-frame QP",
                 parallelism=f"clip-sharded x{world} (no data-path collective)",
-                l2="inputs (37 MB/frame) larger than L2; no flush needed")
+                l2=f"inputs ({40 * H * W * args.clips * args.frames / 1e6:.0f} MB per step) and every feature map "
+                   "pass exceed L2 between reuses; no flush needed" if 40 * H * W * args.clips * args.frames > 200e6
+                   else "three resident batches are rotated so that consecutive steps read different inputs")
 
 
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-def make_device_clip(frames, seed, crf, dev):
+def make_device_batch(cfg, frames, n, seed, crf0, dev):
+    """n clips of the config's shape; CRFs cycle inside the batch starting at index crf0 (mixed-CRF batches)."""
     from pnpvcve_b200 import synthetic
-    return synthetic.make_clip(H, W, frames, seed=seed, crf=crf, mv_qpel=64, ipb=False, device=dev)
+    return synthetic.cat_clips([
+        synthetic.make_clip(cfg["h"], cfg["w"], frames, seed=seed + 3 * k, crf=CRFS[(crf0 + k) % len(CRFS)],
+                            mv_qpel=cfg["mv_qpel"], ipb=cfg["ipb"], pattern=cfg["pattern"], device=dev)
+        for k in range(n)])
 
 
 def mean_event_ms(pairs):
     return sum(a.elapsed_time(b) for a, b in pairs) / max(len(pairs), 1)
+
+
+def ncu_traffic(substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes) of the first kernel whose name contains
+    `substr`, read from the newest committed capture profiles/r*_kernels_ncu_summary.csv (720p launches)."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_kernels_ncu_summary.csv")))
+    for path in reversed(files):
+        with open(path, newline="") as f:
+            rows = list(csv.reader(f))
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+        try:
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+        for r in rows[2:]:
+            if substr in r[0] and len(r) > max(ir, iw):
+                return (float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0),
+                        os.path.relpath(path, ROOT))
+    return None, None
 
 
 #: the ONE JSON line goes to the process's original stdout; everything else that native libraries print there
@@ -197,16 +286,71 @@ def _emit(line):
     out.flush()
 
 
+def timed_resident(net, batches, steps, warmup, dev):
+    """frames/s of `steps` resident steps (CUDA events, no events inside the steps)."""
+    from pnpvcve_b200 import synthetic
+    with torch.no_grad():
+        for i in range(warmup):
+            net(*synthetic.generator_args(batches[i % len(batches)]))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            net(*synthetic.generator_args(batches[(warmup + i) % len(batches)]))
+        e1.record()
+        torch.cuda.synchronize()
+    n, t = batches[0]["lq"].shape[:2]
+    return steps * n * t / (e0.elapsed_time(e1) * 1e-3), net.gpu_launches
+
+
+def other_configs_block(net, dev, main_name, cpu_budget_s=45.0):
+    """Short resident runs of the BASELINE configs that are not the selected one + a CPU-oracle sample of each
+    (CPU frames/s beside ours and the max-abs error of the CUDA path on that very sample)."""
+    from pnpvcve_b200 import synthetic, weights
+    res = {}
+    sd = weights.random_state_dict(0)
+    plan = dict(C2=dict(t=20, steps=2, warm=1), C3=dict(t=20, steps=2, warm=1), C4=dict(t=100, steps=2, warm=1),
+                C5=dict(t=2, steps=20, warm=3))
+    names = [n for n in ("C3", "C4", "C5", "C2") if n != main_name][:3]
+    for name in names:
+        cfg = dict(CONFIGS[name], name=name)
+        pl = plan[name]
+        net._engine.buf = None
+        torch.cuda.empty_cache()
+        batches = [make_device_batch(cfg, pl["t"], cfg["clips"], 5000 + 100 * j, j, dev) for j in range(2)]
+        fps, launches = timed_resident(net, batches, pl["steps"], pl["warm"], dev)
+        del batches
+        h, w, frames = cpu_sample(cpu_budget_s / len(names), 1, cfg)
+        clip = make_cpu_clip(cfg, h, w, frames, crf=35)
+        kept = []
+        dt = cpu_oracle_step(sd, clip, keep=kept)
+        with torch.no_grad():
+            got = net(*[a.to(dev) for a in synthetic.generator_args(clip)]).float().cpu()
+        res[name] = dict(workload=f"{cfg['desc']}, {cfg['clips']} clip(s) x {pl['t']} frames per step, mixed CRFs",
+                         frames_per_s=fps, mpx_per_s=fps * cfg["h"] * cfg["w"] / 1e6, steps=pl["steps"],
+                         gpu_launches_per_step=launches,
+                         tflops=FLOP_PER_PX_FRAME * cfg["h"] * cfg["w"] * fps / 1e12,
+                         max_abs_err=float((got - kept[0]).abs().max()), tolerance=2e-3,
+                         cpu_frames_per_s=frames * (h * w) / float(cfg["h"] * cfg["w"]) / dt,
+                         sample=sample_text(cfg, h, w, frames) + ", CUDA path vs CPU oracle port, CRF 35")
+    net._engine.buf = None
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=100)
-    ap.add_argument("--clips", type=int, default=1, help="clips per GPU per step")
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS),
+                    help="BASELINE.json config (default: C2 at --gpus 1, C3 at --gpus > 1)")
+    ap.add_argument("--frames", type=int, default=0, help="frames per clip (default: the config's)")
+    ap.add_argument("--clips", type=int, default=0, help="clips per GPU per step (default: the config's)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--prof-every", type=int, default=8,
                     help="bracket every N-th launch of the profiled kernels with CUDA events")
     args = ap.parse_args()
@@ -222,6 +366,7 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    cfg = select_config(args)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -235,12 +380,11 @@ def main():
     net.load_state_dict(weights.random_state_dict(0), strict=True)
     net = net.to(dev).eval()
     T = args.frames
-    n_steps = args.warmup + args.steps
-    # resident batches of `args.clips` clips, one batch per CRF, reused across steps (generation is not
-    # part of the job)
     nc = args.clips
-    clips = [synthetic.cat_clips([make_device_clip(T, 2000 + 10 * rank + 3 * k + j, CRFS[j], dev)
-                                  for k in range(nc)]) for j in range(len(CRFS))]
+    px = H * W * nc                              # pixels per launch (nc images)
+    # three resident batches of `nc` clips, reused across steps (generation is not part of the job); with one clip
+    # per step the CRF cycles 15/25/35 over the steps, with several the CRFs are mixed inside every batch
+    clips = [make_device_batch(cfg, T, nc, 2000 + 10 * rank + 100 * j, j, dev) for j in range(len(CRFS))]
 
     def barrier():
         if world > 1:
@@ -306,35 +450,38 @@ def main():
     a_ms = mean_event_ms(prof["block_a"])
     b_ms = mean_event_ms(prof["block_b"])
     w_ms = mean_event_ms(prof["warp"])
-    a_tflops = FLOP_BLOCK_A_PER_PX * H * W / (a_ms * 1e-3) / 1e12 if a_ms else 0.0
-    w_gbs = WARP_BYTES_PER_PX * H * W / (w_ms * 1e-3) / 1e9 if w_ms else 0.0
+    a_tflops = FLOP_BLOCK_A_PER_PX * px / (a_ms * 1e-3) / 1e12 if a_ms else 0.0
+    w_gbs = WARP_BYTES_PER_PX * px / (w_ms * 1e-3) / 1e9 if w_ms else 0.0
     steps_ms = total_ms / args.steps
     # share of the (profiled) step spent in this kernel: bracketed launches x sampling stride / profiled step time
     share_a = a_ms * len(prof["block_a"]) * args.prof_every / prof_steps / prof_step_ms if a_ms else 0.0
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch at 720p from the newest committed ncu capture (algorithmic
+    # bytes of launch A: 118 (x) + 11 (partition planes) + 118 (t) = 247 MB; of the warp: 243 MB); null off 720p
+    at_720p = (H, W, nc) == (720, 1280, 1)
+    a_traffic, a_src = ncu_traffic("conv3x3_rows_kernel<1") if at_720p else (None, None)
+    w_traffic, w_src = ncu_traffic("mv_warp_kernel") if at_720p else (None, None)
+    per_gpu_tflops = FLOP_PER_PX_FRAME * H * W * (value / world) / 1e12
+    pair_flop = (FLOP_BLOCK_A_PER_PX + 2 * 64 * 64 * 9) * px
     roofline = dict(bound="tensor", kernel="conv3x3_rows_kernel<1,0> (block launch A: row-stacked 3x3 + three partition 1x1 convs, N=192 MMAs, split-role epilogue)",
                     achieved=a_tflops, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
                     frac=a_tflops / peaks["bf16_tflops_sustained"],
-                    # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at 720p, from the
-                    # committed capture profiles/r01c_kernels_ncu_summary.csv (135.55 + 74.66 MB); the
-                    # algorithmic bytes are 118 (x) + 11 (partition planes) + 118 (t) = 247 MB
-                    traffic=210.21e6, traffic_unit="bytes/launch",
+                    traffic=a_traffic, traffic_unit="bytes/launch", traffic_source=a_src,
+                    algorithmic_flop_per_launch=FLOP_BLOCK_A_PER_PX * px,
                     peak_source=f"{peaks['source']} sustained cuBLAS bf16 (kernel timed inside a long step)",
                     ms_per_launch=a_ms, launches_timed=len(prof["block_a"]), timed_every=args.prof_every,
                     share_of_step=share_a,
                     # launch A + launch B of one BAE block, from phase-boundary events around the undisturbed 8-block stacks
-                    block_pair=dict(us=pair_us, tflops=(FLOP_BLOCK_A_PER_PX + 2 * 64 * 64 * 9) * H * W / (pair_us * 1e-6) / 1e12
-                                    if pair_us else 0.0,
-                                    frac=(FLOP_BLOCK_A_PER_PX + 2 * 64 * 64 * 9) * H * W / (pair_us * 1e-6) / 1e12
-                                    / peaks["bf16_tflops_sustained"] if pair_us else 0.0,
+                    block_pair=dict(us=pair_us, tflops=pair_flop / (pair_us * 1e-6) / 1e12 if pair_us else 0.0,
+                                    frac=pair_flop / (pair_us * 1e-6) / 1e12 / peaks["bf16_tflops_sustained"] if pair_us else 0.0,
                                     note="bracketing single launches defeats programmatic dependent launch, so ms_per_launch "
                                          "is an upper bound; this is the in-situ time of the A+B pair"),
-                    whole_path_tflops=FLOP_PER_PX_FRAME * H * W * value / 1e12,
-                    whole_path_frac=FLOP_PER_PX_FRAME * H * W * value / 1e12 / peaks["bf16_tflops_sustained"])
+                    # per GPU: the all-rank value divided by the world size
+                    whole_path_tflops=per_gpu_tflops,
+                    whole_path_frac=per_gpu_tflops / peaks["bf16_tflops_sustained"])
     roofline_warp = dict(bound="hbm", kernel="mv_warp_kernel", achieved=w_gbs, peak=peaks["hbm_gbs"],
                          unit="GB/s", frac=w_gbs / peaks["hbm_gbs"],
-                         # profiles/r01c_kernels_ncu_summary.csv: 92.36 + 71.24 MB (algorithmic 243.3 MB;
-                         # part of the source rows is still in L2 from the producing kernel)
-                         traffic=163.61e6, traffic_unit="bytes/launch", ms_per_launch=w_ms,
+                         traffic=w_traffic, traffic_unit="bytes/launch", traffic_source=w_src,
+                         algorithmic_bytes_per_launch=WARP_BYTES_PER_PX * px, ms_per_launch=w_ms,
                          launches_timed=len(prof["warp"]), peak_source=peaks["source"])
 
     # ---------------- end to end from pinned host buffers (e2e)
@@ -342,23 +489,9 @@ def main():
     out_host = torch.empty((nc, T, 3, H, W), dtype=torch.float32).pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     d2h = out_host.numel() * out_host.element_size()
+    streamer = driver.ClipStreamer(net, dev, chunk=max(1, min(10, T)))
 
-    # Software-pipelined like a real serving loop: a copy stream uploads clip i+1 while clip i is
-    # enhanced, a second one downloads the frames of clip i-1.  Every step still pays its full H2D
-    # and D2H inside the timed region; only their overlap with compute is exploited.
-    main = torch.cuda.current_stream()
-    up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-
-    def upload():
-        with torch.cuda.stream(up):
-            clip = {k: v.to(dev, non_blocking=True) for k, v in host[0].items()}
-            ev = torch.cuda.Event()
-            ev.record(up)
-        return clip, ev
-
-    streamer = driver.ClipStreamer(net, dev, chunk=10) if nc == 1 else None
-
-    def run_e2e_streamed(n_steps):
+    def run_e2e(n_steps):
         """The public host-clip API (driver.ClipStreamer): frames are uploaded in chunks in the order the backward-time
         pass reads them, finished frames are downloaded chunk by chunk; every step still copies all of its inputs from
         pinned host memory and all of its frames back inside the timed region."""
@@ -371,35 +504,13 @@ def main():
             ticket = nxt
         streamer.finish()
 
-    def run_e2e(n_steps):
-        if streamer is not None:
-            return run_e2e_streamed(n_steps)
-        nxt = upload()
-        for i in range(n_steps):
-            clip, ev = nxt
-            if i + 1 < n_steps:
-                nxt = upload()
-            main.wait_event(ev)
-            out = net(*synthetic.generator_args(clip))
-            for v in clip.values():
-                v.record_stream(main)
-            local = driver.frame_metrics(out)
-            driver.gather_metrics(local.mean(0, keepdim=True), world, rank, world)
-            done = torch.cuda.Event()
-            done.record(main)
-            with torch.cuda.stream(down):
-                down.wait_event(done)
-                out_host.copy_(out, non_blocking=True)
-                out.record_stream(down)
-        main.wait_stream(down)
-
     del clips
     torch.cuda.empty_cache()
     with torch.no_grad():
         # two warm-up steps: the streamer double-buffers its device copies, so the second step still allocates
         # (GB-sized cudaMallocs inside the timed region made this number swing between 230 and 300 frames/s)
         e2e_warm = min(args.warmup, 2) if args.frames >= 50 else args.warmup
-        run_e2e(max(e2e_warm, 1))
+        run_e2e(max(e2e_warm, 2))
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2e_steps = args.steps
@@ -411,27 +522,33 @@ def main():
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_steps * T * nc / (float(ms2.item()) / 1e3)
+    del streamer, host, out_host
+    torch.cuda.empty_cache()
 
     # ---------------- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample
     cpu_baseline = None
     parity = None
+    others = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        h, w = cpu_sample_shape(30.0, 1)
+        h, w, frames = cpu_sample(30.0, 1)
         sd = weights.random_state_dict(0)
-        clip = synthetic.make_clip(h, w, 2, seed=2000, crf=25, mv_qpel=64)
+        clip = make_cpu_clip(cfg, h, w, frames)
         kept = []
         dt = cpu_oracle_step(sd, clip, keep=kept)
         # the oracle's frames of that sample double as the checker of the CUDA path on the same inputs (max-abs on
-        # [0,1] frames, tolerance 2e-3 of north_star) -- the sample is 720p whenever the budget allows
+        # [0,1] frames, tolerance 2e-3 of north_star) -- the sample has the config's frame size whenever the budget allows
         with torch.no_grad():
             got = net(*[a.to(dev) for a in synthetic.generator_args(clip)]).float().cpu()
         parity = dict(max_abs_err=float((got - kept[0]).abs().max()), tolerance=2e-3,
-                      sample=f"2 frames of a {w}x{h} synthetic clip, CUDA path vs CPU oracle port")
-        cpu_baseline = dict(value=2 * (h * w) / float(H * W) / dt, unit="frames/s", cores=cores, kind="port",
-                            sample=f"oracle port (PyTorch fp32, {cores} threads), 2 frames of a {w}x{h} "
-                                   f"synthetic clip, one timed run after a 128x128 warm-up, 720p-equivalent")
+                      sample=sample_text(cfg, h, w, frames) + ", CUDA path vs CPU oracle port; the headline lengths "
+                             "(T=100) are covered by tests/test_gpu_headline.py, table in profiles/r02_error_vs_frame.json")
+        cpu_baseline = dict(value=frames * (h * w) / float(H * W) / dt, unit="frames/s", cores=cores, kind="port",
+                            sample=f"oracle port (PyTorch fp32, {cores} threads), " + sample_text(cfg, h, w, frames)
+                                   + ", one timed run after a 128x128 warm-up")
+        if not args.no_other_configs:
+            others = other_configs_block(net, dev, cfg["name"])
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps,
@@ -439,11 +556,11 @@ def main():
                     vs_baseline=None, dtype="bf16", data="synthetic", config=workload_config(args, world),
                     clocks=clocks, e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d,
                                             d2h_bytes_per_step=d2h, steps=e2e_steps,
-                                            api="pnpvcve_b200.driver.ClipStreamer (chunked H2D/D2H overlapped with the kernels)"
-                                            if streamer is not None else "net(...) per clip, whole-clip copies on side streams"),
-                    gpu_launches=launches * world, roofline=roofline, roofline_warp=roofline_warp,
+                                            api="pnpvcve_b200.driver.ClipStreamer (chunked H2D/D2H overlapped with the kernels)"),
+                    gpu_launches=launches * world, launch_mode=net._engine.last_mode, roofline=roofline,
+                    roofline_warp=roofline_warp,
                     kernels_ms=dict(block=mean_event_ms(prof["block"]), block_a=a_ms, block_b=b_ms, warp=w_ms),
-                    cpu_baseline=cpu_baseline, parity=parity)
+                    mpx_per_s=value * H * W / 1e6, cpu_baseline=cpu_baseline, parity=parity, other_configs=others)
         _emit(line)
     if world > 1:
         dist.barrier()

@@ -129,6 +129,7 @@ class BaeEngine:
         self.buf_key = None
         self.buf = None
         self.launch_count = 0
+        self.last_mode = "eager"   # how the last forward launched its frame steps: "eager" | "graph"
         self._done = None         # (device, event recorded behind the last forward)
         #: set to {label: []} (labels: "block_a", "block_b", "input", "hr", "last", "warp") to have the
         #: next forward bracket those launches with CUDA events on the launching stream (bench.py);
