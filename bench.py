@@ -315,7 +315,7 @@ def other_configs_block(net, dev, main_name, cpu_budget_s=45.0):
     for name in names:
         cfg = dict(CONFIGS[name], name=name)
         pl = plan[name]
-        net._engine.buf = None
+        net._engine.prog = None
         torch.cuda.empty_cache()
         batches = [make_device_batch(cfg, pl["t"], cfg["clips"], 5000 + 100 * j, j, dev) for j in range(2)]
         fps, launches = timed_resident(net, batches, pl["steps"], pl["warm"], dev)
@@ -333,7 +333,7 @@ def other_configs_block(net, dev, main_name, cpu_budget_s=45.0):
                          max_abs_err=float((got - kept[0]).abs().max()), tolerance=2e-3,
                          cpu_frames_per_s=frames * (h * w) / float(cfg["h"] * cfg["w"]) / dt,
                          sample=sample_text(cfg, h, w, frames) + ", CUDA path vs CPU oracle port, CRF 35")
-    net._engine.buf = None
+    net._engine.prog = None
     torch.cuda.empty_cache()
     return res
 

@@ -35,10 +35,45 @@ typedef enum pnp_status {
 int pnp_abi_version(void);
 const char* pnp_last_error(void);          /* message of the last failing call in this thread */
 int pnp_device_check(void);                /* PNP_OK iff the current device is sm_100 */
-/* Diagnostic knob for the UMMA shared-memory descriptor of pixel-shifted views.
- * 0 (default, measured-correct on B200): base_offset = 0 (swizzle acts on absolute address bits);
- * 1: base_offset = (addr >> 7) & 7. */
-int pnp_set_base_offset_mode(int mode);
+
+/*
+ * Launch tables and CUDA graphs -- the launch-free frame loop.
+ *
+ * The reference's generator is a Python loop over frames that launches ~300 library kernels per frame
+ * (mmedit/models/backbones/sr_backbones/iconvsr_ipb_par.py:71-147).  Here a frame step is a fixed sequence of
+ * ~20-25 kernels whose operands differ from frame to frame only in a few pointers / image indices.  Those live in a
+ * device-resident TABLE of 64-byte entries written once per clip; a kernel launched in table mode reads entry
+ *     table[*step * stride + node]
+ * so its kernel parameters are constant for the clip and the whole step can be captured ONCE in a CUDA graph and
+ * replayed for every frame: per step the host sets the step word and launches one graph (pnp_graph_launch).
+ * Entry layout by operation (unused fields are ignored):
+ *   pnp_conv3x3  : p[0] wpack, p[1] bias, p[2] par, p[3] lq, p[4] outf, p[5] img_off (int64 pairs, see below) or 0;
+ *                  i[0..3] first image of src / aux / idt / out inside the buffers the descriptor points to
+ *   pnp_mv_warp  : p[0] src, p[1] flow_x, p[2] flow_y, p[3] dst
+ *   pnp_lr_im2col: p[0] lr, p[1] dst
+ */
+typedef struct pnp_dyn_entry {
+  uint64_t p[6];
+  int32_t i[4];
+} pnp_dyn_entry;
+
+typedef struct pnp_dyn_ref {
+  const pnp_dyn_entry* table; /* device memory; NULL = static launch (operands are the call's own arguments) */
+  const int32_t* step;        /* device word holding the current step */
+  int32_t node;               /* index of this launch inside its step */
+  int32_t stride;             /* entries per step */
+} pnp_dyn_ref;
+
+/* Stream capture of the calls made between begin and end into an executable graph (thin wrappers over
+ * cudaStreamBeginCapture / cudaStreamEndCapture / cudaGraphInstantiate; programmatic-dependent-launch edges between the
+ * conv kernels are kept).  The graph handle is the only object this library ever owns; destroy it with
+ * pnp_graph_destroy.  pnp_graph_launch first stores `step_value` into *step_word (stream ordered; NULL to skip) and
+ * then launches the graph; pnp_set_step does only the store (for launching the same sequence without a graph). */
+int pnp_graph_begin(void* stream);
+int pnp_graph_end(void* stream, void** graph_exec);
+int pnp_graph_launch(void* graph_exec, int32_t* step_word, int32_t step_value, void* stream);
+int pnp_graph_destroy(void* graph_exec);
+int pnp_set_step(int32_t* step_word, int32_t step_value, void* stream);
 
 /*
  * K1 -- MV-guided bilinear warp of a 64-channel feature map.
@@ -53,6 +88,9 @@ int pnp_set_base_offset_mode(int mode);
 int pnp_mv_warp(const void* src, const float* flow_x, const float* flow_y, int64_t flow_row_stride,
                 int64_t flow_image_stride, void* dst, int N, int H, int W, int32_t* dbg_x0,
                 int32_t* dbg_y0, void* stream);
+/* table mode: src / flow_x / flow_y / dst come from the launch table (no debug outputs) */
+int pnp_mv_warp_dyn(const pnp_dyn_ref* dyn, int64_t flow_row_stride, int64_t flow_image_stride, int N, int H, int W,
+                    void* stream);
 
 /*
  * LR frames -> im2col'd bf16 operand (N, H, W, 64), channel k = tap*3 + c for k < 27, zero for
@@ -62,36 +100,36 @@ int pnp_mv_warp(const void* src, const float* flow_x, const float* flow_y, int64
  */
 int pnp_lr_im2col(const float* lr, int64_t sn, int64_t sc, int64_t sy, void* dst, int N, int H, int W,
                   void* stream);
+/* table mode: lr / dst come from the launch table */
+int pnp_lr_im2col_dyn(const pnp_dyn_ref* dyn, int64_t sn, int64_t sc, int64_t sy, int N, int H, int W, void* stream);
 
 /*
- * K4 -- weight packing (run once per checkpoint / once per distinct CRF, results stay resident).
- * A packed conv is a sequence of 8192-byte blocks, [64 out][64 in] bf16, rows pre-swizzled for the
- * tensor-core shared-memory layout, centre tap first (center_chunks blocks), then taps
- * 0,1,2,3,5,6,7,8.
- *   pnp_pack_conv3x3: w is fp32 (E, out_ch, in_total, 3, 3); block = sum_e coef[e]*w[e] restricted to
- *     input channels [in_begin, in_begin+in_count) (+ the slice at in_begin2 if >= 0).  coef is a
- *     DEVICE pointer to E floats or NULL (E must then be 1).  Replaces the per-block, per-frame
- *     torch.mm expert mixing of Dynamic_conv2d_se.forward (sr_backbone_utils.py:198-199).  row_scale is a
- *     DEVICE pointer to out_ch floats multiplied into the rows (the SE gain of sr_backbone_utils.py:207-208
- *     folded into the kernel: (conv(x,W)+b)*g == conv(x, g*W) + g*b), or NULL.
- *   pnp_pack_rows: fp32 matrix (rows<=64, cols<=64; element strides) into packed rows
- *     row_offset.. of dst (used for the three 1x1 partition convs, sr_backbone_utils.py:285-287,
- *     stacked under the centre tap: rows 64.., 128.., 192..).
+ * K4 -- weight packing (run once per checkpoint / once per distinct (CRF, QP) condition, results stay resident).
+ * Packed operands are 128-byte rows [out channel][64 in channels] bf16, pre-swizzled for the tensor-core
+ * shared-memory layout (16-byte column group g of row r at g ^ (r & 7)).
+ *   pnp_pack_conv3x3_rowstack: w is fp32 (E, out_ch, in_total, 3, 3); the result is sum_e coef[e]*w[e] restricted to
+ *     input channels [in_begin, in_begin+in_count) (+ the slice at in_begin2 if >= 0), laid out per kx as one block of
+ *     3*tap_n rows, sub-block sb = 0,1,2 holding ky = 2 - sb (flip_ky: ky = sb), so that one source row can be multiplied
+ *     against the weights of the three output rows it feeds in a single N = 3*tap_n MMA.  tap_n is 64, or 16 for the
+ *     64->3 tail; 9*tap_n*128 bytes.  coef is a DEVICE pointer to E floats or NULL (E must then be 1); it replaces the
+ *     per-block, per-frame torch.mm expert mixing of Dynamic_conv2d_se.forward (sr_backbone_utils.py:198-199).
+ *     row_scale is a DEVICE pointer to out_ch floats multiplied into the rows (the SE gain of
+ *     sr_backbone_utils.py:207-208 folded into the kernel: (conv(x,W)+b)*g == conv(x, g*W) + g*b), or NULL.
+ *   pnp_pack_rows: fp32 matrix (rows<=64, cols<=64; element strides) into packed rows row_offset.. of dst (the three
+ *     1x1 partition convs, sr_backbone_utils.py:285-287, as 192 rows behind a row-stacked pack).
  *   pnp_pack_aux: first 3 input channels of w (out_ch, in_total, 3, 3) as one [64][tap*3+c] block.
+ *   pnp_pack_mix_blocks: the block-launch-A packs of ALL n_blocks BAE blocks for one condition in one launch:
+ *     w2 fp32 (n_blocks, E, 64, 64, 3, 3), w1x1 fp32 (n_blocks, 3, 64, 64); block b is written at
+ *     dst + b*dst_block_stride as [row-stacked row_scale*sum_e coef[e]*w2[b][e] (73728 B)][192 rows of w1x1[b] (24576 B)].
  */
-int pnp_pack_conv3x3(const float* w, int n_experts, const float* coef, const float* row_scale, int out_ch,
-                     int in_total, int in_begin, int in_begin2, int in_count, void* dst, int center_chunks,
-                     void* stream);
-int pnp_pack_rows(const float* w, int rows, int cols, int64_t row_stride, int64_t col_stride, void* dst,
-                  int row_offset, void* stream);
-/* Row-stacked layout (pnp_conv_desc.wlayout = PNP_WLAYOUT_ROWSTACK): per kx one block of 3*tap_n
- * 128-byte rows, sub-block sb = 0,1,2 holding ky = 2 - sb, so that one source row can be multiplied
- * against the weights of the three output rows it feeds in a single N = 3*tap_n MMA.  tap_n is 64, or
- * 16 for the 64->3 tail; total 9*tap_n*128 bytes.  Same mixing arguments as pnp_pack_conv3x3. */
 int pnp_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, const float* row_scale,
                               int out_ch, int in_total, int in_begin, int in_begin2, int in_count, void* dst,
                               int tap_n, int flip_ky, void* stream);
+int pnp_pack_rows(const float* w, int rows, int cols, int64_t row_stride, int64_t col_stride, void* dst,
+                  int row_offset, void* stream);
 int pnp_pack_aux(const float* w, int out_ch, int in_total, void* dst, void* stream);
+int pnp_pack_mix_blocks(const float* w2, const float* w1x1, int n_blocks, int n_experts, const float* coef,
+                        const float* row_scale, void* dst, int64_t dst_block_stride, void* stream);
 
 /*
  * CAA heads for `frames` frames: experts (frames, n_experts) = Base_Predictor(base_qp)
@@ -157,7 +195,6 @@ int pnp_frame_quality(const float* a, int64_t a_sf, int64_t a_sc, int64_t a_sy, 
  * input_conv (basicvsr_net.py:484,515), conv_hr/conv_last (iconvsr_ipb_par.py:144-146).
  */
 enum { PNP_CONV_BF16 = 0, PNP_CONV_LAST = 1 };
-enum { PNP_WLAYOUT_TAPMAJOR = 0, PNP_WLAYOUT_ROWSTACK = 1 };
 enum { PNP_ACT_NONE = 0, PNP_ACT_LRELU = 1, PNP_ACT_RELU = 2 };
 
 typedef struct pnp_conv_desc {
@@ -165,36 +202,32 @@ typedef struct pnp_conv_desc {
   const void* aux;     /* bf16 (N,H,W,64) im2col'd LR, or NULL */
   const void* idt;     /* bf16 (N,H,W,64) added before the activation, or NULL */
   void* out;           /* bf16 (N,H,W,64); PNP_CONV_BF16 only */
-  const void* wpack;   /* packed weights, n_wchunks * 8192 bytes */
+  const void* wpack;   /* pnp_pack_conv3x3_rowstack output (9*tap_n*128 bytes), followed by the 8192-byte
+                          pnp_pack_aux block when aux is given, or by the three 1x1 partition convs as 192 packed rows
+                          (pnp_pack_rows, offsets 0/64/128 from there) when par is given; par excludes aux and idt */
   const float* scale;  /* [64] or NULL */
   const float* bias;   /* [64] ([3] for PNP_CONV_LAST) or NULL */
-  const float* par;    /* fp32 (N,3,H,W) view of the partition map or NULL; needs center_n == 256 */
+  const float* par;    /* fp32 (N,3,H,W) view of the partition map or NULL: block launch A */
   int64_t par_sn, par_sc, par_sy;
   const float* lq;     /* PNP_CONV_LAST: fp32 (N,3,H,W) view */
   int64_t lq_sn, lq_sc, lq_sy;
   float* outf;         /* PNP_CONV_LAST: fp32 (N,3,H,W) view */
   int64_t of_sn, of_sc, of_sy;
   int32_t N, H, W;
-  int32_t n_wchunks;   /* 9, 10 (with aux) or 12 (with par) */
-  int32_t center_n;    /* 64, 256 (with par) or 16 (PNP_CONV_LAST) */
-  int32_t tap_n;       /* 64 or 16 */
+  int32_t tap_n;       /* 64, or 16 for PNP_CONV_LAST */
   int32_t aux_k16;     /* K/16 of aux (2 for the 27-entry LR im2col), 0 without aux */
   int32_t act;
   int32_t mode;
-  int32_t wlayout;     /* PNP_WLAYOUT_TAPMAJOR (n_wchunks blocks) or PNP_WLAYOUT_ROWSTACK (9*tap_n*128 bytes,
-                          followed by the 8192-byte aux block when aux is given, or by the three 1x1
-                          partition convs as 192 packed rows (pnp_pack_rows, offsets 0/64/128 from there)
-                          when par is given; par then excludes aux and idt) */
-  int32_t flip_y;      /* PNP_WLAYOUT_ROWSTACK only: process rows bottom-up.  The result is identical when wpack
-                          was packed with flip_ky = 1; alternating directions between dependent launches
-                          makes each launch read first what its predecessor wrote last (L2 hits). */
+  int32_t flip_y;      /* process rows bottom-up.  The result is identical when wpack was packed with flip_ky = 1;
+                          alternating directions between dependent launches makes each launch read first what its
+                          predecessor wrote last (L2 hits). */
   int64_t out_spx, out_sy, out_sn; /* element strides of `out` between pixels / rows / images; all 0 = contiguous
                           (64, 64*W, 64*H*W).  A strided view makes the TMA store a scatter: launch g of a
                           PixelShufflePack (upsample.py:46-49, scale 2) writes its 64 channels to
                           up[:, i::2, j::2, :] -- the pixel shuffle is the store epilogue.  Multiples of 8. */
   int32_t lq_up4;      /* PNP_CONV_LAST: 1 = `lq` is the (N,3,H/4,W/4) low-resolution frame and the epilogue adds its
                           x4 bilinear upsampling (nn.Upsample(scale_factor=4, mode='bilinear', align_corners=False),
-                          iconvsr_ipb_par.py:41,140-141) instead of lq itself; row-stacked layout only */
+                          iconvsr_ipb_par.py:41,140-141) instead of lq itself */
   int32_t par_sparse;  /* 1: the reference's eval-mode sparse_val=True path (sr_backbone_utils.py:294-302): the 1x1 conv of
                           the LAST partition class whose map is non-zero at the pixel, divided by 255 -- the
                           map's value is not used.  0: dense sum_k par_k * conv1x1_k(src). */
@@ -202,36 +235,20 @@ typedef struct pnp_conv_desc {
                           (weights are packed once per checkpoint / clip, long before the frame loop), so the
                           kernel may fetch it while the previous kernel is still draining (programmatic dependent
                           launch).  0: fetch it only after the previous kernel has completed. */
+  int32_t per_image;   /* 1: every image of the launch has its OWN weights and bias (clips with different CRF / QP
+                          conditions in one launch -- the reference's per-sample grouped conv, groups = batch,
+                          sr_backbone_utils.py:196-204): image n uses wpack + img_off[2n] bytes and bias + img_off[2n+1]
+                          floats.  CTAs are then partitioned by image; N must not exceed the SM count. */
+  const int64_t* img_off; /* per_image (static launches): device array of N (weight byte offset, bias float offset) pairs */
+  /* table mode (dyn.table != NULL): wpack / bias / par / lq / outf / img_off and the first-image indices of src / aux /
+     idt / out come from the launch table; src / aux / idt / out above are then the BASES of buffers holding
+     src_images / aux_images / idt_images / out_images images (0 = N) -- typically one pool that contains every frame's
+     features and the work buffers -- and bias / par / lq / outf / aux / idt only say (non-NULL) that the operand exists. */
+  pnp_dyn_ref dyn;
+  int32_t src_images, aux_images, idt_images, out_images;
 } pnp_conv_desc;
 
 int pnp_conv3x3(const pnp_conv_desc* desc, void* stream);
-
-/*
- * K3 fused -- one whole BAE residual block per launch (ResidualBlockNoBNDynamic_drt.forward,
- * sr_backbone_utils.py:304-333), the intermediate activation never leaving the chip:
- *   t   = relu( conv3x3(x, W2) + bias1 + sum_k par_k * conv1x1_k(x) )     bf16, on-chip only
- *   out = x + conv3x3(t, W1) + bias2                                        bf16 NHWC
- * Runs on CTA pairs (thread-block clusters of 2): one SM holds W2 + the 1x1s, its partner holds W1,
- * rows of t travel through distributed shared memory.  Same numerics as pnp_conv3x3 launch A followed
- * by launch B (t rounded to bf16 once, fp32 accumulation).
- *   w_stage1: 98304 bytes = pnp_pack_conv3x3_rowstack(conv2 expert mix, row_scale = SE gain, tap_n 64)
- *             followed by the three 1x1 partition convs as 192 packed rows (pnp_pack_rows at row offsets
- *             0/64/128 from byte 73728) -- the PNP_WLAYOUT_ROWSTACK + par layout of pnp_conv3x3.
- *   w_stage2: 73728 bytes = pnp_pack_conv3x3_rowstack(conv1, tap_n 64, flip_ky 0).
- */
-typedef struct pnp_block_desc {
-  const void* x;          /* bf16 (N,H,W,64): block input and identity */
-  void* out;              /* bf16 (N,H,W,64); must not alias x */
-  const void* w_stage1;
-  const void* w_stage2;
-  const float* bias1;     /* [64] SE gain * mixed conv2 bias (pnp_mix_bias), or NULL */
-  const float* bias2;     /* [64] conv1 bias, or NULL */
-  const float* par;       /* fp32 (N,3,H,W) view of the partition map */
-  int64_t par_sn, par_sc, par_sy;
-  int32_t N, H, W;
-} pnp_block_desc;
-
-int pnp_resblock(const pnp_block_desc* desc, void* stream);
 
 #ifdef __cplusplus
 }

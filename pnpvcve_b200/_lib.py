@@ -13,18 +13,23 @@ LIB_PATH = os.environ.get("PNP_LIB_PATH") or os.path.join(HERE, "libpnpvcve.so")
 
 PNP_CONV_BF16, PNP_CONV_LAST = 0, 1
 PNP_ACT_NONE, PNP_ACT_LRELU, PNP_ACT_RELU = 0, 1, 2
-PNP_WLAYOUT_TAPMAJOR, PNP_WLAYOUT_ROWSTACK = 0, 1
 
 #: every symbol include/pnp_vcve.h declares
 EXPORTS = [
-    "pnp_abi_version", "pnp_last_error", "pnp_device_check", "pnp_set_base_offset_mode",
-    "pnp_mv_warp", "pnp_lr_im2col", "pnp_pack_conv3x3", "pnp_pack_conv3x3_rowstack", "pnp_pack_rows",
-    "pnp_pack_aux",
-    "pnp_caa_heads", "pnp_mix_bias", "pnp_mv_rasterize", "pnp_conv3x3", "pnp_resblock", "pnp_frame_quality",
+    "pnp_abi_version", "pnp_last_error", "pnp_device_check",
+    "pnp_graph_begin", "pnp_graph_end", "pnp_graph_launch", "pnp_graph_destroy", "pnp_set_step",
+    "pnp_mv_warp", "pnp_mv_warp_dyn", "pnp_lr_im2col", "pnp_lr_im2col_dyn", "pnp_pack_conv3x3_rowstack",
+    "pnp_pack_rows", "pnp_pack_aux", "pnp_pack_mix_blocks",
+    "pnp_caa_heads", "pnp_mix_bias", "pnp_mv_rasterize", "pnp_conv3x3", "pnp_frame_quality",
 ]
 
 _c = ctypes
 _vp, _i, _i64 = _c.c_void_p, _c.c_int, _c.c_int64
+
+
+class DynRef(_c.Structure):
+    """struct pnp_dyn_ref"""
+    _fields_ = [("table", _vp), ("step", _vp), ("node", _c.c_int32), ("stride", _c.c_int32)]
 
 
 class ConvDesc(_c.Structure):
@@ -36,30 +41,34 @@ class ConvDesc(_c.Structure):
         ("lq", _vp), ("lq_sn", _i64), ("lq_sc", _i64), ("lq_sy", _i64),
         ("outf", _vp), ("of_sn", _i64), ("of_sc", _i64), ("of_sy", _i64),
         ("N", _c.c_int32), ("H", _c.c_int32), ("W", _c.c_int32),
-        ("n_wchunks", _c.c_int32), ("center_n", _c.c_int32), ("tap_n", _c.c_int32),
-        ("aux_k16", _c.c_int32), ("act", _c.c_int32), ("mode", _c.c_int32),
-        ("wlayout", _c.c_int32), ("flip_y", _c.c_int32),
-        ("out_spx", _i64), ("out_sy", _i64), ("out_sn", _i64), ("lq_up4", _c.c_int32), ("par_sparse", _c.c_int32), ("wpack_stable", _c.c_int32),
+        ("tap_n", _c.c_int32), ("aux_k16", _c.c_int32), ("act", _c.c_int32), ("mode", _c.c_int32),
+        ("flip_y", _c.c_int32),
+        ("out_spx", _i64), ("out_sy", _i64), ("out_sn", _i64),
+        ("lq_up4", _c.c_int32), ("par_sparse", _c.c_int32), ("wpack_stable", _c.c_int32), ("per_image", _c.c_int32),
+        ("img_off", _vp),
+        ("dyn", DynRef),
+        ("src_images", _c.c_int32), ("aux_images", _c.c_int32), ("idt_images", _c.c_int32), ("out_images", _c.c_int32),
     ]
 
 
-class BlockDesc(_c.Structure):
-    """struct pnp_block_desc"""
-    _fields_ = [
-        ("x", _vp), ("out", _vp), ("w_stage1", _vp), ("w_stage2", _vp), ("bias1", _vp), ("bias2", _vp),
-        ("par", _vp), ("par_sn", _i64), ("par_sc", _i64), ("par_sy", _i64),
-        ("N", _c.c_int32), ("H", _c.c_int32), ("W", _c.c_int32),
-    ]
+#: one 64-byte launch-table entry = 8 uint64 words: p[0..5], then (i[0] | i[1] << 32), (i[2] | i[3] << 32)
+DYN_ENTRY_WORDS = 8
 
 
 _PROTOS = {
     "pnp_abi_version": (_i, []),
     "pnp_last_error": (_c.c_char_p, []),
     "pnp_device_check": (_i, []),
-    "pnp_set_base_offset_mode": (_i, [_i]),
+    "pnp_graph_begin": (_i, [_vp]),
+    "pnp_graph_end": (_i, [_vp, _c.POINTER(_vp)]),
+    "pnp_graph_launch": (_i, [_vp, _vp, _c.c_int32, _vp]),
+    "pnp_graph_destroy": (_i, [_vp]),
+    "pnp_set_step": (_i, [_vp, _c.c_int32, _vp]),
+    "pnp_mv_warp_dyn": (_i, [_c.POINTER(DynRef), _i64, _i64, _i, _i, _i, _vp]),
+    "pnp_lr_im2col_dyn": (_i, [_c.POINTER(DynRef), _i64, _i64, _i64, _i, _i, _i, _vp]),
+    "pnp_pack_mix_blocks": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i64, _vp]),
     "pnp_mv_warp": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pnp_lr_im2col": (_i, [_vp, _i64, _i64, _i64, _vp, _i, _i, _i, _vp]),
-    "pnp_pack_conv3x3": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "pnp_pack_conv3x3_rowstack": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "pnp_pack_rows": (_i, [_vp, _i, _i, _i64, _i64, _vp, _i, _vp]),
     "pnp_pack_aux": (_i, [_vp, _i, _i, _vp, _vp]),
@@ -67,7 +76,6 @@ _PROTOS = {
     "pnp_mix_bias": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "pnp_mv_rasterize": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pnp_conv3x3": (_i, [_c.POINTER(ConvDesc), _vp]),
-    "pnp_resblock": (_i, [_c.POINTER(BlockDesc), _vp]),
     "pnp_frame_quality": (_i, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
 

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpnpvcve.so")
-SOURCES = ["pnp_api.cu", "pnp_conv.cu", "pnp_conv_rows.cu", "pnp_block.cu", "pnp_ops.cu", "pnp_raster.cu", "pnp_metrics.cu"]
+SOURCES = ["pnp_api.cu", "pnp_conv_rows.cu", "pnp_ops.cu", "pnp_raster.cu", "pnp_metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
 
@@ -24,7 +24,10 @@ def build(force=False, verbose=False):
     if not force and os.path.isfile(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("PNP_DIAG", "0") != "0":     # diagnostics build for tools/ (what-if bits, clock traces)
+        flags.append("-DPNP_DIAG")
+    cmd = [nvcc] + flags + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -3,19 +3,20 @@
 #include <cstddef>
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "../../include/pnp_vcve.h"
-#include "pnp_block.cuh"
 #include "pnp_conv.cuh"
 #include "pnp_ops.cuh"
 
 namespace {
 
 thread_local char g_err[512] = "";
-int g_base_off_mode = 0;
+
+static_assert(sizeof(pnp_dyn_entry) == sizeof(pnp::DynEntry), "launch-table entry layout");
 
 int fail(int code, const char* fmt, const char* detail = "") {
   snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -30,27 +31,94 @@ int cuda_fail(cudaError_t e, const char* where) {
 struct DeviceInfo {
   bool ok = false;
   int sms = 0;
+  cudaError_t err = cudaSuccess;
 };
 
-// One entry per device ordinal; queried lazily.  Read-only after first use.
+// One entry per device ordinal, filled exactly once (std::call_once) and read-only afterwards: properties, and the
+// shared-memory opt-in of every conv kernel variant (done here so that it never happens inside a stream capture).
 DeviceInfo g_dev[64];
-bool g_dev_known[64] = {false};
+std::once_flag g_dev_once[64];
 
 int device_info(DeviceInfo** out) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
   if (dev < 0 || dev >= 64) return fail(PNP_ERR_ARG, "device ordinal out of range");
-  if (!g_dev_known[dev]) {
+  std::call_once(g_dev_once[dev], [dev]() {
     cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, dev);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
-    g_dev[dev].ok = (prop.major == 10);
-    g_dev[dev].sms = prop.multiProcessorCount;
-    g_dev_known[dev] = true;
-  }
+    cudaError_t e2 = cudaGetDeviceProperties(&prop, dev);
+    if (e2 == cudaSuccess) {
+      g_dev[dev].ok = (prop.major == 10);
+      g_dev[dev].sms = prop.multiProcessorCount;
+      if (g_dev[dev].ok) e2 = pnp::conv_rows_prepare();
+    }
+    g_dev[dev].err = e2;
+  });
   *out = &g_dev[dev];
+  if (g_dev[dev].err != cudaSuccess) return cuda_fail(g_dev[dev].err, "device initialisation");
   if (!g_dev[dev].ok) return fail(PNP_ERR_ARCH, "libpnpvcve needs an sm_100 device (B200)");
+  return PNP_OK;
+}
+
+// Process-wide switches, read ONCE when the library is first used.  Only performance-neutral layout knobs exist in the
+// default build; the what-if / trace knobs that make results wrong or write through a pointer taken from the
+// environment exist only in PNP_DIAG builds (tools/).
+struct Knobs {
+  int l2_hints = 0;        // PNP_L2_HINTS=1: evict_first on launch B's dead reads (measured: no effect)
+  int par_split = 1;       // PNP_PAR_SPLIT=0: single-role epilogue of block launch A
+  int rings_nio = 0, rings_sa = 0;   // PNP_RINGS="<n_io>,<s_a>": shared-memory split override
+  int debug_skip = 0;      // PNP_DIAG only
+  long long* trace = nullptr;   // PNP_DIAG only
+};
+
+const Knobs& knobs() {
+  static const Knobs k = []() {
+    Knobs v;
+    if (const char* e = getenv("PNP_L2_HINTS")) v.l2_hints = atoi(e) != 0;
+    if (const char* e = getenv("PNP_PAR_SPLIT")) v.par_split = atoi(e) != 0;
+    if (const char* e = getenv("PNP_RINGS")) {
+      if (sscanf(e, "%d,%d", &v.rings_nio, &v.rings_sa) != 2) v.rings_nio = v.rings_sa = 0;
+    }
+#ifdef PNP_DIAG
+    if (const char* e = getenv("PNP_DEBUG_SKIP")) v.debug_skip = atoi(e);
+    if (const char* e = getenv("PNP_TRACE_PTR")) v.trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 10));
+#endif
+    return v;
+  }();
+  return k;
+}
+
+pnp::DynRef dyn_ref(const pnp_dyn_ref* d) {
+  pnp::DynRef r;
+  r.table = d ? reinterpret_cast<const pnp::DynEntry*>(d->table) : nullptr;
+  r.step = d ? d->step : nullptr;
+  r.node = d ? d->node : 0;
+  r.stride = d ? d->stride : 0;
+  return r;
+}
+
+typedef CUresult (*MemsetD32AsyncFn)(CUdeviceptr, unsigned int, size_t, CUstream);
+
+MemsetD32AsyncFn memset32_fn() {
+  static MemsetD32AsyncFn fn = []() -> MemsetD32AsyncFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemsetD32Async", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<MemsetD32AsyncFn>(p);
+    return nullptr;
+  }();
+  return fn;
+}
+
+int store_step(int32_t* word, int32_t value, cudaStream_t stream) {
+  MemsetD32AsyncFn fn = memset32_fn();
+  if (fn == nullptr) return fail(PNP_ERR_CUDA, "cuMemsetD32Async entry point not available");
+  CUresult r = fn(reinterpret_cast<CUdeviceptr>(word), static_cast<unsigned int>(value), 1, stream);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuMemsetD32Async failed with CUresult %d", (int)r);
+    return PNP_ERR_CUDA;
+  }
   return PNP_OK;
 }
 
@@ -60,14 +128,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapFloatOOBfill);
 
 EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
+      return reinterpret_cast<EncodeTiledFn>(p);
+    return nullptr;
+  }();
   return fn;
 }
 
@@ -102,10 +170,11 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 extern "C" {
 
-static_assert(sizeof(pnp_conv_desc) == 240 && offsetof(pnp_conv_desc, out_spx) == 200 &&
-                  offsetof(pnp_conv_desc, wpack_stable) == 232,
+static_assert(sizeof(pnp_conv_desc) == 272 && offsetof(pnp_conv_desc, out_spx) == 184 &&
+                  offsetof(pnp_conv_desc, img_off) == 224 && offsetof(pnp_conv_desc, dyn) == 232 &&
+                  offsetof(pnp_conv_desc, src_images) == 256,
               "pnp_conv_desc layout is part of the ABI (mirrored by pnpvcve_b200/_lib.py: ConvDesc)");
-int pnp_abi_version(void) { return 6; }
+int pnp_abi_version(void) { return 7; }
 
 const char* pnp_last_error(void) { return g_err; }
 
@@ -114,10 +183,51 @@ int pnp_device_check(void) {
   return device_info(&d);
 }
 
-int pnp_set_base_offset_mode(int mode) {
-  if (mode != 0 && mode != 1) return fail(PNP_ERR_ARG, "base offset mode must be 0 or 1");
-  g_base_off_mode = mode;
+int pnp_graph_begin(void* stream) {
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  // relaxed: unrelated CUDA calls of other threads (allocator, copies on other streams) do not invalidate the capture
+  cudaError_t e = cudaStreamBeginCapture(static_cast<cudaStream_t>(stream), cudaStreamCaptureModeRelaxed);
+  return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_graph_begin");
+}
+
+int pnp_graph_end(void* stream, void** graph_exec) {
+  if (!graph_exec) return fail(PNP_ERR_ARG, "pnp_graph_end: null output");
+  *graph_exec = nullptr;
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(static_cast<cudaStream_t>(stream), &g);
+  if (e != cudaSuccess || g == nullptr) {
+    if (g) cudaGraphDestroy(g);
+    return cuda_fail(e != cudaSuccess ? e : cudaErrorUnknown, "pnp_graph_end: capture");
+  }
+  cudaGraphExec_t x = nullptr;
+  e = cudaGraphInstantiate(&x, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return cuda_fail(e, "pnp_graph_end: instantiate");
+  *graph_exec = x;
   return PNP_OK;
+}
+
+int pnp_graph_launch(void* graph_exec, int32_t* step_word, int32_t step_value, void* stream) {
+  if (!graph_exec) return fail(PNP_ERR_ARG, "pnp_graph_launch: null graph");
+  if (step_word) {
+    int rc = store_step(step_word, step_value, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+  }
+  cudaError_t e = cudaGraphLaunch(static_cast<cudaGraphExec_t>(graph_exec), static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_graph_launch");
+}
+
+int pnp_graph_destroy(void* graph_exec) {
+  if (!graph_exec) return PNP_OK;
+  cudaError_t e = cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(graph_exec));
+  return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_graph_destroy");
+}
+
+int pnp_set_step(int32_t* step_word, int32_t step_value, void* stream) {
+  if (!step_word) return fail(PNP_ERR_ARG, "pnp_set_step: null step word");
+  return store_step(step_word, step_value, static_cast<cudaStream_t>(stream));
 }
 
 int pnp_mv_warp(const void* src, const float* flow_x, const float* flow_y, int64_t flow_row_stride,
@@ -133,8 +243,20 @@ int pnp_mv_warp(const void* src, const float* flow_x, const float* flow_y, int64
   int rc = device_info(&d);
   if (rc) return rc;
   cudaError_t e = pnp::launch_mv_warp(src, flow_x, flow_y, flow_row_stride, flow_image_stride, dst, N, H, W, dbg_x0,
-                                      dbg_y0, d->sms, static_cast<cudaStream_t>(stream));
+                                      dbg_y0, dyn_ref(nullptr), static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_mv_warp");
+}
+
+int pnp_mv_warp_dyn(const pnp_dyn_ref* dyn, int64_t flow_row_stride, int64_t flow_image_stride, int N, int H, int W,
+                    void* stream) {
+  if (!dyn || !dyn->table || !dyn->step) return fail(PNP_ERR_ARG, "pnp_mv_warp_dyn: null launch table");
+  if (N <= 0 || H <= 0 || W <= 0) return fail(PNP_ERR_ARG, "pnp_mv_warp_dyn: bad shape");
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  cudaError_t e = pnp::launch_mv_warp(nullptr, nullptr, nullptr, flow_row_stride, flow_image_stride, nullptr, N, H, W,
+                                      nullptr, nullptr, dyn_ref(dyn), static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_mv_warp_dyn");
 }
 
 int pnp_lr_im2col(const float* lr, int64_t sn, int64_t sc, int64_t sy, void* dst, int N, int H, int W,
@@ -144,25 +266,18 @@ int pnp_lr_im2col(const float* lr, int64_t sn, int64_t sc, int64_t sy, void* dst
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
-  cudaError_t e = pnp::launch_lr_im2col(lr, sn, sc, sy, dst, N, H, W, d->sms, static_cast<cudaStream_t>(stream));
+  cudaError_t e = pnp::launch_lr_im2col(lr, sn, sc, sy, dst, N, H, W, dyn_ref(nullptr), static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_lr_im2col");
 }
 
-int pnp_pack_conv3x3(const float* w, int n_experts, const float* coef, const float* row_scale, int out_ch,
-                     int in_total, int in_begin, int in_begin2, int in_count, void* dst, int center_chunks,
-                     void* stream) {
-  if (!w || !dst) return fail(PNP_ERR_ARG, "pnp_pack_conv3x3: null pointer");
-  if (n_experts < 1 || (coef == nullptr && n_experts != 1) || out_ch < 1 || out_ch > 64 || in_count < 1 ||
-      in_count > 64 || in_begin < 0 || in_begin + in_count > in_total ||
-      (in_begin2 >= 0 && in_begin2 + in_count > in_total) || (center_chunks != 1 && center_chunks != 4) ||
-      !aligned16(dst))
-    return fail(PNP_ERR_ARG, "pnp_pack_conv3x3: bad argument");
+int pnp_lr_im2col_dyn(const pnp_dyn_ref* dyn, int64_t sn, int64_t sc, int64_t sy, int N, int H, int W, void* stream) {
+  if (!dyn || !dyn->table || !dyn->step) return fail(PNP_ERR_ARG, "pnp_lr_im2col_dyn: null launch table");
+  if (N <= 0 || H <= 0 || W <= 0) return fail(PNP_ERR_ARG, "pnp_lr_im2col_dyn: bad shape");
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
-  cudaError_t e = pnp::launch_pack_conv3x3(w, n_experts, coef, row_scale, out_ch, in_total, in_begin, in_begin2, in_count,
-                                           dst, center_chunks, static_cast<cudaStream_t>(stream));
-  return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_pack_conv3x3");
+  cudaError_t e = pnp::launch_lr_im2col(nullptr, sn, sc, sy, nullptr, N, H, W, dyn_ref(dyn), static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_lr_im2col_dyn");
 }
 
 int pnp_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef, const float* row_scale,
@@ -203,6 +318,20 @@ int pnp_pack_aux(const float* w, int out_ch, int in_total, void* dst, void* stre
   if (rc) return rc;
   cudaError_t e = pnp::launch_pack_aux(w, out_ch, in_total, dst, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_pack_aux");
+}
+
+int pnp_pack_mix_blocks(const float* w2, const float* w1x1, int n_blocks, int n_experts, const float* coef,
+                        const float* row_scale, void* dst, int64_t dst_block_stride, void* stream) {
+  if (!w2 || !w1x1 || !coef || !row_scale || !dst) return fail(PNP_ERR_ARG, "pnp_pack_mix_blocks: null pointer");
+  if (n_blocks < 1 || n_blocks > 65535 || n_experts < 1 || dst_block_stride < 12 * 8192 || (dst_block_stride & 15) ||
+      !aligned16(dst))
+    return fail(PNP_ERR_ARG, "pnp_pack_mix_blocks: bad argument");
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  cudaError_t e = pnp::launch_pack_mix_blocks(w2, w1x1, n_blocks, n_experts, coef, row_scale, dst, dst_block_stride,
+                                              static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_pack_mix_blocks");
 }
 
 int pnp_caa_heads(const float* base_qp, const float* qp, int frames, const float* base0_w,
@@ -276,57 +405,61 @@ int pnp_frame_quality(const float* a, int64_t a_sf, int64_t a_sc, int64_t a_sy, 
 
 int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   if (!c) return fail(PNP_ERR_ARG, "pnp_conv3x3: null descriptor");
-  if (!c->src || !c->wpack) return fail(PNP_ERR_ARG, "pnp_conv3x3: null src/wpack");
+  const bool table = c->dyn.table != nullptr;
+  if (!c->src || (!table && !c->wpack)) return fail(PNP_ERR_ARG, "pnp_conv3x3: null src/wpack");
+  if (table && (!c->dyn.step || c->dyn.node < 0 || c->dyn.stride <= c->dyn.node))
+    return fail(PNP_ERR_ARG, "pnp_conv3x3: bad launch-table reference");
   if (c->N < 1 || c->H < 1 || c->W < 1) return fail(PNP_ERR_ARG, "pnp_conv3x3: bad shape");
   const bool last = (c->mode == PNP_CONV_LAST);
   if (c->mode != PNP_CONV_BF16 && !last) return fail(PNP_ERR_ARG, "pnp_conv3x3: bad mode");
+  const bool par = c->par != nullptr;
   if (last) {
-    if (!c->lq || !c->outf || c->center_n != 16 || c->tap_n != 16 || c->aux || c->idt || c->par)
-      return fail(PNP_ERR_ARG, "pnp_conv3x3: PNP_CONV_LAST needs lq/outf, N=16, no aux/idt/par");
+    if (!c->lq || !c->outf || c->tap_n != 16 || c->aux || c->idt || par)
+      return fail(PNP_ERR_ARG, "pnp_conv3x3: PNP_CONV_LAST needs lq/outf, tap_n=16, no aux/idt/par");
   } else {
-    if (!c->out || c->tap_n != 64 || (c->center_n != 64 && c->center_n != 256))
-      return fail(PNP_ERR_ARG, "pnp_conv3x3: PNP_CONV_BF16 needs out, tap_n=64, center_n in {64,256}");
-    if ((c->par != nullptr) != (c->center_n == 256))
-      return fail(PNP_ERR_ARG, "pnp_conv3x3: par requires center_n == 256 and vice versa");
-    if (c->out == c->src) return fail(PNP_ERR_ARG, "pnp_conv3x3: out must not alias src (halo rows)");
+    if (!c->out || c->tap_n != 64) return fail(PNP_ERR_ARG, "pnp_conv3x3: PNP_CONV_BF16 needs out and tap_n=64");
+    if (c->out == c->src && !table) return fail(PNP_ERR_ARG, "pnp_conv3x3: out must not alias src (halo rows)");
   }
   if ((c->aux != nullptr) != (c->aux_k16 > 0) || c->aux_k16 < 0 || c->aux_k16 > 4)
     return fail(PNP_ERR_ARG, "pnp_conv3x3: aux / aux_k16 mismatch");
-  if (c->aux && c->center_n == 256) return fail(PNP_ERR_ARG, "pnp_conv3x3: aux and par are exclusive");
-  const bool rowstack = (c->wlayout == PNP_WLAYOUT_ROWSTACK);
-  if (c->wlayout != PNP_WLAYOUT_TAPMAJOR && !rowstack) return fail(PNP_ERR_ARG, "pnp_conv3x3: bad wlayout");
-  if (rowstack && c->center_n == 256 && (c->aux || c->idt))
-    return fail(PNP_ERR_ARG, "pnp_conv3x3: row-stacked layout with partition convs takes no aux / idt");
-  const int center_chunks = (c->center_n == 256) ? 4 : 1;
-  const int need_chunks = center_chunks + 8 + (c->aux ? 1 : 0);
-  if (!rowstack && c->n_wchunks != need_chunks)
-    return fail(PNP_ERR_ARG, "pnp_conv3x3: n_wchunks does not match the layout");
+  if (par && (c->aux || c->idt)) return fail(PNP_ERR_ARG, "pnp_conv3x3: par takes no aux / idt");
   if (c->act < 0 || c->act > 2) return fail(PNP_ERR_ARG, "pnp_conv3x3: bad act");
   const bool strided_out = c->out_spx != 0 || c->out_sy != 0 || c->out_sn != 0;
   if (strided_out && (last || c->out_spx < 64 || c->out_sy < c->out_spx * c->W || (c->N > 1 && c->out_sn < c->out_sy * c->H) ||
                       ((c->out_spx | c->out_sy | c->out_sn) & 7)))
     return fail(PNP_ERR_ARG, "pnp_conv3x3: out strides must be non-overlapping multiples of 8 elements (PNP_CONV_BF16 only)");
-  if (c->lq_up4 && (!last || !rowstack || (c->H & 3) || (c->W & 3)))
-    return fail(PNP_ERR_ARG, "pnp_conv3x3: lq_up4 needs PNP_CONV_LAST, the row-stacked layout and H, W multiples of 4");
-  if (!aligned16(c->src) || !aligned16(c->wpack) || (c->aux && !aligned16(c->aux)) ||
+  if (c->lq_up4 && (!last || (c->H & 3) || (c->W & 3)))
+    return fail(PNP_ERR_ARG, "pnp_conv3x3: lq_up4 needs PNP_CONV_LAST and H, W multiples of 4");
+  if (!aligned16(c->src) || (c->wpack && !aligned16(c->wpack)) || (c->aux && !aligned16(c->aux)) ||
       (c->idt && !aligned16(c->idt)) || (c->out && !aligned16(c->out)))
     return fail(PNP_ERR_ARG, "pnp_conv3x3: pointers must be 16-byte aligned");
+  if (c->src_images < 0 || c->aux_images < 0 || c->idt_images < 0 || c->out_images < 0)
+    return fail(PNP_ERR_ARG, "pnp_conv3x3: negative image count");
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
+  if (c->per_image && (c->N > d->sms || (!table && !c->img_off)))
+    return fail(PNP_ERR_ARG, "pnp_conv3x3: per_image needs img_off and at most one image per SM");
 
+  const Knobs& kn = knobs();
   pnp::ConvParams p;
   memset(&p, 0, sizeof(p));
-  if ((rc = make_map(&p.tm_src, c->src, c->N, c->H, c->W, pnp::kHaloPx))) return rc;
-  if (c->aux && (rc = make_map(&p.tm_aux, c->aux, c->N, c->H, c->W, pnp::kTilePx))) return rc;
-  if (c->idt && (rc = make_map(&p.tm_id, c->idt, c->N, c->H, c->W, pnp::kTilePx))) return rc;
-  if (!last && (rc = make_map(&p.tm_out, c->out, c->N, c->H, c->W, pnp::kTilePx, c->out_spx, c->out_sy, c->out_sn)))
+  auto images = [&](int32_t n) { return n > 0 ? n : c->N; };
+  if ((rc = make_map(&p.tm_src, c->src, images(c->src_images), c->H, c->W, pnp::kHaloPx))) return rc;
+  if (c->aux && (rc = make_map(&p.tm_aux, c->aux, images(c->aux_images), c->H, c->W, pnp::kTilePx))) return rc;
+  if (c->idt && (rc = make_map(&p.tm_id, c->idt, images(c->idt_images), c->H, c->W, pnp::kTilePx))) return rc;
+  if (!last && (rc = make_map(&p.tm_out, c->out, images(c->out_images), c->H, c->W, pnp::kTilePx, c->out_spx, c->out_sy,
+                              c->out_sn)))
     return rc;
   if (last) p.tm_out = p.tm_src;  // never used; keeps the prefetch harmless
+  p.dyn = dyn_ref(&c->dyn);
   p.wpack = c->wpack;
   p.scale = c->scale;
   p.bias = c->bias;
+  p.has_bias = c->bias != nullptr;
+  p.img_off = c->per_image ? reinterpret_cast<const long long*>(c->img_off) : nullptr;
   p.par = c->par;
+  p.has_par = par ? 1 : 0;
   p.par_sn = c->par_sn; p.par_sc = c->par_sc; p.par_sy = c->par_sy;
   p.lq = c->lq;
   p.lq_sn = c->lq_sn; p.lq_sc = c->lq_sc; p.lq_sy = c->lq_sy;
@@ -337,117 +470,67 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   const long long tiles = (long long)c->N * p.strips * c->H;
   if (tiles > 0x7fffffffLL) return fail(PNP_ERR_ARG, "pnp_conv3x3: too many tiles");
   p.tiles_total = (int)tiles;
-  int grid = d->sms < p.tiles_total ? d->sms : p.tiles_total;
-  p.tiles_per_cta = (p.tiles_total + grid - 1) / grid;
-  grid = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
-  p.n_wchunks = c->n_wchunks;
-  p.center_n = c->center_n;
+  int grid;
+  if (c->per_image) {
+    // CTAs are partitioned by image so that each can hold its image's weights: cpi CTAs walk one image
+    const int tiles_img = p.strips * c->H;
+    int cpi = d->sms / c->N;
+    if (cpi > tiles_img) cpi = tiles_img;
+    p.tiles_per_cta = (tiles_img + cpi - 1) / cpi;
+    cpi = (tiles_img + p.tiles_per_cta - 1) / p.tiles_per_cta;
+    p.cpi = cpi;
+    grid = cpi * c->N;
+  } else {
+    grid = d->sms < p.tiles_total ? d->sms : p.tiles_total;
+    p.tiles_per_cta = (p.tiles_total + grid - 1) / grid;
+    grid = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  }
   p.tap_n = c->tap_n;
   p.aux_k16 = c->aux_k16;
   p.has_id = c->idt != nullptr;
   p.act = c->act;
   p.mode = last ? pnp::kModeLast : pnp::kModeBf16;
-  p.flip_y = (rowstack && c->flip_y) ? 1 : 0;
+  p.flip_y = c->flip_y ? 1 : 0;
   p.w_stable = c->wpack_stable ? 1 : 0;
   p.lq_up4 = c->lq_up4 ? 1 : 0;
-  p.par_sparse = (c->par && c->par_sparse) ? 1 : 0;
-  {
-    // diagnostic: block launch B (row-stacked, identity, bottom-up) reads t and x for the last time
-    const char* hp = getenv("PNP_L2_HINTS");
-    p.l2_dead_reads = (hp && atoi(hp) != 0 && rowstack && c->idt && c->flip_y) ? 1 : 0;
-  }
-  {
-    const char* sp = getenv("PNP_PAR_SPLIT");     // diagnostic switch for the row-stacked partition variant (default on)
-    p.par_split = (rowstack && c->par && !(sp && atoi(sp) == 0)) ? 1 : 0;
-  }
-  p.base_off_mode = g_base_off_mode;
-  {
-    const char* dbg = getenv("PNP_DEBUG_SKIP");   // what-if profiling only; results are wrong when set
-    p.debug_skip = dbg ? atoi(dbg) : 0;
-    const char* trc = getenv("PNP_TRACE_PTR");    // device pointer (decimal) of a >= 4 KB buffer
-    p.trace = trc ? reinterpret_cast<long long*>(strtoull(trc, nullptr, 10)) : nullptr;
-  }
+  p.par_sparse = (par && c->par_sparse) ? 1 : 0;
+  // block launch B (identity, bottom-up) reads t and x for the last time
+  p.l2_dead_reads = (kn.l2_hints && c->idt && c->flip_y) ? 1 : 0;
+  p.par_split = (par && kn.par_split) ? 1 : 0;
+  p.debug_skip = kn.debug_skip;
+  p.trace = kn.trace;
   // shared-memory budget: weights + (aux ring) + staging ring + source-row ring from what is left.
   // With an identity operand the staging ring also prefetches identity tiles (n_io - 2 tiles ahead),
   // so it gets 4 slots as long as 5 source rows (3 in use + 2 in flight) still fit.
   const long long budget = 232448 - 2048;
-  const long long w_bytes = rowstack ? (((long long)9 * c->tap_n * 128 + (c->aux ? pnp::kWChunkBytes : 0) +
-                                         (c->center_n == 256 ? 3 * 64 * 128 : 0) + 1023) & ~1023LL)
-                                     : (long long)p.n_wchunks * pnp::kWChunkBytes;
+  const long long w_bytes = ((long long)9 * c->tap_n * 128 + (c->aux ? pnp::kWChunkBytes : 0) +
+                             (par ? 3 * 64 * 128 : 0) + 1023) & ~1023LL;
   auto fixed_bytes = [&](int n_io) {
     return w_bytes + (c->aux ? 2 * pnp::kTileBytes : 0) + (long long)n_io * pnp::kTileBytes;
   };
   p.n_io = 2;
-  if (rowstack && c->par) p.n_io = 3;   // the next row's 1x1 blend is parked in its staging slot one row early
+  if (par) p.n_io = 3;   // the next row's 1x1 blend is parked in its staging slot one row early
   if (c->idt) {
     p.n_io = 4;
     while (p.n_io > 2 && (budget - fixed_bytes(p.n_io)) / pnp::kASlotBytes < 5) --p.n_io;
   }
   long long slots = (budget - fixed_bytes(p.n_io)) / pnp::kASlotBytes;
-  const long long max_slots = rowstack ? 6 : pnp::kMaxASlots;   // a row lives one step there: 6 = 5 in flight
+  const long long max_slots = 6;   // a row lives one step there: 6 = 5 in flight
   if (slots > max_slots) slots = max_slots;
   if (slots < 4) return fail(PNP_ERR_RESOURCE, "pnp_conv3x3: shared-memory budget cannot hold 4 source rows");
-  // the row-stacked MMA thread checks the next step's barriers before the current step is committed;
-  // with an identity operand that needs a staging ring of >= 3 slots to stay deadlock free
-  if (rowstack && c->idt && p.n_io < 3)
-    return fail(PNP_ERR_RESOURCE, "pnp_conv3x3: row-stacked layout with idt needs 3 staging slots (drop aux)");
+  // the MMA thread checks the next step's barriers before the current step is committed; with an identity operand
+  // that needs a staging ring of >= 3 slots to stay deadlock free
+  if (c->idt && p.n_io < 3)
+    return fail(PNP_ERR_RESOURCE, "pnp_conv3x3: idt needs 3 staging slots (drop aux)");
   p.s_a = (int)slots;
-  if (const char* ov = getenv("PNP_RINGS")) {     // diagnostic: "<n_io>,<s_a>" override of the shared-memory split
-    int nio = 0, sa = 0;
-    if (sscanf(ov, "%d,%d", &nio, &sa) == 2 && nio >= 2 && nio <= pnp::kMaxIoSlots && sa >= 4 && sa <= pnp::kMaxASlots &&
-        fixed_bytes(nio) + (long long)sa * pnp::kASlotBytes <= budget && !(rowstack && c->idt && nio < 3) &&
-        !(rowstack && c->par && nio != 3)) {
-      p.n_io = nio;
-      p.s_a = sa;
-    }
+  if (kn.rings_nio >= 2 && kn.rings_nio <= pnp::kMaxIoSlots && kn.rings_sa >= 4 && kn.rings_sa <= pnp::kMaxASlots &&
+      fixed_bytes(kn.rings_nio) + (long long)kn.rings_sa * pnp::kASlotBytes <= budget && !(c->idt && kn.rings_nio < 3) &&
+      !(par && kn.rings_nio != 3)) {
+    p.n_io = kn.rings_nio;
+    p.s_a = kn.rings_sa;
   }
-  cudaError_t e = rowstack ? pnp::launch_conv_rows(p, grid, static_cast<cudaStream_t>(stream))
-                           : pnp::launch_conv(p, grid, static_cast<cudaStream_t>(stream));
+  cudaError_t e = pnp::launch_conv_rows(p, grid, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_conv3x3");
-}
-
-int pnp_resblock(const pnp_block_desc* c, void* stream) {
-  if (!c) return fail(PNP_ERR_ARG, "pnp_resblock: null descriptor");
-  if (!c->x || !c->out || !c->w_stage1 || !c->w_stage2 || !c->par)
-    return fail(PNP_ERR_ARG, "pnp_resblock: null x/out/weights/par");
-  if (c->N < 1 || c->H < 1 || c->W < 1) return fail(PNP_ERR_ARG, "pnp_resblock: bad shape");
-  if (c->out == c->x) return fail(PNP_ERR_ARG, "pnp_resblock: out must not alias x (halo rows, identity)");
-  if (!aligned16(c->x) || !aligned16(c->out) || !aligned16(c->w_stage1) || !aligned16(c->w_stage2))
-    return fail(PNP_ERR_ARG, "pnp_resblock: pointers must be 16-byte aligned");
-  DeviceInfo* d;
-  int rc = device_info(&d);
-  if (rc) return rc;
-  if (d->sms < 2) return fail(PNP_ERR_RESOURCE, "pnp_resblock: needs at least one SM pair");
-
-  pnp::BlockParams p;
-  memset(&p, 0, sizeof(p));
-  if ((rc = make_map(&p.tm_src, c->x, c->N, c->H, c->W, pnp::kHaloPx))) return rc;
-  if ((rc = make_map(&p.tm_out, c->out, c->N, c->H, c->W, pnp::kBlockOutPx))) return rc;
-  p.w0 = c->w_stage1;
-  p.w1 = c->w_stage2;
-  p.bias0 = c->bias1;
-  p.bias1 = c->bias2;
-  p.par = c->par;
-  p.par_sn = c->par_sn; p.par_sc = c->par_sc; p.par_sy = c->par_sy;
-  p.x = c->x;
-  p.H = c->H; p.W = c->W; p.N = c->N;
-  p.strips = (c->W + pnp::kBlockOutPx - 1) / pnp::kBlockOutPx;
-  const long long tiles = (long long)c->N * p.strips * c->H;
-  if (tiles > 0x7fffffffLL) return fail(PNP_ERR_ARG, "pnp_resblock: too many tiles");
-  p.tiles_total = (int)tiles;
-  int pairs = d->sms / 2 < p.tiles_total ? d->sms / 2 : p.tiles_total;
-  p.tiles_per_pair = (p.tiles_total + pairs - 1) / pairs;
-  pairs = (p.tiles_total + p.tiles_per_pair - 1) / p.tiles_per_pair;
-  p.s_a = 5;
-  p.n_t = 5;
-  {
-    const char* dbg = getenv("PNP_DEBUG_SKIP");   // what-if profiling only; results are wrong when set
-    p.debug_skip = dbg ? atoi(dbg) : 0;
-    const char* trc = getenv("PNP_TRACE_PTR");    // device pointer (decimal) of a >= 8 KB buffer
-    p.trace = trc ? reinterpret_cast<long long*>(strtoull(trc, nullptr, 10)) : nullptr;
-  }
-  cudaError_t e = pnp::launch_block(p, pairs, static_cast<cudaStream_t>(stream));
-  return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_resblock");
 }
 
 }  // extern "C"

@@ -1,4 +1,4 @@
-// Parameters of the tcgen05 implicit-GEMM 3x3 convolution kernel (pnp_conv.cu).
+// Parameters of the row-stacked tcgen05 implicit-GEMM 3x3 convolution kernel (pnp_conv_rows.cu).
 #pragma once
 #include <cuda.h>
 #include <stdint.h>
@@ -11,25 +11,44 @@ constexpr int kRowBytes = kHaloPx * 128;     // 16640: one staged source row, 64
 constexpr int kASlotBytes = 17 * 1024;       // ring slot (1024-aligned, >= kRowBytes)
 constexpr int kTileBytes = kTilePx * 128;    // 16384: one 128-pixel x 64-channel bf16 tile
 constexpr int kWChunkBytes = 8192;           // one 64(N) x 64(K) bf16 weight block
-constexpr int kConvThreads = 320;            // warp0 TMA producer, warp1 MMA issuer, warps2-9 epilogue
-constexpr int kRowsThreads = 352;            // row-stacked kernel: + warp10 barrier scout
+constexpr int kRowsThreads = 352;            // warp0 TMA producer, warp1 MMA issuer, warps2-9 epilogue, warp10 barrier scout
 constexpr int kEpilogueWarps = 8;
 constexpr int kMaxASlots = 8;
 constexpr int kMaxIoSlots = 4;
 constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;              // TMEM columns per accumulator buffer (2 buffers)
 
 enum ConvMode { kModeBf16 = 0, kModeLast = 1 };
 enum ConvAct { kActNone = 0, kActLrelu = 1, kActRelu = 2 };
 
+// One entry of a device-resident launch table (include/pnp_vcve.h: pnp_dyn_entry): the operands of a launch that
+// change from frame step to frame step.  A kernel launched in table mode reads entry
+// table[*step * stride + node]; everything else in its parameters is constant for the clip, so the launch can sit
+// in a CUDA graph that is replayed for every frame.
+struct DynEntry {
+  unsigned long long p[6];
+  int i[4];
+};
+static_assert(sizeof(DynEntry) == 64, "launch-table entry is 64 bytes (ABI)");
+
+struct DynRef {
+  const DynEntry* table;   // nullptr: static launch, every operand is in the kernel parameters
+  const int* step;
+  int node, stride;
+  __device__ __forceinline__ const DynEntry* entry() const {
+    return table ? table + ((long long)(*step) * stride + node) : nullptr;
+  }
+};
+
 struct ConvParams {
-  CUtensorMap tm_src;   // (64, W, H, N) bf16, box (64,130,1,1), SWIZZLE_128B
+  CUtensorMap tm_src;   // (64, W, H, images) bf16, box (64,130,1,1), SWIZZLE_128B
   CUtensorMap tm_aux;   // box (64,128,1,1)
   CUtensorMap tm_id;    // box (64,128,1,1)
   CUtensorMap tm_out;   // box (64,128,1,1)
-  const void* wpack;    // n_wchunks * 8192 bytes, pre-swizzled, in consumption order
+  DynRef dyn;           // table mode: conv entry = p{wpack, bias, par, lq, outf, img_off}, i{src_f, aux_f, idt_f, out_f}
+  const void* wpack;    // packed weights, pre-swizzled, in consumption order
   const float* scale;   // [64] per-output-channel scale of the 3x3 accumulator, or null
   const float* bias;    // [64] ([3] in kModeLast), or null
+  const long long* img_off;  // per-image (weight byte offset, bias float offset) pairs, or null; needs cpi > 0
   const float* par;     // partition map (n,3,H,W) fp32 view, or null
   long long par_sn, par_sc, par_sy;
   const float* lq;      // kModeLast: (n,3,H,W) fp32 view added to the output
@@ -38,24 +57,24 @@ struct ConvParams {
   long long of_sn, of_sc, of_sy;
   int H, W, N, strips;
   int tiles_total, tiles_per_cta;
-  int n_wchunks;
-  int center_n;         // N of the centre-tap MMA: 64, 256 (3x3 + three 1x1 partition convs) or 16
-  int tap_n;            // N of the other taps: 64 or 16
-  int aux_k16;          // K/16 of the aux source (centre tap only); 0 = no aux
+  int cpi;              // > 0: CTAs per image -- a CTA's tiles never cross an image (per-image weights / bias)
+  int has_par;          // 3x3 + three partition 1x1 convs (block launch A)
+  int has_bias;
+  int tap_n;            // N of one dy sub-block: 64, or 16 for the 64->3 tail
+  int aux_k16;          // K/16 of the aux source (centre row only); 0 = no aux
   int has_id;
   int act;
   int mode;
-  int flip_y;           // row-stacked kernel: walk the image bottom-up (weights packed with ky mirrored)
-  int l2_dead_reads;    // row-stacked kernel: src and identity are dead after this launch -> L2 evict_first on their loads
-  int par_split;        // row-stacked partition variant: dedicated reader warps for the 1x1 accumulator region
+  int flip_y;           // walk the image bottom-up (weights packed with ky mirrored)
+  int l2_dead_reads;    // src and identity are dead after this launch -> L2 evict_first on their loads
+  int par_split;        // partition variant: dedicated reader warps for the 1x1 accumulator region
   int par_sparse;       // partition blend: last non-zero class only, / 255 (the reference's sparse_val eval path)
   int lq_up4;           // kModeLast: lq is the (H/4, W/4) frame, the epilogue adds its x4 bilinear upsampling
   int w_stable;         // weights may be fetched before the previous kernel in the stream has completed
   int s_a;              // A ring slots
   int n_io;             // id/out staging slots
-  long long* trace;      // optional device buffer for per-tile clock64 stamps of CTA 0 (diagnostics)
-  int debug_skip;        // what-if profiling bits (results are WRONG): 1 skip row loads, 2 skip output staging/store, 4 skip TMEM loads
-  int base_off_mode;    // 0: descriptor base_offset = 0 (measured-correct on B200); 1: (addr>>7)&7
+  long long* trace;     // PNP_DIAG builds: device buffer for per-tile clock64 stamps of CTA 0
+  int debug_skip;       // PNP_DIAG builds: what-if profiling bits (results are WRONG)
 };
 
 // sparse_val eval path of the reference (sr_backbone_utils.py:294-302, basicvsr_net.py:511-514): per class the
@@ -71,10 +90,9 @@ __device__ __forceinline__ void par_sparse_select(float& p0, float& p1, float& p
   p0 = (!n2 && !n1 && n0) ? c : 0.f;
 }
 
-size_t conv_smem_bytes(const ConvParams& p);
-cudaError_t launch_conv(const ConvParams& p, int grid, cudaStream_t stream);
-// row-stacked kernel (pnp_conv_rows.cu): weights packed as [dx][dy sub-block][tap_n rows]
+// weights packed as [dx][dy sub-block][tap_n rows] (pnp_pack_conv3x3_rowstack)
 size_t conv_rows_smem_bytes(const ConvParams& p);
+cudaError_t conv_rows_prepare();     // opt every kernel variant in to 227 KB of shared memory on the current device
 cudaError_t launch_conv_rows(const ConvParams& p, int grid, cudaStream_t stream);
 
 }  // namespace pnp

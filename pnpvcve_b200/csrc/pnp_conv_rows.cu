@@ -20,6 +20,16 @@
 #include "pnp_conv.cuh"
 #include "pnp_ptx.cuh"
 
+// Diagnostics (what-if bits, clock traces) exist only in PNP_DIAG builds (PNP_DIAG=1 python -m pnpvcve_b200.build):
+// the default library neither reads such knobs nor carries their code.
+#ifdef PNP_DIAG
+#define PNP_DBG(bit) ((p.debug_skip & (bit)) != 0)
+#define PNP_TRACING (p.trace != nullptr)
+#else
+#define PNP_DBG(bit) false
+#define PNP_TRACING false
+#endif
+
 namespace pnp {
 
 namespace {
@@ -132,8 +142,32 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int t_begin = blockIdx.x * p.tiles_per_cta;
-  const int t_end = min(p.tiles_total, t_begin + p.tiles_per_cta);
+  // Tile range.  cpi > 0: `cpi` CTAs per image, so that a CTA never crosses an image and can use that image's own
+  // weights / bias (clips with different CRF / QP conditions in ONE launch: the reference's groups=batch grouped conv,
+  // sr_backbone_utils.py:196-204).
+  int t_begin, t_end, img = 0;
+  if (p.cpi > 0) {
+    img = blockIdx.x / p.cpi;
+    const int tiles_img = p.strips * p.H;
+    t_begin = img * tiles_img + (blockIdx.x - img * p.cpi) * p.tiles_per_cta;
+    t_end = min((img + 1) * tiles_img, t_begin + p.tiles_per_cta);
+  } else {
+    t_begin = blockIdx.x * p.tiles_per_cta;
+    t_end = min(p.tiles_total, t_begin + p.tiles_per_cta);
+  }
+  // Operands that change per frame step come from the launch table in table mode (constant kernel parameters
+  // otherwise).  The table and the step word were written by stream operations that completed before the first
+  // kernel of this step started, so they may be read ahead of griddepcontrol.wait.
+  const DynEntry* dyn = p.dyn.entry();
+  const long long* img_off = dyn ? reinterpret_cast<const long long*>(dyn->p[5]) : p.img_off;
+  const long long w_off = img_off ? img_off[2 * img] : 0, b_off = img_off ? img_off[2 * img + 1] : 0;
+  const uint8_t* const wpack = (dyn ? reinterpret_cast<const uint8_t*>(dyn->p[0]) : static_cast<const uint8_t*>(p.wpack)) + w_off;
+  const float* const bias_g = p.has_bias ? (dyn ? reinterpret_cast<const float*>(dyn->p[1]) : p.bias) + b_off : nullptr;
+  const float* const par_g = dyn ? reinterpret_cast<const float*>(dyn->p[2]) : p.par;
+  const float* const lq_g = dyn ? reinterpret_cast<const float*>(dyn->p[3]) : p.lq;
+  float* const outf_g = dyn ? reinterpret_cast<float*>(dyn->p[4]) : p.outf;
+  const int src_f = dyn ? dyn->i[0] : 0, aux_f = dyn ? dyn->i[1] : 0, idt_f = dyn ? dyn->i[2] : 0,
+            out_f = dyn ? dyn->i[3] : 0;
   const int s_a = p.s_a;
   const int n_io = p.n_io;
   const bool last_mode = (p.mode == kModeLast);
@@ -146,7 +180,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
   if (threadIdx.x < 64) {
     misc->scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.0f;
     const int nb = last_mode ? 3 : 64;
-    misc->bias[threadIdx.x] = (p.bias && threadIdx.x < nb) ? p.bias[threadIdx.x] : 0.0f;
+    misc->bias[threadIdx.x] = (bias_g && threadIdx.x < nb) ? bias_g[threadIdx.x] : 0.0f;
   }
   if (warp == 0) {
     if (lane == 0) {
@@ -186,7 +220,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
     mbar_arrive_expect_tx(wbar, w_bytes);
     for (int off = 0; off < w_bytes; off += kWChunkBytes) {
       const int n = min(kWChunkBytes, w_bytes - off);
-      bulk_load_1d(w_smem_early + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, n, wbar);
+      bulk_load_1d(w_smem_early + off, wpack + off, n, wbar);
     }
   };
   // stable weights (packed long before this launch) are fetched while the previous kernel drains
@@ -195,16 +229,16 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
     __syncwarp();
   }
   griddep_wait();
-  if (p.trace != nullptr && threadIdx.x == 0) {            // per-CTA body start (cycles, ns): stored, not kept live
+  if (PNP_TRACING && threadIdx.x == 0) {            // per-CTA body start (cycles, ns): stored, not kept live
     p.trace[2048 + blockIdx.x] = -clock64();
     p.trace[2208 + blockIdx.x] = (long long)globaltimer_ns();
   }
   // Threads that merely wait for work poll patiently (one lane per warp, hardware suspend hint): hot
   // try_wait loops of 256 epilogue lanes compete with the MMA operand fetch for the shared-memory pipe
   // (measured: N=192 MMAs ~25 % slower).  debug bit 32 selects patient polling, bit 64 shortens the hint.
-  const bool par_defer = kPar && p.par_split && (p.debug_skip & 1024);    // diagnostic, see the MMA issuer
-  const bool hot_waits = (p.debug_skip & 32) == 0;
-  const uint32_t hint_ns = (p.debug_skip & 64) ? 40u : 200u;
+  const bool par_defer = kPar && p.par_split && PNP_DBG(1024);    // diagnostic, see the MMA issuer
+  const bool hot_waits = !PNP_DBG(32);
+  const uint32_t hint_ns = PNP_DBG(64) ? 40u : 200u;
   auto pwait = [&](uint32_t bar, uint32_t parity, int tag) {      // one elected lane
     if (hot_waits) mbar_wait(bar, parity, tag); else mbar_wait_patient(bar, parity, tag, hint_ns);
   };
@@ -234,14 +268,14 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
             pwait(smem_u32(&misc->step_done[ps & (kStepRing - 1)]), (ps >> 3) & 1, 1);
           }
           const uint32_t fb = smem_u32(&misc->a_full[ar.slot]);
-          if ((p.debug_skip & 1) && sc >= (uint32_t)s_a) {
+          if (PNP_DBG(1) && sc >= (uint32_t)s_a) {
             mbar_arrive(fb);
           } else {
             mbar_arrive_expect_tx(fb, kRowBytes);
             if (p.l2_dead_reads)
-              tma_load_4d_hint(a_smem + ar.slot * kASlotBytes, &p.tm_src, fb, 0, x0 - 1, PNP_Y(s.y_b + j), s.n, pol_dead);
+              tma_load_4d_hint(a_smem + ar.slot * kASlotBytes, &p.tm_src, fb, 0, x0 - 1, PNP_Y(s.y_b + j), s.n + src_f, pol_dead);
             else
-              tma_load_4d(a_smem + ar.slot * kASlotBytes, &p.tm_src, fb, 0, x0 - 1, PNP_Y(s.y_b + j), s.n);
+              tma_load_4d(a_smem + ar.slot * kASlotBytes, &p.tm_src, fb, 0, x0 - 1, PNP_Y(s.y_b + j), s.n + src_f);
           }
           if (j >= 0 && j < s.len) {       // per-output-row operands of row y_b + j
             if (p.aux_k16 > 0) {
@@ -253,7 +287,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
               aux_step[as] = sc;           // consumed in this very step (centre row)
               const uint32_t ab = smem_u32(&misc->aux_full[as]);
               mbar_arrive_expect_tx(ab, kTileBytes);
-              tma_load_4d(aux_smem + as * kTileBytes, &p.tm_aux, ab, 0, x0, PNP_Y(s.y_b + j), s.n);
+              tma_load_4d(aux_smem + as * kTileBytes, &p.tm_aux, ab, 0, x0, PNP_Y(s.y_b + j), s.n + aux_f);
             }
             ++ord;
           }
@@ -350,11 +384,11 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       // last value read from go_step: the scout usually runs several steps ahead (A ring depth, free
       // accumulator slots), so most steps need no shared-memory poll and no fence at all
       uint32_t go_seen = 0;
-      const bool dbg_nopoll = (p.debug_skip & 8) != 0, dbg_nofence = (p.debug_skip & 16) != 0;
+      const bool dbg_nopoll = PNP_DBG(8), dbg_nofence = PNP_DBG(16);
       if (cur.valid) go_seen = spin_until_ge_v(go_step, 1, 5);
       tc_fence_after();
       while (cur.valid) {
-        const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && cur.sc < 64 && !(p.debug_skip & 128);
+        const bool tr = PNP_TRACING && blockIdx.x == 0 && cur.sc < 64 && !PNP_DBG(128);
         if (tr) p.trace[cur.sc * 8 + 0] = clock64();
         int lo, cnt, old_cnt;
         ranges(cur, lo, cnt, old_cnt);
@@ -537,7 +571,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       const int x = c.s.strip * kTilePx + row;
       q0 = q1 = q2 = 0.f;
       if (x < p.W) {
-        const float* pp = p.par + (long long)c.s.n * p.par_sn + (long long)PNP_Y(c.s.y_b + c.o) * p.par_sy + x;
+        const float* pp = par_g + (long long)c.s.n * p.par_sn + (long long)PNP_Y(c.s.y_b + c.o) * p.par_sy + x;
         q0 = __ldg(pp);
         q1 = __ldg(pp + p.par_sc);
         q2 = __ldg(pp + 2 * p.par_sc);
@@ -660,7 +694,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
           named_bar_sync(2, 128);
           if (store_warp) {
             if (elect_one()) {
-              tma_store_4d(&p.tm_out, io_smem + ior.slot * kTileBytes, 0, s.strip * kTilePx, y, s.n);
+              tma_store_4d(&p.tm_out, io_smem + ior.slot * kTileBytes, 0, s.strip * kTilePx, y, s.n + out_f);
               tma_store_commit();
             }
             __syncwarp();
@@ -702,10 +736,10 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       const uint32_t ib = smem_u32(&misc->id_full[slot]);
       mbar_arrive_expect_tx(ib, kTileBytes);
       if (p.l2_dead_reads)
-        tma_load_4d_hint(io_smem + slot * kTileBytes, &p.tm_id, ib, 0, c.s.strip * kTilePx, PNP_Y(c.s.y_b + c.o), c.s.n,
+        tma_load_4d_hint(io_smem + slot * kTileBytes, &p.tm_id, ib, 0, c.s.strip * kTilePx, PNP_Y(c.s.y_b + c.o), c.s.n + idt_f,
                          l2_policy_evict_first());
       else
-        tma_load_4d(io_smem + slot * kTileBytes, &p.tm_id, ib, 0, c.s.strip * kTilePx, PNP_Y(c.s.y_b + c.o), c.s.n);
+        tma_load_4d(io_smem + slot * kTileBytes, &p.tm_id, ib, 0, c.s.strip * kTilePx, PNP_Y(c.s.y_b + c.o), c.s.n + idt_f);
     };
     if (p.has_id && store_warp) {
       if (elect_one()) {
@@ -744,8 +778,8 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
             const int y1 = y0 + (y0 < hl - 1 ? 1 : 0), x1 = x0 + (x0 < wl - 1 ? 1 : 0);
             const float ly1 = sy - (float)y0, lx1 = sx - (float)x0;
             const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-            const float* b0 = p.lq + (long long)s.n * p.lq_sn + (long long)y0 * p.lq_sy;
-            const float* b1 = p.lq + (long long)s.n * p.lq_sn + (long long)y1 * p.lq_sy;
+            const float* b0 = lq_g + (long long)s.n * p.lq_sn + (long long)y0 * p.lq_sy;
+            const float* b1 = lq_g + (long long)s.n * p.lq_sn + (long long)y1 * p.lq_sy;
             float r[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -757,7 +791,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
             r1 = r[1];
             r2 = r[2];
           } else {
-            const float* lp = p.lq + (long long)s.n * p.lq_sn + (long long)y * p.lq_sy + x;
+            const float* lp = lq_g + (long long)s.n * p.lq_sn + (long long)y * p.lq_sy + x;
             r0 = __ldg(lp);
             r1 = __ldg(lp + p.lq_sc);
             r2 = __ldg(lp + 2 * p.lq_sc);
@@ -773,7 +807,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         tc_fence_before();
         warp_arrive(smem_u32(&misc->acc_free[slot]));
         if (valid && half == 0) {
-          float* op = p.outf + (long long)s.n * p.of_sn + (long long)y * p.of_sy + x;
+          float* op = outf_g + (long long)s.n * p.of_sn + (long long)y * p.of_sy + x;
           op[0] = v[0] + misc->bias[0] + r0;
           op[p.of_sc] = v[1] + misc->bias[1] + r1;
           op[2 * p.of_sc] = v[2] + misc->bias[2] + r2;
@@ -781,7 +815,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         cur = nxt;
         continue;
       }
-      const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && ord < 64 && threadIdx.x == 64 && !(p.debug_skip & 128);
+      const bool tr = PNP_TRACING && blockIdx.x == 0 && ord < 64 && threadIdx.x == 64 && !PNP_DBG(128);
       // Partition path: the 1x1 accumulators of the NEXT row finish with the same step that completes
       // this row's 3x3 result (they are issued last in that step), so both are fetched from TMEM in
       // one batch behind one barrier wait; the blend of the next row is parked in its staging slot.
@@ -820,7 +854,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       if (tr) p.trace[ord * 8 + 3] = clock64();
       uint8_t* rowp = sgen + L.io + s_io * kTileBytes + row * 128;
       float v[32];
-      if (p.debug_skip & 4) {
+      if (PNP_DBG(4)) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       } else {
@@ -881,7 +915,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         o1.y = pack_bf16x2(vv[10], vv[11]);
         o1.z = pack_bf16x2(vv[12], vv[13]);
         o1.w = pack_bf16x2(vv[14], vv[15]);
-        if (!(p.debug_skip & 2)) {
+        if (!PNP_DBG(2)) {
           *c0 = o0;
           *c1 = o1;
         }
@@ -892,8 +926,8 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       if (tr) p.trace[ord * 8 + 5] = clock64();
       if (store_warp) {
         if (elect_one()) {
-          if (!(p.debug_skip & 2)) {
-            tma_store_4d(&p.tm_out, io_smem + s_io * kTileBytes, 0, s.strip * kTilePx, y, s.n);
+          if (!PNP_DBG(2)) {
+            tma_store_4d(&p.tm_out, io_smem + s_io * kTileBytes, 0, s.strip * kTilePx, y, s.n + out_f);
             tma_store_commit();
           }
         }
@@ -916,7 +950,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (p.trace != nullptr && threadIdx.x == 0) {            // per-CTA body cycles, start and end time (ns)
+  if (PNP_TRACING && threadIdx.x == 0) {            // per-CTA body cycles, start and end time (ns)
     p.trace[2048 + blockIdx.x] += clock64();
     p.trace[2368 + blockIdx.x] = (long long)globaltimer_ns();
   }
@@ -929,23 +963,13 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
 #undef PNP_Y
 
 size_t conv_rows_smem_bytes(const ConvParams& p) {
-  const int w_bytes = 3 * 3 * p.tap_n * 128 + (p.aux_k16 > 0 ? kWChunkBytes : 0) +
-                      (p.center_n == 256 ? 3 * 64 * 128 : 0);
+  const int w_bytes = 3 * 3 * p.tap_n * 128 + (p.aux_k16 > 0 ? kWChunkBytes : 0) + (p.has_par ? 3 * 64 * 128 : 0);
   return rows_layout(w_bytes, p.s_a, p.aux_k16 > 0, p.n_io).total + 1024;
 }
 
 namespace {
 template <bool kPar, bool kScale>
 cudaError_t launch_rows_variant(const ConvParams& p, int grid, size_t smem, cudaStream_t stream) {
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    e = cudaFuncSetAttribute(conv3x3_rows_kernel<kPar, kScale>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    if (e != cudaSuccess) return e;
-    attr_set[dev] = true;
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kRowsThreads);
@@ -958,11 +982,24 @@ cudaError_t launch_rows_variant(const ConvParams& p, int grid, size_t smem, cuda
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, conv3x3_rows_kernel<kPar, kScale>, p);
 }
+template <bool kPar, bool kScale>
+cudaError_t prepare_variant() {
+  return cudaFuncSetAttribute(conv3x3_rows_kernel<kPar, kScale>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+}
 }  // namespace
+
+// once per device, before the first launch (and before any stream capture): the API layer calls it under call_once
+cudaError_t conv_rows_prepare() {
+  cudaError_t e;
+  if ((e = prepare_variant<true, true>()) != cudaSuccess) return e;
+  if ((e = prepare_variant<true, false>()) != cudaSuccess) return e;
+  if ((e = prepare_variant<false, true>()) != cudaSuccess) return e;
+  return prepare_variant<false, false>();
+}
 
 cudaError_t launch_conv_rows(const ConvParams& p, int grid, cudaStream_t stream) {
   const size_t smem = conv_rows_smem_bytes(p);
-  const bool par = (p.center_n == 256), scale = (p.scale != nullptr);
+  const bool par = p.has_par != 0, scale = (p.scale != nullptr);
   if (par) return scale ? launch_rows_variant<true, true>(p, grid, smem, stream)
                         : launch_rows_variant<true, false>(p, grid, smem, stream);
   return scale ? launch_rows_variant<false, true>(p, grid, smem, stream)

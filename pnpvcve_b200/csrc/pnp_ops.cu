@@ -2,6 +2,7 @@
 // expert mixing (K4) and the CAA heads.
 #include <cstdlib>
 
+#include "pnp_conv.cuh"
 #include "pnp_ops.cuh"
 #include "pnp_ptx.cuh"
 
@@ -97,8 +98,14 @@ template <int kTileW, int kTileH>
 __global__ void __launch_bounds__(256)
 mv_warp_kernel(const uint4* __restrict__ src, const float* __restrict__ flow_x,
                const float* __restrict__ flow_y, long long flow_sy, long long flow_sn, uint4* __restrict__ dst,
-               int H, int W, int* __restrict__ dbg_x0, int* __restrict__ dbg_y0) {
-  constexpr int kRowsPerIter = 64 / kTileW;               // 256 threads = 64 pixels x 4 quarters per iteration
+               int H, int W, int* __restrict__ dbg_x0, int* __restrict__ dbg_y0, const DynRef dyn) {
+  constexpr int kRowsPerIter = 64 / kTileW;
+  if (const DynEntry* e = dyn.entry()) {                  // table mode: p{src, flow_x, flow_y, dst}
+    src = reinterpret_cast<const uint4*>(e->p[0]);
+    flow_x = reinterpret_cast<const float*>(e->p[1]);
+    flow_y = reinterpret_cast<const float*>(e->p[2]);
+    dst = reinterpret_cast<uint4*>(e->p[3]);
+  }               // 256 threads = 64 pixels x 4 quarters per iteration
   static_assert(kTileW * kRowsPerIter == 64 && kTileH % kRowsPerIter == 0, "tile shape");
   // blockIdx.z = image of the batch: same-shape clips with their own motion fields
   src += (size_t)blockIdx.z * H * W * 8;
@@ -128,28 +135,13 @@ mv_warp_kernel(const uint4* __restrict__ src, const float* __restrict__ flow_x,
 
 cudaError_t launch_mv_warp(const void* src, const float* flow_x, const float* flow_y, long long flow_sy,
                            long long flow_sn, void* dst, int N, int H, int W, int* dbg_x0, int* dbg_y0,
-                           int num_sms, cudaStream_t stream) {
-  (void)num_sms;
+                           const DynRef& dyn, cudaStream_t stream) {
   if ((long long)H * W >= (1LL << 27) || N > 65535) return cudaErrorInvalidValue;   // 32-bit pixel indexing
-  static int variant = -1;                                // diagnostic: PNP_WARP_TILE = 0 (64x1), 1 (32x8), 2 (16x8), 3 (64x4)
-  if (variant < 0) {
-    const char* v = getenv("PNP_WARP_TILE");
-    variant = v ? atoi(v) : 1;
-  }
-  const uint4* s = reinterpret_cast<const uint4*>(src);
-  uint4* d = reinterpret_cast<uint4*>(dst);
-#define PNP_WARP_LAUNCH(TW, TH)                                                                              \
-  mv_warp_kernel<TW, TH><<<dim3((W + TW - 1) / TW, (H + TH - 1) / TH, N), 256, 0, stream>>>(s, flow_x, flow_y, flow_sy, \
-                                                                                           flow_sn, d, H, W, dbg_x0, dbg_y0)
-  switch (variant) {
-    case 0: PNP_WARP_LAUNCH(64, 1); break;
-    case 2: PNP_WARP_LAUNCH(16, 8); break;
-    case 3: PNP_WARP_LAUNCH(64, 4); break;
-    case 4: PNP_WARP_LAUNCH(32, 16); break;
-    case 5: PNP_WARP_LAUNCH(32, 4); break;
-    default: PNP_WARP_LAUNCH(32, 8); break;
-  }
-#undef PNP_WARP_LAUNCH
+  // 32 x 8 pixel tiles (tools/warp_bench.py, cold L2: 64x1 57.5 us, 32x8 53.4, 16x8 54.5, 64x4 53.4, 32x16 54.2)
+  constexpr int TW = 32, TH = 8;
+  mv_warp_kernel<TW, TH><<<dim3((W + TW - 1) / TW, (H + TH - 1) / TH, N), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(src), flow_x, flow_y, flow_sy, flow_sn, reinterpret_cast<uint4*>(dst), H, W, dbg_x0,
+      dbg_y0, dyn);
   return cudaGetLastError();
 }
 
@@ -163,8 +155,12 @@ cudaError_t launch_mv_warp(const void* src, const float* flow_x, const float* fl
 constexpr int kI2cW = 64, kI2cH = 4;
 __global__ void __launch_bounds__(256)
 lr_im2col_kernel(const float* __restrict__ lr, long long sn, long long sc, long long sy, uint4* __restrict__ dst,
-                 int N, int H, int W) {
+                 int N, int H, int W, const DynRef dyn) {
   __shared__ float win[3][kI2cH + 2][kI2cW + 2];
+  if (const DynEntry* e = dyn.entry()) {                  // table mode: p{lr, dst}
+    lr = reinterpret_cast<const float*>(e->p[0]);
+    dst = reinterpret_cast<uint4*>(e->p[1]);
+  }
   const int n = blockIdx.z;
   const int x0 = blockIdx.x * kI2cW, y0 = blockIdx.y * kI2cH;
   const float* base = lr + (long long)n * sn;
@@ -209,19 +205,16 @@ lr_im2col_kernel(const float* __restrict__ lr, long long sn, long long sc, long 
 }
 
 cudaError_t launch_lr_im2col(const float* lr, long long sn, long long sc, long long sy, void* dst, int N,
-                             int H, int W, int num_sms, cudaStream_t stream) {
-  (void)num_sms;
+                             int H, int W, const DynRef& dyn, cudaStream_t stream) {
   if ((H + kI2cH - 1) / kI2cH > 65535 || N > 65535) return cudaErrorInvalidValue;
   dim3 grid((W + kI2cW - 1) / kI2cW, (H + kI2cH - 1) / kI2cH, N);
-  lr_im2col_kernel<<<grid, 256, 0, stream>>>(lr, sn, sc, sy, reinterpret_cast<uint4*>(dst), N, H, W);
+  lr_im2col_kernel<<<grid, 256, 0, stream>>>(lr, sn, sc, sy, reinterpret_cast<uint4*>(dst), N, H, W, dyn);
   return cudaGetLastError();
 }
 
 // =====================================================================================
-// K4: weight packing.  A packed 3x3 conv is a sequence of 8 KB blocks [64 rows = out channel]
-// [64 cols = in channel] bf16, rows of 128 bytes with the 128B swizzle pre-applied (16-byte
-// column group g of row r is stored at g ^ (r & 7)), block order = MMA consumption order:
-// centre tap first (occupying `center_chunks` blocks), then taps 0,1,2,3,5,6,7,8.
+// K4: weight packing.  Packed operands are 128-byte rows [row = out channel][64 cols = in channel] bf16 with
+// the 128B swizzle pre-applied (16-byte column group g of row r is stored at g ^ (r & 7)).
 //
 // With n_experts > 1 the block is the expert mixture  sum_e coef[e] * w[e]  of
 // Dynamic_conv2d_se.forward (sr_backbone_utils.py:198-199), evaluated once per distinct CRF instead
@@ -231,29 +224,6 @@ cudaError_t launch_lr_im2col(const float* lr, long long sn, long long sc, long l
 __device__ __forceinline__ size_t packed_offset(int block, int row, int col) {
   return (size_t)block * kPackBlockBytes + (size_t)row * 128 + (size_t)((((col >> 3) ^ (row & 7)) << 4)) +
          (size_t)(col & 7) * 2;
-}
-
-__global__ void __launch_bounds__(256)
-pack_conv3x3_kernel(const float* __restrict__ w, int n_experts, const float* __restrict__ coef,
-                    const float* __restrict__ row_scale, int out_ch, int in_total, int in_begin, int in_begin2,
-                    int in_count, uint8_t* __restrict__ dst, int center_chunks) {
-  // one thread per (tap, row<64, col<64)
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 9 * 64 * 64) return;
-  const int col = idx & 63, row = (idx >> 6) & 63, tap = idx >> 12;
-  float acc = 0.f;
-  if (row < out_ch && col < in_count) {
-    const size_t per_expert = (size_t)out_ch * in_total * 9;
-    for (int e = 0; e < n_experts; ++e) {
-      const float ce = coef ? coef[e] : 1.0f;
-      float v = w[e * per_expert + ((size_t)row * in_total + in_begin + col) * 9 + tap];
-      if (in_begin2 >= 0) v += w[e * per_expert + ((size_t)row * in_total + in_begin2 + col) * 9 + tap];
-      acc = fmaf(ce, v, acc);
-    }
-    if (row_scale) acc *= row_scale[row];      // SE gain folded into the mixed kernel (per out channel)
-  }
-  const int block = (tap == 4) ? 0 : (center_chunks + (tap < 4 ? tap : tap - 1));
-  *reinterpret_cast<__nv_bfloat16*>(dst + packed_offset(block, row, col)) = __float2bfloat16_rn(acc);
 }
 
 // Row-stacked layout of pnp_conv_rows.cu: per dx one block of 3*tap_n rows, sub-block sb = 0,1,2
@@ -313,12 +283,45 @@ pack_aux_kernel(const float* __restrict__ w, int out_ch, int in_total, uint8_t* 
   *reinterpret_cast<__nv_bfloat16*>(dst + packed_offset(0, row, col)) = __float2bfloat16_rn(v);
 }
 
-cudaError_t launch_pack_conv3x3(const float* w, int n_experts, const float* coef, const float* row_scale,
-                                int out_ch, int in_total, int in_begin, int in_begin2, int in_count, void* dst,
-                                int center_chunks, cudaStream_t stream) {
-  pack_conv3x3_kernel<<<(9 * 64 * 64 + 255) / 256, 256, 0, stream>>>(
-      w, n_experts, coef, row_scale, out_ch, in_total, in_begin, in_begin2, in_count, reinterpret_cast<uint8_t*>(dst),
-      center_chunks);
+// All expert-mixed block-launch-A packs of one (CRF, QP) condition in ONE launch: block b of the stack gets
+// [row-stacked gamma_o * sum_e a_e W2[b][e] (72 KB)][three 1x1 partition convs as 192 rows (24 KB)] at
+// dst + b * dst_stride -- Dynamic_conv2d_se's per-block, per-frame torch.mm (sr_backbone_utils.py:198-208) done
+// once per condition for the whole network.
+__global__ void __launch_bounds__(256)
+pack_mix_blocks_kernel(const float* __restrict__ w2, const float* __restrict__ w1x1, int n_experts,
+                       const float* __restrict__ coef, const float* __restrict__ row_scale,
+                       uint8_t* __restrict__ dst, long long dst_stride) {
+  const int b = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  uint8_t* out = dst + (long long)b * dst_stride;
+  constexpr int kMain = 9 * 64 * 64, kSide = 3 * 64 * 64;
+  if (idx < kMain) {
+    const int dxi = idx / (3 * 64 * 64);
+    const int rem = idx - dxi * (3 * 64 * 64);
+    const int col = rem & 63, r = rem >> 6;
+    const int sb = r >> 6, o = r & 63;
+    const int ky = 2 - sb, kx = dxi;
+    const float* wb = w2 + (size_t)b * n_experts * 64 * 64 * 9;
+    float acc = 0.f;
+    for (int e = 0; e < n_experts; ++e)
+      acc = fmaf(coef[e], wb[(size_t)e * 64 * 64 * 9 + ((size_t)o * 64 + col) * 9 + ky * 3 + kx], acc);
+    acc *= row_scale[o];
+    const size_t off = (size_t)dxi * (3 * 64 * 128) + (size_t)r * 128 + (size_t)((((col >> 3) ^ (r & 7)) << 4)) +
+                       (size_t)(col & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(out + off) = __float2bfloat16_rn(acc);
+  } else if (idx < kMain + kSide) {
+    const int k = idx - kMain;
+    const int col = k & 63, r = k >> 6;             // r = class * 64 + out channel
+    const float v = w1x1[(size_t)b * kSide + (size_t)r * 64 + col];
+    *reinterpret_cast<__nv_bfloat16*>(out + 9 * 64 * 128 + packed_offset(r >> 6, r & 63, col)) = __float2bfloat16_rn(v);
+  }
+}
+
+cudaError_t launch_pack_mix_blocks(const float* w2, const float* w1x1, int n_blocks, int n_experts, const float* coef,
+                                   const float* row_scale, void* dst, long long dst_stride, cudaStream_t stream) {
+  dim3 grid((12 * 64 * 64 + 255) / 256, n_blocks);
+  pack_mix_blocks_kernel<<<grid, 256, 0, stream>>>(w2, w1x1, n_experts, coef, row_scale, reinterpret_cast<uint8_t*>(dst),
+                                                   dst_stride);
   return cudaGetLastError();
 }
 

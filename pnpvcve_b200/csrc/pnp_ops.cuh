@@ -5,16 +5,17 @@
 
 namespace pnp {
 
+struct DynRef;
+
 constexpr int kPackBlockBytes = 8192;
 
 cudaError_t launch_mv_warp(const void* src, const float* flow_x, const float* flow_y, long long flow_sy,
                            long long flow_sn, void* dst, int N, int H, int W, int* dbg_x0, int* dbg_y0,
-                           int num_sms, cudaStream_t stream);
+                           const DynRef& dyn, cudaStream_t stream);
 cudaError_t launch_lr_im2col(const float* lr, long long sn, long long sc, long long sy, void* dst, int N,
-                             int H, int W, int num_sms, cudaStream_t stream);
-cudaError_t launch_pack_conv3x3(const float* w, int n_experts, const float* coef, const float* row_scale,
-                                int out_ch, int in_total, int in_begin, int in_begin2, int in_count, void* dst,
-                                int center_chunks, cudaStream_t stream);
+                             int H, int W, const DynRef& dyn, cudaStream_t stream);
+cudaError_t launch_pack_mix_blocks(const float* w2, const float* w1x1, int n_blocks, int n_experts, const float* coef,
+                                   const float* row_scale, void* dst, long long dst_stride, cudaStream_t stream);
 cudaError_t launch_pack_conv3x3_rowstack(const float* w, int n_experts, const float* coef,
                                          const float* row_scale, int out_ch, int in_total, int in_begin,
                                          int in_begin2, int in_count, void* dst, int tap_n, bool flip_ky,

@@ -1,22 +1,29 @@
-"""Host-side scheduler of the BAE+CAA forward: key-frame schedule, resident packed weights,
-work buffers, and the per-frame kernel sequence.
+"""Host-side scheduler of the BAE+CAA forward: key-frame schedule, resident packed weights, the feature pool, the
+per-call launch table and the CUDA graphs of the frame steps.
 
 Restructures ``IconVSR_restore_wo_refill_mv_ipb_fast_domain_dynamic_with_par.forward``
 (mmedit/models/backbones/sr_backbones/iconvsr_ipb_par.py:44-149) without changing its results:
 
-* the key-frame indices come from ONE device->host copy of ``slices`` instead of
-  ``int(torch.where(...))`` per frame and clip (:81, :116);
-* expert mixing (sr_backbone_utils.py:198-202) is done once per distinct CRF and kept resident;
-* ``torch.cat`` of [lr, key_warp, neighbour(, backward feature)] (:90, :125) is never
-  materialised: each source is its own K slice of ``input_conv.0.weight`` and is accumulated by a
-  chain of conv launches; when the neighbour IS the warped key frame (:85-88) the two K slices are
-  summed into one;
-* SE gain, bias, partition-modulated 1x1 convs, ReLU/LeakyReLU, residual adds and the final
-  ``out += lq`` run in the conv epilogues.
+* the key-frame indices come from ONE device->host copy of ``slices`` instead of ``int(torch.where(...))`` per frame
+  and clip (:81, :116);
+* expert mixing (sr_backbone_utils.py:198-202) is done once per distinct (CRF, QP) condition and kept resident;
+* ``torch.cat`` of [lr, key_warp, neighbour(, backward feature)] (:90, :125) is never materialised: each source is its
+  own K slice of ``input_conv.0.weight`` and is accumulated by a chain of conv launches; when the neighbour IS the
+  warped key frame (:85-88) the two K slices are summed into one;
+* SE gain, bias, partition-modulated 1x1 convs, ReLU/LeakyReLU, residual adds and the final ``out += lq`` run in the
+  conv epilogues;
+* the reference's Python frame loop (:71-147, ~300 library launches per frame) becomes ONE CUDA-graph launch per frame
+  step: every frame's features and all work buffers live in one pool (one TMA tensor map), the operands that change
+  from frame to frame sit in a device-resident launch table written once per call, and the six step variants
+  (backward / forward x first / merged-neighbour / separate-neighbour) are captured once per clip shape;
+* clips of one call that share the key-frame schedule run as ONE sequence with N images per launch even when their
+  CRF / QP conditions differ: per-image weight and bias offsets in the launch (the reference's per-sample grouped conv,
+  ``groups = batch``, sr_backbone_utils.py:196-204).
 """
 import ctypes
 import os
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -24,6 +31,8 @@ from . import _lib, ops
 from .ops import PNP_ACT_LRELU, PNP_ACT_NONE, PNP_ACT_RELU
 
 SLICE_I, SLICE_P = 73, 80
+ROW_BYTES = 9 * 64 * 128           # one row-stacked 64->64 pack
+WORK = ("kw", "pa", "pb", "xa", "xb", "t", "hr", "lr64", "zero")
 
 
 def key_schedule(key_row):
@@ -55,101 +64,112 @@ def keyframe_rows(slices_host):
     return key.tolist()
 
 
-class _Launcher:
-    """Pre-bound ctypes call of pnp_conv3x3 with a reusable descriptor."""
+def group_clips(key_rows, max_batch, batch=True):
+    """Runs of consecutive clips with the same key-frame schedule -> [b0, b1) ranges (at most max_batch clips each).
+    Such clips take the same launch sequence at every step; their CRF / QP conditions may differ (per-image weights)."""
+    groups = []
+    for b, row in enumerate(key_rows):
+        if batch and groups and row == key_rows[groups[-1][0]] and groups[-1][1] - groups[-1][0] < max_batch:
+            groups[-1][1] = b + 1
+        else:
+            groups.append([b, b + 1])
+    return [tuple(g) for g in groups]
 
-    def __init__(self, prof=None, prof_every=1):
-        self.lib = _lib.load()
-        self.fn = self.lib.pnp_conv3x3
-        self.desc = ops.ConvDesc()
-        self.ref = ctypes.byref(self.desc)
-        self.prof = prof          # None or {label: [(start_event, end_event), ...]}
-        self.rows_par = False     # block launch A on the row-stacked kernel (weights packed accordingly)
-        self.par_sparse = False   # sparse_val=True: last non-zero partition class only, / 255
-        self.prof_every = max(int(prof_every), 1)
-        self.seen = {}
 
-    def __call__(self, stream, src, wpack, out=None, aux=None, idt=None, scale=None, bias=None,
-                 par=None, act=PNP_ACT_NONE, lq=None, outf=None, label=None, flip_y=False, lq_up4=False):
-        # row-stacked weight layout (one source row feeds three output rows, N=192 MMAs) for every
-        # conv except the partition-modulated block launch A
-        # wpack_stable: every pack kernel of the call ran before the frame loop started (the launch
-        # right before a conv is always lr_im2col, the warp or another conv)
-        ops.fill_conv_desc(self.desc, src, wpack, out, aux, idt, scale, bias, par, act, lq, outf,
-                           wlayout=0 if (par is not None and not self.rows_par) else 1, flip_y=flip_y,
-                           wpack_stable=True, lq_up4=lq_up4, par_sparse=self.par_sparse)
-        timed = self.prof is not None and label in self.prof
-        if timed:                                  # bracket every prof_every-th launch of this label
-            k = self.seen.get(label, 0)
-            self.seen[label] = k + 1
-            timed = (k % self.prof_every) == 0
-        if timed:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-        rc = self.fn(self.ref, stream)
-        if timed:
-            e1.record()
-            self.prof[label].append((e0, e1))
-        if rc != 0:
-            _lib.check(rc, "pnp_conv3x3")
+def step_variants(bwd_key, fwd_key):
+    """Variant name of each of the 2T frame steps: steps 0..T-1 are the backward-time pass (frame T-1-s), steps
+    T..2T-1 the forward-time pass (frame s-T)."""
+    t = len(bwd_key)
+    names = []
+    for s in range(t):
+        i = t - 1 - s
+        names.append("b_last" if i == t - 1 else ("b_merged" if bwd_key[i] == i + 1 else "b_sep"))
+    for i in range(t):
+        names.append("f_first" if i == 0 else ("f_merged" if fwd_key[i] == i - 1 else "f_sep"))
+    return names
 
-    def block(self, stream, x, out, w_stage1, w_stage2, bias1, bias2, par, label="block"):
-        """One fused residual block (pnp_resblock) with a reusable descriptor."""
-        if getattr(self, "bdesc", None) is None:
-            self.bdesc = ops.BlockDesc()
-            self.bref = ctypes.byref(self.bdesc)
-            self.bfn = self.lib.pnp_resblock
-        ops.fill_block_desc(self.bdesc, x, out, w_stage1, w_stage2, bias1, bias2, par)
-        timed = self.prof is not None and label in self.prof
-        if timed:
-            k = self.seen.get(label, 0)
-            self.seen[label] = k + 1
-            timed = (k % self.prof_every) == 0
-        if timed:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-        rc = self.bfn(self.bref, stream)
-        if timed:
-            e1.record()
-            self.prof[label].append((e0, e1))
-        if rc != 0:
-            _lib.check(rc, "pnp_resblock")
+
+class _Program:
+    """Everything that is fixed for one (clip count, T, H, W) shape: the feature pool, the launch table, the prebuilt
+    descriptors of every step variant and their captured graphs."""
+
+    def __init__(self, n, t, h, w, dev, maxn, nb, vsr, table_steps):
+        self.key = (n, t, h, w, dev, maxn, nb, vsr)
+        self.n, self.t, self.h, self.w, self.dev, self.maxn, self.nb, self.vsr = n, t, h, w, dev, maxn, nb, vsr
+        self.img_bytes = h * w * 128
+        self.pool_images = t * n + len(WORK) * maxn
+        self.pool = torch.empty((self.pool_images, h, w, 64), dtype=torch.bfloat16, device=dev)
+        self.feats = self.pool[: t * n].view(t, n, h, w, 64)      # frame-major: a run of clips at one frame is contiguous
+        self.work = {}
+        for k, name in enumerate(WORK):
+            f0 = t * n + k * maxn
+            self.work[name] = (f0, self.pool[f0:f0 + maxn])
+        self.work["lr64"][1].zero_()
+        self.work["zero"][1].zero_()
+        if vsr:      # x4 tail: 2Hx2W and 4Hx4W feature maps of one frame step
+            self.u1 = ops.new_feature(maxn, 2 * h, 2 * w, dev)
+            self.u2 = ops.new_feature(maxn, 4 * h, 4 * w, dev)
+            self.hr4 = ops.new_feature(maxn, 4 * h, 4 * w, dev)
+        self.stride = 8 + 2 * nb + (8 if vsr else 0)              # launch-table entries per step
+        self.table_steps = 0
+        self.table = self.img_off = self.host_table = self.host_off = None
+        self.nodes = {}          # (variant, nn, per_image, sparse) -> [(kind, label, args)]
+        self.graphs = {}         # same key -> graph handle
+        self.ensure_table(table_steps)
+        self.step_word = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.cap_stream = torch.cuda.Stream(device=dev)   # stream capture is not allowed on the legacy default stream
+        self.uploaded = None     # event behind the last table upload (the pinned staging buffers are reused)
+
+    def ensure_table(self, steps):
+        if steps <= self.table_steps:
+            return
+        steps = max(steps, 2 * self.t)
+        self.release_graphs()    # the table address is baked into the captured kernel parameters
+        self.nodes = {}
+        self.table_steps = steps
+        self.table = torch.zeros((steps, self.stride, _lib.DYN_ENTRY_WORDS), dtype=torch.int64, device=self.dev)
+        self.img_off = torch.zeros((steps, self.maxn, 2), dtype=torch.int64, device=self.dev)
+        self.host_table = torch.zeros((steps, self.stride, _lib.DYN_ENTRY_WORDS), dtype=torch.int64).pin_memory()
+        self.host_off = torch.zeros((steps, self.maxn, 2), dtype=torch.int64).pin_memory()
+
+    def release_graphs(self):
+        graphs, self.graphs = getattr(self, "graphs", {}), {}
+        if graphs:
+            lib = _lib.load()
+            for g in graphs.values():
+                lib.pnp_graph_destroy(g)
+
+    def __del__(self):
+        try:
+            self.release_graphs()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
 
 
 class BaeEngine:
-    """Owns the packed weights and work buffers of one generator instance on one device."""
+    """Owns the packed weights, the feature pool and the step graphs of one generator instance on one device."""
 
     def __init__(self, module):
         self.m = module
         self.static_key = None
         self.static = None
-        self.mix_cache = {}
-        self.buf_key = None
-        self.buf = None
+        self.mix_slots = {}       # (CRF, QP) -> slot of mix_pool
+        self.mix_pool = None      # uint8 (slots, 2*nb, PACK_A_BYTES): expert-mixed block-launch-A packs
+        self.prog = None
         self.launch_count = 0
-        self.last_mode = "eager"   # how the last forward launched its frame steps: "eager" | "graph"
+        self.last_mode = "graph"  # how the last forward launched its frame steps: "graph" | "eager"
         self._done = None         # (device, event recorded behind the last forward)
-        #: set to {label: []} (labels: "block_a", "block_b", "input", "hr", "last", "warp") to have the
-        #: next forward bracket those launches with CUDA events on the launching stream (bench.py);
-        #: prof_every = N brackets only every N-th launch of a label (event records between kernels
-        #: defeat programmatic dependent launch, so the bench samples instead of bracketing everything)
+        #: set to {label: []} (labels: "block_a", "block_b", "input", "hr", "last", "up", "warp", "im2col", "phases") to
+        #: have the next forward bracket those launches with CUDA events on the launching stream (bench.py); such a
+        #: forward launches its kernels one by one instead of replaying graphs.  prof_every = N brackets only every
+        #: N-th launch of a label (event records between kernels defeat programmatic dependent launch).
         self.prof = None
         self.prof_every = 1
-        #: clips of one call can be processed on several concurrent lanes (stream + work buffers each).
-        #: Measured (profiles/r01_notes.md): no gain at 720p (one CTA per SM fills the chip; 285 vs 289
-        #: frames/s) and +5 % at 320x180, where the host launch rate is the limit -- default 1.
-        self.max_lanes = int(os.environ.get("PNP_LANES", "1"))
-        #: batch runs of identically-conditioned clips into N-image launches (up to max_batch clips)
+        #: replay one captured CUDA graph per frame step (default) or launch the same table-mode kernels one by one
+        self.use_graphs = os.environ.get("PNP_GRAPHS", "1") != "0"
+        #: batch runs of clips with the same key-frame schedule into N-image launches (up to max_batch clips)
         self.batch_clips = os.environ.get("PNP_BATCH_CLIPS", "1") != "0"
         self.max_batch = 16
-        #: run each BAE block as ONE launch of the CTA-pair kernel (pnp_resblock: the intermediate activation
-        #: stays on chip) instead of launch A + launch B of pnp_conv3x3
-        self.fused_block = os.environ.get("PNP_FUSED_BLOCK", "0") != "0"
-        #: block launch A (3x3 + three partition 1x1s) on the row-stacked kernel with dedicated reader warps for the
-        #: 1x1 accumulator region (73 vs 84 us at 720p, +5 % frames/s); PNP_ROWS_PAR=0 selects the tap-major kernel
-        self.rows_par = os.environ.get("PNP_ROWS_PAR", "1") != "0"
 
     # ------------------------------------------------------------------ weights
     def _param_key(self):
@@ -161,9 +181,9 @@ class BaeEngine:
     def invalidate(self):
         """Drop the packed / expert-mixed weights (re-packed by the next forward)."""
         self.static = self.static_key = None
-        self.mix_cache = {}
+        self.mix_slots = {}
 
-    # Copies and pickles of the owning module get a FRESH engine: packed weights, work buffers, streams, ctypes
+    # Copies and pickles of the owning module get a FRESH engine: packed weights, the pool, graphs, ctypes
     # descriptors and events are per-process, per-device resources and are rebuilt on first use.
     def __getstate__(self):
         return {"m": self.m}
@@ -183,9 +203,10 @@ class BaeEngine:
         def f32(p):
             return p.detach().to(dev, torch.float32).contiguous()
 
-        for name, branch in (("bwd", m.backward_resblocks), ("fwd", m.forward_resblocks)):
+        conv1_w = torch.zeros((2 * nb, ROW_BYTES), dtype=torch.uint8, device=dev)
+        conv1_b, c2w, c2b, w1x1 = [], [], [], []
+        for br, (name, branch) in enumerate((("bwd", m.backward_resblocks), ("fwd", m.forward_resblocks))):
             w_in = f32(branch.input_conv[0].weight)
-            st[name + "_in_w"] = w_in
             st[name + "_in_bias"] = f32(branch.input_conv[0].bias)
             # K slices of the 131/195-channel input conv: [0:3] lr, [3:67] key_warp, [67:131] neighbour,
             # [131:195] backward feature (iconvsr_ipb_par.py:90,125)
@@ -193,7 +214,7 @@ class BaeEngine:
                 buf = ops.new_wpack_rowstack(dev, with_aux=with_aux)
                 ops.pack_conv3x3_rowstack(w_in, buf, in_begin=in_begin, in_begin2=in_begin2, in_count=64)
                 if with_aux:
-                    ops.pack_aux(w_in, buf[9 * ops.CHUNK_BYTES:])
+                    ops.pack_aux(w_in, buf[ROW_BYTES:])
                 return buf
             if name == "bwd":
                 st["bwd_key_aux"] = pack(3, with_aux=True)          # first pass, separate neighbour
@@ -204,26 +225,20 @@ class BaeEngine:
                 st["fwd_key"] = pack(3)
                 st["fwd_merged"] = pack(3, 67)
                 st["fwd_nb"] = pack(67)
-            conv1_w, conv1_dn, conv1_b, c2w, c2b, onebyone = [], [], [], [], [], []
-            for blk in branch.main:
+            for k, blk in enumerate(branch.main):
                 # block launch B walks the image bottom-up (flip_y): launch A wrote its bottom rows
                 # last, so B finds them in L2; B in turn writes the top rows last, where A starts
-                buf = ops.new_wpack_rowstack(dev)
-                ops.pack_conv3x3_rowstack(f32(blk.conv1.weight), buf, flip_ky=True)
-                conv1_w.append(buf)
-                buf = ops.new_wpack_rowstack(dev)                      # top-down copy for the fused block kernel
-                ops.pack_conv3x3_rowstack(f32(blk.conv1.weight), buf)
-                conv1_dn.append(buf)
+                ops.pack_conv3x3_rowstack(f32(blk.conv1.weight), conv1_w[br * nb + k], flip_ky=True)
                 conv1_b.append(f32(blk.conv1.bias))
                 c2w.append(f32(blk.conv2.weight))
                 c2b.append(f32(blk.conv2.bias))
-                onebyone.append([f32(c.weight).view(64, 64) for c in
-                                 (blk.conv16x16, blk.conv16x8, blk.conv8x8)])
-            st[name + "_conv1_w"], st[name + "_conv1_b"] = conv1_w, conv1_b
-            st[name + "_conv1_dn"] = conv1_dn
-            st[name + "_conv2_w"], st[name + "_1x1"] = c2w, onebyone
-            st[name + "_conv2_bias"] = torch.stack(c2b, 0).contiguous()      # (nb, E, 64)
-        st["conv2_bias_all"] = torch.cat([st["bwd_conv2_bias"], st["fwd_conv2_bias"]], 0).contiguous()
+                w1x1.append(torch.stack([f32(c.weight).view(64, 64) for c in
+                                         (blk.conv16x16, blk.conv16x8, blk.conv8x8)], 0))
+        st["conv1_w"] = conv1_w
+        st["conv1_b"] = torch.stack(conv1_b, 0).contiguous()          # (2nb, 64)
+        st["conv2_w_all"] = torch.stack(c2w, 0).contiguous()          # (2nb, E, 64, 64, 3, 3)
+        st["w1x1_all"] = torch.stack(w1x1, 0).contiguous()            # (2nb, 3, 64, 64)
+        st["conv2_bias_all"] = torch.stack(c2b, 0).contiguous()       # (2nb, E, 64)
         hr = ops.new_wpack_rowstack(dev)
         ops.pack_conv3x3_rowstack(f32(m.conv_hr.weight), hr)
         st["hr_w"], st["hr_b"] = hr, f32(m.conv_hr.bias)
@@ -249,77 +264,252 @@ class BaeEngine:
                          s0w=f32(m.BiasePredictor.fc[0].weight), s2w=f32(m.BiasePredictor.fc[2].weight))
         st["nb"] = nb
         self.static, self.static_key = st, key
-        self.mix_cache = {}
+        self.mix_slots = {}
         return st
 
-    def _mixed_conv2(self, st, key, coef_row, gamma_row, dev):
-        """Expert-mixed conv2 (SE gain folded in) + stacked 1x1 partition convs for every block.
+    def _mix_slots_for(self, st, conds, experts, gamma, dev):
+        """Slot of the expert-mixed packs of every (CRF, QP) condition in ``conds`` ({cond: flat frame index}).
 
-        Dynamic_conv2d_se.forward (sr_backbone_utils.py:198-208) re-mixes per block and frame and
-        multiplies the output by gamma; the mixture only depends on the frame's CRF and gamma on
-        its QP, so the packed kernels gamma_o * sum_e a_e W_e are cached per distinct (CRF, QP)
-        pair -- 3 pairs per clip in the IPB configs, at most ~15 in the CRF config.
-        """
-        key = (key, self.fused_block, self.rows_par)
-        hit = self.mix_cache.get(key)
-        if hit is not None:
-            return hit
-        packs = {}
-        for name in ("bwd", "fwd"):
-            lst = []
-            for k in range(st["nb"]):
-                if self.fused_block or self.rows_par:
-                    # stage-1 pack of pnp_resblock / row-stacked launch A: row-stacked mix + the three 1x1 convs stacked behind it
-                    buf = ops.new_wpack_rowstack(dev, with_par=True)
-                    ops.pack_conv3x3_rowstack(st[name + "_conv2_w"][k], buf, coef=coef_row, row_scale=gamma_row)
-                    for j, w1 in enumerate(st[name + "_1x1"][k]):
-                        ops.pack_rows(w1, buf[9 * ops.CHUNK_BYTES:], 64 * j)
-                    lst.append(buf)
-                    continue
-                # block launch A stays on the tap-major kernel (centre tap N=256): its row-stacked
-                # variant is correct but its single partition-accumulator hand-off is slower for now
-                buf = ops.new_wpack(12, dev)
-                ops.pack_conv3x3(st[name + "_conv2_w"][k], buf, coef=coef_row, center_chunks=4,
-                                 row_scale=gamma_row)
-                for j, w1 in enumerate(st[name + "_1x1"][k]):
-                    ops.pack_rows(w1, buf, 64 * (j + 1))
-                lst.append(buf)
-            packs[name] = lst
-        if len(self.mix_cache) > 64:
-            self.mix_cache.clear()
-        self.mix_cache[key] = packs
-        return packs
+        Dynamic_conv2d_se.forward (sr_backbone_utils.py:198-208) re-mixes per block and frame and multiplies the
+        output by gamma; the mixture only depends on the frame's CRF and gamma on its QP, so the packed kernels
+        gamma_o * sum_e a_e W_e of ALL 2*nb blocks are produced by one launch per distinct condition and kept in a
+        pool -- 3 conditions per clip in the IPB configs, at most ~15 in the CRF config."""
+        nb2 = 2 * st["nb"]
+        pool = self.mix_pool
+        if pool is not None and (pool.device != dev or pool.shape[1] != nb2):
+            pool = self.mix_pool = None
+            self.mix_slots = {}
+        need = [c for c in conds if c not in self.mix_slots]
+        cap = 0 if pool is None else pool.shape[0]
+        if len(self.mix_slots) + len(need) > cap:
+            # recycle every slot (whatever is still enqueued reads its packs in stream order); grow when one call alone
+            # needs more conditions than the pool holds
+            if len(conds) > cap:
+                self.mix_pool = None
+                self.mix_pool = torch.empty((max(48, 2 * len(conds)), nb2, ops.PACK_A_BYTES), dtype=torch.uint8, device=dev)
+            self.mix_slots = {}
+            need = list(conds)
+        for c in need:
+            slot = len(self.mix_slots)
+            f = conds[c]
+            ops.pack_mix_blocks(st["conv2_w_all"], st["w1x1_all"], experts[f], gamma[f], self.mix_pool[slot])
+            self.mix_slots[c] = slot
+        return self.mix_slots
 
-    # ------------------------------------------------------------------ buffers
-    def _buffers(self, n, t, h, w, dev, lanes, maxn):
-        key = (n, t, h, w, dev, lanes, maxn, bool(self.m.vsr))
-        if self.buf is not None and self.buf_key == key:
-            return self.buf
-        self.buf = None                                   # release before re-allocating
-        names = ("kw", "pa", "pb", "xa", "xb", "t", "hr")
-        lane_bufs = []
-        for _ in range(lanes):
-            lb = {k: ops.new_feature(maxn, h, w, dev) for k in names}
-            lb["lr64"] = ops.new_feature(maxn, h, w, dev, zero=True)
-            lb["zero"] = ops.new_feature(maxn, h, w, dev, zero=True)
-            if self.m.vsr:      # x4 tail: 2Hx2W and 4Hx4W feature maps of one frame
-                lb["u1"] = ops.new_feature(maxn, 2 * h, 2 * w, dev)
-                lb["u2"] = ops.new_feature(maxn, 4 * h, 4 * w, dev)
-                lb["hr4"] = ops.new_feature(maxn, 4 * h, 4 * w, dev)
-            lb["launcher"] = _Launcher()
-            lane_bufs.append(lb)
-        # frame-major so that the features of a run of clips at one frame are one contiguous (N,H,W,64) block
-        b = dict(feats=torch.empty((t, n, h, w, 64), dtype=torch.bfloat16, device=dev), lanes=lane_bufs,
-                 streams=[torch.cuda.Stream(device=dev) for _ in range(lanes)] if lanes > 1 else [])
-        self.buf, self.buf_key = b, key
-        return b
+    # ------------------------------------------------------------------ program (pool, table, descriptors, graphs)
+    def _program(self, n, t, h, w, dev, maxn, steps):
+        key = (n, t, h, w, dev, maxn, self.m.num_blocks, bool(self.m.vsr))
+        if self.prog is None or self.prog.key != key:
+            self.prog = None                         # release the old pool before allocating the new one
+            self.prog = _Program(n, t, h, w, dev, maxn, self.m.num_blocks, bool(self.m.vsr), steps)
+        self.prog.ensure_table(steps)
+        return self.prog
+
+    def _build_nodes(self, pg, variant, nn, per_image, sparse, shapes):
+        """Launch sequence of one step variant for a run of ``nn`` clips: [(kind, label, ctypes args)], every operand
+        that changes per step left to the launch table (node index = position in the list)."""
+        lib = _lib.load()
+        nodes = []
+        h, w, nb = pg.h, pg.w, pg.nb
+        pool_ptr = pg.pool.data_ptr()
+
+        def dyn(node):
+            r = _lib.DynRef()
+            r.table, r.step, r.node, r.stride = pg.table.data_ptr(), pg.step_word.data_ptr(), node, pg.stride
+            return r
+
+        def conv(label, aux=False, idt=False, bias=False, par=False, act=PNP_ACT_NONE, flip=False, last=False,
+                 image=False, src=None, out=None, hh=h, ww=w, lq_up4=False):
+            d = ops.ConvDesc()
+            d.src = src.data_ptr() if src is not None else pool_ptr
+            d.src_images = 0 if src is not None else pg.pool_images
+            d.aux, d.aux_images = (pool_ptr, pg.pool_images) if aux else (None, 0)
+            d.idt, d.idt_images = (pool_ptr, pg.pool_images) if idt else (None, 0)
+            d.out_spx = d.out_sy = d.out_sn = 0
+            if last:
+                d.out, d.out_images = None, 0
+            elif out is not None:
+                d.out, d.out_images = out.data_ptr(), 0
+                if not out.is_contiguous():
+                    d.out_sn, d.out_sy, d.out_spx = out.stride(0), out.stride(1), out.stride(2)
+            else:
+                d.out, d.out_images = pool_ptr, pg.pool_images
+            d.wpack, d.scale = None, None
+            d.bias = 1 if bias else None                       # table mode: non-NULL only says "there is a bias"
+            if par:
+                d.par = 1
+                d.par_sn, d.par_sc, d.par_sy = shapes["par"]
+            if last:
+                d.lq, d.outf = 1, 1
+                d.lq_sn, d.lq_sc, d.lq_sy = shapes["lq"]       # with lq_up4: strides of the LR frame itself
+                d.of_sn, d.of_sc, d.of_sy = shapes["outf"]
+            d.N, d.H, d.W = nn, hh, ww
+            d.tap_n = 16 if last else 64
+            d.aux_k16 = 2 if aux else 0
+            d.act, d.mode = act, (ops.PNP_CONV_LAST if last else ops.PNP_CONV_BF16)
+            d.flip_y = 1 if flip else 0
+            d.lq_up4 = 1 if lq_up4 else 0
+            d.par_sparse = 1 if (par and sparse) else 0
+            d.wpack_stable = 1
+            d.per_image = 1 if image else 0
+            d.img_off = None
+            d.dyn = dyn(len(nodes))
+            nodes.append(("conv", label, (lib.pnp_conv3x3, ctypes.byref(d), d)))
+
+        def im2col():
+            r = dyn(len(nodes))
+            sn, sc, sy = shapes["lq"]
+            nodes.append(("im2col", "im2col", (lib.pnp_lr_im2col_dyn, ctypes.byref(r), r, sn, sc, sy, nn, h, w)))
+
+        def warp():
+            r = dyn(len(nodes))
+            fsy, fsn = shapes["flow"]
+            nodes.append(("warp", "warp", (lib.pnp_mv_warp_dyn, ctypes.byref(r), r, fsy, fsn, nn, h, w)))
+
+        bwd = variant.startswith("b_")
+        im2col()
+        if variant not in ("b_last", "f_first"):
+            warp()
+        if variant in ("b_last", "b_merged", "f_first"):
+            conv("input", aux=True, bias=True, act=PNP_ACT_LRELU)
+        elif variant in ("b_sep", "f_merged"):
+            conv("input", aux=True, bias=True)
+            conv("input", idt=True, act=PNP_ACT_LRELU)
+        else:   # f_sep
+            conv("input", aux=True, bias=True)
+            conv("input", idt=True)
+            conv("input", idt=True, act=PNP_ACT_LRELU)
+        for _ in range(nb):     # ResidualBlockNoBNDynamic_drt, sr_backbone_utils.py:304-333: launch A then launch B
+            conv("block_a", bias=True, par=True, act=PNP_ACT_RELU, image=per_image)
+            conv("block_b", idt=True, bias=True, flip=True)
+        if not bwd:
+            if pg.vsr:
+                # x4 tail (:135-142): lrelu(upsample1) -> lrelu(upsample2) -> lrelu(conv_hr) -> conv_last + bilinear x4 of
+                # the LR frame.  Pixel shuffle = strided store of launch g, the bilinear base is computed inside
+                # conv_last's epilogue from the LR frame.
+                u1, u2, hr4 = pg.u1[:nn], pg.u2[:nn], pg.hr4[:nn]
+                for g in range(4):
+                    conv("up", bias=True, act=PNP_ACT_LRELU, out=u1[:, g >> 1::2, g & 1::2, :])
+                for g in range(4):
+                    conv("up", bias=True, act=PNP_ACT_LRELU, src=u1, out=u2[:, g >> 1::2, g & 1::2, :], hh=2 * h, ww=2 * w)
+                conv("hr", bias=True, act=PNP_ACT_LRELU, src=u2, out=hr4, hh=4 * h, ww=4 * w)
+                conv("last", bias=True, last=True, src=hr4, hh=4 * h, ww=4 * w, lq_up4=True)
+            else:
+                # out = conv_last(lrelu(conv_hr(x))) + lq   (:144-146)
+                conv("hr", bias=True, act=PNP_ACT_LRELU)
+                conv("last", bias=True, last=True)
+        assert len(nodes) <= pg.stride
+        return nodes
+
+    def _fill_table(self, pg, st, g_idx, b0, nn, variants, bwd_key, fwd_key, slot_of, ptrs, per_image):
+        """Launch-table rows [g_idx*2T, (g_idx+1)*2T) for one run of clips, vectorised over the steps of each variant."""
+        t, n, nb, h, w = pg.t, pg.n, pg.nb, pg.h, pg.w
+        tab = pg.host_table.numpy()[g_idx * 2 * t:(g_idx + 1) * 2 * t]
+        off = pg.host_off.numpy()[g_idx * 2 * t:(g_idx + 1) * 2 * t]
+        tab[:] = 0
+        off[:] = 0
+        steps = np.arange(2 * t)
+        frame = np.where(steps < t, t - 1 - steps, steps - t)
+        var = np.array(variants)
+        img = pg.img_bytes
+        pool_ptr = pg.pool.data_ptr()
+        work = {k: v[0] for k, v in pg.work.items()}
+        feats = lambda i: i * n + b0                                             # noqa: E731 - pool image of frame i
+        bk, fk = np.array(bwd_key), np.array(fwd_key)
+        up = 4 if pg.vsr else 1
+        plane = h * w * 4
+        lr_ptr = ptrs["lrs"] + (b0 * t + frame) * 3 * plane
+        par_ptr = ptrs["par"] + (b0 * t + frame) * 3 * plane
+        outf_ptr = ptrs["out"] + (b0 * t + frame) * 3 * plane * up * up
+        mv_base = ptrs["mvs"] + (b0 * t + frame) * 4 * plane
+        flow_x = np.where(steps < t, mv_base + 2 * plane, mv_base)               # bwd pass: channels 2,3; fwd: 0,1
+        bias_row = 2 * nb * 64
+        # expert-mixed packs / biases: per-image offsets (per_image) or folded into the base pointers
+        slots = slot_of[b0:b0 + nn][:, frame]                                    # (nn, 2T)
+        slot_stride = self.mix_pool.stride(0)
+        if per_image:
+            off[:, :nn, 0] = (slots * slot_stride).T
+            off[:, :nn, 1] = (((b0 + np.arange(nn))[:, None] * t + frame[None, :]) * bias_row).T
+            w_base = np.full(2 * t, self.mix_pool.data_ptr(), dtype=np.int64)
+            b_base = np.full(2 * t, ptrs["bias_tab"], dtype=np.int64)
+            off_ptr = pg.img_off.data_ptr() + (g_idx * 2 * t + steps) * pg.maxn * 16
+        else:
+            w_base = self.mix_pool.data_ptr() + slots[0] * slot_stride
+            b_base = ptrs["bias_tab"] + (b0 * t + frame) * bias_row * 4
+            off_ptr = np.zeros(2 * t, dtype=np.int64)
+
+        def put(sel, node, p=(), i=(0, 0, 0, 0)):
+            for k, v in enumerate(p):
+                tab[sel, node, k] = v[sel] if isinstance(v, np.ndarray) else v
+            iv = [np.asarray(x[sel] if isinstance(x, np.ndarray) else x, dtype=np.int64) & 0xFFFFFFFF for x in i]
+            tab[sel, node, 6] = iv[0] | (iv[1] << 32)
+            tab[sel, node, 7] = iv[2] | (iv[3] << 32)
+
+        W = {k: v.data_ptr() for k, v in st.items() if isinstance(v, torch.Tensor)}
+        for v in set(variants):
+            sel = var == v
+            bwd = v.startswith("b_")
+            br = 0 if bwd else 1
+            node = 0
+            put(sel, node, p=(lr_ptr, pool_ptr + work["lr64"] * img))            # im2col
+            node += 1
+            cur = feats(frame)
+            if v not in ("b_last", "f_first"):
+                kidx = np.where(steps < t, bk[frame], fk[frame])
+                put(sel, node, p=(pool_ptr + feats(kidx) * img, flow_x, flow_x + plane, pool_ptr + work["kw"] * img))
+                node += 1
+            in_bias = W["bwd_in_bias"] if bwd else W["fwd_in_bias"]
+            if v == "b_last":       # zeros for key_warp / neighbour (:69-70)
+                put(sel, node, p=(W["bwd_merged_aux"], in_bias), i=(work["zero"], work["lr64"], 0, work["xa"]))
+                node += 1
+            elif v == "b_merged":   # align_key: the neighbour is the warped key (:85-88)
+                put(sel, node, p=(W["bwd_merged_aux"], in_bias), i=(work["kw"], work["lr64"], 0, work["xa"]))
+                node += 1
+            elif v == "b_sep":
+                put(sel, node, p=(W["bwd_key_aux"], in_bias), i=(work["kw"], work["lr64"], 0, work["pa"]))
+                put(sel, node + 1, p=(W["bwd_nb"],), i=(feats(frame + 1), 0, work["pa"], work["xa"]))
+                node += 2
+            elif v == "f_first":
+                put(sel, node, p=(W["fwd_bf_aux"], in_bias), i=(cur, work["lr64"], 0, work["xa"]))
+                node += 1
+            elif v == "f_merged":
+                put(sel, node, p=(W["fwd_bf_aux"], in_bias), i=(cur, work["lr64"], 0, work["pa"]))
+                put(sel, node + 1, p=(W["fwd_merged"],), i=(work["kw"], 0, work["pa"], work["xa"]))
+                node += 2
+            else:                   # f_sep
+                put(sel, node, p=(W["fwd_bf_aux"], in_bias), i=(cur, work["lr64"], 0, work["pa"]))
+                put(sel, node + 1, p=(W["fwd_key"],), i=(work["kw"], 0, work["pa"], work["pb"]))
+                put(sel, node + 2, p=(W["fwd_nb"],), i=(feats(frame - 1), 0, work["pb"], work["xa"]))
+                node += 3
+            x, other = work["xa"], work["xb"]
+            for k in range(nb):
+                blk = br * nb + k
+                put(sel, node, p=(w_base + blk * ops.PACK_A_BYTES, b_base + blk * 256, par_ptr, 0, 0, off_ptr),
+                    i=(x, 0, 0, work["t"]))
+                o = cur if k == nb - 1 else other
+                put(sel, node + 1, p=(W["conv1_w"] + blk * ROW_BYTES, W["conv1_b"] + blk * 256),
+                    i=(work["t"], 0, x, o))
+                node += 2
+                x, other = o, x
+            if not bwd:
+                if pg.vsr:
+                    for name, src_f in (("up1", cur), ("up2", 0)):
+                        for g in range(4):
+                            put(sel, node, p=(st[name + "_w"][g].data_ptr(), st[name + "_b"][g].data_ptr()),
+                                i=(src_f, 0, 0, 0))
+                            node += 1
+                    put(sel, node, p=(W["hr_w"], W["hr_b"]), i=(0, 0, 0, 0))
+                    put(sel, node + 1, p=(W["last_w"], W["last_b"], 0, lr_ptr, outf_ptr), i=(0, 0, 0, 0))
+                else:
+                    put(sel, node, p=(W["hr_w"], W["hr_b"]), i=(cur, 0, 0, work["hr"]))
+                    put(sel, node + 1, p=(W["last_w"], W["last_b"], 0, lr_ptr, outf_ptr), i=(work["hr"], 0, 0, 0))
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, lrs, *args, **kwargs):
         """Runs ``_forward`` with ``lrs.device`` as the current CUDA device (every launch of libpnpvcve goes to the
         current device / its current stream; the reference accepts a module on a non-current device) and orders the
-        call behind the previous one: the work buffers are reused, so a call from another stream waits for the event
+        call behind the previous one: the pool is reused, so a call from another stream waits for the event
         the previous call recorded."""
         dev = lrs.device
         if dev.type != "cuda":
@@ -339,10 +529,11 @@ class BaeEngine:
         """cond_host: optional host copies (slices, base_QPs, QPs), each (n,T) -- skips the one device->host copy.
         frame_ready(i): called (host side) before frame i's lq / mvs / par_map are first read, in the backward-time
         pass (i = T-1 .. 0); frame_done(i, out): called after frame i's output has been enqueued.  Both let a caller
-        stream a clip in and out in chunks (driver.stream_clips): they typically enqueue an event wait / record.
+        stream a clip in and out in chunks (driver.ClipStreamer): they typically enqueue an event wait / record.
         out: optional preallocated fp32 (n,T,3,Hout,Wout) result buffer (the caller guarantees nobody still reads it)."""
         m = self.m
         dev = lrs.device
+        lib = _lib.load()
         _lib.require_device()
         n, t, c, h_in, w_in = lrs.shape
         assert h_in >= 64 and w_in >= 64, (
@@ -369,7 +560,6 @@ class BaeEngine:
         # mvs[:, i, :2], i.e. exactly flows_forward[i-1].  No branch (and no host sync) is needed.
 
         st = self._pack_static(dev)
-        nb = st["nb"]
         # one D2H copy for everything the host needs (the reference syncs 2(T-1)n+1 times)
         if cond_host is not None:
             cond = torch.stack([torch.as_tensor(c, dtype=torch.float32).reshape(n, t).cpu() for c in cond_host], 0)
@@ -377,264 +567,151 @@ class BaeEngine:
             cond = torch.stack([slices.reshape(n, t).float(), base_QPs.reshape(n, t).float(),
                                 QPs.reshape(n, t).float()], 0).cpu()
         key_rows = keyframe_rows(cond[0])
-        crf_host, qp_host = cond[1], cond[2]
+        crf_host, qp_host = cond[1].numpy(), cond[2].numpy()
 
         experts, gamma = ops.caa_heads(base_QPs.reshape(-1).float().contiguous(),
                                        QPs.reshape(-1).float().contiguous(), st["caa"], m.num_experts)
         bias_tab = ops.mix_bias(st["conv2_bias_all"], experts, gamma)       # (n*t, 2*nb, 64)
-        # Clips with the same key-frame schedule and the same per-frame (CRF, QP) conditions use the same
-        # weights at every step, so a run of such clips is ONE launch sequence with N images per launch
-        # (the many-clip LR workload): fixed launch cost and the host launch rate are shared N ways.
-        sigs = [(tuple(key_rows[b]), tuple(crf_host[b].tolist()), tuple(qp_host[b].tolist())) for b in range(n)]
-        groups = []
+        # expert-mixed packs of every distinct (CRF, QP) condition of the call, packed up front
+        conds, cond_keys = {}, []
         for b in range(n):
-            if self.batch_clips and groups and sigs[b] == sigs[groups[-1][0]] and \
-                    groups[-1][1] - groups[-1][0] < self.max_batch:
-                groups[-1][1] = b + 1
-            else:
-                groups.append([b, b + 1])
-        maxn = max(g[1] - g[0] for g in groups)
-        lanes = max(1, min(len(groups), self.max_lanes))
-        bufs = self._buffers(n, t, h, w, dev, lanes, maxn)
-        feats = bufs["feats"]
+            row = [(float(crf_host[b, i]), float(qp_host[b, i])) for i in range(t)]
+            cond_keys.append(row)
+            for i, k in enumerate(row):
+                conds.setdefault(k, b * t + i)
+        slot_map = self._mix_slots_for(st, conds, experts, gamma, dev)
+        slot_of = np.array([[slot_map[k] for k in row] for row in cond_keys], dtype=np.int64)
+
+        groups = group_clips(key_rows, self.max_batch, self.batch_clips)
+        maxn = max(b1 - b0 for b0, b1 in groups)
+        pg = self._program(n, t, h, w, dev, maxn, 2 * t * len(groups))
         up = 4 if m.vsr else 1
         if out is None:
             out = torch.empty((n, t, 3, up * h, up * w), dtype=torch.float32, device=dev)
         elif tuple(out.shape) != (n, t, 3, up * h, up * w) or out.dtype != torch.float32 or out.device != dev or \
                 not out.is_contiguous():
             raise ValueError(f"out must be a contiguous fp32 {(n, t, 3, up * h, up * w)} tensor on {dev}")
-        prof = self.prof
-        seen = {}
+        feats = pg.feats
         bwd_feats = torch.empty_like(feats) if return_features else None
-        counts = [0] * lanes
+        # the reference takes the sparse path only in eval mode (sr_backbone_utils.py:307: `self.sparse_val and
+        # not self.training`); a module left in train() under no_grad computes the dense blend
+        sparse = bool(m.sparse_val) and not m.training
 
-        # expert-mixed conv2 packs for every distinct (CRF, QP) pair of the call, packed up front on the
-        # caller's stream so that the clip lanes below only read them
-        mixed_of = {}
-        for b in range(n):
-            for i in range(t):
-                key = (float(crf_host[b, i]), float(qp_host[b, i]))
-                if key not in mixed_of:
-                    f = b * t + i
-                    mixed_of[key] = self._mixed_conv2(st, key, experts[f], gamma[f], dev)
+        # ---------------- launch table of the whole call: one H2D copy
+        if pg.uploaded is not None:
+            pg.uploaded.synchronize()                     # the pinned staging buffers are reused between calls
+        ptrs = dict(lrs=lrs.data_ptr(), par=par_map.data_ptr(), mvs=mvs.data_ptr(), out=out.data_ptr(),
+                    bias_tab=bias_tab.data_ptr())
+        plans = []
+        for g_idx, (b0, b1) in enumerate(groups):
+            bwd_key, fwd_key = key_schedule(key_rows[b0])
+            variants = step_variants(bwd_key, fwd_key)
+            per_image = bool((slot_of[b0:b1] != slot_of[b0:b0 + 1]).any())
+            self._fill_table(pg, st, g_idx, b0, b1 - b0, variants, bwd_key, fwd_key, slot_of, ptrs, per_image)
+            plans.append((b0, b1, variants, per_image))
+        rows = 2 * t * len(groups)
+        pg.table[:rows].copy_(pg.host_table[:rows], non_blocking=True)
+        pg.img_off[:rows].copy_(pg.host_off[:rows], non_blocking=True)
+        pg.uploaded = torch.cuda.Event()
+        pg.uploaded.record()
 
-        def clip_steps(b0, b1, lane):
-            """One run of identically-conditioned clips [b0, b1) on one lane (own stream + work buffers);
-            yields after every frame step so that lanes interleave."""
-            b = b0
-            nn = b1 - b0
-            buf = {k: (v[:nn] if isinstance(v, torch.Tensor) else v) for k, v in bufs["lanes"][lane].items()}
-            conv = buf["launcher"]
-            conv.prof, conv.prof_every, conv.seen = prof, self.prof_every, seen
-            conv.rows_par = self.rows_par
-            # the reference takes the sparse path only in eval mode (sr_backbone_utils.py:307: `self.sparse_val and
-            # not self.training`); a module left in train() under no_grad computes the dense blend
-            conv.par_sparse = bool(m.sparse_val) and not m.training
-            stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        plane = h * w
+        shapes = dict(lq=(t * 3 * plane, plane, w), par=(t * 3 * plane, plane, w), flow=(w, t * 4 * plane),
+                      outf=(t * 3 * plane * up * up, plane * up * up, w * up))
+        prof = self.prof
+        graphs = self.use_graphs and prof is None
+        self.last_mode = "graph" if graphs else "eager"
+        seen = {}
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        step_ptr = ctypes.c_void_p(pg.step_word.data_ptr())
+        launches = 0
 
-            def warp(src, flow, dst):
-                timed = prof is not None and "warp" in prof
-                if timed:
-                    k = seen.get("warp", 0)
-                    seen["warp"] = k + 1
-                    timed = (k % conv.prof_every) == 0
+        def phase(name):
+            """prof["phases"]: one event per phase boundary of a frame step"""
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            prof["phases"].append((name, ev))
+
+        def run_nodes(nodes, stream):
+            for kind, label, a in nodes:
+                timed = prof is not None and label in prof
+                if timed:                                  # bracket every prof_every-th launch of this label
+                    k = seen.get(label, 0)
+                    seen[label] = k + 1
+                    timed = (k % self.prof_every) == 0
                 if timed:
                     e0 = torch.cuda.Event(enable_timing=True)
                     e1 = torch.cuda.Event(enable_timing=True)
                     e0.record()
-                ops.mv_warp(src, flow, dst)
+                if kind == "conv":
+                    rc = a[0](a[1], stream)
+                elif kind == "warp":
+                    rc = a[0](a[1], a[3], a[4], a[5], a[6], a[7], stream)
+                else:
+                    rc = a[0](a[1], a[3], a[4], a[5], a[6], a[7], a[8], stream)
                 if timed:
                     e1.record()
-                    prof["warp"].append((e0, e1))
+                    prof[label].append((e0, e1))
+                if rc != 0:
+                    _lib.check(rc, "pnp_" + kind)
 
-            fast, wptr_cache = {}, {}       # per clip run: pre-filled block descriptors, weight pointers per mix
-
-            def stack(name, blk_off, i, x, dst, mixed):
-                """8 BAE blocks: x (in xa/xb) -> dst.  ResidualBlockNoBNDynamic_drt, sr_backbone_utils.py:304-333"""
-                f = b * t + i
-                par = par_map[b0:b1, i]
-                other = buf["xb"] if x is buf["xa"] else buf["xa"]
-                if self.fused_block:
-                    if conv.par_sparse:
-                        raise NotImplementedError("PNP_FUSED_BLOCK has no sparse_val path; unset it")
-                    for k in range(nb):
-                        o = dst if k == nb - 1 else other
-                        conv.block(stream, x, o, mixed[name][k], st[name + "_conv1_dn"][k],
-                                   bias_tab[f, blk_off + k], st[name + "_conv1_b"][k], par)
-                        x, other = o, x
-                    counts[lane] += nb
-                    return
-                if prof is None or not ("block_a" in prof or "block_b" in prof):
-                    # Fast path (32 of a frame's ~42 launches): the two descriptors of every block are filled once per
-                    # clip run; per launch only the pointers that change are patched -- filling a 40-field ctypes
-                    # descriptor and slicing the bias table per launch cost ~16 us of host time per launch, 40 % of the
-                    # GPU time on a slow host.
-                    key = (name, par.stride(0), par.stride(1), par.stride(2))
-                    descs = fast.get(key)
-                    if descs is None:
-                        descs = []
-                        for k in range(nb):
-                            da, db = ops.ConvDesc(), ops.ConvDesc()
-                            ops.fill_conv_desc(da, x, mixed[name][k], buf["t"], None, None, None, bias_tab[f, blk_off + k],
-                                               par, PNP_ACT_RELU, None, None, wlayout=0 if not conv.rows_par else 1,
-                                               wpack_stable=True, par_sparse=conv.par_sparse)
-                            ops.fill_conv_desc(db, buf["t"], st[name + "_conv1_w"][k], other, None, x, None,
-                                               st[name + "_conv1_b"][k], None, PNP_ACT_NONE, None, None, wlayout=1,
-                                               flip_y=True, wpack_stable=True)
-                            descs.append((da, ctypes.byref(da), db, ctypes.byref(db)))
-                        fast[key] = descs
-                    wptrs = wptr_cache.get(id(mixed[name]))
-                    if wptrs is None:
-                        wptrs = wptr_cache[id(mixed[name])] = [wk.data_ptr() for wk in mixed[name]]
-                    x_ptr, o_ptr, dst_ptr = x.data_ptr(), other.data_ptr(), dst.data_ptr()
-                    par_ptr = par.data_ptr()
-                    bias_ptr = bias_tab.data_ptr() + (f * bias_tab.shape[1] + blk_off) * 256     # 64 fp32 per row
-                    fn = conv.fn
-                    for k in range(nb):
-                        da, ra, db, rb = descs[k]
-                        da.src, da.wpack, da.bias, da.par = x_ptr, wptrs[k], bias_ptr + 256 * k, par_ptr
-                        rc = fn(ra, stream)
-                        if rc != 0:
-                            _lib.check(rc, "pnp_conv3x3")
-                        nxt_ptr = dst_ptr if k == nb - 1 else o_ptr
-                        db.out, db.idt = nxt_ptr, x_ptr
-                        rc = fn(rb, stream)
-                        if rc != 0:
-                            _lib.check(rc, "pnp_conv3x3")
-                        x_ptr, o_ptr = nxt_ptr, x_ptr
-                    counts[lane] += 2 * nb
-                    return
-                for k in range(nb):
-                    conv(stream, x, mixed[name][k], out=buf["t"], bias=bias_tab[f, blk_off + k],
-                         par=par, act=PNP_ACT_RELU, label="block_a")
-                    o = dst if k == nb - 1 else other
-                    conv(stream, buf["t"], st[name + "_conv1_w"][k], out=o, idt=x,
-                         bias=st[name + "_conv1_b"][k], act=PNP_ACT_NONE, label="block_b", flip_y=True)
-                    x, other = o, x
-                counts[lane] += 2 * nb
-
-            def phase(name):
-                """prof["phases"]: one event per phase boundary of a frame step (4 per frame, negligible)"""
+        def run_step(step, variant, nn, per_image):
+            nonlocal launches
+            key = (variant, nn, per_image, sparse)
+            nodes = pg.nodes.get(key)
+            if nodes is None:
+                nodes = pg.nodes[key] = self._build_nodes(pg, variant, nn, per_image, sparse, shapes)
+            launches += len(nodes)
+            if not graphs:
+                _lib.check(lib.pnp_set_step(step_ptr, step, stream), "pnp_set_step")
                 if prof is not None and "phases" in prof:
-                    ev = torch.cuda.Event(enable_timing=True)
-                    ev.record()
-                    prof["phases"].append((name, ev))
+                    # events at the phase boundaries of the step: [im2col, warp, input convs] [blocks] [head]
+                    n_in = sum(1 for k in nodes if k[1] in ("im2col", "warp", "input"))
+                    n_blk = sum(1 for k in nodes if k[1] in ("block_a", "block_b"))
+                    tag = "bwd" if variant.startswith("b_") else "fwd"
+                    phase(tag + "_start")
+                    run_nodes(nodes[:n_in], stream)
+                    phase(tag + "_input_done")
+                    run_nodes(nodes[n_in:n_in + n_blk], stream)
+                    phase(tag + "_stack_done")
+                    run_nodes(nodes[n_in + n_blk:], stream)
+                    if tag == "fwd":
+                        phase("fwd_head_done")
+                else:
+                    run_nodes(nodes, stream)
+                return
+            g = pg.graphs.get(key)
+            if g is None:
+                # capture (nothing executes) on the program's side stream, then replay in the caller's stream
+                cap = ctypes.c_void_p(pg.cap_stream.cuda_stream)
+                _lib.check(lib.pnp_graph_begin(cap), "pnp_graph_begin")
+                handle = ctypes.c_void_p()
+                try:
+                    run_nodes(nodes, cap)
+                finally:
+                    rc = lib.pnp_graph_end(cap, ctypes.byref(handle))
+                _lib.check(rc, "pnp_graph_end")
+                g = pg.graphs[key] = handle
+            rc = lib.pnp_graph_launch(g, step_ptr, step, stream)
+            if rc != 0:
+                _lib.check(rc, "pnp_graph_launch")
 
-            bwd_key, fwd_key = key_schedule(key_rows[b])
+        for g_idx, (b0, b1, variants, per_image) in enumerate(plans):
+            nn = b1 - b0
+            base = g_idx * 2 * t
             # ---------------- backward-time propagation (iconvsr_ipb_par.py:67-100)
-            for i in range(t - 1, -1, -1):
-                mixed = mixed_of[(float(crf_host[b, i]), float(qp_host[b, i]))]
+            for s in range(t):
                 if frame_ready is not None:
-                    frame_ready(i)
-                phase("bwd_start")
-                ops.lr_im2col(lrs[b0:b1, i], buf["lr64"])
-                counts[lane] += 1
-                x0 = buf["xa"]
-                if i < t - 1:
-                    kidx = bwd_key[i]
-                    warp(feats[kidx, b0:b1], mvs[b0:b1, i, 2:4], buf["kw"])
-                    counts[lane] += 1
-                    if kidx == i + 1:                     # align_key: neighbour is the warped key
-                        conv(stream, buf["kw"], st["bwd_merged_aux"], out=x0, aux=buf["lr64"],
-                             bias=st["bwd_in_bias"], act=PNP_ACT_LRELU, label="input")
-                        counts[lane] += 1
-                    else:
-                        conv(stream, buf["kw"], st["bwd_key_aux"], out=buf["pa"], aux=buf["lr64"],
-                             bias=st["bwd_in_bias"], act=PNP_ACT_NONE, label="input")
-                        conv(stream, feats[i + 1, b0:b1], st["bwd_nb"], out=x0, idt=buf["pa"],
-                             act=PNP_ACT_LRELU, label="input")
-                        counts[lane] += 2
-                else:                                     # zeros for key_warp / neighbour (:69-70)
-                    conv(stream, buf["zero"], st["bwd_merged_aux"], out=x0, aux=buf["lr64"],
-                         bias=st["bwd_in_bias"], act=PNP_ACT_LRELU, label="input")
-                    counts[lane] += 1
-                phase("bwd_input_done")
-                stack("bwd", 0, i, x0, feats[i, b0:b1], mixed)
-                phase("bwd_stack_done")
-                yield
+                    frame_ready(t - 1 - s)
+                run_step(base + s, variants[s], nn, per_image)
             if return_features:
                 bwd_feats[:, b0:b1].copy_(feats[:, b0:b1])
             # ---------------- forward-time propagation + reconstruction (:102-147)
             for i in range(t):
-                mixed = mixed_of[(float(crf_host[b, i]), float(qp_host[b, i]))]
-                phase("fwd_start")
-                ops.lr_im2col(lrs[b0:b1, i], buf["lr64"])
-                counts[lane] += 1
-                x0 = buf["xa"]
-                cur = feats[i, b0:b1]                     # backward feature of frame i (outputs[i])
-                if i > 0:
-                    kidx = fwd_key[i]
-                    warp(feats[kidx, b0:b1], mvs[b0:b1, i, 0:2], buf["kw"])
-                    conv(stream, cur, st["fwd_bf_aux"], out=buf["pa"], aux=buf["lr64"],
-                         bias=st["fwd_in_bias"], act=PNP_ACT_NONE, label="input")
-                    counts[lane] += 2
-                    if kidx == i - 1:
-                        conv(stream, buf["kw"], st["fwd_merged"], out=x0, idt=buf["pa"], act=PNP_ACT_LRELU,
-                             label="input")
-                        counts[lane] += 1
-                    else:
-                        conv(stream, buf["kw"], st["fwd_key"], out=buf["pb"], idt=buf["pa"],
-                             act=PNP_ACT_NONE, label="input")
-                        conv(stream, feats[i - 1, b0:b1], st["fwd_nb"], out=x0, idt=buf["pb"],
-                             act=PNP_ACT_LRELU, label="input")
-                        counts[lane] += 2
-                else:
-                    conv(stream, cur, st["fwd_bf_aux"], out=x0, aux=buf["lr64"], bias=st["fwd_in_bias"],
-                         act=PNP_ACT_LRELU, label="input")
-                    counts[lane] += 1
-                phase("fwd_input_done")
-                stack("fwd", nb, i, x0, cur, mixed)
-                phase("fwd_stack_done")
-                if m.vsr:
-                    # x4 tail (:135-142): lrelu(upsample1) -> lrelu(upsample2) -> lrelu(conv_hr) -> conv_last
-                    # + bilinear x4 of the LR frame.  Pixel shuffle = strided store of launch g, the bilinear
-                    # base is computed inside conv_last's epilogue from the LR frame.
-                    for src_f, dst_f, name in ((cur, buf["u1"], "up1"), (buf["u1"], buf["u2"], "up2")):
-                        for g in range(4):
-                            conv(stream, src_f, st[name + "_w"][g], out=dst_f[:, g >> 1::2, g & 1::2, :],
-                                 bias=st[name + "_b"][g], act=PNP_ACT_LRELU, label="up")
-                    conv(stream, buf["u2"], st["hr_w"], out=buf["hr4"], bias=st["hr_b"], act=PNP_ACT_LRELU, label="hr")
-                    conv(stream, buf["hr4"], st["last_w"], bias=st["last_b"], lq=lrs[b0:b1, i],
-                         outf=out[b0:b1, i], label="last", lq_up4=True)
-                    counts[lane] += 10
-                else:
-                    # out = conv_last(lrelu(conv_hr(x))) + lq   (:144-146)
-                    conv(stream, cur, st["hr_w"], out=buf["hr"], bias=st["hr_b"], act=PNP_ACT_LRELU, label="hr")
-                    conv(stream, buf["hr"], st["last_w"], bias=st["last_b"], lq=lrs[b0:b1, i],
-                         outf=out[b0:b1, i], label="last")
-                    counts[lane] += 2
-                phase("fwd_head_done")
+                run_step(base + t + i, variants[t + i], nn, per_image)
                 if frame_done is not None and b1 == n:
                     frame_done(i, out)
-                yield
-
-        def lane_steps(lane):
-            for g in range(lane, len(groups), lanes):     # runs of this lane, one after the other
-                yield from clip_steps(groups[g][0], groups[g][1], lane)
-
-        main = torch.cuda.current_stream()
-        if lanes == 1:
-            for _ in lane_steps(0):
-                pass
-        else:
-            streams = bufs["streams"]
-            gens = []
-            for lane in range(lanes):
-                streams[lane].wait_stream(main)
-                with torch.cuda.stream(streams[lane]):
-                    gens.append(lane_steps(lane))
-            live = list(range(lanes))
-            while live:
-                for lane in list(live):
-                    with torch.cuda.stream(streams[lane]):
-                        try:
-                            next(gens[lane])
-                        except StopIteration:
-                            live.remove(lane)
-            for lane in range(lanes):
-                main.wait_stream(streams[lane])
-        launches = sum(counts)
         self.launch_count = launches
         if return_features:
-            return out, bwd_feats.transpose(0, 1), feats.transpose(0, 1)     # (n, T, H, W, 64) views
+            return out, bwd_feats.transpose(0, 1), feats.clone().transpose(0, 1)     # (n, T, H, W, 64)
         return out

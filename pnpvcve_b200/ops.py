@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import (PNP_ACT_LRELU, PNP_ACT_NONE, PNP_ACT_RELU, PNP_CONV_BF16,  # noqa: F401
-                   PNP_CONV_LAST, BlockDesc, ConvDesc)
+                   PNP_CONV_LAST, ConvDesc, DynRef)
 
 CHUNK_BYTES = 8192
 
@@ -61,10 +61,6 @@ def new_feature(n, h, w, device, zero=False):
     return f((n, h, w, 64), dtype=torch.bfloat16, device=device)
 
 
-def new_wpack(n_chunks, device):
-    return torch.zeros(n_chunks * CHUNK_BYTES, dtype=torch.uint8, device=device)
-
-
 @_on_device_of
 def mv_warp(src, flow, dst, debug=False):
     """K1.  src/dst (N,H,W,64) bf16; flow (2,H,W) or (N,2,H,W) fp32 view (x then y).  Returns (x0,y0) if debug."""
@@ -100,22 +96,6 @@ def lr_im2col(lr, dst):
     lib = _lib.load()
     _lib.check(lib.pnp_lr_im2col(_ptr(lr), lr.stride(0), lr.stride(1), lr.stride(2), _ptr(dst), n, h, w,
                                  _stream()), "pnp_lr_im2col")
-
-
-@_on_device_of
-def pack_conv3x3(w, dst, coef=None, in_begin=0, in_begin2=-1, in_count=None, center_chunks=1,
-                 row_scale=None):
-    """w fp32 (O,I,3,3) or (E,O,I,3,3) contiguous -> packed blocks in dst (uint8)."""
-    if w.dtype != torch.float32 or not w.is_contiguous():
-        raise ValueError("pack_conv3x3: w must be contiguous fp32")
-    if w.dim() == 4:
-        e, (o, i) = 1, w.shape[:2]
-    else:
-        e, o, i = w.shape[:3]
-    in_count = i - in_begin if in_count is None else in_count
-    lib = _lib.load()
-    _lib.check(lib.pnp_pack_conv3x3(_ptr(w), e, _ptr(coef), _ptr(row_scale), o, i, in_begin, in_begin2, in_count,
-                                    _ptr(dst), center_chunks, _stream()), "pnp_pack_conv3x3")
 
 
 def rowstack_bytes(tap_n=64, with_aux=False, with_par=False):
@@ -163,6 +143,24 @@ def pack_aux(w, dst):
     _lib.check(lib.pnp_pack_aux(_ptr(w), w.shape[0], w.shape[1], _ptr(dst), _stream()), "pnp_pack_aux")
 
 
+PACK_A_BYTES = 12 * CHUNK_BYTES      # block-launch-A pack: row-stacked conv2 mix (72 KB) + three stacked 1x1 (24 KB)
+
+
+@_on_device_of
+def pack_mix_blocks(w2, w1x1, coef, row_scale, dst):
+    """All block-launch-A packs of one (CRF, QP) condition: w2 fp32 (B,E,64,64,3,3), w1x1 fp32 (B,3,64,64), coef (E,),
+    row_scale (64,) -> dst uint8 (B, PACK_A_BYTES)."""
+    b, e = w2.shape[:2]
+    if w2.dtype != torch.float32 or w1x1.dtype != torch.float32 or not w2.is_contiguous() or not w1x1.is_contiguous() \
+            or tuple(w2.shape[2:]) != (64, 64, 3, 3) or tuple(w1x1.shape) != (b, 3, 64, 64):
+        raise ValueError("pack_mix_blocks: need contiguous fp32 (B,E,64,64,3,3) and (B,3,64,64)")
+    if dst.dtype != torch.uint8 or dst.dim() != 2 or dst.shape[0] != b or dst.shape[1] < PACK_A_BYTES or dst.stride(1) != 1:
+        raise ValueError("pack_mix_blocks: dst must be uint8 (B, >= PACK_A_BYTES)")
+    lib = _lib.load()
+    _lib.check(lib.pnp_pack_mix_blocks(_ptr(w2), _ptr(w1x1), b, e, _ptr(coef), _ptr(row_scale), _ptr(dst),
+                                       dst.stride(0), _stream()), "pnp_pack_mix_blocks")
+
+
 @_on_device_of
 def caa_heads(base_qp, qp, params, n_experts):
     """base_qp/qp: fp32 (F,) -> experts (F,E), gamma (F,64).  params: dict of the six CAA tensors."""
@@ -191,10 +189,11 @@ def mix_bias(conv2_bias, experts, gamma):
 
 
 def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
-                   act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False, wpack_stable=False,
-                   lq_up4=False, par_sparse=False):
-    """Fill a ConvDesc in place (reusable across launches).  `out` may be a strided (N,H,W,64) view with
-    unit channel stride (e.g. up[:, i::2, j::2, :]: pixel shuffle as the store epilogue)."""
+                   act=PNP_ACT_NONE, lq=None, outf=None, flip_y=False, wpack_stable=False,
+                   lq_up4=False, par_sparse=False, img_off=None):
+    """Fill a ConvDesc in place (static launch: every operand is in the descriptor).  `out` may be a strided
+    (N,H,W,64) view with unit channel stride (e.g. up[:, i::2, j::2, :]: pixel shuffle as the store epilogue).
+    img_off: int64 (N,2) device tensor of per-image (weight byte offset, bias float offset) -> per-image launch."""
     n, h, w, _ = src.shape
     last = outf is not None
     d.src, d.aux, d.idt = src.data_ptr(), (aux.data_ptr() if aux is not None else None), \
@@ -220,25 +219,27 @@ def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias
         d.lq, d.lq_sn, d.lq_sc, d.lq_sy = None, 0, 0, 0
         d.outf, d.of_sn, d.of_sc, d.of_sy = None, 0, 0, 0
     d.N, d.H, d.W = n, h, w
-    d.center_n = 16 if last else (256 if par is not None else 64)
     d.tap_n = 16 if last else 64
     d.aux_k16 = 2 if aux is not None else 0
-    d.n_wchunks = (4 if par is not None else 1) + 8 + (1 if aux is not None else 0)
     d.act = act
     d.mode = PNP_CONV_LAST if last else PNP_CONV_BF16
-    d.wlayout = wlayout
     d.flip_y = 1 if flip_y else 0
     d.wpack_stable = 1 if wpack_stable else 0
+    d.per_image = 1 if img_off is not None else 0
+    d.img_off = img_off.data_ptr() if img_off is not None else None
+    d.dyn.table, d.dyn.step, d.dyn.node, d.dyn.stride = None, None, 0, 0
+    d.src_images = d.aux_images = d.idt_images = d.out_images = 0
     return d
 
 
 @_on_device_of
 def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par=None,
-            act=PNP_ACT_NONE, lq=None, outf=None, wlayout=0, flip_y=False, wpack_stable=False, lq_up4=False,
-            par_sparse=False):
+            act=PNP_ACT_NONE, lq=None, outf=None, flip_y=False, wpack_stable=False, lq_up4=False,
+            par_sparse=False, img_off=None):
     """Fused tcgen05 3x3 conv (see include/pnp_vcve.h: pnp_conv3x3).  `out` may be a strided view with unit
     channel stride (pixel shuffle as the store epilogue); lq_up4: lq is the (N,3,H/4,W/4) frame whose x4
-    bilinear upsampling is added."""
+    bilinear upsampling is added; img_off: per-image weight / bias offsets (one launch, N differently
+    conditioned images)."""
     _feat_check(src, "src")
     for t, nm in ((out, "out"), (aux, "aux"), (idt, "idt")):
         if t is not None:
@@ -253,50 +254,14 @@ def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par
                 hw = (src.shape[1] // 4, src.shape[2] // 4)
             if t.dim() != 4 or t.shape[1] != 3 or t.shape[0] != src.shape[0] or tuple(t.shape[2:]) != hw:
                 raise ValueError(f"conv3x3: {nm} must be (N,3,H,W) matching src" + (" / 4" if hw[0] != src.shape[1] else ""))
-    d = fill_conv_desc(ConvDesc(), src, wpack, out, aux, idt, scale, bias, par, act, lq, outf, wlayout, flip_y,
-                       wpack_stable, lq_up4, par_sparse)
-    need = rowstack_bytes(d.tap_n, aux is not None, par is not None) if wlayout == 1 \
-        else d.n_wchunks * CHUNK_BYTES
-    if wpack.numel() < need:
+    if img_off is not None and (img_off.dtype != torch.int64 or tuple(img_off.shape) != (src.shape[0], 2) or
+                                not img_off.is_contiguous() or not img_off.is_cuda):
+        raise ValueError("conv3x3: img_off must be a contiguous int64 (N,2) CUDA tensor")
+    d = fill_conv_desc(ConvDesc(), src, wpack, out, aux, idt, scale, bias, par, act, lq, outf, flip_y,
+                       wpack_stable, lq_up4, par_sparse, img_off)
+    need = rowstack_bytes(d.tap_n, aux is not None, par is not None)
+    if img_off is None and wpack.numel() < need:
         raise ValueError("conv3x3: packed weight buffer too small for this configuration")
     lib = _lib.load()
     _lib.check(lib.pnp_conv3x3(ctypes.byref(d), _stream()), "pnp_conv3x3")
     return out if outf is None else outf
-
-
-BLOCK_W1_BYTES = 12 * CHUNK_BYTES      # stage 1: row-stacked conv2 mix (9 blocks) + three stacked 1x1 (3 blocks)
-BLOCK_W2_BYTES = 9 * CHUNK_BYTES       # stage 2: row-stacked conv1
-
-
-def fill_block_desc(d, x, out, w_stage1, w_stage2, bias1, bias2, par):
-    """Fill a BlockDesc in place (reusable across launches)."""
-    n, h, w, _ = x.shape
-    d.x, d.out = x.data_ptr(), out.data_ptr()
-    d.w_stage1, d.w_stage2 = w_stage1.data_ptr(), w_stage2.data_ptr()
-    d.bias1 = bias1.data_ptr() if bias1 is not None else None
-    d.bias2 = bias2.data_ptr() if bias2 is not None else None
-    d.par, d.par_sn, d.par_sc, d.par_sy = par.data_ptr(), par.stride(0), par.stride(1), par.stride(2)
-    d.N, d.H, d.W = n, h, w
-    return d
-
-
-@_on_device_of
-def resblock(x, out, w_stage1, w_stage2, par, bias1=None, bias2=None):
-    """One fused BAE residual block (see include/pnp_vcve.h: pnp_resblock)."""
-    _feat_check(x, "x")
-    _feat_check(out, "out")
-    if out.shape != x.shape:
-        raise ValueError(f"resblock: out shape {tuple(out.shape)} != x {tuple(x.shape)}")
-    _plane_view_check(par, "par")
-    if par.dim() != 4 or par.shape[1] != 3 or par.shape[0] != x.shape[0] or \
-            tuple(par.shape[2:]) != tuple(x.shape[1:3]):
-        raise ValueError("resblock: par must be (N,3,H,W) matching x")
-    if w_stage1.numel() < BLOCK_W1_BYTES or w_stage2.numel() < BLOCK_W2_BYTES:
-        raise ValueError("resblock: packed weight buffer too small")
-    for b in (bias1, bias2):
-        if b is not None and (b.dtype != torch.float32 or b.numel() != 64 or not b.is_contiguous()):
-            raise ValueError("resblock: biases must be contiguous fp32 [64]")
-    d = fill_block_desc(BlockDesc(), x, out, w_stage1, w_stage2, bias1, bias2, par)
-    lib = _lib.load()
-    _lib.check(lib.pnp_resblock(ctypes.byref(d), _stream()), "pnp_resblock")
-    return out

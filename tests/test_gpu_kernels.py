@@ -103,21 +103,25 @@ def test_mv_warp_rejects_bad_arguments(dev):
 SHAPES = [(1, 64, 64), (1, 68, 132), (2, 72, 200), (1, 180, 320), (1, 376, 1244)]
 
 
-def _pack(wt, dev, layout, **kw):
-    """Pack a 3x3 conv in the tap-major (0) or row-stacked (1) weight layout."""
-    if layout == 0:
-        wp = ops.new_wpack(10, dev)
-        ops.pack_conv3x3(wt, wp, **kw)
-    else:
-        tap_n = 16 if wt.shape[-4] <= 16 else 64
-        wp = ops.new_wpack_rowstack(dev, tap_n=tap_n, with_aux=True)
-        ops.pack_conv3x3_rowstack(wt, wp, tap_n=tap_n, **kw)
+def _pack(wt, dev, **kw):
+    """Pack a 3x3 conv in the row-stacked weight layout."""
+    tap_n = 16 if wt.shape[-4] <= 16 else 64
+    wp = ops.new_wpack_rowstack(dev, tap_n=tap_n, with_aux=True)
+    ops.pack_conv3x3_rowstack(wt, wp, tap_n=tap_n, **kw)
     return wp
 
 
-@pytest.mark.parametrize("layout", [0, 1], ids=["tapmajor", "rowstack"])
+def _pack_par(wt, w1, dev, **kw):
+    """Block-launch-A pack: row-stacked 3x3 followed by the three 1x1 partition convs as 192 rows."""
+    wpp = ops.new_wpack_rowstack(dev, with_par=True)
+    ops.pack_conv3x3_rowstack(wt, wpp, **kw)
+    for j in range(3):
+        ops.pack_rows(w1[j], wpp[9 * ops.CHUNK_BYTES:], 64 * j)
+    return wpp
+
+
 @pytest.mark.parametrize("n,h,w", SHAPES)
-def test_conv_variants_match_fp32_conv2d(dev, n, h, w, layout):
+def test_conv_variants_match_fp32_conv2d(dev, n, h, w):
     g = torch.Generator(device=dev).manual_seed(n * 100000 + h * 1000 + w)
     x = bf(torch.randn((n, 64, h, w), generator=g, device=dev))
     wt = bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05)
@@ -125,49 +129,40 @@ def test_conv_variants_match_fp32_conv2d(dev, n, h, w, layout):
     scale = torch.rand(64, generator=g, device=dev) + 0.5
     xs = nhwc(x)
     ref0 = F.conv2d(x, wt, padding=1)
-    wp = _pack(wt, dev, layout)
+    wp = _pack(wt, dev)
     out = ops.new_feature(n, h, w, dev)
 
-    ops.conv3x3(xs, wp, out=out, wlayout=layout)
+    ops.conv3x3(xs, wp, out=out)
     assert_bf16_close(nchw(out), ref0, "plain")
-    ops.conv3x3(xs, wp, out=out, bias=bias, act=ops.PNP_ACT_LRELU, wlayout=layout)
+    ops.conv3x3(xs, wp, out=out, bias=bias, act=ops.PNP_ACT_LRELU)
     assert_bf16_close(nchw(out), F.leaky_relu(ref0 + bias.view(1, -1, 1, 1), 0.1), "bias+lrelu")
     idt = bf(torch.randn((n, 64, h, w), generator=g, device=dev))
-    ops.conv3x3(xs, wp, out=out, bias=bias, scale=scale, idt=nhwc(idt), act=ops.PNP_ACT_RELU, wlayout=layout)
+    ops.conv3x3(xs, wp, out=out, bias=bias, scale=scale, idt=nhwc(idt), act=ops.PNP_ACT_RELU)
     assert_bf16_close(nchw(out), F.relu(ref0 * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1) + idt),
                       "scale+bias+id+relu")
 
     # LR frame through the im2col'd aux operand == the first 3 input channels of a 131-ch conv
     lr = torch.rand((n, 3, h, w), generator=g, device=dev)
     w_in = bf(torch.randn((64, 131, 3, 3), generator=g, device=dev) * 0.05)
-    wpa = _pack(w_in, dev, layout, in_begin=3, in_count=64)
+    wpa = _pack(w_in, dev, in_begin=3, in_count=64)
     ops.pack_aux(w_in, wpa[9 * ops.CHUNK_BYTES:])
     lr64 = ops.new_feature(n, h, w, dev, zero=True)
     ops.lr_im2col(lr, lr64)
-    ops.conv3x3(xs, wpa, out=out, aux=lr64, bias=bias, act=ops.PNP_ACT_LRELU, wlayout=layout)
+    ops.conv3x3(xs, wpa, out=out, aux=lr64, bias=bias, act=ops.PNP_ACT_LRELU)
     ref = F.leaky_relu(F.conv2d(torch.cat([bf(lr), x], 1), w_in[:, :67], bias, padding=1), 0.1)
     assert_bf16_close(nchw(out), ref, "aux")
 
     # merged K slices (neighbour == key_warp): weights of two input slices summed
-    wpm = _pack(w_in, dev, layout, in_begin=3, in_begin2=67, in_count=64)
-    ops.conv3x3(xs, wpm, out=out, wlayout=layout)
+    wpm = _pack(w_in, dev, in_begin=3, in_begin2=67, in_count=64)
+    ops.conv3x3(xs, wpm, out=out)
     assert_bf16_close(nchw(out), F.conv2d(x, bf(w_in[:, 3:67] + w_in[:, 67:131]), padding=1), "merged")
 
     # 3x3 + three partition-modulated 1x1 convs, general (non one-hot) float partition map
     par = torch.rand((n, 3, h, w), generator=g, device=dev) * \
         (torch.rand((n, 3, h, w), generator=g, device=dev) > 0.5)
     w1 = [bf(torch.randn((64, 64), generator=g, device=dev) * 0.1) for _ in range(3)]
-    if layout == 0:
-        wpp = ops.new_wpack(12, dev)
-        ops.pack_conv3x3(wt, wpp, center_chunks=4)
-        for j in range(3):
-            ops.pack_rows(w1[j], wpp, 64 * (j + 1))
-    else:
-        wpp = ops.new_wpack_rowstack(dev, with_par=True)
-        ops.pack_conv3x3_rowstack(wt, wpp)
-        for j in range(3):
-            ops.pack_rows(w1[j], wpp[9 * ops.CHUNK_BYTES:], 64 * j)
-    ops.conv3x3(xs, wpp, out=out, scale=scale, bias=bias, par=par, act=ops.PNP_ACT_RELU, wlayout=layout)
+    wpp = _pack_par(wt, w1, dev)
+    ops.conv3x3(xs, wpp, out=out, scale=scale, bias=bias, par=par, act=ops.PNP_ACT_RELU)
     ref = ref0 * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
     dyres = torch.zeros_like(ref0)
     for j in range(3):
@@ -175,45 +170,35 @@ def test_conv_variants_match_fp32_conv2d(dev, n, h, w, layout):
     ref = ref + dyres
     # the row-stacked kernel parks the 1x1 blend in bf16 before adding it: one more rounding of that addend
     # (this test's partition values are O(1); the real maps are {0, 1/255}, where it is ~1e-5)
-    extra = dyres.abs() * 2.0 ** -8 if layout == 1 else None
+    extra = dyres.abs() * 2.0 ** -8
     assert_bf16_close(nchw(out), F.relu(ref), "par", extra)
-    ops.conv3x3(xs, wpp, out=out, bias=bias, par=par, act=ops.PNP_ACT_NONE, wlayout=layout)
+    ops.conv3x3(xs, wpp, out=out, bias=bias, par=par, act=ops.PNP_ACT_NONE)
     assert_bf16_close(nchw(out), ref - ref0 * scale.view(1, -1, 1, 1) + ref0, "par without scale", extra)
-    if layout == 1:      # the single-role epilogue of the row-stacked partition variant (diagnostic switch)
-        os.environ["PNP_PAR_SPLIT"] = "0"
-        try:
-            out.zero_()
-            ops.conv3x3(xs, wpp, out=out, bias=bias, par=par, act=ops.PNP_ACT_NONE, wlayout=layout)
-            torch.cuda.synchronize()
-        finally:
-            del os.environ["PNP_PAR_SPLIT"]
-        assert_bf16_close(nchw(out), ref - ref0 * scale.view(1, -1, 1, 1) + ref0, "par, single-role epilogue", extra)
 
     # reconstruction tail: 64 -> 3, + lq, fp32 NCHW output
     wl = bf(torch.randn((3, 64, 3, 3), generator=g, device=dev) * 0.05)
     bl = torch.randn(3, generator=g, device=dev) * 0.1
-    wpl = _pack(wl, dev, layout)
+    wpl = _pack(wl, dev)
     outf = torch.empty((n, 3, h, w), device=dev)
-    ops.conv3x3(xs, wpl, bias=bl, lq=lr, outf=outf, wlayout=layout)
+    ops.conv3x3(xs, wpl, bias=bl, lq=lr, outf=outf)
     assert (outf - (F.conv2d(x, wl, bl, padding=1) + lr)).abs().max().item() < 1e-4
 
 
 def test_conv_expert_mixing_matches_reference_formula(dev):
-    """pack_conv3x3 with coef == torch.mm(softmax_attention, weight) of Dynamic_conv2d_se."""
+    """pack_conv3x3_rowstack with coef == torch.mm(softmax_attention, weight) of Dynamic_conv2d_se."""
     g = torch.Generator(device=dev).manual_seed(11)
     w = torch.randn((6, 64, 64, 3, 3), generator=g, device=dev) * 0.05
     coef = torch.softmax(torch.randn(6, generator=g, device=dev), 0)
     x = bf(torch.randn((1, 64, 64, 96), generator=g, device=dev))
-    wp = ops.new_wpack(9, dev)
-    ops.pack_conv3x3(w, wp, coef=coef)
+    wp = ops.new_wpack_rowstack(dev)
+    ops.pack_conv3x3_rowstack(w, wp, coef=coef)
     out = ops.new_feature(1, 64, 96, dev)
     ops.conv3x3(nhwc(x), wp, out=out)
     mixed = torch.mm(coef.view(1, 6), w.view(6, -1)).view(64, 64, 3, 3)
     assert_bf16_close(nchw(out), F.conv2d(x, bf(mixed), padding=1), "expert mix")
 
 
-@pytest.mark.parametrize("layout", [0, 1], ids=["tapmajor", "rowstack"])
-def test_conv_full_720p_linearity_and_identity(dev, layout):
+def test_conv_full_720p_linearity_and_identity(dev):
     """Size-independent properties at the full REDS4 shape: identity kernel and linearity."""
     g = torch.Generator(device=dev).manual_seed(5)
     h, w = 720, 1280
@@ -221,18 +206,18 @@ def test_conv_full_720p_linearity_and_identity(dev, layout):
     y = nhwc(bf(torch.randn((1, 64, h, w), generator=g, device=dev)))
     eye = torch.zeros((64, 64, 3, 3), device=dev)
     eye[:, :, 1, 1] = torch.eye(64, device=dev)
-    wp = _pack(eye, dev, layout)
+    wp = _pack(eye, dev)
     out = ops.new_feature(1, h, w, dev)
-    ops.conv3x3(x, wp, out=out, wlayout=layout)
+    ops.conv3x3(x, wp, out=out)
     assert torch.equal(out, x)
     # conv(x) + y through the id operand with the identity kernel == x + y (bf16 rounded once)
-    ops.conv3x3(x, wp, out=out, idt=y, wlayout=layout)
+    ops.conv3x3(x, wp, out=out, idt=y)
     assert torch.equal(out, (x.float() + y.float()).to(torch.bfloat16))
     # shift kernel: tap (0,2) moves the image one pixel left with zero fill at the right edge
     sh = torch.zeros((64, 64, 3, 3), device=dev)
     sh[:, :, 0, 2] = torch.eye(64, device=dev)
-    wp = _pack(sh, dev, layout)
-    ops.conv3x3(x, wp, out=out, wlayout=layout)
+    wp = _pack(sh, dev)
+    ops.conv3x3(x, wp, out=out)
     exp = torch.zeros_like(x)
     exp[:, 1:, : w - 1] = x[:, : h - 1, 1:]
     assert torch.equal(out, exp)
@@ -240,7 +225,7 @@ def test_conv_full_720p_linearity_and_identity(dev, layout):
 
 def test_conv_rejects_bad_descriptors(dev):
     x = ops.new_feature(1, 64, 64, dev)
-    wp = ops.new_wpack(12, dev)
+    wp = ops.new_wpack_rowstack(dev, with_par=True)
     with pytest.raises(_lib.PnpError):
         ops.conv3x3(x, wp, out=x)                       # out aliases src
     with pytest.raises(ValueError):
@@ -276,11 +261,10 @@ def test_pack_row_scale_equals_output_gain(dev):
     gain = torch.rand(64, generator=g, device=dev) * 2.0
     x = bf(torch.randn((1, 64, 64, 128), generator=g, device=dev))
     out = ops.new_feature(1, 64, 128, dev)
-    for layout in (0, 1):
-        wp = ops.new_wpack(9, dev) if layout == 0 else ops.new_wpack_rowstack(dev)
-        (ops.pack_conv3x3 if layout == 0 else ops.pack_conv3x3_rowstack)(w, wp, row_scale=gain)
-        ops.conv3x3(nhwc(x), wp, out=out, wlayout=layout)
-        assert_bf16_close(nchw(out), F.conv2d(x, bf(w * gain.view(-1, 1, 1, 1)), padding=1), "row_scale")
+    wp = ops.new_wpack_rowstack(dev)
+    ops.pack_conv3x3_rowstack(w, wp, row_scale=gain)
+    ops.conv3x3(nhwc(x), wp, out=out)
+    assert_bf16_close(nchw(out), F.conv2d(x, bf(w * gain.view(-1, 1, 1, 1)), padding=1), "row_scale")
 
 
 @pytest.mark.parametrize("n,h,w", [(1, 68, 132), (2, 72, 200), (1, 376, 1244)])
@@ -296,8 +280,8 @@ def test_conv_rowstack_bottom_up_equals_top_down(dev, n, h, w):
     ops.pack_conv3x3_rowstack(wt, down)
     ops.pack_conv3x3_rowstack(wt, up, flip_ky=True)
     a, b = ops.new_feature(n, h, w, dev), ops.new_feature(n, h, w, dev)
-    ops.conv3x3(x, down, out=a, idt=idt, bias=bias, act=ops.PNP_ACT_LRELU, wlayout=1)
-    ops.conv3x3(x, up, out=b, idt=idt, bias=bias, act=ops.PNP_ACT_LRELU, wlayout=1, flip_y=True)
+    ops.conv3x3(x, down, out=a, idt=idt, bias=bias, act=ops.PNP_ACT_LRELU)
+    ops.conv3x3(x, up, out=b, idt=idt, bias=bias, act=ops.PNP_ACT_LRELU, flip_y=True)
     ref = F.leaky_relu(F.conv2d(nchw(x), wt, bias, padding=1) + nchw(idt), 0.1)
     assert_bf16_close(nchw(a), ref, "top-down")
     assert_bf16_close(nchw(b), ref, "bottom-up")
@@ -309,15 +293,14 @@ def test_conv_rowstack_bottom_up_equals_top_down(dev, n, h, w):
     ops.pack_conv3x3_rowstack(wl, d16, tap_n=16)
     ops.pack_conv3x3_rowstack(wl, u16, tap_n=16, flip_ky=True)
     o1, o2 = torch.empty((n, 3, h, w), device=dev), torch.empty((n, 3, h, w), device=dev)
-    ops.conv3x3(x, d16, lq=lq, outf=o1, wlayout=1)
-    ops.conv3x3(x, u16, lq=lq, outf=o2, wlayout=1, flip_y=True)
+    ops.conv3x3(x, d16, lq=lq, outf=o1)
+    ops.conv3x3(x, u16, lq=lq, outf=o2, flip_y=True)
     ref = F.conv2d(nchw(x), wl, padding=1) + lq
     assert (o1 - ref).abs().max().item() < 1e-4 and (o2 - ref).abs().max().item() < 1e-4
 
 
 # ------------------------------------------------------------------ sparse_val partition path
-@pytest.mark.parametrize("layout", [0, 1], ids=["tapmajor", "rowstack"])
-def test_conv_par_sparse_selects_last_nonzero_class(dev, layout):
+def test_conv_par_sparse_selects_last_nonzero_class(dev):
     """sparse_val eval path (sr_backbone_utils.py:294-302): W_k x / 255 of the LAST class whose map is non-zero,
     whatever the map's value; pixels with all-zero maps get nothing.  1x1 weights are large here so that the
     term is O(1) and a wrong class / a dense blend would be far outside the tolerance."""
@@ -329,18 +312,9 @@ def test_conv_par_sparse_selects_last_nonzero_class(dev, layout):
     bias = torch.randn(64, generator=g, device=dev) * 0.1
     par = (torch.rand((n, 3, h, w), generator=g, device=dev) > 0.6).float() * \
         torch.randint(1, 4, (n, 3, h, w), generator=g, device=dev).float() / 255.0
-    if layout == 0:
-        wpp = ops.new_wpack(12, dev)
-        ops.pack_conv3x3(wt, wpp, center_chunks=4)
-        for j in range(3):
-            ops.pack_rows(w1[j], wpp, 64 * (j + 1))
-    else:
-        wpp = ops.new_wpack_rowstack(dev, with_par=True)
-        ops.pack_conv3x3_rowstack(wt, wpp)
-        for j in range(3):
-            ops.pack_rows(w1[j], wpp[9 * ops.CHUNK_BYTES:], 64 * j)
+    wpp = _pack_par(wt, w1, dev)
     out = ops.new_feature(n, h, w, dev)
-    ops.conv3x3(nhwc(x), wpp, out=out, bias=bias, par=par, act=ops.PNP_ACT_NONE, wlayout=layout, par_sparse=True)
+    ops.conv3x3(nhwc(x), wpp, out=out, bias=bias, par=par, act=ops.PNP_ACT_NONE, par_sparse=True)
     dy = torch.zeros_like(x)
     for j in range(3):                                   # later classes overwrite earlier ones
         m = (par[:, j:j + 1] != 0)
@@ -348,10 +322,10 @@ def test_conv_par_sparse_selects_last_nonzero_class(dev, layout):
     dy = dy / 255
     ref = F.conv2d(x, wt, bias, padding=1) + dy
     assert dy.abs().mean().item() > 0.1                  # the term under test is not negligible
-    extra = dy.abs() * 2.0 ** -8 if layout == 1 else None
+    extra = dy.abs() * 2.0 ** -8
     assert_bf16_close(nchw(out), ref, "par_sparse", extra)
     # and it is NOT what the dense blend gives on these maps
-    ops.conv3x3(nhwc(x), wpp, out=out, bias=bias, par=par, act=ops.PNP_ACT_NONE, wlayout=layout)
+    ops.conv3x3(nhwc(x), wpp, out=out, bias=bias, par=par, act=ops.PNP_ACT_NONE)
     assert (nchw(out) - ref).abs().max().item() > 0.05
 
 
@@ -369,7 +343,7 @@ def test_pixel_shuffle_store_and_bilinear_base_epilogues(dev, n, h, w):
         wp = ops.new_wpack_rowstack(dev)
         ops.pack_conv3x3_rowstack(w_up[k::4].contiguous(), wp)
         ops.conv3x3(nhwc(x), wp, out=up[:, k >> 1::2, k & 1::2, :], bias=b_up[k::4].contiguous(),
-                    act=ops.PNP_ACT_LRELU, wlayout=1)
+                    act=ops.PNP_ACT_LRELU)
     ref = F.leaky_relu(F.pixel_shuffle(F.conv2d(x, w_up, b_up, padding=1), 2), 0.1)
     assert torch.isfinite(up.float()).all(), "pixels not covered by the four strided stores"
     assert_bf16_close(nchw(up), ref, "pixel shuffle store")
@@ -382,105 +356,131 @@ def test_pixel_shuffle_store_and_bilinear_base_epilogues(dev, n, h, w):
     wpl = ops.new_wpack_rowstack(dev, tap_n=16)
     ops.pack_conv3x3_rowstack(wl, wpl, tap_n=16)
     outf = torch.empty((n, 3, hh, ww), device=dev)
-    ops.conv3x3(nhwc(y), wpl, bias=bl, lq=lr, outf=outf, wlayout=1, lq_up4=True)
+    ops.conv3x3(nhwc(y), wpl, bias=bl, lq=lr, outf=outf, lq_up4=True)
     base = F.interpolate(lr, scale_factor=4, mode="bilinear", align_corners=False)
     assert (outf - (F.conv2d(y, wl, bl, padding=1) + base)).abs().max().item() < 1e-4
-    with pytest.raises(Exception):       # tap-major layout has no fused upsampling
-        wt = ops.new_wpack(10, dev)
-        ops.pack_conv3x3(wl, wt)
-        ops.conv3x3(nhwc(y), wt, bias=bl, lq=lr, outf=outf, wlayout=0, lq_up4=True)
 
 
-# ------------------------------------------------------------------ fused residual block (CTA pair)
-def _block_weights(dev, g):
-    wt2 = bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05)
-    wt1 = bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05)
-    w1x1 = [bf(torch.randn((64, 64), generator=g, device=dev) * 0.1) for _ in range(3)]
-    b1 = torch.randn(64, generator=g, device=dev) * 0.1
-    b2 = torch.randn(64, generator=g, device=dev) * 0.1
-    ws1 = ops.new_wpack_rowstack(dev, with_par=True)
-    ops.pack_conv3x3_rowstack(wt2, ws1)
-    for j in range(3):
-        ops.pack_rows(w1x1[j], ws1[9 * ops.CHUNK_BYTES:], 64 * j)
-    ws2 = ops.new_wpack_rowstack(dev)
-    ops.pack_conv3x3_rowstack(wt1, ws2)
-    return wt2, wt1, w1x1, b1, b2, ws1, ws2
+# ------------------------------------------------------------------ per-image weights, batched packer, table mode
+def test_pack_mix_blocks_equals_per_block_packers(dev):
+    """One launch packs the block-launch-A weights of ALL blocks for one (CRF, QP) condition: byte-identical to
+    pack_conv3x3_rowstack(coef, row_scale) + pack_rows per block."""
+    g = torch.Generator(device=dev).manual_seed(31)
+    nbk, e = 5, 6
+    w2 = torch.randn((nbk, e, 64, 64, 3, 3), generator=g, device=dev) * 0.05
+    w1 = torch.randn((nbk, 3, 64, 64), generator=g, device=dev) * 0.1
+    coef = torch.softmax(torch.randn(e, generator=g, device=dev), 0)
+    gain = torch.rand(64, generator=g, device=dev) * 2.0
+    dst = torch.zeros((nbk, ops.PACK_A_BYTES), dtype=torch.uint8, device=dev)
+    ops.pack_mix_blocks(w2, w1, coef, gain, dst)
+    for b in range(nbk):
+        ref = _pack_par(w2[b].contiguous(), [w1[b, j] for j in range(3)], dev, coef=coef, row_scale=gain)
+        assert torch.equal(dst[b], ref[:ops.PACK_A_BYTES]), f"block {b}"
 
 
-def _block_reference(x, par, wt2, wt1, w1x1, b1, b2):
-    """ResidualBlockNoBNDynamic_drt.forward with t rounded to bf16 once (as both CUDA paths do)."""
-    t = F.conv2d(x, wt2, padding=1) + b1.view(1, -1, 1, 1)
-    for j in range(3):
-        t = t + F.conv2d(x, w1x1[j].view(64, 64, 1, 1)) * par[:, j:j + 1]
-    t = bf(F.relu(t))
-    return x + F.conv2d(t, wt1, padding=1) + b2.view(1, -1, 1, 1), t
+@pytest.mark.parametrize("n,h,w", [(2, 72, 200), (5, 64, 136), (16, 180, 320)])
+def test_conv_per_image_weights_equal_separate_launches(dev, n, h, w):
+    """per_image: every image of ONE launch uses its own weights and bias (the reference's groups=batch grouped conv,
+    sr_backbone_utils.py:196-204) -- bit-identical to one launch per image."""
+    g = torch.Generator(device=dev).manual_seed(n * 7 + h)
+    x = nhwc(bf(torch.randn((n, 64, h, w), generator=g, device=dev)))
+    par = torch.rand((n, 3, h, w), generator=g, device=dev) * (torch.rand((n, 3, h, w), generator=g, device=dev) > 0.5)
+    n_cond = 3
+    packs = torch.zeros((n_cond, ops.PACK_A_BYTES), dtype=torch.uint8, device=dev)
+    biases = torch.randn((n_cond, 64), generator=g, device=dev) * 0.1
+    for c in range(n_cond):
+        wt = bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05)
+        w1 = [bf(torch.randn((64, 64), generator=g, device=dev) * 0.1) for _ in range(3)]
+        packs[c] = _pack_par(wt, w1, dev)[:ops.PACK_A_BYTES]
+    cond = [(3 * i + 1) % n_cond for i in range(n)]
+    off = torch.tensor([[c * ops.PACK_A_BYTES, c * 64] for c in cond], dtype=torch.int64, device=dev)
+    out = ops.new_feature(n, h, w, dev)
+    ops.conv3x3(x, packs, out=out, bias=biases, par=par, act=ops.PNP_ACT_RELU, img_off=off)
+    for i in range(n):
+        one = ops.new_feature(1, h, w, dev)
+        ops.conv3x3(x[i:i + 1], packs[cond[i]], out=one, bias=biases[cond[i]], par=par[i:i + 1], act=ops.PNP_ACT_RELU)
+        assert torch.equal(out[i:i + 1], one), f"image {i}"
 
 
-@pytest.mark.parametrize("n,h,w", SHAPES + [(1, 64, 126), (1, 70, 127), (3, 64, 253)])
-def test_resblock_pair_matches_fp32_reference(dev, n, h, w):
-    g = torch.Generator(device=dev).manual_seed(n * 100000 + h * 1000 + w + 1)
-    x = bf(torch.randn((n, 64, h, w), generator=g, device=dev))
-    par = torch.rand((n, 3, h, w), generator=g, device=dev) * \
-        (torch.rand((n, 3, h, w), generator=g, device=dev) > 0.5)
-    wt2, wt1, w1x1, b1, b2, ws1, ws2 = _block_weights(dev, g)
-    ref, t_ref = _block_reference(x, par, wt2, wt1, w1x1, b1, b2)
-    xs = nhwc(x)
-    out = torch.full_like(xs, float("nan"))
-    ops.resblock(xs, out, ws1, ws2, par, bias1=b1, bias2=b2)
-    torch.cuda.synchronize()
-    assert torch.isfinite(out.float()).all(), "unwritten or non-finite output pixels"
-    # t is rounded to bf16 before conv1: a one-ulp flip of t (|t| <~ 4) moves the output by <~ 2^-7 * 0.15
-    got = nchw(out)
-    tol = ref.abs() * 2.0 ** -7 + 1e-2
-    bad = (got - ref).abs() > tol
-    assert not bad.any(), f"{int(bad.sum())} of {bad.numel()} off, max {float((got - ref).abs().max())}"
-    assert (got - ref).abs().mean().item() < 2e-3
-    # and the two-launch path (pnp_conv3x3 launch A + launch B) agrees to the same degree
-    t2 = ops.new_feature(n, h, w, dev)
-    o2 = ops.new_feature(n, h, w, dev)
-    ops.conv3x3(xs, ws1, out=t2, bias=b1, par=par, act=ops.PNP_ACT_RELU, wlayout=1)
-    ops.conv3x3(t2, ws2, out=o2, idt=xs, bias=b2, wlayout=1)
-    # (the row-stacked launch A parks the 1x1 blend in bf16 before adding it -- one more rounding of an
-    # addend that is O(1) with this test's partition values, ~1e-5 with the real {0, 1/255} maps)
-    assert (nchw(o2) - got).abs().max().item() <= 0.05
-    assert (nchw(o2) - got).abs().mean().item() < 2e-3
+def test_table_mode_launches_equal_static_launches(dev):
+    """Launch-table mode (operands from a device-resident table selected by a step word) of the warp, the LR im2col and
+    the conv, eagerly and replayed from a captured graph: bit-identical to the static launches."""
+    import ctypes
+    lib = _lib.load()
+    g = torch.Generator(device=dev).manual_seed(77)
+    n, h, w, frames = 2, 72, 136, 3
+    pool = bf(torch.randn((frames * n + 3 * n, h, w, 64), generator=g, device=dev)).to(torch.bfloat16)
+    flow = (torch.randint(-32, 33, (frames, n, 2, h, w), generator=g, device=dev).float() / 4.0)
+    lr = torch.rand((frames, n, 3, h, w), generator=g, device=dev)
+    idt_f, kw_f, out_f = frames * n, frames * n + n, frames * n + 2 * n
+    wt = bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05)
+    wp = _pack(wt, dev)
+    bias = torch.randn(64, generator=g, device=dev) * 0.1
+    img = h * w * 128
+    # expected: static launches per "step" s: warp(frame s -> kw), conv(kw + idt -> out)
+    exp = []
+    for s in range(frames):
+        kw = ops.new_feature(n, h, w, dev)
+        ops.mv_warp(pool[s * n:(s + 1) * n], flow[s], kw)
+        o = ops.new_feature(n, h, w, dev)
+        ops.conv3x3(kw, wp, out=o, idt=pool[idt_f:idt_f + n], bias=bias, act=ops.PNP_ACT_LRELU)
+        aux = ops.new_feature(n, h, w, dev, zero=True)
+        ops.lr_im2col(lr[s], aux)
+        exp.append((o.clone(), aux.clone()))
+    stride = 4
+    table = torch.zeros((frames, stride, 8), dtype=torch.int64)
+    for s in range(frames):
+        table[s, 0, :4] = torch.tensor([pool.data_ptr() + s * n * img, flow[s, 0, 0].data_ptr(), flow[s, 0, 1].data_ptr(),
+                                        pool.data_ptr() + kw_f * img])
+        table[s, 1, :2] = torch.tensor([wp.data_ptr(), bias.data_ptr()])
+        table[s, 1, 6] = kw_f                    # src image | aux image << 32
+        table[s, 1, 7] = idt_f | (out_f << 32)   # idt image | out image << 32
+    table = table.to(dev)
+    step = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    def ref(node):
+        r = _lib.DynRef()
+        r.table, r.step, r.node, r.stride = table.data_ptr(), step.data_ptr(), node, stride
+        return r
 
-def test_resblock_pair_720p_identity_and_shift(dev):
-    """Full REDS4 shape, exact properties: zero weights give out == x; a pure-shift conv2 followed by a
-    pure-shift conv1 moves the (non-negative) image by two pixels with zero fill -- bit for bit."""
-    g = torch.Generator(device=dev).manual_seed(9)
-    h, w = 720, 1280
-    x = nhwc(bf(torch.rand((1, 64, h, w), generator=g, device=dev)))
-    par = torch.zeros((1, 3, h, w), device=dev)
-    zero = torch.zeros((64, 64, 3, 3), device=dev)
-    ws1, ws2 = ops.new_wpack_rowstack(dev, with_par=True), ops.new_wpack_rowstack(dev)
-    ops.pack_conv3x3_rowstack(zero, ws1)
-    ops.pack_conv3x3_rowstack(zero, ws2)
-    out = ops.new_feature(1, h, w, dev)
-    ops.resblock(x, out, ws1, ws2, par)
-    assert torch.equal(out, x)
-    sh2 = torch.zeros((64, 64, 3, 3), device=dev)
-    sh2[:, :, 0, 2] = torch.eye(64, device=dev)          # t(y,x) = x(y-1,x+1)
-    sh1 = torch.zeros((64, 64, 3, 3), device=dev)
-    sh1[:, :, 2, 0] = torch.eye(64, device=dev)          # conv1(t)(y,x) = t(y+1,x-1)
-    ops.pack_conv3x3_rowstack(sh2, ws1)
-    ops.pack_conv3x3_rowstack(sh1, ws2)
-    ops.resblock(x, out, ws1, ws2, par)
-    # t(y+1,x-1) = x(y,x) wherever t's pixel (y+1,x-1) lies inside the image, else 0
-    exp = x.float() * 2.0
-    exp[:, h - 1, :, :] = x[:, h - 1].float()
-    exp[:, :, 0, :] = x[:, :, 0].float()
-    assert torch.equal(out, exp.to(torch.bfloat16))
+    r0 = ref(0)
+    d = ops.ConvDesc()
+    d.src = d.idt = d.out = pool.data_ptr()
+    d.src_images = d.idt_images = d.out_images = pool.shape[0]
+    d.bias = 1
+    d.N, d.H, d.W, d.tap_n, d.act, d.mode, d.wpack_stable = n, h, w, 64, ops.PNP_ACT_LRELU, ops.PNP_CONV_BF16, 1
+    d.dyn = ref(1)
 
+    def sequence(st):
+        _lib.check(lib.pnp_mv_warp_dyn(ctypes.byref(r0), flow.stride(3), flow.stride(1), n, h, w, st), "warp_dyn")
+        _lib.check(lib.pnp_conv3x3(ctypes.byref(d), st), "conv dyn")
 
-def test_resblock_rejects_bad_arguments(dev):
-    x = ops.new_feature(1, 64, 64, dev)
-    ws1, ws2 = ops.new_wpack_rowstack(dev, with_par=True), ops.new_wpack_rowstack(dev)
-    par = torch.zeros((1, 3, 64, 64), device=dev)
-    with pytest.raises(_lib.PnpError):
-        ops.resblock(x, x, ws1, ws2, par)                                  # aliasing
-    with pytest.raises(ValueError):
-        ops.resblock(x, ops.new_feature(1, 64, 64, dev), ws2, ws2, par)    # stage-1 pack too small
-    with pytest.raises(ValueError):
-        ops.resblock(x, ops.new_feature(1, 64, 64, dev), ws1, ws2, par[:, :2])
+    for s in range(frames):                                              # eager table mode
+        _lib.check(lib.pnp_set_step(ctypes.c_void_p(step.data_ptr()), s, stream), "set_step")
+        sequence(stream)
+        assert torch.equal(pool[out_f:out_f + n], exp[s][0]), f"eager step {s}"
+    side = torch.cuda.Stream(device=dev)
+    cap = ctypes.c_void_p(side.cuda_stream)
+    _lib.check(lib.pnp_graph_begin(cap), "graph_begin")
+    sequence(cap)
+    handle = ctypes.c_void_p()
+    _lib.check(lib.pnp_graph_end(cap, ctypes.byref(handle)), "graph_end")
+    for s in reversed(range(frames)):                                    # graph replay, any step order
+        pool[out_f:out_f + n].zero_()
+        _lib.check(lib.pnp_graph_launch(handle, ctypes.c_void_p(step.data_ptr()), s, stream), "graph_launch")
+        assert torch.equal(pool[out_f:out_f + n], exp[s][0]), f"graph step {s}"
+    _lib.check(lib.pnp_graph_destroy(handle), "graph_destroy")
+    # LR im2col in table mode
+    t2 = torch.zeros((frames, 1, 8), dtype=torch.int64)
+    aux = ops.new_feature(n, h, w, dev, zero=True)
+    for s in range(frames):
+        t2[s, 0, 0], t2[s, 0, 1] = lr[s].data_ptr(), aux.data_ptr()
+    t2 = t2.to(dev)
+    r2 = _lib.DynRef()
+    r2.table, r2.step, r2.node, r2.stride = t2.data_ptr(), step.data_ptr(), 0, 1
+    for s in range(frames):
+        _lib.check(lib.pnp_set_step(ctypes.c_void_p(step.data_ptr()), s, stream), "set_step")
+        _lib.check(lib.pnp_lr_im2col_dyn(ctypes.byref(r2), lr.stride(1), lr.stride(2), lr.stride(3), n, h, w, stream),
+                   "im2col_dyn")
+        assert torch.equal(aux, exp[s][1]), f"im2col step {s}"

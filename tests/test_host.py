@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/pnp_vcve.h but not exported"
     assert sorted(_lib.EXPORTS) == syms
-    assert _lib.load().pnp_abi_version() == 6
+    assert _lib.load().pnp_abi_version() == 7
 
 
 def test_abi_argument_errors_without_gpu():
@@ -46,8 +46,10 @@ def test_abi_argument_errors_without_gpu():
     assert lib.pnp_conv3x3(None, None) == -1                      # PNP_ERR_ARG
     assert b"null" in lib.pnp_last_error()
     assert lib.pnp_mv_warp(None, None, None, 0, 0, None, 1, 4, 4, None, None, None) == -1
-    assert lib.pnp_set_base_offset_mode(7) == -1
-    assert lib.pnp_set_base_offset_mode(0) == 0
+    assert lib.pnp_graph_launch(None, None, 0, None) == -1
+    assert lib.pnp_set_step(None, 0, None) == -1
+    assert lib.pnp_mv_warp_dyn(None, 0, 0, 1, 4, 4, None) == -1
+    assert lib.pnp_graph_destroy(None) == 0
     if not torch.cuda.is_available():
         assert lib.pnp_device_check() != 0                         # no device: loud failure, no fallback
         with pytest.raises(_lib.PnpError):
@@ -55,14 +57,15 @@ def test_abi_argument_errors_without_gpu():
 
 
 def test_conv_desc_matches_header_layout():
+    """ctypes mirror of struct pnp_conv_desc / pnp_dyn_ref (the library static_asserts the same offsets)."""
     d = _lib.ConvDesc()
-    # 7 pointers, 3 x (pointer + 3 strides), 11 int32 (+4 pad), 3 int64 out strides, 2 int32
-    assert ctypes.sizeof(d) == 7 * 8 + 4 * 8 + 4 * 8 + 4 * 8 + 11 * 4 + 4 + 3 * 8 + 3 * 4 + 4
-    assert _lib.ConvDesc.N.offset == 152 and _lib.ConvDesc.mode.offset == 184
-    assert _lib.ConvDesc.wlayout.offset == 188 and _lib.ConvDesc.flip_y.offset == 192
-    assert _lib.ConvDesc.out_spx.offset == 200 and _lib.ConvDesc.out_sn.offset == 216
-    assert _lib.ConvDesc.lq_up4.offset == 224 and _lib.ConvDesc.par_sparse.offset == 228
-    assert _lib.ConvDesc.wpack_stable.offset == 232
+    assert ctypes.sizeof(d) == 272 and ctypes.sizeof(_lib.DynRef) == 24
+    assert _lib.ConvDesc.N.offset == 152 and _lib.ConvDesc.mode.offset == 176 and _lib.ConvDesc.flip_y.offset == 180
+    assert _lib.ConvDesc.out_spx.offset == 184 and _lib.ConvDesc.out_sn.offset == 200
+    assert _lib.ConvDesc.lq_up4.offset == 208 and _lib.ConvDesc.per_image.offset == 220
+    assert _lib.ConvDesc.img_off.offset == 224 and _lib.ConvDesc.dyn.offset == 232
+    assert _lib.ConvDesc.src_images.offset == 256 and _lib.ConvDesc.out_images.offset == 268
+    assert _lib.DYN_ENTRY_WORDS * 8 == 64
 
 
 # ------------------------------------------------------------------ registry / boundary
@@ -144,6 +147,21 @@ def test_key_schedule_equals_oracle_on_random_patterns():
             assert rows == O.keyframe_mask(sl).tolist()
             if t > 1:
                 assert engine.key_schedule(rows[0]) == O.key_schedule(rows[0])
+
+
+def test_step_variants_and_clip_grouping():
+    """Host logic of the launch-free frame loop: which of the six step graphs each frame step replays, and which
+    clips of a call share one launch sequence (same key-frame schedule; CRF / QP may differ)."""
+    key = [True, False, False, True, False, True]                   # I B B P B (last forced)
+    bwd, fwd = engine.key_schedule(key)
+    v = engine.step_variants(bwd, fwd)
+    assert v[:6] == ["b_last", "b_merged", "b_sep", "b_merged", "b_sep", "b_sep"]      # frames 5,4,3,2,1,0
+    assert v[6:] == ["f_first", "f_merged", "f_sep", "f_sep", "f_merged", "f_sep"]     # frames 0..5
+    assert engine.step_variants(*engine.key_schedule([True])) == ["b_last", "f_first"]
+    a, b, c = [True, False, True], [True, False, True], [True, True, True]
+    assert engine.group_clips([a, b, c, c, a], 16) == [(0, 2), (2, 4), (4, 5)]
+    assert engine.group_clips([a] * 5, 2) == [(0, 2), (2, 4), (4, 5)]
+    assert engine.group_clips([a, b], 16, batch=False) == [(0, 1), (1, 2)]
 
 
 def test_synthetic_clip_semantics():

@@ -1,7 +1,5 @@
 """Tiny launch sequence for `ncu` captures at the REDS4 shape (720p): per round
-   4x conv3x3_rows_kernel<1,0> (block launch A, row-stacked), 4x conv3x3_umma_kernel (launch A, tap-major
-   alternative), 4x conv3x3_rows_kernel<0,0> (block launch B:
-   + identity, bottom-up), 4x mv_warp.
+   conv3x3_rows_kernel<1,0> (block launch A), conv3x3_rows_kernel<0,0> (block launch B: + identity, bottom-up), mv_warp.
 Not a benchmark: numbers printed under a profiler are never bench values."""
 import os
 import sys
@@ -18,10 +16,6 @@ x = torch.randn((1, h, w, 64), generator=g, device=dev).to(torch.bfloat16)
 idt = torch.randn((1, h, w, 64), generator=g, device=dev).to(torch.bfloat16)
 t = ops.new_feature(1, h, w, dev)
 out = ops.new_feature(1, h, w, dev)
-wa = ops.new_wpack(12, dev)
-ops.pack_conv3x3(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05, wa, center_chunks=4)
-for j in range(3):
-    ops.pack_rows(torch.randn((64, 64), generator=g, device=dev) * 0.1, wa, 64 * (j + 1))
 war = ops.new_wpack_rowstack(dev, with_par=True)          # launch A, row-stacked layout (the engine's default)
 ops.pack_conv3x3_rowstack(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05, war)
 for j in range(3):
@@ -35,9 +29,8 @@ flow = (torch.randint(-64, 65, (2, (h + 7) // 8, (w + 7) // 8), generator=g, dev
         ).repeat_interleave(8, 1).repeat_interleave(8, 2)[:, :h, :w].contiguous()
 torch.cuda.synchronize()
 for _ in range(4):
-    ops.conv3x3(x, war, out=t, bias=bias, par=par, act=ops.PNP_ACT_RELU, wlayout=1)  # block launch A (row-stacked)
-    ops.conv3x3(x, wa, out=t, bias=bias, par=par, act=ops.PNP_ACT_RELU)            # block launch A (tap-major, PNP_ROWS_PAR=0)
-    ops.conv3x3(t, wb, out=out, idt=x, bias=bias, wlayout=1, flip_y=True)           # block launch B
+    ops.conv3x3(x, war, out=t, bias=bias, par=par, act=ops.PNP_ACT_RELU)  # block launch A (row-stacked)
+    ops.conv3x3(t, wb, out=out, idt=x, bias=bias, flip_y=True)           # block launch B
     ops.mv_warp(x, flow, out)
 torch.cuda.synchronize()
 print("done")

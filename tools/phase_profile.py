@@ -9,7 +9,7 @@ from pnpvcve_b200 import synthetic, weights
 dev = torch.device("cuda:0")
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 net = P.build_backbone(bench.GEN_CFG); net.load_state_dict(weights.random_state_dict(0), strict=True); net = net.to(dev).eval()
-clip = bench.make_device_clip(T, 2000, 25, dev)
+clip = bench.make_device_batch(bench.CONFIGS["C2"], T, 1, 2000, 1, dev)
 args = synthetic.generator_args(clip)
 with torch.no_grad():
     for _ in range(2): net(*args)
