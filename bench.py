@@ -497,8 +497,8 @@ def main():
         pinned host memory and all of its frames back inside the timed region."""
         ticket = streamer.upload(host[0])
         for i in range(n_steps):
-            nxt = streamer.upload(host[0]) if i + 1 < n_steps else None
             out = streamer.run(ticket, out_host)
+            nxt = streamer.upload(host[0]) if i + 1 < n_steps else None      # overlaps the kernels just enqueued
             local = driver.frame_metrics(out)
             driver.gather_metrics(local.mean(0, keepdim=True), world, rank, world)
             ticket = nxt

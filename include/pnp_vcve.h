@@ -35,6 +35,12 @@ typedef enum pnp_status {
 int pnp_abi_version(void);
 const char* pnp_last_error(void);          /* message of the last failing call in this thread */
 int pnp_device_check(void);                /* PNP_OK iff the current device is sm_100 */
+int pnp_set_pair_mode(int mode);           /* conv kernel form for later pnp_conv3x3 calls of this process: 0 single CTA,
+                                              1 CTA pairs (tcgen05 cta_group::2) where the shape pairs up without waste,
+                                              2 also with a phantom column, -1 follow the PNP_PAIR environment variable
+                                              (default 0).  Same results either way.  Returns the previous setting. */
+int pnp_device_pairs(void);                /* CTA pairs (clusters of two) the conv kernel's cta_group::2 form can keep
+                                              resident on the current device; < 0: error code */
 
 /*
  * Launch tables and CUDA graphs -- the launch-free frame loop.
@@ -74,6 +80,10 @@ int pnp_graph_end(void* stream, void** graph_exec);
 int pnp_graph_launch(void* graph_exec, int32_t* step_word, int32_t step_value, void* stream);
 int pnp_graph_destroy(void* graph_exec);
 int pnp_set_step(int32_t* step_word, int32_t step_value, void* stream);
+/* Stream-ordered copy of `bytes` (multiple of 16) from PAGE-LOCKED host memory into device memory by a kernel that
+ * reads the host buffer over the bus -- for the launch table: a cudaMemcpyAsync would queue on the H2D copy engine
+ * behind a clip that is being streamed in and hold back the first frame step for its whole upload. */
+int pnp_fetch_pinned(void* dst, const void* src_pinned, int64_t bytes, void* stream);
 
 /*
  * K1 -- MV-guided bilinear warp of a 64-channel feature map.

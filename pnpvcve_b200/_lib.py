@@ -16,8 +16,8 @@ PNP_ACT_NONE, PNP_ACT_LRELU, PNP_ACT_RELU = 0, 1, 2
 
 #: every symbol include/pnp_vcve.h declares
 EXPORTS = [
-    "pnp_abi_version", "pnp_last_error", "pnp_device_check",
-    "pnp_graph_begin", "pnp_graph_end", "pnp_graph_launch", "pnp_graph_destroy", "pnp_set_step",
+    "pnp_abi_version", "pnp_last_error", "pnp_device_check", "pnp_device_pairs", "pnp_set_pair_mode",
+    "pnp_graph_begin", "pnp_graph_end", "pnp_graph_launch", "pnp_graph_destroy", "pnp_set_step", "pnp_fetch_pinned",
     "pnp_mv_warp", "pnp_mv_warp_dyn", "pnp_lr_im2col", "pnp_lr_im2col_dyn", "pnp_pack_conv3x3_rowstack",
     "pnp_pack_rows", "pnp_pack_aux", "pnp_pack_mix_blocks",
     "pnp_caa_heads", "pnp_mix_bias", "pnp_mv_rasterize", "pnp_conv3x3", "pnp_frame_quality",
@@ -59,11 +59,14 @@ _PROTOS = {
     "pnp_abi_version": (_i, []),
     "pnp_last_error": (_c.c_char_p, []),
     "pnp_device_check": (_i, []),
+    "pnp_device_pairs": (_i, []),
+    "pnp_set_pair_mode": (_i, [_i]),
     "pnp_graph_begin": (_i, [_vp]),
     "pnp_graph_end": (_i, [_vp, _c.POINTER(_vp)]),
     "pnp_graph_launch": (_i, [_vp, _vp, _c.c_int32, _vp]),
     "pnp_graph_destroy": (_i, [_vp]),
     "pnp_set_step": (_i, [_vp, _c.c_int32, _vp]),
+    "pnp_fetch_pinned": (_i, [_vp, _vp, _i64, _vp]),
     "pnp_mv_warp_dyn": (_i, [_c.POINTER(DynRef), _i64, _i64, _i, _i, _i, _vp]),
     "pnp_lr_im2col_dyn": (_i, [_c.POINTER(DynRef), _i64, _i64, _i64, _i, _i, _i, _vp]),
     "pnp_pack_mix_blocks": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i64, _vp]),

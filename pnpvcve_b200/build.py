@@ -27,6 +27,8 @@ def build(force=False, verbose=False):
     flags = list(NVCC_FLAGS)
     if os.environ.get("PNP_DIAG", "0") != "0":     # diagnostics build for tools/ (what-if bits, clock traces)
         flags.append("-DPNP_DIAG")
+    if os.environ.get("PNP_SPIN_LIMIT"):           # stress runs: trap a stuck pipeline after fewer polls
+        flags.append("-DPNP_SPIN_LIMIT=" + os.environ["PNP_SPIN_LIMIT"])
     cmd = [nvcc] + flags + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:

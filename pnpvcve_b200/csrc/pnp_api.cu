@@ -15,6 +15,7 @@
 namespace {
 
 thread_local char g_err[512] = "";
+int g_pair_override = -1;      // pnp_set_pair_mode(): -1 = follow PNP_PAIR
 
 static_assert(sizeof(pnp_dyn_entry) == sizeof(pnp::DynEntry), "launch-table entry layout");
 
@@ -31,6 +32,7 @@ int cuda_fail(cudaError_t e, const char* where) {
 struct DeviceInfo {
   bool ok = false;
   int sms = 0;
+  int max_pairs = 0;       // CTA pairs (clusters of 2) of the pair conv variants that can be resident at once
   cudaError_t err = cudaSuccess;
 };
 
@@ -50,7 +52,7 @@ int device_info(DeviceInfo** out) {
     if (e2 == cudaSuccess) {
       g_dev[dev].ok = (prop.major == 10);
       g_dev[dev].sms = prop.multiProcessorCount;
-      if (g_dev[dev].ok) e2 = pnp::conv_rows_prepare();
+      if (g_dev[dev].ok) e2 = pnp::conv_rows_prepare(&g_dev[dev].max_pairs);
     }
     g_dev[dev].err = e2;
   });
@@ -66,6 +68,9 @@ int device_info(DeviceInfo** out) {
 struct Knobs {
   int l2_hints = 0;        // PNP_L2_HINTS=1: evict_first on launch B's dead reads (measured: no effect)
   int par_split = 1;       // PNP_PAR_SPLIT=0: single-role epilogue of block launch A
+  int pair = 0;            // PNP_PAIR=1: CTA-pair (cta_group::2) form of the conv kernel where the shape allows it; 2: also
+                           // with a phantom column.  Off by default: measured level in cycles and 3-5 % slower in time
+                           // under the power cap (profiles/r02_notes.md); pnp_set_pair_mode() overrides at run time
   int rings_nio = 0, rings_sa = 0;   // PNP_RINGS="<n_io>,<s_a>": shared-memory split override
   int debug_skip = 0;      // PNP_DIAG only
   long long* trace = nullptr;   // PNP_DIAG only
@@ -76,6 +81,7 @@ const Knobs& knobs() {
     Knobs v;
     if (const char* e = getenv("PNP_L2_HINTS")) v.l2_hints = atoi(e) != 0;
     if (const char* e = getenv("PNP_PAR_SPLIT")) v.par_split = atoi(e) != 0;
+    if (const char* e = getenv("PNP_PAIR")) v.pair = atoi(e);
     if (const char* e = getenv("PNP_RINGS")) {
       if (sscanf(e, "%d,%d", &v.rings_nio, &v.rings_sa) != 2) v.rings_nio = v.rings_sa = 0;
     }
@@ -183,6 +189,18 @@ int pnp_device_check(void) {
   return device_info(&d);
 }
 
+int pnp_device_pairs(void) {
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  return rc ? rc : d->max_pairs;
+}
+
+int pnp_set_pair_mode(int mode) {
+  const int prev = g_pair_override;
+  g_pair_override = mode < 0 ? -1 : (mode > 2 ? 2 : mode);
+  return prev;
+}
+
 int pnp_graph_begin(void* stream) {
   DeviceInfo* d;
   int rc = device_info(&d);
@@ -228,6 +246,22 @@ int pnp_graph_destroy(void* graph_exec) {
 int pnp_set_step(int32_t* step_word, int32_t step_value, void* stream) {
   if (!step_word) return fail(PNP_ERR_ARG, "pnp_set_step: null step word");
   return store_step(step_word, step_value, static_cast<cudaStream_t>(stream));
+}
+
+int pnp_fetch_pinned(void* dst, const void* src_pinned, int64_t bytes, void* stream) {
+  if (!dst || !src_pinned) return fail(PNP_ERR_ARG, "pnp_fetch_pinned: null pointer");
+  if (bytes < 0 || (bytes & 15) || !aligned16(dst) || !aligned16(src_pinned))
+    return fail(PNP_ERR_ARG, "pnp_fetch_pinned: size and pointers must be multiples of 16 bytes");
+  DeviceInfo* d;
+  int rc = device_info(&d);
+  if (rc) return rc;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, src_pinned);
+  if (e != cudaSuccess) return cuda_fail(e, "pnp_fetch_pinned");
+  if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr)
+    return fail(PNP_ERR_ARG, "pnp_fetch_pinned: src must be page-locked host memory the device can address");
+  e = pnp::launch_fetch_pinned(at.devicePointer, dst, bytes, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_fetch_pinned");
 }
 
 int pnp_mv_warp(const void* src, const float* flow_x, const float* flow_y, int64_t flow_row_stride,
@@ -470,8 +504,36 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   const long long tiles = (long long)c->N * p.strips * c->H;
   if (tiles > 0x7fffffffLL) return fail(PNP_ERR_ARG, "pnp_conv3x3: too many tiles");
   p.tiles_total = (int)tiles;
+  // CTA-pair form (cluster of 2, tcgen05 cta_group::2, see pnp_conv_rows.cu): the two CTAs of a pair walk the same rows
+  // of two adjacent (image, strip) columns, so columns are paired up; an odd column count leaves one phantom column
+  // (taken only when that wastes < 7 %), and with per-image weights both columns of a pair must belong to one image.
+  const long long cols = (long long)c->N * p.strips;
+  const int pair_mode = g_pair_override >= 0 ? g_pair_override : kn.pair;
+  const bool pair_ok = pair_mode != 0 && !last && c->tap_n == 64 && d->max_pairs >= 8 && (!par || kn.par_split) &&
+                       (c->per_image ? (p.strips % 2 == 0 && c->N <= d->max_pairs)
+                                     : (cols % 2 == 0 || cols >= 15 || pair_mode == 2));
   int grid;
-  if (c->per_image) {
+  if (pair_ok) {
+    p.pair = 1;
+    const int max_pairs = d->max_pairs < d->sms / 2 ? d->max_pairs : d->sms / 2;
+    if (c->per_image) {
+      const int tiles_img = (p.strips / 2) * c->H;
+      int cpi = max_pairs / c->N;
+      if (cpi > tiles_img) cpi = tiles_img;
+      p.tiles_per_cta = (tiles_img + cpi - 1) / cpi;
+      cpi = (tiles_img + p.tiles_per_cta - 1) / p.tiles_per_cta;
+      p.cpi = cpi;
+      p.tiles_total = tiles_img * c->N;
+      grid = 2 * cpi * c->N;
+    } else {
+      const long long pair_tiles = ((cols + 1) / 2) * c->H;
+      p.tiles_total = (int)pair_tiles;
+      int clusters = max_pairs < pair_tiles ? max_pairs : (int)pair_tiles;
+      p.tiles_per_cta = (p.tiles_total + clusters - 1) / clusters;
+      clusters = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
+      grid = 2 * clusters;
+    }
+  } else if (c->per_image) {
     // CTAs are partitioned by image so that each can hold its image's weights: cpi CTAs walk one image
     const int tiles_img = p.strips * c->H;
     int cpi = d->sms / c->N;
@@ -503,8 +565,9 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   // With an identity operand the staging ring also prefetches identity tiles (n_io - 2 tiles ahead),
   // so it gets 4 slots as long as 5 source rows (3 in use + 2 in flight) still fit.
   const long long budget = 232448 - 2048;
-  const long long w_bytes = ((long long)9 * c->tap_n * 128 + (c->aux ? pnp::kWChunkBytes : 0) +
-                             (par ? 3 * 64 * 128 : 0) + 1023) & ~1023LL;
+  // (pair mode: a CTA holds half of the aux / 1x1 block, and the 3x3 weights as two half-sized layouts)
+  const long long w_bytes = ((long long)9 * c->tap_n * 128 + (c->aux ? pnp::kWChunkBytes : 0) / (p.pair ? 2 : 1) +
+                             (par ? 3 * 64 * 128 : 0) / (p.pair ? 2 : 1) + 1023) & ~1023LL;
   auto fixed_bytes = [&](int n_io) {
     return w_bytes + (c->aux ? 2 * pnp::kTileBytes : 0) + (long long)n_io * pnp::kTileBytes;
   };

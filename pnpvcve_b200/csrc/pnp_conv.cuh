@@ -71,6 +71,9 @@ struct ConvParams {
   int par_sparse;       // partition blend: last non-zero class only, / 255 (the reference's sparse_val eval path)
   int lq_up4;           // kModeLast: lq is the (H/4, W/4) frame, the epilogue adds its x4 bilinear upsampling
   int w_stable;         // weights may be fetched before the previous kernel in the stream has completed
+  int pair;             // CTA-pair mode (cluster of 2, tcgen05 cta_group::2): a "tile" below is a PAIR of 128-pixel tiles,
+                        // the same row of two adjacent (image, strip) columns; tiles_total / tiles_per_cta / cpi then
+                        // count pair-tiles per cluster
   int s_a;              // A ring slots
   int n_io;             // id/out staging slots
   long long* trace;     // PNP_DIAG builds: device buffer for per-tile clock64 stamps of CTA 0
@@ -92,7 +95,10 @@ __device__ __forceinline__ void par_sparse_select(float& p0, float& p1, float& p
 
 // weights packed as [dx][dy sub-block][tap_n rows] (pnp_pack_conv3x3_rowstack)
 size_t conv_rows_smem_bytes(const ConvParams& p);
-cudaError_t conv_rows_prepare();     // opt every kernel variant in to 227 KB of shared memory on the current device
+// opt every kernel variant in to 227 KB of shared memory on the current device; max_pairs = CTA pairs (clusters of 2)
+// of the pair variants that can be resident at once
+cudaError_t conv_rows_prepare(int* max_pairs);
+// grid = CTAs (p.pair: 2 x clusters)
 cudaError_t launch_conv_rows(const ConvParams& p, int grid, cudaStream_t stream);
 
 }  // namespace pnp

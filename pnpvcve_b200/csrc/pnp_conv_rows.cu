@@ -15,6 +15,16 @@
 // partition-modulated 1x1 convs are one extra N=192 MMA group on the centre row into a dedicated
 // 192-column TMEM region; the epilogue folds sum_k par_k * conv1x1_k(x) into registers one step
 // ahead of the 3x3 result (accumulator ring shrinks to 5 x 64 columns to make room).
+//
+// kPair (round 2): the same kernel as a CLUSTER OF TWO CTAs issuing tcgen05.mma.cta_group::2 (M = 256).  The two CTAs
+// walk the same rows of two adjacent (image, strip) columns in lockstep; every MMA multiplies both CTAs' source rows
+// with ONE weight block of which each CTA holds (and fetches from its shared memory) only half of the rows: 56 instead
+// of 80 shared-memory cycles per N=192 MMA -- the measured bound of this kernel is the 128 B/clk shared-memory pipe.
+// Only the leader (cluster rank 0) runs the MMA issuer and the scout; its "full"/"free" barriers collect the TMA
+// completions and the epilogue arrivals of both CTAs, commits are multicast to both.  Accumulator windows that wrap
+// the TMEM ring (or are clipped at a segment end) cannot be issued as partial-N MMAs out of an N-split weight block,
+// so they run as per-sub-block N=64 MMAs out of a second, per-sub-block-split copy of the weights, chained through the
+// A-operand collector (fill/use/lastuse: the A tile is fetched once; tools/umma_collect_bench.cu).
 #include <type_traits>
 
 #include "pnp_conv.cuh"
@@ -69,6 +79,7 @@ struct RowsMisc {
   uint32_t go_par;                 // epilogue -> MMA: epilogue-warp reads of the partition region (8 or 4 per row)
   uint32_t slot_free;              // split roles: output rows whose TMA stores have finished reading their staging slot
   uint64_t dy_full[kMaxIoSlots];   // split roles: region readers -> main epilogue: the row's 1x1 blend is parked
+  uint64_t peer_w;                 // pair mode, leader: the other CTA's weights have landed
 };
 static_assert(sizeof(RowsMisc) <= 1024, "misc region overflow");
 
@@ -79,10 +90,13 @@ struct Segment {
 };
 
 struct SegIter {
-  int t, t_end, H, strips, n, strip, y_b;
-  __device__ SegIter(const ConvParams& p, int b, int e) : t(b), t_end(e), H(p.H), strips(p.strips) {
-    const int col = b / p.H;
+  int t, t_end, H, strips, n, strip, y_b, dcol;
+  // rank: this CTA's position in its pair (pair mode: tiles count column PAIRS, the CTA walks column 2*pair + rank)
+  __device__ SegIter(const ConvParams& p, int b, int e, int rank = 0) : t(b), t_end(e), H(p.H), strips(p.strips) {
+    int col = b / p.H;
     y_b = b - col * p.H;
+    dcol = p.pair ? 2 : 1;
+    if (p.pair) col = 2 * col + rank;
     n = col / p.strips;
     strip = col - n * p.strips;
   }
@@ -100,8 +114,9 @@ struct SegIter {
   __device__ __forceinline__ void next(const Segment& s) {
     t += s.len;
     y_b = 0;
-    if (++strip == strips) {
-      strip = 0;
+    strip += dcol;
+    while (strip >= strips) {
+      strip -= strips;
       ++n;
     }
   }
@@ -126,17 +141,22 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 
 }  // namespace
 
-template <bool kPar, bool kScale>
+template <bool kPar, bool kScale, bool kPair>
 __global__ void __launch_bounds__(kRowsThreads, 1)
 conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
   constexpr int kAccRing = kPar ? 5 : 8;
+  const int rank = kPair ? (int)cluster_ctarank() : 0;        // position in the CTA pair; 0 = leader
+  const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tile ranges are per CTA / per pair
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - raw);
   const int tap_n = p.tap_n;                            // 64, or 16 for the 64->3 tail
   const int dx_block_bytes = 3 * tap_n * 128;           // [3 dy sub-blocks][tap_n rows][128 B]
-  const int w_bytes = 3 * dx_block_bytes + (p.aux_k16 > 0 ? kWChunkBytes : 0) + (kPar ? 3 * 64 * 128 : 0);
+  // bytes of weights resident in THIS CTA.  Pair mode: half of the rows of every block, twice (N-split layout for
+  // whole N = 3*tap_n windows, per-sub-block-split layout for the N = tap_n MMAs of wrapped / clipped windows)
+  const int w_bytes = kPair ? 3 * dx_block_bytes + (p.aux_k16 > 0 ? kWChunkBytes / 2 : 0) + (kPar ? 3 * 64 * 128 / 2 : 0)
+                            : 3 * dx_block_bytes + (p.aux_k16 > 0 ? kWChunkBytes : 0) + (kPar ? 3 * 64 * 128 : 0);
   const RowsLayout L = rows_layout(w_bytes, p.s_a, p.aux_k16 > 0, p.n_io);
   RowsMisc* misc = reinterpret_cast<RowsMisc*>(sgen + L.misc);
 
@@ -147,12 +167,12 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
   // sr_backbone_utils.py:196-204).
   int t_begin, t_end, img = 0;
   if (p.cpi > 0) {
-    img = blockIdx.x / p.cpi;
-    const int tiles_img = p.strips * p.H;
-    t_begin = img * tiles_img + (blockIdx.x - img * p.cpi) * p.tiles_per_cta;
+    img = unit / p.cpi;
+    const int tiles_img = (kPair ? p.strips >> 1 : p.strips) * p.H;     // pair mode: strips is even here
+    t_begin = img * tiles_img + (unit - img * p.cpi) * p.tiles_per_cta;
     t_end = min((img + 1) * tiles_img, t_begin + p.tiles_per_cta);
   } else {
-    t_begin = blockIdx.x * p.tiles_per_cta;
+    t_begin = unit * p.tiles_per_cta;
     t_end = min(p.tiles_total, t_begin + p.tiles_per_cta);
   }
   // Operands that change per frame step come from the launch table in table mode (constant kernel parameters
@@ -187,8 +207,10 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       mbar_init(smem_u32(&misc->w_full), 1);
       for (int i = 0; i < kMaxASlots; ++i) mbar_init(smem_u32(&misc->a_full[i]), 1);
       for (int i = 0; i < kStepRing; ++i) mbar_init(smem_u32(&misc->step_done[i]), 1);
-      const int acc_readers = (kPar && p.par_split) ? 4 : kEpilogueWarps;
+      // pair mode: the leader's acc_free barriers collect the reader warps of both CTAs
+      const int acc_readers = ((kPar && p.par_split) ? 4 : kEpilogueWarps) * (kPair ? 2 : 1);
       for (int i = 0; i < kAccRingMax; ++i) mbar_init(smem_u32(&misc->acc_free[i]), acc_readers);
+      mbar_init(smem_u32(&misc->peer_w), 1);
       for (int i = 0; i < kMaxIoSlots; ++i) mbar_init(smem_u32(&misc->dy_full[i]), 4);
       misc->slot_free = 0;
       mbar_init(smem_u32(&misc->par_done), 1);
@@ -204,10 +226,12 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       if (!last_mode) tma_prefetch_desc(&p.tm_out);
     }
     __syncwarp();
-    tmem_alloc(smem_u32(&misc->tmem_base), kTmemCols);
+    if (kPair) tmem_alloc2(smem_u32(&misc->tmem_base), kTmemCols);
+    else tmem_alloc(smem_u32(&misc->tmem_base), kTmemCols);
   }
   tc_fence_before();
-  __syncthreads();
+  // pair mode: the peer's barriers must be initialised before the first remote arrival / TMA completion reaches them
+  if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = misc->tmem_base;
   // Programmatic dependent launch: launch latency, block scheduling and the prologue above overlap
@@ -218,9 +242,25 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
   auto load_weights = [&]() {                 // one elected lane of warp 0
     const uint32_t wbar = smem_u32(&misc->w_full);
     mbar_arrive_expect_tx(wbar, w_bytes);
-    for (int off = 0; off < w_bytes; off += kWChunkBytes) {
-      const int n = min(kWChunkBytes, w_bytes - off);
-      bulk_load_1d(w_smem_early + off, wpack + off, n, wbar);
+    if (kPair) {
+      // This CTA's halves, straight out of the ordinary pack [dx][dy sub-block][tap_n rows][128 B] (row counts are
+      // multiples of 8, so the pre-applied 128B swizzle stays valid at the new 1024-aligned offsets):
+      //   [0, 3*h192): per dx the rows [rank*3*tap_n/2, +3*tap_n/2) of the stacked block   (whole-window MMAs)
+      //   then per (dx, sub-block) the rows [rank*tap_n/2, +tap_n/2) of the sub-block      (per-sub-block MMAs)
+      //   then this CTA's half of the LR-im2col block (aux, N = 64) or of the stacked 1x1 block (kPar, N = 192)
+      const int h192 = dx_block_bytes >> 1, h64 = (tap_n * 128) >> 1;
+      for (int dx = 0; dx < 3; ++dx)
+        bulk_load_1d(w_smem_early + dx * h192, wpack + dx * dx_block_bytes + rank * h192, h192, wbar);
+      for (int b = 0; b < 9; ++b)
+        bulk_load_1d(w_smem_early + 3 * h192 + b * h64, wpack + b * (tap_n * 128) + rank * h64, h64, wbar);
+      const int extra = w_bytes - 3 * dx_block_bytes;
+      if (extra > 0)
+        bulk_load_1d(w_smem_early + 3 * dx_block_bytes, wpack + 3 * dx_block_bytes + rank * extra, extra, wbar);
+    } else {
+      for (int off = 0; off < w_bytes; off += kWChunkBytes) {
+        const int n = min(kWChunkBytes, w_bytes - off);
+        bulk_load_1d(w_smem_early + off, wpack + off, n, wbar);
+      }
     }
   };
   // stable weights (packed long before this launch) are fetched while the previous kernel drains
@@ -258,7 +298,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       Ring ar(s_a);
       uint32_t sc = 0, ord = 0;            // step counter, output-row ordinal
       uint32_t aux_step[2] = {0, 0};       // step in which each aux slot was last consumed
-      for (SegIter it(p, t_begin, t_end); it.valid();) {
+      for (SegIter it(p, t_begin, t_end, rank); it.valid();) {
         const Segment s = it.get();
         const int x0 = s.strip * kTilePx;
         for (int j = s.j_first; j <= s.j_last; ++j, ++sc, ar.advance()) {
@@ -268,7 +308,13 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
             pwait(smem_u32(&misc->step_done[ps & (kStepRing - 1)]), (ps >> 3) & 1, 1);
           }
           const uint32_t fb = smem_u32(&misc->a_full[ar.slot]);
-          if (PNP_DBG(1) && sc >= (uint32_t)s_a) {
+          if (kPair) {
+            // both CTAs' rows complete on the LEADER's barrier, which expects the bytes of the two loads (a
+            // completion that overtakes the leader's expect_tx only drives the pending count negative for a while)
+            if (rank == 0) mbar_arrive_expect_tx(fb, 2 * kRowBytes);
+            tma_load_4d_pair(a_smem + ar.slot * kASlotBytes, &p.tm_src, mapa_shared(fb, 0), 0, x0 - 1, PNP_Y(s.y_b + j),
+                             s.n + src_f);
+          } else if (PNP_DBG(1) && sc >= (uint32_t)s_a) {
             mbar_arrive(fb);
           } else {
             mbar_arrive_expect_tx(fb, kRowBytes);
@@ -286,8 +332,14 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
               }
               aux_step[as] = sc;           // consumed in this very step (centre row)
               const uint32_t ab = smem_u32(&misc->aux_full[as]);
-              mbar_arrive_expect_tx(ab, kTileBytes);
-              tma_load_4d(aux_smem + as * kTileBytes, &p.tm_aux, ab, 0, x0, PNP_Y(s.y_b + j), s.n + aux_f);
+              if (kPair) {
+                if (rank == 0) mbar_arrive_expect_tx(ab, 2 * kTileBytes);
+                tma_load_4d_pair(aux_smem + as * kTileBytes, &p.tm_aux, mapa_shared(ab, 0), 0, x0, PNP_Y(s.y_b + j),
+                                 s.n + aux_f);
+              } else {
+                mbar_arrive_expect_tx(ab, kTileBytes);
+                tma_load_4d(aux_smem + as * kTileBytes, &p.tm_aux, ab, 0, x0, PNP_Y(s.y_b + j), s.n + aux_f);
+              }
             }
             ++ord;
           }
@@ -296,16 +348,24 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer (one elected lane)
-    if (elect_one()) {
-      const uint32_t idesc0 = umma_idesc_bf16(128, 0);                  // N field added per MMA
+    // ============================================================ MMA issuer (one elected lane; pair mode: leader only)
+    if (kPair && rank != 0) {
+      if (elect_one()) {      // the leader's MMAs read this CTA's weight halves as well: report them landed
+        mbar_wait(smem_u32(&misc->w_full), 0, 4);
+        mbar_arrive_cluster(mapa_shared(smem_u32(&misc->peer_w), 0));
+      }
+    } else if (elect_one()) {
+      const uint32_t idesc0 = umma_idesc_bf16(kPair ? 256 : 128, 0);    // N field added per MMA
       const uint32_t idesc_step = ((uint32_t)tap_n >> 3) << 17;         // one dy sub-block of N
       const uint32_t w_lo = umma_desc_lo(w_smem);
       const uint32_t dxb = (uint32_t)dx_block_bytes >> 4;      // descriptor units per dx block
       const uint32_t sbb = (uint32_t)(tap_n * 128) >> 4;       // ... per dy sub-block
       const uint32_t aux_w_lo = w_lo + 3 * dxb;                 // LR im2col block (aux) ...
       const uint32_t par_w_lo = w_lo + 3 * dxb;                 // ... or the stacked 1x1 block (kPar)
+      // pair mode: this CTA's halves -- N-split dx blocks at w_lo, per-sub-block-split blocks behind them
+      const uint32_t u192 = dxb >> 1, u64 = sbb >> 1, w64_lo = w_lo + 3 * (dxb >> 1);
       mbar_wait(smem_u32(&misc->w_full), 0, 4);
+      if (kPair) mbar_wait(smem_u32(&misc->peer_w), 0, 14);
       // One step = one in-image source row.  `StepCtx` carries everything the issue code needs, so
       // the barriers of step s+1 can be checked in the MIDDLE of step s: an already-complete
       // mbarrier wait costs ~200 cycles and the tensor pipe only rides out ~300 cycles of silence
@@ -315,7 +375,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         int j, len, j_first;
         uint32_t ord0, sc, a_slot, a_phase;
       };
-      SegIter seg_it(p, t_begin, t_end);
+      SegIter seg_it(p, t_begin, t_end, rank);
       Segment seg = seg_it.valid() ? seg_it.get() : Segment{0, 0, 0, 0, 0, -1};
       Ring ar(s_a);
       StepCtx cur{seg_it.valid(), seg.j_first, seg.len, seg.j_first, 0u, 0u, ar.slot, ar.phase};
@@ -349,6 +409,9 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       const uint32_t go_step = smem_u32(&misc->go_step), go_par = smem_u32(&misc->go_par);
       bool pend = false;
       uint32_t pend_bar = 0;
+      auto commit = [&](uint32_t bar) {
+        if (kPair) umma2_commit(bar); else umma_commit(bar);
+      };
 
       // MMAs of one (dx,k) over `cnt` consecutive accumulator slots starting at slot_lo.  kWrap: the
       // range may run over the end of the ring and is issued as two MMAs.  The two cases are separate
@@ -371,14 +434,29 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       bool ppend = false;
       uint32_t pp_arow = 0, pp_od = 0;
       auto issue_par = [&](uint32_t a_row_, uint32_t od) {
-        // every reader warp has pulled row od-1's region into registers
-        spin_until_ge(go_par, (p.par_split ? 4u : (uint32_t)kEpilogueWarps) * od, 10);
+        // every reader warp (of both CTAs in pair mode) has pulled row od-1's region into registers
+        const uint32_t readers = (p.par_split ? 4u : (uint32_t)kEpilogueWarps) * (kPair ? 2u : 1u);
+        if (kPair) {
+          uint32_t spins = 0;
+          while (ld_volatile_shared(go_par) < readers * od) {
+            if (++spins > PNP_SPIN_LIMIT) {
+              printf("pnp: flag wait timed out (tag 10, block %d, target %u)\n", (int)blockIdx.x, readers * od);
+              __trap();
+            }
+          }
+        } else {
+          spin_until_ge(go_par, readers * od, 10);
+        }
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_lo(tmem_base + kParCol, a_row_ + 8 + 2 * k, kDescHiSw128, par_w_lo + 2 * k, kDescHiSw128,
-                       idesc0 + 3 * idesc_step, k > 0);
-        umma_commit(smem_u32(&misc->par_done));
+        for (int k = 0; k < 4; ++k) {
+          if (kPair)
+            umma2_bf16_lo<0>(tmem_base + kParCol, a_row_ + 8 + 2 * k, par_w_lo + 2 * k, idesc0 + 3 * idesc_step, k > 0);
+          else
+            umma_bf16_lo(tmem_base + kParCol, a_row_ + 8 + 2 * k, kDescHiSw128, par_w_lo + 2 * k, kDescHiSw128,
+                         idesc0 + 3 * idesc_step, k > 0);
+        }
+        commit(smem_u32(&misc->par_done));
       };
 
       // last value read from go_step: the scout usually runs several steps ahead (A ring depth, free
@@ -396,12 +474,16 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         const bool centre = (cur.j >= 0 && cur.j < cur.len);
         const uint32_t slot_lo = (cur.ord0 + lo) % kAccRing;
         const uint32_t a_row = umma_desc_lo(a_smem + cur.a_slot * kASlotBytes);
-        const uint32_t b_row = w_lo + (uint32_t)(lo - (cur.j - 1)) * sbb;   // first dy sub-block in range
+        const uint32_t sb_lo = (uint32_t)(lo - (cur.j - 1));                 // first dy sub-block in range
+        const uint32_t b_row = w_lo + sb_lo * sbb;
         const uint32_t cur_sc = cur.sc;
         const uint32_t cur_od = cur.ord0 + (uint32_t)max(cur.j, 0);
         StepCtx nxt = cur;
         advance(nxt);
-        auto step_body = [&](auto wrap_tag) {
+        // `emit(dx, k)` issues the MMAs of one (dx, k) of this step; everything else a step does between them -- the
+        // previous row's deferred 1x1 convs, the look-ahead at the next step's barriers, the previous step's deferred
+        // commit -- is common to the single-CTA and the pair form
+        auto step_body = [&](auto emit) {
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
             if (kPar && dx == 1 && ppend) {       // previous row's 1x1 convs, behind this step's dx = 0 group
@@ -420,34 +502,92 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint32_t a_lo = a_row + dx * 8 + 2 * k;
-              const uint32_t b_lo = b_row + dx * dxb + 2 * k;
-              if (dx == 0 && k == 0) {
-                // first MMA of the step: rows touched before accumulate, new rows are overwritten
-                if (old_cnt > 0) mma_range(wrap_tag, slot_lo, old_cnt, a_lo, b_lo, 1);
-                if (new_cnt > 0)
-                  mma_range(wrap_tag, (slot_lo + old_cnt) % kAccRing, new_cnt, a_lo, b_lo + old_cnt * sbb, 0);
-                if (pend) {
-                  // the previous step's commit rides behind this step's first MMA
-                  umma_commit(pend_bar);
-                  pend = false;
-                }
-              } else {
-                mma_range(wrap_tag, slot_lo, cnt, a_lo, b_lo, 1);
+              emit(dx, k);
+              if (dx == 0 && k == 0 && pend) {
+                // the previous step's commit rides behind this step's first MMA
+                commit(pend_bar);
+                pend = false;
               }
               if (tr) p.trace[1024 + cur_sc * 16 + dx * 4 + k] = clock64();
             }
           }
         };
-        if (slot_lo + (uint32_t)cnt > (uint32_t)kAccRing)
-          step_body(std::true_type{});
-        else
-          step_body(std::false_type{});
+        if constexpr (kPair) {
+          // Whole window (3 rows, not wrapping): ONE N = 3*tap_n MMA per (dx, k) out of the N-split blocks.  Otherwise,
+          // and always for the first MMA of a step (its rows take different accumulate flags: rows touched before
+          // accumulate, new rows are overwritten): one N = tap_n MMA per row out of the per-sub-block-split blocks,
+          // chained through the A collector so that the A tile is fetched from shared memory once.
+          uint32_t dcol[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            uint32_t sl = slot_lo + (uint32_t)i;
+            if (sl >= (uint32_t)kAccRing) sl -= (uint32_t)kAccRing;
+            dcol[i] = tmem_base + sl * tap_n;
+          }
+          const uint32_t idesc_sb = idesc0 + idesc_step, idesc_win = idesc0 + 3 * idesc_step;
+          auto rows = [&](auto cnt_tag, int dx, int k, uint32_t a_lo, bool first) {
+            constexpr int kCnt = decltype(cnt_tag)::value;
+            const uint32_t b0 = w64_lo + ((uint32_t)dx * 3 + sb_lo) * u64 + 2 * k;
+            const uint32_t acc0 = first ? (old_cnt > 0) : 1u, acc1 = first ? (old_cnt > 1) : 1u,
+                           acc2 = first ? (old_cnt > 2) : 1u;
+            if constexpr (kCnt == 1) {
+              umma2_bf16_lo<0>(dcol[0], a_lo, b0, idesc_sb, acc0);
+            } else if constexpr (kCnt == 2) {
+              umma2_bf16_lo<1>(dcol[0], a_lo, b0, idesc_sb, acc0);
+              umma2_bf16_lo<3>(dcol[1], a_lo, b0 + u64, idesc_sb, acc1);
+            } else {
+              umma2_bf16_lo<1>(dcol[0], a_lo, b0, idesc_sb, acc0);
+              umma2_bf16_lo<2>(dcol[1], a_lo, b0 + u64, idesc_sb, acc1);
+              umma2_bf16_lo<3>(dcol[2], a_lo, b0 + 2 * u64, idesc_sb, acc2);
+            }
+          };
+          if (cnt == 3 && slot_lo + 3u <= (uint32_t)kAccRing) {
+            step_body([&](int dx, int k) {
+              const uint32_t a_lo = a_row + dx * 8 + 2 * k;
+              if (dx == 0 && k == 0) rows(std::integral_constant<int, 3>{}, dx, k, a_lo, true);
+              else umma2_bf16_lo<0>(dcol[0], a_lo, w_lo + (uint32_t)dx * u192 + 2 * k, idesc_win, 1);
+            });
+          } else if (cnt == 3) {
+            step_body([&](int dx, int k) {
+              rows(std::integral_constant<int, 3>{}, dx, k, a_row + dx * 8 + 2 * k, dx == 0 && k == 0);
+            });
+          } else if (cnt == 2) {
+            step_body([&](int dx, int k) {
+              rows(std::integral_constant<int, 2>{}, dx, k, a_row + dx * 8 + 2 * k, dx == 0 && k == 0);
+            });
+          } else {
+            step_body([&](int dx, int k) {
+              rows(std::integral_constant<int, 1>{}, dx, k, a_row + dx * 8 + 2 * k, dx == 0 && k == 0);
+            });
+          }
+        } else {
+          auto emit1 = [&](auto wrap_tag, int dx, int k) {
+            const uint32_t a_lo = a_row + dx * 8 + 2 * k;
+            const uint32_t b_lo = b_row + dx * dxb + 2 * k;
+            if (dx == 0 && k == 0) {
+              // first MMA of the step: rows touched before accumulate, new rows are overwritten
+              if (old_cnt > 0) mma_range(wrap_tag, slot_lo, old_cnt, a_lo, b_lo, 1);
+              if (new_cnt > 0)
+                mma_range(wrap_tag, (slot_lo + old_cnt) % kAccRing, new_cnt, a_lo, b_lo + old_cnt * sbb, 0);
+            } else {
+              mma_range(wrap_tag, slot_lo, cnt, a_lo, b_lo, 1);
+            }
+          };
+          if (slot_lo + (uint32_t)cnt > (uint32_t)kAccRing)
+            step_body([&](int dx, int k) { emit1(std::true_type{}, dx, k); });
+          else
+            step_body([&](int dx, int k) { emit1(std::false_type{}, dx, k); });
+        }
         if (p.aux_k16 > 0 && centre) {
           const uint32_t a_lo = umma_desc_lo(aux_smem + (cur_od & 1) * kTileBytes);
-          for (int k = 0; k < p.aux_k16; ++k)
-            umma_bf16_lo(tmem_base + (cur_od % kAccRing) * tap_n, a_lo + 2 * k, kDescHiSw128,
-                         aux_w_lo + 2 * k, kDescHiSw128, idesc0 + idesc_step, 1);
+          for (int k = 0; k < p.aux_k16; ++k) {
+            if (kPair)
+              umma2_bf16_lo<0>(tmem_base + (cur_od % kAccRing) * tap_n, a_lo + 2 * k, aux_w_lo + 2 * k,
+                               idesc0 + idesc_step, 1);
+            else
+              umma_bf16_lo(tmem_base + (cur_od % kAccRing) * tap_n, a_lo + 2 * k, kDescHiSw128,
+                           aux_w_lo + 2 * k, kDescHiSw128, idesc0 + idesc_step, 1);
+          }
         }
         if (kPar && centre) {
           // Partition 1x1 convs of this row: centre pixel column (dx index 1), N = 192, own TMEM region.
@@ -468,18 +608,19 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         cur = nxt;
       }
       if (kPar && ppend) issue_par(pp_arow, pp_od);      // the last row's 1x1 convs
-      if (pend) umma_commit(pend_bar);
+      if (pend) commit(pend_bar);
     }
   } else if (warp == 10) {
     // ============================================================ barrier scout (one elected lane)
     // Walks the same step sequence as the MMA thread, one or more steps ahead, performs every
     // mbarrier wait the MMAs depend on (an already-complete try_wait costs 220-290 cycles in this
     // kernel) and publishes plain progress counters the MMA thread can poll in ~30 cycles.
-    if (elect_one()) {
+    // Pair mode: the leader's scout alone -- its barriers collect both CTAs' loads and accumulator releases.
+    if ((!kPair || rank == 0) && elect_one()) {
       const uint32_t go_step = smem_u32(&misc->go_step);
       Ring ar(s_a);
       uint32_t sc = 0, ord0 = 0;
-      for (SegIter it(p, t_begin, t_end); it.valid();) {
+      for (SegIter it(p, t_begin, t_end, rank); it.valid();) {
         const Segment s = it.get();
         for (int j = s.j_first; j <= s.j_last; ++j, ++sc, ar.advance()) {
           mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
@@ -529,9 +670,29 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       uint32_t ord, sc0;
       bool valid;
     };
-    TileCur cur{SegIter(p, t_begin, t_end), Segment{0, 0, 0, 0, 0, -1}, 0, 0u, 0u, false};
+    TileCur cur{SegIter(p, t_begin, t_end, rank), Segment{0, 0, 0, 0, 0, -1}, 0, 0u, 0u, false};
     cur.valid = cur.it.valid();
     if (cur.valid) cur.s = cur.it.get();
+    // "this accumulator slot / the 1x1 region has been read": in pair mode both CTAs report to the leader
+    const uint32_t acc_free0 = kPair ? mapa_shared(smem_u32(&misc->acc_free[0]), 0) : smem_u32(&misc->acc_free[0]);
+    const uint32_t go_par_a = kPair ? mapa_shared(smem_u32(&misc->go_par), 0) : smem_u32(&misc->go_par);
+    auto acc_release = [&](uint32_t slot) {
+      __syncwarp();
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(acc_free0 + slot * 8);
+        else mbar_arrive(acc_free0 + slot * 8);
+      }
+    };
+    auto par_release = [&]() {
+      __syncwarp();
+      if (lane == 0) {
+        if (kPair) red_add_cluster(go_par_a);
+        else asm volatile("red.relaxed.cta.shared::cta.add.u32 [%0], 1;" ::"r"(go_par_a) : "memory");
+      }
+    };
+    // pair mode, odd number of (image, strip) columns: the last pair's second CTA walks a column that does not exist
+    // (n == N).  Its loads may hit whatever follows in the pool, its results are never stored.
+    auto phantom = [&](const Segment& sg) { return kPair && sg.n >= p.N; };
     auto tile_next = [](TileCur& c) {
       ++c.ord;
       if (++c.o < c.s.len) return;
@@ -570,7 +731,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
     auto par_load = [&](const TileCur& c, float& q0, float& q1, float& q2) {
       const int x = c.s.strip * kTilePx + row;
       q0 = q1 = q2 = 0.f;
-      if (x < p.W) {
+      if (x < p.W && !phantom(c.s)) {
         const float* pp = par_g + (long long)c.s.n * p.par_sn + (long long)PNP_Y(c.s.y_b + c.o) * p.par_sy + x;
         q0 = __ldg(pp);
         q1 = __ldg(pp + p.par_sc);
@@ -613,7 +774,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
             tmem_ld_wait();
             if (b2 == 1) {                                   // everything is in registers: hand the region back first
               tc_fence_before();
-              warp_flag_add(smem_u32(&misc->go_par));
+              par_release();
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j)
@@ -657,7 +818,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
           for (int b4 = 0; b4 < 4; ++b4) tmem_ld16(taddr + b4 * 16, v + b4 * 16);
           tmem_ld_wait();
           tc_fence_before();
-          warp_arrive(smem_u32(&misc->acc_free[slot]));      // accumulator is in registers: slot reusable
+          acc_release(slot);                                 // accumulator is in registers: slot reusable
           mbar_wait(smem_u32(&misc->dy_full[ior.slot]), ior.phase, 13);
           uint8_t* rowp = sgen + L.io + ior.slot * kTileBytes + row * 128;
 #pragma unroll
@@ -694,7 +855,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
           named_bar_sync(2, 128);
           if (store_warp) {
             if (elect_one()) {
-              tma_store_4d(&p.tm_out, io_smem + ior.slot * kTileBytes, 0, s.strip * kTilePx, y, s.n + out_f);
+              if (!phantom(s)) tma_store_4d(&p.tm_out, io_smem + ior.slot * kTileBytes, 0, s.strip * kTilePx, y, s.n + out_f);
               tma_store_commit();
             }
             __syncwarp();
@@ -724,7 +885,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       tc_fence_after();
       blend_store(sgen + L.io + row * 128, q0, q1, q2);
       tc_fence_before();
-      warp_flag_add(smem_u32(&misc->go_par));
+      par_release();
     }
 
     // Identity tiles are fetched by the epilogue's own store lane: it is the one who knows when a
@@ -805,7 +966,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
           tmem_ld_wait();
         }
         tc_fence_before();
-        warp_arrive(smem_u32(&misc->acc_free[slot]));
+        acc_release(slot);
         if (valid && half == 0) {
           float* op = outf_g + (long long)s.n * p.of_sn + (long long)y * p.of_sy + x;
           op[0] = v[0] + misc->bias[0] + r0;
@@ -870,8 +1031,8 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         }
       }
       tc_fence_before();
-      warp_arrive(smem_u32(&misc->acc_free[slot]));   // accumulator is in registers: slot reusable
-      if (kPar && nxt.valid) warp_flag_add(smem_u32(&misc->go_par));   // ... and so is the 1x1 region
+      acc_release(slot);                              // accumulator is in registers: slot reusable
+      if (kPar && nxt.valid) par_release();           // ... and so is the 1x1 region
 #pragma unroll
       for (int gg = 0; gg < 2; ++gg) {
         const int g = half * 2 + gg;
@@ -927,7 +1088,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       if (store_warp) {
         if (elect_one()) {
           if (!PNP_DBG(2)) {
-            tma_store_4d(&p.tm_out, io_smem + s_io * kTileBytes, 0, s.strip * kTilePx, y, s.n + out_f);
+            if (!phantom(s)) tma_store_4d(&p.tm_out, io_smem + s_io * kTileBytes, 0, s.strip * kTilePx, y, s.n + out_f);
             tma_store_commit();
           }
         }
@@ -949,61 +1110,105 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
   }
 
   tc_fence_before();
-  __syncthreads();
+  // pair mode: neither CTA may leave (or free its TMEM) while the other one's MMAs / arrivals can still reach it
+  if (kPair) cluster_sync_all(); else __syncthreads();
   if (PNP_TRACING && threadIdx.x == 0) {            // per-CTA body cycles, start and end time (ns)
     p.trace[2048 + blockIdx.x] += clock64();
     p.trace[2368 + blockIdx.x] = (long long)globaltimer_ns();
   }
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) tmem_dealloc2(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
 #undef PNP_Y
 
 size_t conv_rows_smem_bytes(const ConvParams& p) {
-  const int w_bytes = 3 * 3 * p.tap_n * 128 + (p.aux_k16 > 0 ? kWChunkBytes : 0) + (p.has_par ? 3 * 64 * 128 : 0);
+  const int full = 3 * 3 * p.tap_n * 128;
+  const int w_bytes = p.pair ? full + (p.aux_k16 > 0 ? kWChunkBytes / 2 : 0) + (p.has_par ? 3 * 64 * 128 / 2 : 0)
+                             : full + (p.aux_k16 > 0 ? kWChunkBytes : 0) + (p.has_par ? 3 * 64 * 128 : 0);
   return rows_layout(w_bytes, p.s_a, p.aux_k16 > 0, p.n_io).total + 1024;
 }
 
 namespace {
-template <bool kPar, bool kScale>
+constexpr int kMaxSmem = 232448;
+
+template <bool kPar, bool kScale, bool kPair>
 cudaError_t launch_rows_variant(const ConvParams& p, int grid, size_t smem, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kRowsThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv3x3_rows_kernel<kPar, kScale>, p);
+  if (kPair) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
+  return cudaLaunchKernelEx(&cfg, conv3x3_rows_kernel<kPar, kScale, kPair>, p);
 }
-template <bool kPar, bool kScale>
-cudaError_t prepare_variant() {
-  return cudaFuncSetAttribute(conv3x3_rows_kernel<kPar, kScale>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+template <bool kPar, bool kScale, bool kPair>
+cudaError_t prepare_variant(int* max_pairs) {
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_rows_kernel<kPar, kScale, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kMaxSmem);
+  if (e != cudaSuccess || !kPair) return e;
+  // how many CTA pairs fit on the device at once (GPCs with an odd number of usable SMs leave one SM unpaired)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * 148);
+  cfg.blockDim = dim3(kRowsThreads);
+  cfg.dynamicSmemBytes = kMaxSmem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  e = cudaOccupancyMaxActiveClusters(&n, conv3x3_rows_kernel<kPar, kScale, kPair>, &cfg);
+  if (e == cudaSuccess && n < *max_pairs) *max_pairs = n;
+  return e;
 }
 }  // namespace
 
 // once per device, before the first launch (and before any stream capture): the API layer calls it under call_once
-cudaError_t conv_rows_prepare() {
+cudaError_t conv_rows_prepare(int* max_pairs) {
   cudaError_t e;
-  if ((e = prepare_variant<true, true>()) != cudaSuccess) return e;
-  if ((e = prepare_variant<true, false>()) != cudaSuccess) return e;
-  if ((e = prepare_variant<false, true>()) != cudaSuccess) return e;
-  return prepare_variant<false, false>();
+  int pairs = 1 << 30;
+  if ((e = prepare_variant<true, true, false>(&pairs)) != cudaSuccess) return e;
+  if ((e = prepare_variant<true, false, false>(&pairs)) != cudaSuccess) return e;
+  if ((e = prepare_variant<false, true, false>(&pairs)) != cudaSuccess) return e;
+  if ((e = prepare_variant<false, false, false>(&pairs)) != cudaSuccess) return e;
+  if ((e = prepare_variant<true, true, true>(&pairs)) != cudaSuccess) return e;
+  if ((e = prepare_variant<true, false, true>(&pairs)) != cudaSuccess) return e;
+  if ((e = prepare_variant<false, true, true>(&pairs)) != cudaSuccess) return e;
+  if ((e = prepare_variant<false, false, true>(&pairs)) != cudaSuccess) return e;
+  if (max_pairs) *max_pairs = pairs == (1 << 30) ? 0 : pairs;
+  return cudaSuccess;
 }
 
 cudaError_t launch_conv_rows(const ConvParams& p, int grid, cudaStream_t stream) {
   const size_t smem = conv_rows_smem_bytes(p);
   const bool par = p.has_par != 0, scale = (p.scale != nullptr);
-  if (par) return scale ? launch_rows_variant<true, true>(p, grid, smem, stream)
-                        : launch_rows_variant<true, false>(p, grid, smem, stream);
-  return scale ? launch_rows_variant<false, true>(p, grid, smem, stream)
-               : launch_rows_variant<false, false>(p, grid, smem, stream);
+  if (p.pair) {
+    if (par) return scale ? launch_rows_variant<true, true, true>(p, grid, smem, stream)
+                          : launch_rows_variant<true, false, true>(p, grid, smem, stream);
+    return scale ? launch_rows_variant<false, true, true>(p, grid, smem, stream)
+                 : launch_rows_variant<false, false, true>(p, grid, smem, stream);
+  }
+  if (par) return scale ? launch_rows_variant<true, true, false>(p, grid, smem, stream)
+                        : launch_rows_variant<true, false, false>(p, grid, smem, stream);
+  return scale ? launch_rows_variant<false, true, false>(p, grid, smem, stream)
+               : launch_rows_variant<false, false, false>(p, grid, smem, stream);
 }
 
 }  // namespace pnp

@@ -213,6 +213,27 @@ cudaError_t launch_lr_im2col(const float* lr, long long sn, long long sc, long l
 }
 
 // =====================================================================================
+// Launch-table upload without the copy engine: the kernel reads PINNED host memory over the bus itself.  A
+// cudaMemcpyAsync of the (small) table queues behind whatever the H2D copy engine is already moving -- with clips
+// streaming in (driver.ClipStreamer) that is up to a whole clip, 67 ms at 720p x 100 frames, during which the first
+// frame step cannot start (measured: 262 instead of 302 frames/s for such steps, tools/e2e_probe.py).
+// =====================================================================================
+__global__ void __launch_bounds__(256) fetch_pinned_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+cudaError_t launch_fetch_pinned(const void* src_dev_view, void* dst, long long bytes, cudaStream_t stream) {
+  const long long n16 = bytes >> 4;
+  long long blocks = (n16 + 255) / 256;
+  if (blocks > 592) blocks = 592;
+  if (blocks < 1) return cudaSuccess;
+  fetch_pinned_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src_dev_view),
+                                                     reinterpret_cast<uint4*>(dst), n16);
+  return cudaGetLastError();
+}
+
+// =====================================================================================
 // K4: weight packing.  Packed operands are 128-byte rows [row = out channel][64 cols = in channel] bf16 with
 // the 128B swizzle pre-applied (16-byte column group g of row r is stored at g ^ (r & 7)).
 //

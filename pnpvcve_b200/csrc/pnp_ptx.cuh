@@ -277,6 +277,80 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                : "memory");
 }
 
+// ------------------------------------------------------------------ CTA pairs (tcgen05 cta_group::2)
+// M = 256 across the two CTAs of a cluster: each CTA supplies its own 128 rows of A and HALF of the rows of B from its
+// own shared memory (same offsets in both CTAs), the accumulator rows of a CTA's pixels land in its own TMEM.  Issued
+// by one thread of the leader CTA (cluster rank 0).  kColl selects the A-operand collector: 0 none, 1 fill (keep A
+// after this MMA), 2 use (re-use the kept A and keep it), 3 lastuse.  Measured (tools/umma_collect_bench.cu,
+// profiles/r02_umma_collect.log): three N=64 MMAs chained fill/use/lastuse cost 110 cycles against 98 for one N=192
+// MMA and 132-146 without the collector -- the 4 KB A tile is fetched from shared memory once.
+template <int kColl>
+__device__ __forceinline__ void umma2_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                              uint32_t accumulate) {
+#define PNP_UMMA2(str)                                                                                          \
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"   \
+               "setp.ne.b32 p, %6, 0;\n\t" str " [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),                       \
+               "r"(a_lo), "r"(kDescHiSw128), "r"(b_lo), "r"(kDescHiSw128), "r"(idesc), "r"(accumulate)           \
+               : "memory")
+  if constexpr (kColl == 0) PNP_UMMA2("tcgen05.mma.cta_group::2.kind::f16");
+  if constexpr (kColl == 1) PNP_UMMA2("tcgen05.mma.cta_group::2.kind::f16.collector::a::fill");
+  if constexpr (kColl == 2) PNP_UMMA2("tcgen05.mma.cta_group::2.kind::f16.collector::a::use");
+  if constexpr (kColl == 3) PNP_UMMA2("tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse");
+#undef PNP_UMMA2
+}
+// the same collector variants for single-CTA MMAs
+template <int kColl>
+__device__ __forceinline__ void umma1_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                              uint32_t accumulate) {
+#define PNP_UMMA1(str)                                                                                          \
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"   \
+               "setp.ne.b32 p, %6, 0;\n\t" str " [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),                       \
+               "r"(a_lo), "r"(kDescHiSw128), "r"(b_lo), "r"(kDescHiSw128), "r"(idesc), "r"(accumulate)           \
+               : "memory")
+  if constexpr (kColl == 0) PNP_UMMA1("tcgen05.mma.cta_group::1.kind::f16");
+  if constexpr (kColl == 1) PNP_UMMA1("tcgen05.mma.cta_group::1.kind::f16.collector::a::fill");
+  if constexpr (kColl == 2) PNP_UMMA1("tcgen05.mma.cta_group::1.kind::f16.collector::a::use");
+  if constexpr (kColl == 3) PNP_UMMA1("tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse");
+#undef PNP_UMMA1
+}
+// commit of a CTA pair's MMAs: the mbarrier at this shared-memory offset arrives in BOTH CTAs
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_dst, uint32_t ncols) {  // warp 0 of BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {   // warp 0 of BOTH CTAs
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 4-D tiled load into this CTA's shared memory whose completion is signalled on an mbarrier of the pair's leader
+// (`cluster_bar`: shared::cluster address, mapa_shared(bar, 0))
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// Arrivals / counter bumps that cross to the other CTA of the cluster.  NOT `.release.cluster`: that form compiles to
+// MEMBAR.ALL.GPU + ERRBAR in front of the arrive (and `.acquire.cluster` waits to a CCTL.IVALL behind it), which made the
+// first pair kernel 75 % slower than the single-CTA one.  What these arrivals hand over are TMEM reads already completed
+// by tcgen05.wait::ld (+ tcgen05.fence::before_thread_sync), as in CUTLASS's 2-SM kernels (ClusterBarrier::arrive).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void red_add_cluster(uint32_t cluster_addr) {
+  asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], 1;" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_volatile_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // ------------------------------------------------------------------ flag hand-off in shared memory
 // A "scout" thread does the (slow, ~250 cycle) mbarrier waits and publishes progress counters; the
 // MMA-issuing thread only needs these ~30-cycle acquire loads on its critical path.

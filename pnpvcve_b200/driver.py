@@ -94,7 +94,9 @@ class ClipStreamer:
     chunk (``forward_streamed``), and finished frames go back to the host chunk by chunk on a second copy stream
     while later frames are still being computed; the upload of clip k+1 overlaps the kernels of clip k (two sets of
     device buffers).  Every clip still pays its full H2D and D2H -- they are just never exposed, except the first
-    chunk in and the last chunk out.  One clip (n = 1) per call.
+    chunk in and the last chunk out.  A call takes a batch of n >= 1 clips (n, T, ...): every copy is issued per clip
+    so that it is one contiguous DMA transfer (a strided (n, chunk) slice of a pinned tensor would be staged through a
+    pageable bounce buffer by the framework and stall the host).
     """
 
     BIG = ("lq", "mvs", "partitions")
@@ -108,6 +110,8 @@ class ClipStreamer:
         self.outs = [None, None]           # ... and result buffers: (tensor, event "its last download has finished")
         self.turn = 0
         self.h2d_bytes = self.d2h_bytes = 0
+        #: diagnostics (tools/e2e_probe.py): skip the big H2D / D2H copies to see what each direction costs
+        self.copy_in = self.copy_out = True
 
     def _chunks(self, t):
         return [(a, min(a + self.chunk, t)) for a in range(0, t, self.chunk)]
@@ -129,9 +133,11 @@ class ClipStreamer:
                 self.up.wait_event(busy)
             for k in self.SMALL:
                 dclip[k].copy_(host_clip[k], non_blocking=True)
+            n = host_clip["lq"].shape[0]
             for a, b in reversed(self._chunks(t)):
-                for k in self.BIG:
-                    dclip[k][:, a:b].copy_(host_clip[k][:, a:b], non_blocking=True)
+                for k in self.BIG if self.copy_in else ():
+                    for c in range(n):
+                        dclip[k][c, a:b].copy_(host_clip[k][c, a:b], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.up)
                 events[(a, b)] = ev
@@ -160,7 +166,8 @@ class ClipStreamer:
                 ev.record(main)
                 with torch.cuda.stream(self.down):
                     self.down.wait_event(ev)
-                    out_host[:, a:b].copy_(out[:, a:b], non_blocking=True)
+                    for c in range(out.shape[0]) if self.copy_out else ():
+                        out_host[c, a:b].copy_(out[c, a:b], non_blocking=True)
 
         main.wait_event(events[chunks[-1]])          # small tensors + the first chunk the kernels need
         waited.add(chunks[-1])
@@ -194,8 +201,7 @@ def stream_clips(net, host_clips, out_hosts, device, chunk=10):
     s = ClipStreamer(net, device, chunk)
     ticket = s.upload(host_clips[0])
     for k in range(len(host_clips)):
-        nxt = s.upload(host_clips[k + 1]) if k + 1 < len(host_clips) else None
         s.run(ticket, out_hosts[k])
-        ticket = nxt
+        ticket = s.upload(host_clips[k + 1]) if k + 1 < len(host_clips) else None    # overlaps clip k's kernels
     s.finish()
     return s

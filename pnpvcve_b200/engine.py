@@ -610,8 +610,9 @@ class BaeEngine:
             self._fill_table(pg, st, g_idx, b0, b1 - b0, variants, bwd_key, fwd_key, slot_of, ptrs, per_image)
             plans.append((b0, b1, variants, per_image))
         rows = 2 * t * len(groups)
-        pg.table[:rows].copy_(pg.host_table[:rows], non_blocking=True)
-        pg.img_off[:rows].copy_(pg.host_off[:rows], non_blocking=True)
+        # (not a cudaMemcpyAsync: the H2D copy engine may be busy with the next clip's upload for tens of ms)
+        ops.fetch_pinned(pg.table[:rows], pg.host_table[:rows])
+        ops.fetch_pinned(pg.img_off[:rows], pg.host_off[:rows])
         pg.uploaded = torch.cuda.Event()
         pg.uploaded.record()
 

@@ -56,6 +56,17 @@ def _plane_view_check(t, name):
         raise ValueError(f"{name} must be an fp32 CUDA view with unit innermost stride")
 
 
+def fetch_pinned(dst, src):
+    """dst (device) <- src (pinned host tensor of the same byte size), stream ordered, WITHOUT the copy engine (the
+    launch table must not queue behind a clip that is being uploaded)."""
+    nbytes = src.numel() * src.element_size()
+    if not src.is_pinned() or not dst.is_cuda or not dst.is_contiguous() or not src.is_contiguous() or \
+            dst.numel() * dst.element_size() != nbytes:
+        raise ValueError("fetch_pinned: dst must be a contiguous CUDA tensor and src a pinned host tensor of the same size")
+    with torch.cuda.device(dst.device):
+        _lib.check(_lib.load().pnp_fetch_pinned(_ptr(dst), _ptr(src), nbytes, _stream()), "pnp_fetch_pinned")
+
+
 def new_feature(n, h, w, device, zero=False):
     f = torch.zeros if zero else torch.empty
     return f((n, h, w, 64), dtype=torch.bfloat16, device=device)

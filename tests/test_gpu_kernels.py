@@ -100,7 +100,9 @@ def test_mv_warp_rejects_bad_arguments(dev):
 
 
 # ------------------------------------------------------------------ conv
-SHAPES = [(1, 64, 64), (1, 68, 132), (2, 72, 200), (1, 180, 320), (1, 376, 1244)]
+# (image, strip) column counts 1, 2, 4, 3, 10, 15: an even count or >= 15 columns takes the CTA-pair (cta_group::2) form
+# of the kernel -- 15 with a phantom column in the last pair --, the others the single-CTA form
+SHAPES = [(1, 64, 64), (1, 68, 132), (2, 72, 200), (1, 180, 320), (1, 376, 1244), (5, 40, 320)]
 
 
 def _pack(wt, dev, **kw):
@@ -400,6 +402,61 @@ def test_conv_per_image_weights_equal_separate_launches(dev, n, h, w):
         one = ops.new_feature(1, h, w, dev)
         ops.conv3x3(x[i:i + 1], packs[cond[i]], out=one, bias=biases[cond[i]], par=par[i:i + 1], act=ops.PNP_ACT_RELU)
         assert torch.equal(out[i:i + 1], one), f"image {i}"
+
+
+@pytest.mark.parametrize("n,h,w,mode", [(1, 68, 132, 1), (2, 72, 200, 1), (1, 376, 1244, 1), (1, 180, 320, 2),
+                                        (1, 64, 64, 2), (5, 40, 320, 1), (1, 720, 1280, 1)])
+def test_conv_pair_form_is_bit_identical_to_single_cta_form(dev, n, h, w, mode):
+    """The CTA-pair form of the conv kernel (cluster of two, tcgen05 cta_group::2, N-split weights, A-collector chains
+    for wrapped / clipped accumulator windows; pnp_set_pair_mode) against the single-CTA form: every operand variant,
+    even and odd column counts (mode 2: phantom column), per-image weights -- torch.equal."""
+    lib = _lib.load()
+    assert lib.pnp_device_pairs() >= 8
+    g = torch.Generator(device=dev).manual_seed(n * 31 + h + w)
+    x = nhwc(bf(torch.randn((n, 64, h, w), generator=g, device=dev)))
+    idt = nhwc(bf(torch.randn((n, 64, h, w), generator=g, device=dev)))
+    wt = bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05)
+    bias = torch.randn(64, generator=g, device=dev) * 0.1
+    scale = torch.rand(64, generator=g, device=dev) + 0.5
+    wp = _pack(wt, dev)
+    lr = torch.rand((n, 3, h, w), generator=g, device=dev)
+    w_in = bf(torch.randn((64, 131, 3, 3), generator=g, device=dev) * 0.05)
+    wpa = _pack(w_in, dev, in_begin=3, in_count=64)
+    ops.pack_aux(w_in, wpa[9 * ops.CHUNK_BYTES:])
+    lr64 = ops.new_feature(n, h, w, dev, zero=True)
+    ops.lr_im2col(lr, lr64)
+    par = torch.rand((n, 3, h, w), generator=g, device=dev) * (torch.rand((n, 3, h, w), generator=g, device=dev) > 0.5)
+    w1 = [bf(torch.randn((64, 64), generator=g, device=dev) * 0.1) for _ in range(3)]
+    wpp = _pack_par(wt, w1, dev)
+    wpf = _pack(wt, dev, flip_ky=True)
+    packs = torch.stack([_pack_par(bf(torch.randn((64, 64, 3, 3), generator=g, device=dev) * 0.05), w1, dev)[:ops.PACK_A_BYTES]
+                         for _ in range(2)], 0)
+    off = torch.tensor([[(i % 2) * ops.PACK_A_BYTES, (i % 2) * 64] for i in range(n)], dtype=torch.int64, device=dev)
+    biases = torch.randn((2, 64), generator=g, device=dev) * 0.1
+    variants = {
+        "plain": lambda o: ops.conv3x3(x, wp, out=o),
+        "bias+lrelu": lambda o: ops.conv3x3(x, wp, out=o, bias=bias, act=ops.PNP_ACT_LRELU),
+        "scale+idt+relu": lambda o: ops.conv3x3(x, wp, out=o, bias=bias, scale=scale, idt=idt, act=ops.PNP_ACT_RELU),
+        "idt bottom-up": lambda o: ops.conv3x3(x, wpf, out=o, bias=bias, idt=idt, flip_y=True),
+        "aux": lambda o: ops.conv3x3(x, wpa, out=o, aux=lr64, bias=bias, act=ops.PNP_ACT_LRELU),
+        "par": lambda o: ops.conv3x3(x, wpp, out=o, bias=bias, par=par, act=ops.PNP_ACT_RELU),
+        "par sparse": lambda o: ops.conv3x3(x, wpp, out=o, bias=bias, par=par, act=ops.PNP_ACT_RELU, par_sparse=True),
+        "par per image": lambda o: ops.conv3x3(x, packs, out=o, bias=biases, par=par, act=ops.PNP_ACT_RELU, img_off=off),
+    }
+    prev = lib.pnp_set_pair_mode(0)
+    try:
+        for name, fn in variants.items():
+            lib.pnp_set_pair_mode(0)
+            single = ops.new_feature(n, h, w, dev)
+            fn(single)
+            lib.pnp_set_pair_mode(mode)
+            paired = ops.new_feature(n, h, w, dev)
+            paired.fill_(7.0)
+            fn(paired)
+            torch.cuda.synchronize()
+            assert torch.equal(single, paired), f"{name}: {int((single != paired).sum())} values differ"
+    finally:
+        lib.pnp_set_pair_mode(prev)
 
 
 def test_table_mode_launches_equal_static_launches(dev):

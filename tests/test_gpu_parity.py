@@ -58,6 +58,23 @@ def test_generator_matches_reference_golden(dev, name):
     print(f"{name}: max-abs vs reference golden {err:.2e}")
 
 
+@pytest.mark.parametrize("name", ["c1_128x128_t7", "n2_64x96_t6_ipb", "edge_68x132_t3"])
+def test_generator_in_pair_form_matches_reference_golden(dev, name):
+    """The whole generator with every eligible conv launch in the CTA-pair (cta_group::2) form, phantom columns
+    included: same reference goldens, and bit-identical to the default form."""
+    from pnpvcve_b200 import _lib
+    lib = _lib.load()
+    sd, clip, gold = build_case(name)
+    ref = run(build(sd, dev), clip, dev)
+    prev = lib.pnp_set_pair_mode(2)
+    try:
+        out = run(build(sd, dev), clip, dev)
+    finally:
+        lib.pnp_set_pair_mode(prev)
+    check_against_golden(out, gold, tol=TOL, lq=clip["lq"], vsr=False)
+    assert torch.equal(out, ref)
+
+
 def psnr_delta(out, ref, seed=0):
     """PSNR (tensor2img uint8, metrics.py psnr) of both outputs against a synthetic ground truth."""
     g = torch.Generator().manual_seed(seed)
