@@ -351,6 +351,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-windows", action="store_true", help="skip the frame-window (single clip, strong scaling) block")
     ap.add_argument("--prof-every", type=int, default=8,
                     help="bracket every N-th launch of the profiled kernels with CUDA events")
     args = ap.parse_args()
@@ -489,20 +490,15 @@ def main():
     out_host = torch.empty((nc, T, 3, H, W), dtype=torch.float32).pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     d2h = out_host.numel() * out_host.element_size()
-    streamer = driver.ClipStreamer(net, dev, chunk=max(1, min(10, T)))
-
     def run_e2e(n_steps):
-        """The public host-clip API (driver.ClipStreamer): frames are uploaded in chunks in the order the backward-time
-        pass reads them, finished frames are downloaded chunk by chunk; every step still copies all of its inputs from
-        pinned host memory and all of its frames back inside the timed region."""
-        ticket = streamer.upload(host[0])
-        for i in range(n_steps):
-            out = streamer.run(ticket, out_host)
-            nxt = streamer.upload(host[0]) if i + 1 < n_steps else None      # overlaps the kernels just enqueued
-            local = driver.frame_metrics(out)
-            driver.gather_metrics(local.mean(0, keepdim=True), world, rank, world)
-            ticket = nxt
-        streamer.finish()
+        """The public host-clip API, driver.enhance_clips on HOST-resident entries: this rank's share of world x n_steps
+        entries streams through driver.ClipStreamer -- frames are uploaded in chunks in the order the backward-time pass
+        reads them, finished frames are downloaded chunk by chunk, the next entry's upload overlaps the kernels; every
+        step still copies all of its inputs from pinned host memory and all of its frames back inside the timed region,
+        and the per-frame metrics of all ranks meet in the job's one fixed-shape gather."""
+        entries = [host[0] if c % world == rank else None for c in range(world * n_steps)]
+        driver.enhance_clips(net, entries, rank, world, device=dev, out_hosts=[out_host] * len(entries),
+                             chunk=max(1, min(10, T)))
 
     del clips
     torch.cuda.empty_cache()
@@ -522,8 +518,37 @@ def main():
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_steps * T * nc / (float(ms2.item()) / 1e3)
-    del streamer, host, out_host
+    del host, out_host
     torch.cuda.empty_cache()
+
+    # ---------------- frame-window sharding: ONE clip of the config cut into `world` windows, one per rank (strong
+    # scaling of a single clip stream; north_star: "sharding independent clips or frame windows per GPU")
+    windows = None
+    if nc == 1 and T >= 2 * world and not args.no_windows:
+        wclip = make_device_batch(cfg, T, 1, 7000, 0, dev)              # the same clip on every rank
+        wlen = driver.balanced_window(T, world)
+        with torch.no_grad():
+            for _ in range(2):
+                driver.enhance_windows(net, [wclip], wlen, rank, world, gather_output=True)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            wsteps = max(2, args.steps)
+            g0.record()
+            for _ in range(wsteps):
+                driver.enhance_windows(net, [wclip], wlen, rank, world, gather_output=True)
+            g1.record()
+            barrier()
+        ms3 = torch.tensor([g0.elapsed_time(g1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+        windows = dict(value=wsteps * T / (float(ms3.item()) / 1e3), unit="frames/s", scaling="strong",
+                       workload=f"ONE {W}x{H}x{T} clip cut into {len(driver.frame_windows(T, wlen))} windows of <= {wlen} "
+                                "frames, one per GPU, each enhanced as a clip of its own (window ends are forced key "
+                                "frames); every rank ends with all frames and metrics (two fixed-shape NCCL all_gathers)",
+                       steps=wsteps, window_frames=wlen, api="pnpvcve_b200.driver.enhance_windows")
+        del wclip
+        net._engine.prog = None
+        torch.cuda.empty_cache()
 
     # ---------------- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample
     cpu_baseline = None
@@ -556,7 +581,9 @@ def main():
                     vs_baseline=None, dtype="bf16", data="synthetic", config=workload_config(args, world),
                     clocks=clocks, e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d,
                                             d2h_bytes_per_step=d2h, steps=e2e_steps,
-                                            api="pnpvcve_b200.driver.ClipStreamer (chunked H2D/D2H overlapped with the kernels)"),
+                                            api="pnpvcve_b200.driver.enhance_clips on pinned host entries (ClipStreamer: "
+                                                "chunked H2D/D2H overlapped with the kernels)"),
+                    frame_windows=windows,
                     gpu_launches=launches * world, launch_mode=net._engine.last_mode, roofline=roofline,
                     roofline_warp=roofline_warp,
                     kernels_ms=dict(block=mean_event_ms(prof["block"]), block_a=a_ms, block_b=b_ms, warp=w_ms),

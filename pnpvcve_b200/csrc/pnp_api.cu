@@ -180,7 +180,7 @@ static_assert(sizeof(pnp_conv_desc) == 272 && offsetof(pnp_conv_desc, out_spx) =
                   offsetof(pnp_conv_desc, img_off) == 224 && offsetof(pnp_conv_desc, dyn) == 232 &&
                   offsetof(pnp_conv_desc, src_images) == 256,
               "pnp_conv_desc layout is part of the ABI (mirrored by pnpvcve_b200/_lib.py: ConvDesc)");
-int pnp_abi_version(void) { return 7; }
+int pnp_abi_version(void) { return 8; }
 
 const char* pnp_last_error(void) { return g_err; }
 

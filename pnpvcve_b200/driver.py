@@ -1,4 +1,4 @@
-"""Clip-sharded multi-GPU driver: one process per GPU, no data-path collective.
+"""Clip-sharded / frame-window-sharded multi-GPU driver: one process per GPU, no data-path collective.
 
 The reference shards its test set by rank-strided sampling (mmedit/datasets/samplers/
 distributed_sampler.py:51-72) and gathers pickled results with two all_gathers
@@ -54,32 +54,156 @@ def gather_metrics(local, num_clips, rank, world, group=None):
 
 
 @torch.no_grad()
-def enhance_clips(net, clips, rank=0, world=1, refs=None, gts=None, crop_border=0):
-    """Run this rank's share of ``clips`` (list of dicts as produced by pnpvcve_b200.synthetic).
+def enhance_clips(net, clips, rank=0, world=1, refs=None, gts=None, crop_border=0, device=None, out_hosts=None,
+                  chunk=10):
+    """Run this rank's share of ``clips``: a list of clip dicts as produced by pnpvcve_b200.synthetic, each holding
+    n >= 1 equally shaped clips (n, T, ...); entries of other ranks may be None.
 
-    Returns (outputs for the local clips, gathered metrics for all clips).  With ``gts`` (ground-truth clips,
-    (1,T,3,H,W) each) the per-frame metric vector is [max-abs, mse, PSNR, SSIM]: PSNR / SSIM as BasicVSR.evaluate
-    computes them (mmedit/models/restorers/basicvsr.py:119-153), but on the device (pnpvcve_b200.metrics) -- the
-    reference's test loop copies every frame to the host and pickles per-clip results through two all_gathers
-    (mmedit/apis/test.py:190-234); here nothing leaves the GPU before the single fixed-shape gather.
+    Device-resident entries are enhanced in place; HOST-resident entries (CPU tensors, pinned or not) stream through
+    ``ClipStreamer`` on ``device``: chunked uploads and downloads overlap the kernels, the upload of the next entry
+    overlaps the kernels of the current one, and the frames land in ``out_hosts[c]`` (pinned buffers, allocated here
+    when not given).  Returns (outputs of the local entries -- device tensors, or the pinned host buffers --, gathered
+    metrics (num_entries * n, T, M) for all clips on every rank).  With ``gts`` (ground truth, (n,T,3,H,W) per entry) the
+    per-frame metric vector is [max-abs, mse, PSNR, SSIM]: PSNR / SSIM as BasicVSR.evaluate computes them
+    (mmedit/models/restorers/basicvsr.py:119-153), but on the device (pnpvcve_b200.metrics) -- the reference's test loop
+    copies every frame to the host and pickles per-clip results through two all_gathers (mmedit/apis/test.py:190-234);
+    here nothing but the frames themselves leaves the GPU before the single fixed-shape gather.
     """
     from .synthetic import generator_args
     from . import metrics as _metrics
     mine = shard_clips(len(clips), rank, world)
+    shape_of = next(c for c in clips if c is not None)["lq"].shape
+    n, t = shape_of[:2]
+    host = bool(mine) and not clips[mine[0]]["lq"].is_cuda
+    dev = torch.device(device) if device is not None else \
+        (torch.device("cuda", torch.cuda.current_device()) if host else next(c for c in clips if c is not None)["lq"].device)
     outs, mets = [], []
-    for c in mine:
-        out = net(*generator_args(clips[c]))
-        outs.append(out)
-        m = frame_metrics(out, None if refs is None else refs[c])[0]
+
+    def measure(c, out):
+        m = frame_metrics(out, None if refs is None else refs[c].to(out.device))
         if gts is not None:
             q = _metrics.frame_quality(out, gts[c].to(out.device), crop_border)
-            m = torch.cat([m, q["psnr"][0].float()[:, None], q["ssim"][0].float()[:, None]], dim=1)
+            m = torch.cat([m, q["psnr"].float()[..., None], q["ssim"].float()[..., None]], dim=-1)
         mets.append(m)
+
+    if host:
+        up = 4 if getattr(net, "vsr", False) else 1
+        pinned = {c: {k: (v if v.is_pinned() else v.pin_memory()) for k, v in clips[c].items()} for c in mine}
+        streamer = ClipStreamer(net, dev, chunk=chunk)
+        ticket = streamer.upload(pinned[mine[0]])
+        for i, c in enumerate(mine):
+            dst = out_hosts[c] if out_hosts is not None else \
+                torch.empty((n, t, 3, shape_of[-2] * up, shape_of[-1] * up), dtype=torch.float32).pin_memory()
+            out = streamer.run(ticket, dst)
+            ticket = streamer.upload(pinned[mine[i + 1]]) if i + 1 < len(mine) else None   # overlaps clip c's kernels
+            measure(c, out)                 # on the device copy, before its buffer is recycled two entries later
+            outs.append(dst)
+        streamer.finish()
+    else:
+        for c in mine:
+            out = net(*generator_args(clips[c]))
+            outs.append(out)
+            measure(c, out)
+    nm = N_METRICS + (2 if gts is not None else 0)
+    local = torch.cat(mets, 0) if mets else torch.empty((0, t, nm), device=dev)
+    per_entry = gather_metrics(local.view(len(mine), n * t, nm) if mets else local.view(0, n * t, nm),
+                               len(clips), rank, world)
+    return outs, per_entry.view(len(clips) * n, t, nm)
+
+
+# ------------------------------------------------------------------------------------------------
+# frame-window sharding: ONE long clip (or a few) spread over the GPUs
+# ------------------------------------------------------------------------------------------------
+def frame_windows(t, window):
+    """Consecutive windows [a, b) of at most ``window`` frames, as the reference's recurrent inference with
+    ``max_seq_len`` cuts a sequence (mmedit/apis/restoration_video_inference.py:121-128: ``data[:, i:i + max_seq_len]``
+    for i in range(0, T, max_seq_len), results concatenated).  Every window is enhanced as a clip of its own, so its
+    first and last frame become forced key frames (iconvsr_ipb_par.py:61-62) and no state crosses a window border."""
+    if window < 1:
+        raise ValueError(f"window must be >= 1, got {window}")
+    return [(a, min(a + window, t)) for a in range(0, t, window)]
+
+
+def balanced_window(t, world, min_window=2):
+    """Window length that cuts a T-frame clip into ``world`` windows of (almost) equal length."""
+    return max(min_window, (t + world - 1) // world)
+
+
+def shard_windows(num_clips, t, window, rank, world):
+    """This rank's (clip, a, b) work items: the windows of all clips in (clip, window) order, item k -> rank k % world."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    items = [(c, a, b) for c in range(num_clips) for a, b in frame_windows(t, window)]
+    return items[rank::world]
+
+
+def clip_window(clip, a, b, overlap=0):
+    """Views of frames [a - overlap, b + overlap) (clamped to the clip) of every tensor of a clip dict, and the position
+    [lo, hi) of the core frames [a, b) inside that window.  ``overlap`` > 0 runs extra context frames whose outputs are
+    discarded: the forced key frames then sit ``overlap`` frames away from the frames that are kept, which bounds the
+    seam error against the uncut clip at the price of (2 overlap / window) extra work.  overlap = 0 is the reference's
+    ``max_seq_len`` semantics exactly."""
+    t = clip["lq"].shape[1]
+    a0, b0 = max(0, a - overlap), min(t, b + overlap)
+    return {k: v[:, a0:b0] for k, v in clip.items()}, a - a0, b - a0
+
+
+@torch.no_grad()
+def enhance_windows(net, clips, window, rank=0, world=1, overlap=0, refs=None, gather_output=False, group=None):
+    """Frame-window sharding (north_star: "sharding independent clips or frame windows per GPU"): the windows of
+    ``clips`` (equally shaped (1,T,...) clip dicts) are dealt to the ranks round robin and enhanced independently.
+
+    Returns (outs, metrics): outs = {(clip, a, b): (1, b-a, 3, H, W) frames} of this rank's windows -- or, with
+    ``gather_output``, the complete (num_clips, T, 3, H, W) result on every rank (one fixed-shape all_gather of frames
+    over NVLink) --, metrics = (num_clips, T, N_METRICS) of ALL frames on every rank (one fixed-shape all_gather).  No
+    collective touches the data path of a window."""
+    from .synthetic import generator_args
+    num_clips = len(clips)
     t = clips[0]["lq"].shape[1]
     dev = clips[0]["lq"].device
-    nm = N_METRICS + (2 if gts is not None else 0)
-    local = torch.stack(mets, 0) if mets else torch.empty((0, t, nm), device=dev)
-    return outs, gather_metrics(local, len(clips), rank, world)
+    mine = shard_windows(num_clips, t, window, rank, world)
+    outs = {}
+    local = torch.full((num_clips, t, N_METRICS), float("nan"), dtype=torch.float32, device=dev)
+    for c, a, b in mine:
+        win, lo, hi = clip_window(clips[c], a, b, overlap)
+        out = net(*generator_args({k: v.contiguous() for k, v in win.items()}))[:, lo:hi]
+        outs[(c, a, b)] = out
+        local[c, a:b] = frame_metrics(out, None if refs is None else refs[c][:, a:b])[0]
+    metrics = merge_sharded(local, world, group)
+    if not gather_output:
+        return outs, metrics
+    # frames: every rank contributes ONLY its own windows, packed into a fixed (items, window, 3, H, W) block
+    up = 4 if getattr(net, "vsr", False) else 1
+    h, w = clips[0]["lq"].shape[-2] * up, clips[0]["lq"].shape[-1] * up
+    items_all = [shard_windows(num_clips, t, window, r, world) for r in range(world)]
+    max_items = max(len(it) for it in items_all)
+    wlen = min(window, t)
+    block = torch.zeros((max_items, wlen, 3, h, w), dtype=torch.float32, device=dev)
+    for i, (c, a, b) in enumerate(mine):
+        block[i, :b - a] = outs[(c, a, b)][0]
+    if world == 1:
+        parts = block[None]
+    else:
+        parts = torch.empty((world,) + tuple(block.shape), dtype=torch.float32, device=dev)
+        dist.all_gather(list(parts.unbind(0)), block, group=group)
+    frames = torch.empty((num_clips, t, 3, h, w), dtype=torch.float32, device=dev)
+    for r in range(world):
+        for i, (c, a, b) in enumerate(items_all[r]):
+            frames[c, a:b] = parts[r, i, :b - a]
+    return frames, metrics
+
+
+def merge_sharded(local, world, group=None):
+    """Every rank holds a tensor of the SAME shape with its own entries filled and NaN elsewhere; returns the union on
+    every rank (one all_gather of that fixed shape).  Entries nobody owns stay NaN."""
+    if world == 1:
+        return local
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local.contiguous(), group=group)
+    full = parts[0]
+    for p in parts[1:]:
+        full = torch.where(torch.isnan(full), p, full)
+    return full
 
 
 # ------------------------------------------------------------------------------------------------

@@ -204,6 +204,48 @@ def test_clip_streamer_equals_plain_forward(dev):
     assert st.d2h_bytes == refs[0].numel() * 4
 
 
+def test_frame_windows_match_oracle_on_the_same_windows(dev):
+    """Frame-window sharding (driver.enhance_windows): every window is a clip of its own -- compared with the oracle run
+    on the SAME windows (the reference's max_seq_len semantics); with overlap the kept frames move away from the forced
+    key frames and the seam error against the UNCUT clip does not grow."""
+    from pnpvcve_b200 import driver
+    sd = weights.random_state_dict(21, num_blocks=2)
+    net = build(sd, dev, num_blocks=2)
+    clip = synthetic.make_clip(64, 96, 11, seed=640, crf=25)
+    dclip = {k: v.to(dev) for k, v in clip.items()}
+    full, met = driver.enhance_windows(net, [dclip], 4, gather_output=True)
+    assert full.shape == (1, 11, 3, 64, 96) and not torch.isnan(full).any() and met.shape == (1, 11, driver.N_METRICS)
+    for a, b in driver.frame_windows(11, 4):
+        win, _, _ = driver.clip_window(clip, a, b)
+        ref = O.generator_forward(sd, *synthetic.generator_args({k: v.contiguous() for k, v in win.items()}), num_blocks=2)
+        err = (full[:, a:b].cpu() - ref).abs().max().item()
+        assert err <= TOL, f"window [{a},{b}): {err}"
+    uncut = O.generator_forward(sd, *synthetic.generator_args(clip), num_blocks=2)
+    seam0 = (full.cpu() - uncut).abs().max().item()
+    lapped, _ = driver.enhance_windows(net, [dclip], 4, overlap=2, gather_output=True)
+    seam2 = (lapped.cpu() - uncut).abs().max().item()
+    print(f"seam error vs the uncut clip: {seam0:.3e} without overlap, {seam2:.3e} with 2 frames of overlap")
+    assert seam2 <= seam0 + 1e-6
+
+
+def test_enhance_clips_streams_host_clips(dev):
+    """driver.enhance_clips on HOST-resident entries (n = 2 clips each) goes through ClipStreamer: same frames as the
+    device-resident call, frames delivered to pinned host buffers, metrics gathered for every clip."""
+    from pnpvcve_b200 import driver
+    sd = weights.random_state_dict(22, num_blocks=2)
+    net = build(sd, dev, num_blocks=2)
+    entries = [synthetic.cat_clips([synthetic.make_clip(64, 96, 7, seed=700 + 2 * i + j, crf=(15, 35)[j]) for j in range(2)])
+               for i in range(3)]
+    on_dev = [{k: v.to(dev) for k, v in e.items()} for e in entries]
+    outs_d, met_d = driver.enhance_clips(net, on_dev)
+    outs_h, met_h = driver.enhance_clips(net, entries, device=dev, chunk=3)
+    torch.cuda.synchronize()
+    assert met_d.shape == (6, 7, driver.N_METRICS)
+    for od, oh in zip(outs_d, outs_h):
+        assert oh.is_pinned() and torch.equal(od.cpu(), oh)
+    assert torch.equal(met_d, met_h)
+
+
 def test_profiled_launch_path_equals_fast_path(dev):
     """bench.py's profile pass brackets block launches with events and therefore takes the per-launch descriptor path;
     the default path patches pre-filled descriptors.  Same kernels, same arguments: bit-identical frames."""

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/pnp_vcve.h but not exported"
     assert sorted(_lib.EXPORTS) == syms
-    assert _lib.load().pnp_abi_version() == 7
+    assert _lib.load().pnp_abi_version() == 8
 
 
 def test_abi_argument_errors_without_gpu():
@@ -219,3 +219,56 @@ def test_clip_sharding_and_metric_gather_world2(num_clips):
     for _, full in got:
         assert torch.equal(full, exp)
     assert sorted(driver.shard_clips(5, 0, 2) + driver.shard_clips(5, 1, 2)) == list(range(5))
+
+
+def _fake_net(lq, *rest):
+    """stands in for the generator on the CPU: the result depends on the window's first and last frame, as the real
+    one does through the forced key frames"""
+    return lq * 2.0 + lq[:, :1] - lq[:, -1:]
+
+
+def _window_worker(rank, world, port, num_clips, t, window, overlap, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    clips = [synthetic.make_clip(16, 16, t, seed=70 + c) for c in range(num_clips)]
+    full, met = driver.enhance_windows(_fake_net, clips, window, rank, world, overlap=overlap, gather_output=True)
+    # (numpy: pickled by value -- a torch tensor would travel as a shared-memory handle that dies with this process)
+    q.put((rank, full.numpy(), met.numpy(), len(driver.shard_windows(num_clips, t, window, rank, world))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("num_clips,t,window,overlap", [(1, 11, 4, 0), (2, 10, 5, 0), (1, 9, 3, 1), (1, 5, 8, 0)])
+def test_frame_window_sharding_world2(num_clips, t, window, overlap):
+    """Frame windows of one (or two) clips dealt to two ranks: every rank ends up with the frames and the metrics of
+    ALL windows, each window computed exactly as a clip of its own (the reference's max_seq_len semantics,
+    restoration_video_inference.py:121-128), overlap frames computed and dropped."""
+    world = 2
+    assert driver.frame_windows(11, 4) == [(0, 4), (4, 8), (8, 11)]
+    assert driver.balanced_window(100, 8) == 13 and len(driver.frame_windows(100, 13)) == 8
+    items = [driver.shard_windows(num_clips, t, window, r, world) for r in range(world)]
+    assert sorted(items[0] + items[1]) == [(c, a, b) for c in range(num_clips) for a, b in driver.frame_windows(t, window)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_window_worker, args=(r, world, port, num_clips, t, window, overlap, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    clips = [synthetic.make_clip(16, 16, t, seed=70 + c) for c in range(num_clips)]
+    exp = torch.empty((num_clips, t, 3, 16, 16))
+    for c in range(num_clips):
+        for a, b in driver.frame_windows(t, window):
+            a0, b0 = max(0, a - overlap), min(t, b + overlap)
+            exp[c, a:b] = _fake_net(clips[c]["lq"][:, a0:b0])[0, a - a0:b - a0]
+    for rank, full, met, n_items in got:
+        full, met = torch.from_numpy(full), torch.from_numpy(met)
+        assert n_items == len(items[rank])
+        assert torch.equal(full, exp)
+        assert met.shape == (num_clips, t, driver.N_METRICS) and not torch.isnan(met).any()
+        assert torch.equal(met[..., 0], exp.abs().amax(dim=(2, 3, 4)))
