@@ -98,9 +98,11 @@ int pnp_fetch_pinned(void* dst, const void* src_pinned, int64_t bytes, void* str
 int pnp_mv_warp(const void* src, const float* flow_x, const float* flow_y, int64_t flow_row_stride,
                 int64_t flow_image_stride, void* dst, int N, int H, int W, int32_t* dbg_x0,
                 int32_t* dbg_y0, void* stream);
-/* table mode: src / flow_x / flow_y / dst come from the launch table (no debug outputs) */
-int pnp_mv_warp_dyn(const pnp_dyn_ref* dyn, int64_t flow_row_stride, int64_t flow_image_stride, int N, int H, int W,
-                    void* stream);
+/* table mode: src / flow_x / flow_y / dst come from the launch table (no debug outputs).  Every entry's src must be an
+ * image-aligned address inside the (src_pool_images, H, W, 64) buffer at src_pool: the tap windows are staged by TMA
+ * through ONE tensor map of that buffer, built when the launch is recorded. */
+int pnp_mv_warp_dyn(const pnp_dyn_ref* dyn, const void* src_pool, int src_pool_images, int64_t flow_row_stride,
+                    int64_t flow_image_stride, int N, int H, int W, void* stream);
 
 /*
  * LR frames -> im2col'd bf16 operand (N, H, W, 64), channel k = tap*3 + c for k < 27, zero for

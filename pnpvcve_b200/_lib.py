@@ -67,7 +67,7 @@ _PROTOS = {
     "pnp_graph_destroy": (_i, [_vp]),
     "pnp_set_step": (_i, [_vp, _c.c_int32, _vp]),
     "pnp_fetch_pinned": (_i, [_vp, _vp, _i64, _vp]),
-    "pnp_mv_warp_dyn": (_i, [_c.POINTER(DynRef), _i64, _i64, _i, _i, _i, _vp]),
+    "pnp_mv_warp_dyn": (_i, [_c.POINTER(DynRef), _vp, _i, _i64, _i64, _i, _i, _i, _vp]),
     "pnp_lr_im2col_dyn": (_i, [_c.POINTER(DynRef), _i64, _i64, _i64, _i, _i, _i, _vp]),
     "pnp_pack_mix_blocks": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i64, _vp]),
     "pnp_mv_warp": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _vp, _vp, _vp]),

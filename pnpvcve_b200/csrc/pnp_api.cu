@@ -53,6 +53,7 @@ int device_info(DeviceInfo** out) {
       g_dev[dev].ok = (prop.major == 10);
       g_dev[dev].sms = prop.multiProcessorCount;
       if (g_dev[dev].ok) e2 = pnp::conv_rows_prepare(&g_dev[dev].max_pairs);
+      if (g_dev[dev].ok && e2 == cudaSuccess) e2 = pnp::warp_prepare();
     }
     g_dev[dev].err = e2;
   });
@@ -68,6 +69,7 @@ int device_info(DeviceInfo** out) {
 struct Knobs {
   int l2_hints = 0;        // PNP_L2_HINTS=1: evict_first on launch B's dead reads (measured: no effect)
   int par_split = 1;       // PNP_PAR_SPLIT=0: single-role epilogue of block launch A
+  int warp_tma = 1;        // PNP_WARP_TMA=0: the warp takes its taps by global gathers only (A/B timing)
   int pair = 0;            // PNP_PAIR=1: CTA-pair (cta_group::2) form of the conv kernel where the shape allows it; 2: also
                            // with a phantom column.  Off by default: measured level in cycles and 3-5 % slower in time
                            // under the power cap (profiles/r02_notes.md); pnp_set_pair_mode() overrides at run time
@@ -82,6 +84,7 @@ const Knobs& knobs() {
     if (const char* e = getenv("PNP_L2_HINTS")) v.l2_hints = atoi(e) != 0;
     if (const char* e = getenv("PNP_PAR_SPLIT")) v.par_split = atoi(e) != 0;
     if (const char* e = getenv("PNP_PAIR")) v.pair = atoi(e);
+    if (const char* e = getenv("PNP_WARP_TMA")) v.warp_tma = atoi(e) != 0;
     if (const char* e = getenv("PNP_RINGS")) {
       if (sscanf(e, "%d,%d", &v.rings_nio, &v.rings_sa) != 2) v.rings_nio = v.rings_sa = 0;
     }
@@ -148,7 +151,7 @@ EncodeTiledFn encode_fn() {
 // (64, W, H, N) bf16 NHWC tensor, box (64, box_w, 1, 1), 128-byte swizzle, zero fill out of range.
 // spx/sy/sn: element strides between pixels / rows / images (0 = contiguous NHWC).
 int make_map(CUtensorMap* m, const void* base, int N, int H, int W, int box_w, long long spx = 0, long long sy = 0,
-             long long sn = 0) {
+             long long sn = 0, int box_h = 1) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(PNP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -158,7 +161,7 @@ int make_map(CUtensorMap* m, const void* base, int N, int H, int W, int box_w, l
     strides[1] = (cuuint64_t)sy * 2;
     strides[2] = (cuuint64_t)sn * 2;
   }
-  cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -180,7 +183,7 @@ static_assert(sizeof(pnp_conv_desc) == 272 && offsetof(pnp_conv_desc, out_spx) =
                   offsetof(pnp_conv_desc, img_off) == 224 && offsetof(pnp_conv_desc, dyn) == 232 &&
                   offsetof(pnp_conv_desc, src_images) == 256,
               "pnp_conv_desc layout is part of the ABI (mirrored by pnpvcve_b200/_lib.py: ConvDesc)");
-int pnp_abi_version(void) { return 8; }
+int pnp_abi_version(void) { return 9; }
 
 const char* pnp_last_error(void) { return g_err; }
 
@@ -276,20 +279,29 @@ int pnp_mv_warp(const void* src, const float* flow_x, const float* flow_y, int64
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
-  cudaError_t e = pnp::launch_mv_warp(src, flow_x, flow_y, flow_row_stride, flow_image_stride, dst, N, H, W, dbg_x0,
-                                      dbg_y0, dyn_ref(nullptr), static_cast<cudaStream_t>(stream));
+  CUtensorMap tm, tmd;
+  if ((rc = make_map(&tm, src, N, H, W, 10, 0, 0, 0, 10))) return rc;
+  if ((rc = make_map(&tmd, dst, N, H, W, 8, 0, 0, 0, 8))) return rc;
+  cudaError_t e = pnp::launch_mv_warp(tm, tmd, src, flow_x, flow_y, flow_row_stride, flow_image_stride, dst, N, H, W, dbg_x0,
+                                      dbg_y0, dyn_ref(nullptr), nullptr, knobs().warp_tma, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_mv_warp");
 }
 
-int pnp_mv_warp_dyn(const pnp_dyn_ref* dyn, int64_t flow_row_stride, int64_t flow_image_stride, int N, int H, int W,
-                    void* stream) {
+int pnp_mv_warp_dyn(const pnp_dyn_ref* dyn, const void* src_pool, int src_pool_images, int64_t flow_row_stride,
+                    int64_t flow_image_stride, int N, int H, int W, void* stream) {
   if (!dyn || !dyn->table || !dyn->step) return fail(PNP_ERR_ARG, "pnp_mv_warp_dyn: null launch table");
   if (N <= 0 || H <= 0 || W <= 0) return fail(PNP_ERR_ARG, "pnp_mv_warp_dyn: bad shape");
+  if (!src_pool || src_pool_images < N || !aligned16(src_pool))
+    return fail(PNP_ERR_ARG, "pnp_mv_warp_dyn: src_pool must be the 16-byte aligned buffer every table entry's src lies in");
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
-  cudaError_t e = pnp::launch_mv_warp(nullptr, nullptr, nullptr, flow_row_stride, flow_image_stride, nullptr, N, H, W,
-                                      nullptr, nullptr, dyn_ref(dyn), static_cast<cudaStream_t>(stream));
+  CUtensorMap tm, tmd;
+  if ((rc = make_map(&tm, src_pool, src_pool_images, H, W, 10, 0, 0, 0, 10))) return rc;
+  if ((rc = make_map(&tmd, src_pool, src_pool_images, H, W, 8, 0, 0, 0, 8))) return rc;
+  cudaError_t e = pnp::launch_mv_warp(tm, tmd, nullptr, nullptr, nullptr, flow_row_stride, flow_image_stride, nullptr, N, H, W,
+                                      nullptr, nullptr, dyn_ref(dyn), src_pool, knobs().warp_tma,
+                                      static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_mv_warp_dyn");
 }
 

@@ -25,124 +25,226 @@ __device__ __forceinline__ float warp_coord(float pos, float mv, float size_m1_d
   return __fmul_rn(__fmul_rn(__fadd_rn(nrm, 1.0f), 0.5f), size_m1);    // ((c+1)/2)*(s-1)
 }
 
-// One pixel quarter (16 channels = 32 bytes) of the warp: coordinates, 4 taps, fp32 blend, store.
-__device__ __forceinline__ void warp_pixel_quarter(const uint4* __restrict__ src, uint4* __restrict__ dst,
-                                                   float fx, float fy, int x, int y, int q, int H, int W,
-                                                   int* __restrict__ dbg_x0, int* __restrict__ dbg_y0) {
+// Per-pixel part shared by both tap sources: coordinates (exact reference op order), weights, integer taps.
+struct WarpTaps {
+  int x0, y0;
+  float wnw, wne, wsw, wse;
+};
+__device__ __forceinline__ WarpTaps warp_taps(float fx, float fy, int x, int y, int H, int W, float& x0f, float& y0f) {
   const float ix = warp_coord((float)x, fx, (float)max(W - 1, 1), (float)(W - 1));
   const float iy = warp_coord((float)y, fy, (float)max(H - 1, 1), (float)(H - 1));
-  const float x0f = floorf(ix), y0f = floorf(iy);
+  x0f = floorf(ix);
+  y0f = floorf(iy);
   const float x1f = __fadd_rn(x0f, 1.0f), y1f = __fadd_rn(y0f, 1.0f);
   const float wx1 = __fsub_rn(ix, x0f), wx0 = __fsub_rn(x1f, ix);
   const float wy1 = __fsub_rn(iy, y0f), wy0 = __fsub_rn(y1f, iy);
-  const float wnw = __fmul_rn(wx0, wy0), wne = __fmul_rn(wx1, wy0);
-  const float wsw = __fmul_rn(wx0, wy1), wse = __fmul_rn(wx1, wy1);
+  WarpTaps t;
+  t.wnw = __fmul_rn(wx0, wy0);
+  t.wne = __fmul_rn(wx1, wy0);
+  t.wsw = __fmul_rn(wx0, wy1);
+  t.wse = __fmul_rn(wx1, wy1);
   // clamp before the int conversion so huge |mv| cannot overflow; out-of-range taps are dropped
-  const int x0 = (int)fminf(fmaxf(x0f, -2.0f), (float)W + 1.0f);
-  const int y0 = (int)fminf(fmaxf(y0f, -2.0f), (float)H + 1.0f);
-  const int pix = y * W + x;
-  if (dbg_x0 != nullptr && q == 0) {
-    dbg_x0[pix] = (int)fminf(fmaxf(x0f, -2147483000.0f), 2147483000.0f);
-    dbg_y0[pix] = (int)fminf(fmaxf(y0f, -2147483000.0f), 2147483000.0f);
-  }
-  const bool okx0 = x0 >= 0 && x0 < W, okx1 = x0 + 1 >= 0 && x0 + 1 < W;
-  const bool oky0 = y0 >= 0 && y0 < H, oky1 = y0 + 1 >= 0 && y0 + 1 < H;
-  const uint4 z = make_uint4(0, 0, 0, 0);
-  const uint4* t00 = src + ((size_t)(y0 * W + x0)) * 8 + q * 2;     // pixel = 8 uint4
-  const uint4* t10 = t00 + (size_t)W * 8;
-  uint4 v[4][2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    v[0][h] = (okx0 && oky0) ? __ldg(t00 + h) : z;
-    v[1][h] = (okx1 && oky0) ? __ldg(t00 + 8 + h) : z;
-    v[2][h] = (okx0 && oky1) ? __ldg(t10 + h) : z;
-    v[3][h] = (okx1 && oky1) ? __ldg(t10 + 8 + h) : z;
-  }
-  uint4 o[2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const uint32_t a[4] = {v[0][h].x, v[0][h].y, v[0][h].z, v[0][h].w};
-    const uint32_t b[4] = {v[1][h].x, v[1][h].y, v[1][h].z, v[1][h].w};
-    const uint32_t c[4] = {v[2][h].x, v[2][h].y, v[2][h].z, v[2][h].w};
-    const uint32_t d[4] = {v[3][h].x, v[3][h].y, v[3][h].z, v[3][h].w};
-    uint32_t r[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      // nw*wnw + ne*wne + sw*wsw + se*wse in fp32 (FMA chain, like ATen's CUDA grid sampler)
-      float lo = bf16_lo(a[j]) * wnw;
-      lo = fmaf(bf16_lo(b[j]), wne, lo);
-      lo = fmaf(bf16_lo(c[j]), wsw, lo);
-      lo = fmaf(bf16_lo(d[j]), wse, lo);
-      float hi = bf16_hi(a[j]) * wnw;
-      hi = fmaf(bf16_hi(b[j]), wne, hi);
-      hi = fmaf(bf16_hi(c[j]), wsw, hi);
-      hi = fmaf(bf16_hi(d[j]), wse, hi);
-      r[j] = pack_bf16x2(lo, hi);
-    }
-    o[h] = make_uint4(r[0], r[1], r[2], r[3]);
-  }
-  uint4* op = dst + (size_t)pix * 8 + q * 2;
-  op[0] = o[0];
-  op[1] = o[1];
+  t.x0 = (int)fminf(fmaxf(x0f, -2.0f), (float)W + 1.0f);
+  t.y0 = (int)fminf(fmaxf(y0f, -2.0f), (float)H + 1.0f);
+  return t;
 }
 
-// The first version of this kernel spent ~550 SASS instructions per 48 bytes moved (64-bit index
-// divisions, per-tap rounded mul/add chains) and was issue-bound at ~45 % of the HBM roofline.
-// Second version: 2-D grid (no divisions), 32-bit indexing, 4 threads per pixel x 32 bytes each, FMA
-// blend, one block = 64 pixels of ONE row -- every source row was then fetched from L2 by two blocks
-// (rows y0 and y0+1 of vertically adjacent outputs), i.e. ~2x the source bytes over the L2->SM path.
-// Now: one block = a kTileW x kTileH pixel tile walked two rows at a time, so the second tap row of one
-// iteration is the first tap row of the next and is found in L1; with the codec's block-constant motion
-// vectors a tile reads a (kTileW+1) x (kTileH+1) window once.
-template <int kTileW, int kTileH>
-__global__ void __launch_bounds__(256)
-mv_warp_kernel(const uint4* __restrict__ src, const float* __restrict__ flow_x,
-               const float* __restrict__ flow_y, long long flow_sy, long long flow_sn, uint4* __restrict__ dst,
-               int H, int W, int* __restrict__ dbg_x0, int* __restrict__ dbg_y0, const DynRef dyn) {
-  constexpr int kRowsPerIter = 64 / kTileW;
-  if (const DynEntry* e = dyn.entry()) {                  // table mode: p{src, flow_x, flow_y, dst}
+// nw*wnw + ne*wne + sw*wsw + se*wse in fp32 (FMA chain, like ATen's CUDA grid sampler) of 8 bf16 channels.  The two
+// channels of a 32-bit word are blended as one packed fp32 pair (FMUL2 / FFMA2 on sm_100: the same IEEE operations per
+// element, half the instructions -- the kernel is bound by instruction issue, not by bytes).
+__device__ __forceinline__ uint4 warp_blend(const uint4& va, const uint4& vb, const uint4& vc, const uint4& vd,
+                                            const WarpTaps& t) {
+  const uint32_t a[4] = {va.x, va.y, va.z, va.w}, b[4] = {vb.x, vb.y, vb.z, vb.w};
+  const uint32_t c[4] = {vc.x, vc.y, vc.z, vc.w}, d[4] = {vd.x, vd.y, vd.z, vd.w};
+  const float2 wnw = make_float2(t.wnw, t.wnw), wne = make_float2(t.wne, t.wne);
+  const float2 wsw = make_float2(t.wsw, t.wsw), wse = make_float2(t.wse, t.wse);
+  uint32_t r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 acc = __fmul2_rn(make_float2(bf16_lo(a[j]), bf16_hi(a[j])), wnw);
+    acc = __ffma2_rn(make_float2(bf16_lo(b[j]), bf16_hi(b[j])), wne, acc);
+    acc = __ffma2_rn(make_float2(bf16_lo(c[j]), bf16_hi(c[j])), wsw, acc);
+    acc = __ffma2_rn(make_float2(bf16_lo(d[j]), bf16_hi(d[j])), wse, acc);
+    r[j] = pack_bf16x2(acc.x, acc.y);
+  }
+  return make_uint4(r[0], r[1], r[2], r[3]);
+}
+
+// History.  v1 spent ~550 SASS instructions per 48 bytes moved (64-bit index divisions, per-tap rounded mul/add chains)
+// and was issue-bound at ~45 % of the HBM roofline.  v2: 2-D grid, 32-bit indexing, 4 threads per pixel x 32 bytes,
+// FMA blend, 32 x 8 pixel tiles walked two rows at a time so that the tap row shared by vertically adjacent outputs is
+// found in L1: 52.9 us at 720p cold (70 % of the measured HBM rate), still issue bound (ncu: DRAM throughput 38 %,
+// issue slots 64 % busy, ~1500 warp instructions per 32 pixels): every tap is a predicated, bounds-checked
+// 64-bit-addressed global load and the four threads of a pixel all redo its coordinate arithmetic.
+//
+// v3 (this kernel): TMA tile staging in both directions, one thread per pixel.  The codec's motion vectors are constant
+// over blocks of >= 8 x 8 pixels, so an 8 x 8 output block reads a 9 x 9 source window (10 x 10 with the one-pixel slack
+// the reference's fp32 normalise / un-normalise round trip can add).  A CTA owns a 32 x 8 pixel tile = four such blocks,
+// 64 threads each.  Every thread computes its pixel's exact integer taps and weights ONCE (motion vectors are call
+// inputs, so this runs ahead of griddepcontrol.wait), the block's tap bounding box is reduced with redux.sync, and one
+// thread per block issues a (64 ch, 10, 10) TMA box load of that window into 128B-swizzled shared memory --
+// out-of-image taps arrive as zeros, which IS grid_sample's padding_mode='zeros'.  The taps are then 16-byte
+// shared-memory reads without bounds checks or global address arithmetic (a warp reads 32 window rows whose chunks the
+// swizzle spreads over all banks), the blended pixel is parked in a swizzled output tile and leaves by a TMA box store
+// (clipped at the image edge).  A block whose taps do not fit a 10 x 10 window (arbitrary per-pixel flow) reads its taps
+// with global loads instead, so any flow field gives the reference's result.
+constexpr int kWarpWin = 10;                             // staged window: kWarpWin x kWarpWin source pixels
+constexpr int kWarpWinBytes = kWarpWin * kWarpWin * 128;   // 12800
+constexpr int kWarpWinPitch = 13 * 1024;                 // 1024-aligned slot (the swizzle is a function of address bits)
+constexpr int kWarpOutBytes = 64 * 128;                  // one 8 x 8 output block
+#ifndef PNP_WARP_BLOCKS
+#define PNP_WARP_BLOCKS 1
+#endif
+constexpr int kWarpBlocks = PNP_WARP_BLOCKS;             // 8 x 8 blocks per CTA (tile 8*kWarpBlocks x 8), 64 threads each
+constexpr int kWarpSmem = kWarpBlocks * kWarpWinPitch + 1024;     // the output tile re-uses its block's window slot
+
+__global__ void __launch_bounds__(64 * kWarpBlocks)
+mv_warp_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_dst,
+               const uint4* __restrict__ src, const float* __restrict__ flow_x, const float* __restrict__ flow_y,
+               long long flow_sy, long long flow_sn, uint4* __restrict__ dst, int H, int W, int* __restrict__ dbg_x0,
+               int* __restrict__ dbg_y0, const DynRef dyn, const uint8_t* pool_base, int use_tma) {
+  extern __shared__ uint8_t warp_smem_raw[];
+  __shared__ uint64_t bar[kWarpBlocks];
+  __shared__ int box[kWarpBlocks][4];                    // min x0, max x0, min y0, max y0 of the block's valid pixels
+  int img_src = 0, img_dst = 0;                          // first image inside the tensor maps
+  if (const DynEntry* e = dyn.entry()) {                 // table mode: p{src, flow_x, flow_y, dst}; both maps span the pool
     src = reinterpret_cast<const uint4*>(e->p[0]);
     flow_x = reinterpret_cast<const float*>(e->p[1]);
     flow_y = reinterpret_cast<const float*>(e->p[2]);
     dst = reinterpret_cast<uint4*>(e->p[3]);
-  }               // 256 threads = 64 pixels x 4 quarters per iteration
-  static_assert(kTileW * kRowsPerIter == 64 && kTileH % kRowsPerIter == 0, "tile shape");
-  // blockIdx.z = image of the batch: same-shape clips with their own motion fields
-  src += (size_t)blockIdx.z * H * W * 8;
-  dst += (size_t)blockIdx.z * H * W * 8;
-  flow_x += (long long)blockIdx.z * flow_sn;
-  flow_y += (long long)blockIdx.z * flow_sn;
-  const int q = threadIdx.x & 3;                          // which 16-channel quarter (two uint4)
-  const int px = threadIdx.x >> 2;                        // 0..63
-  const int x = blockIdx.x * kTileW + (px % kTileW);
-  const int ry = px / kTileW;
-  if (x >= W) return;
-  const int y_base = blockIdx.y * kTileH + ry;
-  // all motion vectors of this thread's pixels first (independent loads), then the gathers
-  float fx[kTileH / kRowsPerIter], fy[kTileH / kRowsPerIter];
-#pragma unroll
-  for (int it = 0; it < kTileH / kRowsPerIter; ++it) {
-    const int y = y_base + it * kRowsPerIter;
-    fx[it] = (y < H) ? __ldg(flow_x + (long long)y * flow_sy + x) : 0.f;
-    fy[it] = (y < H) ? __ldg(flow_y + (long long)y * flow_sy + x) : 0.f;
+    const long long img_bytes = (long long)H * W * 128;
+    img_src = (int)((reinterpret_cast<const uint8_t*>(src) - pool_base) / img_bytes);
+    img_dst = (int)((reinterpret_cast<const uint8_t*>(dst) - pool_base) / img_bytes);
   }
+  const uint32_t raw = smem_u32(warp_smem_raw);
+  const uint32_t sbase = (raw + 1023u) & ~1023u;
+  uint8_t* sgen = warp_smem_raw + (sbase - raw);
+  const int tid = threadIdx.x;
+  const int b = tid >> 6;                                // this thread's 8 x 8 block (two warps per block)
+  const int col = tid & 7, row = (tid >> 3) & 7;         // its pixel inside the block
+  if (tid < kWarpBlocks) {
+    mbar_init(smem_u32(&bar[tid]), 1);
+    box[tid][0] = box[tid][2] = 0x7fffffff;
+    box[tid][1] = box[tid][3] = -0x7fffffff;
+  }
+  if (tid == 0) {
+    mbar_fence_init();
+    tma_prefetch_desc(&tm_src);
+    tma_prefetch_desc(&tm_dst);
+  }
+  griddep_launch_dependents();
+  __syncthreads();
+  // blockIdx.z = image of the batch: same-shape clips with their own motion fields
+  const int n = blockIdx.z;
+  flow_x += (long long)n * flow_sn;
+  flow_y += (long long)n * flow_sn;
+  const int bx = (blockIdx.x * kWarpBlocks + b) * 8, by = blockIdx.y * 8;
+  const int x = bx + col, y = by + row;
+  const bool valid = x < W && y < H;
+  // ---- the pixel's taps and weights (motion vectors are inputs of the call: no dependence on the previous kernel)
+  float fx = 0.f, fy = 0.f;
+  if (valid) {
+    fx = __ldg(flow_x + (long long)y * flow_sy + x);
+    fy = __ldg(flow_y + (long long)y * flow_sy + x);
+  }
+  float x0f, y0f;
+  const WarpTaps t = warp_taps(fx, fy, x, y, H, W, x0f, y0f);
+  if (dbg_x0 != nullptr && valid) {
+    dbg_x0[y * W + x] = (int)fminf(fmaxf(x0f, -2147483000.0f), 2147483000.0f);
+    dbg_y0[y * W + x] = (int)fminf(fmaxf(y0f, -2147483000.0f), 2147483000.0f);
+  }
+  if (use_tma) {
+    const int mnx = __reduce_min_sync(0xffffffffu, valid ? t.x0 : 0x7fffffff);
+    const int mxx = __reduce_max_sync(0xffffffffu, valid ? t.x0 : -0x7fffffff);
+    const int mny = __reduce_min_sync(0xffffffffu, valid ? t.y0 : 0x7fffffff);
+    const int mxy = __reduce_max_sync(0xffffffffu, valid ? t.y0 : -0x7fffffff);
+    if ((tid & 31) == 0 && mnx <= mxx) {                 // two warps per block
+      atomicMin(&box[b][0], mnx);
+      atomicMax(&box[b][1], mxx);
+      atomicMin(&box[b][2], mny);
+      atomicMax(&box[b][3], mxy);
+    }
+  }
+  __syncthreads();
+  griddep_wait();                                        // the source features come from the previous kernel
+  const int bx0 = box[b][0], by0 = box[b][2];
+  const bool any = bx < W && by < H;                     // the block has pixels inside the image
+  const bool staged = use_tma && any && box[b][1] + 2 - bx0 <= kWarpWin && box[b][3] + 2 - by0 <= kWarpWin;
+  // ---- one thread per block: stage its tap window (taps x0..x0+1, y0..y0+1 of every pixel) if it fits
+  if (staged && (tid & 63) == 0) {
+    mbar_arrive_expect_tx(smem_u32(&bar[b]), kWarpWinBytes);
+    tma_load_4d(sbase + b * kWarpWinPitch, &tm_src, smem_u32(&bar[b]), 0, bx0, by0, img_src + n);
+  }
+  // the block's output tile (row = pixel index) takes over its window slot once every thread has read its taps
+  uint8_t* const ob = sgen + b * kWarpWinPitch;
+  const int p = tid & 63;
+  uint4 o[8];
+  if (staged) {
+    mbar_wait(smem_u32(&bar[b]), 0, 20);
+    // (pixels outside the image took no part in the bounding box: their taps may lie outside the window, and their
+    // outputs are clipped by the store anyway)
+    const int r00 = valid ? (t.y0 - by0) * kWarpWin + (t.x0 - bx0) : 0;          // window row of the north-west tap
+    // Rows are 128-byte aligned, so "row + swizzled chunk offset" is (row ^ ((row & 7) << 4)) ^ (chunk << 4): one XOR
+    // with an immediate per load.  Chunks are walked in LOGICAL order -- at a fixed logical chunk the lanes' physical
+    // chunks differ with their rows, which is what keeps the reads free of bank conflicts (walking physical chunks,
+    // tried: every lane on the same four banks, 44 -> 99 us).  Offsets are taken from the 1024-aligned base `sgen`.
+    auto rowx = [&](int r) { return ((uint32_t)(b * kWarpWinPitch) + (uint32_t)r * 128u) ^ (((uint32_t)r & 7u) << 4); };
+    const uint32_t pa = rowx(r00), pb = rowx(r00 + 1), pc = rowx(r00 + kWarpWin), pd = rowx(r00 + kWarpWin + 1);
+    auto lds = [&](uint32_t off) { return *reinterpret_cast<const uint4*>(sgen + off); };
 #pragma unroll
-  for (int it = 0; it < kTileH / kRowsPerIter; ++it) {
-    const int y = y_base + it * kRowsPerIter;
-    if (y < H) warp_pixel_quarter(src, dst, fx[it], fy[it], x, y, q, H, W, dbg_x0, dbg_y0);
+    for (int c = 0; c < 8; ++c) o[c] = warp_blend(lds(pa ^ (16 * c)), lds(pb ^ (16 * c)), lds(pc ^ (16 * c)), lds(pd ^ (16 * c)), t);
+    named_bar_sync(1 + b, 64);                           // every tap of the block has been read
+  } else if (any) {
+    const uint4* sp = src + (size_t)n * H * W * 8;
+    const bool okx0 = valid && t.x0 >= 0 && t.x0 < W, okx1 = valid && t.x0 + 1 >= 0 && t.x0 + 1 < W;
+    const bool oky0 = t.y0 >= 0 && t.y0 < H, oky1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const uint4* t00 = sp + ((long long)t.y0 * W + t.x0) * 8;         // pixel = 8 uint4
+    const uint4* t10 = t00 + (size_t)W * 8;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      o[c] = warp_blend((okx0 && oky0) ? __ldg(t00 + c) : z, (okx1 && oky0) ? __ldg(t00 + 8 + c) : z,
+                        (okx0 && oky1) ? __ldg(t10 + c) : z, (okx1 && oky1) ? __ldg(t10 + 8 + c) : z, t);
+  }
+  if (any) {
+    {
+      const uint32_t orow = (uint32_t)(b * kWarpWinPitch) + (((uint32_t)p * 128u) ^ (((uint32_t)p & 7u) << 4));
+#pragma unroll
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sgen + (orow ^ (16 * c))) = o[c];
+    }
+  }
+  // ---- the block's output tile leaves by one TMA store (pixels outside the image are clipped)
+  fence_proxy_async_smem();
+  named_bar_sync(1 + b, 64);
+  if (any && p == 0) {
+    tma_store_4d(&tm_dst, smem_u32(ob), 0, bx, by, img_dst + n);
+    tma_store_commit();
+    tma_store_wait_read<0>();             // shared memory must stay valid until the store has read it
   }
 }
 
-cudaError_t launch_mv_warp(const void* src, const float* flow_x, const float* flow_y, long long flow_sy,
-                           long long flow_sn, void* dst, int N, int H, int W, int* dbg_x0, int* dbg_y0,
-                           const DynRef& dyn, cudaStream_t stream) {
+cudaError_t warp_prepare() {
+  return cudaFuncSetAttribute(mv_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpSmem);
+}
+
+cudaError_t launch_mv_warp(const CUtensorMap& tm_src, const CUtensorMap& tm_dst, const void* src, const float* flow_x,
+                           const float* flow_y, long long flow_sy, long long flow_sn, void* dst, int N, int H, int W,
+                           int* dbg_x0, int* dbg_y0, const DynRef& dyn, const void* pool_base, int use_tma,
+                           cudaStream_t stream) {
   if ((long long)H * W >= (1LL << 27) || N > 65535) return cudaErrorInvalidValue;   // 32-bit pixel indexing
-  // 32 x 8 pixel tiles (tools/warp_bench.py, cold L2: 64x1 57.5 us, 32x8 53.4, 16x8 54.5, 64x4 53.4, 32x16 54.2)
-  constexpr int TW = 32, TH = 8;
-  mv_warp_kernel<TW, TH><<<dim3((W + TW - 1) / TW, (H + TH - 1) / TH, N), 256, 0, stream>>>(
-      reinterpret_cast<const uint4*>(src), flow_x, flow_y, flow_sy, flow_sn, reinterpret_cast<uint4*>(dst), H, W, dbg_x0,
-      dbg_y0, dyn);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((W + 8 * kWarpBlocks - 1) / (8 * kWarpBlocks), (H + 7) / 8, N);
+  cfg.blockDim = dim3(64 * kWarpBlocks);
+  cfg.dynamicSmemBytes = kWarpSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, mv_warp_kernel, tm_src, tm_dst, reinterpret_cast<const uint4*>(src), flow_x, flow_y,
+                            flow_sy, flow_sn, reinterpret_cast<uint4*>(dst), H, W, dbg_x0, dbg_y0, dyn,
+                            reinterpret_cast<const uint8_t*>(pool_base), use_tma);
 }
 
 // =====================================================================================

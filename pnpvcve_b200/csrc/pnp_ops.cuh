@@ -1,5 +1,6 @@
 // Launchers of the memory-bound kernels in pnp_ops.cu.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -9,9 +10,14 @@ struct DynRef;
 
 constexpr int kPackBlockBytes = 8192;
 
-cudaError_t launch_mv_warp(const void* src, const float* flow_x, const float* flow_y, long long flow_sy,
-                           long long flow_sn, void* dst, int N, int H, int W, int* dbg_x0, int* dbg_y0,
-                           const DynRef& dyn, cudaStream_t stream);
+// tm_src / tm_dst: (64, W, H, images) bf16 maps of the source / destination buffer, boxes (64, 10, 10, 1) / (64, 8, 8, 1),
+// 128B swizzle, zero fill; table mode: both span the pool that starts at pool_base and the entry's pointers select the
+// images
+cudaError_t warp_prepare();
+cudaError_t launch_mv_warp(const CUtensorMap& tm_src, const CUtensorMap& tm_dst, const void* src, const float* flow_x,
+                           const float* flow_y, long long flow_sy, long long flow_sn, void* dst, int N, int H, int W,
+                           int* dbg_x0, int* dbg_y0, const DynRef& dyn, const void* pool_base, int use_tma,
+                           cudaStream_t stream);
 cudaError_t launch_lr_im2col(const float* lr, long long sn, long long sc, long long sy, void* dst, int N,
                              int H, int W, const DynRef& dyn, cudaStream_t stream);
 cudaError_t launch_fetch_pinned(const void* src_dev_view, void* dst, long long bytes, cudaStream_t stream);

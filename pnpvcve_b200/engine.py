@@ -364,7 +364,8 @@ class BaeEngine:
         def warp():
             r = dyn(len(nodes))
             fsy, fsn = shapes["flow"]
-            nodes.append(("warp", "warp", (lib.pnp_mv_warp_dyn, ctypes.byref(r), r, fsy, fsn, nn, h, w)))
+            nodes.append(("warp", "warp", (lib.pnp_mv_warp_dyn, ctypes.byref(r), r, ctypes.c_void_p(pool_ptr), pg.pool_images,
+                                           fsy, fsn, nn, h, w)))
 
         bwd = variant.startswith("b_")
         im2col()
@@ -647,7 +648,7 @@ class BaeEngine:
                 if kind == "conv":
                     rc = a[0](a[1], stream)
                 elif kind == "warp":
-                    rc = a[0](a[1], a[3], a[4], a[5], a[6], a[7], stream)
+                    rc = a[0](a[1], a[3], a[4], a[5], a[6], a[7], a[8], a[9], stream)
                 else:
                     rc = a[0](a[1], a[3], a[4], a[5], a[6], a[7], a[8], stream)
                 if timed:

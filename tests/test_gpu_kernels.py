@@ -91,6 +91,27 @@ def test_mv_warp_zero_and_integer_flow(dev):
     assert_bf16_close(nchw(dst).cpu(), exp, "integer shift")
 
 
+def test_mv_warp_per_pixel_flow_takes_the_gather_path(dev):
+    """A flow field that is NOT block constant (every pixel its own vector, up to +-40 px): the 8 x 8 blocks' taps do not
+    fit the staged 10 x 10 windows, so they are read by global gathers -- same taps, same values as the oracle; mixed
+    with block-constant regions in one launch, and with n = 2 images."""
+    g = torch.Generator().manual_seed(5)
+    h, w = 72, 136
+    x = bf(torch.randn((2, 64, h, w), generator=g))
+    flow = (torch.rand((2, 2, h, w), generator=g) - 0.5) * 80.0
+    flow[:, :, :32, :64] = 2.25                                   # a block-constant corner: staged windows
+    src = nhwc(x).to(dev)
+    dst = ops.new_feature(2, h, w, dev)
+    ops.mv_warp(src, flow.to(dev), dst)
+    torch.cuda.synchronize()
+    for i in range(2):
+        ref = O.warp_bilinear(x[i], flow[i])
+        assert_bf16_close(nchw(dst[i:i + 1])[0].cpu(), ref, f"image {i}")
+        x0, y0 = ops.mv_warp(src[i:i + 1].contiguous(), flow[i].to(dev), ops.new_feature(1, h, w, dev), debug=True)
+        ex0, ey0 = O.warp_taps(flow[i], h, w)
+        assert torch.equal(x0.cpu(), ex0) and torch.equal(y0.cpu(), ey0)
+
+
 def test_mv_warp_rejects_bad_arguments(dev):
     a = ops.new_feature(1, 64, 64, dev)
     with pytest.raises(ValueError):
@@ -510,7 +531,8 @@ def test_table_mode_launches_equal_static_launches(dev):
     d.dyn = ref(1)
 
     def sequence(st):
-        _lib.check(lib.pnp_mv_warp_dyn(ctypes.byref(r0), flow.stride(3), flow.stride(1), n, h, w, st), "warp_dyn")
+        _lib.check(lib.pnp_mv_warp_dyn(ctypes.byref(r0), ctypes.c_void_p(pool.data_ptr()), pool.shape[0], flow.stride(3),
+                                       flow.stride(1), n, h, w, st), "warp_dyn")
         _lib.check(lib.pnp_conv3x3(ctypes.byref(d), st), "conv dyn")
 
     for s in range(frames):                                              # eager table mode

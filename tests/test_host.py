@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/pnp_vcve.h but not exported"
     assert sorted(_lib.EXPORTS) == syms
-    assert _lib.load().pnp_abi_version() == 8
+    assert _lib.load().pnp_abi_version() == 9
 
 
 def test_abi_argument_errors_without_gpu():
@@ -48,7 +48,7 @@ def test_abi_argument_errors_without_gpu():
     assert lib.pnp_mv_warp(None, None, None, 0, 0, None, 1, 4, 4, None, None, None) == -1
     assert lib.pnp_graph_launch(None, None, 0, None) == -1
     assert lib.pnp_set_step(None, 0, None) == -1
-    assert lib.pnp_mv_warp_dyn(None, 0, 0, 1, 4, 4, None) == -1
+    assert lib.pnp_mv_warp_dyn(None, None, 0, 0, 0, 1, 4, 4, None) == -1
     assert lib.pnp_graph_destroy(None) == 0
     if not torch.cuda.is_available():
         assert lib.pnp_device_check() != 0                         # no device: loud failure, no fallback
