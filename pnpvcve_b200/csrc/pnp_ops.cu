@@ -98,7 +98,7 @@ constexpr int kWarpOutBytes = 64 * 128;                  // one 8 x 8 output blo
 constexpr int kWarpBlocks = PNP_WARP_BLOCKS;             // 8 x 8 blocks per CTA (tile 8*kWarpBlocks x 8), 64 threads each
 constexpr int kWarpSmem = kWarpBlocks * kWarpWinPitch + 1024;     // the output tile re-uses its block's window slot
 
-__global__ void __launch_bounds__(64 * kWarpBlocks)
+__global__ void __launch_bounds__(64 * kWarpBlocks, 14 / kWarpBlocks)     // 14 slots of 13 KB + 1 KB per SM
 mv_warp_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_dst,
                const uint4* __restrict__ src, const float* __restrict__ flow_x, const float* __restrict__ flow_y,
                long long flow_sy, long long flow_sn, uint4* __restrict__ dst, int H, int W, int* __restrict__ dbg_x0,
@@ -194,23 +194,42 @@ mv_warp_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant
 #pragma unroll
     for (int c = 0; c < 8; ++c) o[c] = warp_blend(lds(pa ^ (16 * c)), lds(pb ^ (16 * c)), lds(pc ^ (16 * c)), lds(pd ^ (16 * c)), t);
     named_bar_sync(1 + b, 64);                           // every tap of the block has been read
-  } else if (any) {
-    const uint4* sp = src + (size_t)n * H * W * 8;
-    const bool okx0 = valid && t.x0 >= 0 && t.x0 < W, okx1 = valid && t.x0 + 1 >= 0 && t.x0 + 1 < W;
-    const bool oky0 = t.y0 >= 0 && t.y0 < H, oky1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    const uint4* t00 = sp + ((long long)t.y0 * W + t.x0) * 8;         // pixel = 8 uint4
-    const uint4* t10 = t00 + (size_t)W * 8;
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      o[c] = warp_blend((okx0 && oky0) ? __ldg(t00 + c) : z, (okx1 && oky0) ? __ldg(t00 + 8 + c) : z,
-                        (okx0 && oky1) ? __ldg(t10 + c) : z, (okx1 && oky1) ? __ldg(t10 + 8 + c) : z, t);
-  }
-  if (any) {
     {
       const uint32_t orow = (uint32_t)(b * kWarpWinPitch) + (((uint32_t)p * 128u) ^ (((uint32_t)p & 7u) << 4));
 #pragma unroll
       for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(sgen + (orow ^ (16 * c))) = o[c];
+    }
+  } else if (any) {
+    // Gather path (the block's taps do not fit one window -- e.g. the reversed P-frame vectors the reference scatters
+    // at their target positions, loading_ipb.py:352-356, or any per-pixel flow): four lanes per pixel, 32 bytes each,
+    // so that a tap is one full 128-byte line per pixel and neighbouring pixels' lines are found in L1 (the v2
+    // scheme).  A warp owns 32 pixels and handles 8 of them per round; the owner lane's taps travel by shuffle.
+    const uint4* sp = src + (size_t)n * H * W * 8;
+    const int lane = tid & 31, q = lane & 3;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int owner = r * 8 + (lane >> 2);
+      WarpTaps u;
+      u.x0 = __shfl_sync(0xffffffffu, t.x0, owner);
+      u.y0 = __shfl_sync(0xffffffffu, t.y0, owner);
+      u.wnw = __shfl_sync(0xffffffffu, t.wnw, owner);
+      u.wne = __shfl_sync(0xffffffffu, t.wne, owner);
+      u.wsw = __shfl_sync(0xffffffffu, t.wsw, owner);
+      u.wse = __shfl_sync(0xffffffffu, t.wse, owner);
+      const bool uvalid = __shfl_sync(0xffffffffu, (int)valid, owner) != 0;
+      const bool okx0 = uvalid && u.x0 >= 0 && u.x0 < W, okx1 = uvalid && u.x0 + 1 >= 0 && u.x0 + 1 < W;
+      const bool oky0 = u.y0 >= 0 && u.y0 < H, oky1 = u.y0 + 1 >= 0 && u.y0 + 1 < H;
+      const uint4* t00 = sp + ((long long)u.y0 * W + u.x0) * 8 + q * 2;         // pixel = 8 uint4
+      const uint4* t10 = t00 + (size_t)W * 8;
+      const int pp = (p & 32) + owner;                     // the pixel's row in the output tile
+      const uint32_t orow = (uint32_t)(b * kWarpWinPitch) + (((uint32_t)pp * 128u) ^ (((uint32_t)pp & 7u) << 4));
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint4 v = warp_blend((okx0 && oky0) ? __ldg(t00 + h) : z, (okx1 && oky0) ? __ldg(t00 + 8 + h) : z,
+                                   (okx0 && oky1) ? __ldg(t10 + h) : z, (okx1 && oky1) ? __ldg(t10 + 8 + h) : z, u);
+        *reinterpret_cast<uint4*>(sgen + (orow ^ (16 * (2 * q + h)))) = v;
+      }
     }
   }
   // ---- the block's output tile leaves by one TMA store (pixels outside the image are clipped)

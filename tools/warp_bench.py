@@ -12,6 +12,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "run":
     dsts = [ops.new_feature(1, h, w, dev) for _ in range(NS)]
     flows = [(torch.randint(-64, 65, (1, 2, h // 8, w // 8), generator=g, device=dev).float() / 4)
              .repeat_interleave(8, 2).repeat_interleave(8, 3).contiguous() for _ in range(NS)]
+    if os.environ.get("WARP_FIELD") == "shifted":     # vector blocks at unaligned positions (reversed P-frame vectors)
+        flows = [torch.roll(f, shifts=(5, 3), dims=(2, 3)).contiguous() for f in flows]
     def run(iters):
         for i in range(iters):
             ops.mv_warp(srcs[i % NS], flows[i % NS], dsts[i % NS])
@@ -21,5 +23,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "run":
     us = s.elapsed_time(e) / 200 * 1e3
     print(f"PNP_WARP_TMA={os.environ.get('PNP_WARP_TMA', '1')}: {us:6.1f} us per 720p warp = {264 * h * w / us * 1e-3:7.1f} GB/s algorithmic (cold L2)")
 else:
-    for v in ("0", "1"):
-        subprocess.run([sys.executable, __file__, "run"], env=dict(os.environ, PNP_WARP_TMA=v))
+    for v, field in (("0", "aligned"), ("1", "aligned"), ("1", "shifted")):
+        print(f"vector blocks {field}: ", end="", flush=True)
+        subprocess.run([sys.executable, __file__, "run"], env=dict(os.environ, PNP_WARP_TMA=v, WARP_FIELD=field))
