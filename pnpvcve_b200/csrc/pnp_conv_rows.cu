@@ -423,10 +423,15 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         if constexpr (!kWrap) {
           umma_bf16_lo(tmem_base + slot_lo * tap_n, a_lo, kDescHiSw128, b_lo, kDescHiSw128, idesc0 + cnt * idesc_step, acc);
         } else {
+          // the two halves of a wrapped window share the A tile: the second MMA takes it from the collector
+          // (tools/umma_collect_bench.cu) instead of fetching its 4 KB from shared memory again
           const int n1 = min(cnt, kAccRing - (int)slot_lo);
-          umma_bf16_lo(tmem_base + slot_lo * tap_n, a_lo, kDescHiSw128, b_lo, kDescHiSw128, idesc0 + n1 * idesc_step, acc);
-          if (cnt > n1)
-            umma_bf16_lo(tmem_base, a_lo, kDescHiSw128, b_lo + n1 * sbb, kDescHiSw128, idesc0 + (cnt - n1) * idesc_step, acc);
+          if (cnt > n1) {
+            umma1_bf16_lo<1>(tmem_base + slot_lo * tap_n, a_lo, b_lo, idesc0 + n1 * idesc_step, acc);
+            umma1_bf16_lo<3>(tmem_base, a_lo, b_lo + n1 * sbb, idesc0 + (cnt - n1) * idesc_step, acc);
+          } else {
+            umma_bf16_lo(tmem_base + slot_lo * tap_n, a_lo, kDescHiSw128, b_lo, kDescHiSw128, idesc0 + n1 * idesc_step, acc);
+          }
         }
       };
 

@@ -72,7 +72,7 @@ def sustained(fn, seconds=1.5):
     return us, clk[len(clk) // 2], max(pw)
 
 
-print(f"PNP_PAIR={os.environ.get('PNP_PAIR', '1')} shape {n}x{h}x{w}, resident CTA pairs {_lib.load().pnp_device_pairs()}")
+print(f"PNP_PAIR={os.environ.get('PNP_PAIR', '0')} shape {n}x{h}x{w}, resident CTA pairs {_lib.load().pnp_device_pairs()}")
 launch_a()
 for name, fn, res in (("plain", plain, out), ("launch A", launch_a, t), ("launch B", launch_b, out), ("A+B", pair, out)):
     us = timeit(fn)
