@@ -15,8 +15,9 @@ Rank 0 prints ONE JSON line:
 
   value        frames/s with the clip already resident in HBM (CUDA events around the steps, NO events inside
                them, max over ranks)
-  e2e          same from pinned HOST buffers through the public host-clip API (driver.ClipStreamer): H2D of
-               every input and D2H of the enhanced frames inside the timed region, overlapped with the kernels
+  e2e          same from pinned HOST buffers through the public host-clip API (driver.enhance_clips on host entries,
+               ClipStreamer underneath): H2D of every input and D2H of the enhanced frames inside the timed region,
+               overlapped with the kernels
   roofline     dominant kernel (block launch A: 3x3 conv + three partition 1x1 convs): algorithmic FLOPs per
                launch / mean launch duration, CUDA events bracketing every 8th such launch in a separate pass of
                the same steps (an upper bound: the bracketed launch loses its programmatic-dependent-launch
@@ -25,6 +26,9 @@ Rank 0 prints ONE JSON line:
   roofline_warp  K1 (HBM bound), algorithmic bytes 264 B/px
   cpu_baseline the oracle port of the reference on this box's host cores, bounded sample
   parity       max-abs error of the CUDA path against that oracle sample (same inputs, tolerance 2e-3)
+  frame_windows  ONE clip of the config cut into one window per GPU (driver.enhance_windows: the reference's max_seq_len
+               windows, each a clip of its own; frames and metrics gathered on every rank): strong scaling of a single
+               clip stream, beside the weak-scaling `value`
 
 --impl reference times the reference's own algorithm (oracle port, PyTorch CPU, all host threads) on
 the same metric.  The oracle is only ever the thing measured beside us, never part of the product.

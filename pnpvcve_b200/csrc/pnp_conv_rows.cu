@@ -918,6 +918,46 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       __syncwarp();
     }
 
+    // kModeLast: `+ lq` (or its x4 bilinear upsampling) of the pixel this thread finishes in row `c`
+    auto lq_fetch = [&](const TileCur& c, float* r) {
+      r[0] = r[1] = r[2] = 0.f;
+      if (!c.valid || half != 0) return;
+      const int x = c.s.strip * kTilePx + row;
+      const int y = PNP_Y(c.s.y_b + c.o);
+      if (x >= p.W) return;
+      if (p.lq_up4) {
+        // base = nn.Upsample(scale_factor=4, mode='bilinear', align_corners=False)(lr), iconvsr_ipb_par.py:41,
+        // 140-141, fused: ATen's source index scale*(dst+0.5)-0.5 clamped at 0, i1 = i0 + (i0 < size-1),
+        // lambda1 = src - i0, row blend of the two column blends
+        const int hl = p.H >> 2, wl = p.W >> 2;
+        const float sy = fmaxf(0.25f * ((float)y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.25f * ((float)x + 0.5f) - 0.5f, 0.f);
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = y0 + (y0 < hl - 1 ? 1 : 0), x1 = x0 + (x0 < wl - 1 ? 1 : 0);
+        const float ly1 = sy - (float)y0, lx1 = sx - (float)x0;
+        const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+        const float* b0 = lq_g + (long long)c.s.n * p.lq_sn + (long long)y0 * p.lq_sy;
+        const float* b1 = lq_g + (long long)c.s.n * p.lq_sn + (long long)y1 * p.lq_sy;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float* c0 = b0 + ch * p.lq_sc;
+          const float* c1 = b1 + ch * p.lq_sc;
+          r[ch] = ly0 * (lx0 * __ldg(c0 + x0) + lx1 * __ldg(c0 + x1)) + ly1 * (lx0 * __ldg(c1 + x0) + lx1 * __ldg(c1 + x1));
+        }
+      } else {
+        const float* lp = lq_g + (long long)c.s.n * p.lq_sn + (long long)y * p.lq_sy + x;
+        r[0] = __ldg(lp);
+        r[1] = __ldg(lp + p.lq_sc);
+        r[2] = __ldg(lp + 2 * p.lq_sc);
+      }
+    };
+    float lq_a[3] = {0.f, 0.f, 0.f}, lq_b[3] = {0.f, 0.f, 0.f};
+    if (last_mode) {
+      lq_fetch(cur, lq_a);
+      TileCur n1 = cur;
+      if (n1.valid) tile_next(n1);
+      lq_fetch(n1, lq_b);
+    }
+
     Ring ior(n_io);
     while (cur.valid) {
       const Segment& s = cur.s;
@@ -932,36 +972,17 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       TileCur nxt = cur;
       tile_next(nxt);
       if (last_mode) {
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-        if (valid && half == 0) {
-          if (p.lq_up4) {
-            // base = nn.Upsample(scale_factor=4, mode='bilinear', align_corners=False)(lr), iconvsr_ipb_par.py:41,
-            // 140-141, fused: ATen's source index scale*(dst+0.5)-0.5 clamped at 0, i1 = i0 + (i0 < size-1),
-            // lambda1 = src - i0, row blend of the two column blends
-            const int hl = p.H >> 2, wl = p.W >> 2;
-            const float sy = fmaxf(0.25f * ((float)y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.25f * ((float)x + 0.5f) - 0.5f, 0.f);
-            const int y0 = (int)sy, x0 = (int)sx;
-            const int y1 = y0 + (y0 < hl - 1 ? 1 : 0), x1 = x0 + (x0 < wl - 1 ? 1 : 0);
-            const float ly1 = sy - (float)y0, lx1 = sx - (float)x0;
-            const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-            const float* b0 = lq_g + (long long)s.n * p.lq_sn + (long long)y0 * p.lq_sy;
-            const float* b1 = lq_g + (long long)s.n * p.lq_sn + (long long)y1 * p.lq_sy;
-            float r[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const float* c0 = b0 + c * p.lq_sc;
-              const float* c1 = b1 + c * p.lq_sc;
-              r[c] = ly0 * (lx0 * __ldg(c0 + x0) + lx1 * __ldg(c0 + x1)) + ly1 * (lx0 * __ldg(c1 + x0) + lx1 * __ldg(c1 + x1));
-            }
-            r0 = r[0];
-            r1 = r[1];
-            r2 = r[2];
-          } else {
-            const float* lp = lq_g + (long long)s.n * p.lq_sn + (long long)y * p.lq_sy + x;
-            r0 = __ldg(lp);
-            r1 = __ldg(lp + p.lq_sc);
-            r2 = __ldg(lp + 2 * p.lq_sc);
-          }
+        // lq values are fetched TWO rows ahead (lq_a: this row, lq_b: the next one): a row of this N=48 conv is only
+        // ~500 MMA cycles, so a global-load latency inside the row's own iteration was the bound of the whole kernel
+        // (46.5 us at 720p for 141 MB of traffic)
+        const float r0 = lq_a[0], r1 = lq_a[1], r2 = lq_a[2];
+        {
+          TileCur n2 = nxt;
+          if (n2.valid) tile_next(n2);
+          lq_a[0] = lq_b[0];
+          lq_a[1] = lq_b[1];
+          lq_a[2] = lq_b[2];
+          lq_fetch(n2, lq_b);
         }
         ewait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> 3) & 1, 9);
         tc_fence_after();

@@ -24,9 +24,7 @@ def clips_per_rank(num_clips, world):
 
 def frame_metrics(out, ref=None):
     """out (n,T,3,H,W) -> (n,T,N_METRICS) fp32 on the same device (no host sync)."""
-    if ref is None:
-        ref = torch.zeros_like(out)
-    d = (out - ref).float()
+    d = out.float() if ref is None else (out - ref).float()
     return torch.stack([d.abs().amax(dim=(2, 3, 4)), (d * d).mean(dim=(2, 3, 4))], dim=-1)
 
 

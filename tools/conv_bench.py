@@ -39,6 +39,22 @@ def launch_a():
     ops.conv3x3(x, war, out=t, bias=bias, par=par, act=ops.PNP_ACT_RELU)
 
 
+wl = ops.new_wpack_rowstack(dev, tap_n=16)
+ops.pack_conv3x3_rowstack(torch.randn((3, 64, 3, 3), generator=g, device=dev) * 0.05, wl, tap_n=16)
+lq = torch.rand((n, 3, h, w), generator=g, device=dev)
+outf = torch.empty((n, 3, h, w), device=dev)
+bl = torch.randn(3, generator=g, device=dev) * 0.1
+lr64 = ops.new_feature(n, h, w, dev, zero=True)
+
+
+def last():
+    ops.conv3x3(x, wl, bias=bl, lq=lq, outf=outf)
+
+
+def im2col():
+    ops.lr_im2col(lq, lr64)
+
+
 def pair():
     launch_a()
     launch_b()
@@ -74,7 +90,8 @@ def sustained(fn, seconds=1.5):
 
 print(f"PNP_PAIR={os.environ.get('PNP_PAIR', '0')} shape {n}x{h}x{w}, resident CTA pairs {_lib.load().pnp_device_pairs()}")
 launch_a()
-for name, fn, res in (("plain", plain, out), ("launch A", launch_a, t), ("launch B", launch_b, out), ("A+B", pair, out)):
+for name, fn, res in (("plain", plain, out), ("launch A", launch_a, t), ("launch B", launch_b, out), ("A+B", pair, out),
+                      ("conv_last", last, outf), ("lr_im2col", im2col, lr64)):
     us = timeit(fn)
     line = f"  {name:9s} {us:7.1f} us   checksum {res.float().abs().sum().item():.6e}"
     if os.environ.get("PNP_SUSTAINED", "0") != "0":
