@@ -55,7 +55,7 @@ int pnp_device_pairs(void);                /* CTA pairs (clusters of two) the co
  * Entry layout by operation (unused fields are ignored):
  *   pnp_conv3x3  : p[0] wpack, p[1] bias, p[2] par, p[3] lq, p[4] outf, p[5] img_off (int64 pairs, see below) or 0;
  *                  i[0..3] first image of src / aux / idt / out inside the buffers the descriptor points to
- *   pnp_mv_warp  : p[0] src, p[1] flow_x, p[2] flow_y, p[3] dst
+ *   pnp_mv_warp  : p[1] flow_x, p[2] flow_y; i[0] / i[3] image of src / dst inside the call's src_pool
  *   pnp_lr_im2col: p[0] lr, p[1] dst
  */
 typedef struct pnp_dyn_entry {
@@ -98,9 +98,9 @@ int pnp_fetch_pinned(void* dst, const void* src_pinned, int64_t bytes, void* str
 int pnp_mv_warp(const void* src, const float* flow_x, const float* flow_y, int64_t flow_row_stride,
                 int64_t flow_image_stride, void* dst, int N, int H, int W, int32_t* dbg_x0,
                 int32_t* dbg_y0, void* stream);
-/* table mode: src / flow_x / flow_y / dst come from the launch table (no debug outputs).  Every entry's src must be an
- * image-aligned address inside the (src_pool_images, H, W, 64) buffer at src_pool: the tap windows are staged by TMA
- * through ONE tensor map of that buffer, built when the launch is recorded. */
+/* table mode: the flow planes and the src / dst IMAGE INDICES inside the (src_pool_images, H, W, 64) buffer at src_pool
+ * come from the launch table (no debug outputs): tap windows and output tiles move by TMA through tensor maps of that
+ * buffer, built when the launch is recorded. */
 int pnp_mv_warp_dyn(const pnp_dyn_ref* dyn, const void* src_pool, int src_pool_images, int64_t flow_row_stride,
                     int64_t flow_image_stride, int N, int H, int W, void* stream);
 

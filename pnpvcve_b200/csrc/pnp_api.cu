@@ -271,7 +271,7 @@ int pnp_mv_warp(const void* src, const float* flow_x, const float* flow_y, int64
                 int64_t flow_image_stride, void* dst, int N, int H, int W, int32_t* dbg_x0, int32_t* dbg_y0,
                 void* stream) {
   if (!src || !flow_x || !flow_y || !dst) return fail(PNP_ERR_ARG, "pnp_mv_warp: null pointer");
-  if (N <= 0 || H <= 0 || W <= 0) return fail(PNP_ERR_ARG, "pnp_mv_warp: bad shape");
+  if (N <= 0 || H < 10 || W < 10) return fail(PNP_ERR_ARG, "pnp_mv_warp: bad shape (images of at least 10 x 10 pixels)");
   if (!aligned16(src) || !aligned16(dst) || src == dst)
     return fail(PNP_ERR_ARG, "pnp_mv_warp: src/dst must be distinct 16-byte aligned buffers");
   if ((dbg_x0 == nullptr) != (dbg_y0 == nullptr) || (dbg_x0 && N != 1))
@@ -290,7 +290,7 @@ int pnp_mv_warp(const void* src, const float* flow_x, const float* flow_y, int64
 int pnp_mv_warp_dyn(const pnp_dyn_ref* dyn, const void* src_pool, int src_pool_images, int64_t flow_row_stride,
                     int64_t flow_image_stride, int N, int H, int W, void* stream) {
   if (!dyn || !dyn->table || !dyn->step) return fail(PNP_ERR_ARG, "pnp_mv_warp_dyn: null launch table");
-  if (N <= 0 || H <= 0 || W <= 0) return fail(PNP_ERR_ARG, "pnp_mv_warp_dyn: bad shape");
+  if (N <= 0 || H < 10 || W < 10) return fail(PNP_ERR_ARG, "pnp_mv_warp_dyn: bad shape (images of at least 10 x 10 pixels)");
   if (!src_pool || src_pool_images < N || !aligned16(src_pool))
     return fail(PNP_ERR_ARG, "pnp_mv_warp_dyn: src_pool must be the 16-byte aligned buffer every table entry's src lies in");
   DeviceInfo* d;

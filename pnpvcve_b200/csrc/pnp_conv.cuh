@@ -14,7 +14,7 @@ constexpr int kWChunkBytes = 8192;           // one 64(N) x 64(K) bf16 weight bl
 constexpr int kRowsThreads = 352;            // warp0 TMA producer, warp1 MMA issuer, warps2-9 epilogue, warp10 barrier scout
 constexpr int kEpilogueWarps = 8;
 constexpr int kMaxASlots = 8;
-constexpr int kMaxIoSlots = 4;
+constexpr int kMaxIoSlots = 6;
 constexpr int kTmemCols = 512;
 
 enum ConvMode { kModeBf16 = 0, kModeLast = 1 };

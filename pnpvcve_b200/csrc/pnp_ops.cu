@@ -107,14 +107,16 @@ mv_warp_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant
   __shared__ uint64_t bar[kWarpBlocks];
   __shared__ int box[kWarpBlocks][4];                    // min x0, max x0, min y0, max y0 of the block's valid pixels
   int img_src = 0, img_dst = 0;                          // first image inside the tensor maps
-  if (const DynEntry* e = dyn.entry()) {                 // table mode: p{src, flow_x, flow_y, dst}; both maps span the pool
-    src = reinterpret_cast<const uint4*>(e->p[0]);
+  if (const DynEntry* e = dyn.entry()) {
+    // table mode: p{-, flow_x, flow_y, -}, i{src image, -, -, dst image} inside the pool both maps span.  (Image
+    // indices, not pointers: turning a pointer into an image index costs every thread two 64-bit divisions -- and this
+    // kernel is bound by instruction issue and latency, not by bytes, once the SM clock is power-capped.)
     flow_x = reinterpret_cast<const float*>(e->p[1]);
     flow_y = reinterpret_cast<const float*>(e->p[2]);
-    dst = reinterpret_cast<uint4*>(e->p[3]);
-    const long long img_bytes = (long long)H * W * 128;
-    img_src = (int)((reinterpret_cast<const uint8_t*>(src) - pool_base) / img_bytes);
-    img_dst = (int)((reinterpret_cast<const uint8_t*>(dst) - pool_base) / img_bytes);
+    img_src = e->i[0];
+    img_dst = e->i[3];
+    src = reinterpret_cast<const uint4*>(pool_base + (long long)img_src * H * W * 128);
+    dst = reinterpret_cast<uint4*>(const_cast<uint8_t*>(pool_base) + (long long)img_dst * H * W * 128);
   }
   const uint32_t raw = smem_u32(warp_smem_raw);
   const uint32_t sbase = (raw + 1023u) & ~1023u;

@@ -236,7 +236,25 @@ class ClipStreamer:
         self.copy_in = self.copy_out = True
 
     def _chunks(self, t):
-        return [(a, min(a + self.chunk, t)) for a in range(0, t, self.chunk)]
+        """Frame ranges [a, b) in ascending order.  The clip's LAST frames are the first the kernels read (backward-time
+        pass) and the last they deliver, so the chunks there are short (2, 4, 8 frames, then ``chunk``): the first
+        kernel waits for 2 frames instead of ``chunk``, and only 2 frames' download is left when the last one is done."""
+        out, b, size = [], t, min(2, self.chunk)
+        while b > 0:
+            a = max(0, b - size)
+            out.append((a, b))
+            b = a
+            size = min(self.chunk, size * 2)
+        return out[::-1]
+
+    @staticmethod
+    def _chunk_of(chunks, t):
+        """frame index -> its chunk"""
+        owner = [None] * t
+        for c in chunks:
+            for i in range(c[0], c[1]):
+                owner[i] = c
+        return owner
 
     def upload(self, host_clip):
         """Enqueue the upload of one clip; returns a ticket for ``run``."""
@@ -273,16 +291,17 @@ class ClipStreamer:
         main = torch.cuda.current_stream(self.dev)
         t, dclip, events = ticket["t"], ticket["dclip"], ticket["events"]
         chunks = self._chunks(t)
+        owner = self._chunk_of(chunks, t)
         waited = set()
 
         def frame_ready(i):
-            c = chunks[i // self.chunk]
+            c = owner[i]
             if c not in waited:
                 waited.add(c)
                 main.wait_event(events[c])
 
         def frame_done(i, out):
-            a, b = chunks[i // self.chunk]
+            a, b = owner[i]
             if i == b - 1:
                 ev = torch.cuda.Event()
                 ev.record(main)

@@ -457,7 +457,7 @@ class BaeEngine:
             cur = feats(frame)
             if v not in ("b_last", "f_first"):
                 kidx = np.where(steps < t, bk[frame], fk[frame])
-                put(sel, node, p=(pool_ptr + feats(kidx) * img, flow_x, flow_x + plane, pool_ptr + work["kw"] * img))
+                put(sel, node, p=(0, flow_x, flow_x + plane, 0), i=(feats(kidx), 0, 0, work["kw"]))
                 node += 1
             in_bias = W["bwd_in_bias"] if bwd else W["fwd_in_bias"]
             if v == "b_last":       # zeros for key_warp / neighbour (:69-70)

@@ -118,6 +118,8 @@ def test_mv_warp_rejects_bad_arguments(dev):
         ops.mv_warp(a, torch.zeros((2, 60, 64), device=dev), ops.new_feature(1, 64, 64, dev))
     with pytest.raises(_lib.PnpError):
         ops.mv_warp(a, torch.zeros((2, 64, 64), device=dev), a)      # aliasing
+    with pytest.raises(_lib.PnpError):                               # smaller than one staged tap window
+        ops.mv_warp(ops.new_feature(1, 8, 64, dev), torch.zeros((2, 8, 64), device=dev), ops.new_feature(1, 8, 64, dev))
 
 
 # ------------------------------------------------------------------ conv
@@ -480,6 +482,22 @@ def test_conv_pair_form_is_bit_identical_to_single_cta_form(dev, n, h, w, mode):
         lib.pnp_set_pair_mode(prev)
 
 
+def test_fetch_pinned_copies_without_the_copy_engine(dev):
+    """pnp_fetch_pinned: stream-ordered device copy of a PINNED host buffer by a kernel (the launch table's way up);
+    pageable memory and odd sizes are refused."""
+    src = torch.arange(3 * 24 * 8, dtype=torch.int64).view(3, 24, 8).pin_memory()
+    dst = torch.zeros((3, 24, 8), dtype=torch.int64, device=dev)
+    ops.fetch_pinned(dst, src)
+    torch.cuda.synchronize()
+    assert torch.equal(dst.cpu(), src)
+    with pytest.raises(ValueError):
+        ops.fetch_pinned(dst, torch.zeros((3, 24, 8), dtype=torch.int64))            # not pinned
+    lib = _lib.load()
+    assert lib.pnp_fetch_pinned(dst.data_ptr(), src.data_ptr(), 24, None) == -1      # not a multiple of 16 bytes
+    pageable = torch.zeros(64, dtype=torch.int64)
+    assert lib.pnp_fetch_pinned(dst.data_ptr(), pageable.data_ptr(), 64, None) != 0
+
+
 def test_table_mode_launches_equal_static_launches(dev):
     """Launch-table mode (operands from a device-resident table selected by a step word) of the warp, the LR im2col and
     the conv, eagerly and replayed from a captured graph: bit-identical to the static launches."""
@@ -508,8 +526,9 @@ def test_table_mode_launches_equal_static_launches(dev):
     stride = 4
     table = torch.zeros((frames, stride, 8), dtype=torch.int64)
     for s in range(frames):
-        table[s, 0, :4] = torch.tensor([pool.data_ptr() + s * n * img, flow[s, 0, 0].data_ptr(), flow[s, 0, 1].data_ptr(),
-                                        pool.data_ptr() + kw_f * img])
+        table[s, 0, :4] = torch.tensor([0, flow[s, 0, 0].data_ptr(), flow[s, 0, 1].data_ptr(), 0])
+        table[s, 0, 6] = s * n                   # warp: src image | - << 32
+        table[s, 0, 7] = kw_f << 32              #       - | dst image << 32
         table[s, 1, :2] = torch.tensor([wp.data_ptr(), bias.data_ptr()])
         table[s, 1, 6] = kw_f                    # src image | aux image << 32
         table[s, 1, 7] = idt_f | (out_f << 32)   # idt image | out image << 32
