@@ -105,7 +105,7 @@ mv_warp_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant
                int* __restrict__ dbg_y0, const DynRef dyn, const uint8_t* pool_base, int use_tma) {
   extern __shared__ uint8_t warp_smem_raw[];
   __shared__ uint64_t bar[kWarpBlocks];
-  __shared__ int box[kWarpBlocks][4];                    // min x0, max x0, min y0, max y0 of the block's valid pixels
+  __shared__ int part[kWarpBlocks][2][4];                // per block and warp: min x0, max x0, min y0, max y0 of the valid pixels
   int img_src = 0, img_dst = 0;                          // first image inside the tensor maps
   if (const DynEntry* e = dyn.entry()) {
     // table mode: p{-, flow_x, flow_y, -}, i{src image, -, -, dst image} inside the pool both maps span.  (Image
@@ -124,11 +124,7 @@ mv_warp_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant
   const int tid = threadIdx.x;
   const int b = tid >> 6;                                // this thread's 8 x 8 block (two warps per block)
   const int col = tid & 7, row = (tid >> 3) & 7;         // its pixel inside the block
-  if (tid < kWarpBlocks) {
-    mbar_init(smem_u32(&bar[tid]), 1);
-    box[tid][0] = box[tid][2] = 0x7fffffff;
-    box[tid][1] = box[tid][3] = -0x7fffffff;
-  }
+  if (tid < kWarpBlocks) mbar_init(smem_u32(&bar[tid]), 1);
   if (tid == 0) {
     mbar_fence_init();
     tma_prefetch_desc(&tm_src);
@@ -160,18 +156,25 @@ mv_warp_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant
     const int mxx = __reduce_max_sync(0xffffffffu, valid ? t.x0 : -0x7fffffff);
     const int mny = __reduce_min_sync(0xffffffffu, valid ? t.y0 : 0x7fffffff);
     const int mxy = __reduce_max_sync(0xffffffffu, valid ? t.y0 : -0x7fffffff);
-    if ((tid & 31) == 0 && mnx <= mxx) {                 // two warps per block
-      atomicMin(&box[b][0], mnx);
-      atomicMax(&box[b][1], mxx);
-      atomicMin(&box[b][2], mny);
-      atomicMax(&box[b][3], mxy);
+    if ((tid & 31) == 0) {                               // two warps per block: plain stores, combined behind the barrier
+      int* pw = part[b][(tid >> 5) & 1];
+      pw[0] = mnx;
+      pw[1] = mxx;
+      pw[2] = mny;
+      pw[3] = mxy;
     }
   }
   __syncthreads();
   griddep_wait();                                        // the source features come from the previous kernel
-  const int bx0 = box[b][0], by0 = box[b][2];
   const bool any = bx < W && by < H;                     // the block has pixels inside the image
-  const bool staged = use_tma && any && box[b][1] + 2 - bx0 <= kWarpWin && box[b][3] + 2 - by0 <= kWarpWin;
+  int bx0 = 0, by0 = 0;
+  bool staged = false;
+  if (use_tma && any) {
+    bx0 = min(part[b][0][0], part[b][1][0]);
+    by0 = min(part[b][0][2], part[b][1][2]);
+    const int bx1 = max(part[b][0][1], part[b][1][1]), by1 = max(part[b][0][3], part[b][1][3]);
+    staged = bx0 <= bx1 && bx1 + 2 - bx0 <= kWarpWin && by1 + 2 - by0 <= kWarpWin;
+  }
   // ---- one thread per block: stage its tap window (taps x0..x0+1, y0..y0+1 of every pixel) if it fits
   if (staged && (tid & 63) == 0) {
     mbar_arrive_expect_tx(smem_u32(&bar[b]), kWarpWinBytes);
