@@ -70,11 +70,12 @@ def enhance_clips(net, clips, rank=0, world=1, refs=None, gts=None, crop_border=
     from .synthetic import generator_args
     from . import metrics as _metrics
     mine = shard_clips(len(clips), rank, world)
-    shape_of = next(c for c in clips if c is not None)["lq"].shape
+    first = next(c for c in clips if c is not None)["lq"]
+    shape_of = first.shape
     n, t = shape_of[:2]
-    host = bool(mine) and not clips[mine[0]]["lq"].is_cuda
+    host = not first.is_cuda                 # (a rank without work of its own still takes part in the gather, on its GPU)
     dev = torch.device(device) if device is not None else \
-        (torch.device("cuda", torch.cuda.current_device()) if host else next(c for c in clips if c is not None)["lq"].device)
+        (torch.device("cuda", torch.cuda.current_device()) if host else first.device)
     outs, mets = [], []
 
     def measure(c, out):
@@ -84,7 +85,7 @@ def enhance_clips(net, clips, rank=0, world=1, refs=None, gts=None, crop_border=
             m = torch.cat([m, q["psnr"].float()[..., None], q["ssim"].float()[..., None]], dim=-1)
         mets.append(m)
 
-    if host:
+    if host and mine:
         up = 4 if getattr(net, "vsr", False) else 1
         pinned = {c: {k: (v if v.is_pinned() else v.pin_memory()) for k, v in clips[c].items()} for c in mine}
         streamer = ClipStreamer(net, dev, chunk=chunk)
