@@ -148,26 +148,52 @@ def clip_window(clip, a, b, overlap=0):
 
 
 @torch.no_grad()
-def enhance_windows(net, clips, window, rank=0, world=1, overlap=0, refs=None, gather_output=False, group=None):
+def enhance_windows(net, clips, window, rank=0, world=1, overlap=0, refs=None, gather_output=False, group=None,
+                    device=None, chunk=10):
     """Frame-window sharding (north_star: "sharding independent clips or frame windows per GPU"): the windows of
     ``clips`` (equally shaped (1,T,...) clip dicts) are dealt to the ranks round robin and enhanced independently.
+    HOST-resident clips stream their windows through ``ClipStreamer`` on ``device`` (only a rank's own windows ever
+    reach its GPU), device-resident clips are sliced in place.
 
-    Returns (outs, metrics): outs = {(clip, a, b): (1, b-a, 3, H, W) frames} of this rank's windows -- or, with
-    ``gather_output``, the complete (num_clips, T, 3, H, W) result on every rank (one fixed-shape all_gather of frames
-    over NVLink) --, metrics = (num_clips, T, N_METRICS) of ALL frames on every rank (one fixed-shape all_gather).  No
-    collective touches the data path of a window."""
+    Returns (outs, metrics): outs = {(clip, a, b): (1, b-a, 3, H, W) frames} of this rank's windows (device tensors)
+    -- or, with ``gather_output``, the complete (num_clips, T, 3, H, W) result on every rank (one fixed-shape all_gather
+    of frames over NVLink) --, metrics = (num_clips, T, N_METRICS) of ALL frames on every rank (one fixed-shape
+    all_gather).  No collective touches the data path of a window."""
     from .synthetic import generator_args
     num_clips = len(clips)
     t = clips[0]["lq"].shape[1]
-    dev = clips[0]["lq"].device
+    # host-resident clips are streamed when `net` is the generator (anything else -- a stand-in callable in the CPU tests
+    # of the sharding logic -- is simply called on the tensors where they are)
+    host = not clips[0]["lq"].is_cuda and hasattr(net, "forward_streamed")
+    dev = torch.device(device) if device is not None else \
+        (torch.device("cuda", torch.cuda.current_device()) if host else clips[0]["lq"].device)
     mine = shard_windows(num_clips, t, window, rank, world)
     outs = {}
     local = torch.full((num_clips, t, N_METRICS), float("nan"), dtype=torch.float32, device=dev)
-    for c, a, b in mine:
-        win, lo, hi = clip_window(clips[c], a, b, overlap)
-        out = net(*generator_args({k: v.contiguous() for k, v in win.items()}))[:, lo:hi]
+    streamer, ticket, wins = None, None, []
+    if host and mine:
+        up = 4 if getattr(net, "vsr", False) else 1
+        streamer = ClipStreamer(net, dev, chunk=chunk)
+        for c, a, b in mine:          # contiguous pinned copies of this rank's windows (the clip itself may be pageable)
+            win, lo, hi = clip_window(clips[c], a, b, overlap)
+            wins.append(({k: v.contiguous().pin_memory() for k, v in win.items()}, lo, hi))
+        ticket = streamer.upload(wins[0][0])
+    for i, (c, a, b) in enumerate(mine):
+        if host:
+            hwin, lo, hi = wins[i]
+            frames_w = hwin["lq"].shape[1]
+            dst = torch.empty((1, frames_w, 3, hwin["lq"].shape[-2] * up, hwin["lq"].shape[-1] * up),
+                              dtype=torch.float32).pin_memory()
+            full = streamer.run(ticket, dst)
+            ticket = streamer.upload(wins[i + 1][0]) if i + 1 < len(mine) else None
+            out = full[:, lo:hi].clone()            # (the streamer recycles its device buffer two windows later)
+        else:
+            win, lo, hi = clip_window(clips[c], a, b, overlap)
+            out = net(*generator_args({k: v.contiguous() for k, v in win.items()}))[:, lo:hi]
         outs[(c, a, b)] = out
-        local[c, a:b] = frame_metrics(out, None if refs is None else refs[c][:, a:b])[0]
+        local[c, a:b] = frame_metrics(out, None if refs is None else refs[c][:, a:b].to(dev))[0]
+    if streamer is not None:
+        streamer.finish()
     metrics = merge_sharded(local, world, group)
     if not gather_output:
         return outs, metrics

@@ -226,6 +226,9 @@ def test_frame_windows_match_oracle_on_the_same_windows(dev):
     seam2 = (lapped.cpu() - uncut).abs().max().item()
     print(f"seam error vs the uncut clip: {seam0:.3e} without overlap, {seam2:.3e} with 2 frames of overlap")
     assert seam2 <= seam0 + 1e-6
+    # host-resident clip: the windows stream through ClipStreamer, same frames
+    hosted, met_h = driver.enhance_windows(net, [clip], 4, overlap=2, gather_output=True, device=dev, chunk=3)
+    assert torch.equal(hosted, lapped) and met_h.shape == met.shape
 
 
 def test_enhance_clips_streams_host_clips(dev):
