@@ -29,6 +29,8 @@ def build(force=False, verbose=False):
         flags.append("-DPNP_DIAG")
     if os.environ.get("PNP_WARP_BLOCKS"):          # tile-width sweep of the warp kernel (tools/warp_bench.py)
         flags.append("-DPNP_WARP_BLOCKS=" + os.environ["PNP_WARP_BLOCKS"])
+    if os.environ.get("PNP_STEP_RING_LOG2"):       # 3 = the 8-barrier step ring that could dead-lock (validation only)
+        flags.append("-DPNP_STEP_RING_LOG2=" + os.environ["PNP_STEP_RING_LOG2"])
     if os.environ.get("PNP_SPIN_LIMIT"):           # stress runs: trap a stuck pipeline after fewer polls
         flags.append("-DPNP_SPIN_LIMIT=" + os.environ["PNP_SPIN_LIMIT"])
     cmd = [nvcc] + flags + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]

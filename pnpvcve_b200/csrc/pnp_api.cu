@@ -455,7 +455,8 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   if (!c->src || (!table && !c->wpack)) return fail(PNP_ERR_ARG, "pnp_conv3x3: null src/wpack");
   if (table && (!c->dyn.step || c->dyn.node < 0 || c->dyn.stride <= c->dyn.node))
     return fail(PNP_ERR_ARG, "pnp_conv3x3: bad launch-table reference");
-  if (c->N < 1 || c->H < 1 || c->W < 1) return fail(PNP_ERR_ARG, "pnp_conv3x3: bad shape");
+  // (H >= 8: the bound on commits in flight per accumulator ring, pnp_conv_rows.cu kStepRing, assumes it)
+  if (c->N < 1 || c->H < 8 || c->W < 1) return fail(PNP_ERR_ARG, "pnp_conv3x3: bad shape (at least 8 rows)");
   const bool last = (c->mode == PNP_CONV_LAST);
   if (c->mode != PNP_CONV_BF16 && !last) return fail(PNP_ERR_ARG, "pnp_conv3x3: bad mode");
   const bool par = c->par != nullptr;

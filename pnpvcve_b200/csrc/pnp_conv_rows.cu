@@ -45,7 +45,19 @@ namespace pnp {
 namespace {
 
 constexpr int kAccRingMax = 8;   // output-row accumulators in TMEM (8 x 64 columns; 5 with kPar)
-constexpr int kStepRing = 8;     // step-completion barriers
+// Step-completion barriers.  A barrier is re-used every kStepRing steps, so the issuing thread must never commit step
+// s + kStepRing before the slowest waiter has looked at step s.  What holds it back is the ACCUMULATOR ring -- it can
+// be at most 8 output rows (5 with kPar) ahead of the epilogue -- but steps are not rows: two rows can complete with one
+// step (the last two of a segment that ends at the image bottom) and a segment can begin with a step that completes no
+// row, so 9 rows in flight span up to 12 steps (H >= 8).  With 8 barriers the CTA whose range ends a few rows into a new
+// column (at 720p: CTA 102, 42 + 7 rows) could commit step 50 on the barrier of step 42 while its epilogue was a full
+// ring behind and still about to wait for step 42: the phase flips twice, the wait never returns.  Seen once in ~10^6
+// launches, reproduced at will under compute-sanitizer (which slows the epilogue); 16 barriers close it.
+#ifndef PNP_STEP_RING_LOG2
+#define PNP_STEP_RING_LOG2 4     // (3 re-creates the dead-lock for the regression test's own validation)
+#endif
+constexpr int kStepShift = PNP_STEP_RING_LOG2;
+constexpr int kStepRing = 1 << kStepShift;
 constexpr int kParCol = 320;     // TMEM column of the partition 1x1 accumulators (3 x 64)
 
 struct RowsLayout {
@@ -305,7 +317,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
           if (sc >= (uint32_t)s_a) {       // slot last used by step sc - s_a
             // with deferred 1x1 MMAs the row of step ps is still read during step ps + 1
             const uint32_t ps = sc - s_a + (par_defer ? 1u : 0u);
-            pwait(smem_u32(&misc->step_done[ps & (kStepRing - 1)]), (ps >> 3) & 1, 1);
+            pwait(smem_u32(&misc->step_done[ps & (kStepRing - 1)]), (ps >> kStepShift) & 1, 1);
           }
           const uint32_t fb = smem_u32(&misc->a_full[ar.slot]);
           if (kPair) {
@@ -328,7 +340,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
               const uint32_t as = ord & 1;
               if (ord >= 2) {
                 const uint32_t ps = aux_step[as];
-                pwait(smem_u32(&misc->step_done[ps & (kStepRing - 1)]), (ps >> 3) & 1, 2);
+                pwait(smem_u32(&misc->step_done[ps & (kStepRing - 1)]), (ps >> kStepShift) & 1, 2);
               }
               aux_step[as] = sc;           // consumed in this very step (centre row)
               const uint32_t ab = smem_u32(&misc->aux_full[as]);
@@ -816,7 +828,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
             }
             __syncwarp();
           }
-          mbar_wait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> 3) & 1, 9);
+          mbar_wait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> kStepShift) & 1, 9);
           tc_fence_after();
           float v[64];
 #pragma unroll
@@ -984,7 +996,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
           lq_a[2] = lq_b[2];
           lq_fetch(n2, lq_b);
         }
-        ewait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> 3) & 1, 9);
+        ewait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> kStepShift) & 1, 9);
         tc_fence_after();
         float v[16];
         if (half == 0) {
@@ -1035,7 +1047,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
         // it), whereas that step's own step_done commit is deferred into the following step
         ewait(smem_u32(&misc->par_done), (ord + 1) & 1, 11);
       } else {
-        ewait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> 3) & 1, 9);
+        ewait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> kStepShift) & 1, 9);
       }
       tc_fence_after();
       if (tr) p.trace[ord * 8 + 3] = clock64();

@@ -498,6 +498,26 @@ def test_fetch_pinned_copies_without_the_copy_engine(dev):
     assert lib.pnp_fetch_pinned(dst.data_ptr(), pageable.data_ptr(), 64, None) != 0
 
 
+def test_conv_720p_survives_a_slow_epilogue(dev):
+    """Regression for the step-barrier ABA (pnp_conv_rows.cu, kStepRing): with 8 step barriers the CTA whose tile range
+    ends a few rows into a new column (720p: CTA 102) dead-locked whenever its epilogue fell a full accumulator ring
+    behind the MMA thread -- once in ~10^6 launches natively, every time under compute-sanitizer, which slows the
+    epilogue warps but not the tensor pipe.  Runs the 720p conv variants (both kernel forms) under memcheck: must pass,
+    with no memory errors."""
+    import shutil
+    import subprocess
+    import sys
+    tool = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not os.path.exists(tool):
+        pytest.skip("compute-sanitizer not installed")
+    cmd = [tool, "--tool", "memcheck", "--error-exitcode", "9", sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu",
+           "-x", "-q", "-k", "pair_form and 720"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    tail = (res.stdout + res.stderr)[-1500:]
+    assert res.returncode == 0, tail
+    assert "1 passed" in res.stdout and "ERROR SUMMARY: 0 errors" in res.stdout + res.stderr, tail
+
+
 def test_table_mode_launches_equal_static_launches(dev):
     """Launch-table mode (operands from a device-resident table selected by a step word) of the warp, the LR im2col and
     the conv, eagerly and replayed from a captured graph: bit-identical to the static launches."""
