@@ -272,3 +272,18 @@ def test_frame_window_sharding_world2(num_clips, t, window, overlap):
         assert torch.equal(full, exp)
         assert met.shape == (num_clips, t, driver.N_METRICS) and not torch.isnan(met).any()
         assert torch.equal(met[..., 0], exp.abs().amax(dim=(2, 3, 4)))
+
+
+def test_clip_streamer_chunk_layout():
+    """Chunks cover the clip in order; the clip's last frames -- read first by the backward-time pass, delivered last by
+    the forward-time pass -- come in short chunks (2, 4, 8, then `chunk` frames)."""
+    st = driver.ClipStreamer.__new__(driver.ClipStreamer)
+    for t, chunk in ((100, 10), (7, 3), (13, 5), (1, 10), (2, 1), (40, 10)):
+        st.chunk = chunk
+        ch = st._chunks(t)
+        assert ch[0][0] == 0 and ch[-1][1] == t and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+        assert all(0 < b - a <= max(chunk, 1) for a, b in ch)
+        owner = st._chunk_of(ch, t)
+        assert all(owner[i][0] <= i < owner[i][1] for i in range(t))
+    st.chunk = 10
+    assert st._chunks(100)[-3:] == [(86, 94), (94, 98), (98, 100)]
