@@ -67,7 +67,9 @@ int device_info(DeviceInfo** out) {
 // default build; the what-if / trace knobs that make results wrong or write through a pointer taken from the
 // environment exist only in PNP_DIAG builds (tools/).
 struct Knobs {
-  int l2_hints = 0;        // PNP_L2_HINTS=1: evict_first on launch B's dead reads (measured: no effect)
+  int l2_hints = 0;        // PNP_L2_HINTS=1: evict_first on launch B's dead reads (measured: no effect); 2: residency scheme --
+                           // launch A keeps x (evict_last) and streams t (evict_first), launch B streams t and x and
+                           // keeps its output for the next launch A; 3: launch A keeps t instead (B's source)
   int par_split = 1;       // PNP_PAR_SPLIT=0: single-role epilogue of block launch A
   int warp_tma = 1;        // PNP_WARP_TMA=0: the warp takes its taps by global gathers only (A/B timing)
   int pair = 0;            // PNP_PAIR=1: CTA-pair (cta_group::2) form of the conv kernel where the shape allows it; 2: also
@@ -81,7 +83,7 @@ struct Knobs {
 const Knobs& knobs() {
   static const Knobs k = []() {
     Knobs v;
-    if (const char* e = getenv("PNP_L2_HINTS")) v.l2_hints = atoi(e) != 0;
+    if (const char* e = getenv("PNP_L2_HINTS")) v.l2_hints = atoi(e);
     if (const char* e = getenv("PNP_PAR_SPLIT")) v.par_split = atoi(e) != 0;
     if (const char* e = getenv("PNP_PAIR")) v.pair = atoi(e);
     if (const char* e = getenv("PNP_WARP_TMA")) v.warp_tma = atoi(e) != 0;
@@ -570,7 +572,13 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   p.lq_up4 = c->lq_up4 ? 1 : 0;
   p.par_sparse = (par && c->par_sparse) ? 1 : 0;
   // block launch B (identity, bottom-up) reads t and x for the last time
-  p.l2_dead_reads = (kn.l2_hints && c->idt && c->flip_y) ? 1 : 0;
+  if (kn.l2_hints && c->idt && c->flip_y) {            // launch B
+    p.l2_src = p.l2_idt = 1;
+    if (kn.l2_hints >= 2) p.l2_out = 2;
+  } else if (kn.l2_hints >= 2 && par) {                // launch A
+    p.l2_src = kn.l2_hints == 2 ? 2 : 1;
+    p.l2_out = kn.l2_hints == 2 ? 1 : 2;
+  }
   p.par_split = (par && kn.par_split) ? 1 : 0;
   p.debug_skip = kn.debug_skip;
   p.trace = kn.trace;

@@ -66,7 +66,8 @@ struct ConvParams {
   int act;
   int mode;
   int flip_y;           // walk the image bottom-up (weights packed with ky mirrored)
-  int l2_dead_reads;    // src and identity are dead after this launch -> L2 evict_first on their loads
+  int l2_src, l2_idt, l2_out;   // L2 eviction policy of the src / identity loads and the output stores:
+                        // 0 default, 1 evict_first (dead after this access), 2 evict_last (the next launch reads it)
   int par_split;        // partition variant: dedicated reader warps for the 1x1 accumulator region
   int par_sparse;       // partition blend: last non-zero class only, / 255 (the reference's sparse_val eval path)
   int lq_up4;           // kModeLast: lq is the (H/4, W/4) frame, the epilogue adds its x4 bilinear upsampling

@@ -306,7 +306,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
     // ============================================================ TMA producer (one elected lane)
     if (elect_one()) {
       if (!p.w_stable) load_weights();
-      const uint64_t pol_dead = l2_policy_evict_first();
+      const uint64_t pol_src = p.l2_src == 2 ? l2_policy_evict_last() : l2_policy_evict_first();
       Ring ar(s_a);
       uint32_t sc = 0, ord = 0;            // step counter, output-row ordinal
       uint32_t aux_step[2] = {0, 0};       // step in which each aux slot was last consumed
@@ -330,8 +330,8 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
             mbar_arrive(fb);
           } else {
             mbar_arrive_expect_tx(fb, kRowBytes);
-            if (p.l2_dead_reads)
-              tma_load_4d_hint(a_smem + ar.slot * kASlotBytes, &p.tm_src, fb, 0, x0 - 1, PNP_Y(s.y_b + j), s.n + src_f, pol_dead);
+            if (p.l2_src)
+              tma_load_4d_hint(a_smem + ar.slot * kASlotBytes, &p.tm_src, fb, 0, x0 - 1, PNP_Y(s.y_b + j), s.n + src_f, pol_src);
             else
               tma_load_4d(a_smem + ar.slot * kASlotBytes, &p.tm_src, fb, 0, x0 - 1, PNP_Y(s.y_b + j), s.n + src_f);
           }
@@ -872,7 +872,13 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
           named_bar_sync(2, 128);
           if (store_warp) {
             if (elect_one()) {
-              if (!phantom(s)) tma_store_4d(&p.tm_out, io_smem + ior.slot * kTileBytes, 0, s.strip * kTilePx, y, s.n + out_f);
+              if (!phantom(s)) {
+                if (p.l2_out)
+                  tma_store_4d_hint(&p.tm_out, io_smem + ior.slot * kTileBytes, 0, s.strip * kTilePx, y, s.n + out_f,
+                                    p.l2_out == 2 ? l2_policy_evict_last() : l2_policy_evict_first());
+                else
+                  tma_store_4d(&p.tm_out, io_smem + ior.slot * kTileBytes, 0, s.strip * kTilePx, y, s.n + out_f);
+              }
               tma_store_commit();
             }
             __syncwarp();
@@ -913,9 +919,9 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
     auto load_id = [&](const TileCur& c, uint32_t slot) {
       const uint32_t ib = smem_u32(&misc->id_full[slot]);
       mbar_arrive_expect_tx(ib, kTileBytes);
-      if (p.l2_dead_reads)
+      if (p.l2_idt)
         tma_load_4d_hint(io_smem + slot * kTileBytes, &p.tm_id, ib, 0, c.s.strip * kTilePx, PNP_Y(c.s.y_b + c.o), c.s.n + idt_f,
-                         l2_policy_evict_first());
+                         p.l2_idt == 2 ? l2_policy_evict_last() : l2_policy_evict_first());
       else
         tma_load_4d(io_smem + slot * kTileBytes, &p.tm_id, ib, 0, c.s.strip * kTilePx, PNP_Y(c.s.y_b + c.o), c.s.n + idt_f);
     };
@@ -1126,7 +1132,13 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       if (store_warp) {
         if (elect_one()) {
           if (!PNP_DBG(2)) {
-            if (!phantom(s)) tma_store_4d(&p.tm_out, io_smem + s_io * kTileBytes, 0, s.strip * kTilePx, y, s.n + out_f);
+            if (!phantom(s)) {
+              if (p.l2_out)
+                tma_store_4d_hint(&p.tm_out, io_smem + s_io * kTileBytes, 0, s.strip * kTilePx, y, s.n + out_f,
+                                  p.l2_out == 2 ? l2_policy_evict_last() : l2_policy_evict_first());
+              else
+                tma_store_4d(&p.tm_out, io_smem + s_io * kTileBytes, 0, s.strip * kTilePx, y, s.n + out_f);
+            }
             tma_store_commit();
           }
         }
