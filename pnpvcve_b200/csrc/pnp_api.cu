@@ -607,9 +607,9 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   if (c->idt && p.n_io < 3)
     return fail(PNP_ERR_RESOURCE, "pnp_conv3x3: idt needs 3 staging slots (drop aux)");
   p.s_a = (int)slots;
-  if (kn.rings_nio >= 2 && kn.rings_nio <= pnp::kMaxIoSlots && kn.rings_sa >= 4 && kn.rings_sa <= pnp::kMaxASlots &&
+  if (kn.rings_nio >= 2 && kn.rings_nio <= pnp::kMaxIoSlots && kn.rings_sa >= 3 && kn.rings_sa <= pnp::kMaxASlots &&
       fixed_bytes(kn.rings_nio) + (long long)kn.rings_sa * pnp::kASlotBytes <= budget && !(c->idt && kn.rings_nio < 3) &&
-      !(par && kn.rings_nio != 3)) {
+      !(par && kn.rings_nio < 3)) {
     p.n_io = kn.rings_nio;
     p.s_a = kn.rings_sa;
   }

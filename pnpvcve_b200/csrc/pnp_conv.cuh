@@ -12,6 +12,7 @@ constexpr int kASlotBytes = 17 * 1024;       // ring slot (1024-aligned, >= kRow
 constexpr int kTileBytes = kTilePx * 128;    // 16384: one 128-pixel x 64-channel bf16 tile
 constexpr int kWChunkBytes = 8192;           // one 64(N) x 64(K) bf16 weight block
 constexpr int kRowsThreads = 352;            // warp0 TMA producer, warp1 MMA issuer, warps2-9 epilogue, warp10 barrier scout
+constexpr int kRowsThreadsPar = 480;         // block launch A: + warps 11-14, the readers of the 1x1 accumulator region
 constexpr int kEpilogueWarps = 8;
 constexpr int kMaxASlots = 8;
 constexpr int kMaxIoSlots = 6;

@@ -154,7 +154,7 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 }  // namespace
 
 template <bool kPar, bool kScale, bool kPair>
-__global__ void __launch_bounds__(kRowsThreads, 1)
+__global__ void __launch_bounds__(kPar ? kRowsThreadsPar : kRowsThreads, 1)
 conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
   constexpr int kAccRing = kPar ? 5 : 8;
   const int rank = kPair ? (int)cluster_ctarank() : 0;        // position in the CTA pair; 0 = leader
@@ -220,7 +220,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       for (int i = 0; i < kMaxASlots; ++i) mbar_init(smem_u32(&misc->a_full[i]), 1);
       for (int i = 0; i < kStepRing; ++i) mbar_init(smem_u32(&misc->step_done[i]), 1);
       // pair mode: the leader's acc_free barriers collect the reader warps of both CTAs
-      const int acc_readers = ((kPar && p.par_split) ? 4 : kEpilogueWarps) * (kPair ? 2 : 1);
+      const int acc_readers = kEpilogueWarps * (kPair ? 2 : 1);
       for (int i = 0; i < kAccRingMax; ++i) mbar_init(smem_u32(&misc->acc_free[i]), acc_readers);
       mbar_init(smem_u32(&misc->peer_w), 1);
       for (int i = 0; i < kMaxIoSlots; ++i) mbar_init(smem_u32(&misc->dy_full[i]), 4);
@@ -640,7 +640,10 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       for (SegIter it(p, t_begin, t_end, rank); it.valid();) {
         const Segment s = it.get();
         for (int j = s.j_first; j <= s.j_last; ++j, ++sc, ar.advance()) {
+          const bool trs = PNP_TRACING && blockIdx.x == 0 && sc < 64;
+          if (trs) p.trace[2560 + sc * 4 + 0] = clock64();
           mbar_wait(smem_u32(&misc->a_full[ar.slot]), ar.phase, 5);
+          if (trs) p.trace[2560 + sc * 4 + 1] = clock64();
           const int lo = max(j - 1, 0), hi = min(j + 1, s.len - 1);
           const int new_from = (j == s.j_first) ? lo : j + 1;
           for (int o = max(new_from, lo); o <= hi; ++o) {          // rows first touched in this step
@@ -653,13 +656,16 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
             mbar_wait(smem_u32(&misc->aux_full[od & 1]), (od >> 1) & 1, 7);
           }
           st_release_shared(go_step, sc + 1);
+          if (trs) p.trace[2560 + sc * 4 + 2] = clock64();
         }
         ord0 += s.len;
         it.next(s);
       }
     }
+  } else if (warp >= 11 && !(kPar && p.par_split)) {
+    // (block launch A with the single-role epilogue: the region-reader warps have nothing to do)
   } else {
-    // ============================================================ epilogue (8 warps, 256 threads)
+    // ============================================================ epilogue (8 warps, 256 threads; + 4 region readers)
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;          // warps 2..9 only
     const int row = q * 32 + lane;
@@ -764,7 +770,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
     // ---------------------------------------------------------------------------------------------------
     if (kPar && p.par_split) {
       const uint32_t slot_free = smem_u32(&misc->slot_free);
-      if (warp >= 6) {
+      if (warp >= 11) {
         float pn0 = 0.f, pn1 = 0.f, pn2 = 0.f;
         if (cur.valid) par_load(cur, pn0, pn1, pn2);
         Ring sl(n_io);
@@ -773,30 +779,31 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
           tile_next(nxt);
           float pf0 = 0.f, pf1 = 0.f, pf2 = 0.f;
           if (nxt.valid) par_load(nxt, pf0, pf1, pf2);      // one row ahead: consumed a whole step later
+          const bool trr = PNP_TRACING && blockIdx.x == 0 && cur.ord < 64 && warp == 11 && lane == 0;
+          if (trr) p.trace[3072 + cur.ord * 4 + 0] = clock64();
           mbar_wait(smem_u32(&misc->par_done), cur.ord & 1, 11);   // (one poller per warp measured no better)
+          if (trr) p.trace[3072 + cur.ord * 4 + 1] = clock64();
           tc_fence_after();
           if (p.par_sparse) par_sparse_select(pn0, pn1, pn2);
           uint32_t wv[32];
-          // two batches of 32 channels x 3 classes: six tcgen05.ld in flight per wait
+          // four batches of 16 channels x 3 classes (48 values in flight: the 480-thread block leaves 128 registers)
 #pragma unroll
-          for (int b2 = 0; b2 < 2; ++b2) {
-            float a1[32], a2[32], a3[32];
-            const uint32_t col = kParCol + b2 * 32;
+          for (int b4 = 0; b4 < 4; ++b4) {
+            float a1[16], a2[16], a3[16];
+            const uint32_t col = kParCol + b4 * 16;
             tmem_ld16(lane_base + col, a1);
-            tmem_ld16(lane_base + col + 16, a1 + 16);
             tmem_ld16(lane_base + col + 64, a2);
-            tmem_ld16(lane_base + col + 80, a2 + 16);
             tmem_ld16(lane_base + col + 128, a3);
-            tmem_ld16(lane_base + col + 144, a3 + 16);
             tmem_ld_wait();
-            if (b2 == 1) {                                   // everything is in registers: hand the region back first
+            if (b4 == 3) {                                   // everything is in registers: hand the region back first
               tc_fence_before();
               par_release();
+              if (trr) p.trace[3072 + cur.ord * 4 + 2] = clock64();
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              wv[b2 * 16 + j] = pack_bf16x2(fmaf(pn2, a3[2 * j], fmaf(pn1, a2[2 * j], pn0 * a1[2 * j])),
-                                            fmaf(pn2, a3[2 * j + 1], fmaf(pn1, a2[2 * j + 1], pn0 * a1[2 * j + 1])));
+            for (int j = 0; j < 8; ++j)
+              wv[b4 * 8 + j] = pack_bf16x2(fmaf(pn2, a3[2 * j], fmaf(pn1, a2[2 * j], pn0 * a1[2 * j])),
+                                           fmaf(pn2, a3[2 * j + 1], fmaf(pn1, a2[2 * j + 1], pn0 * a1[2 * j + 1])));
           }
           // the row's staging slot was last used by row ord - n_io: its TMA store must have finished reading
           if (cur.ord >= (uint32_t)n_io) spin_until_ge(slot_free, cur.ord - (uint32_t)n_io + 1, 12);
@@ -806,6 +813,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
             *reinterpret_cast<uint4*>(rowp + ((c8 ^ sw) << 4)) =
                 make_uint4(wv[4 * c8], wv[4 * c8 + 1], wv[4 * c8 + 2], wv[4 * c8 + 3]);
           warp_arrive(smem_u32(&misc->dy_full[sl.slot]));    // release: the parked values are visible to warps 2..5
+          if (trr) p.trace[3072 + cur.ord * 4 + 3] = clock64();
           sl.advance();
           pn0 = pf0;
           pn1 = pf1;
@@ -828,19 +836,25 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
             }
             __syncwarp();
           }
+          const bool trm = PNP_TRACING && blockIdx.x == 0 && ord < 64 && warp == 2 && lane == 0;
+          if (trm) p.trace[2816 + ord * 4 + 0] = clock64();
           mbar_wait(smem_u32(&misc->step_done[sc_last & (kStepRing - 1)]), (sc_last >> kStepShift) & 1, 9);
+          if (trm) p.trace[2816 + ord * 4 + 1] = clock64();
           tc_fence_after();
-          float v[64];
-#pragma unroll
-          for (int b4 = 0; b4 < 4; ++b4) tmem_ld16(taddr + b4 * 16, v + b4 * 16);
+          float v[32];                                       // this warp's 32 channels of its 32 pixels
+          tmem_ld16(taddr + half * 32, v);
+          tmem_ld16(taddr + half * 32 + 16, v + 16);
           tmem_ld_wait();
           tc_fence_before();
           acc_release(slot);                                 // accumulator is in registers: slot reusable
+          if (trm) p.trace[2816 + ord * 4 + 2] = clock64();
           mbar_wait(smem_u32(&misc->dy_full[ior.slot]), ior.phase, 13);
+          if (trm) p.trace[2816 + ord * 4 + 3] = clock64();
           uint8_t* rowp = sgen + L.io + ior.slot * kTileBytes + row * 128;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float* vv = v + g * 16;
+          for (int gg = 0; gg < 2; ++gg) {
+            const int g = half * 2 + gg;
+            float* vv = v + gg * 16;
             const float4* sc4 = reinterpret_cast<const float4*>(&misc->scale[g * 16]);
             const float4* bi4 = reinterpret_cast<const float4*>(&misc->bias[g * 16]);
 #pragma unroll
@@ -869,7 +883,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
                              pack_bf16x2(vv[14], vv[15]));
           }
           fence_proxy_async_smem();
-          named_bar_sync(2, 128);
+          named_bar_sync(2, 256);
           if (store_warp) {
             if (elect_one()) {
               if (!phantom(s)) {
@@ -1189,7 +1203,7 @@ template <bool kPar, bool kScale, bool kPair>
 cudaError_t launch_rows_variant(const ConvParams& p, int grid, size_t smem, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kRowsThreads);
+  cfg.blockDim = dim3(kPar ? kRowsThreadsPar : kRowsThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -1214,7 +1228,7 @@ cudaError_t prepare_variant(int* max_pairs) {
   // how many CTA pairs fit on the device at once (GPCs with an odd number of usable SMs leave one SM unpaired)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * 148);
-  cfg.blockDim = dim3(kRowsThreads);
+  cfg.blockDim = dim3(kPar ? kRowsThreadsPar : kRowsThreads);
   cfg.dynamicSmemBytes = kMaxSmem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
