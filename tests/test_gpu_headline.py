@@ -147,6 +147,64 @@ def test_c2_t100_strip_no_drift(dev):
     assert dps.max().item() <= 0.02
 
 
+def test_pytorch_on_the_same_gpu_is_recorded_beside_the_cuda_path(dev):
+    """The reference is a PyTorch model: on a GPU box its users run it through ATen / cuDNN.  This records what the
+    reference's algorithm (the oracle restatement, op for op) reaches on THIS B200 at 720p -- fp32 as the reference
+    runs it, with TF32 allowed, and under bf16 autocast (our arithmetic type) -- next to the CUDA path on the same clip,
+    in gpurun_out/r02_error_vs_frame.json.  Informational; the only assertion is that the hand-written path is not
+    slower than the library path it replaces."""
+    import time
+    sd = weights.random_state_dict(25)
+    t = 6
+    clip = synthetic.make_config_clip("C2", clip_idx=9, t=t, crf=25)
+    args = [a.to(dev) for a in synthetic.generator_args(clip)]
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+
+    def timed(fn, reps=2):
+        fn()                                             # warm-up (cuDNN algorithm selection, graph capture)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return t * reps / (time.perf_counter() - t0)
+
+    def oracle_fn():
+        with torch.no_grad():
+            return O.generator_forward(sd_dev, *args)
+
+    res = {}
+    res["torch_fp32_frames_per_s"] = timed(oracle_fn)
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    res["torch_tf32_frames_per_s"] = timed(oracle_fn)
+
+    def autocast_fn():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return oracle_fn()
+    try:
+        res["torch_bf16_autocast_frames_per_s"] = timed(autocast_fn)
+    except RuntimeError as e:                            # (an op of the restatement that autocast cannot mix)
+        res["torch_bf16_autocast_error"] = str(e).splitlines()[0][:200]
+    net = build(sd, dev)
+
+    def ours():
+        with torch.no_grad():
+            return net(*args)
+    res["cuda_path_frames_per_s"] = timed(ours, reps=4)
+    res["clip"] = f"C2 1280x720, T={t} (short clip: key frames at both ends), CRF 25, resident inputs"
+    path = os.path.join(ROOT, "gpurun_out", "r02_error_vs_frame.json")
+    data = {}
+    if os.path.isfile(path):
+        with open(path) as f:
+            data = json.load(f)
+    data["pytorch_on_this_gpu"] = res
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1)
+    print("720p frames/s on this GPU: " + ", ".join(f"{k} {v:.1f}" for k, v in res.items() if k.endswith("_per_s")))
+    assert res["cuda_path_frames_per_s"] >= max(v for k, v in res.items() if k.startswith("torch_") and k.endswith("_per_s"))
+
+
 def test_generator_on_non_current_device_stream(dev):
     """The launches follow the INPUT's device and the caller's current stream there: run from a side
     stream and, when the box has a second GPU, on a device that is not current."""
