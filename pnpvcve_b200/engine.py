@@ -93,19 +93,26 @@ class _Program:
     """Everything that is fixed for one (clip count, T, H, W) shape: the feature pool, the launch table, the prebuilt
     descriptors of every step variant and their captured graphs."""
 
-    def __init__(self, n, t, h, w, dev, maxn, nb, vsr, table_steps):
-        self.key = (n, t, h, w, dev, maxn, nb, vsr)
+    def __init__(self, n, t, h, w, dev, maxn, nb, vsr, table_steps, lr_once=False):
+        self.key = (n, t, h, w, dev, maxn, nb, vsr, lr_once)
         self.n, self.t, self.h, self.w, self.dev, self.maxn, self.nb, self.vsr = n, t, h, w, dev, maxn, nb, vsr
         self.img_bytes = h * w * 128
-        self.pool_images = t * n + len(WORK) * maxn
+        # lr_once: the LR im2col operand of EVERY frame stays in the pool (images [t*n, 2*t*n), frame-major like feats):
+        # the backward-time pass writes it, the forward-time pass reads it again instead of recomputing it
+        self.lr_once = lr_once
+        self.lr_base = t * n if lr_once else None
+        first_work = (2 if lr_once else 1) * t * n
+        self.pool_images = first_work + len(WORK) * maxn
         self.pool = torch.empty((self.pool_images, h, w, 64), dtype=torch.bfloat16, device=dev)
         self.feats = self.pool[: t * n].view(t, n, h, w, 64)      # frame-major: a run of clips at one frame is contiguous
         self.work = {}
         for k, name in enumerate(WORK):
-            f0 = t * n + k * maxn
+            f0 = first_work + k * maxn
             self.work[name] = (f0, self.pool[f0:f0 + maxn])
         self.work["lr64"][1].zero_()
         self.work["zero"][1].zero_()
+        if lr_once:
+            self.pool[t * n:2 * t * n].zero_()
         if vsr:      # x4 tail: 2Hx2W and 4Hx4W feature maps of one frame step
             self.u1 = ops.new_feature(maxn, 2 * h, 2 * w, dev)
             self.u2 = ops.new_feature(maxn, 4 * h, 4 * w, dev)
@@ -169,6 +176,9 @@ class BaeEngine:
         self.use_graphs = os.environ.get("PNP_GRAPHS", "1") != "0"
         #: batch runs of clips with the same key-frame schedule into N-image launches (up to max_batch clips)
         self.batch_clips = os.environ.get("PNP_BATCH_CLIPS", "1") != "0"
+        #: LR im2col once per frame (kept in the pool between the two passes): None = when the memory is small against
+        #: the device, True / False = forced (PNP_LR_ONCE=1 / 0)
+        self.lr_once = {"0": False, "1": True}.get(os.environ.get("PNP_LR_ONCE", ""), None)
         self.max_batch = 16
 
     # ------------------------------------------------------------------ weights
@@ -298,10 +308,15 @@ class BaeEngine:
 
     # ------------------------------------------------------------------ program (pool, table, descriptors, graphs)
     def _program(self, n, t, h, w, dev, maxn, steps):
-        key = (n, t, h, w, dev, maxn, self.m.num_blocks, bool(self.m.vsr))
+        # LR im2col once per frame instead of once per pass: costs a second t*n-image region of the pool, taken when
+        # it is small against the device (PNP_LR_ONCE=0/1 forces it off / on)
+        extra = t * n * h * w * 128
+        lr_once = self.lr_once if self.lr_once is not None else \
+            extra <= torch.cuda.get_device_properties(dev).total_memory // 8
+        key = (n, t, h, w, dev, maxn, self.m.num_blocks, bool(self.m.vsr), lr_once)
         if self.prog is None or self.prog.key != key:
             self.prog = None                         # release the old pool before allocating the new one
-            self.prog = _Program(n, t, h, w, dev, maxn, self.m.num_blocks, bool(self.m.vsr), steps)
+            self.prog = _Program(n, t, h, w, dev, maxn, self.m.num_blocks, bool(self.m.vsr), steps, lr_once)
         self.prog.ensure_table(steps)
         return self.prog
 
@@ -368,7 +383,8 @@ class BaeEngine:
                                            fsy, fsn, nn, h, w)))
 
         bwd = variant.startswith("b_")
-        im2col()
+        if bwd or not pg.lr_once:
+            im2col()
         if variant not in ("b_last", "f_first"):
             warp()
         if variant in ("b_last", "b_merged", "f_first"):
@@ -447,13 +463,16 @@ class BaeEngine:
             tab[sel, node, 7] = iv[2] | (iv[3] << 32)
 
         W = {k: v.data_ptr() for k, v in st.items() if isinstance(v, torch.Tensor)}
+        # pool image of the frame's LR im2col operand: its own per-frame image (lr_once) or the one work buffer
+        lr64 = (pg.lr_base + frame * n + b0) if pg.lr_once else np.full(2 * t, work["lr64"], dtype=np.int64)
         for v in set(variants):
             sel = var == v
             bwd = v.startswith("b_")
             br = 0 if bwd else 1
             node = 0
-            put(sel, node, p=(lr_ptr, pool_ptr + work["lr64"] * img))            # im2col
-            node += 1
+            if bwd or not pg.lr_once:
+                put(sel, node, p=(lr_ptr, pool_ptr + lr64 * img))                # im2col
+                node += 1
             cur = feats(frame)
             if v not in ("b_last", "f_first"):
                 kidx = np.where(steps < t, bk[frame], fk[frame])
@@ -461,24 +480,24 @@ class BaeEngine:
                 node += 1
             in_bias = W["bwd_in_bias"] if bwd else W["fwd_in_bias"]
             if v == "b_last":       # zeros for key_warp / neighbour (:69-70)
-                put(sel, node, p=(W["bwd_merged_aux"], in_bias), i=(work["zero"], work["lr64"], 0, work["xa"]))
+                put(sel, node, p=(W["bwd_merged_aux"], in_bias), i=(work["zero"], lr64, 0, work["xa"]))
                 node += 1
             elif v == "b_merged":   # align_key: the neighbour is the warped key (:85-88)
-                put(sel, node, p=(W["bwd_merged_aux"], in_bias), i=(work["kw"], work["lr64"], 0, work["xa"]))
+                put(sel, node, p=(W["bwd_merged_aux"], in_bias), i=(work["kw"], lr64, 0, work["xa"]))
                 node += 1
             elif v == "b_sep":
-                put(sel, node, p=(W["bwd_key_aux"], in_bias), i=(work["kw"], work["lr64"], 0, work["pa"]))
+                put(sel, node, p=(W["bwd_key_aux"], in_bias), i=(work["kw"], lr64, 0, work["pa"]))
                 put(sel, node + 1, p=(W["bwd_nb"],), i=(feats(frame + 1), 0, work["pa"], work["xa"]))
                 node += 2
             elif v == "f_first":
-                put(sel, node, p=(W["fwd_bf_aux"], in_bias), i=(cur, work["lr64"], 0, work["xa"]))
+                put(sel, node, p=(W["fwd_bf_aux"], in_bias), i=(cur, lr64, 0, work["xa"]))
                 node += 1
             elif v == "f_merged":
-                put(sel, node, p=(W["fwd_bf_aux"], in_bias), i=(cur, work["lr64"], 0, work["pa"]))
+                put(sel, node, p=(W["fwd_bf_aux"], in_bias), i=(cur, lr64, 0, work["pa"]))
                 put(sel, node + 1, p=(W["fwd_merged"],), i=(work["kw"], 0, work["pa"], work["xa"]))
                 node += 2
             else:                   # f_sep
-                put(sel, node, p=(W["fwd_bf_aux"], in_bias), i=(cur, work["lr64"], 0, work["pa"]))
+                put(sel, node, p=(W["fwd_bf_aux"], in_bias), i=(cur, lr64, 0, work["pa"]))
                 put(sel, node + 1, p=(W["fwd_key"],), i=(work["kw"], 0, work["pa"], work["pb"]))
                 put(sel, node + 2, p=(W["fwd_nb"],), i=(feats(frame - 1), 0, work["pb"], work["xa"]))
                 node += 3

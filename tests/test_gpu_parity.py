@@ -264,3 +264,23 @@ def test_profiled_launch_path_equals_fast_path(dev):
     finally:
         net._engine.prof = None
     assert torch.equal(fast, slow)
+
+
+def test_lr_operand_kept_per_frame_equals_recomputed(dev):
+    """The LR im2col operand of a frame is written once by the backward-time pass and read again by the forward-time
+    pass (engine.lr_once, the default when the pool has room) -- bit-identical to recomputing it in both passes, with
+    one launch fewer per forward step, for single clips, batched runs of clips and several runs in one call."""
+    sd = weights.random_state_dict(19, num_blocks=2)
+    net = build(sd, dev, num_blocks=2)
+    a = synthetic.make_clip(72, 136, 6, seed=21, crf=15, pattern="IBBP", ipb=True)
+    b = synthetic.make_clip(72, 136, 6, seed=22, crf=35, pattern="IBBP", ipb=True)
+    c = synthetic.make_clip(72, 136, 6, seed=23, crf=25, pattern="allB", ipb=True)
+    for clip in (a, synthetic.cat_clips([a, b, c])):
+        net._engine.lr_once = False
+        twice = run(net, clip, dev).clone()
+        launches_twice = net.gpu_launches
+        net._engine.lr_once = True
+        once = run(net, clip, dev)
+        assert net._engine.prog.lr_once
+        assert net.gpu_launches < launches_twice
+        assert torch.equal(once, twice)
