@@ -18,6 +18,9 @@ Rank 0 prints ONE JSON line:
   e2e          same from pinned HOST buffers through the public host-clip API (driver.enhance_clips on host entries,
                ClipStreamer underneath): H2D of every input and D2H of the enhanced frames inside the timed region,
                overlapped with the kernels
+  e2e_sideinfo the same public call fed with COMPACT side information: per-block motion-vector records (40 bytes per
+               block) over the bus instead of the dense mvs / partitions planes, rasterised on the device
+               (pnp_mv_rasterize); informational, `e2e` stays the reference's dense interface
   roofline     dominant kernel (block launch A: 3x3 conv + three partition 1x1 convs): algorithmic FLOPs per
                launch / mean launch duration, CUDA events bracketing every 8th such launch in a separate pass of
                the same steps (an upper bound: the bracketed launch loses its programmatic-dependent-launch
@@ -355,6 +358,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-sideinfo", action="store_true", help="skip the compact side-information end-to-end block")
     ap.add_argument("--no-windows", action="store_true", help="skip the frame-window (single clip, strong scaling) block")
     ap.add_argument("--prof-every", type=int, default=8,
                     help="bracket every N-th launch of the profiled kernels with CUDA events")
@@ -494,13 +498,14 @@ def main():
     out_host = torch.empty((nc, T, 3, H, W), dtype=torch.float32).pin_memory()
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     d2h = out_host.numel() * out_host.element_size()
-    def run_e2e(n_steps):
+    def run_e2e(n_steps, entry=None):
+        entry = host[0] if entry is None else entry
         """The public host-clip API, driver.enhance_clips on HOST-resident entries: this rank's share of world x n_steps
         entries streams through driver.ClipStreamer -- frames are uploaded in chunks in the order the backward-time pass
         reads them, finished frames are downloaded chunk by chunk, the next entry's upload overlaps the kernels; every
         step still copies all of its inputs from pinned host memory and all of its frames back inside the timed region,
         and the per-frame metrics of all ranks meet in the job's one fixed-shape gather."""
-        entries = [host[0] if c % world == rank else None for c in range(world * n_steps)]
+        entries = [entry if c % world == rank else None for c in range(world * n_steps)]
         driver.enhance_clips(net, entries, rank, world, device=dev, out_hosts=[out_host] * len(entries),
                              chunk=max(1, min(10, T)))
 
@@ -522,6 +527,40 @@ def main():
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_steps * T * nc / (float(ms2.item()) / 1e3)
+
+    # ---------------- the same call fed with COMPACT side information: the codec's per-block records
+    # (40 bytes per block) go over the bus instead of the dense mvs / partitions planes and are rasterised on the
+    # device inside the streamer (pnp_mv_rasterize, bit-exact replacement of loading_ipb.py:328-369)
+    e2e_side = None
+    if not args.no_sideinfo:
+        import numpy as np
+        from pnpvcve_b200 import sideinfo
+        types = [chr(int(v)) for v in host[0]["slices"][0].flatten()]
+        tmpl = sideinfo.synthetic_records(H, W, "IBBP", seed=77)          # record lists of an I, two B and a P frame
+        per_type = {"I": [tmpl[0]], "B": [tmpl[1], tmpl[2]], "P": [tmpl[3]]}
+        recs = [per_type[st][f % len(per_type[st])] for f, st in enumerate(types)]
+        flat = np.concatenate(recs, 0)
+        offs = np.cumsum([0] + [len(r) for r in recs])
+        compact = {k: v for k, v in host[0].items() if k not in ("mvs", "partitions")}
+        compact["side"] = [sideinfo.pack_side(flat, offs, types) for _ in range(nc)]
+        side_h2d = sum(v.numel() * v.element_size() for k, v in compact.items() if k != "side") + \
+            sum(sd["records"].numel() * 4 + sd["meta"].numel() * 4 for sd in compact["side"])
+        with torch.no_grad():
+            run_e2e(2, compact)
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            run_e2e(e2e_steps, compact)
+            s1.record()
+            barrier()
+        ms4 = torch.tensor([s0.elapsed_time(s1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms4, op=dist.ReduceOp.MAX)
+        e2e_side = dict(value=world * e2e_steps * T * nc / (float(ms4.item()) / 1e3), unit="frames/s",
+                        h2d_bytes_per_step=side_h2d, d2h_bytes_per_step=d2h, steps=e2e_steps,
+                        records_per_frame=int(len(flat) / max(1, T)),
+                        api="pnpvcve_b200.driver.enhance_clips on pinned host entries carrying `side` (per-block motion-"
+                            "vector records of a synthetic H.264-style partition tree) instead of dense mvs / partitions")
     del host, out_host
     torch.cuda.empty_cache()
 
@@ -587,7 +626,7 @@ def main():
                                             d2h_bytes_per_step=d2h, steps=e2e_steps,
                                             api="pnpvcve_b200.driver.enhance_clips on pinned host entries (ClipStreamer: "
                                                 "chunked H2D/D2H overlapped with the kernels)"),
-                    frame_windows=windows,
+                    e2e_sideinfo=e2e_side, frame_windows=windows,
                     gpu_launches=launches * world, launch_mode=net._engine.last_mode, roofline=roofline,
                     roofline_warp=roofline_warp,
                     kernels_ms=dict(block=mean_event_ms(prof["block"]), block_a=a_ms, block_b=b_ms, warp=w_ms),

@@ -87,7 +87,9 @@ def enhance_clips(net, clips, rank=0, world=1, refs=None, gts=None, crop_border=
 
     if host and mine:
         up = 4 if getattr(net, "vsr", False) else 1
-        pinned = {c: {k: (v if v.is_pinned() else v.pin_memory()) for k, v in clips[c].items()} for c in mine}
+        # (`side`: compact side information packed by sideinfo.pack_side, already pinned -- see ClipStreamer.upload)
+        pinned = {c: {k: (v if k == "side" or v.is_pinned() else v.pin_memory()) for k, v in clips[c].items()}
+                  for c in mine}
         streamer = ClipStreamer(net, dev, chunk=chunk)
         ticket = streamer.upload(pinned[mine[0]])
         for i, c in enumerate(mine):
@@ -97,7 +99,7 @@ def enhance_clips(net, clips, rank=0, world=1, refs=None, gts=None, crop_border=
             ticket = streamer.upload(pinned[mine[i + 1]]) if i + 1 < len(mine) else None   # overlaps clip c's kernels
             measure(c, out)                 # on the device copy, before its buffer is recycled two entries later
             outs.append(dst)
-        streamer.finish()
+        streamer.finish(check=True)
     else:
         for c in mine:
             out = net(*generator_args(clips[c]))
@@ -259,6 +261,7 @@ class ClipStreamer:
         self.outs = [None, None]           # ... and result buffers: (tensor, event "its last download has finished")
         self.turn = 0
         self.h2d_bytes = self.d2h_bytes = 0
+        self.raster_work = self.raster_status = None     # compact side information: rasteriser workspace / error bits
         #: diagnostics (tools/e2e_probe.py): skip the big H2D / D2H copies to see what each direction costs
         self.copy_in = self.copy_out = True
 
@@ -284,32 +287,60 @@ class ClipStreamer:
         return owner
 
     def upload(self, host_clip):
-        """Enqueue the upload of one clip; returns a ticket for ``run``."""
+        """Enqueue the upload of one clip; returns a ticket for ``run``.
+
+        COMPACT side information: a host clip that carries ``side`` (a list of n ``sideinfo.pack_side`` dicts: the
+        codec's per-block motion-vector records, 40 bytes per block) instead of the dense ``mvs`` / ``partitions``
+        planes uploads those records and rasterises them on the device (``pnp_mv_rasterize``, the bit-exact
+        replacement of the loader's per-record loop, loading_ipb.py:328-369) -- 0.5 instead of 25.8 MB per 720p frame
+        over the bus; only ``lq`` is then streamed in chunks."""
         t = host_clip["lq"].shape[1]
         slot = self.turn
         self.turn ^= 1
-        key = tuple((k, tuple(v.shape)) for k, v in sorted(host_clip.items()))
+        side = host_clip.get("side")
+        tensors = {k: v for k, v in host_clip.items() if k != "side"}
+        n, _, _, h, w = host_clip["lq"].shape
+        if side is not None:
+            if len(side) != n or any(sd["t"] != t for sd in side):
+                raise ValueError(f"side information must hold one packed entry of {t} frames per clip ({n})")
+            shapes = dict({k: (tuple(v.shape), v.dtype) for k, v in tensors.items()},
+                          mvs=((n, t, 4, h, w), torch.float32), partitions=((n, t, 3, h, w), torch.float32))
+        else:
+            shapes = {k: (tuple(v.shape), v.dtype) for k, v in tensors.items()}
+        key = tuple((k, sh) for k, (sh, _) in sorted(shapes.items()))
         if self.slots[slot] is None or self.slots[slot][0] != key:
-            self.slots[slot] = (key, {k: torch.empty(v.shape, dtype=v.dtype, device=self.dev) for k, v in host_clip.items()},
+            self.slots[slot] = (key, {k: torch.empty(sh, dtype=dt, device=self.dev) for k, (sh, dt) in shapes.items()},
                                 None)
         dclip = self.slots[slot][1]
         busy = self.slots[slot][2]         # kernels of the clip that last used these buffers
         events = {}
+        side_bytes, side_dev, side_ev = 0, [], None
         with torch.cuda.stream(self.up):
             if busy is not None:
                 self.up.wait_event(busy)
             for k in self.SMALL:
                 dclip[k].copy_(host_clip[k], non_blocking=True)
-            n = host_clip["lq"].shape[0]
+            if side is not None:
+                # only the records cross the bus here; they are rasterised by `run` on the kernels' own stream (on this
+                # copy stream the rasteriser would share the SMs with the previous clip's persistent conv kernels for
+                # tens of ms and slow them: measured 268 instead of 299 frames/s)
+                from . import sideinfo
+                for c in range(n):
+                    rec, meta, nbytes = sideinfo.upload_side(side[c], self.dev)
+                    side_dev.append((rec, meta))
+                    side_bytes += nbytes
+                side_ev = torch.cuda.Event()
+                side_ev.record(self.up)
+            big = [k for k in self.BIG if k in tensors]
             for a, b in reversed(self._chunks(t)):
-                for k in self.BIG if self.copy_in else ():
+                for k in big if self.copy_in else ():
                     for c in range(n):
                         dclip[k][c, a:b].copy_(host_clip[k][c, a:b], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.up)
                 events[(a, b)] = ev
-        self.h2d_bytes = sum(v.numel() * v.element_size() for v in host_clip.values())
-        return dict(slot=slot, dclip=dclip, events=events, t=t,
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in tensors.values()) + side_bytes
+        return dict(slot=slot, dclip=dclip, events=events, t=t, side_dev=side_dev, side_ev=side_ev,
                     cond=(host_clip["slices"], host_clip["base_QPs"], host_clip["QPs"]))
 
     @torch.no_grad()
@@ -339,6 +370,23 @@ class ClipStreamer:
 
         main.wait_event(events[chunks[-1]])          # small tensors + the first chunk the kernels need
         waited.add(chunks[-1])
+        if ticket["side_dev"]:
+            # compact side information: records -> dense mvs / partitions of the whole clip, ahead of its first kernel
+            # (~47 us per 720p frame).  The planes' previous readers ran on this stream, so plain stream order suffices.
+            from . import sideinfo
+            main.wait_event(ticket["side_ev"])
+            h, w = dclip["lq"].shape[-2:]
+            if self.raster_work is None or tuple(self.raster_work.shape[1:]) != (t, h, w):
+                self.raster_work = torch.empty((3, t, h, w), dtype=torch.int32, device=self.dev)
+            if self.raster_status is None:
+                self.raster_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            with torch.cuda.device(self.dev):
+                for c, (rec, meta) in enumerate(ticket["side_dev"]):
+                    rec.record_stream(main)          # allocated on the copy stream, read here
+                    meta.record_stream(main)
+                    sideinfo.rasterize_uploaded(rec, meta, t, dclip["mvs"][c], dclip["partitions"][c],
+                                                self.raster_work, self.raster_status)
+            ticket["side_dev"] = []
         from .synthetic import generator_args
         # result buffers are owned here and recycled under events: a fresh torch.empty per clip that another stream
         # still reads (record_stream) keeps the caching allocator from reusing the block and ends in cudaMalloc stalls
@@ -360,8 +408,13 @@ class ClipStreamer:
         self.d2h_bytes = out.numel() * out.element_size()
         return out
 
-    def finish(self):
+    def finish(self, check=False):
+        """Order the caller's stream behind the last download.  ``check``: synchronise and raise what the reference's
+        loader raises for malformed side information (KeyError / ValueError, see sideinfo.raise_for_status)."""
         torch.cuda.current_stream(self.dev).wait_stream(self.down)
+        if check and self.raster_status is not None:
+            from . import sideinfo
+            sideinfo.raise_for_status(int(self.raster_status.item()))
 
 
 def stream_clips(net, host_clips, out_hosts, device, chunk=10):

@@ -36,6 +36,26 @@ def p_targets(slice_types):
     return tgt
 
 
+def _launch(rec, offs, is_b, tgt, t, h, w, work, mvs, par, status):
+    """pnp_mv_rasterize on the current stream of the tensors' device; ``work`` (3,T,H,W) int32 must be zeroed."""
+    lib = _lib.load()
+    vp = ctypes.c_void_p
+    stream = vp(torch.cuda.current_stream(mvs.device).cuda_stream)
+    _lib.check(lib.pnp_mv_rasterize(vp(rec.data_ptr() if rec.numel() else 0), vp(offs.data_ptr()),
+                                    vp(is_b.data_ptr()), vp(tgt.data_ptr()), t, rec.shape[0], h, w,
+                                    vp(work[0].data_ptr()), vp(work[1].data_ptr()), vp(work[2].data_ptr()),
+                                    vp(mvs.data_ptr()), vp(par.data_ptr()), vp(status.data_ptr()), stream),
+               "pnp_mv_rasterize")
+
+
+def raise_for_status(st):
+    """The reference's loader errors for a device status word of pnp_mv_rasterize."""
+    if st & 1:
+        raise KeyError("block area w*h not in {256, 128, 64} (partition_ch lookup, loading_ipb.py:361)")
+    if st & 2:
+        raise ValueError("reversed P-frame record without a previous non-B frame (p_offset unbound)")
+
+
 def rasterize_clip(records, frame_offsets, slice_types, h, w, device=None, check=True):
     """records (R,10) fp32, frame_offsets (T+1,) int, slice_types: sequence of 'I'|'P'|'B'.
 
@@ -56,22 +76,46 @@ def rasterize_clip(records, frame_offsets, slice_types, h, w, device=None, check
     mvs = torch.empty((t, 4, h, w), dtype=torch.float32, device=dev)
     par = torch.empty((t, 3, h, w), dtype=torch.float32, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    lib = _lib.load()
-    vp = ctypes.c_void_p
     with torch.cuda.device(dev):
-        stream = vp(torch.cuda.current_stream().cuda_stream)
-        _lib.check(lib.pnp_mv_rasterize(vp(rec.data_ptr() if rec.numel() else 0), vp(offs.data_ptr()),
-                                        vp(is_b.data_ptr()), vp(tgt.data_ptr()), t, rec.shape[0], h, w,
-                                        vp(work[0].data_ptr()), vp(work[1].data_ptr()), vp(work[2].data_ptr()),
-                                        vp(mvs.data_ptr()), vp(par.data_ptr()), vp(status.data_ptr()), stream),
-                   "pnp_mv_rasterize")
+        _launch(rec, offs, is_b, tgt, t, h, w, work, mvs, par, status)
     if check:
-        st = int(status.item())
-        if st & 1:
-            raise KeyError("block area w*h not in {256, 128, 64} (partition_ch lookup, loading_ipb.py:361)")
-        if st & 2:
-            raise ValueError("reversed P-frame record without a previous non-B frame (p_offset unbound)")
+        raise_for_status(int(status.item()))
     return mvs, par
+
+
+def pack_side(records, frame_offsets, slice_types):
+    """Host form of one clip's side information for ``driver.ClipStreamer`` / ``driver.enhance_clips`` (the ``side``
+    entry of a host clip that carries no dense ``mvs`` / ``partitions``): pinned records (R,10) fp32 and ONE pinned
+    int32 vector [frame_offsets (T+1) | is_b (T) | p_target (T)] -- two contiguous uploads per clip."""
+    t = len(slice_types)
+    rec = torch.as_tensor(np.ascontiguousarray(np.asarray(records, dtype=np.float32).reshape(-1, 10)))
+    offs = np.asarray(frame_offsets, dtype=np.int32).reshape(-1)
+    if offs.size != t + 1:
+        raise ValueError("frame_offsets must have T+1 entries")
+    meta = np.concatenate([offs, np.asarray([1 if s == "B" else 0 for s in slice_types], dtype=np.int32),
+                           np.asarray(p_targets(slice_types), dtype=np.int32)])
+    pin = torch.cuda.is_available()
+    meta = torch.as_tensor(meta)
+    return dict(records=rec.pin_memory() if pin else rec, meta=meta.pin_memory() if pin else meta, t=t)
+
+
+def upload_side(side, device):
+    """Enqueue the two H2D copies of one clip's packed side information (``pack_side``) on the current stream;
+    returns the device tensors (records, meta) and the bytes that cross the bus."""
+    rec = side["records"].to(device, non_blocking=True)
+    meta = side["meta"].to(device, non_blocking=True)
+    return rec, meta, rec.numel() * 4 + meta.numel() * 4
+
+
+def rasterize_uploaded(rec, meta, t, mvs, par, work, status):
+    """Rasterise uploaded side information (``upload_side``) into ``mvs`` (T,4,H,W) / ``par`` (T,3,H,W) on the CURRENT
+    stream without any host synchronisation; ``work`` (3,T,H,W) int32 is zeroed here, ``status`` accumulates the error
+    bits (check it with ``raise_for_status`` after a synchronisation)."""
+    h, w = mvs.shape[-2], mvs.shape[-1]
+    if tuple(mvs.shape) != (t, 4, h, w) or tuple(par.shape) != (t, 3, h, w) or meta.numel() != 3 * t + 1:
+        raise ValueError(f"side information of {t} frames does not match outputs {tuple(mvs.shape)} / {tuple(par.shape)}")
+    work.zero_()
+    _launch(rec, meta[:t + 1], meta[t + 1:2 * t + 1], meta[2 * t + 1:], t, h, w, work, mvs, par, status)
 
 
 def synthetic_records(h, w, pattern, seed=0, messy=False):

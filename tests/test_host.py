@@ -211,7 +211,7 @@ def test_clip_sharding_and_metric_gather_world2(num_clips):
     procs = [ctx.Process(target=_worker, args=(r, world, port, num_clips, t, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=120) for _ in range(world)]
+    got = [q.get(timeout=300) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -256,7 +256,7 @@ def test_frame_window_sharding_world2(num_clips, t, window, overlap):
              for r in range(world)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=120) for _ in range(world)]
+    got = [q.get(timeout=300) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -115,3 +115,60 @@ def test_rasterised_side_info_drives_the_generator(dev):
         b = net(args[0], args[1], args[2], torch.from_numpy(emv)[None].to(dev), args[4],
                 torch.from_numpy(epar)[None].to(dev))
     assert torch.equal(a, b)
+
+
+def _side_entries(h, w, t, n, seed0, oracle_dense):
+    """(dense host entries, compact host entries) of the same clips: the dense planes come from the numpy oracle
+    of the reference's loader loop (or are left to the caller), the compact form carries the records themselves."""
+    from pnpvcve_b200 import synthetic
+    dense, compact = [], []
+    for e in range(2):
+        clips, sides = [], []
+        for c in range(n):
+            clip = synthetic.make_clip(h, w, t, seed=seed0 + 10 * e + c, crf=(15, 35)[c % 2], ipb=True)
+            types = [chr(int(v)) for v in clip["slices"].flatten()]
+            recs = sideinfo.synthetic_records(h, w, types, seed=seed0 + 100 * e + c, messy=(c == 0))
+            flat = np.concatenate(recs, 0)
+            offs = np.cumsum([0] + [len(r) for r in recs])
+            emv, epar = oracle_dense(recs, types, h, w)
+            clip["mvs"], clip["partitions"] = torch.from_numpy(emv)[None], torch.from_numpy(epar)[None]
+            clips.append(clip)
+            sides.append(sideinfo.pack_side(flat, offs, types))
+        entry = synthetic.cat_clips(clips)
+        dense.append(entry)
+        compact.append(dict({k: v for k, v in entry.items() if k not in ("mvs", "partitions")}, side=sides))
+    return dense, compact
+
+
+@pytest.mark.gpu
+def test_enhance_clips_takes_compact_side_information(dev):
+    """driver.enhance_clips on host entries that carry the codec's per-block records (`side`) instead of the dense
+    mvs / partitions planes: records are uploaded and rasterised on the device inside the streamer -- the frames equal
+    those of the dense feed built by the ORACLE of the reference's loader loop, bit for bit, for n = 2 clips per entry,
+    with 1/50th of the side-information bytes over the bus."""
+    import pnpvcve_b200 as P
+    from pnpvcve_b200 import driver, weights
+    from test_gpu_parity import GENERATOR_CFG
+    net = P.build_backbone(dict(GENERATOR_CFG, num_blocks=2))
+    net.load_state_dict(weights.random_state_dict(2, num_blocks=2), strict=True)
+    net = net.to(dev).eval()
+    dense, compact = _side_entries(64, 96, 7, 2, 40, R.rasterize_clip)
+    outs_d, met_d = driver.enhance_clips(net, dense, device=dev, chunk=3)
+    outs_c, met_c = driver.enhance_clips(net, compact, device=dev, chunk=3)
+    torch.cuda.synchronize()
+    for a, b in zip(outs_d, outs_c):
+        assert b.is_pinned() and torch.equal(a, b)
+    assert torch.equal(met_d, met_c)
+    st = driver.ClipStreamer(net, dev, chunk=3)
+    st.upload(dense[0])
+    dense_bytes = st.h2d_bytes
+    st.upload(compact[0])
+    assert st.h2d_bytes < dense_bytes / 2
+    st.finish(check=True)
+    # malformed records surface as the reference loader's errors once the streamer is finished
+    bad = dict(compact[0])
+    rec = bad["side"][0]["records"].clone()
+    rec[0, 1:3] = 4.0                                     # 4x4 block: area 16 is not in the partition table
+    bad["side"] = [dict(bad["side"][0], records=rec.pin_memory()), bad["side"][1]]
+    with pytest.raises(KeyError):
+        driver.enhance_clips(net, [bad], device=dev)
