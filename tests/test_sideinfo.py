@@ -51,6 +51,19 @@ def test_synthetic_records_tile_the_frame():
     assert par[0].sum() == 0
 
 
+def test_pack_side_layout():
+    """Host form of the compact feed: records (R,10) fp32 + ONE int32 vector [offsets (T+1) | is_b (T) | p_target (T)]."""
+    recs = sideinfo.synthetic_records(32, 32, "IBPB", seed=1)
+    flat = np.concatenate(recs, 0)
+    offs = np.cumsum([0] + [len(r) for r in recs])
+    side = sideinfo.pack_side(flat, offs, list("IBPB"))
+    assert side["t"] == 4 and tuple(side["records"].shape) == (len(flat), 10) and side["records"].dtype == torch.float32
+    meta = side["meta"].tolist()
+    assert meta[:5] == offs.tolist() and meta[5:9] == [0, 1, 0, 1] and meta[9:] == sideinfo.p_targets("IBPB")
+    with pytest.raises(ValueError):
+        sideinfo.pack_side(flat, offs[:-1], list("IBPB"))
+
+
 # ------------------------------------------------------------------ GPU
 @pytest.fixture(scope="module")
 def dev():
