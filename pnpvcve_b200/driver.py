@@ -163,6 +163,10 @@ def enhance_windows(net, clips, window, rank=0, world=1, overlap=0, refs=None, g
     all_gather).  No collective touches the data path of a window."""
     from .synthetic import generator_args
     num_clips = len(clips)
+    if any("side" in c for c in clips):
+        # a P frame's reversed records write into the previous non-B frame, which may lie in another window
+        raise ValueError("frame windows are cut from dense mvs / partitions planes; rasterise compact side information "
+                         "first (pnpvcve_b200.sideinfo.rasterize_clip)")
     t = clips[0]["lq"].shape[1]
     # host-resident clips are streamed when `net` is the generator (anything else -- a stand-in callable in the CPU tests
     # of the sharding logic -- is simply called on the tensors where they are)

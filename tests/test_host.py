@@ -287,3 +287,12 @@ def test_clip_streamer_chunk_layout():
         assert all(owner[i][0] <= i < owner[i][1] for i in range(t))
     st.chunk = 10
     assert st._chunks(100)[-3:] == [(86, 94), (94, 98), (98, 100)]
+
+
+def test_frame_windows_reject_compact_side_information():
+    """Windows are cut from dense planes: a clip that carries per-block records instead raises before any work."""
+    from pnpvcve_b200 import driver
+    clip = synthetic.make_clip(64, 64, 4, seed=1)
+    compact = dict({k: v for k, v in clip.items() if k not in ("mvs", "partitions")}, side=[None])
+    with pytest.raises(ValueError, match="dense"):
+        driver.enhance_windows(_fake_net, [compact], 2)

@@ -154,7 +154,8 @@ def _side_entries(h, w, t, n, seed0, oracle_dense):
 
 
 @pytest.mark.gpu
-def test_enhance_clips_takes_compact_side_information(dev):
+@pytest.mark.parametrize("h,w,t,n", [(64, 96, 7, 2), (720, 1280, 4, 1)])
+def test_enhance_clips_takes_compact_side_information(dev, h, w, t, n):
     """driver.enhance_clips on host entries that carry the codec's per-block records (`side`) instead of the dense
     mvs / partitions planes: records are uploaded and rasterised on the device inside the streamer -- the frames equal
     those of the dense feed built by the ORACLE of the reference's loader loop, bit for bit, for n = 2 clips per entry,
@@ -165,7 +166,7 @@ def test_enhance_clips_takes_compact_side_information(dev):
     net = P.build_backbone(dict(GENERATOR_CFG, num_blocks=2))
     net.load_state_dict(weights.random_state_dict(2, num_blocks=2), strict=True)
     net = net.to(dev).eval()
-    dense, compact = _side_entries(64, 96, 7, 2, 40, R.rasterize_clip)
+    dense, compact = _side_entries(h, w, t, n, 40, R.rasterize_clip)
     outs_d, met_d = driver.enhance_clips(net, dense, device=dev, chunk=3)
     outs_c, met_c = driver.enhance_clips(net, compact, device=dev, chunk=3)
     torch.cuda.synchronize()
@@ -182,6 +183,6 @@ def test_enhance_clips_takes_compact_side_information(dev):
     bad = dict(compact[0])
     rec = bad["side"][0]["records"].clone()
     rec[0, 1:3] = 4.0                                     # 4x4 block: area 16 is not in the partition table
-    bad["side"] = [dict(bad["side"][0], records=rec.pin_memory()), bad["side"][1]]
+    bad["side"] = [dict(bad["side"][0], records=rec.pin_memory())] + list(bad["side"][1:])
     with pytest.raises(KeyError):
         driver.enhance_clips(net, [bad], device=dev)
