@@ -99,6 +99,29 @@ def pack_side(records, frame_offsets, slice_types):
     return dict(records=rec.pin_memory() if pin else rec, meta=meta.pin_memory() if pin else meta, t=t)
 
 
+def mv_record_path(frame_path, dataset="reds"):
+    """Where the reference's loader finds the motion-vector records of an LQ frame (loading_ipb.py:316-323):
+    ``.../png/.../00000012.png -> .../mv/.../00000012.npy``; vimeo septuplets ``.../png/.../im3.png -> .../mv/.../00000002.npy``."""
+    import os
+    if dataset == "vimeo":
+        d, idx = frame_path.split("/im")
+        return os.path.join(d.replace("png", "mv"), "{:08d}.npy".format(int(idx.split(".png")[0]) - 1))
+    return frame_path.replace(".png", ".npy").replace("png", "mv")
+
+
+def side_from_files(frame_paths, slice_types, dataset="reds"):
+    """The compact feed of one clip straight from the files the reference's loader reads: per LQ frame path the ``.npy``
+    record table next to it (``np.load(...).astype(np.float32)``, loading_ipb.py:325; an I frame's table may be empty or
+    missing rows) -> ``pack_side``.  Replaces the raster loop of ``LoadImageFromFileList_ipb`` (:328-369) plus
+    ``RescaleToZeroOne`` / ``FramesToTensor`` on ``mvs`` / ``partitions``: the planes are built on the GPU instead."""
+    if len(frame_paths) != len(slice_types):
+        raise ValueError("one slice type per frame path")
+    tables = [np.load(mv_record_path(str(p), dataset)).astype(np.float32).reshape(-1, 10) for p in frame_paths]
+    flat = np.concatenate(tables, 0) if tables else np.zeros((0, 10), np.float32)
+    offs = np.cumsum([0] + [len(tb) for tb in tables])
+    return pack_side(flat, offs, list(slice_types))
+
+
 def upload_side(side, device):
     """Enqueue the two H2D copies of one clip's packed side information (``pack_side``) on the current stream;
     returns the device tensors (records, meta) and the bytes that cross the bus."""

@@ -64,6 +64,28 @@ def test_pack_side_layout():
         sideinfo.pack_side(flat, offs[:-1], list("IBPB"))
 
 
+def test_side_from_files_follows_the_loader_paths(tmp_path):
+    """Record tables are found where LoadImageFromFileList_ipb looks for them (loading_ipb.py:316-325) and packed in
+    frame order; the oracle of the loader loop on the same tables gives the dense planes the GPU path must produce."""
+    pattern = "IBP"
+    recs = sideinfo.synthetic_records(32, 48, pattern, seed=4)
+    root = tmp_path / "crf25"
+    (root / "png" / "000").mkdir(parents=True)
+    (root / "mv" / "000").mkdir(parents=True)
+    paths = []
+    for f, r in enumerate(recs):
+        paths.append(str(root / "png" / "000" / f"{f:08d}.png"))
+        np.save(str(root / "mv" / "000" / f"{f:08d}.npy"), r.astype(np.float64))       # the codec tool writes float64
+    assert sideinfo.mv_record_path(paths[1]) == str(root / "mv" / "000" / "00000001.npy")
+    assert sideinfo.mv_record_path("/d/png/00001/0001/im3.png", "vimeo") == "/d/mv/00001/0001/00000002.npy"
+    side = sideinfo.side_from_files(paths, pattern)
+    assert side["t"] == 3 and side["records"].shape[0] == sum(len(r) for r in recs)
+    assert torch.equal(side["records"], torch.from_numpy(np.concatenate(recs, 0)))
+    assert side["meta"][:4].tolist() == np.cumsum([0] + [len(r) for r in recs]).tolist()
+    with pytest.raises(ValueError):
+        sideinfo.side_from_files(paths, "IB")
+
+
 # ------------------------------------------------------------------ GPU
 @pytest.fixture(scope="module")
 def dev():
