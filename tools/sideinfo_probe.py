@@ -35,7 +35,8 @@ def rate(c, tag):
     print(f"{tag}: {fps:.1f} frames/s; warp bracketed mean {sum(w) / len(w):.1f} us (min {min(w):.1f}, max {max(w):.1f}); launch A {sum(a_) / len(a_):.1f} us")
 
 
-rate(clip, "synthetic 8x8 block-constant fields")
-rate(clip2, "fields rasterised from records   ")
+for _ in range(3):          # alternate: under the power cap the rate drifts down over the first seconds of load
+    rate(clip, "synthetic 8x8 block-constant fields")
+    rate(clip2, "fields rasterised from records   ")
 rate(dict(clip, mvs=clip2["mvs"]), "records mvs + synthetic partitions")
 rate(dict(clip, partitions=clip2["partitions"]), "synthetic mvs + records partitions")
