@@ -424,7 +424,7 @@ def main():
         # Per-kernel durations come from a SEPARATE pass of the same steps, right behind the timed one (same
         # clocks, same thermal state): an event record between two launches defeats programmatic dependent
         # launch for both neighbours, and bracketing every 8th launch was measured to slow the whole step by
-        # ~10 % (tools/seq_test.py: 151 -> 167 us per block).  `value` is therefore timed without any events
+        # ~10 % (round-1 measurement: 151 -> 167 us per block).  `value` is therefore timed without any events
         # inside the step; the bracketed durations below include the launch overhead PDL normally hides.
         net._engine.prof = {"block": [], "block_a": [], "warp": [], "block_b": []}
         net._engine.prof_every = args.prof_every

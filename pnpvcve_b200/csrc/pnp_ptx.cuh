@@ -221,7 +221,7 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // Shared-memory matrix descriptor, K-major operand stored as 128-byte rows with the 128B swizzle
 // (the layout TMA writes for a box whose inner extent is 64 bf16): 8-row atoms of 1024 bytes,
 // SBO = 1024.  `start` may be any 16-byte aligned address inside a 1024-aligned tile: measured on
-// B200 (tools/gpu_probe.py, profiles/r01_probe.log) the hardware applies the swizzle XOR to the
+// B200 (round-1 probe, profiles/r01_probe.log) the hardware applies the swizzle XOR to the
 // absolute shared-memory address bits, so a view that starts k pixels (k*128 bytes) into a TMA-written
 // tile reads the right data with base_offset = 0; setting base_offset = (start >> 7) & 7 as the PTX
 // ISA text suggests for unaligned starts double-counts the phase and returns garbage.
@@ -413,7 +413,7 @@ __device__ __forceinline__ uint32_t spin_until_ge_v(uint32_t addr, uint32_t targ
 }
 
 // ------------------------------------------------------------------ thread-block clusters / DSMEM
-// Used by the CTA-pair residual-block kernel (pnp_block.cu).  Measured on B200 (tools/dsmem_bench.cu,
+// Cluster / DSMEM helpers (the CTA-pair conv form; first used by round 1's fused residual-block kernel).  Measured on B200 (round-1 microbenchmark,
 // profiles/r01_dsmem_bench.log): the SM-to-SM path moves 21.3 B/cycle with 512 contiguous bytes per
 // warp store or with cp.async.bulk, but only 10.7 B/cycle when each lane writes 16 B at a 128 B stride.
 __device__ __forceinline__ uint32_t cluster_ctarank() {
