@@ -101,11 +101,17 @@ def pack_side(records, frame_offsets, slice_types):
 
 def mv_record_path(frame_path, dataset="reds"):
     """Where the reference's loader finds the motion-vector records of an LQ frame (loading_ipb.py:316-323):
-    ``.../png/.../00000012.png -> .../mv/.../00000012.npy``; vimeo septuplets ``.../png/.../im3.png -> .../mv/.../00000002.npy``."""
+    ``.../png/.../00000012.png -> .../mv/.../00000012.npy``; vimeo septuplets ``.../png/.../im3.png -> .../mv/.../00000002.npy``;
+    KITTI pairs (loading_ipb_kitti.py, same raster loop) ``<root>/png/.../000012_11.png -> <root>/mv/000012/00000001.npy``."""
     import os
     if dataset == "vimeo":
         d, idx = frame_path.split("/im")
         return os.path.join(d.replace("png", "mv"), "{:08d}.npy".format(int(idx.split(".png")[0]) - 1))
+    if dataset == "kitti":
+        # loading_ipb_kitti.py:102-103,127-129: frames are named <sequence>_<index>.png, index 10 is the first frame
+        name = os.path.basename(frame_path)
+        seq, idx = name.split("_")[0], name.split("_")[1].split(".")[0]
+        return "{}/mv/{}/{:08d}.npy".format(frame_path.split("/png/")[0], seq, int(idx) - 10)
     return frame_path.replace(".png", ".npy").replace("png", "mv")
 
 

@@ -78,6 +78,7 @@ def test_side_from_files_follows_the_loader_paths(tmp_path):
         np.save(str(root / "mv" / "000" / f"{f:08d}.npy"), r.astype(np.float64))       # the codec tool writes float64
     assert sideinfo.mv_record_path(paths[1]) == str(root / "mv" / "000" / "00000001.npy")
     assert sideinfo.mv_record_path("/d/png/00001/0001/im3.png", "vimeo") == "/d/mv/00001/0001/00000002.npy"
+    assert sideinfo.mv_record_path("/d/x_crf25/png/000012_11.png", "kitti") == "/d/x_crf25/mv/000012/00000001.npy"
     side = sideinfo.side_from_files(paths, pattern)
     assert side["t"] == 3 and side["records"].shape[0] == sum(len(r) for r in recs)
     assert torch.equal(side["records"], torch.from_numpy(np.concatenate(recs, 0)))
