@@ -105,15 +105,18 @@ int pnp_mv_warp_dyn(const pnp_dyn_ref* dyn, const void* src_pool, int src_pool_i
                     int64_t flow_image_stride, int N, int H, int W, void* stream);
 
 /*
- * LR frames -> im2col'd bf16 operand (N, H, W, 64), channel k = tap*3 + c for k < 27, zero for
- * 27..31; channels 32..63 are not written (allocate the buffer zeroed once).  Carries the
- * 3-channel slice of the reference's input conv (basicvsr_net.py:484 on the cat at
- * iconvsr_ipb_par.py:90,125).  lr is an fp32 (N,3,H,W) view with element strides sn, sc, sy (x: 1).
+ * LR frames -> im2col'd bf16 operand (N, H, W, dst_channels), channel k = tap*3 + c for k < 27, zero for
+ * 27..31.  dst_channels = 32: 64-byte pixels, every byte written (the operand the conv reads through a
+ * SWIZZLE_64B tile, pnp_conv_desc.aux_channels = 32); dst_channels = 64: 128-byte pixels whose channels 32..63
+ * are not written (allocate the buffer zeroed once).  Carries the 3-channel slice of the reference's input conv
+ * (basicvsr_net.py:484 on the cat at iconvsr_ipb_par.py:90,125).  lr is an fp32 (N,3,H,W) view with element
+ * strides sn, sc, sy (x: 1).
  */
 int pnp_lr_im2col(const float* lr, int64_t sn, int64_t sc, int64_t sy, void* dst, int N, int H, int W,
-                  void* stream);
+                  int dst_channels, void* stream);
 /* table mode: lr / dst come from the launch table */
-int pnp_lr_im2col_dyn(const pnp_dyn_ref* dyn, int64_t sn, int64_t sc, int64_t sy, int N, int H, int W, void* stream);
+int pnp_lr_im2col_dyn(const pnp_dyn_ref* dyn, int64_t sn, int64_t sc, int64_t sy, int N, int H, int W, int dst_channels,
+                      void* stream);
 
 /*
  * K4 -- weight packing (run once per checkpoint / once per distinct (CRF, QP) condition, results stay resident).
@@ -211,7 +214,7 @@ enum { PNP_ACT_NONE = 0, PNP_ACT_LRELU = 1, PNP_ACT_RELU = 2 };
 
 typedef struct pnp_conv_desc {
   const void* src;     /* bf16 (N,H,W,64) */
-  const void* aux;     /* bf16 (N,H,W,64) im2col'd LR, or NULL */
+  const void* aux;     /* bf16 (N,H,W,64) -- or (N,H,W,32), see aux_channels -- im2col'd LR, or NULL */
   const void* idt;     /* bf16 (N,H,W,64) added before the activation, or NULL */
   void* out;           /* bf16 (N,H,W,64); PNP_CONV_BF16 only */
   const void* wpack;   /* pnp_pack_conv3x3_rowstack output (9*tap_n*128 bytes), followed by the 8192-byte
@@ -258,6 +261,9 @@ typedef struct pnp_conv_desc {
      features and the work buffers -- and bias / par / lq / outf / aux / idt only say (non-NULL) that the operand exists. */
   pnp_dyn_ref dyn;
   int32_t src_images, aux_images, idt_images, out_images;
+  int32_t aux_channels; /* channels per pixel of `aux`: 64 (or 0) = a (N,H,W,64) tensor; 32 = a (N,H,W,32) tensor of 64-byte
+                          pixels as pnp_lr_im2col writes it with dst_channels = 32 (aux_k16 <= 2) */
+  int32_t reserved0;
 } pnp_conv_desc;
 
 int pnp_conv3x3(const pnp_conv_desc* desc, void* stream);

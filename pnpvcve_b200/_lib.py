@@ -48,6 +48,7 @@ class ConvDesc(_c.Structure):
         ("img_off", _vp),
         ("dyn", DynRef),
         ("src_images", _c.c_int32), ("aux_images", _c.c_int32), ("idt_images", _c.c_int32), ("out_images", _c.c_int32),
+        ("aux_channels", _c.c_int32), ("reserved0", _c.c_int32),
     ]
 
 
@@ -68,10 +69,10 @@ _PROTOS = {
     "pnp_set_step": (_i, [_vp, _c.c_int32, _vp]),
     "pnp_fetch_pinned": (_i, [_vp, _vp, _i64, _vp]),
     "pnp_mv_warp_dyn": (_i, [_c.POINTER(DynRef), _vp, _i, _i64, _i64, _i, _i, _i, _vp]),
-    "pnp_lr_im2col_dyn": (_i, [_c.POINTER(DynRef), _i64, _i64, _i64, _i, _i, _i, _vp]),
+    "pnp_lr_im2col_dyn": (_i, [_c.POINTER(DynRef), _i64, _i64, _i64, _i, _i, _i, _i, _vp]),
     "pnp_pack_mix_blocks": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i64, _vp]),
     "pnp_mv_warp": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _vp, _vp, _vp]),
-    "pnp_lr_im2col": (_i, [_vp, _i64, _i64, _i64, _vp, _i, _i, _i, _vp]),
+    "pnp_lr_im2col": (_i, [_vp, _i64, _i64, _i64, _vp, _i, _i, _i, _i, _vp]),
     "pnp_pack_conv3x3_rowstack": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "pnp_pack_rows": (_i, [_vp, _i, _i, _i64, _i64, _vp, _i, _vp]),
     "pnp_pack_aux": (_i, [_vp, _i, _i, _vp, _vp]),

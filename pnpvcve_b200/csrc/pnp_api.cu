@@ -152,21 +152,24 @@ EncodeTiledFn encode_fn() {
 
 // (64, W, H, N) bf16 NHWC tensor, box (64, box_w, 1, 1), 128-byte swizzle, zero fill out of range.
 // spx/sy/sn: element strides between pixels / rows / images (0 = contiguous NHWC).
+// ch = 32: a (32, W, H, N) tensor of 64-byte pixels, box (32, box_w, 1, 1), 64-byte swizzle (the LR im2col operand).
 int make_map(CUtensorMap* m, const void* base, int N, int H, int W, int box_w, long long spx = 0, long long sy = 0,
-             long long sn = 0, int box_h = 1) {
+             long long sn = 0, int box_h = 1, int ch = 64) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(PNP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+  const cuuint64_t px = (cuuint64_t)ch * 2;
+  cuuint64_t dims[4] = {(cuuint64_t)ch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {px, (cuuint64_t)W * px, (cuuint64_t)H * W * px};
   if (spx != 0) {
     strides[0] = (cuuint64_t)spx * 2;
     strides[1] = (cuuint64_t)sy * 2;
     strides[2] = (cuuint64_t)sn * 2;
   }
-  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t box[4] = {(cuuint32_t)ch, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, ch == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -181,11 +184,11 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 extern "C" {
 
-static_assert(sizeof(pnp_conv_desc) == 272 && offsetof(pnp_conv_desc, out_spx) == 184 &&
+static_assert(sizeof(pnp_conv_desc) == 280 && offsetof(pnp_conv_desc, out_spx) == 184 &&
                   offsetof(pnp_conv_desc, img_off) == 224 && offsetof(pnp_conv_desc, dyn) == 232 &&
-                  offsetof(pnp_conv_desc, src_images) == 256,
+                  offsetof(pnp_conv_desc, src_images) == 256 && offsetof(pnp_conv_desc, aux_channels) == 272,
               "pnp_conv_desc layout is part of the ABI (mirrored by pnpvcve_b200/_lib.py: ConvDesc)");
-int pnp_abi_version(void) { return 9; }
+int pnp_abi_version(void) { return 10; }
 
 const char* pnp_last_error(void) { return g_err; }
 
@@ -308,23 +311,28 @@ int pnp_mv_warp_dyn(const pnp_dyn_ref* dyn, const void* src_pool, int src_pool_i
 }
 
 int pnp_lr_im2col(const float* lr, int64_t sn, int64_t sc, int64_t sy, void* dst, int N, int H, int W,
-                  void* stream) {
+                  int dst_channels, void* stream) {
   if (!lr || !dst) return fail(PNP_ERR_ARG, "pnp_lr_im2col: null pointer");
-  if (N <= 0 || H <= 0 || W <= 0 || !aligned16(dst)) return fail(PNP_ERR_ARG, "pnp_lr_im2col: bad argument");
+  if (N <= 0 || H <= 0 || W <= 0 || !aligned16(dst) || (dst_channels != 64 && dst_channels != 32))
+    return fail(PNP_ERR_ARG, "pnp_lr_im2col: bad argument (dst_channels is 64 or 32)");
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
-  cudaError_t e = pnp::launch_lr_im2col(lr, sn, sc, sy, dst, N, H, W, dyn_ref(nullptr), static_cast<cudaStream_t>(stream));
+  cudaError_t e = pnp::launch_lr_im2col(lr, sn, sc, sy, dst, N, H, W, dst_channels, dyn_ref(nullptr),
+                                        static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_lr_im2col");
 }
 
-int pnp_lr_im2col_dyn(const pnp_dyn_ref* dyn, int64_t sn, int64_t sc, int64_t sy, int N, int H, int W, void* stream) {
+int pnp_lr_im2col_dyn(const pnp_dyn_ref* dyn, int64_t sn, int64_t sc, int64_t sy, int N, int H, int W, int dst_channels,
+                      void* stream) {
   if (!dyn || !dyn->table || !dyn->step) return fail(PNP_ERR_ARG, "pnp_lr_im2col_dyn: null launch table");
-  if (N <= 0 || H <= 0 || W <= 0) return fail(PNP_ERR_ARG, "pnp_lr_im2col_dyn: bad shape");
+  if (N <= 0 || H <= 0 || W <= 0 || (dst_channels != 64 && dst_channels != 32))
+    return fail(PNP_ERR_ARG, "pnp_lr_im2col_dyn: bad shape (dst_channels is 64 or 32)");
   DeviceInfo* d;
   int rc = device_info(&d);
   if (rc) return rc;
-  cudaError_t e = pnp::launch_lr_im2col(nullptr, sn, sc, sy, nullptr, N, H, W, dyn_ref(dyn), static_cast<cudaStream_t>(stream));
+  cudaError_t e = pnp::launch_lr_im2col(nullptr, sn, sc, sy, nullptr, N, H, W, dst_channels, dyn_ref(dyn),
+                                        static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? PNP_OK : cuda_fail(e, "pnp_lr_im2col_dyn");
 }
 
@@ -471,6 +479,10 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   }
   if ((c->aux != nullptr) != (c->aux_k16 > 0) || c->aux_k16 < 0 || c->aux_k16 > 4)
     return fail(PNP_ERR_ARG, "pnp_conv3x3: aux / aux_k16 mismatch");
+  const bool aux32 = c->aux && c->aux_channels == 32;
+  if (c->aux && c->aux_channels != 0 && c->aux_channels != 64 && !aux32)
+    return fail(PNP_ERR_ARG, "pnp_conv3x3: aux_channels is 64 (or 0) or 32");
+  if (aux32 && c->aux_k16 > 2) return fail(PNP_ERR_ARG, "pnp_conv3x3: a 32-channel aux source carries K <= 32");
   if (par && (c->aux || c->idt)) return fail(PNP_ERR_ARG, "pnp_conv3x3: par takes no aux / idt");
   if (c->act < 0 || c->act > 2) return fail(PNP_ERR_ARG, "pnp_conv3x3: bad act");
   const bool strided_out = c->out_spx != 0 || c->out_sy != 0 || c->out_sn != 0;
@@ -495,7 +507,9 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   memset(&p, 0, sizeof(p));
   auto images = [&](int32_t n) { return n > 0 ? n : c->N; };
   if ((rc = make_map(&p.tm_src, c->src, images(c->src_images), c->H, c->W, pnp::kHaloPx))) return rc;
-  if (c->aux && (rc = make_map(&p.tm_aux, c->aux, images(c->aux_images), c->H, c->W, pnp::kTilePx))) return rc;
+  if (c->aux && (rc = make_map(&p.tm_aux, c->aux, images(c->aux_images), c->H, c->W, pnp::kTilePx, 0, 0, 0, 1,
+                               aux32 ? 32 : 64)))
+    return rc;
   if (c->idt && (rc = make_map(&p.tm_id, c->idt, images(c->idt_images), c->H, c->W, pnp::kTilePx))) return rc;
   if (!last && (rc = make_map(&p.tm_out, c->out, images(c->out_images), c->H, c->W, pnp::kTilePx, c->out_spx, c->out_sy,
                               c->out_sn)))
@@ -524,7 +538,8 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   // (taken only when that wastes < 7 %), and with per-image weights both columns of a pair must belong to one image.
   const long long cols = (long long)c->N * p.strips;
   const int pair_mode = g_pair_override >= 0 ? g_pair_override : kn.pair;
-  const bool pair_ok = pair_mode != 0 && !last && c->tap_n == 64 && d->max_pairs >= 8 && (!par || kn.par_split) &&
+  // (a 32-channel aux source is wired for the single-CTA form only: both forms compute identical values)
+  const bool pair_ok = pair_mode != 0 && !last && !aux32 && c->tap_n == 64 && d->max_pairs >= 8 && (!par || kn.par_split) &&
                        (c->per_image ? (p.strips % 2 == 0 && c->N <= d->max_pairs)
                                      : (cols % 2 == 0 || cols >= 15 || pair_mode == 2));
   int grid;
@@ -564,6 +579,7 @@ int pnp_conv3x3(const pnp_conv_desc* c, void* stream) {
   }
   p.tap_n = c->tap_n;
   p.aux_k16 = c->aux_k16;
+  p.aux_pitch64 = aux32 ? 1 : 0;
   p.has_id = c->idt != nullptr;
   p.act = c->act;
   p.mode = last ? pnp::kModeLast : pnp::kModeBf16;

@@ -42,7 +42,7 @@ struct DynRef {
 
 struct ConvParams {
   CUtensorMap tm_src;   // (64, W, H, images) bf16, box (64,130,1,1), SWIZZLE_128B
-  CUtensorMap tm_aux;   // box (64,128,1,1)
+  CUtensorMap tm_aux;   // box (64,128,1,1); aux_pitch64: (32,128,1,1), SWIZZLE_64B
   CUtensorMap tm_id;    // box (64,128,1,1)
   CUtensorMap tm_out;   // box (64,128,1,1)
   DynRef dyn;           // table mode: conv entry = p{wpack, bias, par, lq, outf, img_off}, i{src_f, aux_f, idt_f, out_f}
@@ -63,6 +63,7 @@ struct ConvParams {
   int has_bias;
   int tap_n;            // N of one dy sub-block: 64, or 16 for the 64->3 tail
   int aux_k16;          // K/16 of the aux source (centre row only); 0 = no aux
+  int aux_pitch64;      // the aux source is a (N,H,W,32) tensor: 64-byte pixels, SWIZZLE_64B tiles of 8 KB (single-CTA form only)
   int has_id;
   int act;
   int mode;

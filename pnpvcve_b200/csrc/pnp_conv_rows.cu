@@ -349,7 +349,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
                 tma_load_4d_pair(aux_smem + as * kTileBytes, &p.tm_aux, mapa_shared(ab, 0), 0, x0, PNP_Y(s.y_b + j),
                                  s.n + aux_f);
               } else {
-                mbar_arrive_expect_tx(ab, kTileBytes);
+                mbar_arrive_expect_tx(ab, p.aux_pitch64 ? kTileBytes / 2 : kTileBytes);
                 tma_load_4d(aux_smem + as * kTileBytes, &p.tm_aux, ab, 0, x0, PNP_Y(s.y_b + j), s.n + aux_f);
               }
             }
@@ -373,6 +373,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
       const uint32_t dxb = (uint32_t)dx_block_bytes >> 4;      // descriptor units per dx block
       const uint32_t sbb = (uint32_t)(tap_n * 128) >> 4;       // ... per dy sub-block
       const uint32_t aux_w_lo = w_lo + 3 * dxb;                 // LR im2col block (aux) ...
+      const uint32_t aux_a_hi = p.aux_pitch64 ? kDescHiSw64 : kDescHiSw128;   // 64-byte or 128-byte aux pixels
       const uint32_t par_w_lo = w_lo + 3 * dxb;                 // ... or the stacked 1x1 block (kPar)
       // pair mode: this CTA's halves -- N-split dx blocks at w_lo, per-sub-block-split blocks behind them
       const uint32_t u192 = dxb >> 1, u64 = sbb >> 1, w64_lo = w_lo + 3 * (dxb >> 1);
@@ -602,7 +603,7 @@ conv3x3_rows_kernel(const __grid_constant__ ConvParams p) {
               umma2_bf16_lo<0>(tmem_base + (cur_od % kAccRing) * tap_n, a_lo + 2 * k, aux_w_lo + 2 * k,
                                idesc0 + idesc_step, 1);
             else
-              umma_bf16_lo(tmem_base + (cur_od % kAccRing) * tap_n, a_lo + 2 * k, kDescHiSw128,
+              umma_bf16_lo(tmem_base + (cur_od % kAccRing) * tap_n, a_lo + 2 * k, aux_a_hi,
                            aux_w_lo + 2 * k, kDescHiSw128, idesc0 + idesc_step, 1);
           }
         }

@@ -281,7 +281,7 @@ cudaError_t launch_mv_warp(const CUtensorMap& tm_src, const CUtensorMap& tm_dst,
 constexpr int kI2cW = 64, kI2cH = 4;
 __global__ void __launch_bounds__(256)
 lr_im2col_kernel(const float* __restrict__ lr, long long sn, long long sc, long long sy, uint4* __restrict__ dst,
-                 int N, int H, int W, const DynRef dyn) {
+                 int N, int H, int W, int px16, const DynRef dyn) {   // px16: 16-byte chunks per destination pixel (8 | 4)
   __shared__ float win[3][kI2cH + 2][kI2cW + 2];
   if (const DynEntry* e = dyn.entry()) {                  // table mode: p{lr, dst}
     lr = reinterpret_cast<const float*>(e->p[0]);
@@ -302,9 +302,9 @@ lr_im2col_kernel(const float* __restrict__ lr, long long sn, long long sc, long 
   // Each thread builds its pixel's 27-entry operand (static indexing) and parks the 64 used bytes in shared memory;
   // the tile then leaves as 16-byte chunks with a quad of lanes per pixel (two full 32-byte sectors per pixel and
   // store instruction).  Measured (tools/im2col_bench.py, 720p, cold): 27.4 us with 27 scalar global loads and
-  // per-thread stores, 28.9 with the staged window only, 26.7 like this -- the kernel is bound by writing HALF of
-  // every 128-byte line (59 MB useful at the DRAM cost of 118 MB); a 64-byte-pitch operand would need a
-  // SWIZZLE_64B aux path in the conv kernels.
+  // per-thread stores, 28.9 with the staged window only, 26.7 like this -- with 128-byte destination pixels the kernel
+  // is bound by writing HALF of every 128-byte line (59 MB useful at the DRAM cost of 118 MB); with 64-byte pixels
+  // (dst_channels = 32, the conv kernels' SWIZZLE_64B aux path) the stores are contiguous.
   __shared__ uint4 otile[kI2cW * kI2cH][4];
   {
     const int tx = threadIdx.x % kI2cW, ty = threadIdx.x / kI2cW;
@@ -326,15 +326,15 @@ lr_im2col_kernel(const float* __restrict__ lr, long long sn, long long sc, long 
     const int item = it * 256 + threadIdx.x;
     const int px = item >> 2, q = item & 3;
     const int x = x0 + px % kI2cW, y = y0 + px / kI2cW;
-    if (x < W && y < H) dst[((size_t)((size_t)n * H + y) * W + x) * 8 + q] = otile[px][q];
+    if (x < W && y < H) dst[((size_t)((size_t)n * H + y) * W + x) * px16 + q] = otile[px][q];
   }
 }
 
 cudaError_t launch_lr_im2col(const float* lr, long long sn, long long sc, long long sy, void* dst, int N,
-                             int H, int W, const DynRef& dyn, cudaStream_t stream) {
+                             int H, int W, int dst_channels, const DynRef& dyn, cudaStream_t stream) {
   if ((H + kI2cH - 1) / kI2cH > 65535 || N > 65535) return cudaErrorInvalidValue;
   dim3 grid((W + kI2cW - 1) / kI2cW, (H + kI2cH - 1) / kI2cH, N);
-  lr_im2col_kernel<<<grid, 256, 0, stream>>>(lr, sn, sc, sy, reinterpret_cast<uint4*>(dst), N, H, W, dyn);
+  lr_im2col_kernel<<<grid, 256, 0, stream>>>(lr, sn, sc, sy, reinterpret_cast<uint4*>(dst), N, H, W, dst_channels / 8, dyn);
   return cudaGetLastError();
 }
 

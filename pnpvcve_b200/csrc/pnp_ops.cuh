@@ -19,7 +19,7 @@ cudaError_t launch_mv_warp(const CUtensorMap& tm_src, const CUtensorMap& tm_dst,
                            int* dbg_x0, int* dbg_y0, const DynRef& dyn, const void* pool_base, int use_tma,
                            cudaStream_t stream);
 cudaError_t launch_lr_im2col(const float* lr, long long sn, long long sc, long long sy, void* dst, int N,
-                             int H, int W, const DynRef& dyn, cudaStream_t stream);
+                             int H, int W, int dst_channels, const DynRef& dyn, cudaStream_t stream);
 cudaError_t launch_fetch_pinned(const void* src_dev_view, void* dst, long long bytes, cudaStream_t stream);
 cudaError_t launch_pack_mix_blocks(const float* w2, const float* w1x1, int n_blocks, int n_experts, const float* coef,
                                    const float* row_scale, void* dst, long long dst_stride, cudaStream_t stream);

@@ -257,6 +257,9 @@ __device__ __forceinline__ bool elect_one() {
 }
 // High word shared by every K-major SWIZZLE_128B descriptor here: SBO=1024, version 1, swizzle 128B.
 constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+// K-major operand stored as 64-byte rows with the 64B swizzle (what TMA writes for a box whose inner extent is 32 bf16):
+// 8-row atoms of 512 bytes, SBO = 512, layout type SWIZZLE_64B.  K = 32 per row: the two K=16 slices are 32 bytes apart.
+constexpr uint32_t kDescHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);
 // Low word: start address (>>4) and LBO=1.  Advancing by n bytes == adding n/16 to the low word.
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t start) {
   return ((start & 0x3FFFFu) >> 4) | (1u << 16);

@@ -32,7 +32,7 @@ from .ops import PNP_ACT_LRELU, PNP_ACT_NONE, PNP_ACT_RELU
 
 SLICE_I, SLICE_P = 73, 80
 ROW_BYTES = 9 * 64 * 128           # one row-stacked 64->64 pack
-WORK = ("kw", "pa", "pb", "xa", "xb", "t", "hr", "lr64", "zero")
+WORK = ("kw", "pa", "pb", "xa", "xb", "t", "hr", "zero")
 
 
 def key_schedule(key_row):
@@ -97,11 +97,13 @@ class _Program:
         self.key = (n, t, h, w, dev, maxn, nb, vsr, lr_once)
         self.n, self.t, self.h, self.w, self.dev, self.maxn, self.nb, self.vsr = n, t, h, w, dev, maxn, nb, vsr
         self.img_bytes = h * w * 128
-        # lr_once: the LR im2col operand of EVERY frame stays in the pool (images [t*n, 2*t*n), frame-major like feats):
-        # the backward-time pass writes it, the forward-time pass reads it again instead of recomputing it
+        # The LR im2col operand lives in its own (images, H, W, 32) tensor of 64-byte pixels (SWIZZLE_64B aux tiles).
+        # lr_once: one image per frame and clip (frame-major like feats) -- the backward-time pass writes it, the
+        # forward-time pass reads it again instead of recomputing it; otherwise one image per clip of a run.
         self.lr_once = lr_once
-        self.lr_base = t * n if lr_once else None
-        first_work = (2 if lr_once else 1) * t * n
+        self.lr = torch.zeros((t * n if lr_once else maxn, h, w, 32), dtype=torch.bfloat16, device=dev)
+        self.lr_img_bytes = h * w * 64
+        first_work = t * n
         self.pool_images = first_work + len(WORK) * maxn
         self.pool = torch.empty((self.pool_images, h, w, 64), dtype=torch.bfloat16, device=dev)
         self.feats = self.pool[: t * n].view(t, n, h, w, 64)      # frame-major: a run of clips at one frame is contiguous
@@ -109,10 +111,7 @@ class _Program:
         for k, name in enumerate(WORK):
             f0 = first_work + k * maxn
             self.work[name] = (f0, self.pool[f0:f0 + maxn])
-        self.work["lr64"][1].zero_()
         self.work["zero"][1].zero_()
-        if lr_once:
-            self.pool[t * n:2 * t * n].zero_()
         if vsr:      # x4 tail: 2Hx2W and 4Hx4W feature maps of one frame step
             self.u1 = ops.new_feature(maxn, 2 * h, 2 * w, dev)
             self.u2 = ops.new_feature(maxn, 4 * h, 4 * w, dev)
@@ -310,7 +309,7 @@ class BaeEngine:
     def _program(self, n, t, h, w, dev, maxn, steps):
         # LR im2col once per frame instead of once per pass: costs a second t*n-image region of the pool, taken when
         # it is small against the device (PNP_LR_ONCE=0/1 forces it off / on)
-        extra = t * n * h * w * 128
+        extra = t * n * h * w * 64
         lr_once = self.lr_once if self.lr_once is not None else \
             extra <= torch.cuda.get_device_properties(dev).total_memory // 8
         key = (n, t, h, w, dev, maxn, self.m.num_blocks, bool(self.m.vsr), lr_once)
@@ -338,7 +337,8 @@ class BaeEngine:
             d = ops.ConvDesc()
             d.src = src.data_ptr() if src is not None else pool_ptr
             d.src_images = 0 if src is not None else pg.pool_images
-            d.aux, d.aux_images = (pool_ptr, pg.pool_images) if aux else (None, 0)
+            d.aux, d.aux_images = (pg.lr.data_ptr(), pg.lr.shape[0]) if aux else (None, 0)
+            d.aux_channels = 32 if aux else 0
             d.idt, d.idt_images = (pool_ptr, pg.pool_images) if idt else (None, 0)
             d.out_spx = d.out_sy = d.out_sn = 0
             if last:
@@ -374,7 +374,7 @@ class BaeEngine:
         def im2col():
             r = dyn(len(nodes))
             sn, sc, sy = shapes["lq"]
-            nodes.append(("im2col", "im2col", (lib.pnp_lr_im2col_dyn, ctypes.byref(r), r, sn, sc, sy, nn, h, w)))
+            nodes.append(("im2col", "im2col", (lib.pnp_lr_im2col_dyn, ctypes.byref(r), r, sn, sc, sy, nn, h, w, 32)))
 
         def warp():
             r = dyn(len(nodes))
@@ -463,15 +463,15 @@ class BaeEngine:
             tab[sel, node, 7] = iv[2] | (iv[3] << 32)
 
         W = {k: v.data_ptr() for k, v in st.items() if isinstance(v, torch.Tensor)}
-        # pool image of the frame's LR im2col operand: its own per-frame image (lr_once) or the one work buffer
-        lr64 = (pg.lr_base + frame * n + b0) if pg.lr_once else np.full(2 * t, work["lr64"], dtype=np.int64)
+        # image of the frame's LR im2col operand in pg.lr: its own per-frame image (lr_once) or the run's first image
+        lr64 = (frame * n + b0) if pg.lr_once else np.zeros(2 * t, dtype=np.int64)
         for v in set(variants):
             sel = var == v
             bwd = v.startswith("b_")
             br = 0 if bwd else 1
             node = 0
             if bwd or not pg.lr_once:
-                put(sel, node, p=(lr_ptr, pool_ptr + lr64 * img))                # im2col
+                put(sel, node, p=(lr_ptr, pg.lr.data_ptr() + lr64 * pg.lr_img_bytes))   # im2col
                 node += 1
             cur = feats(frame)
             if v not in ("b_last", "f_first"):
@@ -669,7 +669,7 @@ class BaeEngine:
                 elif kind == "warp":
                     rc = a[0](a[1], a[3], a[4], a[5], a[6], a[7], a[8], a[9], stream)
                 else:
-                    rc = a[0](a[1], a[3], a[4], a[5], a[6], a[7], a[8], stream)
+                    rc = a[0](a[1], a[3], a[4], a[5], a[6], a[7], a[8], a[9], stream)
                 if timed:
                     e1.record()
                     prof[label].append((e0, e1))

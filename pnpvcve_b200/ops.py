@@ -96,17 +96,24 @@ def mv_warp(src, flow, dst, debug=False):
     return (dx, dy) if debug else None
 
 
+def _aux_check(t, name):
+    """LR im2col operand: contiguous bf16 (N,H,W,64) with 32 channels used, or the compact (N,H,W,32) form."""
+    if not (t.dtype == torch.bfloat16 and t.dim() == 4 and t.shape[-1] in (32, 64) and t.is_contiguous() and t.is_cuda):
+        raise ValueError(f"{name} must be a contiguous bf16 (N,H,W,64) or (N,H,W,32) CUDA tensor, got "
+                         f"{tuple(t.shape)} {t.dtype}")
+
+
 @_on_device_of
 def lr_im2col(lr, dst):
-    """lr (N,3,H,W) fp32 view -> dst (N,H,W,64) bf16 (channels 0..31 written)."""
+    """lr (N,3,H,W) fp32 view -> dst (N,H,W,64) bf16 (channels 0..31 written) or the compact (N,H,W,32) form."""
     _plane_view_check(lr, "lr")
-    _feat_check(dst, "dst")
+    _aux_check(dst, "dst")
     n, c, h, w = lr.shape
-    if c != 3 or dst.shape != (n, h, w, 64):
+    if c != 3 or tuple(dst.shape[:3]) != (n, h, w):
         raise ValueError("lr_im2col: shape mismatch")
     lib = _lib.load()
     _lib.check(lib.pnp_lr_im2col(_ptr(lr), lr.stride(0), lr.stride(1), lr.stride(2), _ptr(dst), n, h, w,
-                                 _stream()), "pnp_lr_im2col")
+                                 int(dst.shape[3]), _stream()), "pnp_lr_im2col")
 
 
 def rowstack_bytes(tap_n=64, with_aux=False, with_par=False):
@@ -232,6 +239,7 @@ def fill_conv_desc(d, src, wpack, out=None, aux=None, idt=None, scale=None, bias
     d.N, d.H, d.W = n, h, w
     d.tap_n = 16 if last else 64
     d.aux_k16 = 2 if aux is not None else 0
+    d.aux_channels = int(aux.shape[3]) if aux is not None else 0
     d.act = act
     d.mode = PNP_CONV_LAST if last else PNP_CONV_BF16
     d.flip_y = 1 if flip_y else 0
@@ -252,11 +260,15 @@ def conv3x3(src, wpack, out=None, aux=None, idt=None, scale=None, bias=None, par
     bilinear upsampling is added; img_off: per-image weight / bias offsets (one launch, N differently
     conditioned images)."""
     _feat_check(src, "src")
-    for t, nm in ((out, "out"), (aux, "aux"), (idt, "idt")):
+    for t, nm in ((out, "out"), (idt, "idt")):
         if t is not None:
             _feat_check(t, nm, strided=(nm == "out"))
             if t.shape != src.shape:
                 raise ValueError(f"conv3x3: {nm} shape {tuple(t.shape)} != src {tuple(src.shape)}")
+    if aux is not None:
+        _aux_check(aux, "aux")
+        if aux.shape[:3] != src.shape[:3]:
+            raise ValueError(f"conv3x3: aux shape {tuple(aux.shape)} does not match src {tuple(src.shape)}")
     for t, nm in ((par, "par"), (lq, "lq"), (outf, "outf")):
         if t is not None:
             _plane_view_check(t, nm)

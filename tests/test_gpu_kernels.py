@@ -599,6 +599,37 @@ def test_table_mode_launches_equal_static_launches(dev):
     r2.table, r2.step, r2.node, r2.stride = t2.data_ptr(), step.data_ptr(), 0, 1
     for s in range(frames):
         _lib.check(lib.pnp_set_step(ctypes.c_void_p(step.data_ptr()), s, stream), "set_step")
-        _lib.check(lib.pnp_lr_im2col_dyn(ctypes.byref(r2), lr.stride(1), lr.stride(2), lr.stride(3), n, h, w, stream),
+        _lib.check(lib.pnp_lr_im2col_dyn(ctypes.byref(r2), lr.stride(1), lr.stride(2), lr.stride(3), n, h, w, 64, stream),
                    "im2col_dyn")
         assert torch.equal(aux, exp[s][1]), f"im2col step {s}"
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 64, 64), (2, 72, 200), (1, 180, 320), (1, 376, 1244), (1, 720, 1280)])
+def test_compact_lr_operand_is_bit_identical(dev, n, h, w):
+    """The LR im2col operand as a (N,H,W,32) tensor of 64-byte pixels (what the engine uses: contiguous stores, half the
+    bytes, read by the conv through a SWIZZLE_64B tile and a 64B-swizzle A descriptor) against the (N,H,W,64) form whose
+    upper 32 channels are dead: same operand values, bit-identical conv results -- also next to an identity operand."""
+    g = torch.Generator(device=dev).manual_seed(h * 7 + w)
+    lr = torch.rand((n, 3, h, w), generator=g, device=dev)
+    x = nhwc(bf(torch.randn((n, 64, h, w), generator=g, device=dev)))
+    w_in = bf(torch.randn((64, 131, 3, 3), generator=g, device=dev) * 0.05)
+    bias = torch.randn(64, generator=g, device=dev) * 0.1
+    wpa = _pack(w_in, dev, in_begin=3, in_count=64)
+    ops.pack_aux(w_in, wpa[9 * ops.CHUNK_BYTES:])
+    lr64 = ops.new_feature(n, h, w, dev, zero=True)
+    lr32 = torch.full((n, h, w, 32), float("nan"), dtype=torch.bfloat16, device=dev)
+    ops.lr_im2col(lr, lr64)
+    ops.lr_im2col(lr, lr32)
+    assert torch.equal(lr32, lr64[..., :32])
+    a = ops.new_feature(n, h, w, dev)
+    b = ops.new_feature(n, h, w, dev)
+    ops.conv3x3(x, wpa, out=a, aux=lr64, bias=bias, act=ops.PNP_ACT_LRELU)
+    ops.conv3x3(x, wpa, out=b, aux=lr32, bias=bias, act=ops.PNP_ACT_LRELU)
+    assert torch.equal(a, b)
+    lib = _lib.load()
+    prev = lib.pnp_set_pair_mode(1)          # (the compact operand always takes the single-CTA form)
+    try:
+        ops.conv3x3(x, wpa, out=b, aux=lr32, bias=bias, act=ops.PNP_ACT_LRELU)
+    finally:
+        lib.pnp_set_pair_mode(prev)
+    assert torch.equal(a, b)

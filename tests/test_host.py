@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/pnp_vcve.h but not exported"
     assert sorted(_lib.EXPORTS) == syms
-    assert _lib.load().pnp_abi_version() == 9
+    assert _lib.load().pnp_abi_version() == 10
 
 
 def test_abi_argument_errors_without_gpu():
@@ -59,7 +59,7 @@ def test_abi_argument_errors_without_gpu():
 def test_conv_desc_matches_header_layout():
     """ctypes mirror of struct pnp_conv_desc / pnp_dyn_ref (the library static_asserts the same offsets)."""
     d = _lib.ConvDesc()
-    assert ctypes.sizeof(d) == 272 and ctypes.sizeof(_lib.DynRef) == 24
+    assert ctypes.sizeof(d) == 280 and ctypes.sizeof(_lib.DynRef) == 24
     assert _lib.ConvDesc.N.offset == 152 and _lib.ConvDesc.mode.offset == 176 and _lib.ConvDesc.flip_y.offset == 180
     assert _lib.ConvDesc.out_spx.offset == 184 and _lib.ConvDesc.out_sn.offset == 200
     assert _lib.ConvDesc.lq_up4.offset == 208 and _lib.ConvDesc.per_image.offset == 220

@@ -52,7 +52,7 @@ def last():
 
 
 def im2col():
-    ops.lr_im2col(lq, lr64)
+    ops.lr_im2col(lq, lr64)          # (pass a (n,h,w,32) tensor for the compact operand)
 
 
 def pair():
