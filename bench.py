@@ -567,6 +567,7 @@ def main():
                         api="pnpvcve_b200.driver.enhance_clips on pinned host entries carrying `side` (per-block motion-"
                             "vector records of a synthetic H.264-style partition tree) instead of dense mvs / partitions")
     del host, out_host
+    driver.release_streamers(net)          # (the legs below want the memory back)
     torch.cuda.empty_cache()
 
     # ---------------- frame-window sharding: ONE clip of the config cut into `world` windows, one per rank (strong

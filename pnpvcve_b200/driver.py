@@ -5,6 +5,8 @@ distributed_sampler.py:51-72) and gathers pickled results with two all_gathers
 (mmedit/apis/test.py:190-234).  Clips are independent, so here clip ``c`` goes to rank
 ``c mod world`` and the only communication is ONE fixed-shape all_gather of per-frame metrics.
 """
+import weakref
+
 import torch
 import torch.distributed as dist
 
@@ -90,7 +92,7 @@ def enhance_clips(net, clips, rank=0, world=1, refs=None, gts=None, crop_border=
         # (`side`: compact side information packed by sideinfo.pack_side, already pinned -- see ClipStreamer.upload)
         pinned = {c: {k: (v if k == "side" or v.is_pinned() else v.pin_memory()) for k, v in clips[c].items()}
                   for c in mine}
-        streamer = ClipStreamer(net, dev, chunk=chunk)
+        streamer = streamer_for(net, dev, chunk)
         ticket = streamer.upload(pinned[mine[0]])
         for i, c in enumerate(mine):
             dst = out_hosts[c] if out_hosts is not None else \
@@ -240,6 +242,34 @@ def merge_sharded(local, world, group=None):
 # ------------------------------------------------------------------------------------------------
 # host-resident clips: chunked upload / download overlapped with the kernels
 # ------------------------------------------------------------------------------------------------
+#: net -> {(device, chunk): ClipStreamer}.  enhance_clips keeps its streamer (copy streams, double-buffered device copies
+#: of the inputs, result buffers, rasteriser workspace: ~11 GB for 720p x 100 clips) alive between calls: a new one per
+#: call hands GB-sized blocks back and forth through the caching allocator, which showed up as one-off stalls of
+#: 50-300 ms in the first call after a change of feed (profiles/r02_notes.md section 13).  release_streamers() drops them.
+_STREAMERS = weakref.WeakKeyDictionary()
+
+
+def streamer_for(net, device, chunk=10):
+    """The cached ClipStreamer of (net, device, chunk); created on first use, released with the net."""
+    key = (str(torch.device(device)), int(chunk))
+    try:
+        per_net = _STREAMERS.setdefault(net, {})
+    except TypeError:                      # a stand-in callable that cannot be weakly referenced
+        return ClipStreamer(net, device, chunk=chunk)
+    st = per_net.get(key)
+    if st is None:
+        st = per_net[key] = ClipStreamer(net, device, chunk=chunk)
+    return st
+
+
+def release_streamers(net=None):
+    """Drop the cached streamers (of one generator, or all) and with them their device buffers."""
+    if net is None:
+        _STREAMERS.clear()
+    else:
+        _STREAMERS.pop(net, None)
+
+
 class ClipStreamer:
     """Enhances clips that live in PINNED HOST memory and returns the frames to pinned host memory.
 
@@ -258,7 +288,12 @@ class ClipStreamer:
     SMALL = ("QPs", "slices", "base_QPs")
 
     def __init__(self, net, device, chunk=10):
-        self.net, self.dev, self.chunk = net, torch.device(device), int(chunk)
+        # (weak: streamers are cached per generator in a WeakKeyDictionary, a strong reference would keep it alive)
+        try:
+            self._net = weakref.ref(net)
+        except TypeError:
+            self._net = lambda: net
+        self.dev, self.chunk = torch.device(device), int(chunk)
         self.up = torch.cuda.Stream(device=self.dev)
         self.down = torch.cuda.Stream(device=self.dev)
         self.slots = [None, None]          # double-buffered device copies of the inputs
@@ -268,6 +303,10 @@ class ClipStreamer:
         self.raster_work = self.raster_status = None     # compact side information: rasteriser workspace / error bits
         #: diagnostics (tools/e2e_probe.py): skip the big H2D / D2H copies to see what each direction costs
         self.copy_in = self.copy_out = True
+
+    @property
+    def net(self):
+        return self._net()
 
     def _chunks(self, t):
         """Frame ranges [a, b) in ascending order.  The clip's LAST frames are the first the kernels read (backward-time
@@ -418,7 +457,10 @@ class ClipStreamer:
         torch.cuda.current_stream(self.dev).wait_stream(self.down)
         if check and self.raster_status is not None:
             from . import sideinfo
-            sideinfo.raise_for_status(int(self.raster_status.item()))
+            st = int(self.raster_status.item())
+            if st:
+                self.raster_status.zero_()     # the streamer may serve further calls
+            sideinfo.raise_for_status(st)
 
 
 def stream_clips(net, host_clips, out_hosts, device, chunk=10):
