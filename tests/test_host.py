@@ -296,3 +296,31 @@ def test_frame_windows_reject_compact_side_information():
     compact = dict({k: v for k, v in clip.items() if k not in ("mvs", "partitions")}, side=[None])
     with pytest.raises(ValueError, match="dense"):
         driver.enhance_windows(_fake_net, [compact], 2)
+
+
+def test_streamer_cache_is_per_generator_and_dies_with_it(monkeypatch):
+    """driver.streamer_for: one ClipStreamer per (generator, device, chunk), kept between enhance_clips calls, released
+    with the generator (the streamer itself only holds a weak reference to it) or by release_streamers()."""
+    import gc
+    import weakref
+    from pnpvcve_b200 import driver
+
+    class Net(torch.nn.Module):
+        pass
+
+    class Fake(driver.ClipStreamer):
+        def __init__(self, net, device, chunk=10):      # no CUDA streams on the CPU box
+            self._net = weakref.ref(net)
+            self.dev, self.chunk = torch.device(device), int(chunk)
+
+    monkeypatch.setattr(driver, "ClipStreamer", Fake)
+    a, b = Net(), Net()
+    sa = driver.streamer_for(a, "cpu", 10)
+    assert driver.streamer_for(a, "cpu", 10) is sa and sa.net is a
+    assert driver.streamer_for(a, "cpu", 5) is not sa and driver.streamer_for(b, "cpu", 10) is not sa
+    driver.release_streamers(b)
+    assert b not in driver._STREAMERS and a in driver._STREAMERS
+    ref = weakref.ref(a)
+    del a, sa
+    gc.collect()
+    assert ref() is None and len(driver._STREAMERS) == 0
